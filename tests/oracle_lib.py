@@ -1,0 +1,306 @@
+"""ctypes bindings for the CPU oracle (oracle/libkoifish_oracle.so) and the reference shim (oracle/_ref).
+
+TEST INFRASTRUCTURE ONLY -- the product (koifish_b200/) never imports this module.
+bf16 tensors are numpy uint16 arrays holding the raw bit patterns.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "libkoifish_oracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_ref.so")
+
+RTN_ASYM, RTN_SYM, YYANG = 0, 1, 2
+
+
+def build_oracle(force=False):
+    """Compile oracle/ (and oracle/_ref when /root/reference is present). Building the checker is not using it."""
+    if force or not os.path.exists(ORACLE_SO):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "libkoifish_oracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.exists("/root/reference/src/PackedQ.hpp") and (force or not os.path.exists(REF_SO)):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
+
+
+class ModelConfig(C.Structure):
+    _fields_ = [
+        ("n_layer", C.c_int), ("n_embd", C.c_int), ("n_ff", C.c_int), ("n_head", C.c_int), ("n_kv_head", C.c_int),
+        ("head_dim", C.c_int), ("vocab", C.c_int), ("max_seq", C.c_int),
+        ("rope_theta", C.c_float), ("rms_eps", C.c_float),
+        ("tie_embed", C.c_int),
+        ("attn_bits", C.c_int), ("attn_mode", C.c_int),
+        ("mlp_bits", C.c_int), ("mlp_mode", C.c_int),
+        ("embed_bits", C.c_int), ("embed_mode", C.c_int),
+        ("group", C.c_int),
+        ("seed", C.c_uint64),
+        ("sigma", C.c_float), ("norm_sigma", C.c_float),
+        ("score_bf16", C.c_int),
+    ]
+
+
+class QRange(C.Structure):
+    _fields_ = [("qmin", C.c_int), ("qmax", C.c_int), ("qbias", C.c_int)]
+
+
+_u16p = np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build_oracle()
+        L = C.CDLL(ORACLE_SO)
+        L.kfo_f32_to_bf16.restype = C.c_uint16
+        L.kfo_f32_to_bf16.argtypes = [C.c_float]
+        L.kfo_bf16_to_f32.restype = C.c_float
+        L.kfo_bf16_to_f32.argtypes = [C.c_uint16]
+        L.kfo_bf16_mul.restype = C.c_uint16
+        L.kfo_bf16_mul.argtypes = [C.c_uint16, C.c_uint16]
+        L.kfo_bf16_sub.restype = C.c_uint16
+        L.kfo_bf16_sub.argtypes = [C.c_uint16, C.c_uint16]
+        L.kfo_fill_normal.argtypes = [_u16p, C.c_size_t, C.c_uint64, C.c_float, C.c_float]
+        L.kfo_qrange_of.argtypes = [C.c_int, C.c_int, C.POINTER(QRange)]
+        L.kfo_gama_elems.restype = C.c_size_t
+        L.kfo_gama_elems.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.kfo_quantize.argtypes = [_u16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _u16p]
+        L.kfo_pack_codes.argtypes = [_i32p, C.c_size_t, C.c_int, _u8p]
+        L.kfo_unpack_codes.argtypes = [_u8p, C.c_size_t, C.c_int, _i32p]
+        L.kfo_dequant.argtypes = [_u8p, _u16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u16p]
+        L.kfo_f8e5m2_encode.argtypes = [_u16p, C.c_size_t, _u8p]
+        L.kfo_f8e5m2_decode.argtypes = [_u8p, C.c_size_t, _u16p]
+        L.kfo_linear.argtypes = [_u16p, _u16p, _u16p, C.c_int, C.c_int, C.c_int]
+        L.kfo_linear_f32.argtypes = [_f32p, _u16p, _u16p, C.c_int, C.c_int, C.c_int]
+        L.kfo_rmsnorm.argtypes = [_u16p, _u16p, _u16p, C.c_int, C.c_int, C.c_float]
+        L.kfo_rope.argtypes = [_u16p, C.c_int, C.c_int, C.c_int, C.c_float]
+        L.kfo_swiglu.argtypes = [_u16p, _u16p, _u16p, C.c_size_t]
+        L.kfo_add.argtypes = [_u16p, _u16p, _u16p, C.c_size_t]
+        L.kfo_attention_decode.argtypes = [_u16p, _u16p, _u16p, _u16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.kfo_model_create.restype = C.c_void_p
+        L.kfo_model_create.argtypes = [C.POINTER(ModelConfig)]
+        L.kfo_model_destroy.argtypes = [C.c_void_p]
+        L.kfo_model_reset.argtypes = [C.c_void_p]
+        L.kfo_model_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.kfo_model_layer.argtypes = [C.c_void_p, C.c_int, C.c_int, _u16p]
+        L.kfo_model_weight.restype = C.POINTER(C.c_uint16)
+        L.kfo_model_weight.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
+        L.kfo_model_kcache.restype = C.POINTER(C.c_uint16)
+        L.kfo_model_kcache.argtypes = [C.c_void_p, C.c_int]
+        L.kfo_model_vcache.restype = C.POINTER(C.c_uint16)
+        L.kfo_model_vcache.argtypes = [C.c_void_p, C.c_int]
+        L.kfo_tensor_seed.restype = C.c_uint64
+        L.kfo_tensor_seed.argtypes = [C.c_uint64, C.c_int]
+        L.kfo_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def ref():
+    """The reference's own code (PackedQ.hpp macros, GST_float.cpp primitives); None when it was never built."""
+    global _ref
+    if _ref is None:
+        build_oracle()
+        if not os.path.exists(REF_SO):
+            return None
+        R = C.CDLL(REF_SO)
+        R.ref_pack.argtypes = [_i32p, C.c_size_t, C.c_int, _u8p]
+        R.ref_unpack.argtypes = [_u8p, C.c_size_t, C.c_int, _i32p]
+        R.ref_matvec_f32.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int]
+        R.ref_rmsnorm_f32.restype = C.c_float
+        R.ref_rmsnorm_f32.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_float]
+        _ref = R
+    return _ref
+
+
+# ---------------------------------------------------------------- numpy-level helpers
+def bf16_to_f32(a):
+    a = np.ascontiguousarray(a, dtype=np.uint16)
+    return (a.astype(np.uint32) << 16).view(np.float32)
+
+
+def f32_to_bf16(a):
+    """round-to-nearest-even, vectorised (matches kfo_f32_to_bf16 for finite values)."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    lsb = (u >> 16) & 1
+    return ((u + 0x7FFF + lsb) >> 16).astype(np.uint16)
+
+
+def fill_normal(n, seed, sigma=0.02, mean=0.0):
+    out = np.empty(n, dtype=np.uint16)
+    lib().kfo_fill_normal(out, n, seed, sigma, mean)
+    return out
+
+
+def qrange(bits, mode):
+    r = QRange()
+    assert lib().kfo_qrange_of(bits, mode, C.byref(r)) == 0
+    return r.qmin, r.qmax, r.qbias
+
+
+def quantize(w, rows, cols, bits, group=128, mode=RTN_ASYM):
+    w = np.ascontiguousarray(w, dtype=np.uint16).reshape(-1)
+    data = np.zeros(rows * cols * bits // 8, dtype=np.uint8)
+    gama = np.zeros(lib().kfo_gama_elems(rows, cols, group), dtype=np.uint16)
+    rc = lib().kfo_quantize(w, rows, cols, bits, group, mode, data, gama)
+    assert rc == 0, rc
+    return data, gama
+
+
+def pack_codes(codes, bits):
+    codes = np.ascontiguousarray(codes, dtype=np.int32)
+    out = np.zeros(codes.size * bits // 8, dtype=np.uint8)
+    assert lib().kfo_pack_codes(codes, codes.size, bits, out) == 0
+    return out
+
+
+def unpack_codes(data, n, bits):
+    out = np.zeros(n, dtype=np.int32)
+    assert lib().kfo_unpack_codes(np.ascontiguousarray(data, dtype=np.uint8), n, bits, out) == 0
+    return out
+
+
+def dequant(data, gama, rows, cols, bits, group=128, qbias=0):
+    out = np.zeros(rows * cols, dtype=np.uint16)
+    rc = lib().kfo_dequant(np.ascontiguousarray(data), np.ascontiguousarray(gama), rows, cols, bits, group, qbias, out)
+    assert rc == 0, rc
+    return out.reshape(rows, cols)
+
+
+def f8_encode(w):
+    w = np.ascontiguousarray(w, dtype=np.uint16).reshape(-1)
+    out = np.zeros(w.size, dtype=np.uint8)
+    lib().kfo_f8e5m2_encode(w, w.size, out)
+    return out
+
+
+def f8_decode(b):
+    b = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1)
+    out = np.zeros(b.size, dtype=np.uint16)
+    lib().kfo_f8e5m2_decode(b, b.size, out)
+    return out
+
+
+def linear(w, x, M, N, K):
+    y = np.zeros((M, N), dtype=np.uint16)
+    lib().kfo_linear(y, np.ascontiguousarray(w, dtype=np.uint16), np.ascontiguousarray(x, dtype=np.uint16), M, N, K)
+    return y
+
+
+def linear_f32(w, x, M, N, K):
+    y = np.zeros((M, N), dtype=np.float32)
+    lib().kfo_linear_f32(y, np.ascontiguousarray(w, dtype=np.uint16), np.ascontiguousarray(x, dtype=np.uint16), M, N, K)
+    return y
+
+
+def rmsnorm(x, w, rows, dim, eps=1e-6):
+    out = np.zeros(rows * dim, dtype=np.uint16)
+    lib().kfo_rmsnorm(out, np.ascontiguousarray(x, dtype=np.uint16).reshape(-1), np.ascontiguousarray(w, dtype=np.uint16), rows, dim, eps)
+    return out.reshape(rows, dim)
+
+
+def rope(v, n_heads, head_dim, pos, theta):
+    v = np.array(v, dtype=np.uint16, copy=True).reshape(-1)
+    lib().kfo_rope(v, n_heads, head_dim, pos, theta)
+    return v.reshape(n_heads, head_dim)
+
+
+def swiglu(g, u):
+    g = np.ascontiguousarray(g, dtype=np.uint16).reshape(-1)
+    u = np.ascontiguousarray(u, dtype=np.uint16).reshape(-1)
+    out = np.zeros(g.size, dtype=np.uint16)
+    lib().kfo_swiglu(out, g, u, g.size)
+    return out
+
+
+def add(a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint16).reshape(-1)
+    b = np.ascontiguousarray(b, dtype=np.uint16).reshape(-1)
+    out = np.zeros(a.size, dtype=np.uint16)
+    lib().kfo_add(out, a, b, a.size)
+    return out
+
+
+def attention_decode(q, kc, vc, pos, n_head, n_kv, hd, score_bf16=0):
+    out = np.zeros(n_head * hd, dtype=np.uint16)
+    lib().kfo_attention_decode(out, np.ascontiguousarray(q, dtype=np.uint16).reshape(-1), np.ascontiguousarray(kc, dtype=np.uint16).reshape(-1),
+                               np.ascontiguousarray(vc, dtype=np.uint16).reshape(-1), pos, n_head, n_kv, hd, score_bf16)
+    return out.reshape(n_head, hd)
+
+
+def ref_pack(codes, bits):
+    codes = np.ascontiguousarray(codes, dtype=np.int32)
+    out = np.zeros(codes.size * bits // 8, dtype=np.uint8)
+    assert ref().ref_pack(codes, codes.size, bits, out) == 0
+    return out
+
+
+def ref_unpack(data, n, bits):
+    out = np.zeros(n, dtype=np.int32)
+    assert ref().ref_unpack(np.ascontiguousarray(data, dtype=np.uint8), n, bits, out) == 0
+    return out
+
+
+def tensor_seed(model_seed, tid):
+    return lib().kfo_tensor_seed(model_seed, tid)
+
+
+class OracleModel:
+    """Whole-model CPU decode following the reference op order."""
+
+    def __init__(self, **kw):
+        d = dict(n_layer=2, n_embd=256, n_ff=512, n_head=4, n_kv_head=2, head_dim=64, vocab=1024, max_seq=64,
+                 rope_theta=1e6, rms_eps=1e-6, tie_embed=1, attn_bits=4, attn_mode=RTN_ASYM, mlp_bits=4, mlp_mode=RTN_ASYM,
+                 embed_bits=16, embed_mode=RTN_ASYM, group=128, seed=42, sigma=0.02, norm_sigma=0.0, score_bf16=0)
+        d.update(kw)
+        self.cfg = ModelConfig(**d)
+        self.h = lib().kfo_model_create(C.byref(self.cfg))
+        assert self.h
+
+    def close(self):
+        if self.h:
+            lib().kfo_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        lib().kfo_model_reset(self.h)
+
+    def forward(self, token, pos, want_logits=True):
+        if want_logits:
+            out = np.zeros(self.cfg.vocab, dtype=np.uint16)
+            rc = lib().kfo_model_forward(self.h, token, pos, out.ctypes.data_as(C.c_void_p))
+            assert rc == 0
+            return out
+        assert lib().kfo_model_forward(self.h, token, pos, None) == 0
+        return None
+
+    def layer(self, layer, pos, x):
+        x = np.array(x, dtype=np.uint16, copy=True)
+        assert lib().kfo_model_layer(self.h, layer, pos, x) == 0
+        return x
+
+    def weight(self, tid):
+        n = C.c_size_t()
+        p = lib().kfo_model_weight(self.h, tid, C.byref(n))
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def kcache(self, layer, npos):
+        kd = self.cfg.n_kv_head * self.cfg.head_dim
+        return np.ctypeslib.as_array(lib().kfo_model_kcache(self.h, layer), shape=(npos * kd,)).copy().reshape(npos, kd)
+
+    def vcache(self, layer, npos):
+        kd = self.cfg.n_kv_head * self.cfg.head_dim
+        return np.ctypeslib.as_array(lib().kfo_model_vcache(self.h, layer), shape=(npos * kd,)).copy().reshape(npos, kd)

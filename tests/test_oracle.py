@@ -1,0 +1,328 @@
+"""CPU tests: the oracle against the reference's own macros (oracle/_ref), the committed golden fixtures, the
+in-code invariants the reference asserts, and exact bf16 arithmetic."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "packq_ref.npz"))
+
+
+# ------------------------------------------------------------------ bit layout (PackedQ.hpp:99-239)
+@pytest.mark.parametrize("bits", [4, 2, 1])
+def test_pack_matches_golden_from_reference_macros(bits):
+    codes = GOLD[f"codes{bits}"]
+    assert np.array_equal(ol.pack_codes(codes, bits), GOLD[f"bytes{bits}"])
+    assert np.array_equal(ol.unpack_codes(GOLD[f"bytes{bits}"], codes.size, bits), codes)
+    oh = GOLD[f"onehot_codes{bits}"]
+    assert np.array_equal(ol.pack_codes(oh, bits), GOLD[f"onehot_bytes{bits}"])
+
+
+def test_survey_probe_bytes():
+    # SURVEY.md 8c probe of PACK_4to128_: codes (3+7i)%16 -> low half "5c 7e 90 b2 d4 f6 18 3a", same for the high half
+    b = ol.pack_codes(GOLD["kat4_codes"], 4)
+    want = bytes.fromhex("5c7e90b2d4f6183a") * 2
+    assert bytes(b) == want
+    assert bytes(GOLD["kat4_bytes"]) == want
+
+
+@pytest.mark.parametrize("bits", [4, 2, 1])
+def test_layout_table_A2(bits):
+    # code j of a word -> byte / bit field
+    per = 128 // bits
+    for j in range(per):
+        codes = np.zeros(per, dtype=np.int32)
+        codes[j] = (1 << bits) - 1
+        b = ol.pack_codes(codes, bits)
+        half = per // 2
+        jj = j if j < half else j - half
+        per_byte = 8 // bits
+        byte = (15 if j < half else 7) - jj // per_byte
+        shift = 8 - bits * (jj % per_byte + 1)
+        want = np.zeros(16, dtype=np.uint8)
+        want[byte] = ((1 << bits) - 1) << shift
+        assert np.array_equal(b, want), (bits, j)
+
+
+@pytest.mark.skipif(ol.ref() is None, reason="oracle/_ref not built (no /root/reference)")
+@pytest.mark.parametrize("bits", [4, 2, 1])
+def test_pack_unpack_vs_reference_macros_live(bits):
+    rng = np.random.default_rng(bits)
+    codes = rng.integers(0, 1 << bits, size=(128 // bits) * 257, dtype=np.int32)
+    assert np.array_equal(ol.pack_codes(codes, bits), ol.ref_pack(codes, bits))
+    data = rng.integers(0, 256, size=16 * 300, dtype=np.uint8)
+    n = data.size * 8 // bits
+    assert np.array_equal(ol.unpack_codes(data, n, bits), ol.ref_unpack(data, n, bits))
+
+
+def test_pack_rejects_ragged():
+    L = ol.lib()
+    codes = np.zeros(33, dtype=np.int32)
+    out = np.zeros(64, dtype=np.uint8)
+    assert L.kfo_pack_codes(codes, 33, 4, out) == -2
+    assert L.kfo_pack_codes(codes, 32, 3, out) == -1
+
+
+# ------------------------------------------------------------------ bf16 arithmetic
+def _rn_bf16_from_f64(x):
+    """exact RN-even of a python float to bf16 bits via integer arithmetic (independent of the oracle)."""
+    import math
+    import struct
+    if x == 0:
+        return 0x8000 if math.copysign(1, x) < 0 else 0
+    s = 0x8000 if x < 0 else 0
+    a = abs(x)
+    m, e = math.frexp(a)  # a = m * 2^e, m in [0.5,1)
+    exp = e - 1           # a = (2m) * 2^exp
+    if exp < -126:
+        q = a / 2.0 ** (-126 - 7)  # subnormal: units of 2^-133
+        r = int(math.floor(q))
+        frac = q - r
+        if frac > 0.5 or (frac == 0.5 and (r & 1)):
+            r += 1
+        return s | r
+    q = a / 2.0 ** (exp - 7)  # in [128, 256)
+    r = int(math.floor(q))
+    frac = q - r
+    if frac > 0.5 or (frac == 0.5 and (r & 1)):
+        r += 1
+    if r == 256:
+        r, exp = 128, exp + 1
+    if exp > 127:
+        return s | 0x7F80
+    return s | ((exp + 127) << 7) | (r - 128)
+
+
+def test_bf16_mul_sub_single_rounding():
+    L = ol.lib()
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 1 << 16, size=4000).astype(np.uint16)
+    b = rng.integers(0, 1 << 16, size=4000).astype(np.uint16)
+    # add a family with close exponents (typical step*k vs zero) and a family with far exponents
+    base = ol.f32_to_bf16(rng.normal(0, 0.05, size=4000).astype(np.float32))
+    a = np.concatenate([a, base])
+    b = np.concatenate([b, ol.f32_to_bf16((ol.bf16_to_f32(base) * rng.uniform(0.3, 3, size=4000)).astype(np.float32))])
+    fa, fb = ol.bf16_to_f32(a).astype(np.float64), ol.bf16_to_f32(b).astype(np.float64)
+    for i in range(a.size):
+        if not (np.isfinite(fa[i]) and np.isfinite(fb[i])):
+            continue
+        prod, diff = float(fa[i]) * float(fb[i]), float(fa[i]) - float(fb[i])
+        if abs(prod) < 3e38:
+            assert L.kfo_bf16_mul(int(a[i]), int(b[i])) == _rn_bf16_from_f64(prod)
+        if abs(diff) < 3e38:
+            assert L.kfo_bf16_sub(int(a[i]), int(b[i])) == _rn_bf16_from_f64(diff)
+
+
+def test_f32_to_bf16_vectorised_matches_scalar():
+    L = ol.lib()
+    rng = np.random.default_rng(2)
+    x = rng.normal(0, 1, size=2000).astype(np.float32)
+    v = ol.f32_to_bf16(x)
+    for i in range(x.size):
+        assert L.kfo_f32_to_bf16(float(x[i])) == v[i]
+    # ties go to even
+    assert L.kfo_f32_to_bf16(np.float32(1.0 + 2 ** -8)) == 0x3F80
+    assert L.kfo_f32_to_bf16(np.float32(1.0 + 3 * 2 ** -8)) == 0x3F82
+
+
+# ------------------------------------------------------------------ synthetic weights
+def test_fill_normal_is_deterministic_and_roughly_normal():
+    w = ol.fill_normal(1 << 16, seed=42, sigma=0.02)
+    w2 = ol.fill_normal(1 << 16, seed=42, sigma=0.02)
+    assert np.array_equal(w, w2)
+    assert not np.array_equal(w, ol.fill_normal(1 << 16, seed=43, sigma=0.02))
+    f = ol.bf16_to_f32(w)
+    assert abs(f.mean()) < 5e-4 and abs(f.std() - 0.02) < 5e-4
+    # prefix property: element i does not depend on n
+    assert np.array_equal(w[:100], ol.fill_normal(100, seed=42, sigma=0.02))
+
+
+# ------------------------------------------------------------------ quantiser (GeQuant.cpp:428-628)
+@pytest.mark.parametrize("bits,mode", [(4, ol.RTN_ASYM), (4, ol.RTN_SYM), (2, ol.RTN_ASYM), (2, ol.YYANG), (1, ol.YYANG)])
+def test_quantize_invariants(bits, mode):
+    rows, cols, G = 24, 512, 128
+    w = ol.fill_normal(rows * cols, seed=7 + bits, sigma=0.02)
+    data, gama = ol.quantize(w, rows, cols, bits, G, mode)
+    qmin, qmax, qbias = ol.qrange(bits, mode)
+    nG = rows * cols // G
+    assert gama.size == rows + cols + 2 * nG                 # szGama, GeQuant.cpp:518
+    assert not gama[: rows + cols].any()                     # R/C scales unused
+    codes = ol.unpack_codes(data, rows * cols, bits)
+    assert codes.min() >= qmin + qbias and codes.max() <= qmax + qbias   # assert(qid>=qMin && qid<=qMax), :490
+    assert np.array_equal(ol.pack_codes(codes, bits), data)  # pack->unpack round trip, :500-506
+    zero = ol.bf16_to_f32(gama[rows + cols: rows + cols + nG])
+    step = ol.bf16_to_f32(gama[rows + cols + nG:])
+    wf = ol.bf16_to_f32(w).reshape(nG, G)
+    if mode == ol.RTN_ASYM:
+        assert np.allclose(zero, -wf.min(1), rtol=2 ** -8)
+        assert np.allclose(step, (wf.max(1) - wf.min(1)) / (qmax - qmin), rtol=2 ** -8)
+        # every group uses code 0 (its minimum) and code qmax (its maximum)
+        c = codes.reshape(nG, G)
+        assert (c.min(1) == 0).all() and (c.max(1) == qmax).all()
+    else:
+        assert not zero.any()
+    if mode == ol.YYANG and bits == 2:
+        assert np.allclose(step, np.maximum(1e-5, np.abs(wf).mean(1)), rtol=2 ** -8)
+    if bits == 1:
+        assert np.allclose(step, np.maximum(1e-5, np.sqrt((np.maximum(wf, 0) ** 2).mean(1))), rtol=2 ** -8)
+    # dequant error: within half a step (+ bf16 rounding of step/zero/products) for RTN
+    dq = ol.bf16_to_f32(ol.dequant(data, gama, rows, cols, bits, G, qbias)).reshape(nG, G)
+    if mode in (ol.RTN_ASYM, ol.RTN_SYM):
+        bound = 0.5 * step[:, None] + 2 ** -7 * (np.abs(wf).max(1)[:, None] + np.abs(zero)[:, None])
+        assert (np.abs(dq - wf) <= bound + 1e-9).all()
+
+
+def test_dequant_values_are_two_roundings():
+    # T.cu:274 : w = RN(RN(step*k) - zero), checked against an independent float64 evaluation
+    rows, cols, G, bits = 8, 256, 128, 4
+    w = ol.fill_normal(rows * cols, seed=11, sigma=0.02)
+    data, gama = ol.quantize(w, rows, cols, bits, G, ol.RTN_ASYM)
+    nG = rows * cols // G
+    codes = ol.unpack_codes(data, rows * cols, bits).reshape(nG, G)
+    zero = ol.bf16_to_f32(gama[rows + cols: rows + cols + nG]).astype(np.float64)
+    step = ol.bf16_to_f32(gama[rows + cols + nG:]).astype(np.float64)
+    dq = ol.dequant(data, gama, rows, cols, bits, G, 0).reshape(nG, G)
+    for g in range(nG):
+        for i in range(G):
+            p = _rn_bf16_from_f64(float(step[g]) * int(codes[g, i]))
+            pf = float(ol.bf16_to_f32(np.array([p], dtype=np.uint16))[0])
+            assert dq[g, i] == _rn_bf16_from_f64(pf - float(zero[g]))
+
+
+def test_ternary_and_binary_levels():
+    rows, cols, G = 4, 256, 128
+    w = ol.fill_normal(rows * cols, seed=5, sigma=0.02)
+    for bits in (2, 1):
+        data, gama = ol.quantize(w, rows, cols, bits, G, ol.YYANG)
+        _, _, qbias = ol.qrange(bits, ol.YYANG)
+        nG = rows * cols // G
+        step = gama[rows + cols + nG:]
+        dq = ol.dequant(data, gama, rows, cols, bits, G, qbias).reshape(nG, G)
+        for g in range(nG):
+            allowed = {0, int(step[g])} | ({int(step[g]) | 0x8000, 0x8000} if bits == 2 else set())
+            assert set(int(v) for v in np.unique(dq[g])) <= allowed
+
+
+def test_f8e5m2_truncation():
+    w = ol.fill_normal(4096, seed=3, sigma=0.02)
+    b = ol.f8_encode(w)
+    d = ol.f8_decode(b)
+    f, g = ol.bf16_to_f32(w), ol.bf16_to_f32(d)
+    # truncation toward zero of the fp16 mantissa to 2 bits: |g| <= |f| and relative error < 2^-2
+    assert (np.abs(g) <= np.abs(f) * (1 + 2 ** -10)).all()
+    nz = np.abs(f) > 1e-4
+    assert (np.abs(f - g)[nz] <= np.abs(f)[nz] * 0.25).all()
+    # exact on values already representable in e5m2
+    exact = np.array([0x3F80, 0xBF80, 0x3FC0, 0x3E80, 0x0000], dtype=np.uint16)  # 1, -1, 1.5, 0.25, 0
+    assert np.array_equal(ol.f8_decode(ol.f8_encode(exact)), exact)
+    # idempotent
+    assert np.array_equal(ol.f8_encode(d), b)
+
+
+# ------------------------------------------------------------------ ops
+def test_linear_against_float64():
+    rng = np.random.default_rng(4)
+    M, N, K = 3, 40, 384
+    w = ol.f32_to_bf16(rng.normal(0, 0.02, size=(N, K)).astype(np.float32))
+    x = ol.f32_to_bf16(rng.normal(0, 1, size=(M, K)).astype(np.float32))
+    y = ol.bf16_to_f32(ol.linear(w, x, M, N, K))
+    ref = ol.bf16_to_f32(x).astype(np.float64) @ ol.bf16_to_f32(w).astype(np.float64).T
+    assert np.allclose(y, ref, rtol=2 ** -7, atol=1e-4)
+
+
+@pytest.mark.skipif(ol.ref() is None, reason="oracle/_ref not built")
+def test_linear_and_rmsnorm_against_reference_cpu_primitives():
+    # D_matvec + dotprod_fp32 and rmsnorm from src/Utils/GST_float.cpp (compiled unchanged into oracle/_ref)
+    rng = np.random.default_rng(5)
+    N, K = 64, 512
+    w = ol.f32_to_bf16(rng.normal(0, 0.02, size=(N, K)).astype(np.float32))
+    x = ol.f32_to_bf16(rng.normal(0, 1, size=(1, K)).astype(np.float32))
+    yo = ol.linear_f32(w, x, 1, N, K)[0]
+    wf, xf = np.ascontiguousarray(ol.bf16_to_f32(w)), np.ascontiguousarray(ol.bf16_to_f32(x)[0])
+    yr = np.zeros(N, dtype=np.float32)
+    ol.ref().ref_matvec_f32(yr, xf, wf, K, N)
+    assert np.allclose(yo, yr, rtol=1e-5, atol=1e-6)
+    g = ol.f32_to_bf16(rng.normal(1, 0.1, size=K).astype(np.float32))
+    no = ol.bf16_to_f32(ol.rmsnorm(x, g, 1, K, 1e-6))[0]
+    nr = np.zeros(K, dtype=np.float32)
+    ol.ref().ref_rmsnorm_f32(nr, xf, np.ascontiguousarray(ol.bf16_to_f32(g)), K, 1e-6)
+    assert np.allclose(no, nr, rtol=2 ** -7, atol=1e-6)
+
+
+def test_rope_is_a_rotation_and_identity_at_pos0():
+    rng = np.random.default_rng(6)
+    H, hd = 4, 128
+    v = ol.f32_to_bf16(rng.normal(0, 1, size=(H, hd)).astype(np.float32))
+    assert np.array_equal(ol.rope(v, H, hd, 0, 1e6), v)
+    r = ol.bf16_to_f32(ol.rope(v, H, hd, 37, 1e6))
+    f = ol.bf16_to_f32(v)
+    n0 = f[:, :64] ** 2 + f[:, 64:] ** 2
+    n1 = r[:, :64] ** 2 + r[:, 64:] ** 2
+    assert np.allclose(n0, n1, rtol=0.03, atol=1e-3)
+    # last pair rotates slowest: angle = 37 / theta^(126/128)
+    j = 63
+    ang = 37.0 / (1e6 ** (126 / 128))
+    assert np.allclose(r[:, j], f[:, j] * np.cos(ang) - f[:, j + 64] * np.sin(ang), rtol=2 ** -7, atol=1e-3)
+
+
+def test_attention_decode_matches_numpy_and_variants_agree():
+    rng = np.random.default_rng(8)
+    H, KV, hd, pos, S = 8, 2, 64, 40, 64
+    q = ol.f32_to_bf16(rng.normal(0, 1, size=(H, hd)).astype(np.float32))
+    kc = ol.f32_to_bf16(rng.normal(0, 1, size=(S, KV * hd)).astype(np.float32))
+    vc = ol.f32_to_bf16(rng.normal(0, 1, size=(S, KV * hd)).astype(np.float32))
+    o32 = ol.bf16_to_f32(ol.attention_decode(q, kc, vc, pos, H, KV, hd, 0))
+    o16 = ol.bf16_to_f32(ol.attention_decode(q, kc, vc, pos, H, KV, hd, 1))
+    qf, kf, vf = ol.bf16_to_f32(q).astype(np.float64), ol.bf16_to_f32(kc).astype(np.float64), ol.bf16_to_f32(vc).astype(np.float64)
+    want = np.zeros((H, hd))
+    for h in range(H):
+        kvh = h // (H // KV)
+        s = kf[: pos + 1, kvh * hd:(kvh + 1) * hd] @ qf[h] / np.sqrt(hd)
+        p = np.exp(s - s.max())
+        p /= p.sum()
+        want[h] = p @ vf[: pos + 1, kvh * hd:(kvh + 1) * hd]
+    assert np.allclose(o32, want, rtol=2 ** -7, atol=2e-3)
+    # the reference's two score precisions (bf16 neuron path / fp32 pipe path) agree within the logits tolerance
+    assert np.allclose(o16, o32, rtol=3e-2, atol=3e-2)
+
+
+def test_swiglu_add():
+    rng = np.random.default_rng(9)
+    g = ol.f32_to_bf16(rng.normal(0, 2, size=512).astype(np.float32))
+    u = ol.f32_to_bf16(rng.normal(0, 2, size=512).astype(np.float32))
+    gf, uf = ol.bf16_to_f32(g).astype(np.float64), ol.bf16_to_f32(u).astype(np.float64)
+    assert np.allclose(ol.bf16_to_f32(ol.swiglu(g, u)), gf * uf / (1 + np.exp(-gf)), rtol=2 ** -7, atol=1e-6)
+    assert np.allclose(ol.bf16_to_f32(ol.add(g, u)), gf + uf, rtol=2 ** -7, atol=1e-6)
+
+
+# ------------------------------------------------------------------ whole model
+def test_model_forward_is_deterministic_and_uses_cache():
+    m = ol.OracleModel(n_layer=2, norm_sigma=0.1)
+    toks = [(1000 + 37 * i) % 1024 for i in range(6)]
+    logits = [m.forward(t, i) for i, t in enumerate(toks)]
+    m.reset()
+    logits2 = [m.forward(t, i) for i, t in enumerate(toks)]
+    for a, b in zip(logits, logits2):
+        assert np.array_equal(a, b)
+    # position matters (KV cache + rope): same token at pos 0 vs later gives different logits
+    assert not np.array_equal(logits[0], logits[-1])
+    f = ol.bf16_to_f32(logits[-1])
+    assert np.isfinite(f).all() and f.std() > 0
+    # layer entry point == what forward does for layer 0 at pos 0
+    m.reset()
+    E = m.cfg.n_embd
+    x0 = m.weight(0)[toks[0] * E:(toks[0] + 1) * E]
+    x1 = m.layer(0, 0, x0)
+    assert x1.shape == (E,) and not np.array_equal(x0, x1)
+
+
+def test_model_weight_is_dequant_of_quantized_synthetic():
+    m = ol.OracleModel(n_layer=1)
+    c = m.cfg
+    E, QD = c.n_embd, c.n_head * c.head_dim
+    raw = ol.fill_normal(QD * E, ol.tensor_seed(c.seed, 16 + 1), c.sigma)
+    data, gama = ol.quantize(raw, QD, E, 4, 128, ol.RTN_ASYM)
+    assert np.array_equal(m.weight(17), ol.dequant(data, gama, QD, E, 4, 128, 0).reshape(-1))
+    assert np.array_equal(m.weight(16), np.full(E, 0x3F80, dtype=np.uint16))  # norms are 1 (FIX_1)
