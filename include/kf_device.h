@@ -1,0 +1,171 @@
+/*
+ * kf_device.h -- the C ABI of koifish_b200's device layer (the drop-in boundary for Koifish's quantized-inference
+ * hot path on B200 / sm_100a).
+ *
+ * The reference has no FFI layer: the path sits behind C++ neuron/tensor calls.  Each entry
+ * point below names the reference interface it replaces (file:line relative to the reference tree).  Conventions:
+ *   - plain pointers and sizes only; every pointer called "dev" is a CUDA device pointer, "host" a host pointer;
+ *   - all bf16 tensors are raw uint16 bit patterns (floatX == floatGama == __nv_bfloat16, src/g_float.hpp:246-261);
+ *   - every call returns an int status: 0 = KF_OK, negative = error (never exit(), unlike the reference's
+ *     cudaCheck -> exit(KOIFISH_*), src/Device/CUDA/cuda_common.h:44-76);
+ *   - kernels are launched on the context's stream; no call synchronises unless it says so;
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns KF_ERR_NO_DEVICE.
+ */
+#ifndef KF_DEVICE_H
+#define KF_DEVICE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (reference: exit codes in src/g_def_x.hpp:21-83, e.g. KOIFISH_QUANT_ERR -701) ---- */
+enum {
+    KF_OK              = 0,
+    KF_ERR_NO_DEVICE   = -100,
+    KF_ERR_CUDA        = -101,
+    KF_ERR_BAD_ARG     = -102,
+    KF_ERR_UNSUPPORTED = -103,
+    KF_ERR_OOM         = -104,
+    KF_ERR_NCCL        = -105,
+    KF_ERR_QUANT       = -701,
+};
+
+/* ---- tensor storage types (typNUMBER, src/g_float.hpp:84-117; Bits2Type :177-192) ---- */
+enum {
+    KF_T_BF16     = 0, /* typNUMBER::BF16     16-bit, no quant                                   */
+    KF_T_F8E5M2   = 1, /* typNUMBER::F8E5M2   8-bit = high byte of fp16 (packedN.cuh:80-96)      */
+    KF_T_Q4       = 2, /* typNUMBER::Q4       4-bit codes in 128-bit words (PackedQ.hpp:99-183)  */
+    KF_T_Q2       = 3, /* typNUMBER::Q2       2-bit RTN codes in 128-bit words                   */
+    KF_T_SIGN     = 4, /* typNUMBER::T_SIGN   2-bit ternary {-1,0,1}+1 (yyang / bitnet)          */
+    KF_T_BINARY   = 5, /* typNUMBER::T_BINARY 1-bit {0,1} (yyang)                                */
+};
+
+/* ---- quantisation modes (QUANT_CARD, src/CLI_params.hpp:509-554; GeQuant ctor src/Tensor/GeQuant.cpp:107-124) ---- */
+enum {
+    KF_Q_RTN_ASYM = 0,
+    KF_Q_RTN_SYM  = 1,
+    KF_Q_YYANG    = 2,
+};
+
+/* A (possibly quantised) weight W[rows = N_out][cols = K_in], row-major, as the reference stores it: ONE blob
+ * data || gama (src/Tensor/GTensor.cpp:456-510, :1017):  gama = bf16 [R_SCALE rows][C_SCALE cols][ZERO nG][STEP nG],
+ * nG = rows*cols/group.  gama may be NULL for BF16 / F8E5M2.  Mirrors what TASKA_quant passes to the reference's kernels
+ * (src/Tensor/GeQuant.hpp:147-177). */
+typedef struct kf_tensor_desc {
+    const void* data_dev;
+    const void* gama_dev;
+    int rows, cols;
+    int type;  /* KF_T_* */
+    int group; /* T_group, 128 */
+    int qbias; /* stored code = qid + qbias */
+    /* optional: explicit ZERO / STEP arrays (bf16, one per group, row-major over this tensor's rows).  When NULL they are
+     * located inside gama_dev by the blob layout above.  Used for row-slice views of a tensor (vocab-sharded tied lm_head). */
+    const void* zero_dev;
+    const void* step_dev;
+} kf_tensor_desc;
+
+typedef struct kf_ctx kf_ctx;
+
+/* ---- context: replaces InitCUDA / main_stream / gBUFF scratch (src/Device/CUDA/QKV.cu:501-571, huTensor.cu:922-1003) ---- */
+int kf_ctx_create(int device, void* cuda_stream /* cudaStream_t or NULL: the context creates its own */, kf_ctx** out);
+int kf_ctx_destroy(kf_ctx* ctx);
+int kf_ctx_sync(kf_ctx* ctx);
+void* kf_ctx_stream(kf_ctx* ctx);
+int kf_ctx_sm_count(kf_ctx* ctx);
+const char* kf_status_string(int status);
+const char* kf_last_error(kf_ctx* ctx);
+/* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
+uint64_t kf_launch_count(kf_ctx* ctx);
+/* tuning knobs for sweeps: "gemv_splitk" (0 = heuristic), "gemv_variant" */
+int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value);
+
+/* ---- device memory (huTensor::Alloc_1, src/Device/CUDA/huTensor.cu:70-103) ---- */
+int kf_malloc(kf_ctx* ctx, size_t bytes, void** dev_out);
+int kf_free(kf_ctx* ctx, void* dev);
+int kf_memset(kf_ctx* ctx, void* dev, int value, size_t bytes);
+int kf_h2d(kf_ctx* ctx, void* dev, const void* host, size_t bytes);  /* async on the stream (pinned host) or staged */
+int kf_d2h(kf_ctx* ctx, void* host, const void* dev, size_t bytes);  /* async on the stream; call kf_ctx_sync before reading */
+int kf_d2d(kf_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
+int kf_host_alloc(size_t bytes, void** host_out); /* pinned */
+int kf_host_free(void* host);
+
+/* ---- CUDA graph capture of a launch sequence (no reference equivalent: it launches ~40 kernels/layer eagerly) ---- */
+typedef struct kf_graph kf_graph;
+int kf_graph_begin(kf_ctx* ctx);
+int kf_graph_end(kf_ctx* ctx, kf_graph** out);
+int kf_graph_launch(kf_ctx* ctx, kf_graph* g);
+int kf_graph_destroy(kf_graph* g);
+
+/* ---- synthetic weights: replaces CU_disti_normal in huTensor::InitParam (src/Device/CUDA/huTensor.cu:199-210) ---- */
+int kf_fill_normal(kf_ctx* ctx, void* out_bf16_dev, size_t n, uint64_t seed, float sigma, float mean);
+/* a [rows, cols] window at (row0, col0) of a virtual row-major matrix with ld_global columns: element (r, c) takes the
+ * generator index (row0 + r) * ld_global + col0 + c, so a tensor-parallel shard equals the slice of the full tensor */
+int kf_fill_normal_2d(kf_ctx* ctx, void* out_bf16_dev, int rows, int cols, size_t ld_global, size_t row0, size_t col0, uint64_t seed,
+                      float sigma, float mean);
+
+/* ---- quantise at load: GeQuant::LowBit_worker with flag 0x100 (source on GPU), src/Tensor/GeQuant.cpp:830-905;
+ *      arithmetic of RTN_x :428-533 / YinYang :536-628 ; 8-bit: huTensor::ToF8Ex src/Device/CUDA/huTensor.cu:821-850 ---- */
+size_t kf_quant_data_bytes(int rows, int cols, int type);
+size_t kf_quant_gama_bytes(int rows, int cols, int type, int group);
+int kf_quantize(kf_ctx* ctx, const void* w_bf16_dev, int rows, int cols, int type, int group, int mode, void* data_dev, void* gama_dev,
+                int* qbias_out);
+
+/* ---- GTensor::GetDataX (src/Device/CUDA/kernel/quantizer.cu:249-392): dequantise the whole weight to bf16 [rows, cols].
+ *      Test hook only: the product never materialises dequantised weights. ---- */
+int kf_dequant(kf_ctx* ctx, const kf_tensor_desc* w, void* out_bf16_dev);
+
+/* ---- TASKA_AxB::blasLt as used by SLP::Forw (src/Tensor/GTensor.hpp:703-741, src/Device/CUDA/NeuronFuse.cu:305-381):
+ *      y[M][rows] = x[M][cols] . deq(W)^T, fp32 accumulate, bf16 out.  The reference dequantises W to a scratch and calls
+ *      cuBLASLt; here unpack + dequant are fused into the matmul.
+ *      epilogue flags: KF_EPI_RESIDUAL  y = RN(residual + RN_bf16(acc))   (replaces the following CU_add3, packedN.cuh:867-875)
+ *      M <= 64 takes the HBM-bound skinny path; larger M the tensor-core path. ---- */
+enum { KF_EPI_NONE = 0, KF_EPI_RESIDUAL = 1, KF_EPI_F32 = 4 /* y is float [M][rows], unrounded partial sums (tensor parallel) */ };
+int kf_linear(kf_ctx* ctx, void* y_dev, const kf_tensor_desc* w, const void* x_dev, int M, int epilogue, const void* residual_dev);
+/* up to 3 weights sharing x (Q/K/V: SelfAttention::cuInfer, src/Device/CUDA/QKV.cu:648-652) in one launch; y_dev[i] is [M][rows_i] */
+int kf_linear_multi(kf_ctx* ctx, int n, void* const* y_dev, const kf_tensor_desc* w, const void* x_dev, int M);
+/* FFN gate/up + CU_swiglu_v0 (src/Device/CUDA/NeuronFuse.cu:628-637, Activation.cu:86-93): y = silu(bf16(Wg x)) * bf16(Wu x) */
+int kf_linear_swiglu(kf_ctx* ctx, void* y_dev, const kf_tensor_desc* w_gate, const kf_tensor_desc* w_up, const void* x_dev, int M);
+
+/* ---- LayerNormal::cuFlow chat branch -> CU_rms_infer (src/Device/CUDA/T.cu:569-573, kernel/layernorm.cuh:801-859) ---- */
+int kf_rmsnorm(kf_ctx* ctx, void* out_dev, const void* x_dev, const void* w_dev, int rows, int dim, float eps);
+/* ---- ROPE::cuInfer (src/Device/CUDA/kernel/rope.cu:645-672): per-head QK RMSNorm (layernorm.cuh:750-798), half-split RoPE
+ *      (operator.cuh:735-772) on q and k, and the K/V rows written at `pos` of the cache (the reference aliases K.out/V.out
+ *      onto the cache rows, src/Manifold/TGraph.cpp:198-208).  q is updated in place.  pos_dev: device int32[M] positions.
+ *      rope_table_dev: float2 (cos, sin) [max_seq][head_dim/2] built by kf_rope_table. ---- */
+int kf_rope_table(kf_ctx* ctx, void* table_dev, int max_seq, int head_dim, float theta);
+int kf_qknorm_rope_kvappend(kf_ctx* ctx, void* q_dev, const void* k_dev, const void* v_dev, const void* qnorm_w_dev, const void* knorm_w_dev,
+                            void* kcache_layer_dev, void* vcache_layer_dev, const void* rope_table_dev, const int32_t* pos_dev, int M,
+                            int n_head, int n_kv, int head_dim, int max_seq, float eps, size_t seq_stride);
+/* seq_stride (elements): token m uses the cache at base + m*seq_stride.  0 = all M tokens belong to ONE sequence (prefill panel:
+ * token m attends to positions 0..pos[m]); max_seq*n_kv*head_dim = M independent sequences (batched decode). */
+/* ---- attention_qk_kernel + CU_softmax_multihead + attention_v_kernel (src/Device/CUDA/kernel/operator.cuh:573-632, 252-277,
+ *      650-668): GQA decode attention over a contiguous bf16 cache [max_seq][n_kv*hd] (KVCache, src/Utils/Cache.cpp:14-60),
+ *      split-K over the sequence.  M query tokens; token m attends to positions 0..pos[m]. ---- */
+int kf_attn_decode(kf_ctx* ctx, void* out_dev, const void* q_dev, const void* kcache_layer_dev, const void* vcache_layer_dev,
+                   const int32_t* pos_dev, int M, int n_head, int n_kv, int head_dim, int max_seq, int max_pos_hint, size_t seq_stride);
+/* ---- CU_swiglu_v0 (Activation.cu:86-93), CU_add3 (packedN.cuh:867-875) as stand-alone ops ---- */
+int kf_swiglu(kf_ctx* ctx, void* out_dev, const void* gate_dev, const void* up_dev, size_t n);
+int kf_add(kf_ctx* ctx, void* out_dev, const void* a_dev, const void* b_dev, size_t n);
+/* out = RN(residual + RN_bf16(sum_f32)): the residual add after a tensor-parallel all-reduce of fp32 partial sums */
+int kf_residual_add_f32(kf_ctx* ctx, void* out_dev, const void* residual_dev, const float* sum_f32_dev, size_t n);
+/* pos[m] += 1 ; used by the device-resident greedy decode loop */
+int kf_advance_pos(kf_ctx* ctx, int32_t* pos_dev, int M);
+/* ---- TokenEmbed::cuInfer (src/Device/CUDA/NeuronFuse.cu:176-207, kernel/embed.cuh:55-133): out[m] = deq(W[token[m]]) ---- */
+int kf_embed(kf_ctx* ctx, void* out_dev, const kf_tensor_desc* w, const int32_t* tokens_dev, int M);
+/* greedy sampler on device (the reference copies logits to the host, GoPT.cpp:614-630): out_token[m] = argmax(logits[m]) */
+int kf_argmax(kf_ctx* ctx, int32_t* out_tokens_dev, const void* logits_bf16_dev, int M, int vocab);
+
+/* ---- tensor parallel: no reference equivalent (multi_gpu.cuh is dead code).  One process per GPU;
+ *      the unique id is exchanged by the caller (torch.distributed / MPI) ---- */
+int kf_nccl_unique_id(void* id_out_128_bytes);
+int kf_ctx_init_nccl(kf_ctx* ctx, const void* id_128_bytes, int rank, int world);
+int kf_allreduce_bf16(kf_ctx* ctx, void* buf_dev, size_t count); /* in-place sum over ranks, on the stream */
+int kf_allreduce_f32(kf_ctx* ctx, float* buf_dev, size_t count);
+int kf_allgather(kf_ctx* ctx, void* out_dev, const void* in_dev, size_t bytes_per_rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KF_DEVICE_H */

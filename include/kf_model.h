@@ -1,0 +1,77 @@
+/*
+ * kf_model.h -- C ABI of the host-side Qwen3 runtime (koifish_b200/csrc/Transformer, csrc/Tensor), i.e. what a Koifish
+ * maintainer binds instead of Fish::MakeInstance / Fish::Chat / Fish::ForwardOnRLS (reference src/Manifold/Fish.cpp:13-95,
+ * src/Manifold/GoPT.cpp:1111-1235, src/Manifold/gLLM.cpp:706-787).  Plain pointers and sizes only; every call returns a
+ * kf_device.h status code and never exits.  Token ids / positions / logits cross this boundary in HOST memory; the
+ * host<->device copies happen inside the call.
+ */
+#ifndef KF_MODEL_H
+#define KF_MODEL_H
+#include "kf_device.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kf_model kf_model;
+
+typedef struct kf_model_info {
+    int n_layers, n_embd, n_ff, n_head, n_head_kv, head_dim, vocab, max_seq_len, max_batch, max_tokens;
+    int tp_rank, tp_world;
+    int tie_word_embeddings;
+    float rope_theta, norm_rms_eps;
+    uint64_t weight_bytes;   /* packed weights + gama resident on THIS rank */
+    uint64_t kv_bytes;       /* KV cache bytes on this rank */
+    uint64_t block_weight_bytes_per_layer; /* packed+gama bytes of one transformer block on this rank */
+    uint64_t head_weight_bytes;            /* lm_head bytes read per token on this rank */
+} kf_model_info;
+
+/* config_json: a Koifish JSON config (keys model.arch, model.parameter.{Layer, transformer.{Ctx,Embed,Ffn,Head,KVHead,head_dim},
+ * tie_word_embeddings, max_pos_embeddings}, quantizer.{group_size, <name-substring>:{quant_method,bits,group_size}}, seed,
+ * gpt.max_seq_len -- reference cases/qwen3/qwen3_596M_q4.json, src/Utils/CLI_params.cpp:1480-1545, src/Tensor/GeQuant.cpp:1186-1285)
+ * or an HF config.json (src/Utils/CLI_params.cpp:2224-2300).  Extensions: model.parameter.{vocab_size, rope_theta},
+ * gpt.max_batch, init.{sigma, norm_sigma}.  On error *err_out (if given) receives a malloc'ed message (free with kf_string_free). */
+int kf_model_create(kf_ctx* ctx, const char* config_json, int tp_rank, int tp_world, kf_model** out, char** err_out);
+int kf_model_destroy(kf_model* m);
+const char* kf_model_error(kf_model* m);
+void kf_string_free(char* s);
+int kf_model_info_get(kf_model* m, kf_model_info* out);
+
+/* huTensor::InitParam random path (reference src/Device/CUDA/huTensor.cu:157-231): synthetic N(0, sigma^2)-like weights from the
+ * framework's counter-based generator, quantised at load per the quantizer card (GeQuant::LowBit_worker, GeQuant.cpp:830-905) */
+int kf_model_init_random(kf_model* m);
+/* SERIALIZE path: hand over one FULL (unsharded) bf16 tensor by its HF name (NN2NAME, src/Transformer/QWen.cpp:61-145);
+ * it is sharded for this rank and quantised at load */
+int kf_model_set_tensor(kf_model* m, const char* hf_name, const void* host_bf16, int rows, int cols);
+/* descriptor of the device-resident (possibly packed) tensor: for parity tests (GetDataX equivalent via kf_dequant) */
+int kf_model_tensor_desc(kf_model* m, const char* hf_name, kf_tensor_desc* out);
+int kf_model_tensor_count(kf_model* m);
+const char* kf_model_tensor_name(kf_model* m, int index);
+void* kf_model_kcache(kf_model* m, int layer);
+void* kf_model_vcache(kf_model* m, int layer);
+
+/* One forward over M tokens (Fish::ForwardOnRLS; one call per token in the reference's Chat loop, GoPT.cpp:1139-1146).
+ *   seq_mode 0: the M tokens are consecutive positions of ONE sequence (prefill panel; M <= max_tokens);
+ *   seq_mode 1: M independent sequences, one token each (batched decode; M <= gpt.max_batch).
+ * tokens_host / pos_host: int32[M].  logits_host (optional): bf16 [M][vocab].  next_host (optional): int32[M] greedy argmax.
+ * Synchronous: returns after the results are in host memory. */
+int kf_model_forward(kf_model* m, const int32_t* tokens_host, const int32_t* pos_host, int M, int seq_mode, void* logits_host,
+                     int32_t* next_host);
+/* n_steps greedy decode steps entirely on the device (each step a CUDA-graph replay feeding its argmax back as the next token),
+ * continuing from the tokens/positions of the last kf_model_forward.  Asynchronous; kf_ctx_sync() to wait. */
+int kf_model_decode_loop(kf_model* m, int n_steps, int M);
+/* current device-side tokens / positions (after a decode loop) */
+int kf_model_read_state(kf_model* m, int32_t* tokens_host, int32_t* pos_host, int M);
+int kf_model_set_graphs(kf_model* m, int enable);
+
+/* Host-only config logic (no device needed): parse a config and report the model dimensions, and which storage type the
+ * quantizer block selects for a tensor name (QUANT_CARD::Init4Neuron, reference src/Tensor/GeQuant.cpp:1186-1285; MakeInstance
+ * :23-81).  type_out: KF_T_* (KF_T_BF16 when the tensor is not quantised); mode_out: KF_Q_*. */
+int kf_config_dims(const char* config_json, kf_model_info* out, char** err_out);
+int kf_config_quant_of(const char* config_json, const char* tensor_name, int* type_out, int* group_out, int* mode_out, int* qbias_out,
+                       char** err_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KF_MODEL_H */

@@ -1,0 +1,382 @@
+"""Thin Python view of the C ABI: device context, device arrays, quantised tensors, the hot-path ops and the Qwen3 runtime.
+All compute happens in libkoifish_b200.so (hand-written sm_100a CUDA); numpy is only the host container.
+bf16 data is carried as uint16 bit patterns."""
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import KoifishError, TensorDesc, ModelInfo  # noqa: F401
+
+
+class Context:
+    """kf_ctx: one device + one stream (reference: InitCUDA / main_stream, src/Device/CUDA/QKV.cu:501-571)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = L.load()
+        h = C.c_void_p()
+        st = self.lib.kf_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if st != L.KF_OK:
+            raise KoifishError(st, "kf_ctx_create")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kf_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, st, where):
+        L.check(st, where, self.h)
+
+    def sync(self):
+        self.check(self.lib.kf_ctx_sync(self.h), "kf_ctx_sync")
+
+    @property
+    def stream(self):
+        return self.lib.kf_ctx_stream(self.h)
+
+    @property
+    def sm_count(self):
+        return self.lib.kf_ctx_sm_count(self.h)
+
+    @property
+    def launches(self):
+        return int(self.lib.kf_launch_count(self.h))
+
+    def set_int(self, key, value):
+        self.check(self.lib.kf_ctx_set_int(self.h, key.encode(), int(value)), "kf_ctx_set_int")
+
+    # ---- memory
+    def empty(self, nbytes):
+        return DevArray(self, nbytes)
+
+    def array(self, a):
+        a = np.ascontiguousarray(a)
+        d = DevArray(self, a.nbytes)
+        d.copy_from(a)
+        return d
+
+    def zeros(self, nbytes):
+        d = DevArray(self, nbytes)
+        self.check(self.lib.kf_memset(self.h, d.ptr, 0, nbytes), "kf_memset")
+        return d
+
+
+class DevArray:
+    def __init__(self, ctx, nbytes):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        ctx.check(ctx.lib.kf_malloc(ctx.h, self.nbytes, C.byref(p)), "kf_malloc(%d)" % nbytes)
+        self.ptr = p.value
+
+    def free(self):
+        if getattr(self, "ptr", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.kf_free(self.ctx.h, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def copy_from(self, a):
+        a = np.ascontiguousarray(a)
+        assert a.nbytes <= self.nbytes
+        self.ctx.check(self.ctx.lib.kf_h2d(self.ctx.h, self.ptr, a.ctypes.data, a.nbytes), "kf_h2d")
+        self.ctx.sync()  # pageable host memory: make the copy complete before `a` can go away
+
+    def numpy(self, dtype=np.uint16, shape=None, offset=0, count=None):
+        dtype = np.dtype(dtype)
+        n = (self.nbytes - offset) // dtype.itemsize if count is None else count
+        out = np.empty(n, dtype=dtype)
+        self.ctx.check(self.ctx.lib.kf_d2h(self.ctx.h, out.ctypes.data, self.ptr + offset, out.nbytes), "kf_d2h")
+        self.ctx.sync()
+        return out.reshape(shape) if shape is not None else out
+
+
+class QTensor:
+    """A weight in the reference's storage form: packed data || gama."""
+
+    def __init__(self, ctx, rows, cols, type_, group=128, qbias=0):
+        self.ctx, self.rows, self.cols, self.type, self.group, self.qbias = ctx, rows, cols, type_, group, qbias
+        self.data_bytes = ctx.lib.kf_quant_data_bytes(rows, cols, type_)
+        self.gama_bytes = ctx.lib.kf_quant_gama_bytes(rows, cols, type_, group)
+        self.blob = ctx.empty(self.data_bytes + self.gama_bytes + 16)
+
+    @property
+    def data_ptr(self):
+        return self.blob.ptr
+
+    @property
+    def gama_ptr(self):
+        return self.blob.ptr + self.data_bytes if self.gama_bytes else None
+
+    def desc(self):
+        return TensorDesc(self.data_ptr, self.gama_ptr, self.rows, self.cols, self.type, self.group, self.qbias, None, None)
+
+    def data_numpy(self):
+        return self.blob.numpy(np.uint8, count=self.data_bytes)
+
+    def gama_numpy(self):
+        return self.blob.numpy(np.uint16, offset=self.data_bytes, count=self.gama_bytes // 2)
+
+    @property
+    def nbytes(self):
+        return self.data_bytes + self.gama_bytes
+
+    @classmethod
+    def from_packed(cls, ctx, data, gama, rows, cols, type_, group=128, qbias=0):
+        """wrap bytes produced elsewhere (e.g. by the test oracle's packer)"""
+        t = cls(ctx, rows, cols, type_, group, qbias)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        assert data.nbytes == t.data_bytes
+        ctx.check(ctx.lib.kf_h2d(ctx.h, t.data_ptr, data.ctypes.data, data.nbytes), "kf_h2d")
+        if t.gama_bytes:
+            gama = np.ascontiguousarray(gama, dtype=np.uint16)
+            assert gama.nbytes == t.gama_bytes
+            ctx.check(ctx.lib.kf_h2d(ctx.h, t.gama_ptr, gama.ctypes.data, gama.nbytes), "kf_h2d")
+        ctx.sync()
+        return t
+
+
+def fill_normal(ctx, n, seed, sigma=0.02, mean=0.0):
+    d = ctx.empty(n * 2)
+    ctx.check(ctx.lib.kf_fill_normal(ctx.h, d.ptr, n, seed, sigma, mean), "kf_fill_normal")
+    return d
+
+
+def fill_normal_2d(ctx, rows, cols, ld, row0, col0, seed, sigma=0.02, mean=0.0):
+    d = ctx.empty(rows * cols * 2)
+    ctx.check(ctx.lib.kf_fill_normal_2d(ctx.h, d.ptr, rows, cols, ld, row0, col0, seed, sigma, mean), "kf_fill_normal_2d")
+    return d
+
+
+def quantize(ctx, w_dev, rows, cols, type_, group=128, mode=L.KF_Q_RTN_ASYM):
+    """GeQuant::LowBit_worker(flag 0x100) on the device (reference src/Tensor/GeQuant.cpp:830-905)."""
+    t = QTensor(ctx, rows, cols, type_, group)
+    qb = C.c_int(0)
+    ctx.check(ctx.lib.kf_quantize(ctx.h, w_dev.ptr, rows, cols, type_, group, mode, t.data_ptr, t.gama_ptr, C.byref(qb)), "kf_quantize")
+    t.qbias = qb.value
+    return t
+
+
+def dequant(ctx, t):
+    """GTensor::GetDataX test hook -> DevArray of bf16 [rows, cols]"""
+    out = ctx.empty(t.rows * t.cols * 2)
+    d = t.desc()
+    ctx.check(ctx.lib.kf_dequant(ctx.h, C.byref(d), out.ptr), "kf_dequant")
+    return out
+
+
+def linear(ctx, w, x, M, epilogue=L.KF_EPI_NONE, residual=None, out=None):
+    """TASKA_AxB::blasLt / SLP::Forw: y[M][rows] = x[M][cols] . deq(W)^T"""
+    if out is None:
+        out = ctx.empty(M * w.rows * (4 if epilogue == L.KF_EPI_F32 else 2))
+    d = w.desc()
+    ctx.check(ctx.lib.kf_linear(ctx.h, out.ptr, C.byref(d), x.ptr, M, epilogue, residual.ptr if residual is not None else None), "kf_linear")
+    return out
+
+
+def linear_multi(ctx, ws, x, M):
+    outs = [ctx.empty(M * w.rows * 2) for w in ws]
+    descs = (TensorDesc * len(ws))(*[w.desc() for w in ws])
+    ys = (C.c_void_p * len(ws))(*[o.ptr for o in outs])
+    ctx.check(ctx.lib.kf_linear_multi(ctx.h, len(ws), ys, descs, x.ptr, M), "kf_linear_multi")
+    return outs
+
+
+def linear_swiglu(ctx, wg, wu, x, M):
+    out = ctx.empty(M * wg.rows * 2)
+    dg, du = wg.desc(), wu.desc()
+    ctx.check(ctx.lib.kf_linear_swiglu(ctx.h, out.ptr, C.byref(dg), C.byref(du), x.ptr, M), "kf_linear_swiglu")
+    return out
+
+
+def rmsnorm(ctx, x, w, rows, dim, eps=1e-6):
+    out = ctx.empty(rows * dim * 2)
+    ctx.check(ctx.lib.kf_rmsnorm(ctx.h, out.ptr, x.ptr, w.ptr, rows, dim, eps), "kf_rmsnorm")
+    return out
+
+
+def rope_table(ctx, max_seq, head_dim, theta):
+    t = ctx.empty(max_seq * (head_dim // 2) * 8)
+    ctx.check(ctx.lib.kf_rope_table(ctx.h, t.ptr, max_seq, head_dim, theta), "kf_rope_table")
+    return t
+
+
+def qknorm_rope_kvappend(ctx, q, k, v, qw, kw, kcache, vcache, table, pos, M, n_head, n_kv, hd, max_seq, eps=1e-6, seq_stride=0):
+    ctx.check(ctx.lib.kf_qknorm_rope_kvappend(ctx.h, q.ptr, k.ptr, v.ptr, qw.ptr if qw is not None else None, kw.ptr if kw is not None else None,
+                                              kcache.ptr, vcache.ptr, table.ptr, pos.ptr, M, n_head, n_kv, hd, max_seq, eps, seq_stride),
+              "kf_qknorm_rope_kvappend")
+
+
+def attn_decode(ctx, q, kcache, vcache, pos, M, n_head, n_kv, hd, max_seq, max_pos_hint, seq_stride=0):
+    out = ctx.empty(M * n_head * hd * 2)
+    ctx.check(ctx.lib.kf_attn_decode(ctx.h, out.ptr, q.ptr, kcache.ptr, vcache.ptr, pos.ptr, M, n_head, n_kv, hd, max_seq, max_pos_hint, seq_stride),
+              "kf_attn_decode")
+    return out
+
+
+def swiglu(ctx, g, u, n):
+    out = ctx.empty(n * 2)
+    ctx.check(ctx.lib.kf_swiglu(ctx.h, out.ptr, g.ptr, u.ptr, n), "kf_swiglu")
+    return out
+
+
+def add(ctx, a, b, n):
+    out = ctx.empty(n * 2)
+    ctx.check(ctx.lib.kf_add(ctx.h, out.ptr, a.ptr, b.ptr, n), "kf_add")
+    return out
+
+
+def embed(ctx, w, tokens, M):
+    out = ctx.empty(M * w.cols * 2)
+    d = w.desc()
+    ctx.check(ctx.lib.kf_embed(ctx.h, out.ptr, C.byref(d), tokens.ptr, M), "kf_embed")
+    return out
+
+
+def argmax(ctx, logits, M, vocab):
+    out = ctx.empty(M * 4)
+    ctx.check(ctx.lib.kf_argmax(ctx.h, out.ptr, logits.ptr, M, vocab), "kf_argmax")
+    return out
+
+
+class Model:
+    """The Qwen3 runtime behind include/kf_model.h (reference: Fish::MakeInstance + Fish::Chat's per-token ForwardOnRLS)."""
+
+    def __init__(self, ctx, config, tp_rank=0, tp_world=1):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        text = config if isinstance(config, str) else json.dumps(config)
+        h, err = C.c_void_p(), C.c_void_p()
+        st = self.lib.kf_model_create(ctx.h, text.encode(), tp_rank, tp_world, C.byref(h), C.byref(err))
+        if st != L.KF_OK:
+            msg = C.cast(err, C.c_char_p).value.decode() if err.value else ""
+            if err.value:
+                self.lib.kf_string_free(err)
+            raise KoifishError(st, "kf_model_create", msg)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kf_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st, where):
+        if st != L.KF_OK:
+            raise KoifishError(st, where, self.lib.kf_model_error(self.h).decode() + " | " + self.lib.kf_last_error(self.ctx.h).decode())
+
+    @property
+    def info(self):
+        i = ModelInfo()
+        self._check(self.lib.kf_model_info_get(self.h, C.byref(i)), "kf_model_info_get")
+        return i
+
+    def init_random(self):
+        self._check(self.lib.kf_model_init_random(self.h), "kf_model_init_random")
+
+    def set_tensor(self, name, w_bf16):
+        w = np.ascontiguousarray(w_bf16, dtype=np.uint16)
+        rows, cols = (1, w.size) if w.ndim == 1 else w.shape
+        self._check(self.lib.kf_model_set_tensor(self.h, name.encode(), w.ctypes.data, rows, cols), "kf_model_set_tensor(%s)" % name)
+
+    def tensor_names(self):
+        return [self.lib.kf_model_tensor_name(self.h, i).decode() for i in range(self.lib.kf_model_tensor_count(self.h))]
+
+    def tensor_desc(self, name):
+        d = TensorDesc()
+        self._check(self.lib.kf_model_tensor_desc(self.h, name.encode(), C.byref(d)), "kf_model_tensor_desc(%s)" % name)
+        return d
+
+    def dequant_tensor(self, name):
+        """GetDataX of a resident tensor -> numpy bf16 bits [rows, cols]"""
+        d = self.tensor_desc(name)
+        out = self.ctx.empty(d.rows * d.cols * 2)
+        self.ctx.check(self.lib.kf_dequant(self.ctx.h, C.byref(d), out.ptr), "kf_dequant")
+        return out.numpy(np.uint16, (d.rows, d.cols))
+
+    def forward(self, tokens, pos, seq_mode=0, want_logits=True, want_next=False):
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32).reshape(-1)
+        pos = np.ascontiguousarray(pos, dtype=np.int32).reshape(-1)
+        M = tokens.size
+        vocab = self.info.vocab
+        logits = np.empty((M, vocab), dtype=np.uint16) if want_logits else None
+        nxt = np.empty(M, dtype=np.int32) if want_next else None
+        self._check(self.lib.kf_model_forward(self.h, tokens.ctypes.data, pos.ctypes.data, M, seq_mode,
+                                              logits.ctypes.data if want_logits else None, nxt.ctypes.data if want_next else None), "kf_model_forward")
+        return logits, nxt
+
+    def decode_loop(self, n_steps, M=1):
+        self._check(self.lib.kf_model_decode_loop(self.h, n_steps, M), "kf_model_decode_loop")
+
+    def read_state(self, M=1):
+        t, p = np.empty(M, dtype=np.int32), np.empty(M, dtype=np.int32)
+        self._check(self.lib.kf_model_read_state(self.h, t.ctypes.data, p.ctypes.data, M), "kf_model_read_state")
+        return t, p
+
+    def set_graphs(self, enable):
+        self._check(self.lib.kf_model_set_graphs(self.h, int(bool(enable))), "kf_model_set_graphs")
+
+    def kcache(self, layer, npos, kv_dim):
+        p = self.lib.kf_model_kcache(self.h, layer)
+        out = np.empty(npos * kv_dim, dtype=np.uint16)
+        self.ctx.check(self.lib.kf_d2h(self.ctx.h, out.ctypes.data, p, out.nbytes), "kf_d2h")
+        self.ctx.sync()
+        return out.reshape(npos, kv_dim)
+
+    def vcache(self, layer, npos, kv_dim):
+        p = self.lib.kf_model_vcache(self.h, layer)
+        out = np.empty(npos * kv_dim, dtype=np.uint16)
+        self.ctx.check(self.lib.kf_d2h(self.ctx.h, out.ctypes.data, p, out.nbytes), "kf_d2h")
+        self.ctx.sync()
+        return out.reshape(npos, kv_dim)
+
+
+def qwen3_config(n_layer, n_embd, n_ff, n_head, n_kv_head, head_dim=128, vocab=151936, quantizer=None, tie=False, max_seq_len=1024,
+                 max_batch=1, seed=42, rope_theta=None, sigma=None, norm_sigma=None):
+    """a Koifish-style JSON config (reference cases/qwen3/qwen3_596M_q4.json layout) as a dict"""
+    cfg = {
+        "version": "0.1.0",
+        "model": {"arch": "QWEN3", "parameter": {
+            "Layer": n_layer,
+            "transformer": {"Ctx": max_seq_len, "Embed": n_embd, "Ffn": n_ff, "Head": n_head, "KVHead": n_kv_head, "head_dim": head_dim},
+            "tie_word_embeddings": bool(tie), "max_pos_embeddings": 32768, "vocab_size": vocab}},
+        "gpt": {"max_seq_len": max_seq_len, "max_batch": max_batch},
+        "seed": seed,
+    }
+    if rope_theta is not None:
+        cfg["model"]["parameter"]["rope_theta"] = rope_theta
+    if quantizer:
+        cfg["quantizer"] = quantizer
+    init = {}
+    if sigma is not None:
+        init["sigma"] = sigma
+    if norm_sigma is not None:
+        init["norm_sigma"] = norm_sigma
+    if init:
+        cfg["init"] = init
+    return cfg
+
+
+QWEN3_DIMS = {  # SURVEY.md section 8 table (HF Qwen3 configs)
+    "0.6B": dict(n_layer=28, n_embd=1024, n_ff=3072, n_head=16, n_kv_head=8, tie=True),
+    "8B": dict(n_layer=36, n_embd=4096, n_ff=12288, n_head=32, n_kv_head=8, tie=False),
+    "32B": dict(n_layer=64, n_embd=5120, n_ff=25600, n_head=64, n_kv_head=8, tie=False),
+}

@@ -1,0 +1,138 @@
+// kf_common.cuh -- shared definitions of the device layer (context, error handling, bf16 / PTX helpers).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "kf_device.h"
+
+struct ncclComm;
+
+struct kf_ctx {
+    int device           = 0;
+    cudaStream_t stream  = nullptr;
+    bool own_stream      = false;
+    int sm_count         = 148;
+    uint64_t launches    = 0;
+    bool capturing       = false;
+    // split-K workspace (fp32 partials) + per-row-block arrival counters (self-resetting)
+    float* gemv_ws       = nullptr;
+    size_t gemv_ws_bytes = 0;
+    unsigned* gemv_cnt   = nullptr;
+    int gemv_cnt_n       = 0;
+    // attention split workspace
+    float* attn_ws       = nullptr;
+    size_t attn_ws_bytes = 0;
+    // tuning
+    int gemv_splitk  = 0;
+    int gemv_variant = 0;
+    int attn_split   = 0;
+    // tensor parallel
+    ncclComm* nccl = nullptr;
+    int rank = 0, world = 1;
+    std::string last_error;
+};
+
+#define KF_CUDA(ctx, expr)                                                                                          \
+    do {                                                                                                            \
+        cudaError_t _e = (expr);                                                                                    \
+        if (_e != cudaSuccess) {                                                                                    \
+            if (ctx) {                                                                                              \
+                char _b[512];                                                                                       \
+                snprintf(_b, sizeof(_b), "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));       \
+                (ctx)->last_error = _b;                                                                             \
+            }                                                                                                       \
+            return _e == cudaErrorMemoryAllocation ? KF_ERR_OOM : KF_ERR_CUDA;                                      \
+        }                                                                                                           \
+    } while (0)
+
+#define KF_REQUIRE(ctx, cond, msg)                                                        \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            if (ctx) {                                                                    \
+                char _b[512];                                                             \
+                snprintf(_b, sizeof(_b), "%s:%d requirement failed: %s (%s)", __FILE__, __LINE__, #cond, msg); \
+                (ctx)->last_error = _b;                                                   \
+            }                                                                             \
+            return KF_ERR_BAD_ARG;                                                        \
+        }                                                                                 \
+    } while (0)
+
+#define KF_LAUNCH_CHECK(ctx)                    \
+    do {                                        \
+        (ctx)->launches++;                      \
+        KF_CUDA(ctx, cudaGetLastError());       \
+    } while (0)
+
+static inline int kf_type_bits(int type) {
+    switch (type) {
+        case KF_T_BF16: return 16;
+        case KF_T_F8E5M2: return 8;
+        case KF_T_Q4: return 4;
+        case KF_T_Q2:
+        case KF_T_SIGN: return 2;
+        case KF_T_BINARY: return 1;
+    }
+    return 0;
+}
+static inline bool kf_type_packed(int type) { return type == KF_T_Q4 || type == KF_T_Q2 || type == KF_T_SIGN || type == KF_T_BINARY; }
+
+// gama blob: [R_SCALE rows][C_SCALE cols][ZERO nG][STEP nG]  (src/Tensor/GTensor.cpp:456-510)
+static inline const uint16_t* kf_gama_zero(const kf_tensor_desc& w) {
+    if (w.zero_dev) return (const uint16_t*)w.zero_dev;
+    return (const uint16_t*)w.gama_dev + w.rows + w.cols;
+}
+static inline const uint16_t* kf_gama_step(const kf_tensor_desc& w) {
+    if (w.step_dev) return (const uint16_t*)w.step_dev;
+    return (const uint16_t*)w.gama_dev + w.rows + w.cols + ((size_t)w.rows * w.cols) / w.group;
+}
+static inline bool kf_has_gama(const kf_tensor_desc& w) { return w.gama_dev || (w.zero_dev && w.step_dev); }
+
+int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters);
+int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes);
+// gemv.cu: skinny path (M <= 64); epilogue 0 none / 1 residual / 2 swiglu(gate = w[0], up = w[1])
+int kf_gemv_small(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float bf16_bits_to_f32(uint32_t h) { return __uint_as_float(h << 16); }
+__device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+__device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ __nv_bfloat162 u32_as_bf162(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
+__device__ __forceinline__ uint32_t bf162_as_u32(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
+
+// streaming 128-bit load: weights are read exactly once per token -> do not allocate in L1
+__device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream_v2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#endif

@@ -1,0 +1,40 @@
+// linear.cu -- the matmul entry points of the C ABI (TASKA_AxB::blasLt as used by SLP::Forw; reference
+// src/Tensor/GTensor.hpp:703-741, src/Device/CUDA/NeuronFuse.cu:305-381).  M <= 64 tokens go to the HBM-bound fused
+// dequant-GEMV (gemv.cu); larger M is processed in 64-token panels through the same kernel until the tcgen05 prefill GEMM
+// (gemm_tc.cu) takes over.
+#include "kf_common.cuh"
+
+static int linear_panels(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual) {
+    if (M <= 64) return kf_gemv_small(ctx, n, y, w, x, M, epilogue, residual);
+    const int K = w[0].cols;
+    for (int m0 = 0; m0 < M; m0 += 64) {
+        const int mm = M - m0 < 64 ? M - m0 : 64;
+        void* yy[3];
+        for (int i = 0; i < n; i++) {
+            const int rows = (epilogue == 2 && i == 1) ? 0 : w[i].rows;
+            yy[i]          = y[i] ? (void*)((char*)y[i] + (size_t)m0 * rows * (epilogue == KF_EPI_F32 ? 4 : 2)) : nullptr;
+        }
+        if (epilogue == 2) yy[1] = yy[0];
+        const void* res = residual ? (const void*)((const uint16_t*)residual + (size_t)m0 * w[0].rows) : nullptr;
+        int rc = kf_gemv_small(ctx, n, yy, w, (const uint16_t*)x + (size_t)m0 * K, mm, epilogue, res);
+        if (rc) return rc;
+    }
+    return KF_OK;
+}
+
+extern "C" int kf_linear(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual) {
+    if (!ctx || !y || !w || !x) return KF_ERR_BAD_ARG;
+    KF_REQUIRE(ctx, epilogue == KF_EPI_NONE || epilogue == KF_EPI_RESIDUAL || epilogue == KF_EPI_F32, "epilogue");
+    void* ys[1] = {y};
+    return linear_panels(ctx, 1, ys, w, x, M, epilogue, residual);
+}
+extern "C" int kf_linear_multi(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M) {
+    if (!ctx || !y || !w || !x) return KF_ERR_BAD_ARG;
+    return linear_panels(ctx, n, y, w, x, M, 0, nullptr);
+}
+extern "C" int kf_linear_swiglu(kf_ctx* ctx, void* y, const kf_tensor_desc* wg, const kf_tensor_desc* wu, const void* x, int M) {
+    if (!ctx || !y || !wg || !wu || !x) return KF_ERR_BAD_ARG;
+    kf_tensor_desc w[2] = {*wg, *wu};
+    void* ys[2]         = {y, y};
+    return linear_panels(ctx, 2, ys, w, x, M, 2, nullptr);
+}

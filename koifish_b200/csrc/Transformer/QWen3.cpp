@@ -1,0 +1,482 @@
+// QWen3.cpp -- Qwen3 decode / prefill on top of the device C ABI (see QWen3.hpp for the reference interfaces mirrored here).
+#include "QWen3.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+
+namespace koifish {
+
+#define KF_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        int _rc = (expr);                                                                              \
+        if (_rc != KF_OK) {                                                                            \
+            if (hFishErr) *hFishErr = std::string(#expr) + " -> " + kf_status_string(_rc);             \
+            return _rc;                                                                                \
+        }                                                                                              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------ config
+static int jint(const JSON& j, std::initializer_list<const char*> path, int dflt) {
+    const JSON* p = j.path(path);
+    return p ? p->as_int(dflt) : dflt;
+}
+MODEL_CARD MODEL_CARD::FromJSON(const JSON& j0) {
+    MODEL_CARD c;
+    const JSON* hf = j0.find("hf_config");
+    if (!hf && j0.contains("hidden_size")) hf = &j0;
+    if (hf) {  // HF config.json (MODEL_CARD::InitHugFace, src/Utils/CLI_params.cpp:2224-2300)
+        const JSON& h = *hf;
+        c.n_embd    = jint(h, {"hidden_size"}, 0);
+        c.n_ff      = jint(h, {"intermediate_size"}, 0);
+        c.n_layers  = jint(h, {"num_hidden_layers"}, 0);
+        c.n_head    = jint(h, {"num_attention_heads"}, 0);
+        c.n_head_kv = jint(h, {"num_key_value_heads"}, c.n_head);
+        c.head_dim  = jint(h, {"head_dim"}, c.n_head ? c.n_embd / c.n_head : 128);
+        c.vocab     = jint(h, {"vocab_size"}, c.vocab);
+        c.max_pos_embeddings = jint(h, {"max_position_embeddings"}, c.max_pos_embeddings);
+        if (const JSON* t = h.find("rope_theta")) c.rope_theta = (float)t->as_double(c.rope_theta);
+        if (const JSON* e = h.find("rms_norm_eps")) c.norm_rms_eps = (float)e->as_double(c.norm_rms_eps);
+        if (const JSON* t = h.find("tie_word_embeddings")) c.tie_word_embeddings = t->as_bool(false);
+        if (h.contains("quantization_config"))
+            throw std::runtime_error("HF quantization_config (vendor AWQ) is a 'next' row (SURVEY 8f N2), not built yet");
+    }
+    if (const JSON* m = j0.find("model")) {  // Koifish JSON (cases/qwen3/*.json)
+        if (const JSON* a = m->find("arch")) c.arch = a->as_string(c.arch);
+        c.n_layers  = jint(*m, {"parameter", "Layer"}, c.n_layers);
+        c.n_ctx     = jint(*m, {"parameter", "transformer", "Ctx"}, c.n_ctx);
+        c.n_embd    = jint(*m, {"parameter", "transformer", "Embed"}, c.n_embd);
+        c.n_ff      = jint(*m, {"parameter", "transformer", "Ffn"}, c.n_ff);
+        c.n_head    = jint(*m, {"parameter", "transformer", "Head"}, c.n_head);
+        c.n_head_kv = jint(*m, {"parameter", "transformer", "KVHead"}, c.n_head_kv ? c.n_head_kv : c.n_head);
+        c.head_dim  = jint(*m, {"parameter", "transformer", "head_dim"}, c.head_dim);
+        c.vocab     = jint(*m, {"parameter", "vocab_size"}, c.vocab);
+        c.max_pos_embeddings = jint(*m, {"parameter", "max_pos_embeddings"}, c.max_pos_embeddings);
+        if (const JSON* t = m->path({"parameter", "tie_word_embeddings"})) c.tie_word_embeddings = t->as_bool(false);
+        if (const JSON* t = m->path({"parameter", "rope_theta"})) c.rope_theta = (float)t->as_double(c.rope_theta);
+    }
+    if (const JSON* q = j0.find("quantizer")) c.jQuant = *q;  // "# quantizer" (commented out) is simply another key
+    c.seed        = jint(j0, {"seed"}, c.seed);
+    c.max_seq_len = jint(j0, {"gpt", "max_seq_len"}, c.max_seq_len);
+    c.max_batch   = jint(j0, {"gpt", "max_batch"}, c.max_batch);
+    if (const JSON* s = j0.path({"init", "sigma"})) c.init_sigma = (float)s->as_double(c.init_sigma);
+    if (const JSON* s = j0.path({"init", "norm_sigma"})) c.norm_sigma = (float)s->as_double(c.norm_sigma);
+    std::string a = c.arch;
+    std::transform(a.begin(), a.end(), a.begin(), ::toupper);
+    if (a != "QWEN3") throw std::runtime_error("model.arch '" + c.arch + "' is outside the hot path (only QWEN3 is built)");
+    if (c.n_layers <= 0 || c.n_embd <= 0 || c.n_ff <= 0 || c.n_head <= 0 || c.n_head_kv <= 0 || c.head_dim <= 0 || c.vocab <= 0)
+        throw std::runtime_error("model config incomplete: need Layer/Embed/Ffn/Head/KVHead/head_dim");
+    if (c.n_head % c.n_head_kv) throw std::runtime_error("Head must be a multiple of KVHead");
+    if (c.head_dim != 64 && c.head_dim != 128) throw std::runtime_error("head_dim must be 64 or 128");
+    if (c.max_seq_len <= 0 || c.max_batch <= 0) throw std::runtime_error("gpt.max_seq_len / gpt.max_batch must be positive");
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------------------ neurons
+void* KVCache::Get(CTYPE t, int layer, int pos, int seq) const {
+    uint16_t* base = (uint16_t*)(t == KV_KEY ? key : value);
+    return base + (((size_t)layer * max_batch + seq) * max_seq + pos) * kv_dim;
+}
+int SLP::Forw(void* rhs, const void* lhs, int M, int epilogue, const void* residual) {
+    kf_tensor_desc d = w->Desc();
+    return kf_linear(hFish->ctx, rhs, &d, lhs, M, epilogue, residual);
+}
+int LayerNormal::cuFlow(void* out, const void* inp, int rows) { return kf_rmsnorm(hFish->ctx, out, inp, w->data, rows, w->ne[1], rms_eps); }
+
+int ROPE::cuInfer(SelfAttention* a, int M) {
+    Fish* f        = hFish;
+    const int lay  = a->layid - 1;
+    const size_t ss = f->seq_mode ? f->cache.seq_stride() : 0;
+    return kf_qknorm_rope_kvappend(f->ctx, f->q, f->k, f->v, q_norm ? q_norm->data : nullptr, k_norm ? k_norm->data : nullptr,
+                                   f->cache.Get(KVCache::KV_KEY, lay), f->cache.Get(KVCache::KV_VAL, lay), table, f->d_pos, M, a->n_head,
+                                   a->n_head_kv, a->head_dim, f->cache.max_seq, 1e-6f, ss);
+}
+
+// SelfAttention::cuInfer, reference src/Device/CUDA/QKV.cu:617-706:
+//   norm -> Q/K/V.Forw -> rope->cuInfer (QK-norm, rope, K/V into the cache) -> attention -> proj_cat.Forw -> residual add
+int SelfAttention::cuInfer(void* inpL, int M) {
+    Fish* f = hFish;
+    std::string* hFishErr = &f->error;
+    KF_TRY(norm.cuFlow(f->xb, inpL, M));
+    kf_tensor_desc w3[3] = {Q.w->Desc(), K.w->Desc(), V.w->Desc()};
+    void* y3[3]          = {f->q, f->k, f->v};
+    KF_TRY(kf_linear_multi(f->ctx, 3, y3, w3, f->xb, M));  // the three SLP::Forw calls share one launch
+    KF_TRY(rope.cuInfer(this, M));
+    const int lay   = layid - 1;
+    const size_t ss = f->seq_mode ? f->cache.seq_stride() : 0;
+    KF_TRY(kf_attn_decode(f->ctx, f->att, f->q, f->cache.Get(KVCache::KV_KEY, lay), f->cache.Get(KVCache::KV_VAL, lay), f->d_pos, M, n_head,
+                          n_head_kv, head_dim, f->cache.max_seq, f->attn_hint, ss));
+    const size_t nE = (size_t)M * f->config.n_embd;
+    if (f->tp_world == 1) {
+        KF_TRY(proj_cat.Forw(inpL, f->att, M, KF_EPI_RESIDUAL, inpL));  // out = residual + proj (CU_add3, QKV.cu:682-688)
+    } else {  // row-parallel: fp32 partial sums -> all-reduce over NVLink -> residual add
+        KF_TRY(proj_cat.Forw(f->part_f32, f->att, M, KF_EPI_F32, nullptr));
+        KF_TRY(kf_allreduce_f32(f->ctx, f->part_f32, nE));
+        KF_TRY(kf_residual_add_f32(f->ctx, inpL, inpL, f->part_f32, nE));
+    }
+    return KF_OK;
+}
+// FFN::cuInfer, reference src/Device/CUDA/NeuronFuse.cu:615-656: norm -> gate.Forw, up.Forw -> relu.Forw (SwiGLU) -> down.Forw -> add
+int FFN::cuInfer(void* inpL, int M) {
+    Fish* f = hFish;
+    std::string* hFishErr = &f->error;
+    KF_TRY(norm.cuFlow(f->xb, inpL, M));
+    kf_tensor_desc g = gate.w->Desc(), u = up.w->Desc();
+    KF_TRY(kf_linear_swiglu(f->ctx, f->hb, &g, &u, f->xb, M));
+    const size_t nE = (size_t)M * f->config.n_embd;
+    if (f->tp_world == 1) {
+        KF_TRY(down.Forw(inpL, f->hb, M, KF_EPI_RESIDUAL, inpL));
+    } else {
+        KF_TRY(down.Forw(f->part_f32, f->hb, M, KF_EPI_F32, nullptr));
+        KF_TRY(kf_allreduce_f32(f->ctx, f->part_f32, nE));
+        KF_TRY(kf_residual_add_f32(f->ctx, inpL, inpL, f->part_f32, nE));
+    }
+    return KF_OK;
+}
+int TokenEmbed::cuInfer(void* out, int M) {
+    kf_tensor_desc d = w->Desc();
+    return kf_embed(hFish->ctx, out, &d, hFish->d_tokens, M);
+}
+// Head4Token::cuInfer_1 (NeuronFuse.cu:842-862) preceded by the final LayerNormal.  Under tensor parallelism the vocabulary rows are
+// sharded and the logits all-gathered.
+int Head4Token::cuInfer_1(void* logits, const void* inp, int M) {
+    Fish* f = hFish;
+    std::string* hFishErr = &f->error;
+    KF_TRY(norm.cuFlow(f->xb, inp, M));
+    kf_tensor_desc d = proj.w->Desc();
+    const int W = f->tp_world;
+    if (W == 1) {
+        KF_TRY(kf_linear(f->ctx, logits, &d, f->xb, M, KF_EPI_NONE, nullptr));
+        return KF_OK;
+    }
+    const int vl = f->config.vocab / W;
+    const typNUMBER tp = proj.w->type;
+    const size_t row_bytes = (size_t)((double)d.cols * BitPE(tp) / 8);
+    d.data_dev = (const uint8_t*)d.data_dev + (size_t)f->tp_rank * vl * row_bytes;  // row-slice view of the (replicated) table
+    if (d.gama_dev) {
+        const int gpr      = d.cols / d.group;
+        const uint16_t* g0 = (const uint16_t*)d.gama_dev + d.rows + d.cols;
+        d.zero_dev = g0 + (size_t)f->tp_rank * vl * gpr;
+        d.step_dev = g0 + (size_t)d.rows * gpr + (size_t)f->tp_rank * vl * gpr;
+    }
+    d.rows = vl;
+    // local logits land in the tail of the buffer, then all ranks' pieces are gathered to the front: [W][M][vl]
+    uint16_t* local = (uint16_t*)logits + (size_t)f->max_tokens * f->config.vocab;
+    KF_TRY(kf_linear(f->ctx, local, &d, f->xb, M, KF_EPI_NONE, nullptr));
+    KF_TRY(kf_allgather(f->ctx, logits, local, (size_t)M * vl * 2));
+    if (M > 1) {  // [W][M][vl] -> [M][W*vl]
+        uint16_t* tmp = local;
+        KF_TRY(kf_d2d(f->ctx, tmp, logits, (size_t)M * f->config.vocab * 2));
+        for (int r = 0; r < W; r++)
+            for (int m = 0; m < M; m++)
+                KF_TRY(kf_d2d(f->ctx, (uint16_t*)logits + (size_t)m * f->config.vocab + (size_t)r * vl, tmp + ((size_t)r * M + m) * vl, (size_t)vl * 2));
+    }
+    return KF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------ model
+Fish::Fish(kf_ctx* c, const MODEL_CARD& card, int rank, int world) : ctx(c), config(card), tp_rank(rank), tp_world(world) {}
+Fish::~Fish() {
+    ResetGraphs();
+    tensors.clear();
+    void* bufs[] = {x, xb, q, k, v, att, hb, logits, part_f32, d_tokens, d_pos, d_next, cache.key, cache.value};
+    for (void* b : bufs)
+        if (b) kf_free(ctx, b);
+    if (rope_table_shared) kf_free(ctx, rope_table_shared);
+    if (h_stage) kf_host_free(h_stage);
+    if (h_logits) kf_host_free(h_logits);
+}
+void Fish::ResetGraphs() {
+    for (auto& g : graphs)
+        if (g.second) kf_graph_destroy(g.second);
+    graphs.clear();
+}
+int Fish::AllocTensor(const std::string& name, int rows, int cols, int id, hGTensor& out) {
+    out = std::make_shared<GTensor>(ctx, name, rows, cols);
+    // only 2-D weight matrices are quantised, norms never (isWMAT, GeQuant.cpp:155-156)
+    if (rows > 1) out->hQuant = GeQuant::MakeInstance(name, config.jQuant);
+    tensors[name]    = out;
+    tensor_ids[name] = id;
+    return KF_OK;
+}
+
+// Fish::MakeInstance -> QWen3 ctor -> Build (reference src/Manifold/Fish.cpp:13-95; SelfAttention::Build TGraph.cpp:94-165;
+// FFN::Build EmbedVAE.cpp:427-480; tensor names NN2NAME QWen.cpp:61-145)
+int Fish::Build() {
+    std::string* hFishErr = &error;
+    const MODEL_CARD& c = config;
+    const int W = tp_world;
+    if (W < 1 || tp_rank < 0 || tp_rank >= W) return KF_ERR_BAD_ARG;
+    if (c.n_head % W || c.n_head_kv % W || c.n_ff % W || c.vocab % (16 * W) || (c.n_ff / W) % 128 || ((c.n_head / W) * c.head_dim) % 128) {
+        error = "tensor-parallel degree must divide Head, KVHead, Ffn (in 128-wide groups) and vocab";
+        return KF_ERR_BAD_ARG;
+    }
+    const int E = c.n_embd, hd = c.head_dim, nh = c.n_head / W, nkv = c.n_head_kv / W, ff = c.n_ff / W;
+    const int QD = nh * hd, KD = nkv * hd;
+    embed.hFish = this, embed.name = "model.embed_tokens";
+    AllocTensor("model.embed_tokens.weight", c.vocab, E, 0, embed.w);
+    cls.hFish = this, cls.name = "lm_head";
+    cls.norm.hFish = this, cls.norm.rms_eps = c.norm_rms_eps;
+    AllocTensor("model.norm.weight", 1, E, 1, cls.norm.w);
+    cls.proj.hFish = this, cls.proj.nIn = E, cls.proj.nOut = c.vocab;
+    if (c.tie_word_embeddings)
+        cls.proj.w = embed.w;
+    else
+        AllocTensor("lm_head.weight", c.vocab, E, 2, cls.proj.w);
+    for (int l = 0; l < c.n_layers; l++) {
+        const std::string p = "model.layers." + std::to_string(l) + ".";
+        const int b         = 16 + 16 * l;
+        auto a = std::make_unique<SelfAttention>();
+        a->hFish = this, a->name = p + "self_attn", a->layid = l + 1;
+        a->n_head = nh, a->n_head_kv = nkv, a->head_dim = hd;
+        a->norm.hFish = this, a->norm.rms_eps = c.norm_rms_eps;
+        AllocTensor(p + "input_layernorm.weight", 1, E, b + 0, a->norm.w);
+        SLP* slps[4]      = {&a->Q, &a->K, &a->V, &a->proj_cat};
+        const char* nm[4] = {"self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight", "self_attn.o_proj.weight"};
+        const int rr[4] = {QD, KD, KD, E}, cc[4] = {E, E, E, QD}, ids[4] = {b + 1, b + 2, b + 3, b + 6};
+        for (int i = 0; i < 4; i++) {
+            slps[i]->hFish = this, slps[i]->nIn = cc[i], slps[i]->nOut = rr[i];
+            AllocTensor(p + nm[i], rr[i], cc[i], ids[i], slps[i]->w);
+        }
+        a->rope.hFish = this, a->rope.theta = c.rope_theta;
+        if (c.isQKNormal) {
+            AllocTensor(p + "self_attn.q_norm.weight", 1, hd, b + 4, a->rope.q_norm);
+            AllocTensor(p + "self_attn.k_norm.weight", 1, hd, b + 5, a->rope.k_norm);
+        }
+        attn.push_back(std::move(a));
+        auto m = std::make_unique<FFN>();
+        m->hFish = this, m->name = p + "mlp", m->layid = l + 1, m->latent = ff;
+        m->norm.hFish = this, m->norm.rms_eps = c.norm_rms_eps;
+        AllocTensor(p + "post_attention_layernorm.weight", 1, E, b + 7, m->norm.w);
+        SLP* fs[3]        = {&m->gate, &m->up, &m->down};
+        const char* fn[3] = {"mlp.gate_proj.weight", "mlp.up_proj.weight", "mlp.down_proj.weight"};
+        const int fr[3] = {ff, ff, E}, fc[3] = {E, E, ff}, fi[3] = {b + 8, b + 9, b + 10};
+        for (int i = 0; i < 3; i++) {
+            fs[i]->hFish = this, fs[i]->nIn = fc[i], fs[i]->nOut = fr[i];
+            AllocTensor(p + fn[i], fr[i], fc[i], fi[i], fs[i]->w);
+        }
+        ffn.push_back(std::move(m));
+    }
+    // KV cache (Fish::AllocBuffer, Fish.cpp:895-933) + activations
+    cache.n_layer = c.n_layers, cache.max_batch = c.max_batch, cache.max_seq = c.max_seq_len, cache.kv_dim = KD;
+    KF_TRY(kf_malloc(ctx, cache.bytes() / 2, &cache.key));
+    KF_TRY(kf_malloc(ctx, cache.bytes() / 2, &cache.value));
+    KF_TRY(kf_memset(ctx, cache.key, 0, cache.bytes() / 2));
+    KF_TRY(kf_memset(ctx, cache.value, 0, cache.bytes() / 2));
+    max_tokens = std::max(64, c.max_batch);
+    const size_t T = max_tokens;
+    KF_TRY(kf_malloc(ctx, T * E * 2, &x));
+    KF_TRY(kf_malloc(ctx, T * E * 2, &xb));
+    KF_TRY(kf_malloc(ctx, T * QD * 2, &q));
+    KF_TRY(kf_malloc(ctx, T * KD * 2, &k));
+    KF_TRY(kf_malloc(ctx, T * KD * 2, &v));
+    KF_TRY(kf_malloc(ctx, T * QD * 2, &att));
+    KF_TRY(kf_malloc(ctx, T * ff * 2, &hb));
+    KF_TRY(kf_malloc(ctx, T * c.vocab * 2 * (W > 1 ? 2 : 1), &logits));
+    if (W > 1) KF_TRY(kf_malloc(ctx, T * E * 4, (void**)&part_f32));
+    KF_TRY(kf_malloc(ctx, T * 4, (void**)&d_tokens));
+    KF_TRY(kf_malloc(ctx, T * 4, (void**)&d_pos));
+    KF_TRY(kf_malloc(ctx, T * 4, (void**)&d_next));
+    KF_TRY(kf_host_alloc(T * 4 * 3, (void**)&h_stage));
+    KF_TRY(kf_host_alloc(T * c.vocab * 2, (void**)&h_logits));
+    // one rope table shared by all layers
+    void* table = nullptr;
+    KF_TRY(kf_malloc(ctx, (size_t)c.max_seq_len * (hd / 2) * 8, &table));
+    KF_TRY(kf_rope_table(ctx, table, c.max_seq_len, hd, c.rope_theta));
+    for (auto& a : attn) a->rope.table = table;
+    rope_table_shared = table;
+    attn_hint = c.max_seq_len - 1;
+    return KF_OK;
+}
+
+// which window of the full (unsharded) tensor does this rank hold?
+static void shard_window(const Fish& f, const std::string& name, int rows_l, int cols_l, int* rows_g, int* cols_g, int* row0, int* col0) {
+    const int W = f.tp_world, r = f.tp_rank;
+    *rows_g = rows_l, *cols_g = cols_l, *row0 = 0, *col0 = 0;
+    auto has = [&](const char* s) { return name.find(s) != std::string::npos; };
+    if (has("q_proj") || has("k_proj") || has("v_proj") || has("gate_proj") || has("up_proj"))
+        *rows_g = rows_l * W, *row0 = r * rows_l;  // column-parallel: split output rows
+    else if (has("o_proj") || has("down_proj"))
+        *cols_g = cols_l * W, *col0 = r * cols_l;  // row-parallel: split input columns (whole 128-wide groups)
+}
+
+// huTensor::InitParam random path (reference src/Device/CUDA/huTensor.cu:157-231) + LowBit_worker at load
+int Fish::InitParamRandom() {
+    std::string* hFishErr = &error;
+    size_t most = 0;
+    for (auto& kv : tensors) most = std::max(most, kv.second->size());
+    void* scratch = nullptr;
+    KF_TRY(kf_malloc(ctx, most * 2, &scratch));
+    weight_bytes = 0;
+    for (auto& kv : tensors) {
+        hGTensor t      = kv.second;
+        const int id    = tensor_ids[kv.first];
+        const uint64_t seed = (uint64_t)config.seed * 1000003ull + (uint64_t)id;
+        int rg, cg, r0, c0;
+        shard_window(*this, kv.first, t->ne[0], t->ne[1], &rg, &cg, &r0, &c0);
+        int rc;
+        if (t->ne[0] == 1) {  // norm weights: FIX_1 (or 1 + norm_sigma*z for tests)
+            rc = kf_fill_normal(ctx, scratch, t->size(), seed, config.norm_sigma, 1.0f);
+            if (!rc) rc = t->SetBF16FromDevice(scratch);
+        } else {
+            rc = kf_fill_normal_2d(ctx, scratch, t->ne[0], t->ne[1], (size_t)cg, (size_t)r0, (size_t)c0, seed, config.init_sigma, 0.f);
+            if (!rc) rc = t->hQuant ? t->hQuant->LowBit_worker(t, scratch, 0x100) : t->SetBF16FromDevice(scratch);
+        }
+        if (rc) {
+            error = "InitParam(" + kv.first + ") -> " + kf_status_string(rc) + " : " + kf_last_error(ctx);
+            kf_free(ctx, scratch);
+            return rc;
+        }
+        weight_bytes += t->nByte();
+    }
+    KF_TRY(kf_ctx_sync(ctx));
+    KF_TRY(kf_free(ctx, scratch));
+    ResetGraphs();
+    return KF_OK;
+}
+int Fish::SetTensor(const std::string& name, const void* host, int rows, int cols) {
+    std::string* hFishErr = &error;
+    auto it = tensors.find(name);
+    if (it == tensors.end()) {
+        error = "unknown tensor '" + name + "'";
+        return KF_ERR_BAD_ARG;
+    }
+    hGTensor t = it->second;
+    int rg, cg, r0, c0;
+    shard_window(*this, name, t->ne[0], t->ne[1], &rg, &cg, &r0, &c0);
+    if ((rows != rg || cols != cg) && !(t->ne[0] == 1 && (size_t)rows * cols == t->size())) {
+        error = "tensor '" + name + "': expected full shape [" + std::to_string(rg) + "," + std::to_string(cg) + "]";
+        return KF_ERR_BAD_ARG;
+    }
+    std::vector<uint16_t> shard(t->size());
+    const uint16_t* src = (const uint16_t*)host;
+    for (int r = 0; r < t->ne[0]; r++) memcpy(&shard[(size_t)r * t->ne[1]], src + (size_t)(r0 + r) * cg + c0, (size_t)t->ne[1] * 2);
+    void* dev = nullptr;
+    KF_TRY(kf_malloc(ctx, shard.size() * 2, &dev));
+    KF_TRY(kf_h2d(ctx, dev, shard.data(), shard.size() * 2));
+    int rc = (t->hQuant && t->ne[0] > 1) ? t->hQuant->LowBit_worker(t, dev, 0x100) : t->SetBF16FromDevice(dev);
+    kf_ctx_sync(ctx);
+    kf_free(ctx, dev);
+    ResetGraphs();
+    if (rc) error = "SetTensor(" + name + ") -> " + kf_status_string(rc) + " : " + kf_last_error(ctx);
+    return rc;
+}
+hGTensor Fish::GetTensor(const std::string& name) const {
+    auto it = tensors.find(name);
+    return it == tensors.end() ? nullptr : it->second;
+}
+
+// Fish::ForwardOnRLS (reference src/Manifold/gLLM.cpp:755-769): run every neuron's cuInfer in graph order
+int Fish::ForwardOnRLS(int M, bool want_logits) {
+    std::string* hFishErr = &error;
+    KF_TRY(embed.cuInfer(x, M));
+    for (size_t l = 0; l < attn.size(); l++) {
+        KF_TRY(attn[l]->cuInfer(x, M));
+        KF_TRY(ffn[l]->cuInfer(x, M));
+    }
+    if (want_logits) KF_TRY(cls.cuInfer_1(logits, x, M));
+    return KF_OK;
+}
+
+// graph key: M | want_logits<<8 | seq_mode<<9 | feedback<<10
+int Fish::UseGraph(int M, bool want_logits) { return (M & 0xff) | ((int)want_logits << 8) | (seq_mode << 9); }
+
+int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, uint16_t* logits_out, int32_t* next_out) {
+    std::string* hFishErr = &error;
+    if (!tokens || !pos || M < 1 || M > max_tokens) {
+        error = "Forward: 1 <= M <= " + std::to_string(max_tokens);
+        return KF_ERR_BAD_ARG;
+    }
+    if (mode && M > config.max_batch) {
+        error = "Forward: batched decode needs gpt.max_batch >= M";
+        return KF_ERR_BAD_ARG;
+    }
+    for (int m = 0; m < M; m++) {
+        if (tokens[m] < 0 || tokens[m] >= config.vocab || pos[m] < 0 || pos[m] >= config.max_seq_len) {
+            error = "Forward: token id or position out of range";
+            return KF_ERR_BAD_ARG;
+        }
+        h_stage[m] = tokens[m], h_stage[max_tokens + m] = pos[m];
+    }
+    staged_pos_max = *std::max_element(pos, pos + M);
+    seq_mode = mode ? 1 : 0;
+    KF_TRY(kf_h2d(ctx, d_tokens, h_stage, (size_t)M * 4));
+    KF_TRY(kf_h2d(ctx, d_pos, h_stage + max_tokens, (size_t)M * 4));
+    const bool want_logits = logits_out || next_out;
+    const int key          = UseGraph(M, want_logits) | ((next_out ? 1 : 0) << 11);
+    auto it                = graphs.find(key);
+    if (use_graphs && it == graphs.end() && warm.count(key)) {  // second call with this signature: capture it
+        KF_TRY(kf_graph_begin(ctx));
+        int rc = ForwardOnRLS(M, want_logits);
+        if (!rc && next_out) rc = kf_argmax(ctx, d_next, logits, M, config.vocab);
+        kf_graph* g = nullptr;
+        int rc2     = kf_graph_end(ctx, &g);
+        if (rc || rc2) {
+            error = std::string("graph capture failed: ") + kf_last_error(ctx);
+            return rc ? rc : rc2;
+        }
+        graphs[key] = g;
+        it          = graphs.find(key);
+    }
+    if (use_graphs && it != graphs.end()) {
+        KF_TRY(kf_graph_launch(ctx, it->second));
+    } else {
+        KF_TRY(ForwardOnRLS(M, want_logits));
+        if (next_out) KF_TRY(kf_argmax(ctx, d_next, logits, M, config.vocab));
+        warm.insert(key);
+    }
+    if (logits_out) KF_TRY(kf_d2h(ctx, h_logits, logits, (size_t)M * config.vocab * 2));
+    if (next_out) KF_TRY(kf_d2h(ctx, h_stage + 2 * max_tokens, d_next, (size_t)M * 4));
+    KF_TRY(kf_ctx_sync(ctx));
+    if (logits_out) memcpy(logits_out, h_logits, (size_t)M * config.vocab * 2);
+    if (next_out) memcpy(next_out, h_stage + 2 * max_tokens, (size_t)M * 4);
+    return KF_OK;
+}
+
+// Device-resident greedy decoding: each step = one CUDA-graph replay of [forward, argmax, token feedback, pos++].  The tokens and
+// positions staged by the last Forward() call are the starting state.
+int Fish::DecodeLoop(int n_steps, int M) {
+    std::string* hFishErr = &error;
+    if (M < 1 || M > max_tokens || n_steps < 0) return KF_ERR_BAD_ARG;
+    if (staged_pos_max + n_steps >= config.max_seq_len) {
+        error = "DecodeLoop: would run past gpt.max_seq_len";
+        return KF_ERR_BAD_ARG;
+    }
+    staged_pos_max += n_steps;
+    const int key = UseGraph(M, true) | (1 << 10);
+    auto it       = graphs.find(key);
+    auto body     = [&]() -> int {
+        int rc = ForwardOnRLS(M, true);
+        if (!rc) rc = kf_argmax(ctx, d_next, logits, M, config.vocab);
+        if (!rc) rc = kf_d2d(ctx, d_tokens, d_next, (size_t)M * 4);
+        if (!rc) rc = kf_advance_pos(ctx, d_pos, M);
+        return rc;
+    };
+    int done = 0;
+    if (it == graphs.end()) {
+        if (n_steps == 0) return KF_OK;
+        KF_TRY(body());  // eager first step sizes every workspace
+        done = 1;
+        if (use_graphs) {
+            KF_TRY(kf_graph_begin(ctx));
+            int rc      = body();
+            kf_graph* g = nullptr;
+            int rc2     = kf_graph_end(ctx, &g);
+            if (rc || rc2) {
+                error = std::string("graph capture failed: ") + kf_last_error(ctx);
+                return rc ? rc : rc2;
+            }
+            graphs[key] = g;
+            it          = graphs.find(key);
+        }
+    }
+    for (; done < n_steps; done++) {
+        if (use_graphs && it != graphs.end())
+            KF_TRY(kf_graph_launch(ctx, it->second));
+        else
+            KF_TRY(body());
+    }
+    return KF_OK;
+}
+
+}  // namespace koifish

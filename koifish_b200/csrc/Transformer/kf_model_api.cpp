@@ -1,0 +1,172 @@
+// kf_model_api.cpp -- extern "C" surface of the host runtime (include/kf_model.h).  Exceptions never cross the boundary.
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+#include "QWen3.hpp"
+#include "kf_model.h"
+
+using namespace koifish;
+
+struct kf_model {
+    std::unique_ptr<Fish> fish;
+    std::vector<std::string> names;
+};
+
+static char* dup_cstr(const std::string& s) {
+    char* p = (char*)malloc(s.size() + 1);
+    if (p) memcpy(p, s.c_str(), s.size() + 1);
+    return p;
+}
+
+extern "C" int kf_model_create(kf_ctx* ctx, const char* config_json, int tp_rank, int tp_world, kf_model** out, char** err_out) {
+    if (err_out) *err_out = nullptr;
+    if (!ctx || !config_json || !out) return KF_ERR_BAD_ARG;
+    *out = nullptr;
+    try {
+        JSON j          = JSON::parse(config_json);
+        MODEL_CARD card = MODEL_CARD::FromJSON(j);
+        auto m          = std::make_unique<kf_model>();
+        m->fish         = std::make_unique<Fish>(ctx, card, tp_rank, tp_world);
+        int rc          = m->fish->Build();
+        if (rc) {
+            if (err_out) *err_out = dup_cstr(m->fish->error + " : " + kf_last_error(ctx));
+            return rc;
+        }
+        for (auto& kv : m->fish->tensors) m->names.push_back(kv.first);
+        *out = m.release();
+        return KF_OK;
+    } catch (const std::exception& e) {
+        if (err_out) *err_out = dup_cstr(e.what());
+        return KF_ERR_BAD_ARG;
+    }
+}
+extern "C" int kf_model_destroy(kf_model* m) {
+    if (!m) return KF_ERR_BAD_ARG;
+    delete m;
+    return KF_OK;
+}
+extern "C" const char* kf_model_error(kf_model* m) { return m ? m->fish->error.c_str() : ""; }
+extern "C" void kf_string_free(char* s) { free(s); }
+
+extern "C" int kf_model_info_get(kf_model* m, kf_model_info* o) {
+    if (!m || !o) return KF_ERR_BAD_ARG;
+    Fish& f             = *m->fish;
+    const MODEL_CARD& c = f.config;
+    memset(o, 0, sizeof(*o));
+    o->n_layers = c.n_layers, o->n_embd = c.n_embd, o->n_ff = c.n_ff, o->n_head = c.n_head, o->n_head_kv = c.n_head_kv;
+    o->head_dim = c.head_dim, o->vocab = c.vocab, o->max_seq_len = c.max_seq_len, o->max_batch = c.max_batch, o->max_tokens = f.max_tokens;
+    o->tp_rank = f.tp_rank, o->tp_world = f.tp_world, o->tie_word_embeddings = c.tie_word_embeddings;
+    o->rope_theta = c.rope_theta, o->norm_rms_eps = c.norm_rms_eps;
+    o->weight_bytes = f.weight_bytes, o->kv_bytes = f.cache.bytes();
+    if (!f.attn.empty()) {
+        auto nb = [](const hGTensor& t) { return t ? (uint64_t)t->nByte() : 0ull; };
+        SelfAttention& a = *f.attn[0];
+        FFN& n           = *f.ffn[0];
+        o->block_weight_bytes_per_layer = nb(a.norm.w) + nb(a.Q.w) + nb(a.K.w) + nb(a.V.w) + nb(a.proj_cat.w) + nb(a.rope.q_norm) + nb(a.rope.k_norm) +
+                                          nb(n.norm.w) + nb(n.gate.w) + nb(n.up.w) + nb(n.down.w);
+    }
+    if (f.cls.proj.w) o->head_weight_bytes = (uint64_t)f.cls.proj.w->nByte() / (uint64_t)f.tp_world;
+    return KF_OK;
+}
+extern "C" int kf_model_init_random(kf_model* m) {
+    if (!m) return KF_ERR_BAD_ARG;
+    try {
+        return m->fish->InitParamRandom();
+    } catch (const std::exception& e) {
+        m->fish->error = e.what();
+        return KF_ERR_BAD_ARG;
+    }
+}
+extern "C" int kf_model_set_tensor(kf_model* m, const char* name, const void* host, int rows, int cols) {
+    if (!m || !name || !host) return KF_ERR_BAD_ARG;
+    try {
+        return m->fish->SetTensor(name, host, rows, cols);
+    } catch (const std::exception& e) {
+        m->fish->error = e.what();
+        return KF_ERR_BAD_ARG;
+    }
+}
+extern "C" int kf_model_tensor_desc(kf_model* m, const char* name, kf_tensor_desc* out) {
+    if (!m || !name || !out) return KF_ERR_BAD_ARG;
+    hGTensor t = m->fish->GetTensor(name);
+    if (!t || !t->data) return KF_ERR_BAD_ARG;
+    *out = t->Desc();
+    return KF_OK;
+}
+extern "C" int kf_model_tensor_count(kf_model* m) { return m ? (int)m->names.size() : 0; }
+extern "C" const char* kf_model_tensor_name(kf_model* m, int i) { return (m && i >= 0 && i < (int)m->names.size()) ? m->names[i].c_str() : nullptr; }
+extern "C" void* kf_model_kcache(kf_model* m, int layer) {
+    return (m && layer >= 0 && layer < m->fish->cache.n_layer) ? m->fish->cache.Get(KVCache::KV_KEY, layer) : nullptr;
+}
+extern "C" void* kf_model_vcache(kf_model* m, int layer) {
+    return (m && layer >= 0 && layer < m->fish->cache.n_layer) ? m->fish->cache.Get(KVCache::KV_VAL, layer) : nullptr;
+}
+extern "C" int kf_model_forward(kf_model* m, const int32_t* tokens, const int32_t* pos, int M, int seq_mode, void* logits, int32_t* next) {
+    if (!m) return KF_ERR_BAD_ARG;
+    try {
+        return m->fish->Forward(tokens, pos, M, seq_mode, (uint16_t*)logits, next);
+    } catch (const std::exception& e) {
+        m->fish->error = e.what();
+        return KF_ERR_BAD_ARG;
+    }
+}
+extern "C" int kf_model_decode_loop(kf_model* m, int n_steps, int M) {
+    if (!m) return KF_ERR_BAD_ARG;
+    try {
+        return m->fish->DecodeLoop(n_steps, M);
+    } catch (const std::exception& e) {
+        m->fish->error = e.what();
+        return KF_ERR_BAD_ARG;
+    }
+}
+extern "C" int kf_model_read_state(kf_model* m, int32_t* tokens, int32_t* pos, int M) {
+    if (!m || M < 1 || M > m->fish->max_tokens) return KF_ERR_BAD_ARG;
+    Fish& f = *m->fish;
+    int rc  = KF_OK;
+    if (tokens) rc = kf_d2h(f.ctx, f.h_stage, f.d_tokens, (size_t)M * 4);
+    if (!rc && pos) rc = kf_d2h(f.ctx, f.h_stage + f.max_tokens, f.d_pos, (size_t)M * 4);
+    if (!rc) rc = kf_ctx_sync(f.ctx);
+    if (rc) return rc;
+    if (tokens) memcpy(tokens, f.h_stage, (size_t)M * 4);
+    if (pos) memcpy(pos, f.h_stage + f.max_tokens, (size_t)M * 4);
+    return KF_OK;
+}
+extern "C" int kf_config_dims(const char* config_json, kf_model_info* o, char** err_out) {
+    if (err_out) *err_out = nullptr;
+    if (!config_json || !o) return KF_ERR_BAD_ARG;
+    try {
+        MODEL_CARD c = MODEL_CARD::FromJSON(JSON::parse(config_json));
+        memset(o, 0, sizeof(*o));
+        o->n_layers = c.n_layers, o->n_embd = c.n_embd, o->n_ff = c.n_ff, o->n_head = c.n_head, o->n_head_kv = c.n_head_kv;
+        o->head_dim = c.head_dim, o->vocab = c.vocab, o->max_seq_len = c.max_seq_len, o->max_batch = c.max_batch;
+        o->tp_world = 1, o->tie_word_embeddings = c.tie_word_embeddings, o->rope_theta = c.rope_theta, o->norm_rms_eps = c.norm_rms_eps;
+        return KF_OK;
+    } catch (const std::exception& e) {
+        if (err_out) *err_out = dup_cstr(e.what());
+        return KF_ERR_BAD_ARG;
+    }
+}
+extern "C" int kf_config_quant_of(const char* config_json, const char* tensor_name, int* type_out, int* group_out, int* mode_out,
+                                  int* qbias_out, char** err_out) {
+    if (err_out) *err_out = nullptr;
+    if (!config_json || !tensor_name) return KF_ERR_BAD_ARG;
+    try {
+        MODEL_CARD c = MODEL_CARD::FromJSON(JSON::parse(config_json));
+        hQUANT q     = GeQuant::MakeInstance(tensor_name, c.jQuant);
+        if (type_out) *type_out = q ? kfType(q->params.tpQuant()) : KF_T_BF16;
+        if (group_out) *group_out = q ? q->params.T_group : 0;
+        if (mode_out) *mode_out = q ? q->params.kfMode() : 0;
+        if (qbias_out) *qbias_out = q ? q->qBias : 0;
+        return KF_OK;
+    } catch (const std::exception& e) {
+        if (err_out) *err_out = dup_cstr(e.what());
+        return KF_ERR_UNSUPPORTED;
+    }
+}
+extern "C" int kf_model_set_graphs(kf_model* m, int enable) {
+    if (!m) return KF_ERR_BAD_ARG;
+    m->fish->use_graphs = enable != 0;
+    if (!enable) m->fish->ResetGraphs();
+    return KF_OK;
+}

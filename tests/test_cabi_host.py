@@ -1,0 +1,145 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/*.h declares; host-side config / quant-card logic;
+the product fails loudly without a device (no CPU fallback)."""
+import ctypes as C
+import json
+import os
+import re
+
+import pytest
+
+import koifish_b200 as kf
+from koifish_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for h in ("kf_device.h", "kf_model.h"):
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(kf_[a-z0-9_]+)\s*\(", text))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = kf.load()
+    declared = _declared_symbols()
+    assert len(declared) > 50
+    for name in sorted(declared):
+        assert hasattr(lib, name), "missing export: " + name
+    # and the Python binding covers exactly the declared surface
+    assert set(L.SIGNATURES) == declared
+
+
+def test_headers_compile_as_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "kf_device.h"\n#include "kf_model.h"\nint main(void){ kf_tensor_desc d; (void)d; return KF_OK; }\n')
+    import subprocess
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_status_strings_and_no_cpu_fallback():
+    lib = kf.load()
+    assert lib.kf_status_string(0) == b"KF_OK"
+    assert b"no CPU fallback" in lib.kf_status_string(kf.KF_ERR_NO_DEVICE)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(kf.KoifishError) as e:
+            kf.Context(0)
+        assert e.value.status == kf.KF_ERR_NO_DEVICE
+
+
+def _quant_of(cfg, name):
+    lib = kf.load()
+    t, g, m, qb, err = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_void_p()
+    st = lib.kf_config_quant_of(json.dumps(cfg).encode(), name.encode(), C.byref(t), C.byref(g), C.byref(m), C.byref(qb), C.byref(err))
+    msg = C.cast(err, C.c_char_p).value.decode() if err.value else ""
+    if err.value:
+        lib.kf_string_free(err)
+    return st, t.value, g.value, m.value, qb.value, msg
+
+
+REF_Q4_QUANTIZER = {  # the quantizer block of the reference's cases/qwen3/qwen3_596M_q4.json
+    "#MIQ": ["self_attn"], "train_target": "gama", "group_size": 128,
+    "self_attn": {"quant_method": "RTN", "bits": 4}, "mlp": {"quant_method": "RTN", "bits": 4},
+    "# embed_tokens": {"bits": 4}, "#MINI": "off"}
+
+
+def test_quant_card_selection_matches_reference_rules():
+    cfg = kf.qwen3_config(6, 1024, 3072, 16, 8, quantizer=REF_Q4_QUANTIZER, tie=True)
+    st, t, g, m, qb, _ = _quant_of(cfg, "model.layers.3.self_attn.q_proj.weight")
+    assert (st, t, g, m, qb) == (0, kf.KF_T_Q4, 128, kf.KF_Q_RTN_ASYM, 0)
+    st, t, g, m, qb, _ = _quant_of(cfg, "model.layers.0.mlp.down_proj.weight")
+    assert (st, t, g) == (0, kf.KF_T_Q4, 128)
+    # '#'-prefixed keys are comments: embed_tokens stays bf16
+    st, t, *_ = _quant_of(cfg, "model.embed_tokens.weight")
+    assert (st, t) == (0, kf.KF_T_BF16)
+    # hybrid 8/4-bit, ternary and binary cards
+    cfg = kf.qwen3_config(2, 1024, 3072, 16, 8, quantizer={"self_attn": {"bits": 8}, "mlp": {"quant_method": "RTN", "bits": 4, "group_size": 256}})
+    assert _quant_of(cfg, "model.layers.1.self_attn.k_proj.weight")[1] == kf.KF_T_F8E5M2
+    assert _quant_of(cfg, "model.layers.1.mlp.up_proj.weight")[1:3] == (kf.KF_T_Q4, 256)
+    cfg = kf.qwen3_config(2, 1024, 3072, 16, 8, quantizer={"self_attn": {"quant_method": "yyang", "bits": 2}, "mlp": {"quant_method": "yyang", "bits": 1}})
+    st, t, g, m, qb, _ = _quant_of(cfg, "model.layers.1.self_attn.q_proj.weight")
+    assert (t, m, qb) == (kf.KF_T_SIGN, kf.KF_Q_YYANG, 1)
+    st, t, g, m, qb, _ = _quant_of(cfg, "model.layers.1.mlp.gate_proj.weight")
+    assert (t, m, qb) == (kf.KF_T_BINARY, kf.KF_Q_YYANG, 0)
+
+
+def test_out_of_scope_quant_methods_fail_loudly():
+    for q in ({"self_attn": {"bits": 4}},                       # no method -> NF4 (RTNf): a 'next' row
+              {"self_attn": {"quant_method": "awq", "bits": 4}},  # vendor AWQ: a 'next' row
+              {"self_attn": {"quant_method": "bitnet"}},
+              {"self_attn": {"quant_method": "RTN", "bits": 1}}):
+        cfg = kf.qwen3_config(2, 1024, 3072, 16, 8, quantizer=q)
+        st, *_, msg = _quant_of(cfg, "model.layers.0.self_attn.q_proj.weight")
+        assert st == kf.KF_ERR_UNSUPPORTED and msg
+
+
+def _dims(text):
+    lib = kf.load()
+    info, err = kf.ModelInfo(), C.c_void_p()
+    st = lib.kf_config_dims(text.encode(), C.byref(info), C.byref(err))
+    msg = C.cast(err, C.c_char_p).value.decode() if err.value else ""
+    if err.value:
+        lib.kf_string_free(err)
+    return st, info, msg
+
+
+def test_config_parsing_koifish_and_hf():
+    # the reference's own layout (cases/qwen3/qwen3_596M_q4.json), including '#'-comment keys and nested junk
+    ref_like = {
+        "version": "0.1.0", "quantizer": REF_Q4_QUANTIZER,
+        "model": {"#hf-card": "/x/", "arch": "QWEN3", "parameter": {
+            "Layer": 6, "transformer": {"Ctx": 1024, "Embed": 1024, "Ffn": 3072, "Head": 16, "KVHead": 8, "head_dim": 128},
+            "tie_word_embeddings": True, "max_pos_embeddings": 32768},
+            "backbone": {"embed_tokens": {"Embedding": []}, "layer": {"self_attn": {"QKV": []}, "mlp": {"FFN": []}}}},
+        "train": {"batch": 16, "learning-rate": 0.0006}, "debug": {"prompts": ["hello", "天命"], "fake_quant": -1}, "seed": 42}
+    st, info, msg = _dims(json.dumps(ref_like))
+    assert st == 0, msg
+    assert (info.n_layers, info.n_embd, info.n_ff, info.n_head, info.n_head_kv, info.head_dim) == (6, 1024, 3072, 16, 8, 128)
+    assert info.vocab == 151936 and info.tie_word_embeddings == 1 and info.max_seq_len == 1024
+    assert abs(info.rope_theta - 10000.0) < 1e-3 and abs(info.norm_rms_eps - 1e-6) < 1e-12
+    hf = {"architectures": ["Qwen3ForCausalLM"], "hidden_size": 5120, "intermediate_size": 25600, "num_hidden_layers": 64,
+          "num_attention_heads": 64, "num_key_value_heads": 8, "head_dim": 128, "vocab_size": 151936, "rope_theta": 1000000,
+          "rms_norm_eps": 1e-06, "tie_word_embeddings": False, "max_position_embeddings": 40960, "model_type": "qwen3"}
+    st, info, msg = _dims(json.dumps(hf))
+    assert st == 0, msg
+    assert (info.n_layers, info.n_embd, info.n_ff, info.n_head, info.n_head_kv) == (64, 5120, 25600, 64, 8)
+    assert info.rope_theta == 1e6 and info.tie_word_embeddings == 0
+
+
+@pytest.mark.parametrize("bad", ['{"model":', '{"model": {"arch": "GPT2", "parameter": {"Layer": 2}}}',
+                                 '{"model": {"arch": "QWEN3", "parameter": {"Layer": 2}}}', "[]", ""])
+def test_bad_configs_return_errors_not_exits(bad):
+    st, _, msg = _dims(bad)
+    assert st == kf.KF_ERR_BAD_ARG and msg
+
+
+def test_integration_doc_names_real_symbols():
+    p = os.path.join(ROOT, "INTEGRATION.md")
+    if not os.path.exists(p):
+        pytest.skip("INTEGRATION.md not written yet")
+    used = set(re.findall(r"\b(kf_[a-z0-9_]+)\s*\(", open(p).read()))
+    assert used and used <= _declared_symbols(), used - _declared_symbols()

@@ -1,0 +1,373 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every kernel behind the C ABI against the CPU oracle on the same seeded
+inputs.  Integer / byte / bf16-dequant work is bit-exact; dot products are compared within a tolerance written in each test."""
+import os
+
+import numpy as np
+import pytest
+
+import koifish_b200 as kf
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "packq_ref.npz"))
+
+KF_TYPE = {(4, ol.RTN_ASYM): kf.KF_T_Q4, (4, ol.RTN_SYM): kf.KF_T_Q4, (2, ol.RTN_ASYM): kf.KF_T_Q2, (2, ol.RTN_SYM): kf.KF_T_Q2,
+           (2, ol.YYANG): kf.KF_T_SIGN, (1, ol.YYANG): kf.KF_T_BINARY}
+ALL_QUANT = [(4, ol.RTN_ASYM), (4, ol.RTN_SYM), (2, ol.RTN_ASYM), (2, ol.YYANG), (1, ol.YYANG)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = kf.Context(0)
+    yield c
+    c.close()
+
+
+def oracle_qtensor(ctx, rows, cols, bits, mode, seed, group=128, sigma=0.02):
+    """weights quantised by the ORACLE packer, uploaded as-is: the kernels must read the reference's byte layout"""
+    w = ol.fill_normal(rows * cols, seed, sigma)
+    data, gama = ol.quantize(w, rows, cols, bits, group, mode)
+    _, _, qbias = ol.qrange(bits, mode)
+    t = kf.QTensor.from_packed(ctx, data, gama, rows, cols, KF_TYPE[(bits, mode)], group, qbias)
+    wdq = ol.dequant(data, gama, rows, cols, bits, group, qbias)
+    return t, wdq
+
+
+def make_weight(ctx, kind, rows, cols, seed):
+    """returns (QTensor on device, dequantised bf16 weights [rows, cols] from the oracle)"""
+    if kind == "bf16":
+        w = ol.fill_normal(rows * cols, seed, 0.02)
+        return kf.QTensor.from_packed(ctx, w.view(np.uint8), None, rows, cols, kf.KF_T_BF16), w.reshape(rows, cols)
+    if kind == "f8":
+        w = ol.fill_normal(rows * cols, seed, 0.02)
+        b = ol.f8_encode(w)
+        return kf.QTensor.from_packed(ctx, b, None, rows, cols, kf.KF_T_F8E5M2), ol.f8_decode(b).reshape(rows, cols)
+    bits, mode = kind
+    return oracle_qtensor(ctx, rows, cols, bits, mode, seed)
+
+
+WEIGHT_KINDS = ["bf16", "f8"] + ALL_QUANT
+
+
+def rand_bf16(rng, shape, scale=1.0):
+    return ol.f32_to_bf16((rng.standard_normal(shape) * scale).astype(np.float32))
+
+
+# ---------------------------------------------------------------------------------------------- generator / packer / dequant
+def test_fill_normal_bit_exact(ctx):
+    n = 1 << 18
+    for seed, sigma, mean in ((42, 0.02, 0.0), (7, 0.1, 1.0), (123456789, 1.0, -0.5)):
+        g = kf.fill_normal(ctx, n, seed, sigma, mean).numpy(np.uint16)
+        assert np.array_equal(g, ol.fill_normal(n, seed, sigma, mean))
+    # 2-D window == slice of the full tensor (tensor-parallel shards)
+    full = ol.fill_normal(96 * 640, 5, 0.02).reshape(96, 640)
+    win = kf.fill_normal_2d(ctx, 32, 256, 640, 16, 128, 5, 0.02).numpy(np.uint16, (32, 256))
+    assert np.array_equal(win, full[16:48, 128:384])
+
+
+@pytest.mark.parametrize("bits,mode", ALL_QUANT)
+@pytest.mark.parametrize("rows,cols,group", [(48, 512, 128), (16, 1024, 256), (128, 384, 128)])
+def test_quantize_bit_exact_vs_oracle_packer(ctx, bits, mode, rows, cols, group):
+    w = ol.fill_normal(rows * cols, 100 + bits, 0.02)
+    data_o, gama_o = ol.quantize(w, rows, cols, bits, group, mode)
+    t = kf.quantize(ctx, ctx.array(w), rows, cols, KF_TYPE[(bits, mode)], group, mode)
+    assert t.qbias == ol.qrange(bits, mode)[2]
+    assert np.array_equal(t.gama_numpy(), gama_o)
+    assert np.array_equal(t.data_numpy(), data_o)
+
+
+def test_quantize_edge_cases(ctx):
+    # a constant group (step == 0) and exact-tie values; the oracle documents its step==0 convention
+    rows, cols = 16, 256
+    w = ol.fill_normal(rows * cols, 9, 0.02).reshape(rows, cols)
+    w[0, :128] = 0x3C00          # constant group
+    w[1, :] = 0                  # all zeros
+    w[2, :128] = ol.f32_to_bf16(np.linspace(-1, 1, 128).astype(np.float32))
+    for bits, mode in ALL_QUANT:
+        data_o, gama_o = ol.quantize(w.reshape(-1), rows, cols, bits, 128, mode)
+        t = kf.quantize(ctx, ctx.array(w), rows, cols, KF_TYPE[(bits, mode)], 128, mode)
+        assert np.array_equal(t.data_numpy(), data_o), (bits, mode)
+        assert np.array_equal(t.gama_numpy(), gama_o), (bits, mode)
+    # ragged shapes are rejected, not silently mis-packed
+    with pytest.raises(kf.KoifishError):
+        kf.quantize(ctx, ctx.array(w), rows, cols, kf.KF_T_Q4, 96, ol.RTN_ASYM)
+    with pytest.raises(kf.KoifishError):
+        kf.quantize(ctx, ctx.array(w), rows, cols, kf.KF_T_BINARY, 128, ol.RTN_ASYM)
+
+
+@pytest.mark.parametrize("bits", [4, 2, 1])
+def test_unpack_layout_against_reference_golden_bytes(ctx, bits):
+    # bytes produced by the REFERENCE's PACK_*to128_ macros (tests/golden/make_golden.py); step = 1, zero = 0 => dequant == code
+    codes, data = GOLD[f"codes{bits}"], GOLD[f"bytes{bits}"]
+    n = codes.size
+    rows, cols = n // 128, 128
+    gama = np.zeros(rows + cols + 2 * rows, dtype=np.uint16)
+    gama[rows + cols + rows:] = 0x3F80
+    tp = {4: kf.KF_T_Q4, 2: kf.KF_T_Q2, 1: kf.KF_T_BINARY}[bits]
+    t = kf.QTensor.from_packed(ctx, data, gama, rows, cols, tp, 128, 0)
+    got = ol.bf16_to_f32(kf.dequant(ctx, t).numpy(np.uint16)).astype(np.int32)
+    assert np.array_equal(got, codes)
+
+
+@pytest.mark.parametrize("bits,mode", ALL_QUANT)
+def test_dequant_bit_exact(ctx, bits, mode):
+    rows, cols = 64, 1024
+    t, wdq = oracle_qtensor(ctx, rows, cols, bits, mode, 300 + bits)
+    got = kf.dequant(ctx, t).numpy(np.uint16, (rows, cols))
+    assert np.array_equal(got, wdq)
+
+
+def test_f8_bit_exact(ctx):
+    w = ol.fill_normal(1 << 16, 77, 0.02)
+    w[:8] = [0, 0x8000, 0x3F80, 0xBF80, 0x0001, 0x3380, 0x3800, 0x4700]  # zeros, +-1, tiny / fp16-subnormal range, large
+    t = kf.quantize(ctx, ctx.array(w), 256, 256, kf.KF_T_F8E5M2, 0, 0)
+    assert np.array_equal(t.data_numpy(), ol.f8_encode(w))
+    assert np.array_equal(kf.dequant(ctx, t).numpy(np.uint16), ol.f8_decode(ol.f8_encode(w)))
+
+
+# ---------------------------------------------------------------------------------------------- fused dequant GEMV
+@pytest.mark.parametrize("kind", WEIGHT_KINDS, ids=str)
+@pytest.mark.parametrize("M", [1, 3, 8])
+def test_gemv_onehot_reproduces_dequantised_weights_bit_exact(ctx, kind, M):
+    # x = e_k  =>  y[n] = w[n][k] exactly: pins the in-kernel unpack + dequant (and the k-permutation) against the oracle
+    rows, cols = 160, 512
+    t, wdq = make_weight(ctx, kind, rows, cols, 900)
+    rng = np.random.default_rng(1)
+    for trial in range(6):
+        ks = rng.integers(0, cols, size=M)
+        x = np.zeros((M, cols), dtype=np.uint16)
+        x[np.arange(M), ks] = 0x3F80
+        y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16, (M, rows))
+        for m in range(M):
+            assert np.array_equal(y[m], wdq[:, ks[m]]), (kind, M, trial, m)
+
+
+def _check_linear(y_bits, w_bits, x_bits, M, N, K):
+    ref = ol.linear_f32(w_bits, x_bits, M, N, K)
+    got = ol.bf16_to_f32(y_bits).reshape(M, N)
+    # tolerance: one bf16 rounding of the result (2^-8 relative, half-ulp is 2^-9) + fp32 accumulation-order noise
+    tol = np.abs(ref) * 2.0 ** -8 + 2e-3 * np.sqrt(np.mean(ref ** 2))
+    bad = np.abs(got - ref) > tol
+    assert not bad.any(), "max err %g at %s" % (np.abs(got - ref).max(), np.argwhere(bad)[:4])
+
+
+@pytest.mark.parametrize("kind", WEIGHT_KINDS, ids=str)
+@pytest.mark.parametrize("M,N,K", [(1, 256, 1024), (1, 1040, 4096), (2, 128, 512), (8, 384, 2048), (16, 256, 1024), (33, 128, 1024), (64, 256, 512)])
+def test_gemv_matches_oracle(ctx, kind, M, N, K):
+    t, wdq = make_weight(ctx, kind, N, K, 1000 + M)
+    x = rand_bf16(np.random.default_rng(M * 7 + N), (M, K))
+    y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16)
+    _check_linear(y, wdq, x, M, N, K)
+
+
+@pytest.mark.parametrize("splitk", [1, 2, 3, 7])
+def test_gemv_splitk_deterministic_and_correct(ctx, splitk):
+    M, N, K = 4, 384, 4096
+    t, wdq = make_weight(ctx, (4, ol.RTN_ASYM), N, K, 55)
+    x = rand_bf16(np.random.default_rng(3), (M, K))
+    xd = ctx.array(x)
+    ctx.set_int("gemv_splitk", splitk)
+    try:
+        y1 = kf.linear(ctx, t, xd, M).numpy(np.uint16)
+        y2 = kf.linear(ctx, t, xd, M).numpy(np.uint16)
+    finally:
+        ctx.set_int("gemv_splitk", 0)
+    assert np.array_equal(y1, y2)  # fixed-order reduction: bit-reproducible run to run
+    _check_linear(y1, wdq, x, M, N, K)
+
+
+def test_gemv_group_256_and_large_group(ctx):
+    M, N, K = 2, 128, 2048
+    for group in (256, 512):
+        w = ol.fill_normal(N * K, 66, 0.02)
+        data, gama = ol.quantize(w, N, K, 4, group, ol.RTN_ASYM)
+        t = kf.QTensor.from_packed(ctx, data, gama, N, K, kf.KF_T_Q4, group, 0)
+        wdq = ol.dequant(data, gama, N, K, 4, group, 0)
+        x = rand_bf16(np.random.default_rng(group), (M, K))
+        _check_linear(kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16), wdq, x, M, N, K)
+
+
+def test_gemv_epilogues(ctx):
+    M, N, K = 3, 256, 1024
+    rng = np.random.default_rng(11)
+    t, wdq = make_weight(ctx, (4, ol.RTN_ASYM), N, K, 70)
+    x = rand_bf16(rng, (M, K))
+    xd = ctx.array(x)
+    plain = kf.linear(ctx, t, xd, M).numpy(np.uint16, (M, N))
+    # residual: out = RN(res + RN_bf16(acc))  (reference: bf16 GEMM output, then CU_add3)
+    res = rand_bf16(rng, (M, N))
+    got = kf.linear(ctx, t, xd, M, kf.KF_EPI_RESIDUAL, ctx.array(res)).numpy(np.uint16, (M, N))
+    assert np.array_equal(got, ol.add(res, plain).reshape(M, N))
+    # in-place residual (y aliases residual), as the runtime uses it
+    buf = ctx.array(res)
+    kf.linear(ctx, t, xd, M, kf.KF_EPI_RESIDUAL, buf, out=buf)
+    assert np.array_equal(buf.numpy(np.uint16, (M, N)), got)
+    # fp32 partial sums (tensor-parallel epilogue): rounding them gives the plain result
+    f32 = kf.linear(ctx, t, xd, M, kf.KF_EPI_F32).numpy(np.float32, (M, N))
+    assert np.array_equal(ol.f32_to_bf16(f32), plain)
+
+
+def test_linear_multi_equals_separate_calls(ctx):
+    M, K = 5, 1024
+    ws = [make_weight(ctx, (4, ol.RTN_ASYM), n, K, 80 + i)[0] for i, n in enumerate((512, 128, 128))]
+    xd = ctx.array(rand_bf16(np.random.default_rng(12), (M, K)))
+    outs = kf.linear_multi(ctx, ws, xd, M)
+    for w, o in zip(ws, outs):
+        assert np.array_equal(o.numpy(np.uint16), kf.linear(ctx, w, xd, M).numpy(np.uint16))
+
+
+@pytest.mark.parametrize("kind", [(4, ol.RTN_ASYM), (2, ol.YYANG), "f8"], ids=str)
+def test_linear_swiglu_fused(ctx, kind):
+    M, N, K = 4, 320, 1024
+    wg, _ = make_weight(ctx, kind, N, K, 90)
+    wu, _ = make_weight(ctx, kind, N, K, 91)
+    xd = ctx.array(rand_bf16(np.random.default_rng(13), (M, K)))
+    g = kf.linear(ctx, wg, xd, M).numpy(np.uint16)
+    u = kf.linear(ctx, wu, xd, M).numpy(np.uint16)
+    fused = kf.linear_swiglu(ctx, wg, wu, xd, M).numpy(np.uint16)
+    want = ol.swiglu(g, u)
+    # same op order as the reference (bf16 gate/up, fp32 SwiGLU); expf may differ by an ulp between libm and CUDA
+    diff = np.abs(ol.bf16_to_f32(fused) - ol.bf16_to_f32(want))
+    assert (diff <= np.abs(ol.bf16_to_f32(want)) * 2.0 ** -7 + 1e-30).all()
+    assert (fused == want).mean() > 0.999
+
+
+def test_linear_rejects_bad_shapes(ctx):
+    t, _ = make_weight(ctx, (4, ol.RTN_ASYM), 128, 512, 1)
+    xd = ctx.array(np.zeros((1, 512), dtype=np.uint16))
+    with pytest.raises(kf.KoifishError):
+        kf.linear(ctx, t, xd, 0)
+    bad = kf.QTensor.from_packed(ctx, np.zeros(24 * 512 // 2, dtype=np.uint8), np.zeros(24 + 512 + 2 * 96, dtype=np.uint16), 24, 512, kf.KF_T_Q4)
+    with pytest.raises(kf.KoifishError):
+        kf.linear(ctx, bad, xd, 1)  # rows not a multiple of 16
+
+
+def test_gemv_full_size_properties_qwen3_32b_down_proj(ctx):
+    # BASELINE full size: K = 25600, N = 5120, 4-bit.  Size-independent properties: one-hot columns reproduce the dequantised
+    # weights bit-exactly; x = ones gives the row sums; linearity y(a+b) ~ y(a)+y(b).
+    N, K = 5120, 25600
+    w = kf.fill_normal(ctx, N * K, 4242, 0.02)
+    t = kf.quantize(ctx, w, N, K, kf.KF_T_Q4, 128, ol.RTN_ASYM)
+    wdq = kf.dequant(ctx, t).numpy(np.uint16, (N, K))
+    rng = np.random.default_rng(5)
+    ks = rng.integers(0, K, size=8)
+    x = np.zeros((8, K), dtype=np.uint16)
+    x[np.arange(8), ks] = 0x3F80
+    y = kf.linear(ctx, t, ctx.array(x), 8).numpy(np.uint16, (8, N))
+    for m in range(8):
+        assert np.array_equal(y[m], wdq[:, ks[m]])
+    ones = np.full((1, K), 0x3F80, dtype=np.uint16)
+    ysum = ol.bf16_to_f32(kf.linear(ctx, t, ctx.array(ones), 1).numpy(np.uint16))
+    want = ol.bf16_to_f32(wdq).astype(np.float64).sum(1)
+    assert np.allclose(ysum, want, rtol=2.0 ** -7, atol=2e-2)
+    a, b = rand_bf16(rng, (1, K), 0.5), rand_bf16(rng, (1, K), 0.5)
+    ab = ol.f32_to_bf16(ol.bf16_to_f32(a) + ol.bf16_to_f32(b))
+    ya, yb, yab = (kf.linear(ctx, t, ctx.array(v), 1, kf.KF_EPI_F32).numpy(np.float32) for v in (a, b, ab))
+    # ab is a+b rounded to bf16, so compare against the exact linear image of the rounded input
+    assert np.allclose(yab, ol.linear_f32(wdq, ab, 1, N, K)[0], rtol=1e-3, atol=2e-3)
+    assert np.allclose(ya + yb, yab, rtol=0.05, atol=0.05)
+
+
+# ---------------------------------------------------------------------------------------------- small ops
+@pytest.mark.parametrize("rows,dim", [(1, 1024), (1, 5120), (7, 4096), (64, 256)])
+def test_rmsnorm(ctx, rows, dim):
+    rng = np.random.default_rng(dim)
+    x, w = rand_bf16(rng, (rows, dim), 3.0), rand_bf16(rng, (dim,), 0.5)
+    got = kf.rmsnorm(ctx, ctx.array(x), ctx.array(w), rows, dim, 1e-6).numpy(np.uint16, (rows, dim))
+    want = ol.rmsnorm(x, w, rows, dim, 1e-6)
+    # identical formula; only the order of the fp32 sum of squares differs -> at most one bf16 ulp on a few elements
+    d = np.abs(ol.bf16_to_f32(got) - ol.bf16_to_f32(want))
+    assert (d <= np.abs(ol.bf16_to_f32(want)) * 2.0 ** -7).all()
+    assert (got == want).mean() > 0.98
+
+
+@pytest.mark.parametrize("hd,n_head,n_kv", [(128, 16, 8), (64, 4, 2)])
+@pytest.mark.parametrize("theta", [1e4, 1e6])
+def test_qknorm_rope_kvappend(ctx, hd, n_head, n_kv, theta):
+    rng = np.random.default_rng(hd)
+    M, max_seq = 3, 64
+    pos = np.array([5, 17, 63], dtype=np.int32)
+    q, k, v = rand_bf16(rng, (M, n_head * hd)), rand_bf16(rng, (M, n_kv * hd)), rand_bf16(rng, (M, n_kv * hd))
+    qw, kw = rand_bf16(rng, (hd,), 0.3), rand_bf16(rng, (hd,), 0.3)
+    qd = ctx.array(q)
+    kc, vc = ctx.zeros(max_seq * n_kv * hd * 2), ctx.zeros(max_seq * n_kv * hd * 2)
+    table = kf.rope_table(ctx, max_seq, hd, theta)
+    kf.qknorm_rope_kvappend(ctx, qd, ctx.array(k), ctx.array(v), ctx.array(qw), ctx.array(kw), kc, vc, table, ctx.array(pos), M, n_head, n_kv,
+                            hd, max_seq)
+    q_got = qd.numpy(np.uint16, (M, n_head * hd))
+    k_got = kc.numpy(np.uint16, (max_seq, n_kv * hd))
+    v_got = vc.numpy(np.uint16, (max_seq, n_kv * hd))
+    for m in range(M):
+        q_want = ol.rope(ol.rmsnorm(q[m].reshape(n_head, hd), qw, n_head, hd, 1e-6), n_head, hd, int(pos[m]), theta).reshape(-1)
+        k_want = ol.rope(ol.rmsnorm(k[m].reshape(n_kv, hd), kw, n_kv, hd, 1e-6), n_kv, hd, int(pos[m]), theta).reshape(-1)
+        for got, want in ((q_got[m], q_want), (k_got[pos[m]], k_want)):
+            d = np.abs(ol.bf16_to_f32(got) - ol.bf16_to_f32(want))
+            assert (d <= np.abs(ol.bf16_to_f32(want)) * 2.0 ** -6 + 2e-3).all()
+            assert (got == want).mean() > 0.95
+        assert np.array_equal(v_got[pos[m]], v[m])
+    untouched = np.setdiff1d(np.arange(max_seq), pos)
+    assert not k_got[untouched].any() and not v_got[untouched].any()
+
+
+@pytest.mark.parametrize("hd,n_head,n_kv", [(128, 16, 8), (128, 64, 8), (64, 4, 2)])
+@pytest.mark.parametrize("pos", [0, 1, 31, 200, 1500])
+def test_attention_decode(ctx, hd, n_head, n_kv, pos):
+    # includes pos >= 1024, which the reference's attention_qk_kernel silently truncates
+    rng = np.random.default_rng(pos + hd)
+    max_seq = 2048
+    q = rand_bf16(rng, (1, n_head * hd))
+    kc, vc = rand_bf16(rng, (max_seq, n_kv * hd)), rand_bf16(rng, (max_seq, n_kv * hd))
+    kcd, vcd = ctx.array(kc), ctx.array(vc)
+    want = ol.bf16_to_f32(ol.attention_decode(q, kc, vc, pos, n_head, n_kv, hd, 0)).reshape(-1)
+    for split in (0, 1, 5):
+        ctx.set_int("attn_split", split)
+        try:
+            got = kf.attn_decode(ctx, ctx.array(q), kcd, vcd, ctx.array(np.array([pos], dtype=np.int32)), 1, n_head, n_kv, hd, max_seq, pos)
+        finally:
+            ctx.set_int("attn_split", 0)
+        g = ol.bf16_to_f32(got.numpy(np.uint16))
+        assert np.allclose(g, want, rtol=2.0 ** -6, atol=4e-3), (split, np.abs(g - want).max())
+
+
+def test_attention_batched_sequences_and_prefill_panel(ctx):
+    rng = np.random.default_rng(21)
+    hd, n_head, n_kv, max_seq, M = 128, 16, 8, 256, 4
+    q = rand_bf16(rng, (M, n_head * hd))
+    pos = np.array([3, 77, 150, 255], dtype=np.int32)
+    # (a) M independent sequences: cache [M][max_seq][kv_dim]
+    kc, vc = rand_bf16(rng, (M, max_seq, n_kv * hd)), rand_bf16(rng, (M, max_seq, n_kv * hd))
+    got = kf.attn_decode(ctx, ctx.array(q), ctx.array(kc), ctx.array(vc), ctx.array(pos), M, n_head, n_kv, hd, max_seq, 255,
+                         seq_stride=max_seq * n_kv * hd).numpy(np.uint16, (M, n_head * hd))
+    for m in range(M):
+        want = ol.bf16_to_f32(ol.attention_decode(q[m], kc[m], vc[m], int(pos[m]), n_head, n_kv, hd, 0)).reshape(-1)
+        assert np.allclose(ol.bf16_to_f32(got[m]), want, rtol=2.0 ** -6, atol=4e-3)
+    # (b) one sequence, causal panel: token m attends to 0..pos[m]
+    got = kf.attn_decode(ctx, ctx.array(q), ctx.array(kc[0]), ctx.array(vc[0]), ctx.array(pos), M, n_head, n_kv, hd, max_seq, 255).numpy(
+        np.uint16, (M, n_head * hd))
+    for m in range(M):
+        want = ol.bf16_to_f32(ol.attention_decode(q[m], kc[0], vc[0], int(pos[m]), n_head, n_kv, hd, 0)).reshape(-1)
+        assert np.allclose(ol.bf16_to_f32(got[m]), want, rtol=2.0 ** -6, atol=4e-3)
+
+
+def test_swiglu_add_embed_argmax(ctx):
+    rng = np.random.default_rng(31)
+    n = 5000
+    g, u = rand_bf16(rng, (n,), 2.0), rand_bf16(rng, (n,), 2.0)
+    sw = kf.swiglu(ctx, ctx.array(g), ctx.array(u), n).numpy(np.uint16)
+    want = ol.swiglu(g, u)
+    assert (sw == want).mean() > 0.999 and np.allclose(ol.bf16_to_f32(sw), ol.bf16_to_f32(want), rtol=2.0 ** -7, atol=1e-30)
+    assert np.array_equal(kf.add(ctx, ctx.array(g), ctx.array(u), n).numpy(np.uint16), ol.add(g, u))
+    # embedding rows, plain and quantised tables
+    rows, cols = 1024, 512
+    toks = np.array([0, 1023, 77, 77], dtype=np.int32)
+    for kind in ("bf16", "f8", (4, ol.RTN_ASYM), (2, ol.YYANG), (1, ol.YYANG)):
+        t, wdq = make_weight(ctx, kind, rows, cols, 44)
+        e = kf.embed(ctx, t, ctx.array(toks), toks.size).numpy(np.uint16, (toks.size, cols))
+        assert np.array_equal(e, wdq[toks]), kind
+    # argmax with ties -> lowest index
+    logits = rand_bf16(rng, (3, 151936))
+    logits[1, 5] = logits[1, 100000] = 0x4700
+    logits[2, :] = 0x3F80
+    am = kf.argmax(ctx, ctx.array(logits), 3, 151936).numpy(np.int32)
+    assert am[0] == int(np.argmax(ol.bf16_to_f32(logits[0]))) and am[1] == 5 and am[2] == 0

@@ -1,0 +1,195 @@
+"""GPU parity tests of the whole decode path through the reference-facing C ABI (kf_model_*), against the CPU oracle's model on
+the same synthetic weights (same generator definition, same quantiser).  Gates: dequantised weights bit-exact;
+logits max error <= 1e-2 of the logit scale; top-1 agreement on teacher-forced tokens."""
+import numpy as np
+import pytest
+
+import koifish_b200 as kf
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_RTOL = 1e-2  # north_star: "logits within a stated relative tolerance (e.g. 1e-2 bf16 / top-1 token agreement)"
+
+MODE_NAME = {ol.RTN_ASYM: "RTN", ol.YYANG: "yyang"}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = kf.Context(0)
+    yield c
+    c.close()
+
+
+def quant_entry(bits, mode):
+    if bits == 16:
+        return None
+    if bits == 8:
+        return {"bits": 8}
+    return {"quant_method": MODE_NAME[mode], "bits": bits}
+
+
+def build_pair(ctx, n_layer=2, n_embd=256, n_ff=512, n_head=4, n_kv_head=2, head_dim=64, vocab=1024, max_seq=64, attn=(4, ol.RTN_ASYM),
+               mlp=(4, ol.RTN_ASYM), embed=(16, ol.RTN_ASYM), tie=True, theta=1e6, norm_sigma=0.1, max_batch=1, seed=42):
+    quantizer = {"group_size": 128}
+    for key, (bits, mode) in (("self_attn", attn), ("mlp", mlp), ("embed_tokens", embed)):
+        e = quant_entry(bits, mode)
+        if e:
+            quantizer[key] = e
+    cfg = kf.qwen3_config(n_layer, n_embd, n_ff, n_head, n_kv_head, head_dim, vocab, quantizer, tie, max_seq, max_batch, seed, theta,
+                          norm_sigma=norm_sigma)
+    model = kf.Model(ctx, cfg)
+    model.init_random()
+    oracle = ol.OracleModel(n_layer=n_layer, n_embd=n_embd, n_ff=n_ff, n_head=n_head, n_kv_head=n_kv_head, head_dim=head_dim, vocab=vocab,
+                            max_seq=max_seq, rope_theta=theta, tie_embed=int(tie), attn_bits=attn[0], attn_mode=attn[1], mlp_bits=mlp[0],
+                            mlp_mode=mlp[1], embed_bits=embed[0], embed_mode=embed[1], seed=seed, norm_sigma=norm_sigma)
+    return model, oracle
+
+
+def logits_close(got_bits, want_bits):
+    g, w = ol.bf16_to_f32(got_bits), ol.bf16_to_f32(want_bits)
+    scale = np.abs(w).max()
+    err = np.abs(g - w).max() / scale
+    return err, g, w
+
+
+def prompt(n, vocab):
+    return [(1000 + 37 * i) % vocab for i in range(n)]
+
+
+TENSOR_IDS = {"model.embed_tokens.weight": 0, "model.norm.weight": 1, "model.layers.0.input_layernorm.weight": 16,
+              "model.layers.0.self_attn.q_proj.weight": 17, "model.layers.0.self_attn.k_proj.weight": 18,
+              "model.layers.0.self_attn.v_proj.weight": 19, "model.layers.0.self_attn.q_norm.weight": 20,
+              "model.layers.0.self_attn.o_proj.weight": 22, "model.layers.1.post_attention_layernorm.weight": 39,
+              "model.layers.1.mlp.gate_proj.weight": 40, "model.layers.1.mlp.up_proj.weight": 41, "model.layers.1.mlp.down_proj.weight": 42}
+
+
+@pytest.mark.parametrize("attn,mlp,embed", [((4, ol.RTN_ASYM), (4, ol.RTN_ASYM), (16, 0)), ((8, 0), (4, ol.RTN_ASYM), (16, 0)),
+                                            ((2, ol.YYANG), (1, ol.YYANG), (4, ol.RTN_ASYM))], ids=["q4", "hybrid8_4", "ternary_binary_q4embed"])
+def test_resident_weights_bit_exact(ctx, attn, mlp, embed):
+    model, oracle = build_pair(ctx, attn=attn, mlp=mlp, embed=embed)
+    for name, tid in TENSOR_IDS.items():
+        got = model.dequant_tensor(name).reshape(-1)
+        assert np.array_equal(got, oracle.weight(tid)), name
+
+
+@pytest.mark.parametrize("attn,mlp,embed,tie", [((4, ol.RTN_ASYM), (4, ol.RTN_ASYM), (16, 0), True), ((8, 0), (4, ol.RTN_ASYM), (16, 0), True),
+                                                ((2, ol.YYANG), (2, ol.YYANG), (16, 0), False), ((1, ol.YYANG), (1, ol.YYANG), (16, 0), False),
+                                                ((16, 0), (16, 0), (16, 0), True), ((4, ol.RTN_ASYM), (4, ol.RTN_ASYM), (4, ol.RTN_ASYM), True)],
+                         ids=["q4", "hybrid8_4", "ternary", "binary", "bf16", "q4_all"])
+def test_decode_logits_match_oracle(ctx, attn, mlp, embed, tie):
+    model, oracle = build_pair(ctx, attn=attn, mlp=mlp, embed=embed, tie=tie)
+    toks = prompt(14, 1024)
+    agree = decided = 0
+    for pos, tok in enumerate(toks):  # teacher-forced on the same tokens
+        lg, nxt = model.forward([tok], [pos], want_logits=True, want_next=True)
+        want = oracle.forward(tok, pos)
+        err, g, w = logits_close(lg[0], want)
+        assert err <= LOGIT_RTOL, "pos %d: logits rel err %g" % (pos, err)
+        assert nxt[0] == int(np.argmax(g))  # device argmax == argmax of the logits it returned
+        top2 = np.sort(w)[-2:]
+        if top2[1] - top2[0] > 2 * LOGIT_RTOL * np.abs(w).max():  # the oracle itself is decisive
+            decided += 1
+            agree += int(np.argmax(g) == np.argmax(w))
+    assert agree == decided
+    # K/V rows written by the path (K after QK-norm + RoPE) match the oracle's cache
+    kd = 2 * 64
+    for layer in (0, 1):
+        for got, want in ((model.kcache(layer, len(toks), kd), oracle.kcache(layer, len(toks))), (model.vcache(layer, len(toks), kd), oracle.vcache(layer, len(toks)))):
+            d = np.abs(ol.bf16_to_f32(got) - ol.bf16_to_f32(want))
+            assert d.max() <= 2e-2 * max(1e-6, np.abs(ol.bf16_to_f32(want)).max())
+
+
+def test_prefill_panel_equals_token_by_token(ctx):
+    model, _ = build_pair(ctx)
+    toks = prompt(20, 1024)
+    for pos, tok in enumerate(toks):
+        last, _ = model.forward([tok], [pos])
+    k_seq = model.kcache(1, len(toks), 128).copy()
+    model2, _ = build_pair(ctx)
+    panel, _ = model2.forward(toks, list(range(len(toks))), seq_mode=0)
+    err, *_ = logits_close(panel[-1], last[0])
+    assert err <= 2e-3
+    d = np.abs(ol.bf16_to_f32(model2.kcache(1, len(toks), 128)) - ol.bf16_to_f32(k_seq))
+    assert d.max() <= 1e-2 * np.abs(ol.bf16_to_f32(k_seq)).max()
+
+
+def test_batched_decode_equals_independent_sequences(ctx):
+    B = 3
+    model, _ = build_pair(ctx, max_batch=B)
+    seqs = [[(11 + 5 * b + 37 * i) % 1024 for i in range(6)] for b in range(B)]
+    for i in range(6):
+        batched, _ = model.forward([s[i] for s in seqs], [i] * B, seq_mode=1)
+    single, _ = build_pair(ctx, max_batch=1)
+    for b in range(B):
+        m1, _ = build_pair(ctx)
+        for i in range(6):
+            lg, _ = m1.forward([seqs[b][i]], [i])
+        err, *_ = logits_close(batched[b], lg[0])
+        assert err <= 2e-3, (b, err)
+
+
+def test_decode_loop_and_graph_replay_match_stepwise(ctx):
+    model, _ = build_pair(ctx)
+    toks = prompt(5, 1024)
+    for pos, tok in enumerate(toks[:-1]):
+        model.forward([tok], [pos], want_logits=False)
+    # stepwise greedy, host round trip each token (eager first, captured graph from the second call on)
+    seq, tok, pos = [], toks[-1], len(toks) - 1
+    for _ in range(10):
+        _, nxt = model.forward([tok], [pos], want_logits=True, want_next=True)
+        tok, pos = int(nxt[0]), pos + 1
+        seq.append(tok)
+    # same continuation, graphs disabled
+    m2, _ = build_pair(ctx)
+    m2.set_graphs(False)
+    for p, t in enumerate(toks[:-1]):
+        m2.forward([t], [p], want_logits=False)
+    seq2, tok, pos = [], toks[-1], len(toks) - 1
+    for _ in range(10):
+        _, nxt = m2.forward([tok], [pos], want_logits=True, want_next=True)
+        tok, pos = int(nxt[0]), pos + 1
+        seq2.append(tok)
+    assert seq == seq2
+    # device-resident loop: feed the first token, then 9 more steps without touching the host
+    m3, _ = build_pair(ctx)
+    for p, t in enumerate(toks[:-1]):
+        m3.forward([t], [p], want_logits=False)
+    _, nxt = m3.forward([toks[-1]], [len(toks) - 1], want_logits=True, want_next=True)
+    assert int(nxt[0]) == seq[0]
+    m3.forward([seq[0]], [len(toks)], want_logits=False)  # stage (token, pos) for the loop; recomputed by its first step
+    m3.decode_loop(9, 1)
+    ctx.sync()
+    t, p = m3.read_state(1)
+    assert int(p[0]) == len(toks) + 9 and int(t[0]) == seq[9]
+
+
+def test_forward_argument_errors(ctx):
+    model, _ = build_pair(ctx)
+    for toks, pos, mode in (([5000], [0], 0), ([1], [64], 0), ([1, 2], [0, 0], 1), ([], [], 0)):
+        with pytest.raises(kf.KoifishError):
+            model.forward(toks, pos, seq_mode=mode)
+    with pytest.raises(kf.KoifishError):
+        kf.Model(ctx, kf.qwen3_config(2, 256, 512, 4, 2, 64, 1024, {"self_attn": {"bits": 4}}))  # NF4: not built
+    with pytest.raises(kf.KoifishError):
+        model.set_tensor("model.layers.0.nope.weight", np.zeros((4, 4), dtype=np.uint16))
+
+
+def test_set_tensor_quantises_external_weights(ctx):
+    model, oracle = build_pair(ctx)
+    name, rows, cols = "model.layers.0.mlp.up_proj.weight", 512, 256
+    w = ol.fill_normal(rows * cols, 987654, 0.05).reshape(rows, cols)
+    model.set_tensor(name, w)
+    data, gama = ol.quantize(w, rows, cols, 4, 128, ol.RTN_ASYM)
+    assert np.array_equal(model.dequant_tensor(name), ol.dequant(data, gama, rows, cols, 4, 128, 0))
+
+
+def test_qwen3_0p6b_dims_two_layers_full_vocab(ctx):
+    # BASELINE config 1 shapes (E 1024, FFN 3072, H16/KV8, hd 128, vocab 151936, tied bf16 head, 4-bit blocks), 2 of the 28 layers
+    model, oracle = build_pair(ctx, n_layer=2, n_embd=1024, n_ff=3072, n_head=16, n_kv_head=8, head_dim=128, vocab=151936, max_seq=64,
+                               norm_sigma=0.0)
+    toks = prompt(6, 151936)
+    for pos, tok in enumerate(toks):
+        lg, _ = model.forward([tok], [pos])
+        err, g, w = logits_close(lg[0], oracle.forward(tok, pos))
+        assert err <= LOGIT_RTOL, (pos, err)
