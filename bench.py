@@ -202,7 +202,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: torch events and our kernels share it
+    torch.cuda.set_stream(stream)
     ctx = kf.Context(local, stream.cuda_stream)
     if world > 1:
         idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")

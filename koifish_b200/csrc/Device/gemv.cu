@@ -119,11 +119,11 @@ __device__ __forceinline__ uint32_t deq_pair(uint32_t reg, int shift, uint32_t s
     if (MODE == MODE_AFFINE) {
         // qbias == 0:  RN(step*(v-128)) == fma(v, step, -128*step) (single rounding of the exact product step*c) ; then RN(p - zero)
         __nv_bfloat162 p = __hfma2(u32_as_bf162(v), u32_as_bf162(step2), u32_as_bf162(nbias2));
-        return bf162_as_u32(__hsub2(p, u32_as_bf162(zero2)));
+        return bf162_as_u32(__hsub2_rn(p, u32_as_bf162(zero2)));
     } else if (MODE == MODE_AFFINE_SYM) {
         __nv_bfloat162 k = __hsub2(u32_as_bf162(v), u32_as_bf162(bias2));  // exact small integer
-        __nv_bfloat162 p = __hmul2(u32_as_bf162(step2), k);
-        return bf162_as_u32(__hsub2(p, u32_as_bf162(zero2)));
+        __nv_bfloat162 p = __hmul2_rn(u32_as_bf162(step2), k);
+        return bf162_as_u32(__hsub2_rn(p, u32_as_bf162(zero2)));
     } else {  // MODE_SCALE: A = code - qbias ; the group step is applied to the fp32 group sum
         return bf162_as_u32(__hsub2(u32_as_bf162(v), u32_as_bf162(bias2)));
     }
@@ -480,7 +480,7 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     S = std::max(S, (p.steps_total + max_steps - 1) / max_steps);
     S = std::max(1, std::min(S, p.steps_total));
     p.S = S;
-    const int nsteps_max = (p.steps_total + S - 1) / S + 1;
+    const int nsteps_max = (p.steps_total + S - 1) / S;  // floor/ceil slicing never exceeds ceil(steps/S) <= max_steps
     if (S > 1) {
         int rc = kf_ensure_gemv_ws(ctx, (size_t)S * rb * MXs * kRowsCta * sizeof(float) * (M == 1 ? 8 : 1), rb);
         if (rc) return rc;

@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(256) kf_embed_kernel(uint16_t* __restrict__ ou
         const int jj   = j < half ? j : j - half;
         const int code = (int)((src >> (64 - bits * (jj + 1))) & ((1u << bits) - 1));
         const size_t g = e / group;
-        const __nv_bfloat16 p = __hmul(__ushort_as_bfloat16(gStep[g]), __int2bfloat16_rn(code - qbias));
-        r = __bfloat16_as_ushort(__hsub(p, __ushort_as_bfloat16(gZero[g])));
+        const __nv_bfloat16 p = __hmul_rn(__ushort_as_bfloat16(gStep[g]), __int2bfloat16_rn(code - qbias));
+        r = __bfloat16_as_ushort(__hsub_rn(p, __ushort_as_bfloat16(gZero[g])));
     }
     out[(size_t)m * cols + c] = r;
 }

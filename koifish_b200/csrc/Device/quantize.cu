@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(256) kf_dequant_kernel(const uint4* __restrict
         const int jj   = j < HALF ? j : j - HALF;
         const int code = (int)((src >> (64 - BITS * (jj + 1))) & ((1u << BITS) - 1));
         __nv_bfloat16 k = __int2bfloat16_rn(code - qBias);
-        __nv_bfloat16 p = __hmul(step, k);
-        out[e0 + j]     = __bfloat16_as_ushort(__hsub(p, zero));
+        __nv_bfloat16 p = __hmul_rn(step, k);  // _rn: never contracted with the subtraction (two roundings, as on the reference build)
+        out[e0 + j]     = __bfloat16_as_ushort(__hsub_rn(p, zero));
     }
 }
 __global__ void __launch_bounds__(256) kf_f8e5m2_decode_kernel(const uint8_t* __restrict__ in, size_t n, uint16_t* __restrict__ out) {

@@ -40,7 +40,8 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-default) stream shared by torch events and our kernels
+    torch.cuda.set_stream(stream)
     ctx = kf.Context(0, stream.cuda_stream)
     peak = 6452.8
     try:
