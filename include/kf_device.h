@@ -128,6 +128,13 @@ int kf_linear_multi(kf_ctx* ctx, int n, void* const* y_dev, const kf_tensor_desc
 /* FFN gate/up + CU_swiglu_v0 (src/Device/CUDA/NeuronFuse.cu:628-637, Activation.cu:86-93): y = silu(bf16(Wg x)) * bf16(Wu x) */
 int kf_linear_swiglu(kf_ctx* ctx, void* y_dev, const kf_tensor_desc* w_gate, const kf_tensor_desc* w_up, const void* x_dev, int M);
 
+/* LayerNormal::cuFlow (CU_rms_infer, layernorm.cuh:801-859) folded into the matmul(s) that consume its output, as
+ * SelfAttention::cuInfer / FFN::cuInfer / Head4Token chain them (QKV.cu:640-652, NeuronFuse.cu:624-637): the normalised activations
+ * are produced while x is staged on chip and never touch HBM.  Same arithmetic and rounding points as kf_rmsnorm followed by
+ * kf_linear_multi (mode 0, n <= 3 outputs y[i] = [M][rows_i]) or kf_linear_swiglu (mode 2, w[0] gate, w[1] up -> y[0]). */
+int kf_rmsnorm_linear(kf_ctx* ctx, int n, void* const* y_dev, const kf_tensor_desc* w, const void* x_dev, const void* norm_w_dev, float eps,
+                      int M, int mode);
+
 /* ---- LayerNormal::cuFlow chat branch -> CU_rms_infer (src/Device/CUDA/T.cu:569-573, kernel/layernorm.cuh:801-859) ---- */
 int kf_rmsnorm(kf_ctx* ctx, void* out_dev, const void* x_dev, const void* w_dev, int rows, int dim, float eps);
 /* ---- ROPE::cuInfer (src/Device/CUDA/kernel/rope.cu:645-672): per-head QK RMSNorm (layernorm.cuh:750-798), half-split RoPE

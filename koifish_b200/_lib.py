@@ -71,6 +71,7 @@ SIGNATURES = {
     "kf_linear_multi": (_I, [_P, _I, C.POINTER(_P), _DESCP, _P, _I]),
     "kf_linear_swiglu": (_I, [_P, _P, _DESCP, _DESCP, _P, _I]),
     "kf_rmsnorm": (_I, [_P, _P, _P, _P, _I, _I, _F]),
+    "kf_rmsnorm_linear": (_I, [_P, _I, C.POINTER(_P), _DESCP, _P, _P, _F, _I, _I]),
     "kf_rope_table": (_I, [_P, _P, _I, _I, _F]),
     "kf_qknorm_rope_kvappend": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _SZ]),
     "kf_attn_decode": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _SZ]),

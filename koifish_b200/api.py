@@ -202,6 +202,15 @@ def linear_swiglu(ctx, wg, wu, x, M):
     return out
 
 
+def rmsnorm_linear(ctx, ws, x, norm_w, M, eps=1e-6, swiglu=False):
+    """RMSNorm folded into the matmul(s) consuming it (norm -> Q/K/V, norm -> gate/up+SwiGLU, final norm -> lm_head)"""
+    outs = [ctx.empty(M * ws[0].rows * 2)] if swiglu else [ctx.empty(M * w.rows * 2) for w in ws]
+    descs = (TensorDesc * len(ws))(*[w.desc() for w in ws])
+    ys = (C.c_void_p * len(ws))(*[o.ptr for o in (outs * len(ws) if swiglu else outs)])
+    ctx.check(ctx.lib.kf_rmsnorm_linear(ctx.h, len(ws), ys, descs, x.ptr, norm_w.ptr, eps, M, 2 if swiglu else 0), "kf_rmsnorm_linear")
+    return outs[0] if swiglu else outs
+
+
 def rmsnorm(ctx, x, w, rows, dim, eps=1e-6):
     out = ctx.empty(rows * dim * 2)
     ctx.check(ctx.lib.kf_rmsnorm(ctx.h, out.ptr, x.ptr, w.ptr, rows, dim, eps), "kf_rmsnorm")

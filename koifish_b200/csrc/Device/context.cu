@@ -116,6 +116,8 @@ extern "C" int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value) {
         ctx->gemv_splitk = value;
     else if (!strcmp(key, "gemv_variant"))
         ctx->gemv_variant = value;
+    else if (!strcmp(key, "gemv_exact"))
+        ctx->gemv_exact = value;
     else if (!strcmp(key, "attn_split"))
         ctx->attn_split = value;
     else

@@ -2,20 +2,25 @@
 //
 // Replaces the reference pair  GTensor::GetDataX (whole-matrix dequant to a bf16 scratch, src/Device/CUDA/kernel/quantizer.cu:
 // 249-392, T.cu:245-294)  +  CU_mm_blasLt (cuBLASLt bf16 GEMM, src/Device/CUDA/kernel/gemm.cu:93-214)  as called from
-// SLP::Forw (src/Device/CUDA/NeuronFuse.cu:305-381), plus the CU_swiglu_v0 / CU_add3 launches that follow it.
+// SLP::Forw (src/Device/CUDA/NeuronFuse.cu:305-381), plus the launches around it: the preceding CU_rms_infer (layernorm.cuh:
+// 801-859) can be folded into the activation staging, the following CU_swiglu_v0 / CU_add3 into the epilogue.
 //
 // Design (HBM-bound; roofline = bytes of packed weights + gama):
-//   * every packed byte is read from HBM exactly once, straight into registers, with 16/8/4-byte loads whose quad-wise union
-//     is a contiguous 64/32/16-byte run of one weight row; PF steps are kept in flight per thread;
+//   * every packed byte is read from HBM exactly once.  Each thread copies the 16/8/4-byte words it will consume into its own slot
+//     of a shared-memory ring with cp.async (no register staging, DEPTH k-steps in flight per thread, no block barrier: a thread
+//     only ever reads what it copied itself).  The first DEPTH copies are issued before the prologue, so the weight stream runs
+//     while the activations are being normalised / staged;
 //   * the codes are expanded in registers to the *bit-exact* bf16 weights the reference's dequant kernel produces
 //     (p = RN(step*k), w = RN(p - zero), both bf16) and fed directly as the A fragments of mma.sync.m16n8k16 (bf16 in, fp32
 //     accumulate -- the accumulation type cuBLASLt uses in the reference).  Tensor-core *throughput* is irrelevant here (the op
-//     is bandwidth bound); the MMA is used because it takes bf16 pairs without an unpack-to-fp32 and does the 16x8x16 FMAs in
-//     one issue slot, which is what keeps the CUDA-core instruction count below the HBM rate;
+//     is bandwidth bound, the MMA pipe runs at < 20 %); the MMA is used because it takes bf16 pairs without an unpack-to-fp32
+//     and does the 16x8x16 FMAs in one issue slot -- the kernel is issue-slot limited, not DRAM limited, once the loads are
+//     deep enough (profiles/r01_ncu_gemv_q4_v1.txt);
 //   * the k-order inside a 128-wide group is permuted to make code extraction cheap (nibbles 16 bits apart form one bf16x2
 //     register); the activations are staged in shared memory in the same permuted order, so no weight is ever shuffled;
-//   * split-K across CTAs with a deterministic (fixed-order) last-CTA reduction; bias-free epilogues fuse the residual add or
-//     SwiGLU(gate, up).
+//   * per-group zero/step are staged once per CTA in shared memory with wide batched loads;
+//   * a warp owns RT row tiles of 16 rows that share every activation fragment;
+//   * split-K across CTAs with a deterministic (fixed-order) last-CTA reduction; epilogues fuse the residual add or SwiGLU.
 #include <string.h>
 
 #include <algorithm>
@@ -25,20 +30,26 @@
 namespace {
 
 enum { FMT_BF16 = 0, FMT_F8 = 1, FMT_Q4 = 2, FMT_Q2 = 3, FMT_Q1 = 4 };
-enum { MODE_PLAIN = 0, MODE_AFFINE = 1, MODE_AFFINE_SYM = 2, MODE_SCALE = 3 };
+enum { MODE_PLAIN = 0, MODE_AFFINE = 1, MODE_AFFINE_SYM = 2, MODE_SCALE = 3, MODE_FACTOR = 4 };
+// MODE_FACTOR (opt-in, ctx knob gemv_exact = 0): A = 128 + code, un-dequantised; per group y += step*(acc_g - (128+qbias)*Sx) - zero*Sx with
+// Sx = sum of the group's activations.  Mathematically the same affine map, but WITHOUT the reference's two bf16 roundings of the
+// weights (result differs from the exact modes by about one bf16 ulp of y); it exists to measure what the roundings cost.
 enum { EPI_NONE = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_F32 = 4 };
 
 constexpr int kThreads = 256;
-constexpr int kWarps   = 8;
-constexpr int kRowsCta = 128;
-constexpr int kTileStride = 132;  // fp32 tile row stride (padded: conflict-free fragment scatter)
+constexpr int KSTEP    = 128;  // k per step for every format (= one quantisation group of the packed formats)
+constexpr int UNITS    = 4;    // 8-element activation units per thread slot and step
+constexpr int KT       = 32;   // k per thread slot
 
+// CPB: bytes per cp.async ; NCH: copies per (row, k-step) and thread ; D1 / D2: ring depth for 16 / 32 rows per warp
 template <int FMT> struct Fmt;
-template <> struct Fmt<FMT_Q4>   { static constexpr int KSTEP = 128, UNITS = 4, LOADB = 16, PF = 4, BITS = 4; };
-template <> struct Fmt<FMT_Q2>   { static constexpr int KSTEP = 128, UNITS = 4, LOADB = 8,  PF = 6, BITS = 2; };
-template <> struct Fmt<FMT_Q1>   { static constexpr int KSTEP = 128, UNITS = 4, LOADB = 4,  PF = 8, BITS = 1; };
-template <> struct Fmt<FMT_F8>   { static constexpr int KSTEP = 64,  UNITS = 2, LOADB = 16, PF = 4, BITS = 8; };
-template <> struct Fmt<FMT_BF16> { static constexpr int KSTEP = 32,  UNITS = 1, LOADB = 16, PF = 4, BITS = 16; };
+template <> struct Fmt<FMT_Q4>   { static constexpr int BITS = 4,  CPB = 16, NCH = 1, D1 = 5,  D2 = 3; };
+template <> struct Fmt<FMT_Q2>   { static constexpr int BITS = 2,  CPB = 8,  NCH = 1, D1 = 8,  D2 = 5; };
+template <> struct Fmt<FMT_Q1>   { static constexpr int BITS = 1,  CPB = 4,  NCH = 1, D1 = 12, D2 = 8; };
+template <> struct Fmt<FMT_F8>   { static constexpr int BITS = 8,  CPB = 16, NCH = 2, D1 = 3,  D2 = 2; };
+template <> struct Fmt<FMT_BF16> { static constexpr int BITS = 16, CPB = 16, NCH = 4, D1 = 2,  D2 = 2; };
+
+__host__ __device__ constexpr int fmt_tb(int bits) { return KT * bits / 8; }  // bytes per thread, row and k-step
 
 struct GemvSeg {
     const uint8_t* data;
@@ -53,12 +64,17 @@ struct GemvParams {
     int nseg;
     const uint16_t* x;
     const uint16_t* residual;
+    const uint16_t* norm_w;  // optional fused RMSNorm of x (weights [K]); nullptr = x is used as is
+    float norm_eps;
     int M, K;
     int steps_total;  // K / KSTEP
     int S;            // k-splits
+    int nsteps_max;   // ceil(steps_total / S): sizes the shared-memory regions
     int total_rb;
     int qbias;
-    int gshift;  // log2(group / 128): gama index = row*(K/group) + (step >> gshift)
+    int ring_off;  // byte offset of the weight ring inside dynamic shared memory (16-byte aligned)
+    int sx_off;    // byte offset of the activation group sums (MODE_FACTOR)
+    int gshift;    // log2(group / 128): gama index = row*(K/group) + (step >> gshift)
     int epilogue;
     uint32_t lop_mask, lop_magic;  // code-field mask (0x000F000F / 0x00030003 / 0x00010001) and bf16x2 128.0 (0x43004300)
     float* ws;
@@ -69,9 +85,9 @@ struct GemvParams {
 template <int FMT>
 __host__ __device__ constexpr int xperm(int o) {
     const int u = o >> 3, e = o & 7;
-    if (FMT == FMT_Q4) return 8 * u + ((e & 1) ? 3 : 7) - (e >> 1);                               // {7,3,6,2,5,1,4,0}
-    if (FMT == FMT_Q2) return 16 * (u >> 1) + ((e & 1) ? 7 : 15) - (e >> 1) - 4 * (u & 1);        // {15,7,14,6,13,5,12,4} / -4
-    if (FMT == FMT_Q1) return ((e & 1) ? 15 : 31) - (e >> 1) - 4 * u;                             // {31,15,30,14,29,13,28,12} - 4u
+    if (FMT == FMT_Q4) return 8 * u + ((e & 1) ? 3 : 7) - (e >> 1);                         // {7,3,6,2,5,1,4,0}
+    if (FMT == FMT_Q2) return 16 * (u >> 1) + ((e & 1) ? 7 : 15) - (e >> 1) - 4 * (u & 1);  // {15,7,14,6,13,5,12,4} / -4
+    if (FMT == FMT_Q1) return ((e & 1) ? 15 : 31) - (e >> 1) - 4 * u;                       // {31,15,30,14,29,13,28,12} - 4u
     return o;
 }
 
@@ -82,29 +98,23 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int LOADB> struct LoadT;
-template <> struct LoadT<16> { using type = uint4; };
-template <> struct LoadT<8>  { using type = uint2; };
-template <> struct LoadT<4>  { using type = uint32_t; };
+// asynchronous global -> shared copy (LDGSTS): no register staging, so many k-steps can be in flight per thread
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    else if constexpr (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
-__device__ __forceinline__ void ldw(uint4& r, const uint8_t* p) { r = ldg_stream_v4(p); }
-__device__ __forceinline__ void ldw(uint2& r, const uint8_t* p) { r = ldg_stream_v2(p); }
-__device__ __forceinline__ void ldw(uint32_t& r, const uint8_t* p) { r = ldg_stream_u32(p); }
-
-// 32-bit register #idx (in code order: idx 0 holds the first codes of the thread's slot)
-__device__ __forceinline__ uint32_t reg_of(const uint4& q, int idx) { return idx == 0 ? q.w : idx == 1 ? q.z : idx == 2 ? q.y : q.x; }
-__device__ __forceinline__ uint32_t reg_of(const uint2& q, int idx) { return idx == 0 ? q.y : q.x; }
-__device__ __forceinline__ uint32_t reg_of(const uint32_t& q, int) { return q; }
-// natural order (byte / bf16 streams)
-__device__ __forceinline__ uint32_t nat_of(const uint4& q, int idx) { return idx == 0 ? q.x : idx == 1 ? q.y : idx == 2 ? q.z : q.w; }
-
-template <int FMT>
-struct Stage {
-    typename LoadT<Fmt<FMT>::LOADB>::type qa, qb;  // row g, row g+8
-    uint32_t ga, gb;                               // zero | step<<16 for the two rows
-};
-
-// Expand one pair of codes (16 bits apart in `reg` after the shift) to the bf16x2 weights.
 // (a & b) | c in ONE LOP3: mask and magic come from kernel parameters so that ptxas keeps them as register / constant-bank
 // operands instead of splitting the op into two immediate-form LOP3s.
 __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
@@ -112,57 +122,212 @@ __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-template <int FMT, int MODE>
+// Expand one pair of codes (16 bits apart in `reg` after the shift) to the bf16x2 weights.  The _rn intrinsics are never
+// contracted by ptxas: the two roundings of the reference build (bf16 multiply, then bf16 subtract) are preserved.
+template <int MODE>
 __device__ __forceinline__ uint32_t deq_pair(uint32_t reg, int shift, uint32_t step2, uint32_t zero2, uint32_t nbias2, uint32_t bias2,
                                              uint32_t mask, uint32_t magic) {
     uint32_t v = and_or(reg >> shift, mask, magic);  // bf16x2 {128 + c_lo, 128 + c_hi}, exact
+    if (MODE == MODE_FACTOR) return v;
     if (MODE == MODE_AFFINE) {
         // qbias == 0:  RN(step*(v-128)) == fma(v, step, -128*step) (single rounding of the exact product step*c) ; then RN(p - zero)
         __nv_bfloat162 p = __hfma2(u32_as_bf162(v), u32_as_bf162(step2), u32_as_bf162(nbias2));
         return bf162_as_u32(__hsub2_rn(p, u32_as_bf162(zero2)));
     } else if (MODE == MODE_AFFINE_SYM) {
-        __nv_bfloat162 k = __hsub2(u32_as_bf162(v), u32_as_bf162(bias2));  // exact small integer
+        __nv_bfloat162 k = __hsub2_rn(u32_as_bf162(v), u32_as_bf162(bias2));  // exact small integer
         __nv_bfloat162 p = __hmul2_rn(u32_as_bf162(step2), k);
         return bf162_as_u32(__hsub2_rn(p, u32_as_bf162(zero2)));
     } else {  // MODE_SCALE: A = code - qbias ; the group step is applied to the fp32 group sum
-        return bf162_as_u32(__hsub2(u32_as_bf162(v), u32_as_bf162(bias2)));
+        return bf162_as_u32(__hsub2_rn(u32_as_bf162(v), u32_as_bf162(bias2)));
     }
 }
 // E5M2-by-truncation bytes -> bf16x2 (exact): fp16 bits (b<<8) re-biased into bf16 via a 2^112 multiply
 __device__ __forceinline__ uint32_t f8_pair(uint32_t reg, uint32_t sel) {
     uint32_t h2 = __byte_perm(reg, 0u, sel);  // {b_hi<<8 : b_lo<<8} as fp16x2
     uint32_t t  = ((h2 >> 3) & 0x0FE00FE0u) | (h2 & 0x80008000u);
-    return bf162_as_u32(__hmul2(u32_as_bf162(t), u32_as_bf162(0x77807780u)));  // * 2^112
+    return bf162_as_u32(__hmul2_rn(u32_as_bf162(t), u32_as_bf162(0x77807780u)));  // * 2^112
 }
 
-template <int FMT, int MODE, int NT, bool M1>
-__global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : 2)) kf_gemv_kernel(const GemvParams p) {
+// A fragments of mma #(2u+h) of the current k-step for one row tile.  wa / wb: the thread's TB bytes of rows g / g+8 as 32-bit
+// registers in MEMORY order (the 128-bit word formats keep the first codes in the LAST register: PackedQ.hpp:28-31).
+template <int FMT, int MODE, int NR>
+__device__ __forceinline__ void build_a(uint32_t (&a)[4], const uint32_t (&wa)[NR], const uint32_t (&wb)[NR], int u, int h, const uint32_t (&gm)[6],
+                                        uint32_t bias2, uint32_t mask, uint32_t magic) {
+    // gm = {step2a, zero2a, nb2a, step2b, zero2b, nb2b}
+    if constexpr (FMT == FMT_Q4) {
+        const uint32_t ra = wa[3 - u], rb = wb[3 - u];
+        a[0] = deq_pair<MODE>(ra, 8 * h, gm[0], gm[1], gm[2], bias2, mask, magic);
+        a[1] = deq_pair<MODE>(rb, 8 * h, gm[3], gm[4], gm[5], bias2, mask, magic);
+        a[2] = deq_pair<MODE>(ra, 8 * h + 4, gm[0], gm[1], gm[2], bias2, mask, magic);
+        a[3] = deq_pair<MODE>(rb, 8 * h + 4, gm[3], gm[4], gm[5], bias2, mask, magic);
+    } else if constexpr (FMT == FMT_Q2) {
+        const uint32_t ra = wa[1 - (u >> 1)], rb = wb[1 - (u >> 1)];
+        const int m4 = 4 * (2 * (u & 1) + h);
+        a[0] = deq_pair<MODE>(ra, m4, gm[0], gm[1], gm[2], bias2, mask, magic);
+        a[1] = deq_pair<MODE>(rb, m4, gm[3], gm[4], gm[5], bias2, mask, magic);
+        a[2] = deq_pair<MODE>(ra, m4 + 2, gm[0], gm[1], gm[2], bias2, mask, magic);
+        a[3] = deq_pair<MODE>(rb, m4 + 2, gm[3], gm[4], gm[5], bias2, mask, magic);
+    } else if constexpr (FMT == FMT_Q1) {
+        const uint32_t ra = wa[0], rb = wb[0];
+        const int m2 = 2 * (2 * u + h);
+        a[0] = deq_pair<MODE>(ra, m2, gm[0], gm[1], gm[2], bias2, mask, magic);
+        a[1] = deq_pair<MODE>(rb, m2, gm[3], gm[4], gm[5], bias2, mask, magic);
+        a[2] = deq_pair<MODE>(ra, m2 + 1, gm[0], gm[1], gm[2], bias2, mask, magic);
+        a[3] = deq_pair<MODE>(rb, m2 + 1, gm[3], gm[4], gm[5], bias2, mask, magic);
+    } else if constexpr (FMT == FMT_F8) {  // 32 bytes per thread and row: register 2u+h holds k = 8u+4h .. +3
+        const uint32_t ra = wa[2 * u + h], rb = wb[2 * u + h];
+        a[0] = f8_pair(ra, 0x1404u), a[1] = f8_pair(rb, 0x1404u);
+        a[2] = f8_pair(ra, 0x3424u), a[3] = f8_pair(rb, 0x3424u);
+    } else {  // FMT_BF16: 64 bytes per thread and row: registers 4u+2h, 4u+2h+1 hold k = 8u+4h .. +3
+        a[0] = wa[4 * u + 2 * h], a[1] = wb[4 * u + 2 * h];
+        a[2] = wa[4 * u + 2 * h + 1], a[3] = wb[4 * u + 2 * h + 1];
+    }
+}
+
+// NT: 8-token column tiles ; M1: single token (activations broadcast) ; RT: 16-row tiles per warp
+template <int FMT, int MODE, int NT, bool M1, int RT>
+__global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? 3 : 2)) kf_gemv_kernel(const GemvParams p) {
     using F = Fmt<FMT>;
-    constexpr int KSTEP = F::KSTEP, UNITS = F::UNITS, PF = F::PF, KT = KSTEP / 4;
-    constexpr int MX = M1 ? 1 : 8 * NT;  // token rows staged in shared memory
-    constexpr int MP = 8 * NT;           // token columns of the fp32 tile
+    constexpr int DEPTH = RT == 2 ? F::D2 : F::D1, CPB = F::CPB, NCH = F::NCH;
+    constexpr int TB = fmt_tb(F::BITS), NR = TB / 4;  // bytes / 32-bit registers per thread, row and k-step
+    constexpr int STEPB = KSTEP * F::BITS / 8;         // bytes per row per k-step
+    constexpr int MX = M1 ? 1 : 8 * NT;                // token rows staged in shared memory
+    constexpr int MP = 8 * NT;                         // token columns of the fp32 tile
+    constexpr int ROWS = 128 * RT, HALF = ROWS / 2, WROWS = 16 * RT, TS = ROWS + 4, GS = ROWS + 1;
+    static_assert(TB == CPB * NCH, "ring chunking");
     extern __shared__ uint4 smem[];
     __shared__ int s_last;
+    __shared__ float s_red[32];
+    __shared__ float s_scale[64];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int rb = blockIdx.x, split = blockIdx.y;
     const bool swiglu = p.epilogue == EPI_SWIGLU;
 
-    // ---- which rows does this warp own? -------------------------------------------------------------------------------------
+    // ---- which rows does this CTA / warp own? -------------------------------------------------------------------------------
     int segi = 0;
     if (!swiglu) {
         if (p.nseg > 1 && rb >= p.seg[1].rb0) segi = 1;
         if (p.nseg > 2 && rb >= p.seg[2].rb0) segi = 2;
-    } else {
-        segi = warp >> 2;
     }
-    const GemvSeg& sg = p.seg[segi];
-    const int row0    = swiglu ? rb * 64 + (warp & 3) * 16 : (rb - sg.rb0) * kRowsCta + warp * 16;
-    const bool active = row0 + 16 <= sg.rows;
+    const GemvSeg& sgw = p.seg[swiglu ? (warp >> 2) : segi];  // segment of this warp
+    const int wrow0    = swiglu ? rb * HALF + (warp & 3) * WROWS : (rb - sgw.rb0) * ROWS + warp * WROWS;
 
     const int s_begin = (int)(((long long)split * p.steps_total) / p.S);
     const int s_end   = (int)(((long long)(split + 1) * p.steps_total) / p.S);
     const int nsteps  = s_end - s_begin;
+    uint32_t* sgam    = reinterpret_cast<uint32_t*>(smem + (size_t)p.nsteps_max * UNITS * MX * 4);
+    // per-thread ring of packed weight words: [DEPTH][RT][2 (row g / g+8)][NCH][256 threads] x CPB bytes
+    uint8_t* ring = reinterpret_cast<uint8_t*>(smem) + p.ring_off;
+
+    // ---- weight stream: start the first DEPTH k-steps NOW -- they do not depend on the activations, so the copies overlap the
+    //      whole prologue (norm, activation staging, gama staging) --------------------------------------------------------------
+    const bool wactive     = nsteps > 0 && wrow0 < sgw.rows;
+    const size_t row_bytes = (size_t)p.K * F::BITS / 8;
+    const uint8_t* pa[RT];
+    {
+        int toff;  // byte offset of this thread's slot inside one k-step of a row
+        if (FMT == FMT_Q2)
+            toff = 16 * (t >> 1) + 8 * (1 - (t & 1));  // word.high holds the first 32 codes (PackedQ.hpp:185-198)
+        else if (FMT == FMT_Q1)
+            toff = 12 - 4 * t;                          // high.hi32 holds codes 0..31 (PackedQ.hpp:200-211)
+        else
+            toff = 16 * t;  // 16-byte formats: chunk ch of thread t sits at (4*ch + t)*16, so a quad always covers 64 contiguous bytes
+#pragma unroll
+        for (int rt = 0; rt < RT; rt++) {
+            int r0 = wrow0 + rt * 16;
+            if (r0 + 16 > sgw.rows) r0 = sgw.rows - 16;  // out-of-range tile: read valid rows, results are dropped by the epilogue
+            pa[rt] = sgw.data + (size_t)(r0 + g) * row_bytes + (size_t)s_begin * STEPB + toff;
+        }
+    }
+    auto ring_at = [&](int slot_, int rt, int half, int ch) -> uint8_t* {
+        return ring + ((size_t)(((slot_ * RT + rt) * 2 + half) * NCH + ch) * kThreads + tid) * CPB;
+    };
+    auto issue_stage = [&](int slot_, int sl) {
+#pragma unroll
+        for (int rt = 0; rt < RT; rt++)
+#pragma unroll
+            for (int half = 0; half < 2; half++)
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++)
+                    cp_async<CPB>(ring_at(slot_, rt, half, ch), pa[rt] + (size_t)half * 8 * row_bytes + (size_t)sl * STEPB + ch * 64);
+    };
+    if (wactive) {
+#pragma unroll
+        for (int i = 0; i < DEPTH; i++) {
+            if (i < nsteps) issue_stage(i, i);
+            cp_async_commit();
+        }
+    }
+
+    // ---- stage zero/step of every (row, k-step) of the CTA tile.  One thread per (row, array): a contiguous run of nsteps bf16,
+    //      fetched with 16-byte loads that are all issued before the first use (one DRAM round trip, not one per element) -----------
+    if (MODE != MODE_PLAIN && nsteps > 0) {
+        const int gpr = (p.K >> 7) >> p.gshift;  // groups per row
+        for (int idx = tid; idx < 2 * ROWS; idx += kThreads) {
+            const int r = idx % ROWS, which = idx / ROWS;  // which: 0 = zero, 1 = step
+            const GemvSeg& sr = p.seg[swiglu ? (r >= HALF) : segi];
+            const int grow    = swiglu ? rb * HALF + (r & (HALF - 1)) : (rb - sr.rb0) * ROWS + r;
+            uint16_t* dst     = reinterpret_cast<uint16_t*>(sgam + r) + which;  // low half = zero, high half = step
+            if (grow >= sr.rows) {
+                for (int s = 0; s < nsteps; s++) dst[(size_t)s * GS * 2] = 0;
+                continue;
+            }
+            const uint16_t* src = (which ? sr.step : sr.zero) + (size_t)grow * gpr;
+            if (p.gshift == 0 && ((reinterpret_cast<uintptr_t>(src + s_begin) & 15) == 0)) {
+                const uint4* v4 = reinterpret_cast<const uint4*>(src + s_begin);
+                int s = 0;
+                for (; s + 32 <= nsteps; s += 32) {  // 4 x 16 bytes in flight
+                    uint4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[j] = __ldg(v4 + (s >> 3) + j);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t q[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                        for (int e = 0; e < 8; e++) dst[(size_t)(s + 8 * j + e) * GS * 2] = (uint16_t)(q[e >> 1] >> ((e & 1) * 16));
+                    }
+                }
+                for (; s + 8 <= nsteps; s += 8) {
+                    const uint4 v = __ldg(v4 + (s >> 3));
+                    const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 8; e++) dst[(size_t)(s + e) * GS * 2] = (uint16_t)(q[e >> 1] >> ((e & 1) * 16));
+                }
+                for (; s < nsteps; s++) dst[(size_t)s * GS * 2] = __ldg(src + s_begin + s);
+            } else {
+                int s = 0;
+                for (; s + 8 <= nsteps; s += 8) {
+                    uint16_t v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[e] = __ldg(src + ((s_begin + s + e) >> p.gshift));
+#pragma unroll
+                    for (int e = 0; e < 8; e++) dst[(size_t)(s + e) * GS * 2] = v[e];
+                }
+                for (; s < nsteps; s++) dst[(size_t)s * GS * 2] = __ldg(src + ((s_begin + s) >> p.gshift));
+            }
+        }
+    }
+
+    // ---- optional fused RMSNorm: the same arithmetic, in the same order, as kf_rmsnorm_kernel (ops.cu) --------------------------
+    if (p.norm_w) {
+        for (int m = 0; m < p.M; m++) {
+            const uint16_t* xr = p.x + (size_t)m * p.K;
+            float ss = 0.f;
+            for (int i = tid * 8; i < p.K; i += kThreads * 8) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + i));
+                const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float a = bf16lo(q[j]), b = bf16hi(q[j]);
+                    ss = fmaf(a, a, ss), ss = fmaf(b, b, ss);
+                }
+            }
+            ss = block_sum(ss, s_red);
+            if (tid == 0) s_scale[m] = 1.0f / sqrtf(fmaf(ss, 1.0f / (float)p.K, p.norm_eps));
+        }
+        __syncthreads();
+    }
 
     // ---- stage the activations of this k-slice in shared memory, permuted to the fragment order --------------------------------
     {
@@ -171,11 +336,26 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : 2)) kf_gemv_kernel(co
             const int tt = it & 3, m = (it >> 2) % MX, s = it / (4 * MX);
             uint32_t src[KT / 2];
             if (m < p.M) {
-                const uint4* gp = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + (size_t)(s_begin + s) * KSTEP + tt * KT);
+                const size_t k0 = (size_t)(s_begin + s) * KSTEP + tt * KT;
+                const uint4* gp = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + k0);
 #pragma unroll
                 for (int i = 0; i < KT / 8; i++) {
                     uint4 v = __ldg(gp + i);
                     src[4 * i + 0] = v.x, src[4 * i + 1] = v.y, src[4 * i + 2] = v.z, src[4 * i + 3] = v.w;
+                }
+                if (p.norm_w) {  // (x * s) * w, rounded to bf16 like the stand-alone kernel's output
+                    const float sc  = s_scale[m];
+                    const uint4* wp = reinterpret_cast<const uint4*>(p.norm_w + k0);
+#pragma unroll
+                    for (int i = 0; i < KT / 8; i++) {
+                        const uint4 wv = __ldg(wp + i);
+                        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t xv = src[4 * i + j];
+                            src[4 * i + j]    = pack_bf16x2((bf16lo(xv) * sc) * bf16lo(ww[j]), (bf16hi(xv) * sc) * bf16hi(ww[j]));
+                        }
+                    }
                 }
             } else {
 #pragma unroll
@@ -191,159 +371,175 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : 2)) kf_gemv_kernel(co
                     const uint32_t hi = (src[e1 >> 1] >> ((e1 & 1) * 16)) & 0xffffu;
                     o[j] = lo | (hi << 16);
                 }
-                smem[((s * UNITS + u) * MX + m) * 4 + tt] = make_uint4(o[0], o[1], o[2], o[3]);
+                // destination (unit, thread slot): packed formats keep the 32-k slot of thread tt; the byte / bf16 streams interleave
+                // 16-byte chunks across the quad (chunk ch of thread t covers bytes (4*ch + t)*16 of the k-step)
+                int du = u, dt = tt;
+                if (FMT == FMT_BF16) {
+                    du = tt, dt = u;  // natural 8-k block B = 4*tt + u  ->  unit B >> 2, thread B & 3
+                } else if (FMT == FMT_F8) {
+                    const int C = 2 * tt + (u >> 1);  // 16-k chunk index
+                    du = 2 * (C >> 2) + (u & 1), dt = C & 3;
+                }
+                smem[((s * UNITS + du) * MX + m) * 4 + dt] = make_uint4(o[0], o[1], o[2], o[3]);
             }
         }
     }
     __syncthreads();
-
-    float acc[NT][4];
+    float* sxs = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem) + p.sx_off);  // [nsteps][MX] group sums of the activations
+    if (MODE == MODE_FACTOR) {
+        for (int it = tid; it < nsteps * MX; it += kThreads) {
+            const int s = it / MX, m = it - s * MX;
+            float sum = 0.f;
+            for (int u = 0; u < UNITS; u++)
 #pragma unroll
-    for (int nt = 0; nt < NT; nt++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[nt][j] = 0.f;
-
-    if (active && nsteps > 0) {
-        const size_t row_bytes = (size_t)p.K * F::BITS / 8;
-        int toff;  // byte offset of this thread's slot inside one k-step of a row
-        if (FMT == FMT_Q2)
-            toff = 16 * (t >> 1) + 8 * (1 - (t & 1));  // word.high holds the first 32 codes (PackedQ.hpp:185-198)
-        else if (FMT == FMT_Q1)
-            toff = 12 - 4 * t;                          // high.hi32 holds codes 0..31 (PackedQ.hpp:200-211)
-        else
-            toff = 16 * t;
-        constexpr int STEPB = KSTEP * F::BITS / 8;  // bytes per row per k-step
-        const uint8_t* pa = sg.data + (size_t)(row0 + g) * row_bytes + (size_t)s_begin * STEPB + toff;
-        const uint8_t* pb = pa + 8 * row_bytes;
-        const int gpr     = (p.K >> 7) >> p.gshift;  // groups per row
-        const uint16_t *za = nullptr, *sa = nullptr, *zb = nullptr, *sb = nullptr;
-        if (MODE != MODE_PLAIN) {
-            za = sg.zero + (size_t)(row0 + g) * gpr, sa = sg.step + (size_t)(row0 + g) * gpr;
-            zb = za + (size_t)8 * gpr, sb = sa + (size_t)8 * gpr;
-        }
-        const uint32_t bias2 = pack_bf16x2((float)(128 + p.qbias), (float)(128 + p.qbias));
-
-        Stage<FMT> st[PF];
-        auto load_stage = [&](Stage<FMT>& s_, int sl) {
-            ldw(s_.qa, pa + (size_t)sl * STEPB);
-            ldw(s_.qb, pb + (size_t)sl * STEPB);
-            if (MODE != MODE_PLAIN) {
-                const int gi = (s_begin + sl) >> p.gshift;
-                s_.ga = (uint32_t)__ldg(za + gi) | ((uint32_t)__ldg(sa + gi) << 16);
-                s_.gb = (uint32_t)__ldg(zb + gi) | ((uint32_t)__ldg(sb + gi) << 16);
-            }
-        };
-#pragma unroll
-        for (int i = 0; i < PF; i++)
-            if (i < nsteps) load_stage(st[i], i);
-
-        const int xlane = (M1 ? 0 : g) * 4 + t;
-        for (int s0 = 0; s0 < nsteps; s0 += PF) {
-#pragma unroll
-            for (int i = 0; i < PF; i++) {
-                const int s = s0 + i;
-                if (s >= nsteps) break;
-                const Stage<FMT>& cur = st[i];
-
-                uint32_t step2a = 0, zero2a = 0, nb2a = 0, step2b = 0, zero2b = 0, nb2b = 0;
-                if (MODE != MODE_PLAIN) {
-                    step2a = __byte_perm(cur.ga, 0u, 0x3232), zero2a = __byte_perm(cur.ga, 0u, 0x1010);
-                    step2b = __byte_perm(cur.gb, 0u, 0x3232), zero2b = __byte_perm(cur.gb, 0u, 0x1010);
-                    if (MODE == MODE_AFFINE) {
-                        nb2a = bf162_as_u32(__hmul2(u32_as_bf162(step2a), u32_as_bf162(0xC300C300u)));  // -128*step, exact
-                        nb2b = bf162_as_u32(__hmul2(u32_as_bf162(step2b), u32_as_bf162(0xC300C300u)));
-                    }
+                for (int tt = 0; tt < 4; tt++) {
+                    const uint4 v = smem[((s * UNITS + u) * MX + m) * 4 + tt];
+                    sum += bf16lo(v.x), sum += bf16hi(v.x), sum += bf16lo(v.y), sum += bf16hi(v.y);
+                    sum += bf16lo(v.z), sum += bf16hi(v.z), sum += bf16lo(v.w), sum += bf16hi(v.w);
                 }
-                float accg[NT][4];
-                if (MODE == MODE_SCALE) {
+            sxs[it] = sum;
+        }
+        __syncthreads();
+    }
+
+    float acc[RT][NT][4];
+#pragma unroll
+    for (int rt = 0; rt < RT; rt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[rt][nt][j] = 0.f;
+
+    if (wactive) {
+        const uint32_t bias2  = pack_bf16x2((float)(128 + p.qbias), (float)(128 + p.qbias));
+        const int xlane       = (M1 ? 0 : g) * 4 + t;
+        const uint32_t* gbase = sgam + warp * WROWS + g;
+        int slot = 0;
+#pragma unroll 1
+        for (int s = 0; s < nsteps; s++) {
+            cp_async_wait<DEPTH - 1>();  // this thread's copies of k-step s have landed (each thread reads only what it copied)
+            uint32_t wreg[RT][2][NR];
+#pragma unroll
+            for (int rt = 0; rt < RT; rt++)
+#pragma unroll
+                for (int half = 0; half < 2; half++)
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ch++) {
+                        if constexpr (CPB == 16) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(ring_at(slot, rt, half, ch));
+                            wreg[rt][half][4 * ch + 0] = v.x, wreg[rt][half][4 * ch + 1] = v.y;
+                            wreg[rt][half][4 * ch + 2] = v.z, wreg[rt][half][4 * ch + 3] = v.w;
+                        } else if constexpr (CPB == 8) {
+                            const uint2 v = *reinterpret_cast<const uint2*>(ring_at(slot, rt, half, ch));
+                            wreg[rt][half][0] = v.x, wreg[rt][half][1] = v.y;
+                        } else {
+                            wreg[rt][half][0] = *reinterpret_cast<const uint32_t*>(ring_at(slot, rt, half, ch));
+                        }
+                    }
+            uint32_t gm[RT][6];
+            float fstep[RT][2];
+            if (MODE != MODE_PLAIN && MODE != MODE_FACTOR) {
+#pragma unroll
+                for (int rt = 0; rt < RT; rt++) {
+                    const uint32_t ga = gbase[s * GS + rt * 16], gb = gbase[s * GS + rt * 16 + 8];
+                    gm[rt][0] = __byte_perm(ga, 0u, 0x3232), gm[rt][1] = __byte_perm(ga, 0u, 0x1010);
+                    gm[rt][3] = __byte_perm(gb, 0u, 0x3232), gm[rt][4] = __byte_perm(gb, 0u, 0x1010);
+                    gm[rt][2] = gm[rt][5] = 0u;
+                    if (MODE == MODE_AFFINE) {
+                        gm[rt][2] = bf162_as_u32(__hmul2_rn(u32_as_bf162(gm[rt][0]), u32_as_bf162(0xC300C300u)));  // -128*step, exact
+                        gm[rt][5] = bf162_as_u32(__hmul2_rn(u32_as_bf162(gm[rt][3]), u32_as_bf162(0xC300C300u)));
+                    }
+                    fstep[rt][0] = bf16hi(ga), fstep[rt][1] = bf16hi(gb);
+                }
+            }
+            float accg[RT][NT][4];
+            if (MODE == MODE_SCALE || MODE == MODE_FACTOR) {
+#pragma unroll
+                for (int rt = 0; rt < RT; rt++)
 #pragma unroll
                     for (int nt = 0; nt < NT; nt++)
 #pragma unroll
-                        for (int j = 0; j < 4; j++) accg[nt][j] = 0.f;
-                }
+                        for (int j = 0; j < 4; j++) accg[rt][nt][j] = 0.f;
+            }
 #pragma unroll
-                for (int u = 0; u < UNITS; u++) {
-                    uint4 xb[NT];
+            for (int u = 0; u < UNITS; u++) {
+                uint4 xb[NT];
 #pragma unroll
-                    for (int nt = 0; nt < NT; nt++) xb[nt] = smem[((s * UNITS + u) * MX + (M1 ? 0 : nt * 8)) * 4 + xlane];
+                for (int nt = 0; nt < NT; nt++) xb[nt] = smem[((s * UNITS + u) * MX + (M1 ? 0 : nt * 8)) * 4 + xlane];
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
+                for (int h = 0; h < 2; h++) {
+#pragma unroll
+                    for (int rt = 0; rt < RT; rt++) {
                         uint32_t a[4];
-                        if constexpr (FMT == FMT_Q4) {
-                            const uint32_t ra = reg_of(cur.qa, u), rb_ = reg_of(cur.qb, u);
-                            a[0] = deq_pair<FMT, MODE>(ra, 8 * h, step2a, zero2a, nb2a, bias2, p.lop_mask, p.lop_magic);
-                            a[1] = deq_pair<FMT, MODE>(rb_, 8 * h, step2b, zero2b, nb2b, bias2, p.lop_mask, p.lop_magic);
-                            a[2] = deq_pair<FMT, MODE>(ra, 8 * h + 4, step2a, zero2a, nb2a, bias2, p.lop_mask, p.lop_magic);
-                            a[3] = deq_pair<FMT, MODE>(rb_, 8 * h + 4, step2b, zero2b, nb2b, bias2, p.lop_mask, p.lop_magic);
-                        } else if constexpr (FMT == FMT_Q2) {
-                            const uint32_t ra = reg_of(cur.qa, u >> 1), rb_ = reg_of(cur.qb, u >> 1);
-                            const int m4 = 4 * (2 * (u & 1) + h);
-                            a[0] = deq_pair<FMT, MODE>(ra, m4, step2a, zero2a, nb2a, bias2, p.lop_mask, p.lop_magic);
-                            a[1] = deq_pair<FMT, MODE>(rb_, m4, step2b, zero2b, nb2b, bias2, p.lop_mask, p.lop_magic);
-                            a[2] = deq_pair<FMT, MODE>(ra, m4 + 2, step2a, zero2a, nb2a, bias2, p.lop_mask, p.lop_magic);
-                            a[3] = deq_pair<FMT, MODE>(rb_, m4 + 2, step2b, zero2b, nb2b, bias2, p.lop_mask, p.lop_magic);
-                        } else if constexpr (FMT == FMT_Q1) {
-                            const uint32_t ra = reg_of(cur.qa, 0), rb_ = reg_of(cur.qb, 0);
-                            const int m2 = 2 * (2 * u + h);
-                            a[0] = deq_pair<FMT, MODE>(ra, m2, step2a, zero2a, nb2a, bias2, p.lop_mask, p.lop_magic);
-                            a[1] = deq_pair<FMT, MODE>(rb_, m2, step2b, zero2b, nb2b, bias2, p.lop_mask, p.lop_magic);
-                            a[2] = deq_pair<FMT, MODE>(ra, m2 + 1, step2a, zero2a, nb2a, bias2, p.lop_mask, p.lop_magic);
-                            a[3] = deq_pair<FMT, MODE>(rb_, m2 + 1, step2b, zero2b, nb2b, bias2, p.lop_mask, p.lop_magic);
-                        } else if constexpr (FMT == FMT_F8) {
-                            const uint32_t ra = nat_of(*reinterpret_cast<const uint4*>(&cur.qa), 2 * u + h);
-                            const uint32_t rb_ = nat_of(*reinterpret_cast<const uint4*>(&cur.qb), 2 * u + h);
-                            a[0] = f8_pair(ra, 0x1404u), a[1] = f8_pair(rb_, 0x1404u);
-                            a[2] = f8_pair(ra, 0x3424u), a[3] = f8_pair(rb_, 0x3424u);
-                        } else {  // FMT_BF16
-                            a[0] = nat_of(*reinterpret_cast<const uint4*>(&cur.qa), 2 * h);
-                            a[1] = nat_of(*reinterpret_cast<const uint4*>(&cur.qb), 2 * h);
-                            a[2] = nat_of(*reinterpret_cast<const uint4*>(&cur.qa), 2 * h + 1);
-                            a[3] = nat_of(*reinterpret_cast<const uint4*>(&cur.qb), 2 * h + 1);
-                        }
+                        build_a<FMT, MODE, NR>(a, wreg[rt][0], wreg[rt][1], u, h, gm[rt], bias2, p.lop_mask, p.lop_magic);
 #pragma unroll
                         for (int nt = 0; nt < NT; nt++) {
                             const uint32_t b0 = h ? xb[nt].z : xb[nt].x, b1 = h ? xb[nt].w : xb[nt].y;
-                            if (MODE == MODE_SCALE)
-                                mma_bf16_16816(accg[nt], a, b0, b1);
+                            if (MODE == MODE_SCALE || MODE == MODE_FACTOR)
+                                mma_bf16_16816(accg[rt][nt], a, b0, b1);
                             else
-                                mma_bf16_16816(acc[nt], a, b0, b1);
+                                mma_bf16_16816(acc[rt][nt], a, b0, b1);
                         }
                     }
                 }
-                if (MODE == MODE_SCALE) {
-                    const float fa = bf16hi(cur.ga), fb = bf16hi(cur.gb);  // step of row g / row g+8
+            }
+            if (MODE == MODE_SCALE) {
+#pragma unroll
+                for (int rt = 0; rt < RT; rt++)
 #pragma unroll
                     for (int nt = 0; nt < NT; nt++) {
-                        acc[nt][0] = fmaf(fa, accg[nt][0], acc[nt][0]);
-                        acc[nt][1] = fmaf(fa, accg[nt][1], acc[nt][1]);
-                        acc[nt][2] = fmaf(fb, accg[nt][2], acc[nt][2]);
-                        acc[nt][3] = fmaf(fb, accg[nt][3], acc[nt][3]);
+                        acc[rt][nt][0] = fmaf(fstep[rt][0], accg[rt][nt][0], acc[rt][nt][0]);
+                        acc[rt][nt][1] = fmaf(fstep[rt][0], accg[rt][nt][1], acc[rt][nt][1]);
+                        acc[rt][nt][2] = fmaf(fstep[rt][1], accg[rt][nt][2], acc[rt][nt][2]);
+                        acc[rt][nt][3] = fmaf(fstep[rt][1], accg[rt][nt][3], acc[rt][nt][3]);
+                    }
+            }
+            if (MODE == MODE_FACTOR) {
+                const float off = (float)(128 + p.qbias);
+#pragma unroll
+                for (int rt = 0; rt < RT; rt++) {
+                    const uint32_t ga = gbase[s * GS + rt * 16], gb = gbase[s * GS + rt * 16 + 8];
+                    const float sa = bf16hi(ga), sb = bf16hi(gb);
+                    const float ka = fmaf(off, sa, bf16lo(ga)), kb = fmaf(off, sb, bf16lo(gb));  // (128+qbias)*step + zero
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) {
+                        const float2 sx = M1 ? make_float2(sxs[s], sxs[s]) : *reinterpret_cast<const float2*>(sxs + s * MX + nt * 8 + 2 * t);
+                        acc[rt][nt][0] += fmaf(sa, accg[rt][nt][0], -ka * sx.x);
+                        acc[rt][nt][1] += fmaf(sa, accg[rt][nt][1], -ka * sx.y);
+                        acc[rt][nt][2] += fmaf(sb, accg[rt][nt][2], -kb * sx.x);
+                        acc[rt][nt][3] += fmaf(sb, accg[rt][nt][3], -kb * sx.y);
                     }
                 }
-                if (s + PF < nsteps) load_stage(st[i], s + PF);  // slot is dead now: refill it PF steps ahead
             }
+            // the slot has been consumed (its registers fed the MMAs above): refill it DEPTH steps ahead
+            if (s + DEPTH < nsteps) issue_stage(slot, s + DEPTH);
+            cp_async_commit();  // one group per k-step, empty at the tail, so the wait count stays uniform
+            slot = slot + 1 == DEPTH ? 0 : slot + 1;
         }
     }
+    cp_async_wait<0>();
 
-    // ---- scatter fragments to the fp32 tile [MP][128 rows] in shared memory -------------------------------------------------
-    __syncthreads();  // everyone is done reading x
+    // ---- scatter fragments to the fp32 tile [MP][ROWS] in shared memory ---------------------------------------------------------
+    __syncthreads();  // everyone is done reading x / gama / ring
     float* tile = reinterpret_cast<float*>(smem);
 #pragma unroll
-    for (int nt = 0; nt < NT; nt++) {
-        const int m0 = nt * 8 + 2 * t, r = warp * 16 + g;
-        tile[(m0 + 0) * kTileStride + r]     = acc[nt][0];
-        tile[(m0 + 1) * kTileStride + r]     = acc[nt][1];
-        tile[(m0 + 0) * kTileStride + r + 8] = acc[nt][2];
-        tile[(m0 + 1) * kTileStride + r + 8] = acc[nt][3];
-    }
+    for (int rt = 0; rt < RT; rt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+            const int m0 = nt * 8 + 2 * t, r = warp * WROWS + rt * 16 + g;
+            tile[(m0 + 0) * TS + r]     = acc[rt][nt][0];
+            tile[(m0 + 1) * TS + r]     = acc[rt][nt][1];
+            tile[(m0 + 0) * TS + r + 8] = acc[rt][nt][2];
+            tile[(m0 + 1) * TS + r + 8] = acc[rt][nt][3];
+        }
     __syncthreads();
 
     // ---- split-K: publish the partial tile; the last CTA of this row block reduces in fixed order ---------------------------
     if (p.S > 1) {
-        float* wsp = p.ws + ((size_t)split * p.total_rb + rb) * (size_t)(MP * kRowsCta);
-        for (int e = tid; e < p.M * kRowsCta; e += kThreads) {
-            const int m = e >> 7, r = e & 127;
-            __stcg(wsp + m * kRowsCta + r, tile[m * kTileStride + r]);
+        float* wsp = p.ws + ((size_t)split * p.total_rb + rb) * (size_t)(MP * ROWS);
+        for (int e = tid; e < p.M * ROWS; e += kThreads) {
+            const int m = e / ROWS, r = e % ROWS;
+            __stcg(wsp + m * ROWS + r, tile[m * TS + r]);
         }
         __threadfence();
         __syncthreads();
@@ -354,11 +550,11 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : 2)) kf_gemv_kernel(co
         __syncthreads();
         if (!s_last) return;
         __threadfence();
-        for (int e = tid; e < p.M * kRowsCta; e += kThreads) {
-            const int m = e >> 7, r = e & 127;
+        for (int e = tid; e < p.M * ROWS; e += kThreads) {
+            const int m = e / ROWS, r = e % ROWS;
             float sum = 0.f;
-            for (int sp = 0; sp < p.S; sp++) sum += __ldcg(p.ws + ((size_t)sp * p.total_rb + rb) * (size_t)(MP * kRowsCta) + m * kRowsCta + r);
-            tile[m * kTileStride + r] = sum;
+            for (int sp = 0; sp < p.S; sp++) sum += __ldcg(p.ws + ((size_t)sp * p.total_rb + rb) * (size_t)(MP * ROWS) + m * ROWS + r);
+            tile[m * TS + r] = sum;
         }
         if (tid == 0) p.cnt[rb] = 0u;  // self-reset for the next launch
         __syncthreads();
@@ -366,43 +562,73 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : 2)) kf_gemv_kernel(co
 
     // ---- epilogue -----------------------------------------------------------------------------------------------------------
     if (!swiglu) {
-        const int rbase = (rb - sg.rb0) * kRowsCta;
-        for (int e = tid; e < p.M * kRowsCta; e += kThreads) {
-            const int m = e >> 7, r = e & 127, row = rbase + r;
+        const GemvSeg& sg = p.seg[segi];
+        const int rbase   = (rb - sg.rb0) * ROWS;
+        for (int e = tid; e < p.M * ROWS; e += kThreads) {
+            const int m = e / ROWS, r = e % ROWS, row = rbase + r;
             if (row >= sg.rows) continue;
             if (p.epilogue == EPI_F32) {  // tensor-parallel partial sums stay fp32 until the all-reduce
-                reinterpret_cast<float*>(sg.y)[(size_t)m * sg.rows + row] = tile[m * kTileStride + r];
+                reinterpret_cast<float*>(sg.y)[(size_t)m * sg.rows + row] = tile[m * TS + r];
                 continue;
             }
-            uint16_t v = f32_to_bf16_bits(tile[m * kTileStride + r]);  // the reference's GEMM writes bf16 (gemm.cu:124-126)
-            if (p.epilogue == EPI_RESIDUAL)                            // then CU_add3 adds the residual in fp32 (packedN.cuh:867-875)
+            uint16_t v = f32_to_bf16_bits(tile[m * TS + r]);  // the reference's GEMM writes bf16 (gemm.cu:124-126)
+            if (p.epilogue == EPI_RESIDUAL)                   // then CU_add3 adds the residual in fp32 (packedN.cuh:867-875)
                 v = f32_to_bf16_bits(bf16_bits_to_f32(p.residual[(size_t)m * sg.rows + row]) + bf16_bits_to_f32(v));
             sg.y[(size_t)m * sg.rows + row] = v;
         }
     } else {
         const int rows = p.seg[0].rows;
-        for (int e = tid; e < p.M * 64; e += kThreads) {
-            const int m = e >> 6, r = e & 63, row = rb * 64 + r;
+        for (int e = tid; e < p.M * HALF; e += kThreads) {
+            const int m = e / HALF, r = e % HALF, row = rb * HALF + r;
             if (row >= rows) continue;
-            const float gt = bf16_bits_to_f32(f32_to_bf16_bits(tile[m * kTileStride + r]));
-            const float up = bf16_bits_to_f32(f32_to_bf16_bits(tile[m * kTileStride + 64 + r]));
+            const float gt = bf16_bits_to_f32(f32_to_bf16_bits(tile[m * TS + r]));
+            const float up = bf16_bits_to_f32(f32_to_bf16_bits(tile[m * TS + HALF + r]));
             p.seg[0].y[(size_t)m * rows + row] = f32_to_bf16_bits((gt * up) / (1.0f + expf(-gt)));  // CU_swiglu_v0, Activation.cu:86-93
         }
     }
 }
 
-template <int FMT, int MODE, int NT, bool M1>
-int launch_one(kf_ctx* ctx, const GemvParams& p, int nsteps_max) {
-    using F = Fmt<FMT>;
-    constexpr int MX = M1 ? 1 : 8 * NT, MP = 8 * NT;
-    size_t xbytes    = (size_t)nsteps_max * F::UNITS * MX * 4 * 16;
-    size_t tilebytes = (size_t)MP * kTileStride * 4;
-    size_t smem      = std::max(xbytes, tilebytes);
-    auto kern        = kf_gemv_kernel<FMT, MODE, NT, M1>;
-    static size_t smem_set = 0;  // per instantiation
-    if (smem > 48 * 1024 && smem > smem_set) {
-        KF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        smem_set = 100 * 1024;
+// ---- host side ------------------------------------------------------------------------------------------------------------------
+constexpr size_t kSmemCap  = 100 * 1024;  // two CTAs per SM
+constexpr size_t kSmemSoft = 73 * 1024;   // three CTAs per SM (24 warps)
+
+struct FmtInfo {
+    int bits, cpb, nch, d1, d2;
+};
+static FmtInfo fmt_info(int fmt) {
+    switch (fmt) {
+        case FMT_Q4: return {Fmt<FMT_Q4>::BITS, Fmt<FMT_Q4>::CPB, Fmt<FMT_Q4>::NCH, Fmt<FMT_Q4>::D1, Fmt<FMT_Q4>::D2};
+        case FMT_Q2: return {Fmt<FMT_Q2>::BITS, Fmt<FMT_Q2>::CPB, Fmt<FMT_Q2>::NCH, Fmt<FMT_Q2>::D1, Fmt<FMT_Q2>::D2};
+        case FMT_Q1: return {Fmt<FMT_Q1>::BITS, Fmt<FMT_Q1>::CPB, Fmt<FMT_Q1>::NCH, Fmt<FMT_Q1>::D1, Fmt<FMT_Q1>::D2};
+        case FMT_F8: return {Fmt<FMT_F8>::BITS, Fmt<FMT_F8>::CPB, Fmt<FMT_F8>::NCH, Fmt<FMT_F8>::D1, Fmt<FMT_F8>::D2};
+        default: return {Fmt<FMT_BF16>::BITS, Fmt<FMT_BF16>::CPB, Fmt<FMT_BF16>::NCH, Fmt<FMT_BF16>::D1, Fmt<FMT_BF16>::D2};
+    }
+}
+static size_t ring_bytes(int fmt, int rt) {
+    const FmtInfo f = fmt_info(fmt);
+    return (size_t)(rt == 2 ? f.d2 : f.d1) * rt * 2 * f.nch * kThreads * f.cpb;
+}
+// shared bytes per k-step: activations + gama
+static size_t step_bytes(int mode, int mx, int rows_cta) {
+    return (size_t)UNITS * mx * 64 + (mode == MODE_PLAIN ? 0 : (size_t)(rows_cta + 1) * 4) + (mode == MODE_FACTOR ? (size_t)mx * 4 : 0);
+}
+
+template <int FMT, int MODE, int NT, bool M1, int RT>
+int launch_one(kf_ctx* ctx, const GemvParams& p0) {
+    constexpr int MX = M1 ? 1 : 8 * NT, MP = 8 * NT, ROWS = 128 * RT;
+    GemvParams p     = p0;
+    size_t head      = (size_t)p.nsteps_max * step_bytes(MODE, MX, ROWS);
+    size_t tilebytes = (size_t)MP * (ROWS + 4) * 4;
+    p.ring_off       = (int)((head + 15) & ~(size_t)15);
+    p.sx_off         = (int)(p.ring_off + ring_bytes(FMT, RT));
+    size_t sxbytes   = MODE == MODE_FACTOR ? (size_t)p.nsteps_max * MX * 4 : 0;
+    size_t smem      = std::max((size_t)p.sx_off + sxbytes, tilebytes);
+    KF_REQUIRE(ctx, smem <= kSmemCap, "internal: k-slice does not fit shared memory");
+    auto kern            = kf_gemv_kernel<FMT, MODE, NT, M1, RT>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        KF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
+        attr_set = true;
     }
     dim3 grid(p.total_rb, p.S);
     kern<<<grid, kThreads, smem, ctx->stream>>>(p);
@@ -411,85 +637,108 @@ int launch_one(kf_ctx* ctx, const GemvParams& p, int nsteps_max) {
 }
 
 template <int FMT, int MODE>
-int launch_nt(kf_ctx* ctx, const GemvParams& p, int nsteps_max) {
-    if (p.M == 1) return launch_one<FMT, MODE, 1, true>(ctx, p, nsteps_max);
-    if (p.M <= 8) return launch_one<FMT, MODE, 1, false>(ctx, p, nsteps_max);
-    if (p.M <= 16) return launch_one<FMT, MODE, 2, false>(ctx, p, nsteps_max);
-    if (p.M <= 32) return launch_one<FMT, MODE, 4, false>(ctx, p, nsteps_max);
-    return launch_one<FMT, MODE, 8, false>(ctx, p, nsteps_max);
+int launch_nt(kf_ctx* ctx, const GemvParams& p, int rt) {
+    if (p.M == 1) return rt == 2 ? launch_one<FMT, MODE, 1, true, 2>(ctx, p) : launch_one<FMT, MODE, 1, true, 1>(ctx, p);
+    if (p.M <= 8) return rt == 2 ? launch_one<FMT, MODE, 1, false, 2>(ctx, p) : launch_one<FMT, MODE, 1, false, 1>(ctx, p);
+    if (p.M <= 16) return launch_one<FMT, MODE, 2, false, 1>(ctx, p);
+    if (p.M <= 32) return launch_one<FMT, MODE, 4, false, 1>(ctx, p);
+    return launch_one<FMT, MODE, 8, false, 1>(ctx, p);
 }
 
-int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual) {
+int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
+                  const void* norm_w, float norm_eps) {
     KF_REQUIRE(ctx, n >= 1 && n <= 3 && M >= 1 && M <= 64 && x, "1..3 weights, 1..64 tokens");
     const int type = w[0].type, K = w[0].cols;
     int fmt, mode;
     switch (type) {
         case KF_T_BF16: fmt = FMT_BF16, mode = MODE_PLAIN; break;
         case KF_T_F8E5M2: fmt = FMT_F8, mode = MODE_PLAIN; break;
-        case KF_T_Q4: fmt = FMT_Q4, mode = w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
-        case KF_T_Q2: fmt = FMT_Q2, mode = w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
+        case KF_T_Q4: fmt = FMT_Q4, mode = !ctx->gemv_exact ? MODE_FACTOR : w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
+        case KF_T_Q2: fmt = FMT_Q2, mode = !ctx->gemv_exact ? MODE_FACTOR : w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
         case KF_T_SIGN: fmt = FMT_Q2, mode = MODE_SCALE; break;
         case KF_T_BINARY: fmt = FMT_Q1, mode = MODE_SCALE; break;
         default: return KF_ERR_UNSUPPORTED;
     }
-    const int kstep = fmt == FMT_BF16 ? 32 : fmt == FMT_F8 ? 64 : 128;
-    KF_REQUIRE(ctx, K % kstep == 0 && K % 8 == 0, "K must be a multiple of the k-step");
+    KF_REQUIRE(ctx, K % KSTEP == 0, "K must be a multiple of 128");
     GemvParams p;
     memset(&p, 0, sizeof(p));
     p.nseg = n, p.x = (const uint16_t*)x, p.residual = (const uint16_t*)residual, p.M = M, p.K = K;
-    p.steps_total = K / kstep, p.qbias = w[0].qbias, p.epilogue = epilogue;
+    p.norm_w = (const uint16_t*)norm_w, p.norm_eps = norm_eps;
+    p.steps_total = K / KSTEP, p.qbias = w[0].qbias, p.epilogue = epilogue;
     p.lop_mask = fmt == FMT_Q4 ? 0x000F000Fu : fmt == FMT_Q2 ? 0x00030003u : 0x00010001u, p.lop_magic = 0x43004300u;
-    int rb = 0;
+    int total_rows = 0;
     for (int i = 0; i < n; i++) {
         KF_REQUIRE(ctx, w[i].type == type && w[i].cols == K && w[i].qbias == w[0].qbias && w[i].group == w[0].group,
                    "fused weights must share type / K / quant card");
-        KF_REQUIRE(ctx, w[i].rows % 16 == 0 && w[i].data_dev && y[i], "rows must be a multiple of 16");
-        p.seg[i].data = (const uint8_t*)w[i].data_dev, p.seg[i].y = (uint16_t*)y[i], p.seg[i].rows = w[i].rows, p.seg[i].rb0 = rb;
-        if (mode != MODE_PLAIN) {
+        KF_REQUIRE(ctx, w[i].rows % 16 == 0 && w[i].rows >= 16 && w[i].data_dev && y[i], "rows must be a multiple of 16");
+        if (mode != MODE_PLAIN)
             KF_REQUIRE(ctx, kf_has_gama(w[i]) && w[i].group >= 128 && (w[i].group & (w[i].group - 1)) == 0 && K % w[i].group == 0,
                        "fused path needs group = 128 * 2^n dividing K");
-            p.seg[i].zero = kf_gama_zero(w[i]), p.seg[i].step = kf_gama_step(w[i]);
-        }
-        rb += (w[i].rows + kRowsCta - 1) / kRowsCta;
+        total_rows += w[i].rows;
     }
     if (mode != MODE_PLAIN) {
         int gs = 0;
         while ((128 << gs) < w[0].group) gs++;
         p.gshift = gs;
     }
-    if (epilogue == EPI_SWIGLU) {
-        KF_REQUIRE(ctx, n == 2 && w[0].rows == w[1].rows, "swiglu needs gate and up of equal shape");
-        rb = (w[0].rows + 63) / 64;
-    }
+    if (epilogue == EPI_SWIGLU) KF_REQUIRE(ctx, n == 2 && w[0].rows == w[1].rows, "swiglu needs gate and up of equal shape");
     if (epilogue == EPI_RESIDUAL) KF_REQUIRE(ctx, n == 1 && residual, "residual epilogue takes one weight");
+
+    // ---- tile shape: 32 rows per warp (RT = 2) when there are enough rows to keep every SM busy, else 16 -------------------------
+    int rt = 1;
+    if (M <= 8 && fmt != FMT_BF16 && fmt != FMT_F8) {
+        rt = 1;  // measured (profiles/r01_gemv_sweep_v4.txt): 16 rows per warp is never slower than 32 on B200
+        (void)total_rows;
+        if (ctx->gemv_variant == 2) rt = 2;
+    }
+    const int rows_cta = 128 * rt;
+    int rb = 0;
+    for (int i = 0; i < n; i++) {
+        p.seg[i].data = (const uint8_t*)w[i].data_dev, p.seg[i].y = (uint16_t*)y[i], p.seg[i].rows = w[i].rows, p.seg[i].rb0 = rb;
+        if (mode != MODE_PLAIN) p.seg[i].zero = kf_gama_zero(w[i]), p.seg[i].step = kf_gama_step(w[i]);
+        rb += (w[i].rows + rows_cta - 1) / rows_cta;
+    }
+    if (epilogue == EPI_SWIGLU) rb = (w[0].rows + rows_cta / 2 - 1) / (rows_cta / 2);
     p.total_rb = rb;
 
-    // ---- k-split heuristic: enough CTAs for ~2 waves of 2 resident CTAs per SM, slices that fit shared memory ----------------
-    const int MXs        = M == 1 ? 1 : (M <= 8 ? 8 : M <= 16 ? 16 : M <= 32 ? 32 : 64);
-    const int units      = fmt == FMT_BF16 ? 1 : fmt == FMT_F8 ? 2 : 4;
-    const size_t stepsm  = (size_t)units * MXs * 64;  // shared bytes per k-step
-    const int max_steps  = (int)std::max<size_t>(1, (96 * 1024) / stepsm);
+    // ---- k-split: pick the S that minimises  waves(S) x (fixed CTA cost + k-steps per CTA)  under the shared-memory budget -------
+    const int MXs      = M == 1 ? 1 : (M <= 8 ? 8 : M <= 16 ? 16 : M <= 32 ? 32 : 64);
+    const size_t stepb = step_bytes(mode, MXs, rows_cta), ringb = ring_bytes(fmt, rt);
+    const int hard_steps = (int)std::max<size_t>(1, (kSmemCap - 256 - ringb) / stepb);
+    const int soft_steps = ringb + 4 * stepb <= kSmemSoft ? (int)((kSmemSoft - ringb) / stepb) : 0;
+    const int S_min      = (p.steps_total + hard_steps - 1) / hard_steps;
     int S                = ctx->gemv_splitk;
     if (S <= 0) {
-        const int target = ctx->sm_count * 4;
-        S                = (target + rb - 1) / rb;
-        const int min_steps = fmt == FMT_BF16 ? 16 : 8;
-        S                = std::min(S, std::max(1, p.steps_total / min_steps));
-        S                = std::min(S, 32);
+        const int per_sm3 = MXs <= 8 ? 3 : (MXs <= 16 ? 2 : 1), per_sm2 = MXs <= 16 ? 2 : 1;
+        double best = 1e30;
+        S           = S_min;
+        for (int cand = S_min; cand <= std::min(p.steps_total, 64); cand++) {
+            const int nst = (p.steps_total + cand - 1) / cand;
+            if (nst < 2 && cand > S_min) break;
+            const int per_sm  = (soft_steps && nst <= soft_steps) ? per_sm3 : per_sm2;
+            const int slots   = ctx->sm_count * per_sm;
+            const int waves   = (rb * cand + slots - 1) / slots;
+            // cost in k-step units: each wave pays a prologue (~6 steps incl. split-K traffic) plus its steps; CTAs sharing an SM
+            // share its issue slots, so a fuller SM is not proportionally faster: weight the per-wave time by occupancy^0.5
+            const double cost = waves * (6.0 + nst) * (per_sm == 3 ? 1.22 : per_sm == 2 ? 1.0 : 0.75);
+            if (cost < best - 1e-9) best = cost, S = cand;
+        }
     }
-    S = std::max(S, (p.steps_total + max_steps - 1) / max_steps);
+    S = std::max(S, S_min);
     S = std::max(1, std::min(S, p.steps_total));
-    p.S = S;
-    const int nsteps_max = (p.steps_total + S - 1) / S;  // floor/ceil slicing never exceeds ceil(steps/S) <= max_steps
+    p.S          = S;
+    p.nsteps_max = (p.steps_total + S - 1) / S;  // floor/ceil slicing never exceeds ceil(steps/S)
     if (S > 1) {
-        int rc = kf_ensure_gemv_ws(ctx, (size_t)S * rb * MXs * kRowsCta * sizeof(float) * (M == 1 ? 8 : 1), rb);
+        int rc = kf_ensure_gemv_ws(ctx, (size_t)S * rb * (M == 1 ? 8 : MXs) * rows_cta * sizeof(float), rb);
         if (rc) return rc;
         p.ws = ctx->gemv_ws, p.cnt = ctx->gemv_cnt;
     }
 #define KF_GEMV_CASE(F, MD) \
-    if (fmt == F && mode == MD) return launch_nt<F, MD>(ctx, p, nsteps_max);
+    if (fmt == F && mode == MD) return launch_nt<F, MD>(ctx, p, rt);
     KF_GEMV_CASE(FMT_Q4, MODE_AFFINE)
     KF_GEMV_CASE(FMT_Q4, MODE_AFFINE_SYM)
+    KF_GEMV_CASE(FMT_Q4, MODE_FACTOR)
+    KF_GEMV_CASE(FMT_Q2, MODE_FACTOR)
     KF_GEMV_CASE(FMT_Q2, MODE_AFFINE)
     KF_GEMV_CASE(FMT_Q2, MODE_AFFINE_SYM)
     KF_GEMV_CASE(FMT_Q2, MODE_SCALE)
@@ -502,6 +751,7 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
 
 }  // namespace
 
-int kf_gemv_small(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual) {
-    return gemv_dispatch(ctx, n, y, w, x, M, epilogue, residual);
+int kf_gemv_small(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
+                  const void* norm_w, float norm_eps) {
+    return gemv_dispatch(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
 }

@@ -30,6 +30,7 @@ struct kf_ctx {
     // tuning
     int gemv_splitk  = 0;
     int gemv_variant = 0;
+    int gemv_exact   = 1;  // 1: in-kernel dequant reproduces the reference's bf16 roundings bit for bit ; 0: factored scale/zero (MODE_FACTOR)
     int attn_split   = 0;
     // tensor parallel
     ncclComm* nccl = nullptr;
@@ -95,7 +96,9 @@ static inline bool kf_has_gama(const kf_tensor_desc& w) { return w.gama_dev || (
 int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters);
 int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes);
 // gemv.cu: skinny path (M <= 64); epilogue 0 none / 1 residual / 2 swiglu(gate = w[0], up = w[1])
-int kf_gemv_small(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual);
+// norm_w != nullptr: x is RMS-normalised (weights norm_w, eps norm_eps) while it is staged, as kf_rmsnorm would have done
+int kf_gemv_small(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
+                  const void* norm_w, float norm_eps);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float bf16_bits_to_f32(uint32_t h) { return __uint_as_float(h << 16); }
@@ -129,6 +132,18 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+// block-wide sum with a fixed reduction order (warp butterflies, then the warps in index order): deterministic, and shared by the
+// stand-alone RMSNorm kernel and the RMSNorm folded into the GEMV so that both produce the same scale bit for bit.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < nw; i++) t += red[i];
+    return t;
 }
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

@@ -4,8 +4,9 @@
 // (gemm_tc.cu) takes over.
 #include "kf_common.cuh"
 
-static int linear_panels(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual) {
-    if (M <= 64) return kf_gemv_small(ctx, n, y, w, x, M, epilogue, residual);
+static int linear_panels(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
+                         const void* norm_w, float norm_eps) {
+    if (M <= 64) return kf_gemv_small(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
     const int K = w[0].cols;
     for (int m0 = 0; m0 < M; m0 += 64) {
         const int mm = M - m0 < 64 ? M - m0 : 64;
@@ -16,7 +17,7 @@ static int linear_panels(kf_ctx* ctx, int n, void* const* y, const kf_tensor_des
         }
         if (epilogue == 2) yy[1] = yy[0];
         const void* res = residual ? (const void*)((const uint16_t*)residual + (size_t)m0 * w[0].rows) : nullptr;
-        int rc = kf_gemv_small(ctx, n, yy, w, (const uint16_t*)x + (size_t)m0 * K, mm, epilogue, res);
+        int rc = kf_gemv_small(ctx, n, yy, w, (const uint16_t*)x + (size_t)m0 * K, mm, epilogue, res, norm_w, norm_eps);
         if (rc) return rc;
     }
     return KF_OK;
@@ -26,15 +27,28 @@ extern "C" int kf_linear(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const vo
     if (!ctx || !y || !w || !x) return KF_ERR_BAD_ARG;
     KF_REQUIRE(ctx, epilogue == KF_EPI_NONE || epilogue == KF_EPI_RESIDUAL || epilogue == KF_EPI_F32, "epilogue");
     void* ys[1] = {y};
-    return linear_panels(ctx, 1, ys, w, x, M, epilogue, residual);
+    return linear_panels(ctx, 1, ys, w, x, M, epilogue, residual, nullptr, 0.f);
 }
 extern "C" int kf_linear_multi(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M) {
     if (!ctx || !y || !w || !x) return KF_ERR_BAD_ARG;
-    return linear_panels(ctx, n, y, w, x, M, 0, nullptr);
+    return linear_panels(ctx, n, y, w, x, M, 0, nullptr, nullptr, 0.f);
 }
 extern "C" int kf_linear_swiglu(kf_ctx* ctx, void* y, const kf_tensor_desc* wg, const kf_tensor_desc* wu, const void* x, int M) {
     if (!ctx || !y || !wg || !wu || !x) return KF_ERR_BAD_ARG;
     kf_tensor_desc w[2] = {*wg, *wu};
     void* ys[2]         = {y, y};
-    return linear_panels(ctx, 2, ys, w, x, M, 2, nullptr);
+    return linear_panels(ctx, 2, ys, w, x, M, 2, nullptr, nullptr, 0.f);
+}
+// RMSNorm folded into the activation staging of the matmul(s) that consume it: the normalised activations are never written to
+// HBM.  mode: 0 = n plain outputs (n <= 3), 2 = SwiGLU(w[0] gate, w[1] up) -> y[0].
+extern "C" int kf_rmsnorm_linear(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, const void* norm_w, float eps, int M,
+                                 int mode) {
+    if (!ctx || !y || !w || !x || !norm_w) return KF_ERR_BAD_ARG;
+    KF_REQUIRE(ctx, mode == 0 || mode == 2, "mode");
+    if (mode == 2) {
+        KF_REQUIRE(ctx, n == 2, "swiglu takes gate and up");
+        void* ys[2] = {y[0], y[0]};
+        return linear_panels(ctx, 2, ys, w, x, M, 2, nullptr, norm_w, eps);
+    }
+    return linear_panels(ctx, n, y, w, x, M, 0, nullptr, norm_w, eps);
 }

@@ -9,16 +9,6 @@
 // ---------------------------------------------------------------------------------------------------------------- RMSNorm
 // rms_norm_kernel / CU_rms_infer (reference src/Device/CUDA/kernel/layernorm.cuh:801-859): y = (x * rsqrt(mean(x^2)+eps)) * w, fp32
 // math, bf16 RN.  The reference runs ONE block for the single decode row; here one block per row (batched decode), 16-byte loads.
-__device__ __forceinline__ float block_sum(float v, float* red) {
-    v = warp_sum(v);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    float t = 0.f;
-    for (int i = 0; i < nw; i++) t += red[i];  // fixed order: deterministic
-    return t;
-}
 __global__ void __launch_bounds__(256) kf_rmsnorm_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ x, const uint16_t* __restrict__ w,
                                                           int dim, float eps) {
     __shared__ float red[32];

@@ -97,10 +97,10 @@ int ROPE::cuInfer(SelfAttention* a, int M) {
 int SelfAttention::cuInfer(void* inpL, int M) {
     Fish* f = hFish;
     std::string* hFishErr = &f->error;
-    KF_TRY(norm.cuFlow(f->xb, inpL, M));
     kf_tensor_desc w3[3] = {Q.w->Desc(), K.w->Desc(), V.w->Desc()};
     void* y3[3]          = {f->q, f->k, f->v};
-    KF_TRY(kf_linear_multi(f->ctx, 3, y3, w3, f->xb, M));  // the three SLP::Forw calls share one launch
+    // norm.cuFlow + the three SLP::Forw calls share one launch; the normalised activations never leave the chip
+    KF_TRY(kf_rmsnorm_linear(f->ctx, 3, y3, w3, inpL, norm.w->data, norm.rms_eps, M, 0));
     KF_TRY(rope.cuInfer(this, M));
     const int lay   = layid - 1;
     const size_t ss = f->seq_mode ? f->cache.seq_stride() : 0;
@@ -120,9 +120,9 @@ int SelfAttention::cuInfer(void* inpL, int M) {
 int FFN::cuInfer(void* inpL, int M) {
     Fish* f = hFish;
     std::string* hFishErr = &f->error;
-    KF_TRY(norm.cuFlow(f->xb, inpL, M));
-    kf_tensor_desc g = gate.w->Desc(), u = up.w->Desc();
-    KF_TRY(kf_linear_swiglu(f->ctx, f->hb, &g, &u, f->xb, M));
+    kf_tensor_desc gu[2] = {gate.w->Desc(), up.w->Desc()};
+    void* y2[2]          = {f->hb, f->hb};
+    KF_TRY(kf_rmsnorm_linear(f->ctx, 2, y2, gu, inpL, norm.w->data, norm.rms_eps, M, 2));  // norm + gate/up + SwiGLU in one launch
     const size_t nE = (size_t)M * f->config.n_embd;
     if (f->tp_world == 1) {
         KF_TRY(down.Forw(inpL, f->hb, M, KF_EPI_RESIDUAL, inpL));
@@ -142,13 +142,14 @@ int TokenEmbed::cuInfer(void* out, int M) {
 int Head4Token::cuInfer_1(void* logits, const void* inp, int M) {
     Fish* f = hFish;
     std::string* hFishErr = &f->error;
-    KF_TRY(norm.cuFlow(f->xb, inp, M));
     kf_tensor_desc d = proj.w->Desc();
     const int W = f->tp_world;
     if (W == 1) {
-        KF_TRY(kf_linear(f->ctx, logits, &d, f->xb, M, KF_EPI_NONE, nullptr));
+        void* y1[1] = {logits};
+        KF_TRY(kf_rmsnorm_linear(f->ctx, 1, y1, &d, inp, norm.w->data, norm.rms_eps, M, 0));  // final norm folded into the lm_head GEMV
         return KF_OK;
     }
+    KF_TRY(norm.cuFlow(f->xb, inp, M));
     const int vl = f->config.vocab / W;
     const typNUMBER tp = proj.w->type;
     const size_t row_bytes = (size_t)((double)d.cols * BitPE(tp) / 8);

@@ -234,6 +234,47 @@ def test_linear_swiglu_fused(ctx, kind):
     assert (fused == want).mean() > 0.999
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("kind", WEIGHT_KINDS, ids=str)
+def test_gemv_tile_variants(ctx, variant, kind):
+    # 16 or 32 rows per warp (RT = 1 / 2), ragged row blocks (N = 400 is neither a multiple of 128 nor of 256), M = 1 and 6
+    N, K = 400, 1024
+    t, wdq = make_weight(ctx, kind, N, K, 321)
+    ctx.set_int("gemv_variant", variant)
+    try:
+        for M in (1, 6):
+            x = rand_bf16(np.random.default_rng(M + variant), (M, K))
+            y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16)
+            _check_linear(y, wdq, x, M, N, K)
+            ks = np.arange(M) * 97 % K
+            x1 = np.zeros((M, K), dtype=np.uint16)
+            x1[np.arange(M), ks] = 0x3F80
+            y1 = kf.linear(ctx, t, ctx.array(x1), M).numpy(np.uint16, (M, N))
+            for m in range(M):
+                assert np.array_equal(ol.bf16_to_f32(y1[m]), ol.bf16_to_f32(wdq[:, ks[m]]))
+    finally:
+        ctx.set_int("gemv_variant", 0)
+
+
+@pytest.mark.parametrize("M", [1, 5, 20])
+def test_rmsnorm_folded_into_linear_is_bit_identical_to_unfused(ctx, M):
+    rng = np.random.default_rng(M)
+    K = 2048
+    x, nw = rand_bf16(rng, (M, K), 2.0), rand_bf16(rng, (K,), 0.5)
+    xd, nwd = ctx.array(x), ctx.array(nw)
+    xn = kf.rmsnorm(ctx, xd, nwd, M, K, 1e-6)
+    ws = [make_weight(ctx, (4, ol.RTN_ASYM), n, K, 500 + i)[0] for i, n in enumerate((512, 128, 128))]
+    want = kf.linear_multi(ctx, ws, xn, M)
+    got = kf.rmsnorm_linear(ctx, ws, xd, nwd, M, 1e-6)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.numpy(np.uint16), b.numpy(np.uint16))
+    wg, wu = make_weight(ctx, (4, ol.RTN_ASYM), 640, K, 600)[0], make_weight(ctx, (4, ol.RTN_ASYM), 640, K, 601)[0]
+    assert np.array_equal(kf.rmsnorm_linear(ctx, [wg, wu], xd, nwd, M, 1e-6, swiglu=True).numpy(np.uint16),
+                          kf.linear_swiglu(ctx, wg, wu, xn, M).numpy(np.uint16))
+    head = make_weight(ctx, "bf16", 1024, K, 700)[0]
+    assert np.array_equal(kf.rmsnorm_linear(ctx, [head], xd, nwd, M, 1e-6)[0].numpy(np.uint16), kf.linear(ctx, head, xn, M).numpy(np.uint16))
+
+
 def test_linear_rejects_bad_shapes(ctx):
     t, _ = make_weight(ctx, (4, ol.RTN_ASYM), 128, 512, 1)
     xd = ctx.array(np.zeros((1, 512), dtype=np.uint16))

@@ -37,12 +37,15 @@ def main():
     ap.add_argument("--types", default="q4,q2t,q1,f8,bf16")
     ap.add_argument("--ms", default="1,16")
     ap.add_argument("--shapes", default="")
+    ap.add_argument("--variants", default="0", help="gemv_variant values: 0 auto, 1 = 16 rows/warp, 2 = 32 rows/warp")
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--out", default="")
+    ap.add_argument("--exact", type=int, default=1, help="gemv_exact knob: 1 = reference-exact in-kernel dequant, 0 = factored scale/zero")
     args = ap.parse_args()
     stream = torch.cuda.Stream()  # a real (non-default) stream shared by torch events and our kernels
     torch.cuda.set_stream(stream)
     ctx = kf.Context(0, stream.cuda_stream)
+    ctx.set_int("gemv_exact", args.exact)
     peak = 6452.8
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -67,8 +70,9 @@ def main():
             for M in [int(m) for m in args.ms.split(",")]:
                 x = kf.fill_normal(ctx, M * K, 7, 1.0)
                 y = ctx.empty(M * N * 2)
-                for sk in [int(s) for s in args.splitk.split(",")]:
+                for sk, variant in [(int(s), int(v)) for s in args.splitk.split(",") for v in args.variants.split(",")]:
                     ctx.set_int("gemv_splitk", sk)
+                    ctx.set_int("gemv_variant", variant)
                     descs = [w.desc() for w in ws]
                     for i in range(3):
                         ctx.check(ctx.lib.kf_linear(ctx.h, y.ptr, C.byref(descs[i % nbuf]), x.ptr, M, 0, None), "kf_linear")
@@ -82,7 +86,7 @@ def main():
                     us = e0.elapsed_time(e1) * 1e3 / args.iters
                     ab = alg_bytes(N, K, bits, M)
                     gbs = ab / (us * 1e-6) / 1e9
-                    rec = {"type": tname, "N": N, "K": K, "M": M, "splitk": sk, "us": round(us, 2), "alg_MB": round(ab / 1e6, 2), "GBps": round(gbs, 1),
+                    rec = {"type": tname, "N": N, "K": K, "M": M, "splitk": sk, "variant": variant, "us": round(us, 2), "alg_MB": round(ab / 1e6, 2), "GBps": round(gbs, 1),
                            "frac_measured": round(gbs / peak, 3), "frac_8TBps": round(gbs / 8000.0, 3), "tflops": round(2.0 * M * N * K / (us * 1e-6) / 1e12, 2),
                            "nbuf": nbuf}
                     print(json.dumps(rec), flush=True)
@@ -90,6 +94,7 @@ def main():
                         out.write(json.dumps(rec) + "\n")
                         out.flush()
                 ctx.set_int("gemv_splitk", 0)
+                ctx.set_int("gemv_variant", 0)
             del ws
     ctx.close()
 
