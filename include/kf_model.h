@@ -70,6 +70,9 @@ int kf_model_set_graphs(kf_model* m, int enable);
 int kf_config_dims(const char* config_json, kf_model_info* out, char** err_out);
 int kf_config_quant_of(const char* config_json, const char* tensor_name, int* type_out, int* group_out, int* mode_out, int* qbias_out,
                        char** err_out);
+/* tensor-parallel shard plan: shape_out[6] = {rows_global, cols_global, rows_local, cols_local, row0, col0} of `tensor_name` on
+ * rank `rank` of `world` (Q/K/V/gate/up split by output rows, O/down by input columns in whole quant groups, the rest replicated) */
+int kf_config_shard_of(const char* config_json, const char* tensor_name, int rank, int world, int* shape_out, char** err_out);
 
 #ifdef __cplusplus
 }

@@ -105,6 +105,7 @@ SIGNATURES = {
     "kf_model_set_graphs": (_I, [_P, _I]),
     "kf_config_dims": (_I, [C.c_char_p, C.POINTER(ModelInfo), C.POINTER(_P)]),
     "kf_config_quant_of": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_P)]),
+    "kf_config_shard_of": (_I, [C.c_char_p, C.c_char_p, _I, _I, C.POINTER(_I), C.POINTER(_P)]),
 }
 
 _lib = None

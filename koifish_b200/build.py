@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
     "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(CSRC, "Device"),
     "-diag-suppress", "177",
-]
+] + os.environ.get("KF_NVCC_DEFS", "").split()  # e.g. KF_NVCC_DEFS=-DKF_GEMV_OCC=4 for tuning experiments
 HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 

@@ -186,7 +186,10 @@ __device__ __forceinline__ void build_a(uint32_t (&a)[4], const uint32_t (&wa)[N
 
 // NT: 8-token column tiles ; M1: single token (activations broadcast) ; RT: 16-row tiles per warp
 template <int FMT, int MODE, int NT, bool M1, int RT>
-__global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? 3 : 2)) kf_gemv_kernel(const GemvParams p) {
+#ifndef KF_GEMV_OCC
+#define KF_GEMV_OCC 3
+#endif
+__global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC : 2)) kf_gemv_kernel(const GemvParams p) {
     using F = Fmt<FMT>;
     constexpr int DEPTH = RT == 2 ? F::D2 : F::D1, CPB = F::CPB, NCH = F::NCH;
     constexpr int TB = fmt_tb(F::BITS), NR = TB / 4;  // bytes / 32-bit registers per thread, row and k-step
@@ -590,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? 3 : 2)) kf_
 
 // ---- host side ------------------------------------------------------------------------------------------------------------------
 constexpr size_t kSmemCap  = 100 * 1024;  // two CTAs per SM
-constexpr size_t kSmemSoft = 73 * 1024;   // three CTAs per SM (24 warps)
+constexpr size_t kSmemSoft = (KF_GEMV_OCC == 4 ? 55 : 73) * 1024;  // KF_GEMV_OCC CTAs per SM
 
 struct FmtInfo {
     int bits, cpb, nch, d1, d2;
@@ -709,7 +712,7 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     const int S_min      = (p.steps_total + hard_steps - 1) / hard_steps;
     int S                = ctx->gemv_splitk;
     if (S <= 0) {
-        const int per_sm3 = MXs <= 8 ? 3 : (MXs <= 16 ? 2 : 1), per_sm2 = MXs <= 16 ? 2 : 1;
+        const int per_sm3 = MXs <= 8 ? KF_GEMV_OCC : (MXs <= 16 ? 2 : 1), per_sm2 = MXs <= 16 ? 2 : 1;
         double best = 1e30;
         S           = S_min;
         for (int cand = S_min; cand <= std::min(p.steps_total, 64); cand++) {
@@ -720,7 +723,7 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
             const int waves   = (rb * cand + slots - 1) / slots;
             // cost in k-step units: each wave pays a prologue (~6 steps incl. split-K traffic) plus its steps; CTAs sharing an SM
             // share its issue slots, so a fuller SM is not proportionally faster: weight the per-wave time by occupancy^0.5
-            const double cost = waves * (6.0 + nst) * (per_sm == 3 ? 1.22 : per_sm == 2 ? 1.0 : 0.75);
+            const double cost = waves * (6.0 + nst) * (per_sm >= 3 ? 1.22 : per_sm == 2 ? 1.0 : 0.75);
             if (cost < best - 1e-9) best = cost, S = cand;
         }
     }

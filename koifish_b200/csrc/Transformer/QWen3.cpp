@@ -301,6 +301,33 @@ static void shard_window(const Fish& f, const std::string& name, int rows_l, int
         *cols_g = cols_l * W, *col0 = r * cols_l;  // row-parallel: split input columns (whole 128-wide groups)
 }
 
+// Host-only shard plan (no device): full shape of a tensor by its HF name and the window rank `rank` of `world` holds.
+// Megatron-style: Q/K/V/gate/up split by output rows (heads / ffn), O/down by input columns in whole 128-wide quant groups, the
+// rest replicated.  Returns false for an unknown name or an indivisible configuration.
+bool ShardPlan(const MODEL_CARD& c, const std::string& name, int rank, int world, int* rows_g, int* cols_g, int* rows_l, int* cols_l, int* row0,
+               int* col0) {
+    if (world < 1 || rank < 0 || rank >= world) return false;
+    if (c.n_head % world || c.n_head_kv % world || c.n_ff % world || (c.n_ff / world) % 128 || ((c.n_head / world) * c.head_dim) % 128) return false;
+    auto has = [&](const char* s) { return name.find(s) != std::string::npos; };
+    const int E = c.n_embd, QD = c.q_dim(), KD = c.kv_dim(), F = c.n_ff;
+    int R, C;
+    if (has("q_proj")) R = QD, C = E;
+    else if (has("k_proj") || has("v_proj")) R = KD, C = E;
+    else if (has("o_proj")) R = E, C = QD;
+    else if (has("gate_proj") || has("up_proj")) R = F, C = E;
+    else if (has("down_proj")) R = E, C = F;
+    else if (has("embed_tokens") || has("lm_head")) R = c.vocab, C = E;
+    else if (has("q_norm") || has("k_norm")) R = 1, C = c.head_dim;
+    else if (has("norm")) R = 1, C = E;
+    else return false;
+    *rows_g = R, *cols_g = C, *rows_l = R, *cols_l = C, *row0 = 0, *col0 = 0;
+    if (has("q_proj") || has("k_proj") || has("v_proj") || has("gate_proj") || has("up_proj"))
+        *rows_l = R / world, *row0 = rank * (R / world);
+    else if (has("o_proj") || has("down_proj"))
+        *cols_l = C / world, *col0 = rank * (C / world);
+    return true;
+}
+
 // huTensor::InitParam random path (reference src/Device/CUDA/huTensor.cu:157-231) + LowBit_worker at load
 int Fish::InitParamRandom() {
     std::string* hFishErr = &error;

@@ -40,6 +40,8 @@ struct MODEL_CARD {
 };
 
 struct Fish;
+bool ShardPlan(const MODEL_CARD& c, const std::string& name, int rank, int world, int* rows_g, int* cols_g, int* rows_l, int* cols_l, int* row0,
+               int* col0);
 
 // ---- neurons --------------------------------------------------------------------------------------------------------------
 struct GeNeuron {

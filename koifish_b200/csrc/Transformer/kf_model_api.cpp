@@ -164,6 +164,22 @@ extern "C" int kf_config_quant_of(const char* config_json, const char* tensor_na
         return KF_ERR_UNSUPPORTED;
     }
 }
+extern "C" int kf_config_shard_of(const char* config_json, const char* tensor_name, int rank, int world, int* shape_out /* rows_g, cols_g, rows_l,
+                                  cols_l, row0, col0 */, char** err_out) {
+    if (err_out) *err_out = nullptr;
+    if (!config_json || !tensor_name || !shape_out) return KF_ERR_BAD_ARG;
+    try {
+        MODEL_CARD c = MODEL_CARD::FromJSON(JSON::parse(config_json));
+        if (!ShardPlan(c, tensor_name, rank, world, shape_out, shape_out + 1, shape_out + 2, shape_out + 3, shape_out + 4, shape_out + 5)) {
+            if (err_out) *err_out = dup_cstr("unknown tensor name or tensor-parallel degree does not divide the model");
+            return KF_ERR_BAD_ARG;
+        }
+        return KF_OK;
+    } catch (const std::exception& e) {
+        if (err_out) *err_out = dup_cstr(e.what());
+        return KF_ERR_BAD_ARG;
+    }
+}
 extern "C" int kf_model_set_graphs(kf_model* m, int enable) {
     if (!m) return KF_ERR_BAD_ARG;
     m->fish->use_graphs = enable != 0;
