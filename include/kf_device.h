@@ -152,6 +152,15 @@ int kf_qknorm_rope_kvappend(kf_ctx* ctx, void* q_dev, const void* k_dev, const v
  *      split-K over the sequence.  M query tokens; token m attends to positions 0..pos[m]. ---- */
 int kf_attn_decode(kf_ctx* ctx, void* out_dev, const void* q_dev, const void* kcache_layer_dev, const void* vcache_layer_dev,
                    const int32_t* pos_dev, int M, int n_head, int n_kv, int head_dim, int max_seq, int max_pos_hint, size_t seq_stride);
+/* ---- ROPE::cuInfer + the three attention kernels of SelfAttention::cuInfer (src/Device/CUDA/QKV.cu:660-674) in ONE launch for decode:
+ *      QK-norm + RoPE of q and of the current k in registers, K / V appended at pos, split-K attention over the cache, slices merged
+ *      by the last CTA.  Same arithmetic and rounding points as kf_qknorm_rope_kvappend followed by kf_attn_decode.  Precondition:
+ *      M == 1, or the M tokens belong to M different sequences (seq_stride > 0).  q_dev is NOT updated (the reference's in-place
+ *      normalised q is only ever consumed by this attention). ---- */
+int kf_qkv_attention(kf_ctx* ctx, void* out_dev, const void* q_dev, const void* k_dev, const void* v_dev, const void* qnorm_w_dev,
+                     const void* knorm_w_dev, void* kcache_layer_dev, void* vcache_layer_dev, const void* rope_table_dev,
+                     const int32_t* pos_dev, int M, int n_head, int n_kv, int head_dim, int max_seq, float eps, size_t seq_stride,
+                     int max_pos_hint);
 /* ---- CU_swiglu_v0 (Activation.cu:86-93), CU_add3 (packedN.cuh:867-875) as stand-alone ops ---- */
 int kf_swiglu(kf_ctx* ctx, void* out_dev, const void* gate_dev, const void* up_dev, size_t n);
 int kf_add(kf_ctx* ctx, void* out_dev, const void* a_dev, const void* b_dev, size_t n);

@@ -236,6 +236,15 @@ def attn_decode(ctx, q, kcache, vcache, pos, M, n_head, n_kv, hd, max_seq, max_p
     return out
 
 
+def qkv_attention(ctx, q, k, v, qw, kw, kcache, vcache, table, pos, M, n_head, n_kv, hd, max_seq, max_pos_hint, eps=1e-6, seq_stride=0):
+    """QK-norm + RoPE + KV append + split-K attention in one launch (decode: one sequence per token)"""
+    out = ctx.empty(M * n_head * hd * 2)
+    ctx.check(ctx.lib.kf_qkv_attention(ctx.h, out.ptr, q.ptr, k.ptr, v.ptr, qw.ptr if qw is not None else None, kw.ptr if kw is not None else None,
+                                       kcache.ptr, vcache.ptr, table.ptr, pos.ptr, M, n_head, n_kv, hd, max_seq, eps, seq_stride, max_pos_hint),
+              "kf_qkv_attention")
+    return out
+
+
 def swiglu(ctx, g, u, n):
     out = ctx.empty(n * 2)
     ctx.check(ctx.lib.kf_swiglu(ctx.h, out.ptr, g.ptr, u.ptr, n), "kf_swiglu")

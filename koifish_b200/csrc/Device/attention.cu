@@ -115,7 +115,196 @@ __global__ void kf_attn_combine_kernel(uint16_t* __restrict__ out, const float* 
     }
     out[((size_t)m * n_head + h) * HD + d] = f32_to_bf16_bits(o * (1.0f / L_));
 }
+// ---- one launch for ROPE::cuInfer + the three attention kernels (decode: every token of the launch belongs to its own sequence) ----
+// Each CTA (head h, token m, split) re-derives the normalised + rotated q of its head and the k / v of the current position in
+// registers (128 elements: cheaper than a launch), attends to the cached positions < pos of its slice plus -- in the last slice --
+// the current position straight from registers, and the last CTA to arrive for (m, h) merges the slices in fixed order.  The K / V
+// rows of position pos are written to the cache by one designated CTA per kv head; nobody reads row pos from the cache here.
+template <int DPL>
+__device__ __forceinline__ void norm_rope_row(float (&o)[DPL], const uint16_t* src, const uint16_t* nw, const float2* cs_row, int lane, float eps) {
+    constexpr int HD = DPL * 32;
+    float x[DPL];
+    load_row<DPL>(x, src + lane * DPL);
+    if (nw) {
+        float ss = 0.f;
+#pragma unroll
+        for (int d = 0; d < DPL; d++) ss = fmaf(x[d], x[d], ss);
+        ss            = warp_sum(ss);
+        const float s = 1.0f / sqrtf(fmaf(ss, 1.0f / (float)HD, eps));
+        float w[DPL];
+        load_row<DPL>(w, nw + lane * DPL);
+#pragma unroll
+        for (int d = 0; d < DPL; d++) x[d] = bf16_bits_to_f32(f32_to_bf16_bits((x[d] * s) * w[d]));  // the norm kernel's bf16 output
+    }
+    // half-split rotation: dim j pairs with j + HD/2, held by lane ^ 16
+#pragma unroll
+    for (int d = 0; d < DPL; d++) {
+        const float other = __shfl_xor_sync(0xffffffffu, x[d], 16);
+        const int j       = (lane & 15) * DPL + d;
+        const float2 cs   = cs_row[j];
+        const float r     = lane < 16 ? fmaf(x[d], cs.x, -(other * cs.y)) : fmaf(other, cs.y, x[d] * cs.x);
+        o[d]              = bf16_bits_to_f32(f32_to_bf16_bits(r));
+    }
+}
+
+template <int DPL>
+__global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_fused_kernel(uint16_t* __restrict__ out, float* __restrict__ ws, unsigned* __restrict__ cnt,
+                                                                        const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
+                                                                        const uint16_t* __restrict__ v, const uint16_t* __restrict__ qw,
+                                                                        const uint16_t* __restrict__ kw, uint16_t* __restrict__ kc,
+                                                                        uint16_t* __restrict__ vc, const float2* __restrict__ table,
+                                                                        const int32_t* __restrict__ pos_dev, int n_head, int n_kv, int nsplit,
+                                                                        float sqrt_hd, float eps, size_t seq_stride) {
+    constexpr int HD = DPL * 32;
+    __shared__ float s_acc[kAttnWarps][HD];
+    __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
+    __shared__ int s_last;
+    const int h = blockIdx.x, m = blockIdx.y, split = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = n_head / n_kv, kvh = h / group, kv_dim = n_kv * HD;
+    kf_grid_launch_dependents();
+    kf_grid_dependency_wait();  // q / k / v come from the QKV GEMV right before us
+    const int pos = pos_dev[m], len = pos + 1;
+    const int t0 = (int)(((long long)split * len) / nsplit), t1 = (int)(((long long)(split + 1) * len) / nsplit);
+    const float2* cs_row = table + (size_t)pos * (HD / 2);
+
+    float qf[DPL], knew[DPL], vnew[DPL];
+    norm_rope_row<DPL>(qf, q + ((size_t)m * n_head + h) * HD, qw, cs_row, lane, eps);
+    const bool has_new = t1 == len;  // the last slice owns the current position
+    if (has_new) {
+        norm_rope_row<DPL>(knew, k + ((size_t)m * n_kv + kvh) * HD, kw, cs_row, lane, eps);
+        load_row<DPL>(vnew, v + ((size_t)m * n_kv + kvh) * HD + lane * DPL);
+        if (h % group == 0 && warp == 0) {  // append K / V of this kv head at row pos (KVCache, Cache.cpp:43-58)
+            uint16_t* kd = kc + (size_t)m * seq_stride + (size_t)pos * kv_dim + (size_t)kvh * HD + lane * DPL;
+            uint16_t* vd = vc + (size_t)m * seq_stride + (size_t)pos * kv_dim + (size_t)kvh * HD + lane * DPL;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) kd[d] = f32_to_bf16_bits(knew[d]), vd[d] = f32_to_bf16_bits(vnew[d]);
+        }
+    }
+    float mx = -INFINITY, l = 0.f, acc[DPL];
+#pragma unroll
+    for (int d = 0; d < DPL; d++) acc[d] = 0.f;
+    const uint16_t* kbase = kc + (size_t)m * seq_stride + (size_t)kvh * HD + lane * DPL;
+    const uint16_t* vbase = vc + (size_t)m * seq_stride + (size_t)kvh * HD + lane * DPL;
+    for (int t = t0 + warp; t < t1; t += kAttnWarps) {
+        float kf[DPL], vf[DPL];
+        if (t == pos) {
+#pragma unroll
+            for (int d = 0; d < DPL; d++) kf[d] = knew[d], vf[d] = vnew[d];
+        } else {
+            load_row<DPL>(kf, kbase + (size_t)t * kv_dim);
+            load_row<DPL>(vf, vbase + (size_t)t * kv_dim);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < DPL; d++) s = fmaf(qf[d], kf[d], s);
+        s = warp_sum(s) / sqrt_hd;
+        const float mn = fmaxf(mx, s);
+        const float c  = expf(mx - mn);
+        const float p  = expf(s - mn);
+        l = l * c + p;
+#pragma unroll
+        for (int d = 0; d < DPL; d++) acc[d] = fmaf(p, vf[d], acc[d] * c);
+        mx = mn;
+    }
+#pragma unroll
+    for (int d = 0; d < DPL; d++) s_acc[warp][lane * DPL + d] = acc[d];
+    if (lane == 0) s_m[warp] = mx, s_l[warp] = l;
+    __syncthreads();
+    float M_ = -INFINITY, L_ = 0.f, o[DPL];
+    if (warp == 0) {
+#pragma unroll
+        for (int w = 0; w < kAttnWarps; w++) M_ = fmaxf(M_, s_m[w]);
+#pragma unroll
+        for (int d = 0; d < DPL; d++) o[d] = 0.f;
+#pragma unroll
+        for (int w = 0; w < kAttnWarps; w++) {
+            const float c = s_m[w] == -INFINITY ? 0.f : expf(s_m[w] - M_);
+            L_ += s_l[w] * c;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) o[d] = fmaf(s_acc[w][lane * DPL + d], c, o[d]);
+        }
+        if (nsplit == 1) {
+            const float inv = 1.0f / L_;
+            uint16_t* op    = out + ((size_t)m * n_head + h) * HD + lane * DPL;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) op[d] = f32_to_bf16_bits(o[d] * inv);
+        } else {
+            float* wp = ws + (((size_t)m * n_head + h) * nsplit + split) * (HD + 2);
+#pragma unroll
+            for (int d = 0; d < DPL; d++) __stcg(wp + lane * DPL + d, o[d]);
+            if (lane == 0) __stcg(wp + HD, M_), __stcg(wp + HD + 1, L_);
+        }
+    }
+    if (nsplit == 1) return;
+    // last CTA of (m, h) merges the slices in split order (deterministic)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(cnt + (size_t)m * n_head + h, 1u);
+        s_last              = prev == (unsigned)(nsplit - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (warp == 0) {
+        const float* wp = ws + ((size_t)m * n_head + h) * nsplit * (HD + 2);
+        float Mx = -INFINITY;
+        for (int s = 0; s < nsplit; s++) Mx = fmaxf(Mx, __ldcg(wp + s * (HD + 2) + HD));
+        float Ls = 0.f, oo[DPL];
+#pragma unroll
+        for (int d = 0; d < DPL; d++) oo[d] = 0.f;
+        for (int s = 0; s < nsplit; s++) {
+            const float ms = __ldcg(wp + s * (HD + 2) + HD);
+            const float c  = ms == -INFINITY ? 0.f : expf(ms - Mx);
+            Ls += __ldcg(wp + s * (HD + 2) + HD + 1) * c;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) oo[d] = fmaf(__ldcg(wp + s * (HD + 2) + lane * DPL + d), c, oo[d]);
+        }
+        const float inv = 1.0f / Ls;
+        uint16_t* op    = out + ((size_t)m * n_head + h) * HD + lane * DPL;
+#pragma unroll
+        for (int d = 0; d < DPL; d++) op[d] = f32_to_bf16_bits(oo[d] * inv);
+        if (lane == 0) cnt[(size_t)m * n_head + h] = 0u;  // self-reset
+    }
+}
 }  // namespace
+
+// ROPE::cuInfer (rope.cu:645-672) + attention_qk / softmax / attention_v (operator.cuh:573-668) of SelfAttention::cuInfer (QKV.cu:660-674)
+// in ONE launch.  Precondition: the M tokens belong to M different sequences (seq_stride = per-sequence cache stride) or M == 1.
+extern "C" int kf_qkv_attention(kf_ctx* ctx, void* out, const void* q, const void* k, const void* v, const void* qw, const void* kw, void* kc,
+                                void* vc, const void* table, const int32_t* pos_dev, int M, int n_head, int n_kv, int hd, int max_seq,
+                                float eps, size_t seq_stride, int max_pos_hint) {
+    if (!ctx || !out || !q || !k || !v || !kc || !vc || !table || !pos_dev) return KF_ERR_BAD_ARG;
+    KF_REQUIRE(ctx, (hd == 128 || hd == 64) && n_head % n_kv == 0 && M >= 1 && max_seq >= 1, "head_dim 64/128, GQA");
+    KF_REQUIRE(ctx, M == 1 || seq_stride > 0, "the fused path needs one sequence per token (use kf_qknorm_rope_kvappend + kf_attn_decode for panels)");
+    int nsplit = ctx->attn_split;
+    if (nsplit <= 0) {
+        const int len = std::max(1, std::min(max_seq, max_pos_hint + 1));
+        nsplit        = (2 * ctx->sm_count + n_head * M - 1) / (n_head * M);
+        nsplit        = std::min(nsplit, std::max(1, len / (kAttnWarps * 16)));
+        nsplit        = std::max(1, std::min(nsplit, 64));
+    }
+    float* ws = nullptr;
+    if (nsplit > 1) {
+        int rc = kf_ensure_attn_ws(ctx, (size_t)M * n_head * nsplit * (hd + 2) * sizeof(float));
+        if (!rc) rc = kf_ensure_attn_cnt(ctx, M * n_head);
+        if (rc) return rc;
+        ws = ctx->attn_ws;
+    }
+    dim3 grid(n_head, M, nsplit);
+    const float sq = sqrtf((float)hd);
+    if (hd == 128)
+        KF_CUDA(ctx, kf_launch_pdl(ctx, kf_attn_fused_kernel<4>, grid, dim3(kAttnWarps * 32), 0, (uint16_t*)out, ws, ctx->attn_cnt, (const uint16_t*)q,
+                                   (const uint16_t*)k, (const uint16_t*)v, (const uint16_t*)qw, (const uint16_t*)kw, (uint16_t*)kc, (uint16_t*)vc,
+                                   (const float2*)table, pos_dev, n_head, n_kv, nsplit, sq, eps, seq_stride));
+    else
+        KF_CUDA(ctx, kf_launch_pdl(ctx, kf_attn_fused_kernel<2>, grid, dim3(kAttnWarps * 32), 0, (uint16_t*)out, ws, ctx->attn_cnt, (const uint16_t*)q,
+                                   (const uint16_t*)k, (const uint16_t*)v, (const uint16_t*)qw, (const uint16_t*)kw, (uint16_t*)kc, (uint16_t*)vc,
+                                   (const float2*)table, pos_dev, n_head, n_kv, nsplit, sq, eps, seq_stride));
+    KF_LAUNCH_CHECK(ctx);
+    return KF_OK;
+}
 
 extern "C" int kf_attn_decode(kf_ctx* ctx, void* out, const void* q, const void* kc, const void* vc, const int32_t* pos_dev, int M, int n_head,
                               int n_kv, int hd, int max_seq, int max_pos_hint, size_t seq_stride) {

@@ -94,6 +94,8 @@ extern "C" int kf_ctx_destroy(kf_ctx* ctx) {
         cudaFree(ctx->gemv_cnt);
     if (ctx->attn_ws)
         cudaFree(ctx->attn_ws);
+    if (ctx->attn_cnt)
+        cudaFree(ctx->attn_cnt);
     if (ctx->own_stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -118,6 +120,8 @@ extern "C" int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value) {
         ctx->gemv_variant = value;
     else if (!strcmp(key, "gemv_exact"))
         ctx->gemv_exact = value;
+    else if (!strcmp(key, "pdl"))
+        ctx->pdl = value;
     else if (!strcmp(key, "attn_split"))
         ctx->attn_split = value;
     else
@@ -158,6 +162,21 @@ int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes) {
         ctx->attn_ws = nullptr, ctx->attn_ws_bytes = 0;
         KF_CUDA(ctx, cudaMalloc(&ctx->attn_ws, bytes * 2));
         ctx->attn_ws_bytes = bytes * 2;
+    }
+    return KF_OK;
+}
+
+int kf_ensure_attn_cnt(kf_ctx* ctx, int counters) {
+    if (counters > ctx->attn_cnt_n) {
+        KF_REQUIRE(ctx, !ctx->capturing, "attention counters must be sized before graph capture");
+        KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->attn_cnt)
+            cudaFree(ctx->attn_cnt);
+        ctx->attn_cnt = nullptr, ctx->attn_cnt_n = 0;
+        const int want = counters * 2 + 256;
+        KF_CUDA(ctx, cudaMalloc(&ctx->attn_cnt, sizeof(unsigned) * want));
+        KF_CUDA(ctx, cudaMemsetAsync(ctx->attn_cnt, 0, sizeof(unsigned) * want, ctx->stream));
+        ctx->attn_cnt_n = want;
     }
     return KF_OK;
 }

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int rb = blockIdx.x, split = blockIdx.y;
     const bool swiglu = p.epilogue == EPI_SWIGLU;
+    kf_grid_launch_dependents();  // the next kernel of the stream may start its own weight prefetch as soon as all our CTAs are running
 
     // ---- which rows does this CTA / warp own? -------------------------------------------------------------------------------
     int segi = 0;
@@ -311,6 +312,11 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
             }
         }
     }
+
+    // ---- everything above touched only the weights.  From here on the kernel reads what its predecessor in the stream wrote (x,
+    //      residual) and writes buffers the predecessor may still be using (split-K workspace, y): wait for it to finish.  Under
+    //      programmatic dependent launch this CTA may have been running for a while already, with its weight stream in flight -------
+    kf_grid_dependency_wait();
 
     // ---- optional fused RMSNorm: the same arithmetic, in the same order, as kf_rmsnorm_kernel (ops.cu) --------------------------
     if (p.norm_w) {
@@ -634,7 +640,7 @@ int launch_one(kf_ctx* ctx, const GemvParams& p0) {
         attr_set = true;
     }
     dim3 grid(p.total_rb, p.S);
-    kern<<<grid, kThreads, smem, ctx->stream>>>(p);
+    KF_CUDA(ctx, kf_launch_pdl(ctx, kern, grid, dim3(kThreads), smem, p));
     KF_LAUNCH_CHECK(ctx);
     return KF_OK;
 }

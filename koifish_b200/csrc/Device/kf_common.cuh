@@ -27,6 +27,9 @@ struct kf_ctx {
     // attention split workspace
     float* attn_ws       = nullptr;
     size_t attn_ws_bytes = 0;
+    unsigned* attn_cnt   = nullptr;  // per (token, head) arrival counters of the fused attention (self-resetting)
+    int attn_cnt_n       = 0;
+    int pdl              = 1;        // programmatic dependent launch between consecutive kernels of a decode step
     // tuning
     int gemv_splitk  = 0;
     int gemv_variant = 0;
@@ -95,6 +98,24 @@ static inline bool kf_has_gama(const kf_tensor_desc& w) { return w.gama_dev || (
 
 int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters);
 int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes);
+int kf_ensure_attn_cnt(kf_ctx* ctx, int counters);
+
+#ifdef __CUDACC__
+// Launch with the programmatic-dependent-launch attribute (when ctx->pdl): the kernel may start while its predecessor in the stream
+// is still draining; it must execute kf_grid_dependency_wait() before touching anything the predecessor writes.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t kf_launch_pdl(kf_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = ctx->pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+__device__ __forceinline__ void kf_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void kf_grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 // gemv.cu: skinny path (M <= 64); epilogue 0 none / 1 residual / 2 swiglu(gate = w[0], up = w[1])
 // norm_w != nullptr: x is RMS-normalised (weights norm_w, eps norm_eps) while it is staged, as kf_rmsnorm would have done
 int kf_gemv_small(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,

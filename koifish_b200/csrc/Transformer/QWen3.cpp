@@ -101,11 +101,17 @@ int SelfAttention::cuInfer(void* inpL, int M) {
     void* y3[3]          = {f->q, f->k, f->v};
     // norm.cuFlow + the three SLP::Forw calls share one launch; the normalised activations never leave the chip
     KF_TRY(kf_rmsnorm_linear(f->ctx, 3, y3, w3, inpL, norm.w->data, norm.rms_eps, M, 0));
-    KF_TRY(rope.cuInfer(this, M));
     const int lay   = layid - 1;
     const size_t ss = f->seq_mode ? f->cache.seq_stride() : 0;
-    KF_TRY(kf_attn_decode(f->ctx, f->att, f->q, f->cache.Get(KVCache::KV_KEY, lay), f->cache.Get(KVCache::KV_VAL, lay), f->d_pos, M, n_head,
-                          n_head_kv, head_dim, f->cache.max_seq, f->attn_hint, ss));
+    if (M == 1 || f->seq_mode) {  // decode: rope->cuInfer + the attention kernels in one launch
+        KF_TRY(kf_qkv_attention(f->ctx, f->att, f->q, f->k, f->v, rope.q_norm ? rope.q_norm->data : nullptr,
+                                rope.k_norm ? rope.k_norm->data : nullptr, f->cache.Get(KVCache::KV_KEY, lay), f->cache.Get(KVCache::KV_VAL, lay),
+                                rope.table, f->d_pos, M, n_head, n_head_kv, head_dim, f->cache.max_seq, 1e-6f, ss, f->attn_hint));
+    } else {  // prefill panel: the tokens attend to each other's fresh K/V rows, so the append must complete first
+        KF_TRY(rope.cuInfer(this, M));
+        KF_TRY(kf_attn_decode(f->ctx, f->att, f->q, f->cache.Get(KVCache::KV_KEY, lay), f->cache.Get(KVCache::KV_VAL, lay), f->d_pos, M, n_head,
+                              n_head_kv, head_dim, f->cache.max_seq, f->attn_hint, ss));
+    }
     const size_t nE = (size_t)M * f->config.n_embd;
     if (f->tp_world == 1) {
         KF_TRY(proj_cat.Forw(inpL, f->att, M, KF_EPI_RESIDUAL, inpL));  // out = residual + proj (CU_add3, QKV.cu:682-688)

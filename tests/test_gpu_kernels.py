@@ -392,6 +392,47 @@ def test_attention_batched_sequences_and_prefill_panel(ctx):
         assert np.allclose(ol.bf16_to_f32(got[m]), want, rtol=2.0 ** -6, atol=4e-3)
 
 
+@pytest.mark.parametrize("hd,n_head,n_kv", [(128, 16, 8), (128, 64, 8), (64, 4, 2)])
+@pytest.mark.parametrize("split", [0, 1, 3])
+def test_fused_qkv_attention_equals_unfused_path(ctx, hd, n_head, n_kv, split):
+    rng = np.random.default_rng(hd + n_head)
+    M, max_seq, theta = 3, 256, 1e6
+    pos = np.array([0, 37, 255], dtype=np.int32)
+    q, k, v = rand_bf16(rng, (M, n_head * hd)), rand_bf16(rng, (M, n_kv * hd)), rand_bf16(rng, (M, n_kv * hd))
+    qw, kw = rand_bf16(rng, (hd,), 0.3), rand_bf16(rng, (hd,), 0.3)
+    kc0, vc0 = rand_bf16(rng, (M, max_seq, n_kv * hd)), rand_bf16(rng, (M, max_seq, n_kv * hd))
+    table = kf.rope_table(ctx, max_seq, hd, theta)
+    stride = max_seq * n_kv * hd
+    posd = ctx.array(pos)
+    # unfused reference path
+    qd, kc, vc = ctx.array(q), ctx.array(kc0), ctx.array(vc0)
+    kf.qknorm_rope_kvappend(ctx, qd, ctx.array(k), ctx.array(v), ctx.array(qw), ctx.array(kw), kc, vc, table, posd, M, n_head, n_kv, hd, max_seq,
+                            seq_stride=stride)
+    want = kf.attn_decode(ctx, qd, kc, vc, posd, M, n_head, n_kv, hd, max_seq, 255, seq_stride=stride).numpy(np.uint16)
+    # fused
+    kc2, vc2 = ctx.array(kc0), ctx.array(vc0)
+    ctx.set_int("attn_split", split)
+    try:
+        got = kf.qkv_attention(ctx, ctx.array(q), ctx.array(k), ctx.array(v), ctx.array(qw), ctx.array(kw), kc2, vc2, table, posd, M, n_head, n_kv,
+                               hd, max_seq, 255, seq_stride=stride).numpy(np.uint16)
+    finally:
+        ctx.set_int("attn_split", 0)
+    g, w = ol.bf16_to_f32(got), ol.bf16_to_f32(want)
+    assert np.allclose(g, w, rtol=2.0 ** -6, atol=4e-3), np.abs(g - w).max()
+    assert np.array_equal(vc2.numpy(np.uint16), vc.numpy(np.uint16))          # V rows are plain copies
+    kd = np.abs(ol.bf16_to_f32(kc2.numpy(np.uint16)) - ol.bf16_to_f32(kc.numpy(np.uint16)))
+    assert kd.max() <= 4e-2 and (kc2.numpy(np.uint16) == kc.numpy(np.uint16)).mean() > 0.999  # K rows: same formula, other sum order
+    # the oracle agrees as well
+    for m in range(M):
+        kco, vco = kc.numpy(np.uint16).reshape(M, max_seq, -1)[m], vc.numpy(np.uint16).reshape(M, max_seq, -1)[m]
+        qn = ol.rope(ol.rmsnorm(q[m].reshape(n_head, hd), qw, n_head, hd, 1e-6), n_head, hd, int(pos[m]), theta)
+        wo = ol.bf16_to_f32(ol.attention_decode(qn, kco, vco, int(pos[m]), n_head, n_kv, hd, 0)).reshape(-1)
+        assert np.allclose(g.reshape(M, -1)[m], wo, rtol=2.0 ** -6, atol=6e-3)
+    with pytest.raises(kf.KoifishError):  # several tokens of ONE sequence must use the two-step path
+        kf.qkv_attention(ctx, ctx.array(q), ctx.array(k), ctx.array(v), ctx.array(qw), ctx.array(kw), kc2, vc2, table, posd, M, n_head, n_kv, hd,
+                         max_seq, 255, seq_stride=0)
+
+
 def test_swiglu_add_embed_argmax(ctx):
     rng = np.random.default_rng(31)
     n = 5000
