@@ -205,6 +205,9 @@ def main():
     stream = torch.cuda.Stream()          # a real (non-default) stream: torch events and our kernels share it
     torch.cuda.set_stream(stream)
     ctx = kf.Context(local, stream.cuda_stream)
+    for knob in ("attn_split", "gemv_splitk", "pdl", "gemv_exact"):  # tuning experiments only, e.g. KF_ATTN_SPLIT=16
+        if os.environ.get("KF_" + knob.upper()):
+            ctx.set_int(knob, int(os.environ["KF_" + knob.upper()]))
     if world > 1:
         idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -245,10 +248,17 @@ def main():
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    profiling = bool(os.environ.get("KF_PROFILE"))  # ncu --profile-from-start off: capture exactly the timed decode steps
+    if profiling:
+        model.set_graphs(False)                      # individual launches instead of one graph node
+        torch.cuda.profiler.start()
     e0.record(stream)
     model.decode_loop(args.steps, 1)
     e1.record(stream)
     barrier()
+    if profiling:
+        torch.cuda.profiler.stop()
+        model.set_graphs(True)
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     launches = ctx.launches - l0
     if world > 1:

@@ -15,6 +15,7 @@
 
 namespace {
 constexpr int kAttnWarps = 4;
+constexpr int kTokBatch  = 8;  // cache rows in flight per warp (fused kernel: the first batch is requested before the dependency wait)
 
 template <int DPL>  // dims per lane: 4 (hd 128) or 2 (hd 64)
 __device__ __forceinline__ void load_row(float (&f)[DPL], const uint16_t* p) {
@@ -50,21 +51,38 @@ __global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_decode_kernel(uint16_
 
     const uint16_t* kbase = kc + (size_t)m * seq_stride + (size_t)kvh * HD + lane * DPL;
     const uint16_t* vbase = vc + (size_t)m * seq_stride + (size_t)kvh * HD + lane * DPL;
-    for (int t = t0 + warp; t < t1; t += kAttnWarps) {
-        float kf[DPL], vf[DPL];
-        load_row<DPL>(kf, kbase + (size_t)t * kv_dim);
-        load_row<DPL>(vf, vbase + (size_t)t * kv_dim);
-        float s = 0.f;
+    // kTokBatch rows of K and V are requested before any of them is used: the loop is latency bound otherwise
+    for (int tb = t0 + warp * kTokBatch; tb < t1; tb += kAttnWarps * kTokBatch) {
+        float kf[kTokBatch][DPL], vf[kTokBatch][DPL];
 #pragma unroll
-        for (int d = 0; d < DPL; d++) s = fmaf(qf[d], kf[d], s);
-        s = warp_sum(s) / sqrt_hd;  // the reference divides (operator.cuh:630)
-        const float mn = fmaxf(mx, s);
-        const float c  = expf(mx - mn);  // 0 on the first token (mx = -inf)
-        const float p  = expf(s - mn);
-        l = l * c + p;
+        for (int u = 0; u < kTokBatch; u++) {
+            const int t = min(tb + u, t1 - 1);  // clamped rows are loaded but not used
+            load_row<DPL>(kf[u], kbase + (size_t)t * kv_dim);
+            load_row<DPL>(vf[u], vbase + (size_t)t * kv_dim);
+        }
+        float s[kTokBatch];
 #pragma unroll
-        for (int d = 0; d < DPL; d++) acc[d] = fmaf(p, vf[d], acc[d] * c);
-        mx = mn;
+        for (int u = 0; u < kTokBatch; u++) {
+            s[u] = 0.f;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) s[u] = fmaf(qf[d], kf[u][d], s[u]);
+        }
+#pragma unroll
+        for (int o_ = 16; o_ > 0; o_ >>= 1)
+#pragma unroll
+            for (int u = 0; u < kTokBatch; u++) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o_);
+#pragma unroll
+        for (int u = 0; u < kTokBatch; u++) {
+            if (tb + u >= t1) break;
+            const float sc = s[u] / sqrt_hd;  // the reference divides (operator.cuh:630)
+            const float mn = fmaxf(mx, sc);
+            const float c  = expf(mx - mn);  // 0 on the first token (mx = -inf)
+            const float p  = expf(sc - mn);
+            l = l * c + p;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) acc[d] = fmaf(p, vf[u][d], acc[d] * c);
+            mx = mn;
+        }
     }
     // merge the warps of this CTA (fixed order)
 #pragma unroll
@@ -163,10 +181,28 @@ __global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_fused_kernel(uint16_t
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = n_head / n_kv, kvh = h / group, kv_dim = n_kv * HD;
     kf_grid_launch_dependents();
-    kf_grid_dependency_wait();  // q / k / v come from the QKV GEMV right before us
+    // Everything up to the wait is independent of the QKV GEMV that precedes this kernel: the position, the slice and the FIRST batch
+    // of cached K / V rows (rows < pos were written by earlier tokens).  Under programmatic dependent launch these loads overlap the
+    // predecessor's tail.
     const int pos = pos_dev[m], len = pos + 1;
     const int t0 = (int)(((long long)split * len) / nsplit), t1 = (int)(((long long)(split + 1) * len) / nsplit);
-    const float2* cs_row = table + (size_t)pos * (HD / 2);
+    const float2* cs_row  = table + (size_t)pos * (HD / 2);
+    const uint16_t* kbase = kc + (size_t)m * seq_stride + (size_t)kvh * HD + lane * DPL;
+    const uint16_t* vbase = vc + (size_t)m * seq_stride + (size_t)kvh * HD + lane * DPL;
+    float kf[kTokBatch][DPL], vf[kTokBatch][DPL];
+    auto load_batch = [&](int tb_) {
+#pragma unroll
+        for (int u = 0; u < kTokBatch; u++) {
+            const int t = tb_ + u;
+            if (t < t1 && t != pos) {
+                load_row<DPL>(kf[u], kbase + (size_t)t * kv_dim);
+                load_row<DPL>(vf[u], vbase + (size_t)t * kv_dim);
+            }
+        }
+    };
+    int tb = t0 + warp * kTokBatch;
+    if (tb < t1) load_batch(tb);
+    kf_grid_dependency_wait();  // q / k / v come from the QKV GEMV right before us
 
     float qf[DPL], knew[DPL], vnew[DPL];
     norm_rope_row<DPL>(qf, q + ((size_t)m * n_head + h) * HD, qw, cs_row, lane, eps);
@@ -184,28 +220,37 @@ __global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_fused_kernel(uint16_t
     float mx = -INFINITY, l = 0.f, acc[DPL];
 #pragma unroll
     for (int d = 0; d < DPL; d++) acc[d] = 0.f;
-    const uint16_t* kbase = kc + (size_t)m * seq_stride + (size_t)kvh * HD + lane * DPL;
-    const uint16_t* vbase = vc + (size_t)m * seq_stride + (size_t)kvh * HD + lane * DPL;
-    for (int t = t0 + warp; t < t1; t += kAttnWarps) {
-        float kf[DPL], vf[DPL];
-        if (t == pos) {
+    for (; tb < t1; tb += kAttnWarps * kTokBatch) {
 #pragma unroll
-            for (int d = 0; d < DPL; d++) kf[d] = knew[d], vf[d] = vnew[d];
-        } else {
-            load_row<DPL>(kf, kbase + (size_t)t * kv_dim);
-            load_row<DPL>(vf, vbase + (size_t)t * kv_dim);
+        for (int u = 0; u < kTokBatch; u++)
+            if (tb + u == pos) {  // the current position comes from registers, never from the cache
+#pragma unroll
+                for (int d = 0; d < DPL; d++) kf[u][d] = knew[d], vf[u][d] = vnew[d];
+            }
+        float s[kTokBatch];
+#pragma unroll
+        for (int u = 0; u < kTokBatch; u++) {
+            s[u] = 0.f;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) s[u] = fmaf(qf[d], kf[u][d], s[u]);
         }
-        float s = 0.f;
 #pragma unroll
-        for (int d = 0; d < DPL; d++) s = fmaf(qf[d], kf[d], s);
-        s = warp_sum(s) / sqrt_hd;
-        const float mn = fmaxf(mx, s);
-        const float c  = expf(mx - mn);
-        const float p  = expf(s - mn);
-        l = l * c + p;
+        for (int o_ = 16; o_ > 0; o_ >>= 1)
 #pragma unroll
-        for (int d = 0; d < DPL; d++) acc[d] = fmaf(p, vf[d], acc[d] * c);
-        mx = mn;
+            for (int u = 0; u < kTokBatch; u++) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o_);
+#pragma unroll
+        for (int u = 0; u < kTokBatch; u++) {
+            if (tb + u >= t1) break;
+            const float sc = s[u] / sqrt_hd;
+            const float mn = fmaxf(mx, sc);
+            const float c  = expf(mx - mn);
+            const float p  = expf(sc - mn);
+            l = l * c + p;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) acc[d] = fmaf(p, vf[u][d], acc[d] * c);
+            mx = mn;
+        }
+        if (tb + kAttnWarps * kTokBatch < t1) load_batch(tb + kAttnWarps * kTokBatch);
     }
 #pragma unroll
     for (int d = 0; d < DPL; d++) s_acc[warp][lane * DPL + d] = acc[d];
@@ -281,8 +326,8 @@ extern "C" int kf_qkv_attention(kf_ctx* ctx, void* out, const void* q, const voi
     int nsplit = ctx->attn_split;
     if (nsplit <= 0) {
         const int len = std::max(1, std::min(max_seq, max_pos_hint + 1));
-        nsplit        = (2 * ctx->sm_count + n_head * M - 1) / (n_head * M);
-        nsplit        = std::min(nsplit, std::max(1, len / (kAttnWarps * 16)));
+        nsplit        = (4 * ctx->sm_count + n_head * M - 1) / (n_head * M);
+        nsplit        = std::min(nsplit, std::max(1, len / (kAttnWarps * 2 * kTokBatch)));  // two batches per warp measured best
         nsplit        = std::max(1, std::min(nsplit, 64));
     }
     float* ws = nullptr;
@@ -314,8 +359,8 @@ extern "C" int kf_attn_decode(kf_ctx* ctx, void* out, const void* q, const void*
     int nsplit = ctx->attn_split;
     if (nsplit <= 0) {
         const int len = std::max(1, std::min(max_seq, max_pos_hint + 1));
-        nsplit        = (2 * ctx->sm_count + n_head * M - 1) / (n_head * M);
-        nsplit        = std::min(nsplit, std::max(1, len / (kAttnWarps * 16)));
+        nsplit        = (4 * ctx->sm_count + n_head * M - 1) / (n_head * M);
+        nsplit        = std::min(nsplit, std::max(1, len / (kAttnWarps * 2 * kTokBatch)));  // two batches per warp measured best
         nsplit        = std::max(1, std::min(nsplit, 64));
     }
     float* ws = nullptr;
