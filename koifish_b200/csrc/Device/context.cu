@@ -96,6 +96,10 @@ extern "C" int kf_ctx_destroy(kf_ctx* ctx) {
         cudaFree(ctx->attn_ws);
     if (ctx->attn_cnt)
         cudaFree(ctx->attn_cnt);
+    void* scratch[4] = {ctx->xperm, ctx->xnorm, ctx->tmp0, ctx->tmp1};
+    for (void* b : scratch)
+        if (b)
+            cudaFree(b);
     if (ctx->own_stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -122,6 +126,8 @@ extern "C" int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value) {
         ctx->gemv_exact = value;
     else if (!strcmp(key, "pdl"))
         ctx->pdl = value;
+    else if (!strcmp(key, "tc_min_m"))
+        ctx->tc_min_m = value;
     else if (!strcmp(key, "attn_split"))
         ctx->attn_split = value;
     else
@@ -166,6 +172,18 @@ int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes) {
     return KF_OK;
 }
 
+int kf_ensure_buf(kf_ctx* ctx, void** buf, size_t* cap, size_t bytes) {
+    if (bytes > *cap) {
+        KF_REQUIRE(ctx, !ctx->capturing, "scratch buffers must be sized before graph capture (run one eager step first)");
+        KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (*buf)
+            cudaFree(*buf);
+        *buf = nullptr, *cap = 0;
+        KF_CUDA(ctx, cudaMalloc(buf, bytes + bytes / 8 + 256));
+        *cap = bytes + bytes / 8;
+    }
+    return KF_OK;
+}
 int kf_ensure_attn_cnt(kf_ctx* ctx, int counters) {
     if (counters > ctx->attn_cnt_n) {
         KF_REQUIRE(ctx, !ctx->capturing, "attention counters must be sized before graph capture");

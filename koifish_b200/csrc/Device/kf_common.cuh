@@ -30,6 +30,10 @@ struct kf_ctx {
     unsigned* attn_cnt   = nullptr;  // per (token, head) arrival counters of the fused attention (self-resetting)
     int attn_cnt_n       = 0;
     int pdl              = 1;        // programmatic dependent launch between consecutive kernels of a decode step
+    // scratch of the tensor-core (M > 64) path: permuted / normalised activations and the gate / up panels of a SwiGLU
+    void *xperm = nullptr, *xnorm = nullptr, *tmp0 = nullptr, *tmp1 = nullptr;
+    size_t xperm_bytes = 0, xnorm_bytes = 0, tmp0_bytes = 0, tmp1_bytes = 0;
+    int tc_min_m = 65;  // token count from which kf_linear* use the tcgen05 GEMM (0 = never)
     // tuning
     int gemv_splitk  = 0;
     int gemv_variant = 0;
@@ -99,6 +103,9 @@ static inline bool kf_has_gama(const kf_tensor_desc& w) { return w.gama_dev || (
 int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters);
 int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes);
 int kf_ensure_attn_cnt(kf_ctx* ctx, int counters);
+int kf_ensure_buf(kf_ctx* ctx, void** buf, size_t* cap, size_t bytes);
+// gemm_tc.cu: tcgen05 / TMEM dequant-GEMM for M > 64 tokens; epilogue 0 none / 1 residual / 4 fp32
+int kf_gemm_tc(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual);
 
 #ifdef __CUDACC__
 // Launch with the programmatic-dependent-launch attribute (when ctx->pdl): the kernel may start while its predecessor in the stream

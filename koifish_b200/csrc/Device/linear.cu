@@ -1,9 +1,9 @@
 // linear.cu -- the matmul entry points of the C ABI (TASKA_AxB::blasLt as used by SLP::Forw; reference
 // src/Tensor/GTensor.hpp:703-741, src/Device/CUDA/NeuronFuse.cu:305-381).  M <= 64 tokens go to the HBM-bound fused
-// dequant-GEMV (gemv.cu); larger M is processed in 64-token panels through the same kernel until the tcgen05 prefill GEMM
-// (gemm_tc.cu) takes over.
+// dequant-GEMV (gemv.cu); larger M to the tcgen05 / TMEM dequant-GEMM (gemm_tc.cu).
 #include "kf_common.cuh"
 
+// M > 64 through the skinny kernel in 64-token panels (used when the tensor-core path is switched off: ctx knob tc_min_m = 0)
 static int linear_panels(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                          const void* norm_w, float norm_eps) {
     if (M <= 64) return kf_gemv_small(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
@@ -23,32 +23,64 @@ static int linear_panels(kf_ctx* ctx, int n, void* const* y, const kf_tensor_des
     return KF_OK;
 }
 
+// epilogue: 0 none, 1 residual, 2 swiglu(w[0] gate, w[1] up -> y[0]), 4 fp32
+static int linear_any(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
+                      const void* norm_w, float norm_eps) {
+    if (M <= 64 || ctx->tc_min_m <= 0 || M < ctx->tc_min_m) return linear_panels(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
+    // ---- tensor-core path: RMSNorm (if any) once into a scratch, then one tcgen05 GEMM per weight ----
+    const int K    = w[0].cols;
+    const void* xin = x;
+    if (norm_w) {
+        int rc = kf_ensure_buf(ctx, &ctx->xnorm, &ctx->xnorm_bytes, (size_t)M * K * 2);
+        if (!rc) rc = kf_rmsnorm(ctx, ctx->xnorm, x, norm_w, M, K, norm_eps);
+        if (rc) return rc;
+        xin = ctx->xnorm;
+    }
+    if (epilogue == 2) {
+        const size_t bytes = (size_t)M * w[0].rows * 2;
+        int rc = kf_ensure_buf(ctx, &ctx->tmp0, &ctx->tmp0_bytes, bytes);
+        if (!rc) rc = kf_ensure_buf(ctx, &ctx->tmp1, &ctx->tmp1_bytes, bytes);
+        if (!rc) rc = kf_gemm_tc(ctx, ctx->tmp0, &w[0], xin, M, 0, nullptr);
+        if (!rc) rc = kf_gemm_tc(ctx, ctx->tmp1, &w[1], xin, M, 0, nullptr);
+        if (!rc) rc = kf_swiglu(ctx, y[0], ctx->tmp0, ctx->tmp1, (size_t)M * w[0].rows);  // CU_swiglu_v0 on the bf16 gate / up, as the reference
+        return rc;
+    }
+    for (int i = 0; i < n; i++) {
+        int rc = kf_gemm_tc(ctx, y[i], &w[i], xin, M, epilogue, residual);
+        if (rc) return rc;
+    }
+    return KF_OK;
+}
+
 extern "C" int kf_linear(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual) {
     if (!ctx || !y || !w || !x) return KF_ERR_BAD_ARG;
     KF_REQUIRE(ctx, epilogue == KF_EPI_NONE || epilogue == KF_EPI_RESIDUAL || epilogue == KF_EPI_F32, "epilogue");
+    KF_REQUIRE(ctx, M >= 1, "M");
     void* ys[1] = {y};
-    return linear_panels(ctx, 1, ys, w, x, M, epilogue, residual, nullptr, 0.f);
+    return linear_any(ctx, 1, ys, w, x, M, epilogue, residual, nullptr, 0.f);
 }
 extern "C" int kf_linear_multi(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M) {
     if (!ctx || !y || !w || !x) return KF_ERR_BAD_ARG;
-    return linear_panels(ctx, n, y, w, x, M, 0, nullptr, nullptr, 0.f);
+    KF_REQUIRE(ctx, M >= 1 && n >= 1 && n <= 3, "M, n");
+    return linear_any(ctx, n, y, w, x, M, 0, nullptr, nullptr, 0.f);
 }
 extern "C" int kf_linear_swiglu(kf_ctx* ctx, void* y, const kf_tensor_desc* wg, const kf_tensor_desc* wu, const void* x, int M) {
     if (!ctx || !y || !wg || !wu || !x) return KF_ERR_BAD_ARG;
+    KF_REQUIRE(ctx, M >= 1, "M");
     kf_tensor_desc w[2] = {*wg, *wu};
     void* ys[2]         = {y, y};
-    return linear_panels(ctx, 2, ys, w, x, M, 2, nullptr, nullptr, 0.f);
+    return linear_any(ctx, 2, ys, w, x, M, 2, nullptr, nullptr, 0.f);
 }
 // RMSNorm folded into the activation staging of the matmul(s) that consume it: the normalised activations are never written to
-// HBM.  mode: 0 = n plain outputs (n <= 3), 2 = SwiGLU(w[0] gate, w[1] up) -> y[0].
+// HBM (M <= 64).  mode: 0 = n plain outputs (n <= 3), 2 = SwiGLU(w[0] gate, w[1] up) -> y[0].
 extern "C" int kf_rmsnorm_linear(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, const void* norm_w, float eps, int M,
                                  int mode) {
     if (!ctx || !y || !w || !x || !norm_w) return KF_ERR_BAD_ARG;
-    KF_REQUIRE(ctx, mode == 0 || mode == 2, "mode");
+    KF_REQUIRE(ctx, (mode == 0 || mode == 2) && M >= 1 && n >= 1 && n <= 3, "mode / M / n");
     if (mode == 2) {
         KF_REQUIRE(ctx, n == 2, "swiglu takes gate and up");
         void* ys[2] = {y[0], y[0]};
-        return linear_panels(ctx, 2, ys, w, x, M, 2, nullptr, norm_w, eps);
+        return linear_any(ctx, 2, ys, w, x, M, 2, nullptr, norm_w, eps);
     }
-    return linear_panels(ctx, n, y, w, x, M, 0, nullptr, norm_w, eps);
+    return linear_any(ctx, n, y, w, x, M, 0, nullptr, norm_w, eps);
 }

@@ -275,6 +275,59 @@ def test_rmsnorm_folded_into_linear_is_bit_identical_to_unfused(ctx, M):
     assert np.array_equal(kf.rmsnorm_linear(ctx, [head], xd, nwd, M, 1e-6)[0].numpy(np.uint16), kf.linear(ctx, head, xn, M).numpy(np.uint16))
 
 
+# ---------------------------------------------------------------------------------------------- tcgen05 / TMEM dequant GEMM (M > 64)
+@pytest.mark.parametrize("kind", WEIGHT_KINDS, ids=str)
+@pytest.mark.parametrize("M,N,K", [(65, 128, 256), (128, 256, 512), (200, 384, 1024), (300, 128, 2048), (513, 144, 512)])
+def test_gemm_tc_matches_oracle(ctx, kind, M, N, K):
+    t, wdq = make_weight(ctx, kind, N, K, 2000 + M)
+    x = rand_bf16(np.random.default_rng(M + N), (M, K))
+    y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16)
+    _check_linear(y, wdq, x, M, N, K)
+
+
+@pytest.mark.parametrize("kind", WEIGHT_KINDS, ids=str)
+def test_gemm_tc_onehot_reproduces_dequantised_weights(ctx, kind):
+    # every token selects one column k: y[m][n] == w[n][k] exactly -> pins the dequant, the k permutation of A and B, the swizzled
+    # shared-memory layout and the TMEM lane/column mapping of the tensor-core path
+    M, N, K = 192, 256, 512
+    t, wdq = make_weight(ctx, kind, N, K, 3000)
+    ks = (np.arange(M) * 37 + 5) % K
+    x = np.zeros((M, K), dtype=np.uint16)
+    x[np.arange(M), ks] = 0x3F80
+    y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16, (M, N))
+    for m in range(M):
+        assert np.array_equal(ol.bf16_to_f32(y[m]), ol.bf16_to_f32(wdq[:, ks[m]])), (kind, m)
+
+
+def test_gemm_tc_equals_skinny_panels_and_epilogues(ctx):
+    M, N, K = 160, 384, 1024
+    rng = np.random.default_rng(77)
+    t, wdq = make_weight(ctx, (4, ol.RTN_ASYM), N, K, 4000)
+    x, res = rand_bf16(rng, (M, K)), rand_bf16(rng, (M, N))
+    xd = ctx.array(x)
+    y_tc = kf.linear(ctx, t, xd, M).numpy(np.uint16)
+    ctx.set_int("tc_min_m", 0)  # same call through 64-token panels of the skinny kernel
+    try:
+        y_sk = kf.linear(ctx, t, xd, M).numpy(np.uint16)
+    finally:
+        ctx.set_int("tc_min_m", 65)
+    d = np.abs(ol.bf16_to_f32(y_tc) - ol.bf16_to_f32(y_sk))
+    assert (d <= np.abs(ol.bf16_to_f32(y_sk)) * 2.0 ** -7 + 1e-3).all() and (y_tc == y_sk).mean() > 0.97
+    got = kf.linear(ctx, t, xd, M, kf.KF_EPI_RESIDUAL, ctx.array(res)).numpy(np.uint16)
+    assert np.array_equal(got, ol.add(res, y_tc))
+    f32 = kf.linear(ctx, t, xd, M, kf.KF_EPI_F32).numpy(np.float32)
+    assert np.array_equal(ol.f32_to_bf16(f32), y_tc)
+    # fused norm + multi / swiglu entry points take the tensor-core path for M > 64 as well
+    nw = rand_bf16(rng, (K,), 0.5)
+    xn = kf.rmsnorm(ctx, xd, ctx.array(nw), M, K, 1e-6)
+    wg, wu = make_weight(ctx, (4, ol.RTN_ASYM), 256, K, 4001)[0], make_weight(ctx, (4, ol.RTN_ASYM), 256, K, 4002)[0]
+    a = kf.rmsnorm_linear(ctx, [wg, wu], xd, ctx.array(nw), M, 1e-6, swiglu=True).numpy(np.uint16)
+    g = kf.linear(ctx, wg, xn, M).numpy(np.uint16)
+    u = kf.linear(ctx, wu, xn, M).numpy(np.uint16)
+    want = ol.swiglu(g, u)
+    assert (a == want).mean() > 0.999
+
+
 def test_linear_rejects_bad_shapes(ctx):
     t, _ = make_weight(ctx, (4, ol.RTN_ASYM), 128, 512, 1)
     xd = ctx.array(np.zeros((1, 512), dtype=np.uint16))
