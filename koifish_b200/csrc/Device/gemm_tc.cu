@@ -1,19 +1,25 @@
-// gemm_tc.cu -- dequant-fused tensor-core GEMM for prefill / large batches (M > 64 tokens) on the 5th-generation tensor cores:
-//   Y[M][N] = X[M][K] . deq(W[N][K])^T       tcgen05.mma (kind::f16, bf16 x bf16 -> fp32), accumulators in TMEM
+// gemm_tc.cu -- dequant-fused tensor-core GEMM on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), persistent:
+//   Y[M][N] = X[M][K] . deq(W[N][K])^T       tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), accumulators in TMEM
 //
-// Replaces, for nToken >= 65, the same reference pair as gemv.cu: GTensor::GetDataX (whole-matrix dequant to a bf16 scratch,
+// Replaces the same reference pair as gemv.cu: GTensor::GetDataX (whole-matrix dequant to a bf16 scratch,
 // src/Device/CUDA/kernel/quantizer.cu:249-392) + CU_mm_blasLt (src/Device/CUDA/kernel/gemm.cu:93-214) behind SLP::Forw
-// (src/Device/CUDA/NeuronFuse.cu:305-381).  The packed weights are read once per 128/256-token panel and expanded on chip.
+// (src/Device/CUDA/NeuronFuse.cu:305-381).  The packed weights cross HBM once per token panel and are expanded on chip.
 //
-// Tiling: one CTA computes a [128 weight rows] x [BN tokens] tile of Y^T.  The weights are the A operand (UMMA_M = 128 rows), the
-// activations the B operand (UMMA_N = BN tokens), both K-major in shared memory in the canonical SWIZZLE_128B layout, BK = 64:
-//   * warps 0-3 (128 threads, one weight row each): load the row's packed words of the k-block, expand them to the reference's
-//     bit-exact bf16 weights (same two-rounding arithmetic as gemv.cu) and store the 128-byte row into the swizzled A tile; copy the
-//     activation rows into the B tile with cp.async.  The k-order inside each 32-wide slot is the extraction-friendly permutation of
-//     gemv.cu; the activations are permuted identically beforehand by kf_permute_x_kernel, so the contraction is unchanged;
-//   * warp 4: one elected thread issues tcgen05.mma for the stage (4 x K16), tcgen05.commit releases the stage / signals the end;
-//   * warps 0-3 then read the accumulator from TMEM (tcgen05.ld 32x32b: lane = weight row, column = token) and write Y.
-// Pipeline: STAGES-deep ring of {A, B} tiles guarded by full/empty mbarriers.  Every wait is bounded and traps instead of hanging.
+// Work item = [128 weight rows] x [BN tokens] x [one K range (split-K)].  The weights are the A operand (UMMA_M = 128), the tokens
+// the B operand (UMMA_N = BN), BK = 64.  One CTA per SM walks the items round-robin; its 15 warps are specialised:
+//   * warp 9  (1 thread): TMA of the PACKED weight bytes, 64 B per row per stage, into a raw ring (SWIZZLE_64B, conflict-free reads);
+//   * warp 10 (1 thread): TMA of the activation tile (already permuted, see below) into the B ring (SWIZZLE_128B, K-major);
+//   * warps 0-7 (producers, thread = weight row x 32-weight slot): raw bytes -> the reference's bit-exact bf16 weights (the same
+//     two-rounding arithmetic as gemv.cu) -> tcgen05.st into the A ring that lives in TENSOR MEMORY (lane = row, 2 weights / column);
+//     the expanded weights never touch shared memory, which stays free for the B operand;
+//   * warp 8  (1 thread): tcgen05.mma [D], [A in TMEM], B-descriptor; tcgen05.commit frees the stage / publishes the accumulator;
+//   * warps 11-14 (epilogue): tcgen05.ld the accumulator (double-buffered, so the next item's main loop overlaps), then either the
+//     final store (bf16 / +residual / fp32) or, with split-K, an fp32 partial + arrival counter; the last CTA to arrive reduces the
+//     partials in fixed order (deterministic) and stores.
+// bf16 weights need no expansion: warp 9 TMA-loads them straight into a swizzled A tile in shared memory (classic SS MMA).
+// The k order inside every 32-wide slot is the extraction-friendly permutation of gemv.cu; kf_tc_prepare_x permutes the activations
+// identically, so the contraction is unchanged.  Every barrier wait is bounded and traps instead of hanging the GPU.
+#include <cuda.h>
 #include <string.h>
 
 #include <algorithm>
@@ -25,21 +31,30 @@ namespace {
 enum { TF_BF16 = 0, TF_F8 = 1, TF_Q4 = 2, TF_Q2 = 3, TF_Q1 = 4 };
 enum { TM_PLAIN = 0, TM_AFFINE = 1, TM_AFFINE_SYM = 2, TM_SCALE = 3 };
 
-constexpr int BM = 128;  // weight rows per CTA (UMMA M)
-constexpr int BK = 64;   // k per stage: 64 bf16 = one 128-byte swizzle row
-constexpr int kProducerThreads = 128;
-constexpr int kThreadsTC       = kProducerThreads + 32;
+constexpr int BM = 128;    // weight rows per item (UMMA M)
+constexpr int BK = 64;     // k per stage: 64 bf16 = one 128-byte swizzle row of the B tile
+constexpr int RAWB = 64;   // packed bytes per weight row per raw stage
+constexpr int kProducerWarps = 8, kMmaWarp = 8, kRawWarp = 9, kXWarp = 10, kEpiWarp0 = 11;
+constexpr int kThreadsTC = 15 * 32;
 
 struct GemmParams {
-    const uint8_t* data;
     const uint16_t* zero;
     const uint16_t* step;
-    const uint16_t* xp;        // activations, permuted inside every 32-wide k slot: [M][K]
     void* y;                   // bf16 [M][N] (or float when epilogue == 4)
     const uint16_t* residual;  // bf16 [M][N] or nullptr
+    float* ws;                 // split-K partials
+    unsigned* cnt;             // split-K arrival counters (self-resetting)
     int M, N, K;
     int qbias, gshift, epilogue;
+    int n_tiles, m_tiles, splits, n_items;
     uint32_t lop_mask, lop_magic;
+};
+
+template <int FMT>
+struct Fmt {
+    static constexpr int BITS  = FMT == TF_BF16 ? 16 : FMT == TF_F8 ? 8 : FMT == TF_Q4 ? 4 : FMT == TF_Q2 ? 2 : 1;
+    static constexpr int SLOTB = 4 * BITS;                             // packed bytes of one 32-weight slot
+    static constexpr int KBR   = FMT == TF_BF16 ? 1 : RAWB / (2 * SLOTB);  // k-blocks per raw stage
 };
 
 // ---- k permutation inside a 32-wide slot (identical to gemv.cu's xperm) ------------------------------------------------------------
@@ -81,10 +96,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
-    for (uint32_t it = 0; it < (1u << 22); it++) {
+    for (uint32_t it = 0; it < (1u << 24); it++) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -97,13 +115,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
     __trap();
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, bool valid) {
-    const uint32_t d = smem_u32(dst);
-    const int sz     = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
 }
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor bit layout)
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
@@ -119,17 +136,40 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]),
+                 "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t and_or3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
@@ -182,218 +222,473 @@ __device__ __forceinline__ void expand_slot(uint32_t (&o)[16], const uint32_t* w
     } else if constexpr (FMT == TF_Q1) {  // 1 register
 #pragma unroll
         for (int p = 0; p < 16; p++) o[p] = tdeq<MODE>(w[0], p, step2, zero2, nb2, bias2, mask, magic);
-    } else if constexpr (FMT == TF_F8) {  // 8 registers, natural order
+    } else {  // F8: 8 registers, natural order
 #pragma unroll
         for (int r = 0; r < 8; r++) o[2 * r] = tf8_pair(w[r], 0x1404u), o[2 * r + 1] = tf8_pair(w[r], 0x3424u);
-    } else {  // bf16: 16 registers, natural order
-#pragma unroll
-        for (int r = 0; r < 16; r++) o[r] = w[r];
     }
 }
 
-template <int FMT, int MODE, int BN, int STAGES>
-__global__ void __launch_bounds__(kThreadsTC, 1) kf_gemm_tc_kernel(const GemmParams p) {
-    constexpr int BITS    = FMT == TF_BF16 ? 16 : FMT == TF_F8 ? 8 : FMT == TF_Q4 ? 4 : FMT == TF_Q2 ? 2 : 1;
-    constexpr int SLOTB   = 32 * BITS / 8;  // packed bytes of one 32-weight slot
-    constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
+// byte offset of 32-weight slot q inside the 64-byte raw row of a stage (PackedQ.hpp:160-211: the first codes sit in word.high)
+template <int FMT>
+__device__ __forceinline__ int slot_offset(int q) {
+    if (FMT == TF_Q4) return 16 * q;
+    if (FMT == TF_Q2) return 16 * (q >> 1) + 8 * (1 - (q & 1));
+    if (FMT == TF_Q1) return 16 * (q >> 2) + 12 - 4 * (q & 3);
+    return 32 * q;  // F8
+}
+
+__host__ __device__ constexpr int tc_stages(bool a_tmem, int bn) { return bn == 256 ? 4 : (!a_tmem && bn == 128) ? 6 : 8; }
+
+struct Item {
+    int n0, m0, z, tile;  // tile = tn * m_tiles + mt
+    int kb0, kb1;         // k-block range
+};
+template <int KBR>
+__device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
+    Item it;
+    const int mt = item % p.m_tiles;
+    const int t  = item / p.m_tiles;
+    it.z         = t % p.splits;
+    const int tn = t / p.splits;
+    it.n0 = tn * BM, it.m0 = mt, it.tile = tn * p.m_tiles + mt;  // m0 = token-tile index (the caller scales it by BN)
+    const int nkb  = p.K / BK;
+    const int nraw = (nkb + KBR - 1) / KBR;
+    const int base = nraw / p.splits, rem = nraw % p.splits;
+    const int r0 = it.z * base + min(it.z, rem), r1 = r0 + base + (it.z < rem ? 1 : 0);
+    it.kb0 = r0 * KBR, it.kb1 = min(r1 * KBR, nkb);
+    return it;
+}
+
+template <int FMT, int MODE, int BN>
+__global__ void __launch_bounds__(kThreadsTC, 1)
+    kf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
+    using F                  = Fmt<FMT>;
+    constexpr bool A_TMEM    = FMT != TF_BF16;
+    constexpr int KBR        = F::KBR;
+    constexpr int S          = tc_stages(A_TMEM, BN);      // stages of the {A, B} ring
+    constexpr int RS         = A_TMEM ? 8 : 1;             // stages of the raw (packed bytes) ring
+    constexpr int NACC       = (A_TMEM && BN == 256) ? 1 : 2;  // accumulator buffers in TMEM (512 columns in all)
+    constexpr int A_BYTES    = A_TMEM ? 0 : BM * 128;
+    constexpr int B_BYTES    = BN * 128;
+    constexpr int STAGE      = A_BYTES + B_BYTES;
+    constexpr int RAW_BYTES  = BM * RAWB;
+    constexpr int A_COL0     = NACC * BN;                  // TMEM: accumulators first, then the A ring (32 columns per stage)
+    constexpr int TMEM_NEED  = A_COL0 + (A_TMEM ? S * 32 : 0);
+    constexpr int TMEM_COLS  = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+    constexpr uint32_t FULL_COUNT = A_TMEM ? kProducerWarps * 32 + 1 : 2;
+
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // 1024-byte aligned tiles (the 128-byte swizzle is a function of address bits [4,10))
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    uint8_t* raws  = tiles + (size_t)S * STAGE;
+    __shared__ uint64_t full_bar[S], empty_bar[S], raw_full[RS], raw_empty[RS], tmem_full[NACC], tmem_empty[NACC];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ int last_flag;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n0 = blockIdx.x * BM, m0 = blockIdx.y * BN;
-    const int nkb = p.K / BK;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) mbar_init(&full_bar[s], kProducerThreads), mbar_init(&empty_bar[s], 1);
-        mbar_init(&tmem_full_bar, 1);
+        for (int s = 0; s < S; s++) mbar_init(&full_bar[s], FULL_COUNT), mbar_init(&empty_bar[s], 1);
+        for (int s = 0; s < RS; s++) mbar_init(&raw_full[s], 1), mbar_init(&raw_empty[s], kProducerWarps * 32);
+        for (int s = 0; s < NACC; s++) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {  // TMEM: BN fp32 columns x 128 lanes
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)BN) : "memory");
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)TMEM_COLS)
+                     : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = tmem_base_smem;
+    const uint32_t tmem_base = tmem_base_smem;
+    kf_grid_launch_dependents();
 
-    if (warp < 4) {
-        // =================================== producers: one weight row / one token row per thread ===================================
-        const int r           = tid;  // row inside the tile
-        const int grow        = min(n0 + r, p.N - 1);
-        const size_t row_bytes = (size_t)p.K * BITS / 8;
-        const uint8_t* wrow   = p.data + (size_t)grow * row_bytes;
-        const int gpr         = (p.K >> 7) >> p.gshift;
-        const uint16_t* zrow  = MODE == TM_PLAIN ? nullptr : p.zero + (size_t)grow * gpr;
-        const uint16_t* srow  = MODE == TM_PLAIN ? nullptr : p.step + (size_t)grow * gpr;
-        const uint32_t bias2  = pack_bf16x2((float)(128 + p.qbias), (float)(128 + p.qbias));
-        const int mrow        = m0 + r;  // token row this thread copies (BN == 128: one each; BN == 256: two each)
-        const uint32_t sw     = (uint32_t)(r & 7);
-        for (int kb = 0; kb < nkb; kb++) {
-            const int s = kb % STAGES;
-            mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
-            uint8_t* a_tile = tiles + (size_t)s * (A_BYTES + B_BYTES);
-            uint8_t* b_tile = a_tile + A_BYTES;
-            // ---- B: activation rows (already permuted), 128 bytes each, async ----
-#pragma unroll
-            for (int rep = 0; rep < BN / 128; rep++) {
-                const int mr      = r + rep * 128;
-                const int gm      = mrow + rep * 128;
-                const bool valid  = gm < p.M;
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.xp + (size_t)(valid ? gm : 0) * p.K + (size_t)kb * BK);
-                uint8_t* dst       = b_tile + (mr >> 3) * 1024 + (mr & 7) * 128;
-#pragma unroll
-                for (int c = 0; c < 8; c++) cp_async16_zfill(dst + ((c ^ (mr & 7)) << 4), src + c * 16, valid);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            // ---- A: this row's two 32-weight slots of the k-block -> 64 bf16 = one swizzled 128-byte row ----
-            uint8_t* arow = a_tile + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-            for (int slot = 0; slot < 2; slot++) {
-                const int kslot = kb * 2 + slot;  // 32-wide slot index along K
-                uint32_t w[SLOTB / 4 > 0 ? SLOTB / 4 : 1];
-                int off = kslot * SLOTB;
-                if (FMT == TF_Q4) {
-                    off = (kslot >> 2) * 64 + (kslot & 3) * 16;  // word t of the group
-                } else if (FMT == TF_Q2) {
-                    const int g4 = kslot & 3;                    // word.high holds the first 32 codes (PackedQ.hpp:185-198)
-                    off = (kslot >> 2) * 32 + 16 * (g4 >> 1) + 8 * (1 - (g4 & 1));
-                } else if (FMT == TF_Q1) {
-                    off = (kslot >> 2) * 16 + 12 - 4 * (kslot & 3);  // high.hi32 holds codes 0..31 (PackedQ.hpp:200-211)
-                }
-                if constexpr (SLOTB >= 16) {
-#pragma unroll
-                    for (int j = 0; j < SLOTB / 16; j++) {
-                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow + off) + j);
-                        w[4 * j] = v.x, w[4 * j + 1] = v.y, w[4 * j + 2] = v.z, w[4 * j + 3] = v.w;
-                    }
-                } else if constexpr (SLOTB == 8) {
-                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(wrow + off));
-                    w[0] = v.x, w[1] = v.y;
-                } else {
-                    w[0] = __ldg(reinterpret_cast<const uint32_t*>(wrow + off));
-                }
-                uint32_t step2 = 0, zero2 = 0, nb2 = 0;
+    if (warp < kProducerWarps) {
+        if constexpr (A_TMEM) {
+            // ============ producers: thread = (weight row, 32-weight slot of the k-block): raw bytes -> bf16 -> TMEM ============
+            const int quad = warp & 3, slot = warp >> 2;
+            const int row  = quad * 32 + lane;
+            const int gpr  = (p.K >> 7) >> p.gshift;
+            const uint32_t bias2 = pack_bf16x2((float)(128 + p.qbias), (float)(128 + p.qbias));
+            const uint32_t rsw   = (uint32_t)((row >> 1) & 3);  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
+            const uint8_t* rrow  = raws + row * RAWB;
+            uint32_t it = 0, rit = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const Item w = decode_item<KBR>(p, item);
+                const int grow       = min(w.n0 + row, p.N - 1);
+                const uint16_t* zrow = MODE == TM_PLAIN ? nullptr : p.zero + (size_t)grow * gpr;
+                const uint16_t* srow = MODE == TM_PLAIN ? nullptr : p.step + (size_t)grow * gpr;
+                // scale / zero of the current group and of the next two (register queue; the loads are 1-2 groups ahead of their use)
+                int gcur = 0;
+                uint32_t zq0 = 0, sq0 = 0, zq1 = 0, sq1 = 0, zq2 = 0, sq2 = 0;
                 if (MODE != TM_PLAIN) {
-                    const int gi      = (kslot >> 2) >> p.gshift;
-                    const uint32_t zz = __ldg(zrow + gi), ss = __ldg(srow + gi);
-                    step2 = ss | (ss << 16), zero2 = zz | (zz << 16);
-                    if (MODE == TM_AFFINE) nb2 = bf162_as_u32(__hmul2_rn(u32_as_bf162(step2), u32_as_bf162(0xC300C300u)));
+                    gcur = (w.kb0 >> 1) >> p.gshift;
+                    zq0 = __ldg(zrow + gcur), sq0 = __ldg(srow + gcur);
+                    const int g1 = min(gcur + 1, gpr - 1), g2 = min(gcur + 2, gpr - 1);
+                    zq1 = __ldg(zrow + g1), sq1 = __ldg(srow + g1);
+                    zq2 = __ldg(zrow + g2), sq2 = __ldg(srow + g2);
                 }
-                uint32_t o[16];
-                expand_slot<FMT, MODE>(o, w, step2, zero2, nb2, bias2, p.lop_mask, p.lop_magic);
+                int rs = 0;
+                for (int kb = w.kb0; kb < w.kb1; kb++) {
+                    const int kin = kb % KBR;
+                    if (kin == 0) {
+                        rs = rit % RS;
+                        mbar_wait(&raw_full[rs], (rit / RS) & 1);
+                    }
+                    // ---- the slot's packed bytes ----
+                    uint32_t wreg[F::SLOTB / 4 > 0 ? F::SLOTB / 4 : 1];
+                    const int boff     = slot_offset<FMT>(kin * 2 + slot);
+                    const uint8_t* src = rrow + (size_t)rs * RAW_BYTES;
+                    if constexpr (F::SLOTB == 32) {
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const uint32_t chunk = (uint32_t)(slot * 4 + c) ^ sw;
-                    *reinterpret_cast<uint4*>(arow + (chunk << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                        for (int j = 0; j < 2; j++) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(src + ((((boff >> 4) + j) ^ rsw) << 4));
+                            wreg[4 * j] = v.x, wreg[4 * j + 1] = v.y, wreg[4 * j + 2] = v.z, wreg[4 * j + 3] = v.w;
+                        }
+                    } else if constexpr (F::SLOTB == 16) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(src + (((boff >> 4) ^ rsw) << 4));
+                        wreg[0] = v.x, wreg[1] = v.y, wreg[2] = v.z, wreg[3] = v.w;
+                    } else if constexpr (F::SLOTB == 8) {
+                        const uint2 v = *reinterpret_cast<const uint2*>(src + (((boff >> 4) ^ rsw) << 4) + (boff & 15));
+                        wreg[0] = v.x, wreg[1] = v.y;
+                    } else {
+                        wreg[0] = *reinterpret_cast<const uint32_t*>(src + (((boff >> 4) ^ rsw) << 4) + (boff & 15));
+                    }
+                    if (kin == KBR - 1 || kb == w.kb1 - 1) {  // last read of this raw stage: hand it back to the loader
+                        mbar_arrive(&raw_empty[rs]);
+                        rit++;
+                    }
+                    uint32_t step2 = 0, zero2 = 0, nb2 = 0;
+                    if (MODE != TM_PLAIN) {
+                        const int gi = (kb >> 1) >> p.gshift;
+                        if (gi != gcur) {  // rotate the queue, fetch two groups ahead
+                            gcur = gi;
+                            zq0 = zq1, sq0 = sq1, zq1 = zq2, sq1 = sq2;
+                            const int g2 = min(gi + 2, gpr - 1);
+                            zq2 = __ldg(zrow + g2), sq2 = __ldg(srow + g2);
+                        }
+                        step2 = sq0 | (sq0 << 16), zero2 = zq0 | (zq0 << 16);
+                        if (MODE == TM_AFFINE) nb2 = bf162_as_u32(__hmul2_rn(u32_as_bf162(step2), u32_as_bf162(0xC300C300u)));
+                    }
+                    uint32_t o[16];
+                    expand_slot<FMT, MODE>(o, wreg, step2, zero2, nb2, bias2, p.lop_mask, p.lop_magic);
+                    const int s = it % S;
+                    mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
+                    tc_fence_after();
+                    tmem_st16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(A_COL0 + s * 32 + slot * 16), o);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    mbar_arrive(&full_bar[s]);
+                    it++;
                 }
             }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            fence_proxy_async();  // generic-proxy writes (st.shared, cp.async) -> visible to the tensor core's async proxy
-            mbar_arrive(&full_bar[s]);
         }
-        // =================================== epilogue: TMEM -> registers -> Y ===================================
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
-        const int row       = n0 + warp * 32 + lane;  // TMEM lane == weight row; warp w owns lanes 32w .. 32w+31
-        const bool row_ok   = row < p.N;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
-                "%26,%27,%28,%29,%30,%31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-                  "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-                  "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
-                  "=r"(v[31])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row_ok) {
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int m = m0 + c0 + j;
-                    if (m >= p.M) break;
-                    const float acc = __uint_as_float(v[j]);
-                    const size_t idx = (size_t)m * p.N + row;
-                    if (p.epilogue == 4) {
-                        reinterpret_cast<float*>(p.y)[idx] = acc;
-                    } else {
-                        uint16_t b = f32_to_bf16_bits(acc);  // the reference's GEMM output is bf16 (gemm.cu:124-126)
-                        if (p.epilogue == 1) b = f32_to_bf16_bits(bf16_bits_to_f32(p.residual[idx]) + bf16_bits_to_f32(b));
-                        reinterpret_cast<uint16_t*>(p.y)[idx] = b;
+    } else if (warp == kRawWarp) {
+        if (lane == 0) {
+            // ============ weight loader: packed bytes (or, for bf16, the A tile itself) by TMA ============
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const Item w = decode_item<KBR>(p, item);
+                if constexpr (A_TMEM) {
+                    for (int r = w.kb0 / KBR; r * KBR < w.kb1; r++) {
+                        const int rs = it % RS;
+                        mbar_wait(&raw_empty[rs], ((it / RS) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&raw_full[rs], RAW_BYTES);
+                        tma_load_2d(raws + (size_t)rs * RAW_BYTES, &tm_w, r * RAWB, w.n0, &raw_full[rs]);
+                        it++;
+                    }
+                } else {
+                    for (int kb = w.kb0; kb < w.kb1; kb++) {
+                        const int s = it % S;
+                        mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[s], A_BYTES);
+                        tma_load_2d(tiles + (size_t)s * STAGE, &tm_w, kb * BK, w.n0, &full_bar[s]);
+                        it++;
                     }
                 }
             }
         }
-        tc_fence_before();
-    } else if (lane == 0) {
-        // =================================== MMA issuer: a single thread ===================================
-        constexpr uint32_t idesc = make_idesc_bf16(BN);
-        for (int kb = 0; kb < nkb; kb++) {
-            const int s = kb % STAGES;
-            mbar_wait(&full_bar[s], (kb / STAGES) & 1);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(tiles + (size_t)s * (A_BYTES + B_BYTES));
-            const uint64_t adesc = make_desc_sw128(a_addr), bdesc = make_desc_sw128(a_addr + A_BYTES);
-#pragma unroll
-            for (int k = 0; k < BK / 16; k++)  // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in 16-byte units
-                umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&empty_bar[s]);  // arrives when the MMAs above have finished reading the stage
+    } else if (warp == kXWarp) {
+        if (lane == 0) {
+            // ============ activation loader: B tile by TMA (reads what the previous kernel wrote -> dependency wait first) ============
+            kf_grid_dependency_wait();
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const Item w = decode_item<KBR>(p, item);
+                for (int kb = w.kb0; kb < w.kb1; kb++) {
+                    const int s = it % S;
+                    mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
+                    tma_load_2d(tiles + (size_t)s * STAGE + A_BYTES, &tm_x, kb * BK, w.m0 * BN, &full_bar[s]);
+                    it++;
+                }
+            }
         }
-        umma_commit(&tmem_full_bar);
+    } else if (warp == kMmaWarp) {
+        if (lane == 0) {
+            // ============ MMA issuer: a single thread ============
+            constexpr uint32_t idesc = make_idesc_bf16(BN);
+            uint32_t it = 0, ait = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const Item w  = decode_item<KBR>(p, item);
+                const int buf = ait % NACC;
+                mbar_wait(&tmem_empty[buf], ((ait / NACC) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = w.kb0; kb < w.kb1; kb++) {
+                    const int s = it % S;
+                    mbar_wait(&full_bar[s], (it / S) & 1);
+                    tc_fence_after();
+                    const uint32_t st_addr = smem_u32(tiles + (size_t)s * STAGE);
+                    const uint64_t bdesc   = make_desc_sw128(st_addr + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++) {  // 16 bf16 of K per MMA: +32 bytes inside the swizzle row / +8 TMEM columns
+                        const uint32_t acc = (kb > w.kb0 || k > 0) ? 1u : 0u;
+                        if constexpr (A_TMEM)
+                            umma_ts(tmem_d, tmem_base + (uint32_t)(A_COL0 + s * 32 + k * 8), bdesc + (uint64_t)(2 * k), idesc, acc);
+                        else
+                            umma_ss(tmem_d, make_desc_sw128(st_addr) + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+                    }
+                    umma_commit(&empty_bar[s]);  // arrives when the MMAs above have finished reading the stage
+                    it++;
+                }
+                umma_commit(&tmem_full[buf]);
+                ait++;
+            }
+        }
+    } else {
+        // ============ epilogue: TMEM -> registers -> Y (or split-K partial + ordered reduction by the last CTA) ============
+        kf_grid_dependency_wait();  // residual / workspace / counters may still be in use by the previous kernel
+        const int quad = warp & 3;
+        const int row  = quad * 32 + lane;
+        const int et   = (warp - kEpiWarp0) * 32 + lane;  // 0..127
+        uint32_t ait   = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const Item w  = decode_item<KBR>(p, item);
+            const int buf = ait % NACC;
+            const int m0  = w.m0 * BN;
+            const int cnt = min(BN, p.M - m0);
+            const int grow = w.n0 + row;
+            const bool row_ok = grow < p.N;
+            mbar_wait(&tmem_full[buf], (ait / NACC) & 1);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+            float* wsp = p.ws + ((size_t)w.tile * p.splits + w.z) * (size_t)(BN * BM);
+            for (int c0 = 0; c0 < cnt; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tbase + (uint32_t)c0, v);
+                if (p.splits > 1) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if (c0 + j < cnt) wsp[(size_t)(c0 + j) * BM + row] = __uint_as_float(v[j]);
+                } else if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        if (c0 + j < cnt) {
+                            const float acc  = __uint_as_float(v[j]);
+                            const size_t idx = (size_t)(m0 + c0 + j) * p.N + grow;
+                            if (p.epilogue == 4) {
+                                reinterpret_cast<float*>(p.y)[idx] = acc;
+                            } else {
+                                uint16_t b = f32_to_bf16_bits(acc);  // the reference's GEMM output is bf16 (gemm.cu:124-126)
+                                if (p.epilogue == 1) b = f32_to_bf16_bits(bf16_bits_to_f32(p.residual[idx]) + bf16_bits_to_f32(b));
+                                reinterpret_cast<uint16_t*>(p.y)[idx] = b;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[buf]);  // the accumulator buffer may be overwritten by the next item
+            ait++;
+            if (p.splits > 1) {
+                __threadfence();
+                epi_bar_sync();
+                if (et == 0) {
+                    const unsigned old = atomicAdd(&p.cnt[w.tile], 1u);
+                    last_flag          = (old == (unsigned)(p.splits - 1));
+                    if (last_flag) p.cnt[w.tile] = 0;  // self-reset for the next launch
+                }
+                epi_bar_sync();
+                if (last_flag) {
+                    __threadfence();
+                    const float* base = p.ws + (size_t)w.tile * p.splits * (size_t)(BN * BM);
+                    if (row_ok) {
+                        for (int j = 0; j < cnt; j++) {
+                            float acc = 0.f;
+                            for (int z = 0; z < p.splits; z++) acc += __ldcg(base + (size_t)z * (BN * BM) + (size_t)j * BM + row);
+                            const size_t idx = (size_t)(m0 + j) * p.N + grow;
+                            if (p.epilogue == 4) {
+                                reinterpret_cast<float*>(p.y)[idx] = acc;
+                            } else {
+                                uint16_t b = f32_to_bf16_bits(acc);
+                                if (p.epilogue == 1) b = f32_to_bf16_bits(bf16_bits_to_f32(p.residual[idx]) + bf16_bits_to_f32(b));
+                                reinterpret_cast<uint16_t*>(p.y)[idx] = b;
+                            }
+                        }
+                    }
+                }
+                epi_bar_sync();  // last_flag is rewritten by the next item
+            }
+        }
     }
+    tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
+// ---- host side --------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+int make_map_2d(kf_ctx* ctx, CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                uint32_t box_outer, CUtensorMapSwizzle sw) {
+    EncodeTiledFn fn = encode_fn();
+    KF_REQUIRE(ctx, fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    KF_REQUIRE(ctx, ((uintptr_t)base & 15) == 0 && (inner * esize) % 16 == 0, "TMA needs 16-byte aligned rows");
+    cuuint64_t dims[2]    = {inner, outer};
+    cuuint64_t strides[1] = {inner * (uint64_t)esize};
+    cuuint32_t box[2]     = {box_inner, box_outer};
+    cuuint32_t estr[2]    = {1, 1};
+    CUresult r = fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[128];
+        snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        ctx->last_error = b;
+        return KF_ERR_CUDA;
+    }
+    return KF_OK;
+}
+
 template <int FMT, int MODE, int BN>
-int launch_tc(kf_ctx* ctx, const GemmParams& p) {
-    constexpr int STAGES = BN == 256 ? 4 : 6;
-    const size_t smem    = (size_t)STAGES * (BM * 128 + BN * 128) + 1024;
-    auto kern            = kf_gemm_tc_kernel<FMT, MODE, BN, STAGES>;
+int launch_tc(kf_ctx* ctx, GemmParams& p, const void* wdata, const void* xp) {
+    using F              = Fmt<FMT>;
+    constexpr bool A_TMEM = FMT != TF_BF16;
+    constexpr int S      = tc_stages(A_TMEM, BN);
+    constexpr int RS     = A_TMEM ? 8 : 1;
+    const size_t smem    = (size_t)S * ((A_TMEM ? 0 : BM * 128) + BN * 128) + (A_TMEM ? (size_t)RS * BM * RAWB : 0) + 1024;
+    auto kern            = kf_gemm_tc_kernel<FMT, MODE, BN>;
     static bool attr_set = false;
     if (!attr_set) {
         KF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    dim3 grid((p.N + BM - 1) / BM, (p.M + BN - 1) / BN);
-    kern<<<grid, kThreadsTC, smem, ctx->stream>>>(p);
+    // ---- decomposition: row tiles x token tiles x split-K, walked round-robin by one CTA per SM ----
+    p.n_tiles = (p.N + BM - 1) / BM, p.m_tiles = (p.M + BN - 1) / BN;
+    const int nkb = p.K / BK, nraw = (nkb + F::KBR - 1) / F::KBR;
+    const int base_items = p.n_tiles * p.m_tiles;
+    int splits = 1;
+    if (ctx->gemv_splitk > 0) {
+        splits = ctx->gemv_splitk;
+    } else {
+        double best = 1e30;
+        for (int s = 1; s <= 16; s++) {
+            if (s > nraw) break;
+            const int waves  = (base_items * s + ctx->sm_count - 1) / ctx->sm_count;
+            const double len = (double)((nraw + s - 1) / s) * F::KBR + (s > 1 ? 10.0 : 6.0);  // k-blocks per item + epilogue / fix-up
+            const double c   = waves * len;
+            if (c < best * 0.97) best = c, splits = s;
+        }
+    }
+    splits = std::max(1, std::min(splits, nraw));
+    p.splits = splits, p.n_items = base_items * splits;
+    if (splits > 1) {
+        int rc = kf_ensure_gemv_ws(ctx, (size_t)p.n_items * BN * BM * sizeof(float), base_items);
+        if (rc) return rc;
+        p.ws = ctx->gemv_ws, p.cnt = ctx->gemv_cnt;
+    }
+    CUtensorMap tm_w, tm_x;
+    int rc;
+    if (A_TMEM)
+        rc = make_map_2d(ctx, &tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, wdata, (uint64_t)p.K * F::BITS / 8, (uint64_t)p.N, RAWB, BM, CU_TENSOR_MAP_SWIZZLE_64B);
+    else
+        rc = make_map_2d(ctx, &tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wdata, (uint64_t)p.K, (uint64_t)p.N, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (!rc) rc = make_map_2d(ctx, &tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xp, (uint64_t)p.K, (uint64_t)p.M, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    const int grid = std::min(p.n_items, ctx->sm_count);
+    KF_CUDA(ctx, kf_launch_pdl(ctx, kern, dim3(grid), dim3(kThreadsTC), smem, tm_w, tm_x, p));
     KF_LAUNCH_CHECK(ctx);
     return KF_OK;
 }
 template <int FMT, int MODE>
-int launch_tc_bn(kf_ctx* ctx, const GemmParams& p) {
-    return p.M > 128 ? launch_tc<FMT, MODE, 256>(ctx, p) : launch_tc<FMT, MODE, 128>(ctx, p);
+int launch_tc_bn(kf_ctx* ctx, GemmParams& p, const void* wdata, const void* xp) {
+    if (p.M > 128) return launch_tc<FMT, MODE, 256>(ctx, p, wdata, xp);
+    if (p.M > 64) return launch_tc<FMT, MODE, 128>(ctx, p, wdata, xp);
+    if (p.M > 32) return launch_tc<FMT, MODE, 64>(ctx, p, wdata, xp);
+    if (p.M > 16) return launch_tc<FMT, MODE, 32>(ctx, p, wdata, xp);
+    return launch_tc<FMT, MODE, 16>(ctx, p, wdata, xp);
+}
+
+int tc_format(const kf_tensor_desc* w, int* fmt, int* mode) {
+    switch (w->type) {
+        case KF_T_BF16: *fmt = TF_BF16, *mode = TM_PLAIN; return KF_OK;
+        case KF_T_F8E5M2: *fmt = TF_F8, *mode = TM_PLAIN; return KF_OK;
+        case KF_T_Q4: *fmt = TF_Q4, *mode = w->qbias == 0 ? TM_AFFINE : TM_AFFINE_SYM; return KF_OK;
+        case KF_T_Q2: *fmt = TF_Q2, *mode = w->qbias == 0 ? TM_AFFINE : TM_AFFINE_SYM; return KF_OK;
+        case KF_T_SIGN: *fmt = TF_Q2, *mode = TM_SCALE; return KF_OK;
+        case KF_T_BINARY: *fmt = TF_Q1, *mode = TM_SCALE; return KF_OK;
+    }
+    return KF_ERR_UNSUPPORTED;
 }
 
 }  // namespace
 
-// xp_scratch: device buffer of M*K bf16 for the permuted activations (owned by the caller / context)
-int kf_gemm_tc(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual) {
-    KF_REQUIRE(ctx, y && w && x && M >= 1, "args");
+// The k order the tensor-core kernel expects for weights of w's type: identity for bf16 / f8, the extraction-friendly permutation
+// inside every 32-wide slot for the packed types.  Returns x itself or the context's scratch holding the permuted copy.
+int kf_tc_prepare_x(kf_ctx* ctx, const kf_tensor_desc* w, const void* x, int M, const void** xp_out) {
+    int fmt, mode;
+    if (tc_format(w, &fmt, &mode)) return KF_ERR_UNSUPPORTED;
+    if (fmt == TF_BF16 || fmt == TF_F8) {
+        *xp_out = x;
+        return KF_OK;
+    }
+    const int K         = w->cols;
+    const size_t xbytes = (size_t)M * K * 2;
+    int rc = kf_ensure_buf(ctx, &ctx->xperm, &ctx->xperm_bytes, xbytes);
+    if (rc) return rc;
+    const size_t n_slots  = (size_t)M * K / 32;
+    const unsigned blocks = (unsigned)((n_slots + 255) / 256);
+    if (fmt == TF_Q4)
+        kf_permute_x_kernel<TF_Q4><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)ctx->xperm, (const uint16_t*)x, n_slots);
+    else if (fmt == TF_Q2)
+        kf_permute_x_kernel<TF_Q2><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)ctx->xperm, (const uint16_t*)x, n_slots);
+    else
+        kf_permute_x_kernel<TF_Q1><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)ctx->xperm, (const uint16_t*)x, n_slots);
+    KF_LAUNCH_CHECK(ctx);
+    *xp_out = ctx->xperm;
+    return KF_OK;
+}
+// 0 when both weights want the same activation order (one prepared copy serves both)
+int kf_tc_same_order(const kf_tensor_desc* a, const kf_tensor_desc* b) {
+    int fa, fb, ma, mb;
+    if (tc_format(a, &fa, &ma) || tc_format(b, &fb, &mb)) return 1;
+    const bool pa = !(fa == TF_BF16 || fa == TF_F8), pb = !(fb == TF_BF16 || fb == TF_F8);
+    if (!pa && !pb) return 0;
+    return fa == fb ? 0 : 1;
+}
+
+// xp: activations as returned by kf_tc_prepare_x for a weight of the same type
+int kf_gemm_tc(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* xp, int M, int epilogue, const void* residual) {
+    KF_REQUIRE(ctx, y && w && xp && M >= 1, "args");
     const int K = w->cols, N = w->rows;
     KF_REQUIRE(ctx, K % 128 == 0 && N % 16 == 0, "K must be a multiple of 128, rows of 16");
     int fmt, mode;
-    switch (w->type) {
-        case KF_T_BF16: fmt = TF_BF16, mode = TM_PLAIN; break;
-        case KF_T_F8E5M2: fmt = TF_F8, mode = TM_PLAIN; break;
-        case KF_T_Q4: fmt = TF_Q4, mode = w->qbias == 0 ? TM_AFFINE : TM_AFFINE_SYM; break;
-        case KF_T_Q2: fmt = TF_Q2, mode = w->qbias == 0 ? TM_AFFINE : TM_AFFINE_SYM; break;
-        case KF_T_SIGN: fmt = TF_Q2, mode = TM_SCALE; break;
-        case KF_T_BINARY: fmt = TF_Q1, mode = TM_SCALE; break;
-        default: return KF_ERR_UNSUPPORTED;
-    }
+    if (tc_format(w, &fmt, &mode)) return KF_ERR_UNSUPPORTED;
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    p.data = (const uint8_t*)w->data_dev, p.y = y, p.residual = (const uint16_t*)residual, p.M = M, p.N = N, p.K = K;
+    p.y = y, p.residual = (const uint16_t*)residual, p.M = M, p.N = N, p.K = K;
     p.qbias = w->qbias, p.epilogue = epilogue;
     p.lop_mask = fmt == TF_Q4 ? 0x000F000Fu : fmt == TF_Q2 ? 0x00030003u : 0x00010001u, p.lop_magic = 0x43004300u;
     if (mode != TM_PLAIN) {
@@ -404,24 +699,8 @@ int kf_gemm_tc(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* x, int
         p.gshift = gs;
     }
     if (epilogue == 1) KF_REQUIRE(ctx, residual, "residual");
-    // permute the activations once per GEMM (shared by every row tile)
-    const size_t xbytes = (size_t)M * K * 2;
-    int rc = kf_ensure_buf(ctx, &ctx->xperm, &ctx->xperm_bytes, xbytes);
-    if (rc) return rc;
-    p.xp = (const uint16_t*)ctx->xperm;
-    const size_t n_slots = (size_t)M * K / 32;
-    const unsigned blocks = (unsigned)((n_slots + 255) / 256);
-    if (fmt == TF_Q4)
-        kf_permute_x_kernel<TF_Q4><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)ctx->xperm, (const uint16_t*)x, n_slots);
-    else if (fmt == TF_Q2)
-        kf_permute_x_kernel<TF_Q2><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)ctx->xperm, (const uint16_t*)x, n_slots);
-    else if (fmt == TF_Q1)
-        kf_permute_x_kernel<TF_Q1><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)ctx->xperm, (const uint16_t*)x, n_slots);
-    else
-        p.xp = (const uint16_t*)x;  // byte / bf16 streams keep the natural order
-    if (p.xp != (const uint16_t*)x) KF_LAUNCH_CHECK(ctx);
 #define KF_TC_CASE(F, MD) \
-    if (fmt == F && mode == MD) return launch_tc_bn<F, MD>(ctx, p);
+    if (fmt == F && mode == MD) return launch_tc_bn<F, MD>(ctx, p, w->data_dev, xp);
     KF_TC_CASE(TF_Q4, TM_AFFINE)
     KF_TC_CASE(TF_Q4, TM_AFFINE_SYM)
     KF_TC_CASE(TF_Q2, TM_AFFINE)

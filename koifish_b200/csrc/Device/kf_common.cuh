@@ -104,8 +104,11 @@ int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters);
 int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes);
 int kf_ensure_attn_cnt(kf_ctx* ctx, int counters);
 int kf_ensure_buf(kf_ctx* ctx, void** buf, size_t* cap, size_t bytes);
-// gemm_tc.cu: tcgen05 / TMEM dequant-GEMM for M > 64 tokens; epilogue 0 none / 1 residual / 4 fp32
-int kf_gemm_tc(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual);
+// gemm_tc.cu: tcgen05 / TMEM dequant-GEMM; epilogue 0 none / 1 residual / 4 fp32.  xp = the activations in the k order the kernel
+// wants for w's type, as returned by kf_tc_prepare_x (x itself, or the context scratch holding the permuted copy)
+int kf_tc_prepare_x(kf_ctx* ctx, const kf_tensor_desc* w, const void* x, int M, const void** xp_out);
+int kf_tc_same_order(const kf_tensor_desc* a, const kf_tensor_desc* b);  // 0: one prepared copy serves both weights
+int kf_gemm_tc(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* xp, int M, int epilogue, const void* residual);
 
 #ifdef __CUDACC__
 // Launch with the programmatic-dependent-launch attribute (when ctx->pdl): the kernel may start while its predecessor in the stream

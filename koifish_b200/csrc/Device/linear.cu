@@ -26,7 +26,7 @@ static int linear_panels(kf_ctx* ctx, int n, void* const* y, const kf_tensor_des
 // epilogue: 0 none, 1 residual, 2 swiglu(w[0] gate, w[1] up -> y[0]), 4 fp32
 static int linear_any(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                       const void* norm_w, float norm_eps) {
-    if (M <= 64 || ctx->tc_min_m <= 0 || M < ctx->tc_min_m) return linear_panels(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
+    if (ctx->tc_min_m <= 0 || M < ctx->tc_min_m) return linear_panels(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
     // ---- tensor-core path: RMSNorm (if any) once into a scratch, then one tcgen05 GEMM per weight ----
     const int K    = w[0].cols;
     const void* xin = x;
@@ -36,17 +36,23 @@ static int linear_any(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* 
         if (rc) return rc;
         xin = ctx->xnorm;
     }
+    // the activations in the k order of the weights' type: prepared once, shared by every weight of the same type
+    const void* xp = nullptr;
+    int rc = kf_tc_prepare_x(ctx, &w[0], xin, M, &xp);
+    if (rc) return rc;
     if (epilogue == 2) {
         const size_t bytes = (size_t)M * w[0].rows * 2;
-        int rc = kf_ensure_buf(ctx, &ctx->tmp0, &ctx->tmp0_bytes, bytes);
+        rc = kf_ensure_buf(ctx, &ctx->tmp0, &ctx->tmp0_bytes, bytes);
         if (!rc) rc = kf_ensure_buf(ctx, &ctx->tmp1, &ctx->tmp1_bytes, bytes);
-        if (!rc) rc = kf_gemm_tc(ctx, ctx->tmp0, &w[0], xin, M, 0, nullptr);
-        if (!rc) rc = kf_gemm_tc(ctx, ctx->tmp1, &w[1], xin, M, 0, nullptr);
+        if (!rc) rc = kf_gemm_tc(ctx, ctx->tmp0, &w[0], xp, M, 0, nullptr);
+        if (!rc && kf_tc_same_order(&w[0], &w[1])) rc = kf_tc_prepare_x(ctx, &w[1], xin, M, &xp);
+        if (!rc) rc = kf_gemm_tc(ctx, ctx->tmp1, &w[1], xp, M, 0, nullptr);
         if (!rc) rc = kf_swiglu(ctx, y[0], ctx->tmp0, ctx->tmp1, (size_t)M * w[0].rows);  // CU_swiglu_v0 on the bf16 gate / up, as the reference
         return rc;
     }
     for (int i = 0; i < n; i++) {
-        int rc = kf_gemm_tc(ctx, y[i], &w[i], xin, M, epilogue, residual);
+        if (i > 0 && kf_tc_same_order(&w[i - 1], &w[i])) rc = kf_tc_prepare_x(ctx, &w[i], xin, M, &xp);
+        if (!rc) rc = kf_gemm_tc(ctx, y[i], &w[i], xp, M, epilogue, residual);
         if (rc) return rc;
     }
     return KF_OK;

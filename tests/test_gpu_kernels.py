@@ -507,3 +507,59 @@ def test_swiglu_add_embed_argmax(ctx):
     logits[2, :] = 0x3F80
     am = kf.argmax(ctx, ctx.array(logits), 3, 151936).numpy(np.int32)
     assert am[0] == int(np.argmax(ol.bf16_to_f32(logits[0]))) and am[1] == 5 and am[2] == 0
+
+
+@pytest.mark.parametrize("kind", WEIGHT_KINDS, ids=str)
+@pytest.mark.parametrize("M", [1, 7, 16, 24, 48, 64])
+def test_gemm_tc_small_token_counts(ctx, kind, M):
+    # the same kernel with 16 / 32 / 64-token tiles (ctx knob tc_min_m = 1 routes every M to it); K = 1536 gives a ragged last raw
+    # stage for the 1-bit / 2-bit formats, N = 400 a ragged last row tile
+    N, K = 400, 1536
+    t, wdq = make_weight(ctx, kind, N, K, 5000 + M)
+    x = rand_bf16(np.random.default_rng(M), (M, K))
+    ctx.set_int("tc_min_m", 1)
+    try:
+        y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16)
+    finally:
+        ctx.set_int("tc_min_m", 65)
+    _check_linear(y, wdq, x, M, N, K)
+
+
+@pytest.mark.parametrize("splitk", [2, 3, 5])
+@pytest.mark.parametrize("M", [3, 40, 130])
+def test_gemm_tc_splitk_is_deterministic_and_matches(ctx, splitk, M):
+    N, K = 272, 2048
+    rng = np.random.default_rng(splitk * 100 + M)
+    t, wdq = make_weight(ctx, (4, ol.RTN_ASYM), N, K, 6000)
+    x, res = rand_bf16(rng, (M, K)), rand_bf16(rng, (M, N))
+    xd = ctx.array(x)
+    ctx.set_int("tc_min_m", 1)
+    try:
+        f1 = kf.linear(ctx, t, xd, M, kf.KF_EPI_F32).numpy(np.float32)
+        ctx.set_int("gemv_splitk", splitk)
+        ys = [kf.linear(ctx, t, xd, M).numpy(np.uint16) for _ in range(3)]
+        fs = kf.linear(ctx, t, xd, M, kf.KF_EPI_F32).numpy(np.float32)
+        yr = kf.linear(ctx, t, xd, M, kf.KF_EPI_RESIDUAL, ctx.array(res)).numpy(np.uint16)
+    finally:
+        ctx.set_int("gemv_splitk", 0)
+        ctx.set_int("tc_min_m", 65)
+    assert all(np.array_equal(ys[0], y) for y in ys[1:])  # ordered reduction by the last CTA: run-to-run identical
+    _check_linear(ys[0], wdq, x, M, N, K)
+    assert np.allclose(fs, f1, rtol=1e-5, atol=1e-4)
+    assert np.array_equal(yr, ol.add(res, ys[0]))
+
+
+def test_gemm_tc_onehot_small_m(ctx):
+    M, N, K = 16, 256, 1024
+    for kind in WEIGHT_KINDS:
+        t, wdq = make_weight(ctx, kind, N, K, 7000)
+        ks = (np.arange(M) * 61 + 3) % K
+        x = np.zeros((M, K), dtype=np.uint16)
+        x[np.arange(M), ks] = 0x3F80
+        ctx.set_int("tc_min_m", 1)
+        try:
+            y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16, (M, N))
+        finally:
+            ctx.set_int("tc_min_m", 65)
+        for m in range(M):
+            assert np.array_equal(ol.bf16_to_f32(y[m]), ol.bf16_to_f32(wdq[:, ks[m]])), (kind, m)
