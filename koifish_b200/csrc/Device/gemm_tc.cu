@@ -99,21 +99,40 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    return ok;
+}
 // bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    for (uint32_t it = 0; it < (1u << 24); it++) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(a), "r"(parity)
-            : "memory");
-        if (ok) return;
-    }
+__device__ __noinline__ void mbar_wait_slow(uint32_t a, uint32_t parity) {
+    for (uint32_t it = 0; it < (1u << 24); it++)
+        if (mbar_try(a, parity)) return;
     __trap();
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t a, uint32_t parity) {
+    if (!mbar_try(a, parity)) mbar_wait_slow(a, parity);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
+__device__ __forceinline__ void lds128(uint32_t a, uint32_t* r) {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void lds64(uint32_t a, uint32_t* r) {
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
+    return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -259,6 +278,32 @@ __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
     return it;
 }
 
+// Store NC consecutive tokens (the first `valid` of them exist) of weight row `grow`: bf16, bf16 + residual, or fp32.  The residual
+// values are all fetched before the first store (y may alias the residual, element for element).
+template <int NC>
+__device__ __forceinline__ void store_cols(const GemmParams& p, const float (&acc)[NC], int m_first, int valid, int grow) {
+    const size_t idx0 = (size_t)m_first * p.N + grow;
+    if (p.epilogue == 4) {
+#pragma unroll
+        for (int j = 0; j < NC; j++)
+            if (j < valid) reinterpret_cast<float*>(p.y)[idx0 + (size_t)j * p.N] = acc[j];
+        return;
+    }
+    uint16_t res[NC];
+    if (p.epilogue == 1) {
+#pragma unroll
+        for (int j = 0; j < NC; j++) res[j] = j < valid ? p.residual[idx0 + (size_t)j * p.N] : (uint16_t)0;
+    }
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        if (j < valid) {
+            uint16_t b = f32_to_bf16_bits(acc[j]);  // the reference's GEMM output is bf16 (gemm.cu:124-126)
+            if (p.epilogue == 1) b = f32_to_bf16_bits(bf16_bits_to_f32(res[j]) + bf16_bits_to_f32(b));
+            reinterpret_cast<uint16_t*>(p.y)[idx0 + (size_t)j * p.N] = b;
+        }
+    }
+}
+
 template <int FMT, int MODE, int BN>
 __global__ void __launch_bounds__(kThreadsTC, 1)
     kf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
@@ -311,75 +356,85 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
             const int gpr  = (p.K >> 7) >> p.gshift;
             const uint32_t bias2 = pack_bf16x2((float)(128 + p.qbias), (float)(128 + p.qbias));
             const uint32_t rsw   = (uint32_t)((row >> 1) & 3);  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
-            const uint8_t* rrow  = raws + row * RAWB;
-            uint32_t it = 0, rit = 0;
+            constexpr int UNIT = KBR >= 2 ? 2 : 1;  // k-blocks expanded together (independent work for the scheduler)
+            constexpr int NW   = F::SLOTB / 4;      // registers of one packed slot
+            const uint32_t raw_thread = smem_u32(raws) + (uint32_t)(row * RAWB);
+            const uint32_t a_thread   = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(A_COL0 + slot * 16);
+            const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+            const uint32_t rfull0 = smem_u32(&raw_full[0]), rempty0 = smem_u32(&raw_empty[0]);
+            uint32_t s = 0, eph = 1, rs = 0, rph = 0;  // ring positions and the parities to wait for
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const Item w = decode_item<KBR>(p, item);
                 const int grow       = min(w.n0 + row, p.N - 1);
                 const uint16_t* zrow = MODE == TM_PLAIN ? nullptr : p.zero + (size_t)grow * gpr;
                 const uint16_t* srow = MODE == TM_PLAIN ? nullptr : p.step + (size_t)grow * gpr;
-                // scale / zero of the current group and of the next two (register queue; the loads are 1-2 groups ahead of their use)
+                // scale / zero of the current group and of the next two (register queue; the loads run 1-2 groups ahead of their use)
                 int gcur = 0;
                 uint32_t zq0 = 0, sq0 = 0, zq1 = 0, sq1 = 0, zq2 = 0, sq2 = 0;
+                uint32_t step2 = 0, zero2 = 0, nb2 = 0;
                 if (MODE != TM_PLAIN) {
                     gcur = (w.kb0 >> 1) >> p.gshift;
                     zq0 = __ldg(zrow + gcur), sq0 = __ldg(srow + gcur);
                     const int g1 = min(gcur + 1, gpr - 1), g2 = min(gcur + 2, gpr - 1);
                     zq1 = __ldg(zrow + g1), sq1 = __ldg(srow + g1);
                     zq2 = __ldg(zrow + g2), sq2 = __ldg(srow + g2);
+                    step2 = __byte_perm(sq0, 0u, 0x1010), zero2 = __byte_perm(zq0, 0u, 0x1010);
+                    if (MODE == TM_AFFINE) nb2 = bf162_as_u32(__hmul2_rn(u32_as_bf162(step2), u32_as_bf162(0xC300C300u)));
                 }
-                int rs = 0;
-                for (int kb = w.kb0; kb < w.kb1; kb++) {
-                    const int kin = kb % KBR;
-                    if (kin == 0) {
-                        rs = rit % RS;
-                        mbar_wait(&raw_full[rs], (rit / RS) & 1);
-                    }
-                    // ---- the slot's packed bytes ----
-                    uint32_t wreg[F::SLOTB / 4 > 0 ? F::SLOTB / 4 : 1];
-                    const int boff     = slot_offset<FMT>(kin * 2 + slot);
-                    const uint8_t* src = rrow + (size_t)rs * RAW_BYTES;
-                    if constexpr (F::SLOTB == 32) {
+                const int r1 = (w.kb1 + KBR - 1) / KBR;
+                for (int r = w.kb0 / KBR; r < r1; r++) {
+                    // ---- this thread's slots of the raw stage: one per k-block ----
+                    mbar_wait_a(rfull0 + rs * 8, rph);
+                    const uint32_t src = raw_thread + rs * RAW_BYTES;
+                    uint32_t wreg[KBR][NW];
 #pragma unroll
-                        for (int j = 0; j < 2; j++) {
-                            const uint4 v = *reinterpret_cast<const uint4*>(src + ((((boff >> 4) + j) ^ rsw) << 4));
-                            wreg[4 * j] = v.x, wreg[4 * j + 1] = v.y, wreg[4 * j + 2] = v.z, wreg[4 * j + 3] = v.w;
+                    for (int kin = 0; kin < KBR; kin++) {
+                        const int boff = slot_offset<FMT>(kin * 2 + slot);
+                        if constexpr (F::SLOTB == 32) {
+                            lds128(src + ((((uint32_t)(boff >> 4) + 0) ^ rsw) << 4), &wreg[kin][0]);
+                            lds128(src + ((((uint32_t)(boff >> 4) + 1) ^ rsw) << 4), &wreg[kin][4]);
+                        } else if constexpr (F::SLOTB == 16) {
+                            lds128(src + (((uint32_t)(boff >> 4) ^ rsw) << 4), &wreg[kin][0]);
+                        } else if constexpr (F::SLOTB == 8) {
+                            lds64(src + (((uint32_t)(boff >> 4) ^ rsw) << 4) + (boff & 15), &wreg[kin][0]);
+                        } else {
+                            wreg[kin][0] = lds32(src + (((uint32_t)(boff >> 4) ^ rsw) << 4) + (boff & 15));
                         }
-                    } else if constexpr (F::SLOTB == 16) {
-                        const uint4 v = *reinterpret_cast<const uint4*>(src + (((boff >> 4) ^ rsw) << 4));
-                        wreg[0] = v.x, wreg[1] = v.y, wreg[2] = v.z, wreg[3] = v.w;
-                    } else if constexpr (F::SLOTB == 8) {
-                        const uint2 v = *reinterpret_cast<const uint2*>(src + (((boff >> 4) ^ rsw) << 4) + (boff & 15));
-                        wreg[0] = v.x, wreg[1] = v.y;
-                    } else {
-                        wreg[0] = *reinterpret_cast<const uint32_t*>(src + (((boff >> 4) ^ rsw) << 4) + (boff & 15));
                     }
-                    if (kin == KBR - 1 || kb == w.kb1 - 1) {  // last read of this raw stage: hand it back to the loader
-                        mbar_arrive(&raw_empty[rs]);
-                        rit++;
-                    }
-                    uint32_t step2 = 0, zero2 = 0, nb2 = 0;
-                    if (MODE != TM_PLAIN) {
-                        const int gi = (kb >> 1) >> p.gshift;
-                        if (gi != gcur) {  // rotate the queue, fetch two groups ahead
-                            gcur = gi;
-                            zq0 = zq1, sq0 = sq1, zq1 = zq2, sq1 = sq2;
-                            const int g2 = min(gi + 2, gpr - 1);
-                            zq2 = __ldg(zrow + g2), sq2 = __ldg(srow + g2);
+                    mbar_arrive_a(rempty0 + rs * 8);  // the bytes are in registers: hand the stage back to the loader
+                    if (++rs == RS) rs = 0, rph ^= 1;
+#pragma unroll
+                    for (int kin = 0; kin < KBR; kin += UNIT) {
+                        const int kb = r * KBR + kin;
+                        if (KBR > 2 && kb >= w.kb1) break;  // ragged last raw stage (K is a multiple of 128: never splits a unit)
+                        if (MODE != TM_PLAIN) {
+                            const int gi = (kb >> 1) >> p.gshift;
+                            if (gi != gcur) {  // rotate the queue, fetch two groups ahead
+                                gcur = gi;
+                                zq0 = zq1, sq0 = sq1, zq1 = zq2, sq1 = sq2;
+                                const int g2 = min(gi + 2, gpr - 1);
+                                zq2 = __ldg(zrow + g2), sq2 = __ldg(srow + g2);
+                                step2 = __byte_perm(sq0, 0u, 0x1010), zero2 = __byte_perm(zq0, 0u, 0x1010);
+                                if (MODE == TM_AFFINE) nb2 = bf162_as_u32(__hmul2_rn(u32_as_bf162(step2), u32_as_bf162(0xC300C300u)));
+                            }
                         }
-                        step2 = sq0 | (sq0 << 16), zero2 = zq0 | (zq0 << 16);
-                        if (MODE == TM_AFFINE) nb2 = bf162_as_u32(__hmul2_rn(u32_as_bf162(step2), u32_as_bf162(0xC300C300u)));
+                        uint32_t o[UNIT][16];
+#pragma unroll
+                        for (int u = 0; u < UNIT; u++) expand_slot<FMT, MODE>(o[u], wreg[kin + u], step2, zero2, nb2, bias2, p.lop_mask, p.lop_magic);
+                        uint32_t sfull[UNIT];
+#pragma unroll
+                        for (int u = 0; u < UNIT; u++) {
+                            mbar_wait_a(empty0 + s * 8, eph);
+                            tc_fence_after();
+                            tmem_st16(a_thread + s * 32, o[u]);
+                            sfull[u] = full0 + s * 8;
+                            if (++s == S) s = 0, eph ^= 1;
+                        }
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+#pragma unroll
+                        for (int u = 0; u < UNIT; u++) mbar_arrive_a(sfull[u]);
                     }
-                    uint32_t o[16];
-                    expand_slot<FMT, MODE>(o, wreg, step2, zero2, nb2, bias2, p.lop_mask, p.lop_magic);
-                    const int s = it % S;
-                    mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
-                    tc_fence_after();
-                    tmem_st16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(A_COL0 + s * 32 + slot * 16), o);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    tc_fence_before();
-                    mbar_arrive(&full_bar[s]);
-                    it++;
                 }
             }
         }
@@ -482,20 +537,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
                     for (int j = 0; j < 16; j++)
                         if (c0 + j < cnt) wsp[(size_t)(c0 + j) * BM + row] = __uint_as_float(v[j]);
                 } else if (row_ok) {
+                    float acc[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        if (c0 + j < cnt) {
-                            const float acc  = __uint_as_float(v[j]);
-                            const size_t idx = (size_t)(m0 + c0 + j) * p.N + grow;
-                            if (p.epilogue == 4) {
-                                reinterpret_cast<float*>(p.y)[idx] = acc;
-                            } else {
-                                uint16_t b = f32_to_bf16_bits(acc);  // the reference's GEMM output is bf16 (gemm.cu:124-126)
-                                if (p.epilogue == 1) b = f32_to_bf16_bits(bf16_bits_to_f32(p.residual[idx]) + bf16_bits_to_f32(b));
-                                reinterpret_cast<uint16_t*>(p.y)[idx] = b;
-                            }
-                        }
-                    }
+                    for (int j = 0; j < 16; j++) acc[j] = __uint_as_float(v[j]);
+                    store_cols<16>(p, acc, m0 + c0, cnt - c0, grow);
                 }
             }
             tc_fence_before();
@@ -514,17 +559,25 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
                     __threadfence();
                     const float* base = p.ws + (size_t)w.tile * p.splits * (size_t)(BN * BM);
                     if (row_ok) {
-                        for (int j = 0; j < cnt; j++) {
-                            float acc = 0.f;
-                            for (int z = 0; z < p.splits; z++) acc += __ldcg(base + (size_t)z * (BN * BM) + (size_t)j * BM + row);
-                            const size_t idx = (size_t)(m0 + j) * p.N + grow;
-                            if (p.epilogue == 4) {
-                                reinterpret_cast<float*>(p.y)[idx] = acc;
-                            } else {
-                                uint16_t b = f32_to_bf16_bits(acc);
-                                if (p.epilogue == 1) b = f32_to_bf16_bits(bf16_bits_to_f32(p.residual[idx]) + bf16_bits_to_f32(b));
-                                reinterpret_cast<uint16_t*>(p.y)[idx] = b;
+                        // 8 tokens x 2 partials in flight per thread; the partials are added in split order (deterministic)
+                        for (int j0 = 0; j0 < cnt; j0 += 8) {
+                            float acc[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) acc[u] = 0.f;
+                            for (int z = 0; z < p.splits; z += 2) {
+                                float t0[8], t1[8];
+                                const float* b0 = base + (size_t)z * (BN * BM) + (size_t)j0 * BM + row;
+                                const bool two  = z + 1 < p.splits;
+#pragma unroll
+                                for (int u = 0; u < 8; u++) {
+                                    const bool ok = j0 + u < cnt;
+                                    t0[u] = ok ? __ldcg(b0 + u * BM) : 0.f;
+                                    t1[u] = (ok && two) ? __ldcg(b0 + BN * BM + u * BM) : 0.f;
+                                }
+#pragma unroll
+                                for (int u = 0; u < 8; u++) acc[u] = (acc[u] + t0[u]) + t1[u];
                             }
+                            store_cols<8>(p, acc, m0 + j0, cnt - j0, grow);
                         }
                     }
                 }
@@ -597,9 +650,10 @@ int launch_tc(kf_ctx* ctx, GemmParams& p, const void* wdata, const void* xp) {
         for (int s = 1; s <= 16; s++) {
             if (s > nraw) break;
             const int waves  = (base_items * s + ctx->sm_count - 1) / ctx->sm_count;
-            const double len = (double)((nraw + s - 1) / s) * F::KBR + (s > 1 ? 10.0 : 6.0);  // k-blocks per item + epilogue / fix-up
+            // k-blocks per item + restart of the pipeline + (split) partial write / ordered fix-up, which grows with the token tile
+            const double len = (double)((nraw + s - 1) / s) * F::KBR + 2.0 + (s > 1 ? BN / 16.0 : 0.0);
             const double c   = waves * len;
-            if (c < best * 0.97) best = c, splits = s;
+            if (c < best * 0.95) best = c, splits = s;
         }
     }
     splits = std::max(1, std::min(splits, nraw));
