@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkoifish_b200.so")
+LIB_PATH = os.environ.get("KF_LIB_PATH") or os.path.join(HERE, "libkoifish_b200.so")  # KF_LIB_PATH: tuning builds only
 
 KF_OK = 0
 KF_ERR_NO_DEVICE, KF_ERR_CUDA, KF_ERR_BAD_ARG, KF_ERR_UNSUPPORTED, KF_ERR_OOM, KF_ERR_NCCL, KF_ERR_QUANT = -100, -101, -102, -103, -104, -105, -701

@@ -26,6 +26,10 @@
 
 #include "kf_common.cuh"
 
+#ifndef KF_TC_EXP
+#define KF_TC_EXP 0  // tuning experiments only (bit 0: no expansion, 1: no TMEM store, 2: no scale / zero fetch in the loop)
+#endif
+
 namespace {
 
 enum { TF_BF16 = 0, TF_F8 = 1, TF_Q4 = 2, TF_Q2 = 3, TF_Q1 = 4 };
@@ -33,7 +37,10 @@ enum { TM_PLAIN = 0, TM_AFFINE = 1, TM_AFFINE_SYM = 2, TM_SCALE = 3 };
 
 constexpr int BM = 128;    // weight rows per item (UMMA M)
 constexpr int BK = 64;     // k per stage: 64 bf16 = one 128-byte swizzle row of the B tile
-constexpr int RAWB = 64;   // packed bytes per weight row per raw stage
+#ifndef KF_TC_RAWB
+#define KF_TC_RAWB 128
+#endif
+constexpr int RAWB = KF_TC_RAWB;  // packed bytes per weight row per raw stage (64: SWIZZLE_64B, 128: SWIZZLE_128B)
 constexpr int kProducerWarps = 8, kMmaWarp = 8, kRawWarp = 9, kXWarp = 10, kEpiWarp0 = 11;
 constexpr int kThreadsTC = 15 * 32;
 
@@ -54,7 +61,7 @@ template <int FMT>
 struct Fmt {
     static constexpr int BITS  = FMT == TF_BF16 ? 16 : FMT == TF_F8 ? 8 : FMT == TF_Q4 ? 4 : FMT == TF_Q2 ? 2 : 1;
     static constexpr int SLOTB = 4 * BITS;                             // packed bytes of one 32-weight slot
-    static constexpr int KBR   = FMT == TF_BF16 ? 1 : RAWB / (2 * SLOTB);  // k-blocks per raw stage
+    static constexpr int KBR   = FMT == TF_BF16 ? 2 : RAWB / (2 * SLOTB);  // k-blocks per raw stage (bf16: granularity of a K split)
 };
 
 // ---- k permutation inside a 32-wide slot (identical to gemv.cu's xperm) ------------------------------------------------------------
@@ -123,6 +130,15 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t a, uint32_t parity) {
     if (!mbar_try(a, parity)) mbar_wait_slow(a, parity);
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
+// for the warps that wait a long time (epilogue): back off between polls so the spinning does not take issue slots from the producers
+__device__ __noinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 22); it++) {
+        if (mbar_try(a, parity)) return;
+        __nanosleep(200);
+    }
+    __trap();
+}
 __device__ __forceinline__ void lds128(uint32_t a, uint32_t* r) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
 }
@@ -155,24 +171,32 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
+// The MMA / commit helpers are executed by the whole (converged) warp; elect.sync picks one lane -- the same one every time, so all
+// MMAs and the commits that track them come from a single thread -- and only that lane issues the instruction.
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit_a(uint32_t bar_addr) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_addr)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(v[0]),
@@ -256,7 +280,24 @@ __device__ __forceinline__ int slot_offset(int q) {
     return 32 * q;  // F8
 }
 
-__host__ __device__ constexpr int tc_stages(bool a_tmem, int bn) { return bn == 256 ? 4 : (!a_tmem && bn == 128) ? 6 : 8; }
+// Ring depths.  The three rings are decoupled because their latencies differ: the raw ring hides DRAM latency (bytes in flight per SM
+// = RS x 8 KB must cover ~2 us x 44 GB/s), the B ring hides the L2 round trip of the (small, L2-resident) activation tiles, the A ring
+// only the on-chip producer -> MMA hand-off.  Sized so that shared memory stays below ~210 KB and tensor memory within 512 columns.
+template <int FMT, int BN>
+struct Rings {
+    static constexpr bool A_TMEM = FMT != TF_BF16;
+    static constexpr int U       = BN <= 128 ? 2 : 1;  // k-blocks per ring stage: below 256 tokens the barrier traffic, not the MMA, paces a k-block
+    static constexpr int NACC    = (A_TMEM && BN == 256) ? 1 : 2;
+    static constexpr int A_BYTES = A_TMEM ? 0 : BM * 128;
+    static constexpr int SUB     = A_BYTES + BN * 128;  // one k-block of a stage: [A tile (bf16 weights only)][B tile]
+    static constexpr int STAGE   = U * SUB;
+    static constexpr int SA      = !A_TMEM ? 0 : (BN <= 64 ? 12 : 8) / U;
+    static constexpr int SB      = (A_TMEM ? (BN == 16 ? 32 : BN == 32 ? 16 : BN == 64 ? 10 : BN == 128 ? 6 : 4)
+                                           : (BN == 16 ? 10 : BN == 32 ? 10 : BN == 64 ? 8 : BN == 128 ? 6 : 4)) / U;
+    static constexpr int RS      = !A_TMEM ? 0 : (BN <= 64 ? 128 : BN == 128 ? 112 : 80) * 1024 / (BM * RAWB);
+    static constexpr size_t SMEM = (size_t)SB * STAGE + (size_t)RS * BM * RAWB + 1024;
+    static_assert(SMEM <= 216 * 1024, "shared memory budget");
+};
 
 struct Item {
     int n0, m0, z, tile;  // tile = tn * m_tiles + mt
@@ -308,33 +349,39 @@ template <int FMT, int MODE, int BN>
 __global__ void __launch_bounds__(kThreadsTC, 1)
     kf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
     using F                  = Fmt<FMT>;
-    constexpr bool A_TMEM    = FMT != TF_BF16;
+    using C                  = Rings<FMT, BN>;
+    constexpr bool A_TMEM    = C::A_TMEM;
     constexpr int KBR        = F::KBR;
-    constexpr int S          = tc_stages(A_TMEM, BN);      // stages of the {A, B} ring
-    constexpr int RS         = A_TMEM ? 8 : 1;             // stages of the raw (packed bytes) ring
-    constexpr int NACC       = (A_TMEM && BN == 256) ? 1 : 2;  // accumulator buffers in TMEM (512 columns in all)
-    constexpr int A_BYTES    = A_TMEM ? 0 : BM * 128;
+    constexpr int SA         = C::SA;    // A ring (expanded weights, tensor memory, 32 columns per stage)
+    constexpr int SB         = C::SB;    // B ring (activation tiles, shared memory; for bf16 weights the stage also holds the A tile)
+    constexpr int RS         = C::RS;    // raw ring (packed weight bytes, shared memory)
+    constexpr int NACC       = C::NACC;  // accumulator buffers in tensor memory
+    constexpr int A_BYTES    = C::A_BYTES;
     constexpr int B_BYTES    = BN * 128;
-    constexpr int STAGE      = A_BYTES + B_BYTES;
+    constexpr int STAGE      = C::STAGE;
+    constexpr int SUB        = C::SUB;
+    constexpr int U          = C::U;     // k-blocks per stage of the A and B rings
     constexpr int RAW_BYTES  = BM * RAWB;
-    constexpr int A_COL0     = NACC * BN;                  // TMEM: accumulators first, then the A ring (32 columns per stage)
-    constexpr int TMEM_NEED  = A_COL0 + (A_TMEM ? S * 32 : 0);
+    constexpr int A_COL0     = NACC * BN;  // TMEM: accumulators first, then the A ring
+    constexpr int TMEM_NEED  = A_COL0 + SA * U * 32;
     constexpr int TMEM_COLS  = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
-    constexpr uint32_t FULL_COUNT = A_TMEM ? kProducerWarps * 32 + 1 : 2;
+    static_assert(TMEM_NEED <= 512, "tensor memory has 512 columns");
+    constexpr int SA1 = SA > 0 ? SA : 1, RS1 = RS > 0 ? RS : 1;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* raws  = tiles + (size_t)S * STAGE;
-    __shared__ uint64_t full_bar[S], empty_bar[S], raw_full[RS], raw_empty[RS], tmem_full[NACC], tmem_empty[NACC];
+    uint8_t* raws  = tiles + (size_t)SB * STAGE;
+    __shared__ uint64_t a_full[SA1], a_empty[SA1], b_full[SB], b_empty[SB], raw_full[RS1], raw_empty[RS1], tmem_full[NACC], tmem_empty[NACC];
     __shared__ uint32_t tmem_base_smem;
     __shared__ int last_flag;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < S; s++) mbar_init(&full_bar[s], FULL_COUNT), mbar_init(&empty_bar[s], 1);
-        for (int s = 0; s < RS; s++) mbar_init(&raw_full[s], 1), mbar_init(&raw_empty[s], kProducerWarps * 32);
-        for (int s = 0; s < NACC; s++) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], 128);
+        for (int s = 0; s < SA; s++) mbar_init(&a_full[s], kProducerWarps), mbar_init(&a_empty[s], 1);  // one arrival per producer WARP
+        for (int s = 0; s < SB; s++) mbar_init(&b_full[s], A_TMEM ? 1 : 2), mbar_init(&b_empty[s], 1);
+        for (int s = 0; s < RS; s++) mbar_init(&raw_full[s], 1), mbar_init(&raw_empty[s], kProducerWarps);
+        for (int s = 0; s < NACC; s++) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
@@ -355,12 +402,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
             const int row  = quad * 32 + lane;
             const int gpr  = (p.K >> 7) >> p.gshift;
             const uint32_t bias2 = pack_bf16x2((float)(128 + p.qbias), (float)(128 + p.qbias));
-            const uint32_t rsw   = (uint32_t)((row >> 1) & 3);  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
+            // TMA swizzle of the raw stage: the 16-byte chunk index is XORed with address bits [7,9) (64-byte rows) / [7,10) (128-byte rows)
+            const uint32_t rsw   = RAWB == 64 ? (uint32_t)((row >> 1) & 3) : (uint32_t)(row & 7);
             constexpr int UNIT = KBR >= 2 ? 2 : 1;  // k-blocks expanded together (independent work for the scheduler)
             constexpr int NW   = F::SLOTB / 4;      // registers of one packed slot
             const uint32_t raw_thread = smem_u32(raws) + (uint32_t)(row * RAWB);
             const uint32_t a_thread   = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(A_COL0 + slot * 16);
-            const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+            const uint32_t full0 = smem_u32(&a_full[0]), empty0 = smem_u32(&a_empty[0]);
             const uint32_t rfull0 = smem_u32(&raw_full[0]), rempty0 = smem_u32(&raw_empty[0]);
             uint32_t s = 0, eph = 1, rs = 0, rph = 0;  // ring positions and the parities to wait for
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -401,7 +449,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
                             wreg[kin][0] = lds32(src + (((uint32_t)(boff >> 4) ^ rsw) << 4) + (boff & 15));
                         }
                     }
-                    mbar_arrive_a(rempty0 + rs * 8);  // the bytes are in registers: hand the stage back to the loader
+                    // the bytes are in registers: hand the stage back to the loader.  One arrival per warp: 256 per-thread arrivals on
+                    // one barrier word serialise in the shared-memory atomic unit and were the bottleneck of the whole kernel
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(rempty0 + rs * 8);
                     if (++rs == RS) rs = 0, rph ^= 1;
 #pragma unroll
                     for (int kin = 0; kin < KBR; kin += UNIT) {
@@ -413,27 +464,45 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
                                 gcur = gi;
                                 zq0 = zq1, sq0 = sq1, zq1 = zq2, sq1 = sq2;
                                 const int g2 = min(gi + 2, gpr - 1);
+#if !(KF_TC_EXP & 4)
                                 zq2 = __ldg(zrow + g2), sq2 = __ldg(srow + g2);
+#endif
                                 step2 = __byte_perm(sq0, 0u, 0x1010), zero2 = __byte_perm(zq0, 0u, 0x1010);
                                 if (MODE == TM_AFFINE) nb2 = bf162_as_u32(__hmul2_rn(u32_as_bf162(step2), u32_as_bf162(0xC300C300u)));
                             }
                         }
                         uint32_t o[UNIT][16];
 #pragma unroll
-                        for (int u = 0; u < UNIT; u++) expand_slot<FMT, MODE>(o[u], wreg[kin + u], step2, zero2, nb2, bias2, p.lop_mask, p.lop_magic);
+                        for (int u = 0; u < UNIT; u++) {
+#if KF_TC_EXP & 1
+                            for (int i = 0; i < 16; i++) o[u][i] = wreg[kin + u][i % NW] ^ step2;
+#else
+                            expand_slot<FMT, MODE>(o[u], wreg[kin + u], step2, zero2, nb2, bias2, p.lop_mask, p.lop_magic);
+#endif
+                        }
                         uint32_t sfull[UNIT];
 #pragma unroll
                         for (int u = 0; u < UNIT; u++) {
-                            mbar_wait_a(empty0 + s * 8, eph);
-                            tc_fence_after();
-                            tmem_st16(a_thread + s * 32, o[u]);
+                            if (u % U == 0) {
+                                mbar_wait_a(empty0 + s * 8, eph);
+                                tc_fence_after();
+                            }
+#if KF_TC_EXP & 2
+                            asm volatile("" ::"r"(o[u][0] ^ o[u][5] ^ o[u][10] ^ o[u][15]));
+#else
+                            tmem_st16(a_thread + s * (32 * U) + (u % U) * 32, o[u]);
+#endif
                             sfull[u] = full0 + s * 8;
-                            if (++s == S) s = 0, eph ^= 1;
+                            if (u % U == U - 1)
+                                if (++s == SA) s = 0, eph ^= 1;
                         }
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
 #pragma unroll
-                        for (int u = 0; u < UNIT; u++) mbar_arrive_a(sfull[u]);
+                            for (int u = U - 1; u < UNIT; u += U) mbar_arrive_a(sfull[u]);
+                        }
                     }
                 }
             }
@@ -448,16 +517,21 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
                     for (int r = w.kb0 / KBR; r * KBR < w.kb1; r++) {
                         const int rs = it % RS;
                         mbar_wait(&raw_empty[rs], ((it / RS) & 1) ^ 1);
+#if KF_TC_EXP & 8
+                        mbar_arrive(&raw_full[rs]);
+#else
                         mbar_arrive_expect_tx(&raw_full[rs], RAW_BYTES);
                         tma_load_2d(raws + (size_t)rs * RAW_BYTES, &tm_w, r * RAWB, w.n0, &raw_full[rs]);
+#endif
                         it++;
                     }
                 } else {
-                    for (int kb = w.kb0; kb < w.kb1; kb++) {
-                        const int s = it % S;
-                        mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&full_bar[s], A_BYTES);
-                        tma_load_2d(tiles + (size_t)s * STAGE, &tm_w, kb * BK, w.n0, &full_bar[s]);
+                    for (int kb = w.kb0; kb < w.kb1; kb += U) {
+                        const int s = it % SB;
+                        mbar_wait(&b_empty[s], ((it / SB) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&b_full[s], U * A_BYTES);
+#pragma unroll
+                        for (int u = 0; u < U; u++) tma_load_2d(tiles + (size_t)s * STAGE + u * SUB, &tm_w, (kb + u) * BK, w.n0, &b_full[s]);
                         it++;
                     }
                 }
@@ -470,46 +544,72 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
             uint32_t it = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const Item w = decode_item<KBR>(p, item);
-                for (int kb = w.kb0; kb < w.kb1; kb++) {
-                    const int s = it % S;
-                    mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
-                    tma_load_2d(tiles + (size_t)s * STAGE + A_BYTES, &tm_x, kb * BK, w.m0 * BN, &full_bar[s]);
+                for (int kb = w.kb0; kb < w.kb1; kb += U) {
+                    const int s = it % SB;
+                    mbar_wait(&b_empty[s], ((it / SB) & 1) ^ 1);
+#if KF_TC_EXP & 16
+                    mbar_arrive(&b_full[s]);
+#else
+                    mbar_arrive_expect_tx(&b_full[s], U * B_BYTES);
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        tma_load_2d(tiles + (size_t)s * STAGE + u * SUB + A_BYTES, &tm_x, (kb + u) * BK, w.m0 * BN, &b_full[s]);
+#endif
                     it++;
                 }
             }
         }
     } else if (warp == kMmaWarp) {
-        if (lane == 0) {
-            // ============ MMA issuer: a single thread ============
-            constexpr uint32_t idesc = make_idesc_bf16(BN);
-            uint32_t it = 0, ait = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item w  = decode_item<KBR>(p, item);
-                const int buf = ait % NACC;
-                mbar_wait(&tmem_empty[buf], ((ait / NACC) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-                for (int kb = w.kb0; kb < w.kb1; kb++) {
-                    const int s = it % S;
-                    mbar_wait(&full_bar[s], (it / S) & 1);
-                    tc_fence_after();
-                    const uint32_t st_addr = smem_u32(tiles + (size_t)s * STAGE);
-                    const uint64_t bdesc   = make_desc_sw128(st_addr + A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; k++) {  // 16 bf16 of K per MMA: +32 bytes inside the swizzle row / +8 TMEM columns
-                        const uint32_t acc = (kb > w.kb0 || k > 0) ? 1u : 0u;
-                        if constexpr (A_TMEM)
-                            umma_ts(tmem_d, tmem_base + (uint32_t)(A_COL0 + s * 32 + k * 8), bdesc + (uint64_t)(2 * k), idesc, acc);
-                        else
-                            umma_ss(tmem_d, make_desc_sw128(st_addr) + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
-                    }
-                    umma_commit(&empty_bar[s]);  // arrives when the MMAs above have finished reading the stage
-                    it++;
+        // ============ MMA issuer.  The whole warp walks the loop converged (ring state and descriptors stay in uniform registers);
+        // one elected lane -- always the same one -- issues the MMAs and the commits (elect.sync inside the asm) ============
+        constexpr uint32_t idesc = make_idesc_bf16(BN);
+        uint32_t ait = 0;
+        uint32_t sa = 0, aph = 0, sb = 0, bph = 0;  // ring positions and the parities to wait for
+        const uint32_t bfull0 = smem_u32(&b_full[0]), bempty0 = smem_u32(&b_empty[0]);
+        const uint32_t afull0 = smem_u32(&a_full[0]), aempty0 = smem_u32(&a_empty[0]);
+        const uint32_t tiles0 = smem_u32(tiles);
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const Item w  = decode_item<KBR>(p, item);
+            const int buf = ait % NACC;
+            mbar_wait(&tmem_empty[buf], ((ait / NACC) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+            uint32_t acc = 0;
+            for (int kb = w.kb0; kb < w.kb1; kb += U) {
+                {  // both polls are issued before either result is consumed (a try_wait takes ~90 cycles even when complete)
+                    const uint32_t ab = bfull0 + sb * 8, aa = afull0 + (A_TMEM ? sa : 0) * 8;
+                    const uint32_t okb = mbar_try(ab, bph), oka = A_TMEM ? mbar_try(aa, aph) : 1u;
+                    if (!okb) mbar_wait_slow(ab, bph);
+                    if (!oka) mbar_wait_slow(aa, aph);
                 }
-                umma_commit(&tmem_full[buf]);
-                ait++;
+                tc_fence_after();
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t st_addr = tiles0 + sb * STAGE + u * SUB;
+                    const uint64_t bdesc   = make_desc_sw128(st_addr + A_BYTES);
+                    if constexpr (A_TMEM) {
+                        const uint32_t ta = tmem_base + (uint32_t)(A_COL0 + sa * (32 * U) + u * 32);
+#pragma unroll
+                        for (int k = 0; k < ((KF_TC_EXP & 32) ? 0 : BK / 16); k++)  // 16 bf16 of K per MMA: +32 bytes in the swizzle row / +8 TMEM columns
+                            umma_ts(tmem_d, ta + (uint32_t)(k * 8), bdesc + (uint64_t)(2 * k), idesc, (k > 0 || u > 0) ? 1u : acc);
+                    } else {
+                        const uint64_t adesc = make_desc_sw128(st_addr);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++)
+                            umma_ss(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (k > 0 || u > 0) ? 1u : acc);
+                    }
+                }
+                acc = 1;
+                // the commits arrive when the MMAs above have finished reading the stages
+                umma_commit_a(bempty0 + sb * 8);
+                if (++sb == SB) sb = 0, bph ^= 1;
+                if constexpr (A_TMEM) {
+                    umma_commit_a(aempty0 + sa * 8);
+                    if (++sa == SA) sa = 0, aph ^= 1;
+                }
             }
+            umma_commit_a(smem_u32(&tmem_full[buf]));
+            ait++;
         }
     } else {
         // ============ epilogue: TMEM -> registers -> Y (or split-K partial + ordered reduction by the last CTA) ============
@@ -525,7 +625,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
             const int cnt = min(BN, p.M - m0);
             const int grow = w.n0 + row;
             const bool row_ok = grow < p.N;
-            mbar_wait(&tmem_full[buf], (ait / NACC) & 1);
+            if (NACC == 2)
+                mbar_wait_sleepy(&tmem_full[buf], (ait / NACC) & 1);  // a whole main loop away: poll politely
+            else
+                mbar_wait(&tmem_full[buf], (ait / NACC) & 1);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
             float* wsp = p.ws + ((size_t)w.tile * p.splits + w.z) * (size_t)(BN * BM);
@@ -544,7 +647,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty[buf]);  // the accumulator buffer may be overwritten by the next item
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);  // the accumulator buffer may be overwritten by the next item
             ait++;
             if (p.splits > 1) {
                 __threadfence();
@@ -629,9 +733,7 @@ template <int FMT, int MODE, int BN>
 int launch_tc(kf_ctx* ctx, GemmParams& p, const void* wdata, const void* xp) {
     using F              = Fmt<FMT>;
     constexpr bool A_TMEM = FMT != TF_BF16;
-    constexpr int S      = tc_stages(A_TMEM, BN);
-    constexpr int RS     = A_TMEM ? 8 : 1;
-    const size_t smem    = (size_t)S * ((A_TMEM ? 0 : BM * 128) + BN * 128) + (A_TMEM ? (size_t)RS * BM * RAWB : 0) + 1024;
+    const size_t smem    = Rings<FMT, BN>::SMEM;
     auto kern            = kf_gemm_tc_kernel<FMT, MODE, BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -666,7 +768,8 @@ int launch_tc(kf_ctx* ctx, GemmParams& p, const void* wdata, const void* xp) {
     CUtensorMap tm_w, tm_x;
     int rc;
     if (A_TMEM)
-        rc = make_map_2d(ctx, &tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, wdata, (uint64_t)p.K * F::BITS / 8, (uint64_t)p.N, RAWB, BM, CU_TENSOR_MAP_SWIZZLE_64B);
+        rc = make_map_2d(ctx, &tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, wdata, (uint64_t)p.K * F::BITS / 8, (uint64_t)p.N, RAWB, BM,
+                         RAWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     else
         rc = make_map_2d(ctx, &tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wdata, (uint64_t)p.K, (uint64_t)p.N, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (!rc) rc = make_map_2d(ctx, &tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xp, (uint64_t)p.K, (uint64_t)p.M, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
