@@ -78,7 +78,8 @@ const char* kf_status_string(int status);
 const char* kf_last_error(kf_ctx* ctx);
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t kf_launch_count(kf_ctx* ctx);
-/* tuning knobs for sweeps: "gemv_splitk" (0 = heuristic), "gemv_variant" */
+/* tuning knobs for sweeps: "gemv_splitk" (0 = heuristic), "gemv_variant", "gemv_exact", "attn_split", "pdl",
+ * "tc_min_m" (token count from which kf_linear* use the tcgen05 GEMM: -1 = measured per-type crossover, 0 = never, n = from n) */
 int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value);
 
 /* ---- device memory (huTensor::Alloc_1, src/Device/CUDA/huTensor.cu:70-103) ---- */
@@ -120,7 +121,8 @@ int kf_dequant(kf_ctx* ctx, const kf_tensor_desc* w, void* out_bf16_dev);
  *      y[M][rows] = x[M][cols] . deq(W)^T, fp32 accumulate, bf16 out.  The reference dequantises W to a scratch and calls
  *      cuBLASLt; here unpack + dequant are fused into the matmul.
  *      epilogue flags: KF_EPI_RESIDUAL  y = RN(residual + RN_bf16(acc))   (replaces the following CU_add3, packedN.cuh:867-875)
- *      M <= 64 takes the HBM-bound skinny path; larger M the tensor-core path. ---- */
+ *      Few tokens take the HBM-bound skinny kernel (mma.sync GEMV), more the persistent tcgen05 / TMEM / TMA kernel; the crossover
+ *      is per weight type (bf16: always tcgen05, f8: 9 tokens, packed 4/2/1-bit: 16; profiles/r01_tc_crossover.txt). ---- */
 enum { KF_EPI_NONE = 0, KF_EPI_RESIDUAL = 1, KF_EPI_F32 = 4 /* y is float [M][rows], unrounded partial sums (tensor parallel) */ };
 int kf_linear(kf_ctx* ctx, void* y_dev, const kf_tensor_desc* w, const void* x_dev, int M, int epilogue, const void* residual_dev);
 /* up to 3 weights sharing x (Q/K/V: SelfAttention::cuInfer, src/Device/CUDA/QKV.cu:648-652) in one launch; y_dev[i] is [M][rows_i] */

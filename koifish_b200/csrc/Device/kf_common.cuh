@@ -33,7 +33,7 @@ struct kf_ctx {
     // scratch of the tensor-core (M > 64) path: permuted / normalised activations and the gate / up panels of a SwiGLU
     void *xperm = nullptr, *xnorm = nullptr, *tmp0 = nullptr, *tmp1 = nullptr;
     size_t xperm_bytes = 0, xnorm_bytes = 0, tmp0_bytes = 0, tmp1_bytes = 0;
-    int tc_min_m = 65;  // token count from which kf_linear* use the tcgen05 GEMM (0 = never)
+    int tc_min_m = -1;  // token count from which kf_linear* use the tcgen05 GEMM: -1 = per weight type (linear.cu), 0 = never
     // tuning
     int gemv_splitk  = 0;
     int gemv_variant = 0;

@@ -23,10 +23,23 @@ static int linear_panels(kf_ctx* ctx, int n, void* const* y, const kf_tensor_des
     return KF_OK;
 }
 
+// Token count from which the tensor-core kernel beats the skinny one (measured on B200, profiles/r01_tc_crossover.txt): bf16 weights
+// always (TMA streams them at the full HBM rate), f8 from 9 tokens, the packed formats from 16 (below that the in-register expansion
+// of the skinny kernel is cheaper than the producer -> TMEM hand-off).  ctx knob tc_min_m: -1 auto, 0 never, n > 0 fixed threshold.
+static bool use_tensor_cores(const kf_ctx* ctx, int n, const kf_tensor_desc* w, int M) {
+    if (ctx->tc_min_m == 0) return false;
+    for (int i = 0; i < n; i++) {
+        if (w[i].cols % 128 != 0 || w[i].rows % 16 != 0 || ((uintptr_t)w[i].data_dev & 15)) return false;
+        const int need = ctx->tc_min_m > 0 ? ctx->tc_min_m : w[i].type == KF_T_BF16 ? 1 : w[i].type == KF_T_F8E5M2 ? 9 : 16;
+        if (M < need) return false;
+    }
+    return true;
+}
+
 // epilogue: 0 none, 1 residual, 2 swiglu(w[0] gate, w[1] up -> y[0]), 4 fp32
 static int linear_any(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                       const void* norm_w, float norm_eps) {
-    if (ctx->tc_min_m <= 0 || M < ctx->tc_min_m) return linear_panels(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
+    if (!use_tensor_cores(ctx, n, w, M)) return linear_panels(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
     // ---- tensor-core path: RMSNorm (if any) once into a scratch, then one tcgen05 GEMM per weight ----
     const int K    = w[0].cols;
     const void* xin = x;

@@ -310,7 +310,7 @@ def test_gemm_tc_equals_skinny_panels_and_epilogues(ctx):
     try:
         y_sk = kf.linear(ctx, t, xd, M).numpy(np.uint16)
     finally:
-        ctx.set_int("tc_min_m", 65)
+        ctx.set_int("tc_min_m", -1)
     d = np.abs(ol.bf16_to_f32(y_tc) - ol.bf16_to_f32(y_sk))
     assert (d <= np.abs(ol.bf16_to_f32(y_sk)) * 2.0 ** -7 + 1e-3).all() and (y_tc == y_sk).mean() > 0.97
     got = kf.linear(ctx, t, xd, M, kf.KF_EPI_RESIDUAL, ctx.array(res)).numpy(np.uint16)
@@ -521,7 +521,7 @@ def test_gemm_tc_small_token_counts(ctx, kind, M):
     try:
         y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16)
     finally:
-        ctx.set_int("tc_min_m", 65)
+        ctx.set_int("tc_min_m", -1)
     _check_linear(y, wdq, x, M, N, K)
 
 
@@ -542,7 +542,7 @@ def test_gemm_tc_splitk_is_deterministic_and_matches(ctx, splitk, M):
         yr = kf.linear(ctx, t, xd, M, kf.KF_EPI_RESIDUAL, ctx.array(res)).numpy(np.uint16)
     finally:
         ctx.set_int("gemv_splitk", 0)
-        ctx.set_int("tc_min_m", 65)
+        ctx.set_int("tc_min_m", -1)
     assert all(np.array_equal(ys[0], y) for y in ys[1:])  # ordered reduction by the last CTA: run-to-run identical
     _check_linear(ys[0], wdq, x, M, N, K)
     assert np.allclose(fs, f1, rtol=1e-5, atol=1e-4)
@@ -560,6 +560,6 @@ def test_gemm_tc_onehot_small_m(ctx):
         try:
             y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16, (M, N))
         finally:
-            ctx.set_int("tc_min_m", 65)
+            ctx.set_int("tc_min_m", -1)
         for m in range(M):
             assert np.array_equal(ol.bf16_to_f32(y[m]), ol.bf16_to_f32(wdq[:, ks[m]])), (kind, m)

@@ -40,7 +40,7 @@ def main():
     ap.add_argument("--variants", default="0", help="gemv_variant values: 0 auto, 1 = 16 rows/warp, 2 = 32 rows/warp")
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--out", default="")
-    ap.add_argument("--tc", default="65", help="tc_min_m values: token count from which the tcgen05 GEMM is used (0 = never, 1 = always)")
+    ap.add_argument("--tc", default="-1", help="tc_min_m values: token count from which the tcgen05 GEMM is used (-1 = auto per type, 0 = never, 1 = always)")
     ap.add_argument("--exact", type=int, default=1, help="gemv_exact knob: 1 = reference-exact in-kernel dequant, 0 = factored scale/zero")
     args = ap.parse_args()
     stream = torch.cuda.Stream()  # a real (non-default) stream shared by torch events and our kernels
@@ -88,7 +88,7 @@ def main():
                     us = e0.elapsed_time(e1) * 1e3 / args.iters
                     ab = alg_bytes(N, K, bits, M)
                     gbs = ab / (us * 1e-6) / 1e9
-                    rec = {"type": tname, "N": N, "K": K, "M": M, "tc": int(tc > 0 and M >= tc), "splitk": sk, "variant": variant, "us": round(us, 2), "alg_MB": round(ab / 1e6, 2), "GBps": round(gbs, 1),
+                    rec = {"type": tname, "N": N, "K": K, "M": M, "tc": tc, "splitk": sk, "variant": variant, "us": round(us, 2), "alg_MB": round(ab / 1e6, 2), "GBps": round(gbs, 1),
                            "frac_measured": round(gbs / peak, 3), "frac_8TBps": round(gbs / 8000.0, 3), "tflops": round(2.0 * M * N * K / (us * 1e-6) / 1e12, 2),
                            "nbuf": nbuf}
                     print(json.dumps(rec), flush=True)
