@@ -313,6 +313,209 @@ __global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_fused_kernel(uint16_t
         if (lane == 0) cnt[(size_t)m * n_head + h] = 0u;  // self-reset
     }
 }
+
+// ---- the same fused step for contexts up to ~1K tokens: the slices of one (token, head) form a THREAD-BLOCK CLUSTER and are merged
+// through distributed shared memory instead of a global workspace + arrival counter + last-CTA pass.  What is left on the critical
+// path after the QKV GEMV finishes is one L2 round trip (q / k / v of the new token), the score / softmax arithmetic of 16 cached rows
+// per warp -- all of which were requested BEFORE the dependency wait, as packed bf16 -- and one cluster barrier.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_f32(float* local_ptr, int cta_rank, float v) {
+    uint32_t remote;
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(local_ptr);
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(cta_rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+template <int DPL>
+__device__ __forceinline__ uint2 load_raw(const uint16_t* p) {
+    if constexpr (DPL == 4) return *reinterpret_cast<const uint2*>(p);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(p), 0u);
+}
+template <int DPL>
+__device__ __forceinline__ void unpack_raw(float (&f)[DPL], uint2 v) {
+    f[0] = bf16lo(v.x), f[1] = bf16hi(v.x);
+    if constexpr (DPL == 4) f[2] = bf16lo(v.y), f[3] = bf16hi(v.y);
+}
+constexpr int kWarpTok    = 16;  // cached rows per warp per pass, all in flight at once (packed: 2 x 16 x 2 registers for hd 128)
+constexpr int kMaxCluster = 8;   // portable cluster size
+
+template <int DPL>
+__global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_cluster_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ q,
+                                                                          const uint16_t* __restrict__ k, const uint16_t* __restrict__ v,
+                                                                          const uint16_t* __restrict__ qw, const uint16_t* __restrict__ kw,
+                                                                          uint16_t* __restrict__ kc, uint16_t* __restrict__ vc,
+                                                                          const float2* __restrict__ table, const int32_t* __restrict__ pos_dev,
+                                                                          int n_head, int n_kv, int nsplit, float sqrt_hd, float eps,
+                                                                          size_t seq_stride) {
+    constexpr int HD = DPL * 32;
+    __shared__ float s_acc[kAttnWarps][HD];
+    __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
+    __shared__ float s_part[kMaxCluster][HD + 2];  // rank 0's copy receives the partial (acc[hd], max, sum) of every slice
+    const int h = blockIdx.x, m = blockIdx.y, split = blockIdx.z;  // cluster = (1, 1, nsplit): rank in cluster == split
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = n_head / n_kv, kvh = h / group, kv_dim = n_kv * HD;
+    kf_grid_launch_dependents();
+    if (nsplit > 1) cluster_arrive();  // matched by the wait in front of the first remote store: by then every CTA of the cluster runs
+    // ---- independent of the QKV GEMV: position, slice, rotation table row and ALL cached rows of this warp's first pass ----
+    const int pos = pos_dev[m], len = pos + 1;
+    const int t0 = (int)(((long long)split * len) / nsplit), t1 = (int)(((long long)(split + 1) * len) / nsplit);
+    const float2* cs_row  = table + (size_t)pos * (HD / 2);
+    const uint16_t* kbase = kc + (size_t)m * seq_stride + (size_t)kvh * HD + lane * DPL;
+    const uint16_t* vbase = vc + (size_t)m * seq_stride + (size_t)kvh * HD + lane * DPL;
+    uint2 kr[kWarpTok], vr[kWarpTok];
+    auto load_pass = [&](int tb_) {
+#pragma unroll
+        for (int u = 0; u < kWarpTok; u++) {
+            const int t = tb_ + u;
+            if (t < t1 && t != pos) kr[u] = load_raw<DPL>(kbase + (size_t)t * kv_dim), vr[u] = load_raw<DPL>(vbase + (size_t)t * kv_dim);
+        }
+    };
+    int tb = t0 + warp * kWarpTok;
+    if (tb < t1) load_pass(tb);
+    kf_grid_dependency_wait();  // q / k / v come from the QKV GEMV right before us
+
+    float qf[DPL], knew[DPL], vnew[DPL];
+    norm_rope_row<DPL>(qf, q + ((size_t)m * n_head + h) * HD, qw, cs_row, lane, eps);
+    const bool has_new = t1 == len;  // the last slice owns the current position
+    if (has_new) {
+        norm_rope_row<DPL>(knew, k + ((size_t)m * n_kv + kvh) * HD, kw, cs_row, lane, eps);
+        load_row<DPL>(vnew, v + ((size_t)m * n_kv + kvh) * HD + lane * DPL);
+        if (h % group == 0 && warp == 0) {  // append K / V of this kv head at row pos (KVCache, Cache.cpp:43-58)
+            uint16_t* kd = kc + (size_t)m * seq_stride + (size_t)pos * kv_dim + (size_t)kvh * HD + lane * DPL;
+            uint16_t* vd = vc + (size_t)m * seq_stride + (size_t)pos * kv_dim + (size_t)kvh * HD + lane * DPL;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) kd[d] = f32_to_bf16_bits(knew[d]), vd[d] = f32_to_bf16_bits(vnew[d]);
+        }
+    }
+    float mx = -INFINITY, l = 0.f, acc[DPL];
+#pragma unroll
+    for (int d = 0; d < DPL; d++) acc[d] = 0.f;
+    for (; tb < t1; tb += kAttnWarps * kWarpTok) {
+        // scores of the pass: per-lane partial dot products, then one butterfly over the 16 values
+        float s[kWarpTok];
+#pragma unroll
+        for (int u = 0; u < kWarpTok; u++) {
+            float kf[DPL];
+            unpack_raw<DPL>(kf, kr[u]);
+            if (tb + u == pos) {  // the current position comes from registers, never from the cache
+#pragma unroll
+                for (int d = 0; d < DPL; d++) kf[d] = knew[d];
+            }
+            s[u] = 0.f;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) s[u] = fmaf(qf[d], kf[d], s[u]);
+        }
+#pragma unroll
+        for (int o_ = 16; o_ > 0; o_ >>= 1)
+#pragma unroll
+            for (int u = 0; u < kWarpTok; u++) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o_);
+        // softmax of the pass with ONE rescale (no serial max / exp chain over the tokens)
+        float mb = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < kWarpTok; u++) {
+            s[u] = tb + u < t1 ? s[u] / sqrt_hd : -INFINITY;  // the reference divides (operator.cuh:630)
+            mb   = fmaxf(mb, s[u]);
+        }
+        const float mn = fmaxf(mx, mb);
+        const float c  = expf(mx - mn);  // 0 on the first pass (mx = -inf)
+        float lp = 0.f, ap[DPL];
+#pragma unroll
+        for (int d = 0; d < DPL; d++) ap[d] = 0.f;
+#pragma unroll
+        for (int u = 0; u < kWarpTok; u++) {
+            const float p = expf(s[u] - mn);  // exp(-inf) = 0 for the masked tail
+            float vf[DPL];
+            unpack_raw<DPL>(vf, vr[u]);
+            if (tb + u == pos) {
+#pragma unroll
+                for (int d = 0; d < DPL; d++) vf[d] = vnew[d];
+            }
+            lp += p;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) ap[d] = fmaf(p, tb + u < t1 ? vf[d] : 0.f, ap[d]);
+        }
+        l = l * c + lp;
+#pragma unroll
+        for (int d = 0; d < DPL; d++) acc[d] = fmaf(acc[d], c, ap[d]);
+        mx = mn;
+        if (tb + kAttnWarps * kWarpTok < t1) load_pass(tb + kAttnWarps * kWarpTok);
+    }
+    // ---- merge the warps of this CTA (fixed order) ----
+#pragma unroll
+    for (int d = 0; d < DPL; d++) s_acc[warp][lane * DPL + d] = acc[d];
+    if (lane == 0) s_m[warp] = mx, s_l[warp] = l;
+    __syncthreads();
+    if (nsplit > 1) cluster_wait();  // every CTA of the cluster has started: its shared memory may be written
+    if (warp == 0) {
+        float M_ = -INFINITY, L_ = 0.f, o[DPL];
+#pragma unroll
+        for (int w = 0; w < kAttnWarps; w++) M_ = fmaxf(M_, s_m[w]);
+#pragma unroll
+        for (int d = 0; d < DPL; d++) o[d] = 0.f;
+#pragma unroll
+        for (int w = 0; w < kAttnWarps; w++) {
+            const float c = s_m[w] == -INFINITY ? 0.f : expf(s_m[w] - M_);
+            L_ += s_l[w] * c;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) o[d] = fmaf(s_acc[w][lane * DPL + d], c, o[d]);
+        }
+        if (nsplit == 1) {
+            const float inv = 1.0f / L_;
+            uint16_t* op    = out + ((size_t)m * n_head + h) * HD + lane * DPL;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) op[d] = f32_to_bf16_bits(o[d] * inv);
+        } else {  // hand the slice's partial to rank 0 through distributed shared memory
+#pragma unroll
+            for (int d = 0; d < DPL; d++) st_cluster_f32(&s_part[split][lane * DPL + d], 0, o[d]);
+            if (lane == 0) st_cluster_f32(&s_part[split][HD], 0, M_), st_cluster_f32(&s_part[split][HD + 1], 0, L_);
+        }
+    }
+    if (nsplit == 1) return;
+    cluster_arrive();  // release: the remote stores above are visible to rank 0 after its wait
+    cluster_wait();
+    if (split != 0 || warp != 0) return;
+    {  // rank 0 merges the slices in split order (deterministic)
+        float Mx = -INFINITY;
+        for (int sp = 0; sp < nsplit; sp++) Mx = fmaxf(Mx, s_part[sp][HD]);
+        float Ls = 0.f, oo[DPL];
+#pragma unroll
+        for (int d = 0; d < DPL; d++) oo[d] = 0.f;
+        for (int sp = 0; sp < nsplit; sp++) {
+            const float ms = s_part[sp][HD];
+            const float c  = ms == -INFINITY ? 0.f : expf(ms - Mx);
+            Ls += s_part[sp][HD + 1] * c;
+#pragma unroll
+            for (int d = 0; d < DPL; d++) oo[d] = fmaf(s_part[sp][lane * DPL + d], c, oo[d]);
+        }
+        const float inv = 1.0f / Ls;
+        uint16_t* op    = out + ((size_t)m * n_head + h) * HD + lane * DPL;
+#pragma unroll
+        for (int d = 0; d < DPL; d++) op[d] = f32_to_bf16_bits(oo[d] * inv);
+    }
+}
+
+template <int DPL>
+cudaError_t launch_attn_cluster(kf_ctx* ctx, dim3 grid, int nsplit, uint16_t* out, const uint16_t* q, const uint16_t* k, const uint16_t* v,
+                                const uint16_t* qw, const uint16_t* kw, uint16_t* kc, uint16_t* vc, const float2* table, const int32_t* pos_dev,
+                                int n_head, int n_kv, float sqrt_hd, float eps, size_t seq_stride) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = dim3(kAttnWarps * 32), cfg.dynamicSmemBytes = 0, cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (nsplit > 1) {
+        attr[na].id               = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = (unsigned)nsplit;
+        na++;
+    }
+    if (ctx->pdl) {
+        attr[na].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    cfg.attrs = attr, cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kf_attn_cluster_kernel<DPL>, out, q, k, v, qw, kw, kc, vc, table, pos_dev, n_head, n_kv, nsplit, sqrt_hd, eps,
+                              seq_stride);
+}
 }  // namespace
 
 // ROPE::cuInfer (rope.cu:645-672) + attention_qk / softmax / attention_v (operator.cuh:573-668) of SelfAttention::cuInfer (QKV.cu:660-674)
@@ -324,8 +527,25 @@ extern "C" int kf_qkv_attention(kf_ctx* ctx, void* out, const void* q, const voi
     KF_REQUIRE(ctx, (hd == 128 || hd == 64) && n_head % n_kv == 0 && M >= 1 && max_seq >= 1, "head_dim 64/128, GQA");
     KF_REQUIRE(ctx, M == 1 || seq_stride > 0, "the fused path needs one sequence per token (use kf_qknorm_rope_kvappend + kf_attn_decode for panels)");
     int nsplit = ctx->attn_split;
+    const int len_hint = std::max(1, std::min(max_seq, max_pos_hint + 1));
+    // contexts up to 1K tokens: slices of 64 tokens (16 per warp, all in flight before the dependency wait) merged inside a cluster
+    if ((nsplit <= 0 && len_hint <= kMaxCluster * kAttnWarps * kWarpTok * 2) || (nsplit > 0 && nsplit <= kMaxCluster)) {
+        if (nsplit <= 0) nsplit = std::max(1, std::min(kMaxCluster, (len_hint + kAttnWarps * kWarpTok - 1) / (kAttnWarps * kWarpTok)));
+        dim3 grid(n_head, M, nsplit);
+        const float sq = sqrtf((float)hd);
+        if (hd == 128)
+            KF_CUDA(ctx, launch_attn_cluster<4>(ctx, grid, nsplit, (uint16_t*)out, (const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v,
+                                                (const uint16_t*)qw, (const uint16_t*)kw, (uint16_t*)kc, (uint16_t*)vc, (const float2*)table, pos_dev,
+                                                n_head, n_kv, sq, eps, seq_stride));
+        else
+            KF_CUDA(ctx, launch_attn_cluster<2>(ctx, grid, nsplit, (uint16_t*)out, (const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v,
+                                                (const uint16_t*)qw, (const uint16_t*)kw, (uint16_t*)kc, (uint16_t*)vc, (const float2*)table, pos_dev,
+                                                n_head, n_kv, sq, eps, seq_stride));
+        KF_LAUNCH_CHECK(ctx);
+        return KF_OK;
+    }
     if (nsplit <= 0) {
-        const int len = std::max(1, std::min(max_seq, max_pos_hint + 1));
+        const int len = len_hint;
         nsplit        = (4 * ctx->sm_count + n_head * M - 1) / (n_head * M);
         nsplit        = std::min(nsplit, std::max(1, len / (kAttnWarps * 2 * kTokBatch)));  // two batches per warp measured best
         nsplit        = std::max(1, std::min(nsplit, 64));

@@ -446,7 +446,7 @@ def test_attention_batched_sequences_and_prefill_panel(ctx):
 
 
 @pytest.mark.parametrize("hd,n_head,n_kv", [(128, 16, 8), (128, 64, 8), (64, 4, 2)])
-@pytest.mark.parametrize("split", [0, 1, 3])
+@pytest.mark.parametrize("split", [0, 1, 3, 8, 12])  # <= 8 slices: cluster / DSMEM merge; more: global workspace + last-CTA merge
 def test_fused_qkv_attention_equals_unfused_path(ctx, hd, n_head, n_kv, split):
     rng = np.random.default_rng(hd + n_head)
     M, max_seq, theta = 3, 256, 1e6
