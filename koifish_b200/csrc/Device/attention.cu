@@ -336,11 +336,15 @@ __device__ __forceinline__ void unpack_raw(float (&f)[DPL], uint2 v) {
     f[0] = bf16lo(v.x), f[1] = bf16hi(v.x);
     if constexpr (DPL == 4) f[2] = bf16lo(v.y), f[3] = bf16hi(v.y);
 }
-constexpr int kWarpTok    = 16;  // cached rows per warp per pass, all in flight at once (packed: 2 x 16 x 2 registers for hd 128)
+#ifndef KF_ATTN_WARPTOK
+#define KF_ATTN_WARPTOK 8
+#endif
+constexpr int kWarpTok    = KF_ATTN_WARPTOK;  // cached rows per warp per pass, all in flight at once, held as packed bf16
 constexpr int kMaxCluster = 8;   // portable cluster size
+constexpr int kClusterWarpsMax = 8;
 
 template <int DPL>
-__global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_cluster_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ q,
+__global__ void __launch_bounds__(kClusterWarpsMax * 32) kf_attn_cluster_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ q,
                                                                           const uint16_t* __restrict__ k, const uint16_t* __restrict__ v,
                                                                           const uint16_t* __restrict__ qw, const uint16_t* __restrict__ kw,
                                                                           uint16_t* __restrict__ kc, uint16_t* __restrict__ vc,
@@ -348,8 +352,9 @@ __global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_cluster_kernel(uint16
                                                                           int n_head, int n_kv, int nsplit, float sqrt_hd, float eps,
                                                                           size_t seq_stride) {
     constexpr int HD = DPL * 32;
-    __shared__ float s_acc[kAttnWarps][HD];
-    __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
+    __shared__ float s_acc[kClusterWarpsMax][HD];
+    __shared__ float s_m[kClusterWarpsMax], s_l[kClusterWarpsMax];
+    const int nwarps = blockDim.x >> 5;
     __shared__ float s_part[kMaxCluster][HD + 2];  // rank 0's copy receives the partial (acc[hd], max, sum) of every slice
     const int h = blockIdx.x, m = blockIdx.y, split = blockIdx.z;  // cluster = (1, 1, nsplit): rank in cluster == split
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_cluster_kernel(uint16
     float mx = -INFINITY, l = 0.f, acc[DPL];
 #pragma unroll
     for (int d = 0; d < DPL; d++) acc[d] = 0.f;
-    for (; tb < t1; tb += kAttnWarps * kWarpTok) {
+    for (; tb < t1; tb += nwarps * kWarpTok) {
         // scores of the pass: per-lane partial dot products, then one butterfly over the 16 values
         float s[kWarpTok];
 #pragma unroll
@@ -438,7 +443,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_cluster_kernel(uint16
 #pragma unroll
         for (int d = 0; d < DPL; d++) acc[d] = fmaf(acc[d], c, ap[d]);
         mx = mn;
-        if (tb + kAttnWarps * kWarpTok < t1) load_pass(tb + kAttnWarps * kWarpTok);
+        if (tb + nwarps * kWarpTok < t1) load_pass(tb + nwarps * kWarpTok);
     }
     // ---- merge the warps of this CTA (fixed order) ----
 #pragma unroll
@@ -448,12 +453,10 @@ __global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_cluster_kernel(uint16
     if (nsplit > 1) cluster_wait();  // every CTA of the cluster has started: its shared memory may be written
     if (warp == 0) {
         float M_ = -INFINITY, L_ = 0.f, o[DPL];
-#pragma unroll
-        for (int w = 0; w < kAttnWarps; w++) M_ = fmaxf(M_, s_m[w]);
+        for (int w = 0; w < nwarps; w++) M_ = fmaxf(M_, s_m[w]);
 #pragma unroll
         for (int d = 0; d < DPL; d++) o[d] = 0.f;
-#pragma unroll
-        for (int w = 0; w < kAttnWarps; w++) {
+        for (int w = 0; w < nwarps; w++) {
             const float c = s_m[w] == -INFINITY ? 0.f : expf(s_m[w] - M_);
             L_ += s_l[w] * c;
 #pragma unroll
@@ -495,11 +498,11 @@ __global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_cluster_kernel(uint16
 }
 
 template <int DPL>
-cudaError_t launch_attn_cluster(kf_ctx* ctx, dim3 grid, int nsplit, uint16_t* out, const uint16_t* q, const uint16_t* k, const uint16_t* v,
+cudaError_t launch_attn_cluster(kf_ctx* ctx, dim3 grid, int nsplit, int warps, uint16_t* out, const uint16_t* q, const uint16_t* k, const uint16_t* v,
                                 const uint16_t* qw, const uint16_t* kw, uint16_t* kc, uint16_t* vc, const float2* table, const int32_t* pos_dev,
                                 int n_head, int n_kv, float sqrt_hd, float eps, size_t seq_stride) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid, cfg.blockDim = dim3(kAttnWarps * 32), cfg.dynamicSmemBytes = 0, cfg.stream = ctx->stream;
+    cfg.gridDim = grid, cfg.blockDim = dim3(warps * 32), cfg.dynamicSmemBytes = 0, cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
     if (nsplit > 1) {
@@ -526,19 +529,27 @@ extern "C" int kf_qkv_attention(kf_ctx* ctx, void* out, const void* q, const voi
     if (!ctx || !out || !q || !k || !v || !kc || !vc || !table || !pos_dev) return KF_ERR_BAD_ARG;
     KF_REQUIRE(ctx, (hd == 128 || hd == 64) && n_head % n_kv == 0 && M >= 1 && max_seq >= 1, "head_dim 64/128, GQA");
     KF_REQUIRE(ctx, M == 1 || seq_stride > 0, "the fused path needs one sequence per token (use kf_qknorm_rope_kvappend + kf_attn_decode for panels)");
+    if (ctx->debug_skip & 1) return KF_OK;
     int nsplit = ctx->attn_split;
     const int len_hint = std::max(1, std::min(max_seq, max_pos_hint + 1));
-    // contexts up to 1K tokens: slices of 64 tokens (16 per warp, all in flight before the dependency wait) merged inside a cluster
-    if ((nsplit <= 0 && len_hint <= kMaxCluster * kAttnWarps * kWarpTok * 2) || (nsplit > 0 && nsplit <= kMaxCluster)) {
-        if (nsplit <= 0) nsplit = std::max(1, std::min(kMaxCluster, (len_hint + kAttnWarps * kWarpTok - 1) / (kAttnWarps * kWarpTok)));
+    // contexts up to 2K tokens: every cached row of a warp's first pass is in flight before the dependency wait and the slices of a
+    // head are merged inside a cluster.  Measured on B200 (32B decode, ctx 512; profiles/r01_attn_sweep.txt): what matters is that the
+    // whole grid is resident in ONE wave (2 CTAs of 8 warps per SM) -- 4 slices x 8 warps x 8 rows beats 8 x 4 x 16 and the global-
+    // workspace path; an 8-CTA cluster of 8 warps needs two waves and loses 20%.
+    const int warps = ctx->attn_warps > 0 ? std::min(ctx->attn_warps, kClusterWarpsMax) : kClusterWarpsMax;
+    if ((nsplit <= 0 && len_hint <= 4 * kMaxCluster * warps * kWarpTok) || (nsplit > 0 && nsplit <= kMaxCluster)) {
+        if (nsplit <= 0) {
+            const int one_wave = std::max(1, (2 * ctx->sm_count) / (n_head * M));
+            nsplit = std::max(1, std::min(std::min(kMaxCluster, one_wave), (len_hint + 2 * warps * kWarpTok - 1) / (2 * warps * kWarpTok)));
+        }
         dim3 grid(n_head, M, nsplit);
         const float sq = sqrtf((float)hd);
         if (hd == 128)
-            KF_CUDA(ctx, launch_attn_cluster<4>(ctx, grid, nsplit, (uint16_t*)out, (const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v,
+            KF_CUDA(ctx, launch_attn_cluster<4>(ctx, grid, nsplit, warps, (uint16_t*)out, (const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v,
                                                 (const uint16_t*)qw, (const uint16_t*)kw, (uint16_t*)kc, (uint16_t*)vc, (const float2*)table, pos_dev,
                                                 n_head, n_kv, sq, eps, seq_stride));
         else
-            KF_CUDA(ctx, launch_attn_cluster<2>(ctx, grid, nsplit, (uint16_t*)out, (const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v,
+            KF_CUDA(ctx, launch_attn_cluster<2>(ctx, grid, nsplit, warps, (uint16_t*)out, (const uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v,
                                                 (const uint16_t*)qw, (const uint16_t*)kw, (uint16_t*)kc, (uint16_t*)vc, (const float2*)table, pos_dev,
                                                 n_head, n_kv, sq, eps, seq_stride));
         KF_LAUNCH_CHECK(ctx);

@@ -130,6 +130,10 @@ extern "C" int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value) {
         ctx->tc_min_m = value;
     else if (!strcmp(key, "attn_split"))
         ctx->attn_split = value;
+    else if (!strcmp(key, "attn_warps"))
+        ctx->attn_warps = value;
+    else if (!strcmp(key, "debug_skip"))
+        ctx->debug_skip = value;
     else
         return KF_ERR_BAD_ARG;
     return KF_OK;

@@ -39,6 +39,8 @@ struct kf_ctx {
     int gemv_variant = 0;
     int gemv_exact   = 1;  // 1: in-kernel dequant reproduces the reference's bf16 roundings bit for bit ; 0: factored scale/zero (MODE_FACTOR)
     int attn_split   = 0;
+    int attn_warps   = 0;  // warps per CTA of the cluster attention (0 = default)
+    int debug_skip   = 0;  // timing experiments only (results are garbage): bit 0 skips the attention launch, bit 1 the skinny GEMV launches
     // tensor parallel
     ncclComm* nccl = nullptr;
     int rank = 0, world = 1;

@@ -221,7 +221,29 @@ __global__ void __launch_bounds__(1024) kf_argmax_kernel(int32_t* __restrict__ o
     const uint16_t* row = logits + (size_t)blockIdx.x * vocab;
     float best = -INFINITY;
     int bi     = 0x7fffffff;
-    for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+    // 16-byte loads, four per thread in flight (152K logits: ~5 us instead of ~70 with 2-byte loads); a thread visits its indices in
+    // increasing order, so "first maximum wins" needs only the strict comparison here
+    const int nvec = (vocab % 8 == 0 && ((uintptr_t)row & 15) == 0) ? vocab / 8 : 0;
+    for (int i0 = threadIdx.x; i0 < nvec; i0 += blockDim.x * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * blockDim.x;
+            v[u]        = i < nvec ? __ldg(reinterpret_cast<const uint4*>(row) + i) : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int base      = (i0 + u * blockDim.x) * 8;
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float a = bf16lo(w[j]), b = bf16hi(w[j]);
+                if (a > best) best = a, bi = base + 2 * j;
+                if (b > best) best = b, bi = base + 2 * j + 1;
+            }
+        }
+    }
+    for (int i = nvec * 8 + threadIdx.x; i < vocab; i += blockDim.x) {
         const float v = bf16_bits_to_f32(row[i]);
         if (v > best || (v == best && i < bi)) best = v, bi = i;
     }

@@ -507,6 +507,10 @@ def test_swiglu_add_embed_argmax(ctx):
     logits[2, :] = 0x3F80
     am = kf.argmax(ctx, ctx.array(logits), 3, 151936).numpy(np.int32)
     assert am[0] == int(np.argmax(ol.bf16_to_f32(logits[0]))) and am[1] == 5 and am[2] == 0
+    odd = rand_bf16(rng, (2, 1001))  # not a multiple of 8: scalar path
+    odd[1, 1000] = 0x4700
+    am = kf.argmax(ctx, ctx.array(odd), 2, 1001).numpy(np.int32)
+    assert am[0] == int(np.argmax(ol.bf16_to_f32(odd[0]))) and am[1] == 1000
 
 
 @pytest.mark.parametrize("kind", WEIGHT_KINDS, ids=str)
