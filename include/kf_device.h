@@ -163,6 +163,12 @@ int kf_qkv_attention(kf_ctx* ctx, void* out_dev, const void* q_dev, const void* 
                      const void* knorm_w_dev, void* kcache_layer_dev, void* vcache_layer_dev, const void* rope_table_dev,
                      const int32_t* pos_dev, int M, int n_head, int n_kv, int head_dim, int max_seq, float eps, size_t seq_stride,
                      int max_pos_hint);
+/* ---- prefill attention: causal attention of a panel of M CONSECUTIVE tokens of one sequence (positions pos_dev[0] + m) over the
+ *      cache rows [0, pos_dev[0] + M).  q_dev must already be normalised + rotated and the panel's K / V rows appended
+ *      (kf_qknorm_rope_kvappend).  Replaces the reference's token-by-token prompt loop (src/Manifold/GoPT.cpp:1111-1235) through
+ *      attention_qk / softmax / attention_v (src/Device/CUDA/kernel/operator.cuh:573-668); flash-attention on mma.sync tensor cores. ---- */
+int kf_attn_prefill(kf_ctx* ctx, void* out_dev, const void* q_dev, const void* kcache_layer_dev, const void* vcache_layer_dev,
+                    const int32_t* pos_dev, int M, int n_head, int n_kv, int head_dim, int max_seq);
 /* ---- CU_swiglu_v0 (Activation.cu:86-93), CU_add3 (packedN.cuh:867-875) as stand-alone ops ---- */
 int kf_swiglu(kf_ctx* ctx, void* out_dev, const void* gate_dev, const void* up_dev, size_t n);
 int kf_add(kf_ctx* ctx, void* out_dev, const void* a_dev, const void* b_dev, size_t n);

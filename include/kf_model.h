@@ -52,8 +52,11 @@ void* kf_model_vcache(kf_model* m, int layer);
 
 /* One forward over M tokens (Fish::ForwardOnRLS; one call per token in the reference's Chat loop, GoPT.cpp:1139-1146).
  *   seq_mode 0: the M tokens are consecutive positions of ONE sequence (prefill panel; M <= max_tokens);
- *   seq_mode 1: M independent sequences, one token each (batched decode; M <= gpt.max_batch).
- * tokens_host / pos_host: int32[M].  logits_host (optional): bf16 [M][vocab].  next_host (optional): int32[M] greedy argmax.
+ *   seq_mode 1: M independent sequences, one token each (batched decode; M <= gpt.max_batch);
+ *   seq_mode 2: as 0, but logits_host / next_host receive ONE row: the last token of the panel (long prompts: gpt.max_prefill
+ *               sizes the panel, default 64; consecutive positions run the tensor-core flash attention kf_attn_prefill).
+ * tokens_host / pos_host: int32[M].  logits_host (optional): bf16 [M][vocab] (modes 0 / 1: M <= max(64, gpt.max_batch)).
+ * next_host (optional): int32[M] greedy argmax.
  * Synchronous: returns after the results are in host memory. */
 int kf_model_forward(kf_model* m, const int32_t* tokens_host, const int32_t* pos_host, int M, int seq_mode, void* logits_host,
                      int32_t* next_host);

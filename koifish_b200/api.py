@@ -236,6 +236,13 @@ def attn_decode(ctx, q, kcache, vcache, pos, M, n_head, n_kv, hd, max_seq, max_p
     return out
 
 
+def attn_prefill(ctx, q, kcache, vcache, pos, M, n_head, n_kv, hd, max_seq):
+    """causal attention of a panel of M consecutive tokens of one sequence (pos[0] = position of the first)"""
+    out = ctx.empty(M * n_head * hd * 2)
+    ctx.check(ctx.lib.kf_attn_prefill(ctx.h, out.ptr, q.ptr, kcache.ptr, vcache.ptr, pos.ptr, M, n_head, n_kv, hd, max_seq), "kf_attn_prefill")
+    return out
+
+
 def qkv_attention(ctx, q, k, v, qw, kw, kcache, vcache, table, pos, M, n_head, n_kv, hd, max_seq, max_pos_hint, eps=1e-6, seq_stride=0):
     """QK-norm + RoPE + KV append + split-K attention in one launch (decode: one sequence per token)"""
     out = ctx.empty(M * n_head * hd * 2)
@@ -335,11 +342,25 @@ class Model:
         pos = np.ascontiguousarray(pos, dtype=np.int32).reshape(-1)
         M = tokens.size
         vocab = self.info.vocab
-        logits = np.empty((M, vocab), dtype=np.uint16) if want_logits else None
-        nxt = np.empty(M, dtype=np.int32) if want_next else None
+        R = 1 if seq_mode == 2 else M  # seq_mode 2: prefill panel, outputs of the last token only
+        logits = np.empty((R, vocab), dtype=np.uint16) if want_logits else None
+        nxt = np.empty(R, dtype=np.int32) if want_next else None
         self._check(self.lib.kf_model_forward(self.h, tokens.ctypes.data, pos.ctypes.data, M, seq_mode,
                                               logits.ctypes.data if want_logits else None, nxt.ctypes.data if want_next else None), "kf_model_forward")
         return logits, nxt
+
+    def prefill(self, tokens, pos0=0, want_logits=False):
+        """run a prompt through in panels of info.max_tokens; returns (logits of the last token or None, greedy next token).  Leaves
+        the model ready for decode_loop(n, 1)."""
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32).reshape(-1)
+        P = self.info.max_tokens
+        logits = nxt = None
+        for s in range(0, tokens.size, P):
+            part = tokens[s:s + P]
+            last = s + P >= tokens.size
+            logits, nxt = self.forward(part, np.arange(pos0 + s, pos0 + s + part.size), seq_mode=2, want_logits=want_logits and last,
+                                       want_next=last)
+        return logits, (int(nxt[0]) if nxt is not None else None)
 
     def decode_loop(self, n_steps, M=1):
         self._check(self.lib.kf_model_decode_loop(self.h, n_steps, M), "kf_model_decode_loop")
@@ -368,7 +389,7 @@ class Model:
 
 
 def qwen3_config(n_layer, n_embd, n_ff, n_head, n_kv_head, head_dim=128, vocab=151936, quantizer=None, tie=False, max_seq_len=1024,
-                 max_batch=1, seed=42, rope_theta=None, sigma=None, norm_sigma=None):
+                 max_batch=1, seed=42, rope_theta=None, sigma=None, norm_sigma=None, max_prefill=None):
     """a Koifish-style JSON config (reference cases/qwen3/qwen3_596M_q4.json layout) as a dict"""
     cfg = {
         "version": "0.1.0",
@@ -379,6 +400,8 @@ def qwen3_config(n_layer, n_embd, n_ff, n_head, n_kv_head, head_dim=128, vocab=1
         "gpt": {"max_seq_len": max_seq_len, "max_batch": max_batch},
         "seed": seed,
     }
+    if max_prefill is not None:
+        cfg["gpt"]["max_prefill"] = max_prefill  # tokens per prefill panel (activation buffers); default 64
     if rope_theta is not None:
         cfg["model"]["parameter"]["rope_theta"] = rope_theta
     if quantizer:

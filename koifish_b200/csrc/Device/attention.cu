@@ -519,6 +519,161 @@ cudaError_t launch_attn_cluster(kf_ctx* ctx, dim3 grid, int nsplit, int warps, u
     return cudaLaunchKernelEx(&cfg, kf_attn_cluster_kernel<DPL>, out, q, k, v, qw, kw, kc, vc, table, pos_dev, n_head, n_kv, nsplit, sqrt_hd, eps,
                               seq_stride);
 }
+
+// ---- prefill: causal attention of a panel of M consecutive tokens of ONE sequence over the cache rows [0, pos0 + M) ------------------
+// Replaces running the three decode kernels once per prompt token (the reference's Generate loop feeds the prompt token by token,
+// src/Manifold/GoPT.cpp:1111-1235).  Flash-attention forward on the legacy tensor-core path (mma.sync m16n8k16 bf16, fp32 accumulate):
+// a CTA owns 64 query rows of one head (4 warps x 16 rows, Q fragments in registers), streams 64-token K / V tiles of the head's kv
+// group through a cp.async double buffer (16-byte chunks XOR-swizzled by row so every ldmatrix is conflict-free), keeps the running
+// (max, sum) per row and the 16 x hd output tile in registers.  Scores s = (q.k)/sqrt(hd) and the softmax are fp32; P is rounded to
+// bf16 for the P.V product (the reference's neuron path stores the scores as bf16 as well, TGraph.cpp:123-124).
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+constexpr int kPfQ = 64, kPfKV = 64;
+
+template <int HD>
+__global__ void __launch_bounds__(128) kf_attn_prefill_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ q,
+                                                              const uint16_t* __restrict__ kc, const uint16_t* __restrict__ vc,
+                                                              const int32_t* __restrict__ pos_dev, int M, int n_head, int n_kv, int max_seq,
+                                                              float sqrt_hd) {
+    constexpr int CH = HD / 8;  // 16-byte chunks per row
+    extern __shared__ __align__(16) uint8_t pf_smem[];
+    const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(pf_smem);
+    const uint32_t sK = sQ + kPfQ * HD * 2;            // two K tiles
+    const uint32_t sV = sK + 2 * kPfKV * HD * 2;       // two V tiles
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;  // heavy (late) query tiles first
+    const int h = blockIdx.y, kvh = h / (n_head / n_kv), kv_dim = n_kv * HD, q_dim = n_head * HD;
+    const int pos0 = pos_dev[0];
+    const int q0 = qt * kPfQ;
+    const int kv_len = pos0 + min(M, q0 + kPfQ);  // rows visible to the last query row of this tile
+    const int ntiles = (kv_len + kPfKV - 1) / kPfKV;
+    auto sw = [](int row, int c) { return (uint32_t)((row * CH + (c ^ (row & 7))) * 16); };
+
+    // ---- Q tile + first K / V tile ----
+    for (int i = tid; i < kPfQ * CH; i += 128) {
+        const int r = i / CH, c = i % CH;
+        const bool ok = q0 + r < M;
+        cp16(sQ + sw(r, c), q + (size_t)(ok ? q0 + r : 0) * q_dim + (size_t)h * HD + c * 8, ok);
+    }
+    auto load_kv = [&](int kt, int buf) {
+        for (int i = tid; i < kPfKV * CH; i += 128) {
+            const int r = i / CH, c = i % CH;
+            const int t = min(kt * kPfKV + r, max_seq - 1);  // rows past kv_len are masked below; keep the address inside the cache
+            cp16(sK + buf * (kPfKV * HD * 2) + sw(r, c), kc + (size_t)t * kv_dim + (size_t)kvh * HD + c * 8, true);
+            cp16(sV + buf * (kPfKV * HD * 2) + sw(r, c), vc + (size_t)t * kv_dim + (size_t)kvh * HD + c * 8, true);
+        }
+    };
+    load_kv(0, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    uint32_t qa[HD / 16][4];
+    float o[HD / 8][4];
+#pragma unroll
+    for (int j = 0; j < HD / 8; j++) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+    const int p_lo = pos0 + q0 + warp * 16 + g, p_hi = p_lo + 8;  // positions of this thread's two query rows
+    const float LOG2E = 1.4426950408889634f;
+
+    for (int kt = 0; kt < ntiles; kt++) {
+        const int buf = kt & 1;
+        if (kt + 1 < ntiles) load_kv(kt + 1, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        if (kt == 0) {
+#pragma unroll
+            for (int kc_ = 0; kc_ < HD / 16; kc_++) ldsm_x4(qa[kc_], sQ + sw(warp * 16 + (lane & 15), kc_ * 2 + (lane >> 4)));
+        }
+        const uint32_t kb = sK + buf * (kPfKV * HD * 2), vb = sV + buf * (kPfKV * HD * 2);
+        // ---- S = Q K^T (16 x 64 per warp) ----
+        float sc[kPfKV / 8][4];
+#pragma unroll
+        for (int j = 0; j < kPfKV / 8; j++) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+        for (int kc_ = 0; kc_ < HD / 16; kc_++) {
+#pragma unroll
+            for (int jp = 0; jp < kPfKV / 16; jp++) {
+                uint32_t b[4];
+                ldsm_x4(b, kb + sw(jp * 16 + (lane & 7) + (lane >> 4) * 8, kc_ * 2 + ((lane >> 3) & 1)));
+                mma_bf16(sc[2 * jp], qa[kc_], b[0], b[1]);
+                mma_bf16(sc[2 * jp + 1], qa[kc_], b[2], b[3]);
+            }
+        }
+        // ---- scale, causal mask, online softmax (rows g and g + 8 of the warp's 16) ----
+        float mx_lo = -INFINITY, mx_hi = -INFINITY;
+        const bool diag = (kt + 1) * kPfKV > pos0 + q0;  // only tiles that reach the panel can contain masked columns
+#pragma unroll
+        for (int j = 0; j < kPfKV / 8; j++) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float v = sc[j][e] / sqrt_hd;  // the reference divides (operator.cuh:630)
+                if (diag) {
+                    const int tcol = kt * kPfKV + j * 8 + 2 * t4 + (e & 1);
+                    if (tcol > ((e & 2) ? p_hi : p_lo)) v = -INFINITY;
+                }
+                sc[j][e] = v;
+            }
+            mx_lo = fmaxf(mx_lo, fmaxf(sc[j][0], sc[j][1]));
+            mx_hi = fmaxf(mx_hi, fmaxf(sc[j][2], sc[j][3]));
+        }
+        mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)), mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+        mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)), mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+        const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
+        const float base_lo = mn_lo == -INFINITY ? 0.f : mn_lo, base_hi = mn_hi == -INFINITY ? 0.f : mn_hi;  // fully masked row so far
+        const float c_lo = exp2f((m_lo - base_lo) * LOG2E), c_hi = exp2f((m_hi - base_hi) * LOG2E);
+        m_lo = mn_lo, m_hi = mn_hi;
+        float rs_lo = 0.f, rs_hi = 0.f;
+        uint32_t pa[kPfKV / 16][4];
+#pragma unroll
+        for (int j = 0; j < kPfKV / 8; j++) {
+            const float p0 = exp2f((sc[j][0] - base_lo) * LOG2E), p1 = exp2f((sc[j][1] - base_lo) * LOG2E);
+            const float p2 = exp2f((sc[j][2] - base_hi) * LOG2E), p3 = exp2f((sc[j][3] - base_hi) * LOG2E);
+            rs_lo += p0 + p1, rs_hi += p2 + p3;
+            pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);  // A fragment of P for the 16 tokens of n-tiles (2i, 2i+1)
+            pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+        l_lo = l_lo * c_lo + rs_lo, l_hi = l_hi * c_hi + rs_hi;
+#pragma unroll
+        for (int j = 0; j < HD / 8; j++) o[j][0] *= c_lo, o[j][1] *= c_lo, o[j][2] *= c_hi, o[j][3] *= c_hi;
+        // ---- O += P V ----
+#pragma unroll
+        for (int kc_ = 0; kc_ < kPfKV / 16; kc_++) {
+#pragma unroll
+            for (int jp = 0; jp < HD / 16; jp++) {
+                uint32_t b[4];
+                ldsm_x4_t(b, vb + sw(kc_ * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, jp * 2 + (lane >> 4)));
+                mma_bf16(o[2 * jp], pa[kc_], b[0], b[1]);
+                mma_bf16(o[2 * jp + 1], pa[kc_], b[2], b[3]);
+            }
+        }
+        __syncthreads();  // the other buffer is refilled at the top of the next iteration
+    }
+    // ---- normalise and store ----
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1), l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1), l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+    const int r_lo = q0 + warp * 16 + g, r_hi = r_lo + 8;
+#pragma unroll
+    for (int j = 0; j < HD / 8; j++) {
+        const int d = j * 8 + 2 * t4;
+        if (r_lo < M) *reinterpret_cast<uint32_t*>(out + (size_t)r_lo * q_dim + (size_t)h * HD + d) = pack_bf16x2(o[j][0] * i_lo, o[j][1] * i_lo);
+        if (r_hi < M) *reinterpret_cast<uint32_t*>(out + (size_t)r_hi * q_dim + (size_t)h * HD + d) = pack_bf16x2(o[j][2] * i_hi, o[j][3] * i_hi);
+    }
+}
 }  // namespace
 
 // ROPE::cuInfer (rope.cu:645-672) + attention_qk / softmax / attention_v (operator.cuh:573-668) of SelfAttention::cuInfer (QKV.cu:660-674)
@@ -617,5 +772,35 @@ extern "C" int kf_attn_decode(kf_ctx* ctx, void* out, const void* q, const void*
             kf_attn_combine_kernel<2><<<g2, 64, 0, ctx->stream>>>((uint16_t*)out, ws, n_head, nsplit);
         KF_LAUNCH_CHECK(ctx);
     }
+    return KF_OK;
+}
+
+// Causal attention of a prefill panel: the M query rows q_dev[m] (already normalised + rotated, kf_qknorm_rope_kvappend) sit at the
+// consecutive positions pos_dev[0] + m of ONE sequence whose K / V rows [0, pos_dev[0] + M) are in the cache layer.
+extern "C" int kf_attn_prefill(kf_ctx* ctx, void* out, const void* q, const void* kc, const void* vc, const int32_t* pos_dev, int M, int n_head,
+                               int n_kv, int hd, int max_seq) {
+    if (!ctx || !out || !q || !kc || !vc || !pos_dev) return KF_ERR_BAD_ARG;
+    KF_REQUIRE(ctx, (hd == 128 || hd == 64) && n_head % n_kv == 0 && M >= 1 && max_seq >= 1, "head_dim 64/128, GQA");
+    const size_t smem = (size_t)(kPfQ + 4 * kPfKV) * hd * 2;
+    dim3 grid((M + kPfQ - 1) / kPfQ, n_head);
+    const float sq = sqrtf((float)hd);
+    if (hd == 128) {
+        static bool set = false;
+        if (!set) {
+            KF_CUDA(ctx, cudaFuncSetAttribute(kf_attn_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set = true;
+        }
+        kf_attn_prefill_kernel<128><<<grid, 128, smem, ctx->stream>>>((uint16_t*)out, (const uint16_t*)q, (const uint16_t*)kc, (const uint16_t*)vc,
+                                                                      pos_dev, M, n_head, n_kv, max_seq, sq);
+    } else {
+        static bool set = false;
+        if (!set) {
+            KF_CUDA(ctx, cudaFuncSetAttribute(kf_attn_prefill_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set = true;
+        }
+        kf_attn_prefill_kernel<64><<<grid, 128, smem, ctx->stream>>>((uint16_t*)out, (const uint16_t*)q, (const uint16_t*)kc, (const uint16_t*)vc,
+                                                                     pos_dev, M, n_head, n_kv, max_seq, sq);
+    }
+    KF_LAUNCH_CHECK(ctx);
     return KF_OK;
 }

@@ -59,6 +59,7 @@ MODEL_CARD MODEL_CARD::FromJSON(const JSON& j0) {
     c.seed        = jint(j0, {"seed"}, c.seed);
     c.max_seq_len = jint(j0, {"gpt", "max_seq_len"}, c.max_seq_len);
     c.max_batch   = jint(j0, {"gpt", "max_batch"}, c.max_batch);
+    c.max_prefill = jint(j0, {"gpt", "max_prefill"}, c.max_prefill);
     if (const JSON* s = j0.path({"init", "sigma"})) c.init_sigma = (float)s->as_double(c.init_sigma);
     if (const JSON* s = j0.path({"init", "norm_sigma"})) c.norm_sigma = (float)s->as_double(c.norm_sigma);
     std::string a = c.arch;
@@ -109,8 +110,12 @@ int SelfAttention::cuInfer(void* inpL, int M) {
                                 rope.table, f->d_pos, M, n_head, n_head_kv, head_dim, f->cache.max_seq, 1e-6f, ss, f->attn_hint));
     } else {  // prefill panel: the tokens attend to each other's fresh K/V rows, so the append must complete first
         KF_TRY(rope.cuInfer(this, M));
-        KF_TRY(kf_attn_decode(f->ctx, f->att, f->q, f->cache.Get(KVCache::KV_KEY, lay), f->cache.Get(KVCache::KV_VAL, lay), f->d_pos, M, n_head,
-                              n_head_kv, head_dim, f->cache.max_seq, f->attn_hint, ss));
+        if (M >= 16 && f->panel_consecutive)  // tensor-core flash attention over the panel (positions pos[0] .. pos[0] + M - 1)
+            KF_TRY(kf_attn_prefill(f->ctx, f->att, f->q, f->cache.Get(KVCache::KV_KEY, lay), f->cache.Get(KVCache::KV_VAL, lay), f->d_pos, M, n_head,
+                                   n_head_kv, head_dim, f->cache.max_seq));
+        else
+            KF_TRY(kf_attn_decode(f->ctx, f->att, f->q, f->cache.Get(KVCache::KV_KEY, lay), f->cache.Get(KVCache::KV_VAL, lay), f->d_pos, M, n_head,
+                                  n_head_kv, head_dim, f->cache.max_seq, f->attn_hint, ss));
     }
     const size_t nE = (size_t)M * f->config.n_embd;
     if (f->tp_world == 1) {
@@ -168,7 +173,7 @@ int Head4Token::cuInfer_1(void* logits, const void* inp, int M) {
     }
     d.rows = vl;
     // local logits land in the tail of the buffer, then all ranks' pieces are gathered to the front: [W][M][vl]
-    uint16_t* local = (uint16_t*)logits + (size_t)f->max_tokens * f->config.vocab;
+    uint16_t* local = (uint16_t*)logits + (size_t)f->logit_rows * f->config.vocab;
     KF_TRY(kf_linear(f->ctx, local, &d, f->xb, M, KF_EPI_NONE, nullptr));
     KF_TRY(kf_allgather(f->ctx, logits, local, (size_t)M * vl * 2));
     if (M > 1) {  // [W][M][vl] -> [M][W*vl]
@@ -270,7 +275,8 @@ int Fish::Build() {
     KF_TRY(kf_malloc(ctx, cache.bytes() / 2, &cache.value));
     KF_TRY(kf_memset(ctx, cache.key, 0, cache.bytes() / 2));
     KF_TRY(kf_memset(ctx, cache.value, 0, cache.bytes() / 2));
-    max_tokens = std::max(64, c.max_batch);
+    max_tokens = std::max(std::max(64, c.max_batch), c.max_prefill);
+    logit_rows = std::max(64, c.max_batch);
     const size_t T = max_tokens;
     KF_TRY(kf_malloc(ctx, T * E * 2, &x));
     KF_TRY(kf_malloc(ctx, T * E * 2, &xb));
@@ -279,13 +285,13 @@ int Fish::Build() {
     KF_TRY(kf_malloc(ctx, T * KD * 2, &v));
     KF_TRY(kf_malloc(ctx, T * QD * 2, &att));
     KF_TRY(kf_malloc(ctx, T * ff * 2, &hb));
-    KF_TRY(kf_malloc(ctx, T * c.vocab * 2 * (W > 1 ? 2 : 1), &logits));
+    KF_TRY(kf_malloc(ctx, (size_t)logit_rows * c.vocab * 2 * (W > 1 ? 2 : 1), &logits));
     if (W > 1) KF_TRY(kf_malloc(ctx, T * E * 4, (void**)&part_f32));
     KF_TRY(kf_malloc(ctx, T * 4, (void**)&d_tokens));
     KF_TRY(kf_malloc(ctx, T * 4, (void**)&d_pos));
     KF_TRY(kf_malloc(ctx, T * 4, (void**)&d_next));
     KF_TRY(kf_host_alloc(T * 4 * 3, (void**)&h_stage));
-    KF_TRY(kf_host_alloc(T * c.vocab * 2, (void**)&h_logits));
+    KF_TRY(kf_host_alloc((size_t)logit_rows * c.vocab * 2, (void**)&h_logits));
     // one rope table shared by all layers
     void* table = nullptr;
     KF_TRY(kf_malloc(ctx, (size_t)c.max_seq_len * (hd / 2) * 8, &table));
@@ -408,12 +414,19 @@ int Fish::ForwardOnRLS(int M, bool want_logits) {
         KF_TRY(attn[l]->cuInfer(x, M));
         KF_TRY(ffn[l]->cuInfer(x, M));
     }
-    if (want_logits) KF_TRY(cls.cuInfer_1(logits, x, M));
+    if (want_logits) {
+        if (last_only)  // prefill: only the last token of the panel feeds the sampler
+            KF_TRY(cls.cuInfer_1(logits, (uint16_t*)x + (size_t)(M - 1) * config.n_embd, 1));
+        else
+            KF_TRY(cls.cuInfer_1(logits, x, M));
+    }
     return KF_OK;
 }
 
-// graph key: M | want_logits<<8 | seq_mode<<9 | feedback<<10
-int Fish::UseGraph(int M, bool want_logits) { return (M & 0xff) | ((int)want_logits << 8) | (seq_mode << 9); }
+// graph key: M<<8 | want_logits | seq_mode<<1 | feedback<<2 | argmax<<3 | last_only<<5 | consecutive<<6
+int Fish::UseGraph(int M, bool want_logits) {
+    return (M << 8) | (int)want_logits | (seq_mode << 1) | ((int)last_only << 5) | ((int)panel_consecutive << 6);
+}
 
 int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, uint16_t* logits_out, int32_t* next_out) {
     std::string* hFishErr = &error;
@@ -421,7 +434,7 @@ int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, ui
         error = "Forward: 1 <= M <= " + std::to_string(max_tokens);
         return KF_ERR_BAD_ARG;
     }
-    if (mode && M > config.max_batch) {
+    if (mode == 1 && M > config.max_batch) {
         error = "Forward: batched decode needs gpt.max_batch >= M";
         return KF_ERR_BAD_ARG;
     }
@@ -433,16 +446,24 @@ int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, ui
         h_stage[m] = tokens[m], h_stage[max_tokens + m] = pos[m];
     }
     staged_pos_max = *std::max_element(pos, pos + M);
-    seq_mode = mode ? 1 : 0;
+    seq_mode = mode == 1 ? 1 : 0;
+    last_only = mode == 2;
+    panel_consecutive = seq_mode == 0;
+    for (int m = 1; m < M && panel_consecutive; m++) panel_consecutive = pos[m] == pos[0] + m;
+    const int R = last_only ? 1 : M;  // rows of logits / argmax produced
+    if ((logits_out || next_out) && R > logit_rows) {
+        error = "Forward: logits of more than " + std::to_string(logit_rows) + " tokens requested; use seq_mode 2 (last token only) for long panels";
+        return KF_ERR_BAD_ARG;
+    }
     KF_TRY(kf_h2d(ctx, d_tokens, h_stage, (size_t)M * 4));
     KF_TRY(kf_h2d(ctx, d_pos, h_stage + max_tokens, (size_t)M * 4));
     const bool want_logits = logits_out || next_out;
-    const int key          = UseGraph(M, want_logits) | ((next_out ? 1 : 0) << 11);
+    const int key          = UseGraph(M, want_logits) | ((next_out ? 1 : 0) << 3);
     auto it                = graphs.find(key);
     if (use_graphs && it == graphs.end() && warm.count(key)) {  // second call with this signature: capture it
         KF_TRY(kf_graph_begin(ctx));
         int rc = ForwardOnRLS(M, want_logits);
-        if (!rc && next_out) rc = kf_argmax(ctx, d_next, logits, M, config.vocab);
+        if (!rc && next_out) rc = kf_argmax(ctx, d_next, logits, R, config.vocab);
         kf_graph* g = nullptr;
         int rc2     = kf_graph_end(ctx, &g);
         if (rc || rc2) {
@@ -456,14 +477,21 @@ int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, ui
         KF_TRY(kf_graph_launch(ctx, it->second));
     } else {
         KF_TRY(ForwardOnRLS(M, want_logits));
-        if (next_out) KF_TRY(kf_argmax(ctx, d_next, logits, M, config.vocab));
+        if (next_out) KF_TRY(kf_argmax(ctx, d_next, logits, R, config.vocab));
         warm.insert(key);
     }
-    if (logits_out) KF_TRY(kf_d2h(ctx, h_logits, logits, (size_t)M * config.vocab * 2));
-    if (next_out) KF_TRY(kf_d2h(ctx, h_stage + 2 * max_tokens, d_next, (size_t)M * 4));
+    if (logits_out) KF_TRY(kf_d2h(ctx, h_logits, logits, (size_t)R * config.vocab * 2));
+    if (next_out) KF_TRY(kf_d2h(ctx, h_stage + 2 * max_tokens, d_next, (size_t)R * 4));
     KF_TRY(kf_ctx_sync(ctx));
-    if (logits_out) memcpy(logits_out, h_logits, (size_t)M * config.vocab * 2);
-    if (next_out) memcpy(next_out, h_stage + 2 * max_tokens, (size_t)M * 4);
+    if (logits_out) memcpy(logits_out, h_logits, (size_t)R * config.vocab * 2);
+    if (next_out) memcpy(next_out, h_stage + 2 * max_tokens, (size_t)R * 4);
+    if (last_only && next_out) {  // leave the model ready for DecodeLoop(n, 1): feed the sampled token at the next position
+        h_stage[0] = next_out[0], h_stage[max_tokens] = pos[M - 1] + 1;
+        KF_TRY(kf_h2d(ctx, d_tokens, h_stage, 4));
+        KF_TRY(kf_h2d(ctx, d_pos, h_stage + max_tokens, 4));
+        KF_TRY(kf_ctx_sync(ctx));
+        staged_pos_max = pos[M - 1] + 1;
+    }
     return KF_OK;
 }
 
@@ -477,7 +505,8 @@ int Fish::DecodeLoop(int n_steps, int M) {
         return KF_ERR_BAD_ARG;
     }
     staged_pos_max += n_steps;
-    const int key = UseGraph(M, true) | (1 << 10);
+    seq_mode = M > 1 ? 1 : seq_mode, last_only = false, panel_consecutive = false;
+    const int key = UseGraph(M, true) | (1 << 2);
     auto it       = graphs.find(key);
     auto body     = [&]() -> int {
         int rc = ForwardOnRLS(M, true);

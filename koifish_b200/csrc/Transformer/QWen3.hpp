@@ -32,6 +32,7 @@ struct MODEL_CARD {
     int seed = 42;
     float init_sigma = 0.02f, norm_sigma = 0.0f;  // huTensor.cu:204 ; norms FIX_1
     int max_batch = 1;                            // independent sequences (batched decode)
+    int max_prefill = 64;                         // tokens per prefill panel (gpt.max_prefill): sizes the activation buffers
 
     // accepts a Koifish JSON (cases/qwen3/*.json layout) or an HF config.json, optionally wrapped as {"hf_config": {...}}
     static MODEL_CARD FromJSON(const JSON& j);
@@ -124,6 +125,9 @@ struct Fish {
     int32_t* h_stage  = nullptr;  // pinned staging: tokens | pos | next
     uint16_t* h_logits = nullptr; // pinned
     int seq_mode = 0;             // 0: the M tokens of a forward are one sequence (prefill) ; 1: M independent sequences
+    int logit_rows = 0;           // rows of the logits buffers (max(64, max_batch)); bigger panels report the last token only
+    bool panel_consecutive = false;  // prefill panel at positions pos[0] .. pos[0] + M - 1 -> tensor-core flash attention
+    bool last_only = false;       // mode 2: logits / argmax of the last token of the panel only
     int attn_hint = 0;
     std::map<int, kf_graph*> graphs;  // per (M, mode) replayable token graphs
     std::set<int> warm;               // signatures that already ran eagerly once (workspaces sized) -> next call captures

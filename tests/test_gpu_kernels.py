@@ -567,3 +567,24 @@ def test_gemm_tc_onehot_small_m(ctx):
             ctx.set_int("tc_min_m", -1)
         for m in range(M):
             assert np.array_equal(ol.bf16_to_f32(y[m]), ol.bf16_to_f32(wdq[:, ks[m]])), (kind, m)
+
+
+# ---------------------------------------------------------------------------------------------- prefill (flash) attention
+@pytest.mark.parametrize("hd,n_head,n_kv", [(128, 8, 2), (64, 4, 4)])
+@pytest.mark.parametrize("M,pos0", [(16, 0), (64, 0), (100, 37), (200, 300), (65, 511)])
+def test_attn_prefill_equals_per_token_decode_attention(ctx, hd, n_head, n_kv, M, pos0):
+    # the panel's queries at positions pos0 .. pos0 + M - 1 over cache rows [0, pos0 + M): the tensor-core flash kernel against the
+    # per-token decode kernel (itself pinned to the oracle above) and against the oracle for a few rows
+    rng = np.random.default_rng(M * 7 + pos0 + hd)
+    max_seq = 768
+    q = rand_bf16(rng, (M, n_head * hd))
+    kc, vc = rand_bf16(rng, (max_seq, n_kv * hd)), rand_bf16(rng, (max_seq, n_kv * hd))
+    pos = np.arange(pos0, pos0 + M, dtype=np.int32)
+    qd, kcd, vcd, posd = ctx.array(q), ctx.array(kc), ctx.array(vc), ctx.array(pos)
+    want = kf.attn_decode(ctx, qd, kcd, vcd, posd, M, n_head, n_kv, hd, max_seq, pos0 + M - 1).numpy(np.uint16)
+    got = kf.attn_prefill(ctx, qd, kcd, vcd, posd, M, n_head, n_kv, hd, max_seq).numpy(np.uint16)
+    g, w = ol.bf16_to_f32(got), ol.bf16_to_f32(want)
+    assert np.allclose(g, w, rtol=2.0 ** -6, atol=6e-3), np.abs(g - w).max()
+    for m in (0, M // 2, M - 1):
+        ref = ol.attention_decode(q[m], kc, vc, int(pos[m]), n_head, n_kv, hd)
+        assert np.allclose(g.reshape(M, -1)[m], ol.bf16_to_f32(ref).reshape(-1), rtol=2.0 ** -6, atol=6e-3)
