@@ -169,6 +169,11 @@ int kf_qkv_attention(kf_ctx* ctx, void* out_dev, const void* q_dev, const void* 
  *      attention_qk / softmax / attention_v (src/Device/CUDA/kernel/operator.cuh:573-668); flash-attention on mma.sync tensor cores. ---- */
 int kf_attn_prefill(kf_ctx* ctx, void* out_dev, const void* q_dev, const void* kcache_layer_dev, const void* vcache_layer_dev,
                     const int32_t* pos_dev, int M, int n_head, int n_kv, int head_dim, int max_seq);
+/* ---- decode attention for many sequences per step: same contract as kf_attn_decode, but the query heads that share a kv head are
+ *      processed together on the tensor cores, so every cached row is read once per kv head instead of once per query head
+ *      (batched decode; replaces the same reference kernels, operator.cuh:573-668).  n_head / n_kv <= 16. ---- */
+int kf_attn_decode_gqa(kf_ctx* ctx, void* out_dev, const void* q_dev, const void* kcache_layer_dev, const void* vcache_layer_dev,
+                       const int32_t* pos_dev, int M, int n_head, int n_kv, int head_dim, int max_seq, int max_pos_hint, size_t seq_stride);
 /* ---- CU_swiglu_v0 (Activation.cu:86-93), CU_add3 (packedN.cuh:867-875) as stand-alone ops ---- */
 int kf_swiglu(kf_ctx* ctx, void* out_dev, const void* gate_dev, const void* up_dev, size_t n);
 int kf_add(kf_ctx* ctx, void* out_dev, const void* a_dev, const void* b_dev, size_t n);

@@ -76,6 +76,7 @@ SIGNATURES = {
     "kf_qknorm_rope_kvappend": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _SZ]),
     "kf_attn_decode": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _SZ]),
     "kf_attn_prefill": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
+    "kf_attn_decode_gqa": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _SZ]),
     "kf_qkv_attention": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _SZ, _I]),
     "kf_swiglu": (_I, [_P, _P, _P, _P, _SZ]),
     "kf_add": (_I, [_P, _P, _P, _P, _SZ]),

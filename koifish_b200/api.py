@@ -236,6 +236,14 @@ def attn_decode(ctx, q, kcache, vcache, pos, M, n_head, n_kv, hd, max_seq, max_p
     return out
 
 
+def attn_decode_gqa(ctx, q, kcache, vcache, pos, M, n_head, n_kv, hd, max_seq, max_pos_hint, seq_stride=0):
+    """decode attention with the query heads of a kv group processed together on the tensor cores (batched decode)"""
+    out = ctx.empty(M * n_head * hd * 2)
+    ctx.check(ctx.lib.kf_attn_decode_gqa(ctx.h, out.ptr, q.ptr, kcache.ptr, vcache.ptr, pos.ptr, M, n_head, n_kv, hd, max_seq, max_pos_hint,
+                                         seq_stride), "kf_attn_decode_gqa")
+    return out
+
+
 def attn_prefill(ctx, q, kcache, vcache, pos, M, n_head, n_kv, hd, max_seq):
     """causal attention of a panel of M consecutive tokens of one sequence (pos[0] = position of the first)"""
     out = ctx.empty(M * n_head * hd * 2)

@@ -674,6 +674,153 @@ __global__ void __launch_bounds__(128) kf_attn_prefill_kernel(uint16_t* __restri
         if (r_hi < M) *reinterpret_cast<uint32_t*>(out + (size_t)r_hi * q_dim + (size_t)h * HD + d) = pack_bf16x2(o[j][2] * i_hi, o[j][3] * i_hi);
     }
 }
+
+// ---- batched decode: the `group` query heads that share a kv head are processed TOGETHER on the tensor cores --------------------------
+// With many sequences per step the per-head kernels above read every cached K / V row once per QUERY head (8x for Qwen3-32B) and
+// need thousands of latency-bound CTAs.  Here a CTA owns one (sequence, kv head): the group's query rows (<= 16, zero padded) are the
+// A operand of mma.sync m16n8k16, the cached rows stream once through a cp.async double buffer in 64-token tiles (each warp takes 16
+// tokens of a tile), and softmax / P.V follow the flash recipe of the prefill kernel.  The warps' partial (max, sum, acc) are merged
+// through shared memory; long contexts are split over CTAs and merged by kf_attn_combine_kernel.  q must already be normalised +
+// rotated and the new K / V rows appended (kf_qknorm_rope_kvappend).
+template <int HD>
+__global__ void __launch_bounds__(128) kf_attn_gqa_kernel(uint16_t* __restrict__ out, float* __restrict__ ws, const uint16_t* __restrict__ q,
+                                                          const uint16_t* __restrict__ kc, const uint16_t* __restrict__ vc,
+                                                          const int32_t* __restrict__ pos_dev, int n_head, int n_kv, int nsplit, float sqrt_hd,
+                                                          size_t seq_stride) {
+    constexpr int CH = HD / 8;
+    constexpr int TILE_BYTES = kPfKV * HD * 2;
+    extern __shared__ __align__(16) uint8_t gq_smem[];
+    const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(gq_smem);  // 16 x HD
+    const uint32_t sK = sQ + 16 * HD * 2, sV = sK + 2 * TILE_BYTES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int kvh = blockIdx.x, m = blockIdx.y, split = blockIdx.z;
+    const int group = n_head / n_kv, kv_dim = n_kv * HD;
+    const int len = pos_dev[m] + 1;
+    const int t0 = (int)(((long long)split * len) / nsplit), t1 = (int)(((long long)(split + 1) * len) / nsplit);
+    const int ntiles = (t1 - t0 + kPfKV - 1) / kPfKV;
+    auto sw = [](int row, int c) { return (uint32_t)((row * CH + (c ^ (row & 7))) * 16); };
+    const uint16_t* kbase = kc + (size_t)m * seq_stride + (size_t)kvh * HD;
+    const uint16_t* vbase = vc + (size_t)m * seq_stride + (size_t)kvh * HD;
+    for (int i = tid; i < 16 * CH; i += 128) {
+        const int r = i / CH, c = i % CH;
+        const bool ok = r < group;
+        cp16(sQ + sw(r, c), q + ((size_t)m * n_head + (size_t)kvh * group + (ok ? r : 0)) * HD + c * 8, ok);
+    }
+    auto load_kv = [&](int kt, int buf) {
+        for (int i = tid; i < kPfKV * CH; i += 128) {
+            const int r = i / CH, c = i % CH;
+            const int t = min(t0 + kt * kPfKV + r, t1 - 1);  // the tail of the last tile is masked below
+            cp16(sK + buf * TILE_BYTES + sw(r, c), kbase + (size_t)t * kv_dim + c * 8, true);
+            cp16(sV + buf * TILE_BYTES + sw(r, c), vbase + (size_t)t * kv_dim + c * 8, true);
+        }
+    };
+    if (ntiles > 0) load_kv(0, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    uint32_t qa[HD / 16][4];
+    float o[HD / 8][4];
+#pragma unroll
+    for (int j = 0; j < HD / 8; j++) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+    const float LOG2E = 1.4426950408889634f;
+    for (int kt = 0; kt < ntiles; kt++) {
+        const int buf = kt & 1;
+        if (kt + 1 < ntiles) load_kv(kt + 1, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        if (kt == 0) {
+#pragma unroll
+            for (int kc_ = 0; kc_ < HD / 16; kc_++) ldsm_x4(qa[kc_], sQ + sw(lane & 15, kc_ * 2 + (lane >> 4)));
+        }
+        const uint32_t kb = sK + buf * TILE_BYTES, vb = sV + buf * TILE_BYTES;
+        const int tok0 = t0 + kt * kPfKV + warp * 16;  // this warp's 16 tokens of the tile
+        if (tok0 < t1) {
+            float sc[2][4];
+#pragma unroll
+            for (int j = 0; j < 2; j++) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+            for (int kc_ = 0; kc_ < HD / 16; kc_++) {
+                uint32_t b[4];
+                ldsm_x4(b, kb + sw(warp * 16 + (lane & 7) + (lane >> 4) * 8, kc_ * 2 + ((lane >> 3) & 1)));
+                mma_bf16(sc[0], qa[kc_], b[0], b[1]);
+                mma_bf16(sc[1], qa[kc_], b[2], b[3]);
+            }
+            float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int tcol = tok0 + j * 8 + 2 * t4 + (e & 1);
+                    sc[j][e]       = tcol < t1 ? sc[j][e] / sqrt_hd : -INFINITY;  // the reference divides (operator.cuh:630)
+                }
+                mx_lo = fmaxf(mx_lo, fmaxf(sc[j][0], sc[j][1]));
+                mx_hi = fmaxf(mx_hi, fmaxf(sc[j][2], sc[j][3]));
+            }
+            mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)), mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+            mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)), mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+            const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);  // finite: token tok0 is always valid
+            const float c_lo = exp2f((m_lo - mn_lo) * LOG2E), c_hi = exp2f((m_hi - mn_hi) * LOG2E);
+            m_lo = mn_lo, m_hi = mn_hi;
+            float rs_lo = 0.f, rs_hi = 0.f;
+            uint32_t pa[4];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const float p0 = exp2f((sc[j][0] - mn_lo) * LOG2E), p1 = exp2f((sc[j][1] - mn_lo) * LOG2E);
+                const float p2 = exp2f((sc[j][2] - mn_hi) * LOG2E), p3 = exp2f((sc[j][3] - mn_hi) * LOG2E);
+                rs_lo += p0 + p1, rs_hi += p2 + p3;
+                pa[j * 2 + 0] = pack_bf16x2(p0, p1), pa[j * 2 + 1] = pack_bf16x2(p2, p3);
+            }
+            l_lo = l_lo * c_lo + rs_lo, l_hi = l_hi * c_hi + rs_hi;
+#pragma unroll
+            for (int j = 0; j < HD / 8; j++) o[j][0] *= c_lo, o[j][1] *= c_lo, o[j][2] *= c_hi, o[j][3] *= c_hi;
+#pragma unroll
+            for (int jp = 0; jp < HD / 16; jp++) {
+                uint32_t b[4];
+                ldsm_x4_t(b, vb + sw(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, jp * 2 + (lane >> 4)));
+                mma_bf16(o[2 * jp], pa, b[0], b[1]);
+                mma_bf16(o[2 * jp + 1], pa, b[2], b[3]);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- merge the four warps (fixed order) through shared memory: the tile buffers are free now ----
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float* s_o = reinterpret_cast<float*>(gq_smem + 16 * HD * 2);  // [4][16][HD]
+    float* s_m = s_o + 4 * 16 * HD;                                // [4][16]
+    float* s_l = s_m + 64;
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1), l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1), l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+#pragma unroll
+    for (int j = 0; j < HD / 8; j++) {
+        float* r0 = s_o + ((size_t)warp * 16 + g) * HD + j * 8 + 2 * t4;
+        float* r1 = r0 + 8 * HD;
+        r0[0] = o[j][0], r0[1] = o[j][1], r1[0] = o[j][2], r1[1] = o[j][3];
+    }
+    if (t4 == 0) s_m[warp * 16 + g] = m_lo, s_m[warp * 16 + g + 8] = m_hi, s_l[warp * 16 + g] = l_lo, s_l[warp * 16 + g + 8] = l_hi;
+    __syncthreads();
+    for (int idx = tid; idx < group * HD; idx += 128) {
+        const int r = idx / HD, c = idx % HD;
+        float M_ = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 4; w++) M_ = fmaxf(M_, s_m[w * 16 + r]);
+        float L_ = 0.f, acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const float sc_ = s_m[w * 16 + r] == -INFINITY ? 0.f : exp2f((s_m[w * 16 + r] - M_) * LOG2E);
+            L_ += s_l[w * 16 + r] * sc_;
+            acc = fmaf(s_o[((size_t)w * 16 + r) * HD + c], sc_, acc);
+        }
+        const int h = kvh * group + r;
+        if (nsplit == 1) {
+            out[((size_t)m * n_head + h) * HD + c] = f32_to_bf16_bits(acc / L_);
+        } else {  // partial in the layout kf_attn_combine_kernel reads: [M][n_head][nsplit][HD + 2]
+            float* wp = ws + (((size_t)m * n_head + h) * nsplit + split) * (HD + 2);
+            wp[c] = acc;
+            if (c == 0) wp[HD] = M_, wp[HD + 1] = L_;
+        }
+    }
+}
 }  // namespace
 
 // ROPE::cuInfer (rope.cu:645-672) + attention_qk / softmax / attention_v (operator.cuh:573-668) of SelfAttention::cuInfer (QKV.cu:660-674)
@@ -802,5 +949,56 @@ extern "C" int kf_attn_prefill(kf_ctx* ctx, void* out, const void* q, const void
                                                                      pos_dev, M, n_head, n_kv, max_seq, sq);
     }
     KF_LAUNCH_CHECK(ctx);
+    return KF_OK;
+}
+
+// Decode attention for MANY sequences per step (one token each): the query heads of a kv group share every cached row through the
+// tensor cores (kf_attn_gqa_kernel).  Same contract as kf_attn_decode; q normalised + rotated, K / V of the current position appended.
+extern "C" int kf_attn_decode_gqa(kf_ctx* ctx, void* out, const void* q, const void* kc, const void* vc, const int32_t* pos_dev, int M, int n_head,
+                                  int n_kv, int hd, int max_seq, int max_pos_hint, size_t seq_stride) {
+    if (!ctx || !out || !q || !kc || !vc || !pos_dev) return KF_ERR_BAD_ARG;
+    KF_REQUIRE(ctx, (hd == 128 || hd == 64) && n_head % n_kv == 0 && n_head / n_kv <= 16 && M >= 1 && max_seq >= 1, "head_dim 64/128, group <= 16");
+    KF_REQUIRE(ctx, M == 1 || seq_stride > 0, "one sequence per token");
+    const int len = std::max(1, std::min(max_seq, max_pos_hint + 1));
+    int nsplit    = ctx->attn_split;
+    if (nsplit <= 0) {
+        nsplit = (3 * ctx->sm_count + n_kv * M - 1) / (n_kv * M);
+        nsplit = std::max(1, std::min(std::min(nsplit, 32), len / (2 * kPfKV)));
+    }
+    float* ws = nullptr;
+    if (nsplit > 1) {
+        int rc = kf_ensure_attn_ws(ctx, (size_t)M * n_head * nsplit * (hd + 2) * sizeof(float));
+        if (rc) return rc;
+        ws = ctx->attn_ws;
+    }
+    const size_t smem = std::max((size_t)(16 + 4 * kPfKV) * hd * 2, (size_t)16 * hd * 2 + (size_t)4 * 16 * hd * 4 + 512);
+    dim3 grid(n_kv, M, nsplit);
+    const float sq = sqrtf((float)hd);
+    if (hd == 128) {
+        static bool set = false;
+        if (!set) {
+            KF_CUDA(ctx, cudaFuncSetAttribute(kf_attn_gqa_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set = true;
+        }
+        kf_attn_gqa_kernel<128><<<grid, 128, smem, ctx->stream>>>((uint16_t*)out, ws, (const uint16_t*)q, (const uint16_t*)kc, (const uint16_t*)vc,
+                                                                  pos_dev, n_head, n_kv, nsplit, sq, seq_stride);
+    } else {
+        static bool set = false;
+        if (!set) {
+            KF_CUDA(ctx, cudaFuncSetAttribute(kf_attn_gqa_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set = true;
+        }
+        kf_attn_gqa_kernel<64><<<grid, 128, smem, ctx->stream>>>((uint16_t*)out, ws, (const uint16_t*)q, (const uint16_t*)kc, (const uint16_t*)vc,
+                                                                 pos_dev, n_head, n_kv, nsplit, sq, seq_stride);
+    }
+    KF_LAUNCH_CHECK(ctx);
+    if (nsplit > 1) {
+        dim3 g2(n_head, M);
+        if (hd == 128)
+            kf_attn_combine_kernel<4><<<g2, 128, 0, ctx->stream>>>((uint16_t*)out, ws, n_head, nsplit);
+        else
+            kf_attn_combine_kernel<2><<<g2, 64, 0, ctx->stream>>>((uint16_t*)out, ws, n_head, nsplit);
+        KF_LAUNCH_CHECK(ctx);
+    }
     return KF_OK;
 }

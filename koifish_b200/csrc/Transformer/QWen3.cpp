@@ -104,7 +104,12 @@ int SelfAttention::cuInfer(void* inpL, int M) {
     KF_TRY(kf_rmsnorm_linear(f->ctx, 3, y3, w3, inpL, norm.w->data, norm.rms_eps, M, 0));
     const int lay   = layid - 1;
     const size_t ss = f->seq_mode ? f->cache.seq_stride() : 0;
-    if (M == 1 || f->seq_mode) {  // decode: rope->cuInfer + the attention kernels in one launch
+    if (f->seq_mode && M >= f->gqa_min_batch && n_head / n_head_kv <= 16) {
+        // many sequences: QK-norm + RoPE + append, then the kv-group attention on the tensor cores (each cached row read once per kv head)
+        KF_TRY(rope.cuInfer(this, M));
+        KF_TRY(kf_attn_decode_gqa(f->ctx, f->att, f->q, f->cache.Get(KVCache::KV_KEY, lay), f->cache.Get(KVCache::KV_VAL, lay), f->d_pos, M, n_head,
+                                  n_head_kv, head_dim, f->cache.max_seq, f->attn_hint, ss));
+    } else if (M == 1 || f->seq_mode) {  // decode: rope->cuInfer + the attention kernels in one launch
         KF_TRY(kf_qkv_attention(f->ctx, f->att, f->q, f->k, f->v, rope.q_norm ? rope.q_norm->data : nullptr,
                                 rope.k_norm ? rope.k_norm->data : nullptr, f->cache.Get(KVCache::KV_KEY, lay), f->cache.Get(KVCache::KV_VAL, lay),
                                 rope.table, f->d_pos, M, n_head, n_head_kv, head_dim, f->cache.max_seq, 1e-6f, ss, f->attn_hint));
@@ -299,6 +304,7 @@ int Fish::Build() {
     for (auto& a : attn) a->rope.table = table;
     rope_table_shared = table;
     attn_hint = c.max_seq_len - 1;
+    if (const char* e = getenv("KF_GQA_MIN_BATCH")) gqa_min_batch = atoi(e);  // tuning sweeps only
     return KF_OK;
 }
 

@@ -588,3 +588,26 @@ def test_attn_prefill_equals_per_token_decode_attention(ctx, hd, n_head, n_kv, M
     for m in (0, M // 2, M - 1):
         ref = ol.attention_decode(q[m], kc, vc, int(pos[m]), n_head, n_kv, hd)
         assert np.allclose(g.reshape(M, -1)[m], ol.bf16_to_f32(ref).reshape(-1), rtol=2.0 ** -6, atol=6e-3)
+
+
+@pytest.mark.parametrize("hd,n_head,n_kv", [(128, 64, 8), (128, 8, 2), (64, 16, 8), (128, 16, 1)])
+@pytest.mark.parametrize("split", [0, 1, 3])
+def test_attn_decode_gqa_equals_per_head_decode_attention(ctx, hd, n_head, n_kv, split):
+    # batched decode: M sequences at different positions; the kv-group tensor-core kernel against the per-head kernel
+    rng = np.random.default_rng(hd + n_head + split)
+    M, max_seq = 5, 320
+    pos = np.array([0, 1, 63, 200, 319], dtype=np.int32)
+    q = rand_bf16(rng, (M, n_head * hd))
+    kc, vc = rand_bf16(rng, (M, max_seq, n_kv * hd)), rand_bf16(rng, (M, max_seq, n_kv * hd))
+    stride = max_seq * n_kv * hd
+    qd, kcd, vcd, posd = ctx.array(q), ctx.array(kc), ctx.array(vc), ctx.array(pos)
+    want = kf.attn_decode(ctx, qd, kcd, vcd, posd, M, n_head, n_kv, hd, max_seq, 319, seq_stride=stride).numpy(np.uint16)
+    ctx.set_int("attn_split", split)
+    try:
+        got = kf.attn_decode_gqa(ctx, qd, kcd, vcd, posd, M, n_head, n_kv, hd, max_seq, 319, seq_stride=stride).numpy(np.uint16)
+    finally:
+        ctx.set_int("attn_split", 0)
+    g, w = ol.bf16_to_f32(got), ol.bf16_to_f32(want)
+    assert np.allclose(g, w, rtol=2.0 ** -6, atol=6e-3), np.abs(g - w).max()
+    ref = ol.attention_decode(q[3], kc[3], vc[3], 200, n_head, n_kv, hd)
+    assert np.allclose(g.reshape(M, -1)[3], ol.bf16_to_f32(ref).reshape(-1), rtol=2.0 ** -6, atol=6e-3)
