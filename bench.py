@@ -209,14 +209,11 @@ def main():
         if os.environ.get("KF_" + knob.upper()):
             ctx.set_int(knob, int(os.environ["KF_" + knob.upper()]))
     if world > 1:
-        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            raw = (C.c_ubyte * 128)()
-            ctx.check(ctx.lib.kf_nccl_unique_id(raw), "kf_nccl_unique_id")
-            idbuf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
-        dist.broadcast(idbuf, 0)
-        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
-        ctx.check(ctx.lib.kf_ctx_init_nccl(ctx.h, raw, rank, world), "kf_ctx_init_nccl")
+        if os.environ.get("KF_P2P", "1") == "0":   # library path only (ncclAllReduce + add), for comparison
+            ctx.init_tensor_parallel(rank, world, max_floats=4)
+            ctx.lib.kf_p2p_alloc(ctx.h, 4, world, (C.c_ubyte * 64)())  # drops the attached buffers -> fallback
+        else:
+            ctx.init_tensor_parallel(rank, world)
 
     def barrier():
         if world > 1:

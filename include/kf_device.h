@@ -193,6 +193,16 @@ int kf_ctx_init_nccl(kf_ctx* ctx, const void* id_128_bytes, int rank, int world)
 int kf_allreduce_bf16(kf_ctx* ctx, void* buf_dev, size_t count); /* in-place sum over ranks, on the stream */
 int kf_allreduce_f32(kf_ctx* ctx, float* buf_dev, size_t count);
 int kf_allgather(kf_ctx* ctx, void* out_dev, const void* in_dev, size_t bytes_per_rank);
+/* ---- the decode exchange over NVLink / NVSwitch PEER MEMORY, fused with the residual add (p2p.cu): one launch instead of
+ *      ncclAllReduce + add.  kf_p2p_alloc creates this rank's symmetric buffer for messages of up to max_floats and returns its CUDA
+ *      IPC handle (64 bytes); the caller gathers the handles of all ranks (torch.distributed / MPI) and passes them to kf_p2p_attach.
+ *      kf_allreduce_residual: out = bf16(residual + bf16(sum over ranks of partial)), summed in rank order on every rank
+ *      (bit-identical across ranks); falls back to kf_allreduce_f32 + kf_residual_add_f32 when the peer buffers are not attached
+ *      or the message is larger than max_floats. ---- */
+int kf_p2p_alloc(kf_ctx* ctx, size_t max_floats, int world, void* handle_out_64_bytes);
+int kf_p2p_attach(kf_ctx* ctx, const void* handles_world_x_64_bytes, int rank, int world);
+int kf_p2p_ready(kf_ctx* ctx);
+int kf_allreduce_residual(kf_ctx* ctx, void* out_bf16_dev, const void* residual_bf16_dev, const float* partial_f32_dev, size_t n);
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,10 @@ SIGNATURES = {
     "kf_rope_table": (_I, [_P, _P, _I, _I, _F]),
     "kf_qknorm_rope_kvappend": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _SZ]),
     "kf_attn_decode": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _SZ]),
+    "kf_p2p_alloc": (_I, [_P, _SZ, _I, _P]),
+    "kf_p2p_attach": (_I, [_P, _P, _I, _I]),
+    "kf_p2p_ready": (_I, [_P]),
+    "kf_allreduce_residual": (_I, [_P, _P, _P, _P, _SZ]),
     "kf_attn_prefill": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
     "kf_attn_decode_gqa": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _SZ]),
     "kf_qkv_attention": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _SZ, _I]),

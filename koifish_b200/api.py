@@ -54,6 +54,29 @@ class Context:
     def set_int(self, key, value):
         self.check(self.lib.kf_ctx_set_int(self.h, key.encode(), int(value)), "kf_ctx_set_int")
 
+    def init_tensor_parallel(self, rank, world, max_floats=64 * 8192):
+        """NCCL communicator + peer-memory exchange buffers for this rank; the ids / IPC handles travel through torch.distributed
+        (one process per GPU, process group already initialised)."""
+        import torch
+        import torch.distributed as dist
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            raw = (C.c_ubyte * 128)()
+            self.check(self.lib.kf_nccl_unique_id(raw), "kf_nccl_unique_id")
+            idbuf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
+        self.check(self.lib.kf_ctx_init_nccl(self.h, raw, rank, world), "kf_ctx_init_nccl")
+        if world <= 8:
+            h = (C.c_ubyte * 64)()
+            self.check(self.lib.kf_p2p_alloc(self.h, max_floats, world, h), "kf_p2p_alloc")
+            mine = torch.tensor(list(h), dtype=torch.uint8, device="cuda")
+            allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, mine)
+            flat = (C.c_ubyte * (64 * world))(*[b for t in allh for b in t.cpu().tolist()])
+            self.check(self.lib.kf_p2p_attach(self.h, flat, rank, world), "kf_p2p_attach")
+            dist.barrier()
+
     # ---- memory
     def empty(self, nbytes):
         return DevArray(self, nbytes)

@@ -83,6 +83,7 @@ extern "C" int kf_ctx_destroy(kf_ctx* ctx) {
         return KF_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    kf_p2p_destroy(ctx);
     if (ctx->nccl) {
         auto f = (fn_ncclCommDestroy)nccl_sym("ncclCommDestroy");
         if (f)

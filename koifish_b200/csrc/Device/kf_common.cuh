@@ -44,6 +44,7 @@ struct kf_ctx {
     // tensor parallel
     ncclComm* nccl = nullptr;
     int rank = 0, world = 1;
+    void* p2p = nullptr;  // peer-memory exchange state (p2p.cu)
     std::string last_error;
 };
 
@@ -102,6 +103,7 @@ static inline const uint16_t* kf_gama_step(const kf_tensor_desc& w) {
 }
 static inline bool kf_has_gama(const kf_tensor_desc& w) { return w.gama_dev || (w.zero_dev && w.step_dev); }
 
+void kf_p2p_destroy(kf_ctx* ctx);
 int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters);
 int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes);
 int kf_ensure_attn_cnt(kf_ctx* ctx, int counters);

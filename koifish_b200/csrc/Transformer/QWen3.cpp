@@ -127,8 +127,7 @@ int SelfAttention::cuInfer(void* inpL, int M) {
         KF_TRY(proj_cat.Forw(inpL, f->att, M, KF_EPI_RESIDUAL, inpL));  // out = residual + proj (CU_add3, QKV.cu:682-688)
     } else {  // row-parallel: fp32 partial sums -> all-reduce over NVLink -> residual add
         KF_TRY(proj_cat.Forw(f->part_f32, f->att, M, KF_EPI_F32, nullptr));
-        KF_TRY(kf_allreduce_f32(f->ctx, f->part_f32, nE));
-        KF_TRY(kf_residual_add_f32(f->ctx, inpL, inpL, f->part_f32, nE));
+        KF_TRY(kf_allreduce_residual(f->ctx, inpL, inpL, f->part_f32, nE));  // one launch over NVLink peer memory (p2p.cu); NCCL fallback
     }
     return KF_OK;
 }
@@ -144,8 +143,7 @@ int FFN::cuInfer(void* inpL, int M) {
         KF_TRY(down.Forw(inpL, f->hb, M, KF_EPI_RESIDUAL, inpL));
     } else {
         KF_TRY(down.Forw(f->part_f32, f->hb, M, KF_EPI_F32, nullptr));
-        KF_TRY(kf_allreduce_f32(f->ctx, f->part_f32, nE));
-        KF_TRY(kf_residual_add_f32(f->ctx, inpL, inpL, f->part_f32, nE));
+        KF_TRY(kf_allreduce_residual(f->ctx, inpL, inpL, f->part_f32, nE));  // one launch over NVLink peer memory (p2p.cu); NCCL fallback
     }
     return KF_OK;
 }

@@ -24,14 +24,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = kf.Context(local)
-    idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        raw = (C.c_ubyte * 128)()
-        ctx.check(ctx.lib.kf_nccl_unique_id(raw), "kf_nccl_unique_id")
-        idbuf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
-    dist.broadcast(idbuf, 0)
-    raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
-    ctx.check(ctx.lib.kf_ctx_init_nccl(ctx.h, raw, rank, world), "kf_ctx_init_nccl")
+    ctx.init_tensor_parallel(rank, world)  # NCCL communicator + peer-memory exchange buffers
+    assert ctx.lib.kf_p2p_ready(ctx.h) == 1
 
     quantizer = {"group_size": 128, "self_attn": {"quant_method": "RTN", "bits": 4}, "mlp": {"quant_method": "RTN", "bits": 4}}
     # 8 KV heads so that TP up to 8 divides; small enough to build twice on rank 0
