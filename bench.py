@@ -303,10 +303,12 @@ def main():
         plan.append(("lin", dd))
         for d in (dq, dk, dv, do, dg, du, dd):
             alg_bytes += gemv_algorithmic_bytes(d.rows, d.cols, bits_of(d), d.group, 1)
+    # the bf16 lm_head goes through the TMA-fed tcgen05 kernel (HBM-roofline already, profiles/r01_tc_crossover.txt): it is counted in
+    # the step's bytes but not in the roofline of the dominant kernel, the block GEMVs
     dh = model.tensor_desc("lm_head.weight" if not info.tie_word_embeddings else "model.embed_tokens.weight")
     head_rows = dh.rows // world
-    alg_bytes += gemv_algorithmic_bytes(head_rows, dh.cols, bits_of(dh), dh.group, 1)
-    n_gemv = len(plan) + 1
+    head_bytes = gemv_algorithmic_bytes(head_rows, dh.cols, bits_of(dh), dh.group, 1)
+    n_gemv = len(plan)
 
     def gemv_pass():
         lib, h = ctx.lib, ctx.h
@@ -319,11 +321,6 @@ def main():
                 ctx.check(lib.kf_linear_swiglu(h, ybufs[0].ptr, C.byref(d[0]), C.byref(d[1]), xbuf.ptr, 1), "kf_linear_swiglu")
             else:
                 ctx.check(lib.kf_linear(h, ybufs[0].ptr, C.byref(d), xbuf.ptr, 1, 0, None), "kf_linear")
-        if world == 1:
-            ctx.check(lib.kf_linear(h, ybufs[0].ptr, C.byref(dh), xbuf.ptr, 1, 0, None), "kf_linear")
-        else:
-            dv_ = kf.TensorDesc(dh.data_dev, dh.gama_dev, head_rows, dh.cols, dh.type, dh.group, dh.qbias, None, None)
-            ctx.check(lib.kf_linear(h, ybufs[0].ptr, C.byref(dv_), xbuf.ptr, 1, 0, None), "kf_linear")
 
     gemv_pass()  # eager: sizes the workspaces
     g = C.c_void_p()
@@ -347,8 +344,18 @@ def main():
     per_launch_s = gemv_ms_pass / 1e3 / n_gemv
     achieved = per_launch_bytes / per_launch_s / 1e9
     kv_bytes_tok = 2.0 * info.n_layers * (args.ctx + args.steps // 2) * KD * 2
-    step_alg_bytes = alg_bytes + kv_bytes_tok
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    step_alg_bytes = alg_bytes + head_bytes + kv_bytes_tok
+    # measured DRAM bytes per launch of the same kernel in the same decode step (one ncu pass, tools/gpu_traffic.sh), if committed
+    traffic, traffic_src = None, None
+    if world == 1 and args.workload == "qwen3-32b-q4" and not args.layers:
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_decode.json")))["kernels"]["kf_gemv_kernel"]
+            traffic = t["avg_dram_read_bytes"] + t["avg_dram_write_bytes"]
+            traffic_src = "profiles/r01_traffic_decode.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, avg of %d launches)" % t["launches"]
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "kernel": "kf_gemv_kernel (fused unpack+dequant GEMV, M=1)", "launches_per_step": n_gemv,
                 "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_us": per_launch_s * 1e6, "gemv_share_of_step": gemv_ms_pass / ms_step,
                 "peak_source": peak_src, "frac_of_8TBps": achieved / 8000.0,
@@ -362,7 +369,7 @@ def main():
             "config": {"workload": "Qwen3-%s decode, batch 1, ctx %d, %s" % (dims_key, args.ctx, args.workload), "model": "Qwen3-" + dims_key,
                        "quantizer": quantizer, "global_batch": 1, "seq_len": args.ctx, "parallelism": "tp%d" % world,
                        "weights": "random-init N(0,0.02^2)-like, quantised at load on the GPU", "lm_head": "bf16",
-                       "l2": "weights per token (%.1f GB) exceed the 126 MB L2; no reuse between steps" % (alg_bytes / 1e9),
+                       "l2": "weights per token (%.1f GB) exceed the 126 MB L2; no reuse between steps" % ((alg_bytes + head_bytes) / 1e9),
                        "layers": info.n_layers, "setup_s": round(t_setup, 1)},
             "e2e": {"value": e2e_tok_s, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 151936 * 2 + 4},
             "gpu_launches": int(launches), "launches_per_step": launches / max(1, args.steps),
