@@ -318,14 +318,6 @@ __global__ void __launch_bounds__(kAttnWarps * 32) kf_attn_fused_kernel(uint16_t
 // through distributed shared memory instead of a global workspace + arrival counter + last-CTA pass.  What is left on the critical
 // path after the QKV GEMV finishes is one L2 round trip (q / k / v of the new token), the score / softmax arithmetic of 16 cached rows
 // per warp -- all of which were requested BEFORE the dependency wait, as packed bf16 -- and one cluster barrier.
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void st_cluster_f32(float* local_ptr, int cta_rank, float v) {
-    uint32_t remote;
-    const uint32_t local = (uint32_t)__cvta_generic_to_shared(local_ptr);
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(cta_rank));
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
-}
 template <int DPL>
 __device__ __forceinline__ uint2 load_raw(const uint16_t* p) {
     if constexpr (DPL == 4) return *reinterpret_cast<const uint2*>(p);

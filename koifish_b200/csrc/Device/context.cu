@@ -123,6 +123,8 @@ extern "C" int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value) {
         ctx->gemv_splitk = value;
     else if (!strcmp(key, "gemv_variant"))
         ctx->gemv_variant = value;
+    else if (!strcmp(key, "gemv_cluster"))
+        ctx->gemv_cluster = value;
     else if (!strcmp(key, "gemv_exact"))
         ctx->gemv_exact = value;
     else if (!strcmp(key, "pdl"))

@@ -69,6 +69,8 @@ struct GemvParams {
     int M, K;
     int steps_total;  // K / KSTEP
     int S;            // k-splits
+    int cluster;      // 1: the S CTAs of a row block form a cluster and merge through distributed shared memory (M = 1)
+    int red_off;      // byte offset of the leader's [S][ROWS] fp32 merge area in dynamic shared memory
     int nsteps_max;   // ceil(steps_total / S): sizes the shared-memory regions
     int total_rb;
     int qbias;
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
     const int rb = blockIdx.x, split = blockIdx.y;
     const bool swiglu = p.epilogue == EPI_SWIGLU;
     kf_grid_launch_dependents();  // the next kernel of the stream may start its own weight prefetch as soon as all our CTAs are running
+    if (M1 && p.cluster) cluster_arrive();  // matched by the wait in front of the first remote store: by then every CTA of the cluster runs
 
     // ---- which rows does this CTA / warp own? -------------------------------------------------------------------------------
     int segi = 0;
@@ -544,7 +547,22 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
     __syncthreads();
 
     // ---- split-K: publish the partial tile; the last CTA of this row block reduces in fixed order ---------------------------
-    if (p.S > 1) {
+    if (M1 && p.cluster) {
+        // the k-slices of this row block are the CTAs of one cluster: every slice stores its ROWS partial sums into the leader's shared
+        // memory, the leader adds them in slice order (deterministic).  No global workspace, no atomics, no second DRAM/L2 round trip.
+        float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem) + p.red_off);
+        cluster_wait();
+        for (int e = tid; e < ROWS; e += kThreads) st_cluster_f32(red + split * ROWS + e, 0, tile[e]);
+        cluster_arrive();
+        cluster_wait();
+        if (split != 0) return;
+        for (int e = tid; e < ROWS; e += kThreads) {
+            float sum = 0.f;
+            for (int sp = 0; sp < p.S; sp++) sum += red[sp * ROWS + e];
+            tile[e] = sum;
+        }
+        __syncthreads();
+    } else if (p.S > 1) {
         float* wsp = p.ws + ((size_t)split * p.total_rb + rb) * (size_t)(MP * ROWS);
         for (int e = tid; e < p.M * ROWS; e += kThreads) {
             const int m = e / ROWS, r = e % ROWS;
@@ -632,6 +650,16 @@ int launch_one(kf_ctx* ctx, const GemvParams& p0) {
     p.sx_off         = (int)(p.ring_off + ring_bytes(FMT, RT));
     size_t sxbytes   = MODE == MODE_FACTOR ? (size_t)p.nsteps_max * MX * 4 : 0;
     size_t smem      = std::max((size_t)p.sx_off + sxbytes, tilebytes);
+    if (p.cluster) {
+        p.red_off = (int)((smem + 15) & ~(size_t)15);
+        smem      = (size_t)p.red_off + (size_t)p.S * ROWS * 4;
+        if (!M1 || smem > kSmemCap) {  // no room for the merge area: global workspace + last-CTA reduction
+            p.cluster = 0, smem = std::max((size_t)p.sx_off + sxbytes, tilebytes);
+            int rc = kf_ensure_gemv_ws(ctx, (size_t)p.S * p.total_rb * MP * ROWS * sizeof(float), p.total_rb);
+            if (rc) return rc;
+            p.ws = ctx->gemv_ws, p.cnt = ctx->gemv_cnt;
+        }
+    }
     KF_REQUIRE(ctx, smem <= kSmemCap, "internal: k-slice does not fit shared memory");
     auto kern            = kf_gemv_kernel<FMT, MODE, NT, M1, RT>;
     static bool attr_set = false;  // per instantiation
@@ -640,7 +668,19 @@ int launch_one(kf_ctx* ctx, const GemvParams& p0) {
         attr_set = true;
     }
     dim3 grid(p.total_rb, p.S);
-    KF_CUDA(ctx, kf_launch_pdl(ctx, kern, grid, dim3(kThreads), smem, p));
+    if (p.cluster) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid, cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id               = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1, attr[0].val.clusterDim.y = (unsigned)p.S, attr[0].val.clusterDim.z = 1;
+        attr[1].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr, cfg.numAttrs = ctx->pdl ? 2 : 1;
+        KF_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, p));
+    } else {
+        KF_CUDA(ctx, kf_launch_pdl(ctx, kern, grid, dim3(kThreads), smem, p));
+    }
     KF_LAUNCH_CHECK(ctx);
     return KF_OK;
 }
@@ -735,9 +775,11 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     }
     S = std::max(S, S_min);
     S = std::max(1, std::min(S, p.steps_total));
+    if (M == 1 && ctx->gemv_cluster == 2 && ctx->gemv_splitk <= 0 && S > 8 && S_min <= 8) S = 8;
+    p.cluster    = (M == 1 && ctx->gemv_cluster > 0 && S >= 2 && S <= 8) ? 1 : 0;
     p.S          = S;
     p.nsteps_max = (p.steps_total + S - 1) / S;  // floor/ceil slicing never exceeds ceil(steps/S)
-    if (S > 1) {
+    if (S > 1 && !p.cluster) {
         int rc = kf_ensure_gemv_ws(ctx, (size_t)S * rb * (M == 1 ? 8 : MXs) * rows_cta * sizeof(float), rb);
         if (rc) return rc;
         p.ws = ctx->gemv_ws, p.cnt = ctx->gemv_cnt;

@@ -37,6 +37,7 @@ struct kf_ctx {
     // tuning
     int gemv_splitk  = 0;
     int gemv_variant = 0;
+    int gemv_cluster = 1;  // M = 1 split-K: 1 = merge the k-slices of a row block inside a thread-block cluster (DSMEM) when S <= 8; 2 = also cap S at 8; 0 = global workspace
     int gemv_exact   = 1;  // 1: in-kernel dequant reproduces the reference's bf16 roundings bit for bit ; 0: factored scale/zero (MODE_FACTOR)
     int attn_split   = 0;
     int attn_warps   = 0;  // warps per CTA of the cluster attention (0 = default)
@@ -126,6 +127,15 @@ static inline cudaError_t kf_launch_pdl(kf_ctx* ctx, void (*kernel)(KArgs...), d
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr, cfg.numAttrs = ctx->pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+// thread-block cluster barrier (split arrive / wait) and a store into the shared memory of CTA `cta_rank` of the cluster
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_f32(float* local_ptr, int cta_rank, float v) {
+    uint32_t remote;
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(local_ptr);
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(cta_rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
 }
 __device__ __forceinline__ void kf_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void kf_grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

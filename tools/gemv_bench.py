@@ -41,12 +41,16 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--out", default="")
     ap.add_argument("--tc", default="-1", help="tc_min_m values: token count from which the tcgen05 GEMM is used (-1 = auto per type, 0 = never, 1 = always)")
+    ap.add_argument("--set", default="", help="extra context knobs, e.g. gemv_cluster=0,attn_split=4")
     ap.add_argument("--exact", type=int, default=1, help="gemv_exact knob: 1 = reference-exact in-kernel dequant, 0 = factored scale/zero")
     args = ap.parse_args()
     stream = torch.cuda.Stream()  # a real (non-default) stream shared by torch events and our kernels
     torch.cuda.set_stream(stream)
     ctx = kf.Context(0, stream.cuda_stream)
     ctx.set_int("gemv_exact", args.exact)
+    for kv in [s for s in args.set.split(",") if s]:
+        k, v = kv.split("=")
+        ctx.set_int(k, int(v))
     peak = 6452.8
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
