@@ -209,11 +209,7 @@ def main():
         if os.environ.get("KF_" + knob.upper()):
             ctx.set_int(knob, int(os.environ["KF_" + knob.upper()]))
     if world > 1:
-        if os.environ.get("KF_P2P", "1") == "0":   # library path only (ncclAllReduce + add), for comparison
-            ctx.init_tensor_parallel(rank, world, max_floats=4)
-            ctx.lib.kf_p2p_alloc(ctx.h, 4, world, (C.c_ubyte * 64)())  # drops the attached buffers -> fallback
-        else:
-            ctx.init_tensor_parallel(rank, world)
+        ctx.init_tensor_parallel(rank, world, p2p=os.environ.get("KF_P2P", "1") != "0")  # KF_P2P=0: NCCL exchange only, for comparison
 
     def barrier():
         if world > 1:

@@ -202,6 +202,7 @@ int kf_allgather(kf_ctx* ctx, void* out_dev, const void* in_dev, size_t bytes_pe
 int kf_p2p_alloc(kf_ctx* ctx, size_t max_floats, int world, void* handle_out_64_bytes);
 int kf_p2p_attach(kf_ctx* ctx, const void* handles_world_x_64_bytes, int rank, int world);
 int kf_p2p_ready(kf_ctx* ctx);
+int kf_p2p_release(kf_ctx* ctx); /* drop the peer buffers: kf_allreduce_residual then takes the NCCL path (all ranks must agree) */
 int kf_allreduce_residual(kf_ctx* ctx, void* out_bf16_dev, const void* residual_bf16_dev, const float* partial_f32_dev, size_t n);
 
 #ifdef __cplusplus

@@ -78,6 +78,7 @@ SIGNATURES = {
     "kf_p2p_alloc": (_I, [_P, _SZ, _I, _P]),
     "kf_p2p_attach": (_I, [_P, _P, _I, _I]),
     "kf_p2p_ready": (_I, [_P]),
+    "kf_p2p_release": (_I, [_P]),
     "kf_allreduce_residual": (_I, [_P, _P, _P, _P, _SZ]),
     "kf_attn_prefill": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
     "kf_attn_decode_gqa": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _SZ]),

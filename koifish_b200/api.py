@@ -54,7 +54,7 @@ class Context:
     def set_int(self, key, value):
         self.check(self.lib.kf_ctx_set_int(self.h, key.encode(), int(value)), "kf_ctx_set_int")
 
-    def init_tensor_parallel(self, rank, world, max_floats=64 * 8192):
+    def init_tensor_parallel(self, rank, world, max_floats=64 * 8192, p2p=True):
         """NCCL communicator + peer-memory exchange buffers for this rank; the ids / IPC handles travel through torch.distributed
         (one process per GPU, process group already initialised)."""
         import torch
@@ -67,14 +67,20 @@ class Context:
         dist.broadcast(idbuf, 0)
         raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
         self.check(self.lib.kf_ctx_init_nccl(self.h, raw, rank, world), "kf_ctx_init_nccl")
-        if world <= 8:
+        if world <= 8 and p2p:
+            # peer-memory exchange buffers; if any rank cannot map its peers (no NVLink / IPC), every rank drops them and the exchange
+            # takes the NCCL path -- the decision is collective, so the ranks never disagree on the kernel they run
             h = (C.c_ubyte * 64)()
-            self.check(self.lib.kf_p2p_alloc(self.h, max_floats, world, h), "kf_p2p_alloc")
+            ok = self.lib.kf_p2p_alloc(self.h, max_floats, world, h) == L.KF_OK
             mine = torch.tensor(list(h), dtype=torch.uint8, device="cuda")
             allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
             dist.all_gather(allh, mine)
             flat = (C.c_ubyte * (64 * world))(*[b for t in allh for b in t.cpu().tolist()])
-            self.check(self.lib.kf_p2p_attach(self.h, flat, rank, world), "kf_p2p_attach")
+            ok = ok and self.lib.kf_p2p_attach(self.h, flat, rank, world) == L.KF_OK
+            flag = torch.tensor([1 if ok else 0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                self.lib.kf_p2p_release(self.h)
             dist.barrier()
 
     # ---- memory

@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(128) kf_attn_prefill_kernel(uint16_t* __restri
     for (int j = 0; j < HD / 8; j++) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
     float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
     const int p_lo = pos0 + q0 + warp * 16 + g, p_hi = p_lo + 8;  // positions of this thread's two query rows
-    const float LOG2E = 1.4426950408889634f;
+    const float SC = 1.4426950408889634f / sqrt_hd;  // softmax((q.k)/sqrt(hd)) = 2^((q.k - max) * log2(e)/sqrt(hd)) / sum
 
     for (int kt = 0; kt < ntiles; kt++) {
         const int buf = kt & 1;
@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(128) kf_attn_prefill_kernel(uint16_t* __restri
         for (int j = 0; j < kPfKV / 8; j++) {
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                float v = sc[j][e] / sqrt_hd;  // the reference divides (operator.cuh:630)
+                float v = sc[j][e];  // raw q.k; 1/sqrt(hd) is folded into the exponent below (the max is scale invariant)
                 if (diag) {
                     const int tcol = kt * kPfKV + j * 8 + 2 * t4 + (e & 1);
                     if (tcol > ((e & 2) ? p_hi : p_lo)) v = -INFINITY;
@@ -626,14 +626,14 @@ __global__ void __launch_bounds__(128) kf_attn_prefill_kernel(uint16_t* __restri
         mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)), mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
         const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
         const float base_lo = mn_lo == -INFINITY ? 0.f : mn_lo, base_hi = mn_hi == -INFINITY ? 0.f : mn_hi;  // fully masked row so far
-        const float c_lo = exp2f((m_lo - base_lo) * LOG2E), c_hi = exp2f((m_hi - base_hi) * LOG2E);
+        const float c_lo = exp2f((m_lo - base_lo) * SC), c_hi = exp2f((m_hi - base_hi) * SC);
         m_lo = mn_lo, m_hi = mn_hi;
         float rs_lo = 0.f, rs_hi = 0.f;
         uint32_t pa[kPfKV / 16][4];
 #pragma unroll
         for (int j = 0; j < kPfKV / 8; j++) {
-            const float p0 = exp2f((sc[j][0] - base_lo) * LOG2E), p1 = exp2f((sc[j][1] - base_lo) * LOG2E);
-            const float p2 = exp2f((sc[j][2] - base_hi) * LOG2E), p3 = exp2f((sc[j][3] - base_hi) * LOG2E);
+            const float p0 = exp2f((sc[j][0] - base_lo) * SC), p1 = exp2f((sc[j][1] - base_lo) * SC);
+            const float p2 = exp2f((sc[j][2] - base_hi) * SC), p3 = exp2f((sc[j][3] - base_hi) * SC);
             rs_lo += p0 + p1, rs_hi += p2 + p3;
             pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);  // A fragment of P for the 16 tokens of n-tiles (2i, 2i+1)
             pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);

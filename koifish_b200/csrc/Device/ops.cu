@@ -123,6 +123,20 @@ __global__ void __launch_bounds__(256) kf_swiglu_kernel(uint16_t* __restrict__ o
         out[i]        = f32_to_bf16_bits((g * u) / (1.0f + expf(-g)));
     }
 }
+// the same arithmetic, 8 elements (16 bytes) per thread: the prefill path runs it over tokens x ffn elements (HBM-bound)
+__global__ void __launch_bounds__(256) kf_swiglu_vec_kernel(uint4* __restrict__ out, const uint4* __restrict__ gate, const uint4* __restrict__ up, size_t n8) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const uint4 g4 = __ldg(gate + i), u4 = __ldg(up + i);
+    const uint32_t g[4] = {g4.x, g4.y, g4.z, g4.w}, u[4] = {u4.x, u4.y, u4.z, u4.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float g0 = bf16lo(g[j]), g1 = bf16hi(g[j]), u0 = bf16lo(u[j]), u1 = bf16hi(u[j]);
+        o[j] = pack_bf16x2((g0 * u0) / (1.0f + expf(-g0)), (g1 * u1) / (1.0f + expf(-g1)));
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
 // CU_add3 (reference src/Device/CUDA/kernel/packedN.cuh:867-875): fp32 add, bf16 out (RN here, stochastic there)
 __global__ void __launch_bounds__(256) kf_add_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,7 +166,10 @@ extern "C" int kf_advance_pos(kf_ctx* ctx, int32_t* pos, int M) {
 extern "C" int kf_swiglu(kf_ctx* ctx, void* out, const void* gate, const void* up, size_t n) {
     if (!ctx || !out || !gate || !up) return KF_ERR_BAD_ARG;
     if (!n) return KF_OK;
-    kf_swiglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint16_t*)out, (const uint16_t*)gate, (const uint16_t*)up, n);
+    if (n % 8 == 0 && (((uintptr_t)out | (uintptr_t)gate | (uintptr_t)up) & 15) == 0)
+        kf_swiglu_vec_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, ctx->stream>>>((uint4*)out, (const uint4*)gate, (const uint4*)up, n / 8);
+    else
+        kf_swiglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint16_t*)out, (const uint16_t*)gate, (const uint16_t*)up, n);
     KF_LAUNCH_CHECK(ctx);
     return KF_OK;
 }

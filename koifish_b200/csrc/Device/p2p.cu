@@ -154,6 +154,12 @@ extern "C" int kf_p2p_attach(kf_ctx* ctx, const void* handles_world_x_64_bytes, 
     return KF_OK;
 }
 
+extern "C" int kf_p2p_release(kf_ctx* ctx) {
+    if (!ctx) return KF_ERR_BAD_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    kf_p2p_destroy(ctx);
+    return KF_OK;
+}
 extern "C" int kf_p2p_ready(kf_ctx* ctx) { return ctx && state_of(ctx) && state_of(ctx)->peer[0] ? 1 : 0; }
 
 // out = residual + sum over ranks of partial (both roundings of the single-GPU path); out may alias residual

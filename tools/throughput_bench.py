@@ -36,9 +36,12 @@ def main():
     ap.add_argument("--prefill", type=int, default=0, help="prompt length (0 = skip)")
     ap.add_argument("--panel", type=int, default=1024)
     ap.add_argument("--out", default="")
+    ap.add_argument("--layers", type=int, default=0, help="debug / profiling: override the layer count (not a bench number)")
     args = ap.parse_args()
     dims_key, quantizer = WORKLOADS[args.workload]
     d = dict(kf.QWEN3_DIMS[dims_key])
+    if args.layers:
+        d["n_layer"] = args.layers
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = kf.Context(0, stream.cuda_stream)
@@ -99,8 +102,16 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         reps = 3
+        profiling = bool(os.environ.get("KF_PROFILE"))
+        if profiling:
+            reps = 1
+            model.set_graphs(False)
+            torch.cuda.profiler.start()
         for _ in range(reps):
             _, nxt = model.prefill(toks)
+        if profiling:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         e1.record(stream)
         torch.cuda.synchronize()
         ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / reps
