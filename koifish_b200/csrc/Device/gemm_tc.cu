@@ -44,11 +44,14 @@ constexpr int RAWB = KF_TC_RAWB;  // packed bytes per weight row per raw stage (
 constexpr int kProducerWarps = 8, kMmaWarp = 8, kRawWarp = 9, kXWarp = 10, kEpiWarp0 = 11;
 constexpr int kThreadsTC = 15 * 32;
 
+constexpr int kMaxW = 3;  // weights of one launch (Q/K/V, gate/up): same type, same K, their row tiles share one item space
 struct GemmParams {
-    const uint16_t* zero;
-    const uint16_t* step;
-    void* y;                   // bf16 [M][N] (or float when epilogue == 4)
-    const uint16_t* residual;  // bf16 [M][N] or nullptr
+    const uint16_t* zero[kMaxW];
+    const uint16_t* step[kMaxW];
+    void* y[kMaxW];            // bf16 [M][N_w] (or float when epilogue == 4)
+    int Nw[kMaxW];             // rows of each weight
+    int tile0[kMaxW + 1];      // first row tile of each weight in the launch's tile space (unused entries: INT_MAX)
+    const uint16_t* residual;  // bf16 [M][N] or nullptr (single weight)
     float* ws;                 // split-K partials
     unsigned* cnt;             // split-K arrival counters (self-resetting)
     int M, N, K;
@@ -301,6 +304,7 @@ struct Rings {
 
 struct Item {
     int n0, m0, z, tile;  // tile = tn * m_tiles + mt
+    int wi;               // weight of the launch
     int kb0, kb1;         // k-block range
 };
 template <int KBR>
@@ -310,7 +314,8 @@ __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
     const int t  = item / p.m_tiles;
     it.z         = t % p.splits;
     const int tn = t / p.splits;
-    it.n0 = tn * BM, it.m0 = mt, it.tile = tn * p.m_tiles + mt;  // m0 = token-tile index (the caller scales it by BN)
+    it.wi = (tn >= p.tile0[1] ? 1 : 0) + (tn >= p.tile0[2] ? 1 : 0);
+    it.n0 = (tn - p.tile0[it.wi]) * BM, it.m0 = mt, it.tile = tn * p.m_tiles + mt;  // m0 = token-tile index (the caller scales it by BN)
     const int nkb  = p.K / BK;
     const int nraw = (nkb + KBR - 1) / KBR;
     const int base = nraw / p.splits, rem = nraw % p.splits;
@@ -322,32 +327,33 @@ __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
 // Store NC consecutive tokens (the first `valid` of them exist) of weight row `grow`: bf16, bf16 + residual, or fp32.  The residual
 // values are all fetched before the first store (y may alias the residual, element for element).
 template <int NC>
-__device__ __forceinline__ void store_cols(const GemmParams& p, const float (&acc)[NC], int m_first, int valid, int grow) {
-    const size_t idx0 = (size_t)m_first * p.N + grow;
+__device__ __forceinline__ void store_cols(const GemmParams& p, void* y, int N, const float (&acc)[NC], int m_first, int valid, int grow) {
+    const size_t idx0 = (size_t)m_first * N + grow;
     if (p.epilogue == 4) {
 #pragma unroll
         for (int j = 0; j < NC; j++)
-            if (j < valid) reinterpret_cast<float*>(p.y)[idx0 + (size_t)j * p.N] = acc[j];
+            if (j < valid) reinterpret_cast<float*>(y)[idx0 + (size_t)j * N] = acc[j];
         return;
     }
     uint16_t res[NC];
     if (p.epilogue == 1) {
 #pragma unroll
-        for (int j = 0; j < NC; j++) res[j] = j < valid ? p.residual[idx0 + (size_t)j * p.N] : (uint16_t)0;
+        for (int j = 0; j < NC; j++) res[j] = j < valid ? p.residual[idx0 + (size_t)j * N] : (uint16_t)0;
     }
 #pragma unroll
     for (int j = 0; j < NC; j++) {
         if (j < valid) {
             uint16_t b = f32_to_bf16_bits(acc[j]);  // the reference's GEMM output is bf16 (gemm.cu:124-126)
             if (p.epilogue == 1) b = f32_to_bf16_bits(bf16_bits_to_f32(res[j]) + bf16_bits_to_f32(b));
-            reinterpret_cast<uint16_t*>(p.y)[idx0 + (size_t)j * p.N] = b;
+            reinterpret_cast<uint16_t*>(y)[idx0 + (size_t)j * N] = b;
         }
     }
 }
 
 template <int FMT, int MODE, int BN>
 __global__ void __launch_bounds__(kThreadsTC, 1)
-    kf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
+    kf_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
+                      const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
     using F                  = Fmt<FMT>;
     using C                  = Rings<FMT, BN>;
     constexpr bool A_TMEM    = C::A_TMEM;
@@ -413,9 +419,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
             uint32_t s = 0, eph = 1, rs = 0, rph = 0;  // ring positions and the parities to wait for
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const Item w = decode_item<KBR>(p, item);
-                const int grow       = min(w.n0 + row, p.N - 1);
-                const uint16_t* zrow = MODE == TM_PLAIN ? nullptr : p.zero + (size_t)grow * gpr;
-                const uint16_t* srow = MODE == TM_PLAIN ? nullptr : p.step + (size_t)grow * gpr;
+                const int grow       = min(w.n0 + row, p.Nw[w.wi] - 1);
+                const uint16_t* zrow = MODE == TM_PLAIN ? nullptr : p.zero[w.wi] + (size_t)grow * gpr;
+                const uint16_t* srow = MODE == TM_PLAIN ? nullptr : p.step[w.wi] + (size_t)grow * gpr;
                 // scale / zero of the current group and of the next two (register queue; the loads run 1-2 groups ahead of their use)
                 int gcur = 0;
                 uint32_t zq0 = 0, sq0 = 0, zq1 = 0, sq1 = 0, zq2 = 0, sq2 = 0;
@@ -513,6 +519,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
             uint32_t it = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const Item w = decode_item<KBR>(p, item);
+                const CUtensorMap* tm_w = w.wi == 0 ? &tm_w0 : w.wi == 1 ? &tm_w1 : &tm_w2;
                 if constexpr (A_TMEM) {
                     for (int r = w.kb0 / KBR; r * KBR < w.kb1; r++) {
                         const int rs = it % RS;
@@ -521,7 +528,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
                         mbar_arrive(&raw_full[rs]);
 #else
                         mbar_arrive_expect_tx(&raw_full[rs], RAW_BYTES);
-                        tma_load_2d(raws + (size_t)rs * RAW_BYTES, &tm_w, r * RAWB, w.n0, &raw_full[rs]);
+                        tma_load_2d(raws + (size_t)rs * RAW_BYTES, tm_w, r * RAWB, w.n0, &raw_full[rs]);
 #endif
                         it++;
                     }
@@ -531,7 +538,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
                         mbar_wait(&b_empty[s], ((it / SB) & 1) ^ 1);
                         mbar_arrive_expect_tx(&b_full[s], U * A_BYTES);
 #pragma unroll
-                        for (int u = 0; u < U; u++) tma_load_2d(tiles + (size_t)s * STAGE + u * SUB, &tm_w, (kb + u) * BK, w.n0, &b_full[s]);
+                        for (int u = 0; u < U; u++) tma_load_2d(tiles + (size_t)s * STAGE + u * SUB, tm_w, (kb + u) * BK, w.n0, &b_full[s]);
                         it++;
                     }
                 }
@@ -624,7 +631,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
             const int m0  = w.m0 * BN;
             const int cnt = min(BN, p.M - m0);
             const int grow = w.n0 + row;
-            const bool row_ok = grow < p.N;
+            const int N = p.Nw[w.wi];
+            void* const y = p.y[w.wi];
+            const bool row_ok = grow < N;
             if (NACC == 2)
                 mbar_wait_sleepy(&tmem_full[buf], (ait / NACC) & 1);  // a whole main loop away: poll politely
             else
@@ -643,7 +652,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
                     float acc[16];
 #pragma unroll
                     for (int j = 0; j < 16; j++) acc[j] = __uint_as_float(v[j]);
-                    store_cols<16>(p, acc, m0 + c0, cnt - c0, grow);
+                    store_cols<16>(p, y, N, acc, m0 + c0, cnt - c0, grow);
                 }
             }
             tc_fence_before();
@@ -681,7 +690,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
 #pragma unroll
                                 for (int u = 0; u < 8; u++) acc[u] = (acc[u] + t0[u]) + t1[u];
                             }
-                            store_cols<8>(p, acc, m0 + j0, cnt - j0, grow);
+                            store_cols<8>(p, y, N, acc, m0 + j0, cnt - j0, grow);
                         }
                     }
                 }
@@ -730,7 +739,7 @@ int make_map_2d(kf_ctx* ctx, CUtensorMap* tm, CUtensorMapDataType dt, int esize,
 }
 
 template <int FMT, int MODE, int BN>
-int launch_tc(kf_ctx* ctx, GemmParams& p, const void* wdata, const void* xp) {
+int launch_tc(kf_ctx* ctx, GemmParams& p, const void* const* wdata, int nw, const void* xp) {
     using F              = Fmt<FMT>;
     constexpr bool A_TMEM = FMT != TF_BF16;
     const size_t smem    = Rings<FMT, BN>::SMEM;
@@ -741,7 +750,10 @@ int launch_tc(kf_ctx* ctx, GemmParams& p, const void* wdata, const void* xp) {
         attr_set = true;
     }
     // ---- decomposition: row tiles x token tiles x split-K, walked round-robin by one CTA per SM ----
-    p.n_tiles = (p.N + BM - 1) / BM, p.m_tiles = (p.M + BN - 1) / BN;
+    p.n_tiles = 0;
+    for (int i = 0; i <= kMaxW; i++) p.tile0[i] = 0x7fffffff;
+    for (int i = 0; i < nw; i++) p.tile0[i] = p.n_tiles, p.n_tiles += (p.Nw[i] + BM - 1) / BM;
+    p.m_tiles = (p.M + BN - 1) / BN;
     const int nkb = p.K / BK, nraw = (nkb + F::KBR - 1) / F::KBR;
     const int base_items = p.n_tiles * p.m_tiles;
     int splits = 1;
@@ -765,27 +777,31 @@ int launch_tc(kf_ctx* ctx, GemmParams& p, const void* wdata, const void* xp) {
         if (rc) return rc;
         p.ws = ctx->gemv_ws, p.cnt = ctx->gemv_cnt;
     }
-    CUtensorMap tm_w, tm_x;
-    int rc;
-    if (A_TMEM)
-        rc = make_map_2d(ctx, &tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, wdata, (uint64_t)p.K * F::BITS / 8, (uint64_t)p.N, RAWB, BM,
-                         RAWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
-    else
-        rc = make_map_2d(ctx, &tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wdata, (uint64_t)p.K, (uint64_t)p.N, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap tm_w[kMaxW], tm_x;
+    int rc = KF_OK;
+    for (int i = 0; i < kMaxW && !rc; i++) {
+        const int j = i < nw ? i : 0;  // unused slots repeat the first weight (never dereferenced)
+        if (A_TMEM)
+            rc = make_map_2d(ctx, &tm_w[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, wdata[j], (uint64_t)p.K * F::BITS / 8, (uint64_t)p.Nw[j], RAWB, BM,
+                             RAWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+        else
+            rc = make_map_2d(ctx, &tm_w[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wdata[j], (uint64_t)p.K, (uint64_t)p.Nw[j], BK, BM,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+    }
     if (!rc) rc = make_map_2d(ctx, &tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xp, (uint64_t)p.K, (uint64_t)p.M, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     const int grid = std::min(p.n_items, ctx->sm_count);
-    KF_CUDA(ctx, kf_launch_pdl(ctx, kern, dim3(grid), dim3(kThreadsTC), smem, tm_w, tm_x, p));
+    KF_CUDA(ctx, kf_launch_pdl(ctx, kern, dim3(grid), dim3(kThreadsTC), smem, tm_w[0], tm_w[1], tm_w[2], tm_x, p));
     KF_LAUNCH_CHECK(ctx);
     return KF_OK;
 }
 template <int FMT, int MODE>
-int launch_tc_bn(kf_ctx* ctx, GemmParams& p, const void* wdata, const void* xp) {
-    if (p.M > 128) return launch_tc<FMT, MODE, 256>(ctx, p, wdata, xp);
-    if (p.M > 64) return launch_tc<FMT, MODE, 128>(ctx, p, wdata, xp);
-    if (p.M > 32) return launch_tc<FMT, MODE, 64>(ctx, p, wdata, xp);
-    if (p.M > 16) return launch_tc<FMT, MODE, 32>(ctx, p, wdata, xp);
-    return launch_tc<FMT, MODE, 16>(ctx, p, wdata, xp);
+int launch_tc_bn(kf_ctx* ctx, GemmParams& p, const void* const* wdata, int nw, const void* xp) {
+    if (p.M > 128) return launch_tc<FMT, MODE, 256>(ctx, p, wdata, nw, xp);
+    if (p.M > 64) return launch_tc<FMT, MODE, 128>(ctx, p, wdata, nw, xp);
+    if (p.M > 32) return launch_tc<FMT, MODE, 64>(ctx, p, wdata, nw, xp);
+    if (p.M > 16) return launch_tc<FMT, MODE, 32>(ctx, p, wdata, nw, xp);
+    return launch_tc<FMT, MODE, 16>(ctx, p, wdata, nw, xp);
 }
 
 int tc_format(const kf_tensor_desc* w, int* fmt, int* mode) {
@@ -836,28 +852,40 @@ int kf_tc_same_order(const kf_tensor_desc* a, const kf_tensor_desc* b) {
     return fa == fb ? 0 : 1;
 }
 
-// xp: activations as returned by kf_tc_prepare_x for a weight of the same type
-int kf_gemm_tc(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* xp, int M, int epilogue, const void* residual) {
-    KF_REQUIRE(ctx, y && w && xp && M >= 1, "args");
-    const int K = w->cols, N = w->rows;
-    KF_REQUIRE(ctx, K % 128 == 0 && N % 16 == 0, "K must be a multiple of 128, rows of 16");
+// xp: activations as returned by kf_tc_prepare_x for weights of this type.  n <= 3 weights of the SAME storage type, K and group share
+// one launch (their row tiles form one item space): Q/K/V and gate/up cost one kernel each instead of three / two.
+int kf_gemm_tc_multi(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* xp, int M, int epilogue, const void* residual) {
+    KF_REQUIRE(ctx, n >= 1 && n <= kMaxW && y && w && xp && M >= 1, "args");
+    const int K = w[0].cols;
     int fmt, mode;
-    if (tc_format(w, &fmt, &mode)) return KF_ERR_UNSUPPORTED;
+    if (tc_format(&w[0], &fmt, &mode)) return KF_ERR_UNSUPPORTED;
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    p.y = y, p.residual = (const uint16_t*)residual, p.M = M, p.N = N, p.K = K;
-    p.qbias = w->qbias, p.epilogue = epilogue;
+    const void* wdata[kMaxW] = {};
+    p.residual = (const uint16_t*)residual, p.M = M, p.K = K;
+    p.qbias = w[0].qbias, p.epilogue = epilogue;
     p.lop_mask = fmt == TF_Q4 ? 0x000F000Fu : fmt == TF_Q2 ? 0x00030003u : 0x00010001u, p.lop_magic = 0x43004300u;
+    for (int i = 0; i < n; i++) {
+        int f2, m2;
+        KF_REQUIRE(ctx, y[i] && !tc_format(&w[i], &f2, &m2) && f2 == fmt && m2 == mode && w[i].cols == K && w[i].group == w[0].group &&
+                            w[i].qbias == w[0].qbias,
+                   "weights of one launch must share type, K, group");
+        KF_REQUIRE(ctx, K % 128 == 0 && w[i].rows % 16 == 0, "K must be a multiple of 128, rows of 16");
+        p.y[i] = y[i], p.Nw[i] = w[i].rows, wdata[i] = w[i].data_dev;
+        if (mode != TM_PLAIN) {
+            KF_REQUIRE(ctx, kf_has_gama(w[i]) && w[i].group >= 128 && (w[i].group & (w[i].group - 1)) == 0 && K % w[i].group == 0,
+                       "group = 128 * 2^n dividing K");
+            p.zero[i] = kf_gama_zero(w[i]), p.step[i] = kf_gama_step(w[i]);
+        }
+    }
     if (mode != TM_PLAIN) {
-        KF_REQUIRE(ctx, kf_has_gama(*w) && w->group >= 128 && (w->group & (w->group - 1)) == 0 && K % w->group == 0, "group = 128 * 2^n dividing K");
-        p.zero = kf_gama_zero(*w), p.step = kf_gama_step(*w);
         int gs = 0;
-        while ((128 << gs) < w->group) gs++;
+        while ((128 << gs) < w[0].group) gs++;
         p.gshift = gs;
     }
-    if (epilogue == 1) KF_REQUIRE(ctx, residual, "residual");
+    if (epilogue == 1) KF_REQUIRE(ctx, residual && n == 1, "residual: single weight");
 #define KF_TC_CASE(F, MD) \
-    if (fmt == F && mode == MD) return launch_tc_bn<F, MD>(ctx, p, w->data_dev, xp);
+    if (fmt == F && mode == MD) return launch_tc_bn<F, MD>(ctx, p, wdata, n, xp);
     KF_TC_CASE(TF_Q4, TM_AFFINE)
     KF_TC_CASE(TF_Q4, TM_AFFINE_SYM)
     KF_TC_CASE(TF_Q2, TM_AFFINE)
@@ -868,4 +896,8 @@ int kf_gemm_tc(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* xp, in
     KF_TC_CASE(TF_BF16, TM_PLAIN)
 #undef KF_TC_CASE
     return KF_ERR_UNSUPPORTED;
+}
+int kf_gemm_tc(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* xp, int M, int epilogue, const void* residual) {
+    void* ys[1] = {y};
+    return kf_gemm_tc_multi(ctx, 1, ys, w, xp, M, epilogue, residual);
 }

@@ -114,6 +114,8 @@ int kf_ensure_buf(kf_ctx* ctx, void** buf, size_t* cap, size_t bytes);
 int kf_tc_prepare_x(kf_ctx* ctx, const kf_tensor_desc* w, const void* x, int M, const void** xp_out);
 int kf_tc_same_order(const kf_tensor_desc* a, const kf_tensor_desc* b);  // 0: one prepared copy serves both weights
 int kf_gemm_tc(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* xp, int M, int epilogue, const void* residual);
+// up to 3 weights of the same type / K / group in ONE launch (Q/K/V, gate/up)
+int kf_gemm_tc_multi(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* xp, int M, int epilogue, const void* residual);
 
 #ifdef __CUDACC__
 // Launch with the programmatic-dependent-launch attribute (when ctx->pdl): the kernel may start while its predecessor in the stream

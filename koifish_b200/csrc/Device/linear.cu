@@ -36,6 +36,11 @@ static bool use_tensor_cores(const kf_ctx* ctx, int n, const kf_tensor_desc* w, 
     return true;
 }
 
+// same storage type, K, group and bias: the weights can share one tensor-core launch
+static bool tc_fusable(const kf_tensor_desc* a, const kf_tensor_desc* b) {
+    return a->type == b->type && a->cols == b->cols && a->group == b->group && a->qbias == b->qbias;
+}
+
 // epilogue: 0 none, 1 residual, 2 swiglu(w[0] gate, w[1] up -> y[0]), 4 fp32
 static int linear_any(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                       const void* norm_w, float norm_eps) {
@@ -57,12 +62,20 @@ static int linear_any(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* 
         const size_t bytes = (size_t)M * w[0].rows * 2;
         rc = kf_ensure_buf(ctx, &ctx->tmp0, &ctx->tmp0_bytes, bytes);
         if (!rc) rc = kf_ensure_buf(ctx, &ctx->tmp1, &ctx->tmp1_bytes, bytes);
-        if (!rc) rc = kf_gemm_tc(ctx, ctx->tmp0, &w[0], xp, M, 0, nullptr);
-        if (!rc && kf_tc_same_order(&w[0], &w[1])) rc = kf_tc_prepare_x(ctx, &w[1], xin, M, &xp);
-        if (!rc) rc = kf_gemm_tc(ctx, ctx->tmp1, &w[1], xp, M, 0, nullptr);
+        if (!rc && tc_fusable(&w[0], &w[1])) {  // gate and up in one launch
+            void* gu[2] = {ctx->tmp0, ctx->tmp1};
+            rc          = kf_gemm_tc_multi(ctx, 2, gu, w, xp, M, 0, nullptr);
+        } else {
+            if (!rc) rc = kf_gemm_tc(ctx, ctx->tmp0, &w[0], xp, M, 0, nullptr);
+            if (!rc && kf_tc_same_order(&w[0], &w[1])) rc = kf_tc_prepare_x(ctx, &w[1], xin, M, &xp);
+            if (!rc) rc = kf_gemm_tc(ctx, ctx->tmp1, &w[1], xp, M, 0, nullptr);
+        }
         if (!rc) rc = kf_swiglu(ctx, y[0], ctx->tmp0, ctx->tmp1, (size_t)M * w[0].rows);  // CU_swiglu_v0 on the bf16 gate / up, as the reference
         return rc;
     }
+    bool fuse = n > 1 && epilogue != KF_EPI_RESIDUAL;
+    for (int i = 1; i < n && fuse; i++) fuse = tc_fusable(&w[0], &w[i]);
+    if (fuse) return kf_gemm_tc_multi(ctx, n, y, w, xp, M, epilogue, nullptr);  // Q / K / V in one launch
     for (int i = 0; i < n; i++) {
         if (i > 0 && kf_tc_same_order(&w[i - 1], &w[i])) rc = kf_tc_prepare_x(ctx, &w[i], xin, M, &xp);
         if (!rc) rc = kf_gemm_tc(ctx, y[i], &w[i], xp, M, epilogue, residual);

@@ -611,3 +611,24 @@ def test_attn_decode_gqa_equals_per_head_decode_attention(ctx, hd, n_head, n_kv,
     assert np.allclose(g, w, rtol=2.0 ** -6, atol=6e-3), np.abs(g - w).max()
     ref = ol.attention_decode(q[3], kc[3], vc[3], 200, n_head, n_kv, hd)
     assert np.allclose(g.reshape(M, -1)[3], ol.bf16_to_f32(ref).reshape(-1), rtol=2.0 ** -6, atol=6e-3)
+
+
+@pytest.mark.parametrize("kind", [(4, ol.RTN_ASYM), (2, ol.YYANG), "bf16"], ids=str)
+@pytest.mark.parametrize("M", [16, 48, 300])
+def test_gemm_tc_multi_weight_launch_equals_single_launches(ctx, kind, M):
+    # Q / K / V (and gate / up) share ONE tensor-core launch above the crossover: row tiles of the three weights form one item space
+    K = 1024
+    rows = (400, 128, 144)  # ragged last tiles
+    ws = [make_weight(ctx, kind, n, K, 8000 + i)[0] for i, n in enumerate(rows)]
+    x = ctx.array(rand_bf16(np.random.default_rng(M), (M, K)))
+    ctx.set_int("tc_min_m", 1)
+    try:
+        fused = kf.linear_multi(ctx, ws, x, M)
+        single = [kf.linear(ctx, w, x, M) for w in ws]
+        sw_f = kf.linear_swiglu(ctx, ws[1], ws[1], x, M).numpy(np.uint16)
+    finally:
+        ctx.set_int("tc_min_m", -1)
+    for a, b in zip(fused, single):
+        assert np.array_equal(a.numpy(np.uint16), b.numpy(np.uint16))
+    g = single[1].numpy(np.uint16)
+    assert np.array_equal(sw_f, ol.swiglu(g, g)) or (sw_f == ol.swiglu(g, g)).mean() > 0.999
