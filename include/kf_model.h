@@ -66,6 +66,11 @@ int kf_model_decode_loop(kf_model* m, int n_steps, int M);
 /* current device-side tokens / positions (after a decode loop) */
 int kf_model_read_state(kf_model* m, int32_t* tokens_host, int32_t* pos_host, int M);
 int kf_model_set_graphs(kf_model* m, int enable);
+/* Save / load every resident tensor exactly as it sits in HBM (packed data || gama, the reference's per-tensor SerialGamaData payload,
+ * src/Device/CUDA/huTensor.cu:413-458): loading skips the quantiser.  The file must come from a model built from the same config
+ * (names, shapes, storage types and groups are checked); tensor-parallel ranks use one file per rank. */
+int kf_model_save(kf_model* m, const char* path);
+int kf_model_load(kf_model* m, const char* path);
 
 /* Host-only config logic (no device needed): parse a config and report the model dimensions, and which storage type the
  * quantizer block selects for a tensor name (QUANT_CARD::Init4Neuron, reference src/Tensor/GeQuant.cpp:1186-1285; MakeInstance

@@ -110,6 +110,8 @@ SIGNATURES = {
     "kf_model_forward": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "kf_model_decode_loop": (_I, [_P, _I, _I]),
     "kf_model_read_state": (_I, [_P, _P, _P, _I]),
+    "kf_model_save": (_I, [_P, C.c_char_p]),
+    "kf_model_load": (_I, [_P, C.c_char_p]),
     "kf_model_set_graphs": (_I, [_P, _I]),
     "kf_config_dims": (_I, [C.c_char_p, C.POINTER(ModelInfo), C.POINTER(_P)]),
     "kf_config_quant_of": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_P)]),

@@ -407,6 +407,12 @@ class Model:
         self._check(self.lib.kf_model_read_state(self.h, t.ctypes.data, p.ctypes.data, M), "kf_model_read_state")
         return t, p
 
+    def save(self, path):
+        self._check(self.lib.kf_model_save(self.h, str(path).encode()), "kf_model_save")
+
+    def load(self, path):
+        self._check(self.lib.kf_model_load(self.h, str(path).encode()), "kf_model_load")
+
     def set_graphs(self, enable):
         self._check(self.lib.kf_model_set_graphs(self.h, int(bool(enable))), "kf_model_set_graphs")
 

@@ -546,4 +546,99 @@ int Fish::DecodeLoop(int n_steps, int M) {
     return KF_OK;
 }
 
+// ---- serialisation of the resident tensors: one record per tensor, payload = the device blob `data || gama` byte for byte (what the
+// reference writes per tensor in SerialGamaData, src/Device/CUDA/huTensor.cu:413-458, inside its fish.kun container).  Loading skips the
+// quantiser entirely.  Layout: "KFB1" u32 count, then per tensor: u32 name_len, name, i32 type, rows, cols, group, qbias, u64 szData,
+// u64 szGama, payload.  Tensor-parallel ranks save / load their own shard files.
+int Fish::SaveBlobs(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) {
+        error = "cannot open '" + path + "' for writing";
+        return KF_ERR_BAD_ARG;
+    }
+    std::string* hFishErr = &error;
+    (void)hFishErr;
+    const uint32_t magic = 0x3142464bu, count = (uint32_t)tensors.size();  // "KFB1"
+    fwrite(&magic, 4, 1, f), fwrite(&count, 4, 1, f);
+    std::vector<uint8_t> host;
+    int rc = KF_OK;
+    for (auto& kv : tensors) {
+        const hGTensor& t = kv.second;
+        const uint32_t nl = (uint32_t)kv.first.size();
+        const int32_t meta[5] = {(int32_t)t->type, t->ne[0], t->ne[1], (t->hQuant && t->ne[0] > 1) ? t->hQuant->params.T_group : 0, t->qBias};
+        const uint64_t sz[2] = {t->szData, t->szGama};
+        host.resize(t->nByte());
+        rc = kf_d2h(ctx, host.data(), t->data, t->nByte());
+        if (!rc) rc = kf_ctx_sync(ctx);
+        if (rc) break;
+        fwrite(&nl, 4, 1, f), fwrite(kv.first.data(), 1, nl, f), fwrite(meta, 4, 5, f), fwrite(sz, 8, 2, f);
+        if (fwrite(host.data(), 1, host.size(), f) != host.size()) {
+            error = "short write to '" + path + "'";
+            rc    = KF_ERR_BAD_ARG;
+            break;
+        }
+    }
+    fclose(f);
+    if (rc && error.empty()) error = std::string("SaveBlobs: ") + kf_last_error(ctx);
+    return rc;
+}
+int Fish::LoadBlobs(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) {
+        error = "cannot open '" + path + "'";
+        return KF_ERR_BAD_ARG;
+    }
+    auto fail = [&](const std::string& why) {
+        fclose(f);
+        error = "LoadBlobs('" + path + "'): " + why;
+        return KF_ERR_BAD_ARG;
+    };
+    uint32_t magic = 0, count = 0;
+    if (fread(&magic, 4, 1, f) != 1 || fread(&count, 4, 1, f) != 1 || magic != 0x3142464bu) return fail("not a KFB1 file");
+    if (count != tensors.size()) return fail("tensor count differs from the model built from this config");
+    std::vector<uint8_t> host;
+    for (uint32_t i = 0; i < count; i++) {
+        uint32_t nl = 0;
+        if (fread(&nl, 4, 1, f) != 1 || nl > 4096) return fail("corrupt record header");
+        std::string name(nl, '\0');
+        int32_t meta[5];
+        uint64_t sz[2];
+        if (fread(&name[0], 1, nl, f) != nl || fread(meta, 4, 5, f) != 5 || fread(sz, 8, 2, f) != 2) return fail("truncated record");
+        auto it = tensors.find(name);
+        if (it == tensors.end()) return fail("unknown tensor '" + name + "'");
+        const hGTensor& t = it->second;
+        // what this model's config selects for the tensor: quantised (bits, group of its card) or plain bf16 (norms, or a quantiser
+        // that leaves vectors alone).  A model that has not been initialised yet gets its device blob allocated here.
+        const typNUMBER tp  = (typNUMBER)meta[0];
+        const bool quantised = t->hQuant && t->ne[0] > 1;
+        const int group      = quantised ? t->hQuant->params.T_group : 0;
+        const bool type_ok   = quantised ? ((int)BitPE(tp) == t->hQuant->bits && tp != typNUMBER::BF16) || (t->hQuant->bits == 16 && tp == typNUMBER::BF16)
+                                         : tp == typNUMBER::BF16;
+        if (!type_ok || meta[1] != t->ne[0] || meta[2] != t->ne[1] || meta[3] != group)
+            return fail("tensor '" + name + "' was saved with another shape / storage type / group than this config selects");
+        if (!t->data || t->type != tp || t->szData != sz[0] || t->szGama != sz[1]) {
+            int rc = t->Alloc(tp, group);
+            if (rc) {
+                fclose(f);
+                error = std::string("LoadBlobs: ") + kf_last_error(ctx);
+                return rc;
+            }
+        }
+        if (sz[0] != t->szData || sz[1] != t->szGama) return fail("tensor '" + name + "': byte sizes do not match its shape and type");
+        host.resize(t->nByte());
+        if (fread(host.data(), 1, host.size(), f) != host.size()) return fail("truncated payload of '" + name + "'");
+        t->qBias = meta[4];
+        int rc   = kf_h2d(ctx, t->data, host.data(), host.size());
+        if (!rc) rc = kf_ctx_sync(ctx);
+        if (rc) {
+            fclose(f);
+            error = std::string("LoadBlobs: ") + kf_last_error(ctx);
+            return rc;
+        }
+    }
+    fclose(f);
+    ResetGraphs();
+    return KF_OK;
+}
+
 }  // namespace koifish

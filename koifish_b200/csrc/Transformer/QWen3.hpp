@@ -148,6 +148,9 @@ struct Fish {
     int ForwardOnRLS(int M, bool want_logits);
     // public step: host tokens/pos in, logits (optional) + greedy next tokens (optional) out.  H2D/D2H inside.
     int Forward(const int32_t* tokens, const int32_t* pos, int M, int seq_mode, uint16_t* logits_out, int32_t* next_out);
+    // the resident tensors exactly as they sit in HBM (data || gama per tensor): SerialGamaData, reference huTensor.cu:413-458
+    int SaveBlobs(const std::string& path);
+    int LoadBlobs(const std::string& path);
     // device-resident greedy loop: n_steps graph replays feeding argmax back as the next token (no host round trip)
     int DecodeLoop(int n_steps, int M);
     int UseGraph(int M, bool want_logits);

@@ -180,6 +180,14 @@ extern "C" int kf_config_shard_of(const char* config_json, const char* tensor_na
         return KF_ERR_BAD_ARG;
     }
 }
+extern "C" int kf_model_save(kf_model* m, const char* path) {
+    if (!m || !path) return KF_ERR_BAD_ARG;
+    return m->fish->SaveBlobs(path);
+}
+extern "C" int kf_model_load(kf_model* m, const char* path) {
+    if (!m || !path) return KF_ERR_BAD_ARG;
+    return m->fish->LoadBlobs(path);
+}
 extern "C" int kf_model_set_graphs(kf_model* m, int enable) {
     if (!m) return KF_ERR_BAD_ARG;
     m->fish->use_graphs = enable != 0;

@@ -225,3 +225,29 @@ def test_long_prefill_panels_match_token_by_token_and_continue_decoding(ctx):
     assert int(pb[0]) == n + 8
     with pytest.raises(kf.KoifishError):
         b.forward(toks[:100], list(range(100)), seq_mode=0)  # more than 64 rows of logits: must ask for seq_mode 2
+
+
+def test_save_and_load_packed_blobs_round_trip(ctx, tmp_path):
+    # the resident tensors travel byte for byte (data || gama): a model loaded from the file needs no quantiser and gives identical logits
+    a, _ = build_pair(ctx, attn=(4, ol.RTN_ASYM), mlp=(2, ol.YYANG), embed=(8, ol.RTN_ASYM), tie=False)
+    path = tmp_path / "model.kfb"
+    a.save(path)
+    cfg_kwargs = dict(attn=(4, ol.RTN_ASYM), mlp=(2, ol.YYANG), embed=(8, ol.RTN_ASYM), tie=False)
+    quantizer = {"group_size": 128}
+    for key, (bits, mode) in (("self_attn", cfg_kwargs["attn"]), ("mlp", cfg_kwargs["mlp"]), ("embed_tokens", cfg_kwargs["embed"])):
+        e = quant_entry(bits, mode)
+        if e:
+            quantizer[key] = e
+    b = kf.Model(ctx, kf.qwen3_config(2, 256, 512, 4, 2, 64, 1024, quantizer, False, 64, 1, 42, 1e6, norm_sigma=0.1))  # NOT initialised
+    b.load(path)
+    toks = prompt(6, 1024)
+    for p_, t_ in enumerate(toks):
+        la, _ = a.forward([t_], [p_])
+        lb, _ = b.forward([t_], [p_])
+        assert np.array_equal(la, lb)
+    # a file from another configuration is refused
+    c = kf.Model(ctx, kf.qwen3_config(2, 256, 512, 4, 2, 64, 1024, {"group_size": 128, "mlp": {"quant_method": "RTN", "bits": 4}}, False, 64, 1, 42, 1e6))
+    with pytest.raises(kf.KoifishError):
+        c.load(path)
+    with pytest.raises(kf.KoifishError):
+        c.load(tmp_path / "missing.kfb")
