@@ -75,9 +75,17 @@ __global__ void __launch_bounds__(kP2PThreads) kf_allreduce_residual_kernel(cons
         unsigned* remote = reinterpret_cast<unsigned*>(p.peer[threadIdx.x]) + ((size_t)parity * kMaxCtas + blockIdx.x) * kMaxWorld + p.rank;
         st_release_sys(remote, e);
         const unsigned* mine = reinterpret_cast<const unsigned*>(p.peer[p.rank]) + ((size_t)parity * kMaxCtas + blockIdx.x) * kMaxWorld + threadIdx.x;
+        // a lost peer fails the launch instead of hanging the GPU; the bound is wall-clock (ranks may be seconds apart at the first
+        // exchange, e.g. while one of them still quantises its shard)
         unsigned spins = 0;
+        unsigned long long t_start = 0;
         while ((int)(ld_acquire_sys(mine) - e) < 0) {
-            if (++spins > (1u << 26)) __trap();  // a lost peer fails the launch instead of hanging the GPU
+            if ((++spins & 0x3ff) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (!t_start) t_start = now;
+                if (now - t_start > 120ull * 1000000000ull) __trap();
+            }
         }
     }
     __syncthreads();
