@@ -79,8 +79,10 @@ const char* kf_last_error(kf_ctx* ctx);
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t kf_launch_count(kf_ctx* ctx);
 /* tuning knobs for sweeps: "gemv_splitk" (0 = heuristic), "gemv_variant", "gemv_exact", "attn_split", "pdl",
- * "tc_min_m" (token count from which kf_linear* use the tcgen05 GEMM: -1 = measured per-type crossover, 0 = never, n = from n) */
+ * "gqa_min_ctx" (single-sequence decode: context length beyond which the kv-group tensor-core attention replaces the fused per-head
+ * kernel; default 1024), "tc_min_m" (token count from which kf_linear* use the tcgen05 GEMM: -1 = measured per-type crossover, 0 = never, n = from n) */
 int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value);
+int kf_ctx_get_int(kf_ctx* ctx, const char* key, int* value_out); /* gqa_min_ctx, tc_min_m, pdl, attn_split */
 
 /* ---- device memory (huTensor::Alloc_1, src/Device/CUDA/huTensor.cu:70-103) ---- */
 int kf_malloc(kf_ctx* ctx, size_t bytes, void** dev_out);

@@ -116,6 +116,20 @@ extern "C" void* kf_ctx_stream(kf_ctx* ctx) { return ctx ? (void*)ctx->stream : 
 extern "C" int kf_ctx_sm_count(kf_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 extern "C" const char* kf_last_error(kf_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 extern "C" uint64_t kf_launch_count(kf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int kf_ctx_get_int(kf_ctx* ctx, const char* key, int* value_out) {
+    if (!ctx || !key || !value_out) return KF_ERR_BAD_ARG;
+    if (!strcmp(key, "gqa_min_ctx"))
+        *value_out = ctx->gqa_min_ctx;
+    else if (!strcmp(key, "tc_min_m"))
+        *value_out = ctx->tc_min_m;
+    else if (!strcmp(key, "pdl"))
+        *value_out = ctx->pdl;
+    else if (!strcmp(key, "attn_split"))
+        *value_out = ctx->attn_split;
+    else
+        return KF_ERR_BAD_ARG;
+    return KF_OK;
+}
 extern "C" int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value) {
     if (!ctx || !key)
         return KF_ERR_BAD_ARG;
@@ -133,6 +147,8 @@ extern "C" int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value) {
         ctx->tc_min_m = value;
     else if (!strcmp(key, "attn_split"))
         ctx->attn_split = value;
+    else if (!strcmp(key, "gqa_min_ctx"))
+        ctx->gqa_min_ctx = value;
     else if (!strcmp(key, "attn_warps"))
         ctx->attn_warps = value;
     else if (!strcmp(key, "debug_skip"))

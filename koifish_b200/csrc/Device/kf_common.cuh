@@ -40,6 +40,7 @@ struct kf_ctx {
     int gemv_cluster = 1;  // M = 1 split-K: 1 = merge the k-slices of a row block inside a thread-block cluster (DSMEM) when S <= 8; 2 = also cap S at 8; 0 = global workspace
     int gemv_exact   = 1;  // 1: in-kernel dequant reproduces the reference's bf16 roundings bit for bit ; 0: factored scale/zero (MODE_FACTOR)
     int attn_split   = 0;
+    int gqa_min_ctx  = 1024;  // single-sequence decode: contexts beyond this use the kv-group tensor-core attention (Transformer layer reads it)
     int attn_warps   = 0;  // warps per CTA of the cluster attention (0 = default)
     int debug_skip   = 0;  // timing experiments only (results are garbage): bit 0 skips the attention launch, bit 1 the skinny GEMV launches
     // tensor parallel

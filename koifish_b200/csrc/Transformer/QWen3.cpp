@@ -104,7 +104,10 @@ int SelfAttention::cuInfer(void* inpL, int M) {
     KF_TRY(kf_rmsnorm_linear(f->ctx, 3, y3, w3, inpL, norm.w->data, norm.rms_eps, M, 0));
     const int lay   = layid - 1;
     const size_t ss = f->seq_mode ? f->cache.seq_stride() : 0;
-    if (f->seq_mode && M >= f->gqa_min_batch && n_head / n_head_kv <= 16) {
+    int gqa_min_ctx = 1024;
+    kf_ctx_get_int(f->ctx, "gqa_min_ctx", &gqa_min_ctx);
+    const bool long_ctx = M == 1 && f->attn_hint + 1 > gqa_min_ctx;  // one sequence, long context: stream each cached row once per kv head
+    if (((f->seq_mode && M >= f->gqa_min_batch) || long_ctx) && n_head / n_head_kv <= 16) {
         // many sequences: QK-norm + RoPE + append, then the kv-group attention on the tensor cores (each cached row read once per kv head)
         KF_TRY(rope.cuInfer(this, M));
         KF_TRY(kf_attn_decode_gqa(f->ctx, f->att, f->q, f->cache.Get(KVCache::KV_KEY, lay), f->cache.Get(KVCache::KV_VAL, lay), f->d_pos, M, n_head,
@@ -427,9 +430,16 @@ int Fish::ForwardOnRLS(int M, bool want_logits) {
     return KF_OK;
 }
 
-// graph key: M<<8 | want_logits | seq_mode<<1 | feedback<<2 | argmax<<3 | last_only<<5 | consecutive<<6
+// graph key: M<<12 | ctx bucket<<7 | want_logits | seq_mode<<1 | feedback<<2 | argmax<<3 | last_only<<5 | consecutive<<6
+// contexts are bucketed by powers of two (>= 512): the attention launch geometry (slices, kernel choice) follows the bucket
+int Fish::CtxBucket() const {
+    int b = 9;
+    while ((1 << b) < staged_pos_max + 1 && (1 << b) < config.max_seq_len) b++;
+    return b;
+}
 int Fish::UseGraph(int M, bool want_logits) {
-    return (M << 8) | (int)want_logits | (seq_mode << 1) | ((int)last_only << 5) | ((int)panel_consecutive << 6);
+    attn_hint = std::min(config.max_seq_len, 1 << CtxBucket()) - 1;
+    return (M << 12) | (CtxBucket() << 7) | (int)want_logits | (seq_mode << 1) | ((int)last_only << 5) | ((int)panel_consecutive << 6);
 }
 
 int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, uint16_t* logits_out, int32_t* next_out) {

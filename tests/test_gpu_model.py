@@ -251,3 +251,34 @@ def test_save_and_load_packed_blobs_round_trip(ctx, tmp_path):
         c.load(path)
     with pytest.raises(kf.KoifishError):
         c.load(tmp_path / "missing.kfb")
+
+
+def test_long_context_decode_switches_to_kv_group_attention(ctx):
+    # beyond gqa_min_ctx (default 1024) single-sequence decode runs QK-norm + RoPE + append, then the kv-group tensor-core attention;
+    # the logits must agree with the fused per-head path (knob raised so that it never switches), and the graphs must be re-captured
+    # when the context crosses a power-of-two bucket
+    quantizer = {"group_size": 128, "self_attn": {"quant_method": "RTN", "bits": 4}, "mlp": {"quant_method": "RTN", "bits": 4}}
+    cfg = kf.qwen3_config(2, 256, 512, 8, 2, 64, 1024, quantizer, True, 2048, 1, 42, 1e6, norm_sigma=0.1, max_prefill=256)
+    toks = prompt(1100, 1024)
+
+    def run(min_ctx):
+        ctx.set_int("gqa_min_ctx", min_ctx)
+        m = kf.Model(ctx, cfg)
+        m.init_random()
+        _, nxt = m.prefill(toks)
+        outs = []
+        tok, pos = nxt, len(toks)
+        for _ in range(4):  # eager, then captured graph, then replays
+            lg, nx = m.forward([tok], [pos], want_next=True)
+            outs.append(lg[0].copy())
+            tok, pos = int(nx[0]), pos + 1
+        return outs
+
+    try:
+        a = run(1024)
+        b = run(1 << 30)
+    finally:
+        ctx.set_int("gqa_min_ctx", 1024)
+    for la, lb in zip(a, b):
+        err, g, w = logits_close(la, lb)
+        assert err <= 1e-2 and int(np.argmax(g)) == int(np.argmax(w))
