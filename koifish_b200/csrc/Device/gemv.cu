@@ -43,9 +43,21 @@ constexpr int KT       = 32;   // k per thread slot
 
 // CPB: bytes per cp.async ; NCH: copies per (row, k-step) and thread ; D1 / D2: ring depth for 16 / 32 rows per warp
 template <int FMT> struct Fmt;
-template <> struct Fmt<FMT_Q4>   { static constexpr int BITS = 4,  CPB = 16, NCH = 1, D1 = 5,  D2 = 3; };
-template <> struct Fmt<FMT_Q2>   { static constexpr int BITS = 2,  CPB = 8,  NCH = 1, D1 = 8,  D2 = 5; };
-template <> struct Fmt<FMT_Q1>   { static constexpr int BITS = 1,  CPB = 4,  NCH = 1, D1 = 12, D2 = 8; };
+// cp.async ring depths (k-steps in flight per thread).  Measured inside the decode step (profiles/r01_ring_depth.txt): a SHALLOW ring wins --
+// 3 stages for 4-bit give 155 tok/s on Qwen3-32B against 145 with 5 and 114 with 8: the shared memory a CTA does not take lets the next
+// kernel's CTAs become resident (and start their own weight stream) before this kernel has drained.
+#ifndef KF_GEMV_D1_Q4
+#define KF_GEMV_D1_Q4 3
+#endif
+template <> struct Fmt<FMT_Q4>   { static constexpr int BITS = 4,  CPB = 16, NCH = 1, D1 = KF_GEMV_D1_Q4,  D2 = 3; };
+#ifndef KF_GEMV_D1_Q2
+#define KF_GEMV_D1_Q2 4
+#endif
+#ifndef KF_GEMV_D1_Q1
+#define KF_GEMV_D1_Q1 6
+#endif
+template <> struct Fmt<FMT_Q2>   { static constexpr int BITS = 2,  CPB = 8,  NCH = 1, D1 = KF_GEMV_D1_Q2,  D2 = 5; };
+template <> struct Fmt<FMT_Q1>   { static constexpr int BITS = 1,  CPB = 4,  NCH = 1, D1 = KF_GEMV_D1_Q1, D2 = 8; };
 template <> struct Fmt<FMT_F8>   { static constexpr int BITS = 8,  CPB = 16, NCH = 2, D1 = 3,  D2 = 2; };
 template <> struct Fmt<FMT_BF16> { static constexpr int BITS = 16, CPB = 16, NCH = 4, D1 = 2,  D2 = 2; };
 
@@ -617,7 +629,10 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
 
 // ---- host side ------------------------------------------------------------------------------------------------------------------
 constexpr size_t kSmemCap  = 100 * 1024;  // two CTAs per SM
-constexpr size_t kSmemSoft = (KF_GEMV_OCC == 4 ? 55 : 73) * 1024;  // KF_GEMV_OCC CTAs per SM
+#ifndef KF_GEMV_SOFT_KB
+#define KF_GEMV_SOFT_KB (KF_GEMV_OCC == 4 ? 55 : 73)
+#endif
+constexpr size_t kSmemSoft = (size_t)KF_GEMV_SOFT_KB * 1024;  // KF_GEMV_OCC CTAs per SM
 
 struct FmtInfo {
     int bits, cpb, nch, d1, d2;
