@@ -124,7 +124,7 @@ int kf_dequant(kf_ctx* ctx, const kf_tensor_desc* w, void* out_bf16_dev);
  *      cuBLASLt; here unpack + dequant are fused into the matmul.
  *      epilogue flags: KF_EPI_RESIDUAL  y = RN(residual + RN_bf16(acc))   (replaces the following CU_add3, packedN.cuh:867-875)
  *      Few tokens take the HBM-bound skinny kernel (mma.sync GEMV), more the persistent tcgen05 / TMEM / TMA kernel; the crossover
- *      is per weight type (bf16: always tcgen05, f8: 9 tokens, packed 4/2/1-bit: 16; profiles/r01_tc_crossover.txt). ---- */
+ *      is per weight type (bf16: always tcgen05, everything else from 9 tokens; profiles/r01_tc_crossover.txt). ---- */
 enum { KF_EPI_NONE = 0, KF_EPI_RESIDUAL = 1, KF_EPI_F32 = 4 /* y is float [M][rows], unrounded partial sums (tensor parallel) */ };
 int kf_linear(kf_ctx* ctx, void* y_dev, const kf_tensor_desc* w, const void* x_dev, int M, int epilogue, const void* residual_dev);
 /* up to 3 weights sharing x (Q/K/V: SelfAttention::cuInfer, src/Device/CUDA/QKV.cu:648-652) in one launch; y_dev[i] is [M][rows_i] */

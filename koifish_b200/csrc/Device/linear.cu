@@ -23,14 +23,16 @@ static int linear_panels(kf_ctx* ctx, int n, void* const* y, const kf_tensor_des
     return KF_OK;
 }
 
-// Token count from which the tensor-core kernel beats the skinny one (measured on B200, profiles/r01_tc_crossover.txt): bf16 weights
-// always (TMA streams them at the full HBM rate), f8 from 9 tokens, the packed formats from 16 (below that the in-register expansion
-// of the skinny kernel is cheaper than the producer -> TMEM hand-off).  ctx knob tc_min_m: -1 auto, 0 never, n > 0 fixed threshold.
+// Token count from which the tensor-core kernel beats the skinny one (measured on B200): bf16 weights always (TMA streams them at the
+// full HBM rate), everything else from 9 tokens.  Launch by launch the packed formats cross over between 12 and 16 tokens
+// (profiles/r01_tc_crossover.txt), but inside the model the tensor-core path also shares one launch between Q/K/V and between gate/up,
+// and the skinny kernel's 16-token variant is its weakest: Qwen3-32B batch 12 decodes at 972 tok/s this way against 689
+// (profiles/r01_tc_crossover.txt, in-model table).  ctx knob tc_min_m: -1 auto, 0 never, n > 0 fixed threshold.
 static bool use_tensor_cores(const kf_ctx* ctx, int n, const kf_tensor_desc* w, int M) {
     if (ctx->tc_min_m == 0) return false;
     for (int i = 0; i < n; i++) {
         if (w[i].cols % 128 != 0 || w[i].rows % 16 != 0 || ((uintptr_t)w[i].data_dev & 15)) return false;
-        const int need = ctx->tc_min_m > 0 ? ctx->tc_min_m : w[i].type == KF_T_BF16 ? 1 : w[i].type == KF_T_F8E5M2 ? 9 : 16;
+        const int need = ctx->tc_min_m > 0 ? ctx->tc_min_m : w[i].type == KF_T_BF16 ? 1 : 9;
         if (M < need) return false;
     }
     return true;

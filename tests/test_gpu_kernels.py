@@ -24,6 +24,19 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(autouse=True)
+def _skinny_kernel_for_gemv_tests(request, ctx):
+    """tests named test_gemv_* / test_linear_* pin the mma.sync skinny kernel at every token count up to 64; everything else runs with
+    the product's routing (tcgen05 kernel from 9 tokens, bf16 weights always)"""
+    name = request.node.name
+    if name.startswith("test_gemv_") or name.startswith("test_linear_"):
+        ctx.set_int("tc_min_m", 0)
+        yield
+        ctx.set_int("tc_min_m", -1)
+    else:
+        yield
+
+
 def oracle_qtensor(ctx, rows, cols, bits, mode, seed, group=128, sigma=0.02):
     """weights quantised by the ORACLE packer, uploaded as-is: the kernels must read the reference's byte layout"""
     w = ol.fill_normal(rows * cols, seed, sigma)

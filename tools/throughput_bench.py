@@ -45,6 +45,9 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = kf.Context(0, stream.cuda_stream)
+    for kv in [s for s in os.environ.get("KF_SET", "").split(",") if s]:  # tuning sweeps: KF_SET=tc_min_m=9,attn_split=4
+        k, v = kv.split("=")
+        ctx.set_int(k, int(v))
     out = open(args.out, "a") if args.out else None
     peaks = {}
     try:
