@@ -98,6 +98,48 @@ __global__ void __launch_bounds__(256) kf_permute_x_kernel(uint16_t* __restrict_
     for (int j = 0; j < 4; j++) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
 }
 
+// RMSNorm (the arithmetic and summation order of kf_rmsnorm_kernel, ops.cu: bit-identical output) written directly in the permuted
+// k order: one launch instead of norm + permute in front of the Q/K/V and gate/up launches
+template <int FMT>
+__global__ void __launch_bounds__(256) kf_rmsnorm_permute_kernel(uint16_t* __restrict__ xp, const uint16_t* __restrict__ x, const uint16_t* __restrict__ w,
+                                                                  int dim, float eps) {
+    __shared__ float red[32];
+    const uint16_t* xr = x + (size_t)blockIdx.x * dim;
+    uint16_t* orow     = xp + (size_t)blockIdx.x * dim;
+    float ss = 0.f;
+    for (int i = threadIdx.x * 8; i < dim; i += blockDim.x * 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
+        const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float a = bf16lo(q[j]), b = bf16hi(q[j]);
+            ss = fmaf(a, a, ss), ss = fmaf(b, b, ss);
+        }
+    }
+    ss = block_sum(ss, red);
+    const float s = 1.0f / sqrtf(fmaf(ss, 1.0f / (float)dim, eps));
+    for (int slot = threadIdx.x; slot * 32 < dim; slot += blockDim.x) {
+        uint32_t n[16];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint4 v = *reinterpret_cast<const uint4*>(xr + slot * 32 + c * 8);
+            const uint4 g = *reinterpret_cast<const uint4*>(w + slot * 32 + c * 8);
+            const uint32_t q[4] = {v.x, v.y, v.z, v.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) n[4 * c + j] = pack_bf16x2((bf16lo(q[j]) * s) * bf16lo(gw[j]), (bf16hi(q[j]) * s) * bf16hi(gw[j]));
+        }
+        uint32_t o[16];
+#pragma unroll
+        for (int p = 0; p < 16; p++) {
+            const int e0 = tperm<FMT>(2 * p), e1 = tperm<FMT>(2 * p + 1);
+            o[p] = ((n[e0 >> 1] >> ((e0 & 1) * 16)) & 0xffffu) | (((n[e1 >> 1] >> ((e1 & 1) * 16)) & 0xffffu) << 16);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(orow + slot * 32);
+#pragma unroll
+        for (int j = 0; j < 4; j++) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+}
+
 // ---- PTX helpers ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -839,6 +881,30 @@ int kf_tc_prepare_x(kf_ctx* ctx, const kf_tensor_desc* w, const void* x, int M, 
         kf_permute_x_kernel<TF_Q2><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)ctx->xperm, (const uint16_t*)x, n_slots);
     else
         kf_permute_x_kernel<TF_Q1><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)ctx->xperm, (const uint16_t*)x, n_slots);
+    KF_LAUNCH_CHECK(ctx);
+    *xp_out = ctx->xperm;
+    return KF_OK;
+}
+// RMSNorm + kf_tc_prepare_x in one launch (packed types); bf16 / f8 weights get the plain RMSNorm into the context's xnorm scratch
+int kf_tc_prepare_x_norm(kf_ctx* ctx, const kf_tensor_desc* w, const void* x, const void* norm_w, float eps, int M, const void** xp_out) {
+    int fmt, mode;
+    if (tc_format(w, &fmt, &mode)) return KF_ERR_UNSUPPORTED;
+    const int K = w->cols;
+    KF_REQUIRE(ctx, K % 32 == 0, "K");
+    if (fmt == TF_BF16 || fmt == TF_F8) {
+        int rc = kf_ensure_buf(ctx, &ctx->xnorm, &ctx->xnorm_bytes, (size_t)M * K * 2);
+        if (!rc) rc = kf_rmsnorm(ctx, ctx->xnorm, x, norm_w, M, K, eps);
+        *xp_out = ctx->xnorm;
+        return rc;
+    }
+    int rc = kf_ensure_buf(ctx, &ctx->xperm, &ctx->xperm_bytes, (size_t)M * K * 2);
+    if (rc) return rc;
+    if (fmt == TF_Q4)
+        kf_rmsnorm_permute_kernel<TF_Q4><<<M, 256, 0, ctx->stream>>>((uint16_t*)ctx->xperm, (const uint16_t*)x, (const uint16_t*)norm_w, K, eps);
+    else if (fmt == TF_Q2)
+        kf_rmsnorm_permute_kernel<TF_Q2><<<M, 256, 0, ctx->stream>>>((uint16_t*)ctx->xperm, (const uint16_t*)x, (const uint16_t*)norm_w, K, eps);
+    else
+        kf_rmsnorm_permute_kernel<TF_Q1><<<M, 256, 0, ctx->stream>>>((uint16_t*)ctx->xperm, (const uint16_t*)x, (const uint16_t*)norm_w, K, eps);
     KF_LAUNCH_CHECK(ctx);
     *xp_out = ctx->xperm;
     return KF_OK;

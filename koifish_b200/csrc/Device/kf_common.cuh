@@ -113,6 +113,7 @@ int kf_ensure_buf(kf_ctx* ctx, void** buf, size_t* cap, size_t bytes);
 // gemm_tc.cu: tcgen05 / TMEM dequant-GEMM; epilogue 0 none / 1 residual / 4 fp32.  xp = the activations in the k order the kernel
 // wants for w's type, as returned by kf_tc_prepare_x (x itself, or the context scratch holding the permuted copy)
 int kf_tc_prepare_x(kf_ctx* ctx, const kf_tensor_desc* w, const void* x, int M, const void** xp_out);
+int kf_tc_prepare_x_norm(kf_ctx* ctx, const kf_tensor_desc* w, const void* x, const void* norm_w, float eps, int M, const void** xp_out);
 int kf_tc_same_order(const kf_tensor_desc* a, const kf_tensor_desc* b);  // 0: one prepared copy serves both weights
 int kf_gemm_tc(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* xp, int M, int epilogue, const void* residual);
 // up to 3 weights of the same type / K / group in ONE launch (Q/K/V, gate/up)

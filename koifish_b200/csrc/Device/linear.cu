@@ -50,16 +50,24 @@ static int linear_any(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* 
     // ---- tensor-core path: RMSNorm (if any) once into a scratch, then one tcgen05 GEMM per weight ----
     const int K    = w[0].cols;
     const void* xin = x;
-    if (norm_w) {
-        int rc = kf_ensure_buf(ctx, &ctx->xnorm, &ctx->xnorm_bytes, (size_t)M * K * 2);
-        if (!rc) rc = kf_rmsnorm(ctx, ctx->xnorm, x, norm_w, M, K, norm_eps);
+    const void* xp  = nullptr;
+    int rc          = KF_OK;
+    bool one_order  = true;  // every weight wants the same activation order: RMSNorm can be written in that order directly
+    for (int i = 1; i < n; i++) one_order = one_order && !kf_tc_same_order(&w[0], &w[i]);
+    if (norm_w && one_order) {
+        rc = kf_tc_prepare_x_norm(ctx, &w[0], x, norm_w, norm_eps, M, &xp);  // norm + permutation in one launch
         if (rc) return rc;
-        xin = ctx->xnorm;
+    } else {
+        if (norm_w) {
+            rc = kf_ensure_buf(ctx, &ctx->xnorm, &ctx->xnorm_bytes, (size_t)M * K * 2);
+            if (!rc) rc = kf_rmsnorm(ctx, ctx->xnorm, x, norm_w, M, K, norm_eps);
+            if (rc) return rc;
+            xin = ctx->xnorm;
+        }
+        // the activations in the k order of the weights' type: prepared once, shared by every weight of the same type
+        rc = kf_tc_prepare_x(ctx, &w[0], xin, M, &xp);
+        if (rc) return rc;
     }
-    // the activations in the k order of the weights' type: prepared once, shared by every weight of the same type
-    const void* xp = nullptr;
-    int rc = kf_tc_prepare_x(ctx, &w[0], xin, M, &xp);
-    if (rc) return rc;
     if (epilogue == 2) {
         const size_t bytes = (size_t)M * w[0].rows * 2;
         rc = kf_ensure_buf(ctx, &ctx->tmp0, &ctx->tmp0_bytes, bytes);
