@@ -140,6 +140,9 @@ def run_reference(args, dims):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is meant to use every host thread it can get, and libgomp
+    # reads the variable when it is loaded (below, with the oracle libraries)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import oracle_lib as ol
     ref = None
     try:
