@@ -813,6 +813,44 @@ __global__ void __launch_bounds__(128) kf_attn_gqa_kernel(uint16_t* __restrict__
         }
     }
 }
+
+// ---- QK-norm + RoPE + K/V append for big panels: one WARP per (token, head) (the block-per-head kernel of ops.cu needs 150 K tiny
+// blocks for a 2048-token panel and is scheduling bound: 80 us against 15 us here).  Same arithmetic; the sum of squares is taken in
+// warp-butterfly order as in the fused decode kernel.
+template <int DPL>
+__global__ void __launch_bounds__(256) kf_qknorm_rope_kv_warp_kernel(uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
+                                                                     const uint16_t* __restrict__ v, const uint16_t* __restrict__ qw,
+                                                                     const uint16_t* __restrict__ kw, uint16_t* __restrict__ kcache,
+                                                                     uint16_t* __restrict__ vcache, const float2* __restrict__ table,
+                                                                     const int32_t* __restrict__ pos_dev, int M, int n_head, int n_kv, float eps,
+                                                                     size_t seq_stride) {
+    constexpr int HD = DPL * 32;
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int per_tok   = n_head + n_kv;
+    if (wid >= (long long)M * per_tok) return;
+    const int m = (int)(wid / per_tok), h = (int)(wid % per_tok);
+    const int pos = pos_dev[m];
+    const float2* cs_row = table + (size_t)pos * (HD / 2);
+    const bool is_q = h < n_head;
+    const int kvh   = h - n_head;
+    const uint16_t* src = is_q ? q + ((size_t)m * n_head + h) * HD : k + ((size_t)m * n_kv + kvh) * HD;
+    uint16_t* dst       = is_q ? q + ((size_t)m * n_head + h) * HD : kcache + (size_t)m * seq_stride + ((size_t)pos * n_kv + kvh) * HD;
+    float o[DPL];
+    norm_rope_row<DPL>(o, src, is_q ? qw : kw, cs_row, lane, eps);
+    if constexpr (DPL == 4)
+        *reinterpret_cast<uint2*>(dst + lane * 4) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+    else
+        *reinterpret_cast<uint32_t*>(dst + lane * 2) = pack_bf16x2(o[0], o[1]);
+    if (!is_q) {  // the V row of this kv head
+        const uint16_t* vs = v + ((size_t)m * n_kv + kvh) * HD + lane * DPL;
+        uint16_t* vd       = vcache + (size_t)m * seq_stride + ((size_t)pos * n_kv + kvh) * HD + lane * DPL;
+        if constexpr (DPL == 4)
+            *reinterpret_cast<uint2*>(vd) = *reinterpret_cast<const uint2*>(vs);
+        else
+            *reinterpret_cast<uint32_t*>(vd) = *reinterpret_cast<const uint32_t*>(vs);
+    }
+}
 }  // namespace
 
 // ROPE::cuInfer (rope.cu:645-672) + attention_qk / softmax / attention_v (operator.cuh:573-668) of SelfAttention::cuInfer (QKV.cu:660-674)
@@ -992,5 +1030,22 @@ extern "C" int kf_attn_decode_gqa(kf_ctx* ctx, void* out, const void* q, const v
             kf_attn_combine_kernel<2><<<g2, 64, 0, ctx->stream>>>((uint16_t*)out, ws, n_head, nsplit);
         KF_LAUNCH_CHECK(ctx);
     }
+    return KF_OK;
+}
+
+// warp-per-head variant of kf_qknorm_rope_kvappend for big panels (called from ops.cu); hd 64 / 128 only
+int kf_qknorm_rope_kv_warp(kf_ctx* ctx, void* q, const void* k, const void* v, const void* qw, const void* kw, void* kcache, void* vcache,
+                           const void* table, const int32_t* pos_dev, int M, int n_head, int n_kv, int hd, float eps, size_t seq_stride) {
+    const long long warps = (long long)M * (n_head + n_kv);
+    const unsigned blocks = (unsigned)((warps + 7) / 8);
+    if (hd == 128)
+        kf_qknorm_rope_kv_warp_kernel<4><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v, (const uint16_t*)qw,
+                                                                          (const uint16_t*)kw, (uint16_t*)kcache, (uint16_t*)vcache, (const float2*)table,
+                                                                          pos_dev, M, n_head, n_kv, eps, seq_stride);
+    else
+        kf_qknorm_rope_kv_warp_kernel<2><<<blocks, 256, 0, ctx->stream>>>((uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v, (const uint16_t*)qw,
+                                                                          (const uint16_t*)kw, (uint16_t*)kcache, (uint16_t*)vcache, (const float2*)table,
+                                                                          pos_dev, M, n_head, n_kv, eps, seq_stride);
+    KF_LAUNCH_CHECK(ctx);
     return KF_OK;
 }

@@ -108,6 +108,8 @@ static inline bool kf_has_gama(const kf_tensor_desc& w) { return w.gama_dev || (
 void kf_p2p_destroy(kf_ctx* ctx);
 int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters);
 int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes);
+int kf_qknorm_rope_kv_warp(kf_ctx* ctx, void* q, const void* k, const void* v, const void* qw, const void* kw, void* kcache, void* vcache,
+                           const void* table, const int32_t* pos_dev, int M, int n_head, int n_kv, int hd, float eps, size_t seq_stride);
 int kf_ensure_attn_cnt(kf_ctx* ctx, int counters);
 int kf_ensure_buf(kf_ctx* ctx, void** buf, size_t* cap, size_t bytes);
 // gemm_tc.cu: tcgen05 / TMEM dequant-GEMM; epilogue 0 none / 1 residual / 4 fp32.  xp = the activations in the k order the kernel

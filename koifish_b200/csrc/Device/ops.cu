@@ -106,6 +106,8 @@ extern "C" int kf_qknorm_rope_kvappend(kf_ctx* ctx, void* q, const void* k, cons
                                        int max_seq, float eps, size_t seq_stride) {
     if (!ctx || !q || !k || !v || !kcache || !vcache || !table || !pos_dev) return KF_ERR_BAD_ARG;
     KF_REQUIRE(ctx, M >= 1 && hd % 2 == 0 && hd / 2 <= 1024 && n_head % n_kv == 0 && max_seq > 0, "shape");
+    if (M >= 16 && (hd == 128 || hd == 64))  // big panels: one warp per (token, head), attention.cu
+        return kf_qknorm_rope_kv_warp(ctx, q, k, v, qw, kw, kcache, vcache, table, pos_dev, M, n_head, n_kv, hd, eps, seq_stride);
     dim3 grid(n_head + n_kv, M);
     kf_qknorm_rope_kv_kernel<<<grid, hd / 2, 0, ctx->stream>>>((uint16_t*)q, (const uint16_t*)k, (const uint16_t*)v, (const uint16_t*)qw,
                                                               (const uint16_t*)kw, (uint16_t*)kcache, (uint16_t*)vcache, (const float2*)table,

@@ -391,11 +391,12 @@ def test_rmsnorm(ctx, rows, dim):
 
 
 @pytest.mark.parametrize("hd,n_head,n_kv", [(128, 16, 8), (64, 4, 2)])
+@pytest.mark.parametrize("M", [3, 40])
 @pytest.mark.parametrize("theta", [1e4, 1e6])
-def test_qknorm_rope_kvappend(ctx, hd, n_head, n_kv, theta):
+def test_qknorm_rope_kvappend(ctx, hd, n_head, n_kv, theta, M):
     rng = np.random.default_rng(hd)
-    M, max_seq = 3, 64
-    pos = np.array([5, 17, 63], dtype=np.int32)
+    max_seq = 64
+    pos = np.array([5, 17, 63], dtype=np.int32) if M == 3 else (np.arange(M, dtype=np.int32) + 10)  # M >= 16: warp-per-head kernel
     q, k, v = rand_bf16(rng, (M, n_head * hd)), rand_bf16(rng, (M, n_kv * hd)), rand_bf16(rng, (M, n_kv * hd))
     qw, kw = rand_bf16(rng, (hd,), 0.3), rand_bf16(rng, (hd,), 0.3)
     qd = ctx.array(q)
