@@ -198,8 +198,9 @@ __device__ __forceinline__ void build_a(uint32_t (&a)[4], const uint32_t (&wa)[N
     }
 }
 
-// NT: 8-token column tiles ; M1: single token (activations broadcast) ; RT: 16-row tiles per warp
-template <int FMT, int MODE, int NT, bool M1, int RT>
+// NT: 8-token column tiles ; MXS: token rows staged in shared memory when NT == 1 (1, 2, 4 or 8: the MMA's 8 columns replicate them, so
+// a 2-token step stages a quarter of the activations of an 8-token one) ; RT: 16-row tiles per warp
+template <int FMT, int MODE, int NT, int MXS, int RT>
 #ifndef KF_GEMV_OCC
 #define KF_GEMV_OCC 3
 #endif
@@ -208,7 +209,8 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
     constexpr int DEPTH = RT == 2 ? F::D2 : F::D1, CPB = F::CPB, NCH = F::NCH;
     constexpr int TB = fmt_tb(F::BITS), NR = TB / 4;  // bytes / 32-bit registers per thread, row and k-step
     constexpr int STEPB = KSTEP * F::BITS / 8;         // bytes per row per k-step
-    constexpr int MX = M1 ? 1 : 8 * NT;                // token rows staged in shared memory
+    constexpr int MX = NT == 1 ? MXS : 8 * NT;         // token rows staged in shared memory
+    constexpr bool M1 = MX == 1;
     constexpr int MP = 8 * NT;                         // token columns of the fp32 tile
     constexpr int ROWS = 128 * RT, HALF = ROWS / 2, WROWS = 16 * RT, TS = ROWS + 4, GS = ROWS + 1;
     static_assert(TB == CPB * NCH, "ring chunking");
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
 
     if (wactive) {
         const uint32_t bias2  = pack_bf16x2((float)(128 + p.qbias), (float)(128 + p.qbias));
-        const int xlane       = (M1 ? 0 : g) * 4 + t;
+        const int xlane       = (MX >= 8 ? g : (g & (MX - 1))) * 4 + t;  // column g of the MMA reads token g mod MX
         const uint32_t* gbase = sgam + warp * WROWS + g;
         int slot = 0;
 #pragma unroll 1
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
             for (int u = 0; u < UNITS; u++) {
                 uint4 xb[NT];
 #pragma unroll
-                for (int nt = 0; nt < NT; nt++) xb[nt] = smem[((s * UNITS + u) * MX + (M1 ? 0 : nt * 8)) * 4 + xlane];
+                for (int nt = 0; nt < NT; nt++) xb[nt] = smem[((s * UNITS + u) * MX + (MX >= 8 ? nt * 8 : 0)) * 4 + xlane];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
 #pragma unroll
@@ -527,7 +529,8 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
                     const float ka = fmaf(off, sa, bf16lo(ga)), kb = fmaf(off, sb, bf16lo(gb));  // (128+qbias)*step + zero
 #pragma unroll
                     for (int nt = 0; nt < NT; nt++) {
-                        const float2 sx = M1 ? make_float2(sxs[s], sxs[s]) : *reinterpret_cast<const float2*>(sxs + s * MX + nt * 8 + 2 * t);
+                        const float2 sx = MX >= 8 ? *reinterpret_cast<const float2*>(sxs + s * MX + nt * 8 + 2 * t)
+                                                  : make_float2(sxs[s * MX + ((2 * t) & (MX - 1))], sxs[s * MX + ((2 * t + 1) & (MX - 1))]);
                         acc[rt][nt][0] += fmaf(sa, accg[rt][nt][0], -ka * sx.x);
                         acc[rt][nt][1] += fmaf(sa, accg[rt][nt][1], -ka * sx.y);
                         acc[rt][nt][2] += fmaf(sb, accg[rt][nt][2], -kb * sx.x);
@@ -655,9 +658,10 @@ static size_t step_bytes(int mode, int mx, int rows_cta) {
     return (size_t)UNITS * mx * 64 + (mode == MODE_PLAIN ? 0 : (size_t)(rows_cta + 1) * 4) + (mode == MODE_FACTOR ? (size_t)mx * 4 : 0);
 }
 
-template <int FMT, int MODE, int NT, bool M1, int RT>
+template <int FMT, int MODE, int NT, int MXS, int RT>
 int launch_one(kf_ctx* ctx, const GemvParams& p0) {
-    constexpr int MX = M1 ? 1 : 8 * NT, MP = 8 * NT, ROWS = 128 * RT;
+    constexpr int MX = NT == 1 ? MXS : 8 * NT, MP = 8 * NT, ROWS = 128 * RT;
+    constexpr bool M1 = MX == 1;
     GemvParams p     = p0;
     size_t head      = (size_t)p.nsteps_max * step_bytes(MODE, MX, ROWS);
     size_t tilebytes = (size_t)MP * (ROWS + 4) * 4;
@@ -676,7 +680,7 @@ int launch_one(kf_ctx* ctx, const GemvParams& p0) {
         }
     }
     KF_REQUIRE(ctx, smem <= kSmemCap, "internal: k-slice does not fit shared memory");
-    auto kern            = kf_gemv_kernel<FMT, MODE, NT, M1, RT>;
+    auto kern            = kf_gemv_kernel<FMT, MODE, NT, MXS, RT>;
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
         KF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
@@ -702,11 +706,13 @@ int launch_one(kf_ctx* ctx, const GemvParams& p0) {
 
 template <int FMT, int MODE>
 int launch_nt(kf_ctx* ctx, const GemvParams& p, int rt) {
-    if (p.M == 1) return rt == 2 ? launch_one<FMT, MODE, 1, true, 2>(ctx, p) : launch_one<FMT, MODE, 1, true, 1>(ctx, p);
-    if (p.M <= 8) return rt == 2 ? launch_one<FMT, MODE, 1, false, 2>(ctx, p) : launch_one<FMT, MODE, 1, false, 1>(ctx, p);
-    if (p.M <= 16) return launch_one<FMT, MODE, 2, false, 1>(ctx, p);
-    if (p.M <= 32) return launch_one<FMT, MODE, 4, false, 1>(ctx, p);
-    return launch_one<FMT, MODE, 8, false, 1>(ctx, p);
+    if (p.M == 1) return rt == 2 ? launch_one<FMT, MODE, 1, 1, 2>(ctx, p) : launch_one<FMT, MODE, 1, 1, 1>(ctx, p);
+    if (p.M == 2 && rt != 2) return launch_one<FMT, MODE, 1, 2, 1>(ctx, p);
+    if (p.M <= 4 && rt != 2) return launch_one<FMT, MODE, 1, 4, 1>(ctx, p);
+    if (p.M <= 8) return rt == 2 ? launch_one<FMT, MODE, 1, 8, 2>(ctx, p) : launch_one<FMT, MODE, 1, 8, 1>(ctx, p);
+    if (p.M <= 16) return launch_one<FMT, MODE, 2, 8, 1>(ctx, p);
+    if (p.M <= 32) return launch_one<FMT, MODE, 4, 8, 1>(ctx, p);
+    return launch_one<FMT, MODE, 8, 8, 1>(ctx, p);
 }
 
 int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
@@ -766,7 +772,7 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     p.total_rb = rb;
 
     // ---- k-split: pick the S that minimises  waves(S) x (fixed CTA cost + k-steps per CTA)  under the shared-memory budget -------
-    const int MXs      = M == 1 ? 1 : (M <= 8 ? 8 : M <= 16 ? 16 : M <= 32 ? 32 : 64);
+    const int MXs      = M == 1 ? 1 : M == 2 ? 2 : M <= 4 ? 4 : (M <= 8 ? 8 : M <= 16 ? 16 : M <= 32 ? 32 : 64);
     const size_t stepb = step_bytes(mode, MXs, rows_cta), ringb = ring_bytes(fmt, rt);
     const int hard_steps = (int)std::max<size_t>(1, (kSmemCap - 256 - ringb) / stepb);
     const int soft_steps = ringb + 4 * stepb <= kSmemSoft ? (int)((kSmemSoft - ringb) / stepb) : 0;
@@ -795,7 +801,7 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     p.S          = S;
     p.nsteps_max = (p.steps_total + S - 1) / S;  // floor/ceil slicing never exceeds ceil(steps/S)
     if (S > 1 && !p.cluster) {
-        int rc = kf_ensure_gemv_ws(ctx, (size_t)S * rb * (M == 1 ? 8 : MXs) * rows_cta * sizeof(float), rb);
+        int rc = kf_ensure_gemv_ws(ctx, (size_t)S * rb * std::max(8, MXs) * rows_cta * sizeof(float), rb);
         if (rc) return rc;
         p.ws = ctx->gemv_ws, p.cnt = ctx->gemv_cnt;
     }
