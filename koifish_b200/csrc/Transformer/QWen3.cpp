@@ -107,7 +107,10 @@ int SelfAttention::cuInfer(void* inpL, int M) {
     int gqa_min_ctx = 1024;
     kf_ctx_get_int(f->ctx, "gqa_min_ctx", &gqa_min_ctx);
     const bool long_ctx = M == 1 && f->attn_hint + 1 > gqa_min_ctx;  // one sequence, long context: stream each cached row once per kv head
-    if (((f->seq_mode && M >= f->gqa_min_batch) || long_ctx) && n_head / n_head_kv <= 16) {
+    // several sequences: the fused per-head kernel stays resident in one wave up to 64 (token, head) pairs; beyond that the kv-group
+    // kernel wins (measured: Qwen3-32B from 2 sequences, Qwen3-8B from 3)
+    const bool many = f->seq_mode && (f->gqa_min_batch > 0 ? M >= f->gqa_min_batch : n_head * M > 64);
+    if ((many || long_ctx) && n_head / n_head_kv <= 16) {
         // many sequences: QK-norm + RoPE + append, then the kv-group attention on the tensor cores (each cached row read once per kv head)
         KF_TRY(rope.cuInfer(this, M));
         KF_TRY(kf_attn_decode_gqa(f->ctx, f->att, f->q, f->cache.Get(KVCache::KV_KEY, lay), f->cache.Get(KVCache::KV_VAL, lay), f->d_pos, M, n_head,

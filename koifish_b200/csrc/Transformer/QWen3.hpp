@@ -125,7 +125,7 @@ struct Fish {
     int32_t* h_stage  = nullptr;  // pinned staging: tokens | pos | next
     uint16_t* h_logits = nullptr; // pinned
     int seq_mode = 0;             // 0: the M tokens of a forward are one sequence (prefill) ; 1: M independent sequences
-    int gqa_min_batch = 4;        // batched decode from this many sequences uses kf_attn_decode_gqa (env KF_GQA_MIN_BATCH for sweeps)
+    int gqa_min_batch = 0;        // > 0: batched decode from this many sequences uses kf_attn_decode_gqa (env KF_GQA_MIN_BATCH, sweeps); 0: rule in cuInfer
     int logit_rows = 0;           // rows of the logits buffers (max(64, max_batch)); bigger panels report the last token only
     bool panel_consecutive = false;  // prefill panel at positions pos[0] .. pos[0] + M - 1 -> tensor-core flash attention
     bool last_only = false;       // mode 2: logits / argmax of the last token of the panel only
