@@ -535,9 +535,15 @@ __device__ __forceinline__ void cp16(uint32_t dst, const void* src, bool valid) 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 constexpr int kPfQ = 64, kPfKV = 64;
+#ifndef KF_PF_BKV
+#define KF_PF_BKV 64
+#endif
+#ifndef KF_PF_MINB
+#define KF_PF_MINB 2
+#endif
 
-template <int HD>
-__global__ void __launch_bounds__(128) kf_attn_prefill_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ q,
+template <int HD, int BKV>
+__global__ void __launch_bounds__(128, KF_PF_MINB) kf_attn_prefill_kernel(uint16_t* __restrict__ out, const uint16_t* __restrict__ q,
                                                               const uint16_t* __restrict__ kc, const uint16_t* __restrict__ vc,
                                                               const int32_t* __restrict__ pos_dev, int M, int n_head, int n_kv, int max_seq,
                                                               float sqrt_hd) {
@@ -545,14 +551,14 @@ __global__ void __launch_bounds__(128) kf_attn_prefill_kernel(uint16_t* __restri
     extern __shared__ __align__(16) uint8_t pf_smem[];
     const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(pf_smem);
     const uint32_t sK = sQ + kPfQ * HD * 2;            // two K tiles
-    const uint32_t sV = sK + 2 * kPfKV * HD * 2;       // two V tiles
+    const uint32_t sV = sK + 2 * BKV * HD * 2;       // two V tiles
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;  // heavy (late) query tiles first
     const int h = blockIdx.y, kvh = h / (n_head / n_kv), kv_dim = n_kv * HD, q_dim = n_head * HD;
     const int pos0 = pos_dev[0];
     const int q0 = qt * kPfQ;
     const int kv_len = pos0 + min(M, q0 + kPfQ);  // rows visible to the last query row of this tile
-    const int ntiles = (kv_len + kPfKV - 1) / kPfKV;
+    const int ntiles = (kv_len + BKV - 1) / BKV;
     auto sw = [](int row, int c) { return (uint32_t)((row * CH + (c ^ (row & 7))) * 16); };
 
     // ---- Q tile + first K / V tile ----
@@ -562,11 +568,11 @@ __global__ void __launch_bounds__(128) kf_attn_prefill_kernel(uint16_t* __restri
         cp16(sQ + sw(r, c), q + (size_t)(ok ? q0 + r : 0) * q_dim + (size_t)h * HD + c * 8, ok);
     }
     auto load_kv = [&](int kt, int buf) {
-        for (int i = tid; i < kPfKV * CH; i += 128) {
+        for (int i = tid; i < BKV * CH; i += 128) {
             const int r = i / CH, c = i % CH;
-            const int t = min(kt * kPfKV + r, max_seq - 1);  // rows past kv_len are masked below; keep the address inside the cache
-            cp16(sK + buf * (kPfKV * HD * 2) + sw(r, c), kc + (size_t)t * kv_dim + (size_t)kvh * HD + c * 8, true);
-            cp16(sV + buf * (kPfKV * HD * 2) + sw(r, c), vc + (size_t)t * kv_dim + (size_t)kvh * HD + c * 8, true);
+            const int t = min(kt * BKV + r, max_seq - 1);  // rows past kv_len are masked below; keep the address inside the cache
+            cp16(sK + buf * (BKV * HD * 2) + sw(r, c), kc + (size_t)t * kv_dim + (size_t)kvh * HD + c * 8, true);
+            cp16(sV + buf * (BKV * HD * 2) + sw(r, c), vc + (size_t)t * kv_dim + (size_t)kvh * HD + c * 8, true);
         }
     };
     load_kv(0, 0);
@@ -590,15 +596,15 @@ __global__ void __launch_bounds__(128) kf_attn_prefill_kernel(uint16_t* __restri
 #pragma unroll
             for (int kc_ = 0; kc_ < HD / 16; kc_++) ldsm_x4(qa[kc_], sQ + sw(warp * 16 + (lane & 15), kc_ * 2 + (lane >> 4)));
         }
-        const uint32_t kb = sK + buf * (kPfKV * HD * 2), vb = sV + buf * (kPfKV * HD * 2);
+        const uint32_t kb = sK + buf * (BKV * HD * 2), vb = sV + buf * (BKV * HD * 2);
         // ---- S = Q K^T (16 x 64 per warp) ----
-        float sc[kPfKV / 8][4];
+        float sc[BKV / 8][4];
 #pragma unroll
-        for (int j = 0; j < kPfKV / 8; j++) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+        for (int j = 0; j < BKV / 8; j++) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
 #pragma unroll
         for (int kc_ = 0; kc_ < HD / 16; kc_++) {
 #pragma unroll
-            for (int jp = 0; jp < kPfKV / 16; jp++) {
+            for (int jp = 0; jp < BKV / 16; jp++) {
                 uint32_t b[4];
                 ldsm_x4(b, kb + sw(jp * 16 + (lane & 7) + (lane >> 4) * 8, kc_ * 2 + ((lane >> 3) & 1)));
                 mma_bf16(sc[2 * jp], qa[kc_], b[0], b[1]);
@@ -607,14 +613,14 @@ __global__ void __launch_bounds__(128) kf_attn_prefill_kernel(uint16_t* __restri
         }
         // ---- scale, causal mask, online softmax (rows g and g + 8 of the warp's 16) ----
         float mx_lo = -INFINITY, mx_hi = -INFINITY;
-        const bool diag = (kt + 1) * kPfKV > pos0 + q0;  // only tiles that reach the panel can contain masked columns
+        const bool diag = (kt + 1) * BKV > pos0 + q0;  // only tiles that reach the panel can contain masked columns
 #pragma unroll
-        for (int j = 0; j < kPfKV / 8; j++) {
+        for (int j = 0; j < BKV / 8; j++) {
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 float v = sc[j][e];  // raw q.k; 1/sqrt(hd) is folded into the exponent below (the max is scale invariant)
                 if (diag) {
-                    const int tcol = kt * kPfKV + j * 8 + 2 * t4 + (e & 1);
+                    const int tcol = kt * BKV + j * 8 + 2 * t4 + (e & 1);
                     if (tcol > ((e & 2) ? p_hi : p_lo)) v = -INFINITY;
                 }
                 sc[j][e] = v;
@@ -629,9 +635,9 @@ __global__ void __launch_bounds__(128) kf_attn_prefill_kernel(uint16_t* __restri
         const float c_lo = exp2f((m_lo - base_lo) * SC), c_hi = exp2f((m_hi - base_hi) * SC);
         m_lo = mn_lo, m_hi = mn_hi;
         float rs_lo = 0.f, rs_hi = 0.f;
-        uint32_t pa[kPfKV / 16][4];
+        uint32_t pa[BKV / 16][4];
 #pragma unroll
-        for (int j = 0; j < kPfKV / 8; j++) {
+        for (int j = 0; j < BKV / 8; j++) {
             const float p0 = exp2f((sc[j][0] - base_lo) * SC), p1 = exp2f((sc[j][1] - base_lo) * SC);
             const float p2 = exp2f((sc[j][2] - base_hi) * SC), p3 = exp2f((sc[j][3] - base_hi) * SC);
             rs_lo += p0 + p1, rs_hi += p2 + p3;
@@ -643,7 +649,7 @@ __global__ void __launch_bounds__(128) kf_attn_prefill_kernel(uint16_t* __restri
         for (int j = 0; j < HD / 8; j++) o[j][0] *= c_lo, o[j][1] *= c_lo, o[j][2] *= c_hi, o[j][3] *= c_hi;
         // ---- O += P V ----
 #pragma unroll
-        for (int kc_ = 0; kc_ < kPfKV / 16; kc_++) {
+        for (int kc_ = 0; kc_ < BKV / 16; kc_++) {
 #pragma unroll
             for (int jp = 0; jp < HD / 16; jp++) {
                 uint32_t b[4];
@@ -958,24 +964,24 @@ extern "C" int kf_attn_prefill(kf_ctx* ctx, void* out, const void* q, const void
                                int n_kv, int hd, int max_seq) {
     if (!ctx || !out || !q || !kc || !vc || !pos_dev) return KF_ERR_BAD_ARG;
     KF_REQUIRE(ctx, (hd == 128 || hd == 64) && n_head % n_kv == 0 && M >= 1 && max_seq >= 1, "head_dim 64/128, GQA");
-    const size_t smem = (size_t)(kPfQ + 4 * kPfKV) * hd * 2;
+    const size_t smem = (size_t)(kPfQ + 4 * KF_PF_BKV) * hd * 2;
     dim3 grid((M + kPfQ - 1) / kPfQ, n_head);
     const float sq = sqrtf((float)hd);
     if (hd == 128) {
         static bool set = false;
         if (!set) {
-            KF_CUDA(ctx, cudaFuncSetAttribute(kf_attn_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            KF_CUDA(ctx, cudaFuncSetAttribute(kf_attn_prefill_kernel<128, KF_PF_BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             set = true;
         }
-        kf_attn_prefill_kernel<128><<<grid, 128, smem, ctx->stream>>>((uint16_t*)out, (const uint16_t*)q, (const uint16_t*)kc, (const uint16_t*)vc,
+        kf_attn_prefill_kernel<128, KF_PF_BKV><<<grid, 128, smem, ctx->stream>>>((uint16_t*)out, (const uint16_t*)q, (const uint16_t*)kc, (const uint16_t*)vc,
                                                                       pos_dev, M, n_head, n_kv, max_seq, sq);
     } else {
         static bool set = false;
         if (!set) {
-            KF_CUDA(ctx, cudaFuncSetAttribute(kf_attn_prefill_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            KF_CUDA(ctx, cudaFuncSetAttribute(kf_attn_prefill_kernel<64, KF_PF_BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             set = true;
         }
-        kf_attn_prefill_kernel<64><<<grid, 128, smem, ctx->stream>>>((uint16_t*)out, (const uint16_t*)q, (const uint16_t*)kc, (const uint16_t*)vc,
+        kf_attn_prefill_kernel<64, KF_PF_BKV><<<grid, 128, smem, ctx->stream>>>((uint16_t*)out, (const uint16_t*)q, (const uint16_t*)kc, (const uint16_t*)vc,
                                                                      pos_dev, M, n_head, n_kv, max_seq, sq);
     }
     KF_LAUNCH_CHECK(ctx);
