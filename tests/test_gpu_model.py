@@ -282,3 +282,23 @@ def test_long_context_decode_switches_to_kv_group_attention(ctx):
     for la, lb in zip(a, b):
         err, g, w = logits_close(la, lb)
         assert err <= 1e-2 and int(np.argmax(g)) == int(np.argmax(w))
+
+
+def test_qwen3_32b_dims_one_layer(ctx):
+    # BASELINE headline shapes (E 5120, FFN 25600, H64/KV8, hd 128, 4-bit blocks, untied bf16 head), ONE of the 64 layers and a
+    # 16 K-row vocabulary so that the CPU oracle stays in seconds: the full-size GEMV shapes, the 64-head cluster attention and the
+    # bf16 tensor-core head against the oracle, then a 24-token panel through the tcgen05 dequant-GEMM and the flash attention
+    model, oracle = build_pair(ctx, n_layer=1, n_embd=5120, n_ff=25600, n_head=64, n_kv_head=8, head_dim=128, vocab=16384, max_seq=64,
+                               tie=False, norm_sigma=0.0)
+    toks = prompt(4, 16384)
+    for pos, tok in enumerate(toks):
+        lg, _ = model.forward([tok], [pos])
+        want = oracle.forward(tok, pos)
+        err, g, w = logits_close(lg[0], want)
+        assert err <= LOGIT_RTOL, (pos, err)
+    panel = prompt(28, 16384)[4:]
+    lg, _ = model.forward(panel, list(range(4, 28)), seq_mode=0)
+    for i, tok in enumerate(panel):
+        want = oracle.forward(tok, 4 + i)
+    err, g, w = logits_close(lg[-1], want)
+    assert err <= LOGIT_RTOL, err
