@@ -646,3 +646,31 @@ def test_gemm_tc_multi_weight_launch_equals_single_launches(ctx, kind, M):
         assert np.array_equal(a.numpy(np.uint16), b.numpy(np.uint16))
     g = single[1].numpy(np.uint16)
     assert np.array_equal(sw_f, ol.swiglu(g, g)) or (sw_f == ol.swiglu(g, g)).mean() > 0.999
+
+
+@pytest.mark.parametrize("kind", WEIGHT_KINDS, ids=str)
+@pytest.mark.parametrize("M,N,K", [(20, 48, 128), (9, 16, 256), (70, 16, 128), (33, 272, 384)])
+def test_gemm_tc_edge_shapes(ctx, kind, M, N, K):
+    # fewer rows than one 128-row tile, the shortest K the formats allow (one raw stage or less for the 1- / 2-bit formats), odd token counts
+    t, wdq = make_weight(ctx, kind, N, K, 9000 + M)
+    x = rand_bf16(np.random.default_rng(M + K), (M, K))
+    ctx.set_int("tc_min_m", 1)
+    try:
+        y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16)
+    finally:
+        ctx.set_int("tc_min_m", -1)
+    _check_linear(y, wdq, x, M, N, K)
+
+
+def test_attn_prefill_at_the_end_of_the_cache(ctx):
+    # the last KV tile reaches past max_seq: rows are clamped for the load and masked for the math
+    hd, n_head, n_kv, max_seq, pos0, M = 128, 8, 2, 100, 60, 40
+    rng = np.random.default_rng(5)
+    q = rand_bf16(rng, (M, n_head * hd))
+    kc, vc = rand_bf16(rng, (max_seq, n_kv * hd)), rand_bf16(rng, (max_seq, n_kv * hd))
+    pos = np.arange(pos0, pos0 + M, dtype=np.int32)
+    qd, kcd, vcd, posd = ctx.array(q), ctx.array(kc), ctx.array(vc), ctx.array(pos)
+    want = kf.attn_decode(ctx, qd, kcd, vcd, posd, M, n_head, n_kv, hd, max_seq, max_seq - 1).numpy(np.uint16)
+    got = kf.attn_prefill(ctx, qd, kcd, vcd, posd, M, n_head, n_kv, hd, max_seq).numpy(np.uint16)
+    g, w = ol.bf16_to_f32(got), ol.bf16_to_f32(want)
+    assert np.allclose(g, w, rtol=2.0 ** -6, atol=6e-3), np.abs(g - w).max()
