@@ -40,7 +40,13 @@ constexpr int BK = 64;     // k per stage: 64 bf16 = one 128-byte swizzle row of
 #ifndef KF_TC_RAWB
 #define KF_TC_RAWB 128
 #endif
-constexpr int RAWB = KF_TC_RAWB;  // packed bytes per weight row per raw stage (64: SWIZZLE_64B, 128: SWIZZLE_128B)
+#ifndef KF_TC_RAWB_LOWBIT
+#define KF_TC_RAWB_LOWBIT 64
+#endif
+// packed bytes per weight row per raw stage (64: SWIZZLE_64B, 128: SWIZZLE_128B).  A K split ends on a raw-stage boundary, and 128 bytes
+// are 512 / 1024 weights of the 2- / 1-bit formats: too coarse to balance 148 SMs (1-bit 25600x5120 at 32 tokens: 71 us, 38 us with 64)
+template <int FMT>
+__host__ __device__ constexpr int raw_bytes() { return (FMT == 3 || FMT == 4) ? KF_TC_RAWB_LOWBIT : KF_TC_RAWB; }  // TF_Q2, TF_Q1
 constexpr int kProducerWarps = 8, kMmaWarp = 8, kRawWarp = 9, kXWarp = 10, kEpiWarp0 = 11;
 constexpr int kThreadsTC = 15 * 32;
 
@@ -64,6 +70,7 @@ template <int FMT>
 struct Fmt {
     static constexpr int BITS  = FMT == TF_BF16 ? 16 : FMT == TF_F8 ? 8 : FMT == TF_Q4 ? 4 : FMT == TF_Q2 ? 2 : 1;
     static constexpr int SLOTB = 4 * BITS;                             // packed bytes of one 32-weight slot
+    static constexpr int RAWB  = raw_bytes<FMT>();
     static constexpr int KBR   = FMT == TF_BF16 ? 2 : RAWB / (2 * SLOTB);  // k-blocks per raw stage (bf16: granularity of a K split)
 };
 
@@ -339,6 +346,7 @@ struct Rings {
     static constexpr int SA      = !A_TMEM ? 0 : (BN <= 64 ? 12 : 8) / U;
     static constexpr int SB      = (A_TMEM ? (BN == 16 ? 32 : BN == 32 ? 16 : BN == 64 ? 10 : BN == 128 ? 6 : 4)
                                            : (BN == 16 ? 10 : BN == 32 ? 10 : BN == 64 ? 8 : BN == 128 ? 6 : 4)) / U;
+    static constexpr int RAWB    = raw_bytes<FMT>();
     static constexpr int RS      = !A_TMEM ? 0 : (BN <= 64 ? 128 : BN == 128 ? 112 : 80) * 1024 / (BM * RAWB);
     static constexpr size_t SMEM = (size_t)SB * STAGE + (size_t)RS * BM * RAWB + 1024;
     static_assert(SMEM <= 216 * 1024, "shared memory budget");
@@ -409,6 +417,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
     constexpr int STAGE      = C::STAGE;
     constexpr int SUB        = C::SUB;
     constexpr int U          = C::U;     // k-blocks per stage of the A and B rings
+    constexpr int RAWB       = F::RAWB;
     constexpr int RAW_BYTES  = BM * RAWB;
     constexpr int A_COL0     = NACC * BN;  // TMEM: accumulators first, then the A ring
     constexpr int TMEM_NEED  = A_COL0 + SA * U * 32;
@@ -824,8 +833,8 @@ int launch_tc(kf_ctx* ctx, GemmParams& p, const void* const* wdata, int nw, cons
     for (int i = 0; i < kMaxW && !rc; i++) {
         const int j = i < nw ? i : 0;  // unused slots repeat the first weight (never dereferenced)
         if (A_TMEM)
-            rc = make_map_2d(ctx, &tm_w[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, wdata[j], (uint64_t)p.K * F::BITS / 8, (uint64_t)p.Nw[j], RAWB, BM,
-                             RAWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+            rc = make_map_2d(ctx, &tm_w[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, wdata[j], (uint64_t)p.K * F::BITS / 8, (uint64_t)p.Nw[j], F::RAWB, BM,
+                             F::RAWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
         else
             rc = make_map_2d(ctx, &tm_w[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wdata[j], (uint64_t)p.K, (uint64_t)p.Nw[j], BK, BM,
                              CU_TENSOR_MAP_SWIZZLE_128B);
