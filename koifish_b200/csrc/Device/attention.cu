@@ -999,7 +999,7 @@ extern "C" int kf_attn_decode_gqa(kf_ctx* ctx, void* out, const void* q, const v
     int nsplit    = ctx->attn_split;
     if (nsplit <= 0) {
         nsplit = (3 * ctx->sm_count + n_kv * M - 1) / (n_kv * M);
-        nsplit = std::max(1, std::min(std::min(nsplit, 32), len / (2 * kPfKV)));
+        nsplit = std::max(1, std::min(std::min(nsplit, 24), len / (2 * kPfKV)));  // measured at ctx 4096 / 8192: 12-24 slices equal, 32+ slower
     }
     float* ws = nullptr;
     if (nsplit > 1) {
