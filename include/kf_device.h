@@ -78,7 +78,9 @@ const char* kf_status_string(int status);
 const char* kf_last_error(kf_ctx* ctx);
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t kf_launch_count(kf_ctx* ctx);
-/* tuning knobs for sweeps: "gemv_splitk" (0 = heuristic), "gemv_variant", "gemv_exact", "attn_split", "pdl",
+/* tuning knobs for sweeps: "gemv_splitk" (0 = heuristic), "gemv_variant", "gemv_exact" (0: factored dequant, NOT reference-exact),
+ * "gemv_cluster" (single-token split-K merged inside a thread-block cluster), "attn_split", "attn_warps", "pdl" (programmatic
+ * dependent launch), "debug_skip" (timing experiments only: bit 0 skips attention launches, bit 1 the skinny GEMVs -- results are garbage),
  * "gqa_min_ctx" (single-sequence decode: context length beyond which the kv-group tensor-core attention replaces the fused per-head
  * kernel; default 1024), "tc_min_m" (token count from which kf_linear* use the tcgen05 GEMM: -1 = measured per-type crossover, 0 = never, n = from n) */
 int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value);
