@@ -126,6 +126,10 @@ extern "C" int kf_ctx_get_int(kf_ctx* ctx, const char* key, int* value_out) {
         *value_out = ctx->pdl;
     else if (!strcmp(key, "attn_split"))
         *value_out = ctx->attn_split;
+    else if (!strcmp(key, "deq_fma"))
+        *value_out = ctx->deq_fma;
+    else if (!strcmp(key, "gemv_exact"))
+        *value_out = ctx->gemv_exact;
     else
         return KF_ERR_BAD_ARG;
     return KF_OK;
@@ -141,6 +145,8 @@ extern "C" int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value) {
         ctx->gemv_cluster = value;
     else if (!strcmp(key, "gemv_exact"))
         ctx->gemv_exact = value;
+    else if (!strcmp(key, "deq_fma"))
+        ctx->deq_fma = value ? 1 : 0;
     else if (!strcmp(key, "pdl"))
         ctx->pdl = value;
     else if (!strcmp(key, "tc_min_m"))

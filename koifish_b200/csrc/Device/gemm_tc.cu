@@ -33,7 +33,7 @@
 namespace {
 
 enum { TF_BF16 = 0, TF_F8 = 1, TF_Q4 = 2, TF_Q2 = 3, TF_Q1 = 4 };
-enum { TM_PLAIN = 0, TM_AFFINE = 1, TM_AFFINE_SYM = 2, TM_SCALE = 3 };
+enum { TM_PLAIN = 0, TM_AFFINE = 1, TM_AFFINE_SYM = 2, TM_SCALE = 3, TM_AFFINE_FMA = 4 };  // _FMA: one bf16 rounding (ctx deq_fma, default), see kf_common.cuh
 
 constexpr int BM = 128;    // weight rows per item (UMMA M)
 constexpr int BK = 64;     // k per stage: 64 bf16 = one 128-byte swizzle row of the B tile
@@ -276,6 +276,10 @@ template <int MODE>
 __device__ __forceinline__ uint32_t tdeq(uint32_t reg, int shift, uint32_t step2, uint32_t zero2, uint32_t nb2, uint32_t bias2, uint32_t mask,
                                          uint32_t magic) {
     const uint32_t v = and_or3(reg >> shift, mask, magic);
+    if (MODE == TM_AFFINE_FMA) {  // zero2 holds -zero: RN(step * k - zero), ONE rounding (fma.rn.bf16, as the reference built for sm_90+)
+        __nv_bfloat162 k = __hsub2_rn(u32_as_bf162(v), u32_as_bf162(bias2));
+        return bf162_as_u32(__hfma2(k, u32_as_bf162(step2), u32_as_bf162(zero2)));
+    }
     if (MODE == TM_AFFINE) {
         __nv_bfloat162 p = __hfma2(u32_as_bf162(v), u32_as_bf162(step2), u32_as_bf162(nb2));
         return bf162_as_u32(__hsub2_rn(p, u32_as_bf162(zero2)));
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
                     const int g1 = min(gcur + 1, gpr - 1), g2 = min(gcur + 2, gpr - 1);
                     zq1 = __ldg(zrow + g1), sq1 = __ldg(srow + g1);
                     zq2 = __ldg(zrow + g2), sq2 = __ldg(srow + g2);
-                    step2 = __byte_perm(sq0, 0u, 0x1010), zero2 = __byte_perm(zq0, 0u, 0x1010);
+                    step2 = __byte_perm(sq0, 0u, 0x1010), zero2 = __byte_perm(zq0, 0u, 0x1010) ^ (MODE == TM_AFFINE_FMA ? 0x80008000u : 0u);
                     if (MODE == TM_AFFINE) nb2 = bf162_as_u32(__hmul2_rn(u32_as_bf162(step2), u32_as_bf162(0xC300C300u)));
                 }
                 const int r1 = (w.kb1 + KBR - 1) / KBR;
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
 #if !(KF_TC_EXP & 4)
                                 zq2 = __ldg(zrow + g2), sq2 = __ldg(srow + g2);
 #endif
-                                step2 = __byte_perm(sq0, 0u, 0x1010), zero2 = __byte_perm(zq0, 0u, 0x1010);
+                                step2 = __byte_perm(sq0, 0u, 0x1010), zero2 = __byte_perm(zq0, 0u, 0x1010) ^ (MODE == TM_AFFINE_FMA ? 0x80008000u : 0u);
                                 if (MODE == TM_AFFINE) nb2 = bf162_as_u32(__hmul2_rn(u32_as_bf162(step2), u32_as_bf162(0xC300C300u)));
                             }
                         }
@@ -855,12 +859,12 @@ int launch_tc_bn(kf_ctx* ctx, GemmParams& p, const void* const* wdata, int nw, c
     return launch_tc<FMT, MODE, 16>(ctx, p, wdata, nw, xp);
 }
 
-int tc_format(const kf_tensor_desc* w, int* fmt, int* mode) {
+int tc_format(const kf_tensor_desc* w, int* fmt, int* mode, int deq_fma) {
     switch (w->type) {
         case KF_T_BF16: *fmt = TF_BF16, *mode = TM_PLAIN; return KF_OK;
         case KF_T_F8E5M2: *fmt = TF_F8, *mode = TM_PLAIN; return KF_OK;
-        case KF_T_Q4: *fmt = TF_Q4, *mode = w->qbias == 0 ? TM_AFFINE : TM_AFFINE_SYM; return KF_OK;
-        case KF_T_Q2: *fmt = TF_Q2, *mode = w->qbias == 0 ? TM_AFFINE : TM_AFFINE_SYM; return KF_OK;
+        case KF_T_Q4: *fmt = TF_Q4, *mode = deq_fma ? TM_AFFINE_FMA : w->qbias == 0 ? TM_AFFINE : TM_AFFINE_SYM; return KF_OK;
+        case KF_T_Q2: *fmt = TF_Q2, *mode = deq_fma ? TM_AFFINE_FMA : w->qbias == 0 ? TM_AFFINE : TM_AFFINE_SYM; return KF_OK;
         case KF_T_SIGN: *fmt = TF_Q2, *mode = TM_SCALE; return KF_OK;
         case KF_T_BINARY: *fmt = TF_Q1, *mode = TM_SCALE; return KF_OK;
     }
@@ -873,7 +877,7 @@ int tc_format(const kf_tensor_desc* w, int* fmt, int* mode) {
 // inside every 32-wide slot for the packed types.  Returns x itself or the context's scratch holding the permuted copy.
 int kf_tc_prepare_x(kf_ctx* ctx, const kf_tensor_desc* w, const void* x, int M, const void** xp_out) {
     int fmt, mode;
-    if (tc_format(w, &fmt, &mode)) return KF_ERR_UNSUPPORTED;
+    if (tc_format(w, &fmt, &mode, 1)) return KF_ERR_UNSUPPORTED;
     if (fmt == TF_BF16 || fmt == TF_F8) {
         *xp_out = x;
         return KF_OK;
@@ -897,7 +901,7 @@ int kf_tc_prepare_x(kf_ctx* ctx, const kf_tensor_desc* w, const void* x, int M, 
 // RMSNorm + kf_tc_prepare_x in one launch (packed types); bf16 / f8 weights get the plain RMSNorm into the context's xnorm scratch
 int kf_tc_prepare_x_norm(kf_ctx* ctx, const kf_tensor_desc* w, const void* x, const void* norm_w, float eps, int M, const void** xp_out) {
     int fmt, mode;
-    if (tc_format(w, &fmt, &mode)) return KF_ERR_UNSUPPORTED;
+    if (tc_format(w, &fmt, &mode, 1)) return KF_ERR_UNSUPPORTED;
     const int K = w->cols;
     KF_REQUIRE(ctx, K % 32 == 0, "K");
     if (fmt == TF_BF16 || fmt == TF_F8) {
@@ -921,7 +925,7 @@ int kf_tc_prepare_x_norm(kf_ctx* ctx, const kf_tensor_desc* w, const void* x, co
 // 0 when both weights want the same activation order (one prepared copy serves both)
 int kf_tc_same_order(const kf_tensor_desc* a, const kf_tensor_desc* b) {
     int fa, fb, ma, mb;
-    if (tc_format(a, &fa, &ma) || tc_format(b, &fb, &mb)) return 1;
+    if (tc_format(a, &fa, &ma, 1) || tc_format(b, &fb, &mb, 1)) return 1;
     const bool pa = !(fa == TF_BF16 || fa == TF_F8), pb = !(fb == TF_BF16 || fb == TF_F8);
     if (!pa && !pb) return 0;
     return fa == fb ? 0 : 1;
@@ -933,7 +937,7 @@ int kf_gemm_tc_multi(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w
     KF_REQUIRE(ctx, n >= 1 && n <= kMaxW && y && w && xp && M >= 1, "args");
     const int K = w[0].cols;
     int fmt, mode;
-    if (tc_format(&w[0], &fmt, &mode)) return KF_ERR_UNSUPPORTED;
+    if (tc_format(&w[0], &fmt, &mode, ctx->deq_fma)) return KF_ERR_UNSUPPORTED;
     GemmParams p;
     memset(&p, 0, sizeof(p));
     const void* wdata[kMaxW] = {};
@@ -942,7 +946,7 @@ int kf_gemm_tc_multi(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w
     p.lop_mask = fmt == TF_Q4 ? 0x000F000Fu : fmt == TF_Q2 ? 0x00030003u : 0x00010001u, p.lop_magic = 0x43004300u;
     for (int i = 0; i < n; i++) {
         int f2, m2;
-        KF_REQUIRE(ctx, y[i] && !tc_format(&w[i], &f2, &m2) && f2 == fmt && m2 == mode && w[i].cols == K && w[i].group == w[0].group &&
+        KF_REQUIRE(ctx, y[i] && !tc_format(&w[i], &f2, &m2, ctx->deq_fma) && f2 == fmt && m2 == mode && w[i].cols == K && w[i].group == w[0].group &&
                             w[i].qbias == w[0].qbias,
                    "weights of one launch must share type, K, group");
         KF_REQUIRE(ctx, K % 128 == 0 && w[i].rows % 16 == 0, "K must be a multiple of 128, rows of 16");
@@ -961,6 +965,8 @@ int kf_gemm_tc_multi(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w
     if (epilogue == 1) KF_REQUIRE(ctx, residual && n == 1, "residual: single weight");
 #define KF_TC_CASE(F, MD) \
     if (fmt == F && mode == MD) return launch_tc_bn<F, MD>(ctx, p, wdata, n, xp);
+    KF_TC_CASE(TF_Q4, TM_AFFINE_FMA)
+    KF_TC_CASE(TF_Q2, TM_AFFINE_FMA)
     KF_TC_CASE(TF_Q4, TM_AFFINE)
     KF_TC_CASE(TF_Q4, TM_AFFINE_SYM)
     KF_TC_CASE(TF_Q2, TM_AFFINE)

@@ -30,7 +30,9 @@
 namespace {
 
 enum { FMT_BF16 = 0, FMT_F8 = 1, FMT_Q4 = 2, FMT_Q2 = 3, FMT_Q1 = 4 };
-enum { MODE_PLAIN = 0, MODE_AFFINE = 1, MODE_AFFINE_SYM = 2, MODE_SCALE = 3, MODE_FACTOR = 4 };
+enum { MODE_PLAIN = 0, MODE_AFFINE = 1, MODE_AFFINE_SYM = 2, MODE_SCALE = 3, MODE_FACTOR = 4, MODE_AFFINE_FMA = 5 };
+// MODE_AFFINE / MODE_AFFINE_SYM: the reference's dequant with TWO bf16 roundings (ctx knob deq_fma = 0) ; MODE_AFFINE_FMA: with ONE
+// (fma.rn.bf16, the default: what the reference's kernel computes when built for sm_90+, see kf_common.cuh deq_fma)
 // MODE_FACTOR (opt-in, ctx knob gemv_exact = 0): A = 128 + code, un-dequantised; per group y += step*(acc_g - (128+qbias)*Sx) - zero*Sx with
 // Sx = sum of the group's activations.  Mathematically the same affine map, but WITHOUT the reference's two bf16 roundings of the
 // weights (result differs from the exact modes by about one bf16 ulp of y); it exists to measure what the roundings cost.
@@ -147,6 +149,9 @@ __device__ __forceinline__ uint32_t deq_pair(uint32_t reg, int shift, uint32_t s
         // qbias == 0:  RN(step*(v-128)) == fma(v, step, -128*step) (single rounding of the exact product step*c) ; then RN(p - zero)
         __nv_bfloat162 p = __hfma2(u32_as_bf162(v), u32_as_bf162(step2), u32_as_bf162(nbias2));
         return bf162_as_u32(__hsub2_rn(p, u32_as_bf162(zero2)));
+    } else if (MODE == MODE_AFFINE_FMA) {
+        __nv_bfloat162 k = __hsub2_rn(u32_as_bf162(v), u32_as_bf162(bias2));  // exact small integer
+        return bf162_as_u32(__hfma2(k, u32_as_bf162(step2), u32_as_bf162(zero2)));  // zero2 holds -zero: RN(step*k - zero), one rounding
     } else if (MODE == MODE_AFFINE_SYM) {
         __nv_bfloat162 k = __hsub2_rn(u32_as_bf162(v), u32_as_bf162(bias2));  // exact small integer
         __nv_bfloat162 p = __hmul2_rn(u32_as_bf162(step2), k);
@@ -471,6 +476,7 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
                     gm[rt][0] = __byte_perm(ga, 0u, 0x3232), gm[rt][1] = __byte_perm(ga, 0u, 0x1010);
                     gm[rt][3] = __byte_perm(gb, 0u, 0x3232), gm[rt][4] = __byte_perm(gb, 0u, 0x1010);
                     gm[rt][2] = gm[rt][5] = 0u;
+                    if (MODE == MODE_AFFINE_FMA) gm[rt][1] ^= 0x80008000u, gm[rt][4] ^= 0x80008000u;  // -zero
                     if (MODE == MODE_AFFINE) {
                         gm[rt][2] = bf162_as_u32(__hmul2_rn(u32_as_bf162(gm[rt][0]), u32_as_bf162(0xC300C300u)));  // -128*step, exact
                         gm[rt][5] = bf162_as_u32(__hmul2_rn(u32_as_bf162(gm[rt][3]), u32_as_bf162(0xC300C300u)));
@@ -723,8 +729,8 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     switch (type) {
         case KF_T_BF16: fmt = FMT_BF16, mode = MODE_PLAIN; break;
         case KF_T_F8E5M2: fmt = FMT_F8, mode = MODE_PLAIN; break;
-        case KF_T_Q4: fmt = FMT_Q4, mode = !ctx->gemv_exact ? MODE_FACTOR : w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
-        case KF_T_Q2: fmt = FMT_Q2, mode = !ctx->gemv_exact ? MODE_FACTOR : w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
+        case KF_T_Q4: fmt = FMT_Q4, mode = !ctx->gemv_exact ? MODE_FACTOR : ctx->deq_fma ? MODE_AFFINE_FMA : w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
+        case KF_T_Q2: fmt = FMT_Q2, mode = !ctx->gemv_exact ? MODE_FACTOR : ctx->deq_fma ? MODE_AFFINE_FMA : w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
         case KF_T_SIGN: fmt = FMT_Q2, mode = MODE_SCALE; break;
         case KF_T_BINARY: fmt = FMT_Q1, mode = MODE_SCALE; break;
         default: return KF_ERR_UNSUPPORTED;
@@ -807,6 +813,8 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     }
 #define KF_GEMV_CASE(F, MD) \
     if (fmt == F && mode == MD) return launch_nt<F, MD>(ctx, p, rt);
+    KF_GEMV_CASE(FMT_Q4, MODE_AFFINE_FMA)
+    KF_GEMV_CASE(FMT_Q2, MODE_AFFINE_FMA)
     KF_GEMV_CASE(FMT_Q4, MODE_AFFINE)
     KF_GEMV_CASE(FMT_Q4, MODE_AFFINE_SYM)
     KF_GEMV_CASE(FMT_Q4, MODE_FACTOR)

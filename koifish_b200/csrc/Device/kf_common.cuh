@@ -39,6 +39,11 @@ struct kf_ctx {
     int gemv_variant = 0;
     int gemv_cluster = 1;  // M = 1 split-K: 1 = merge the k-slices of a row block inside a thread-block cluster (DSMEM) when S <= 8; 2 = also cap S at 8; 0 = global workspace
     int gemv_exact   = 1;  // 1: in-kernel dequant reproduces the reference's bf16 roundings bit for bit ; 0: factored scale/zero (MODE_FACTOR)
+    // rounding of the reference's dequant expression (step * k - zero) in bf16 (CU_Q128toX_, T.cu:274), pinned against the reference kernel
+    // compiled both ways (oracle/ref_kernels.cu): 1 = ONE rounding, fma.rn.bf16 -- what nvcc's default -fmad=true (implied by the
+    // reference's -use_fast_math) generates on sm_90+, i.e. what the reference computes on a B200 ; 0 = TWO roundings (bf16 multiply, then
+    // bf16 subtract): -fmad=false and every pre-sm_90 build
+    int deq_fma      = 1;
     int attn_split   = 0;
     int gqa_min_ctx  = 1024;  // single-sequence decode: contexts beyond this use the kv-group tensor-core attention (Transformer layer reads it)
     int attn_warps   = 0;  // warps per CTA of the cluster attention (0 = default)
@@ -161,6 +166,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 __device__ __forceinline__ __nv_bfloat162 u32_as_bf162(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
+// the reference's dequant of one code: (step * (bf16)k - zero) with bf16 operators (CU_Q128toX_, src/Device/CUDA/T.cu:274).  FMA = true:
+// contracted to one fma.rn.bf16 (the reference built with nvcc defaults / -use_fast_math for sm_90+) ; false: multiply and subtract each
+// round (-fmad=false, pre-sm_90).  The _rn intrinsics are never re-contracted by ptxas.
+template <bool FMA>
+__device__ __forceinline__ uint16_t kf_deq_scalar(int k, uint16_t step, uint16_t zero) {
+    const __nv_bfloat16 kk = __int2bfloat16_rn(k), s = __ushort_as_bfloat16(step), z = __ushort_as_bfloat16(zero);
+    if (FMA) return __bfloat16_as_ushort(__hfma(s, kk, __hneg(z)));
+    return __bfloat16_as_ushort(__hsub_rn(__hmul_rn(s, kk), z));
+}
 __device__ __forceinline__ uint32_t bf162_as_u32(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
 // streaming 128-bit load: weights are read exactly once per token -> do not allocate in L1

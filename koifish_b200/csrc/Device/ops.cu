@@ -188,7 +188,7 @@ extern "C" int kf_add(kf_ctx* ctx, void* out, const void* a, const void* b, size
 // dequantised on the fly when the table is stored in 8 bits or in packed 128-bit words.
 __global__ void __launch_bounds__(256) kf_embed_kernel(uint16_t* __restrict__ out, const uint8_t* __restrict__ data, const uint16_t* __restrict__ gZero,
                                                         const uint16_t* __restrict__ gStep, const int32_t* __restrict__ tokens, int rows, int cols,
-                                                        int type, int bits, int group, int qbias) {
+                                                        int type, int bits, int group, int qbias, int deq_fma) {
     const int m = blockIdx.y;
     int tok     = tokens[m];
     tok         = tok < 0 ? 0 : (tok >= rows ? rows - 1 : tok);
@@ -209,8 +209,7 @@ __global__ void __launch_bounds__(256) kf_embed_kernel(uint16_t* __restrict__ ou
         const int jj   = j < half ? j : j - half;
         const int code = (int)((src >> (64 - bits * (jj + 1))) & ((1u << bits) - 1));
         const size_t g = e / group;
-        const __nv_bfloat16 p = __hmul_rn(__ushort_as_bfloat16(gStep[g]), __int2bfloat16_rn(code - qbias));
-        r = __bfloat16_as_ushort(__hsub_rn(p, __ushort_as_bfloat16(gZero[g])));
+        r = deq_fma ? kf_deq_scalar<true>(code - qbias, gStep[g], gZero[g]) : kf_deq_scalar<false>(code - qbias, gStep[g], gZero[g]);
     }
     out[(size_t)m * cols + c] = r;
 }
@@ -226,7 +225,7 @@ extern "C" int kf_embed(kf_ctx* ctx, void* out, const kf_tensor_desc* w, const i
     }
     dim3 grid((w->cols + 255) / 256, M);
     kf_embed_kernel<<<grid, 256, 0, ctx->stream>>>((uint16_t*)out, (const uint8_t*)w->data_dev, gz, gs, tokens, w->rows, w->cols, w->type, bits,
-                                                   w->group, w->qbias);
+                                                   w->group, w->qbias, ctx->deq_fma);
     KF_LAUNCH_CHECK(ctx);
     return KF_OK;
 }

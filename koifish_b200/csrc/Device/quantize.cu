@@ -198,8 +198,8 @@ extern "C" int kf_quantize(kf_ctx* ctx, const void* w, int rows, int cols, int t
 }
 
 // ------------------------------------------------------------------------------------------------ dequant (GetDataX test hook)
-// One thread per 128-bit word.  Arithmetic exactly as CU_Q128toX_ (T.cu:274): bf16 multiply then bf16 subtract.
-template <int BITS>
+// One thread per 128-bit word.  Arithmetic exactly as CU_Q128toX_ (T.cu:274); FMA: see kf_deq_scalar (kf_common.cuh).
+template <int BITS, bool FMA>
 __global__ void __launch_bounds__(256) kf_dequant_kernel(const uint4* __restrict__ words, size_t nWords, int group, int qBias,
                                                           const uint16_t* __restrict__ gZero, const uint16_t* __restrict__ gStep,
                                                           uint16_t* __restrict__ out) {
@@ -211,15 +211,13 @@ __global__ void __launch_bounds__(256) kf_dequant_kernel(const uint4* __restrict
     const unsigned long long low = ((unsigned long long)q.y << 32) | q.x, high = ((unsigned long long)q.w << 32) | q.z;
     const size_t e0 = wi * PER;
     const size_t g  = e0 / group;
-    const __nv_bfloat16 zero = __ushort_as_bfloat16(gZero[g]), step = __ushort_as_bfloat16(gStep[g]);
+    const ushort2 zero_step = make_ushort2(gZero[g], gStep[g]);
 #pragma unroll 8
     for (int j = 0; j < PER; j++) {
         const unsigned long long src = j < HALF ? high : low;
         const int jj   = j < HALF ? j : j - HALF;
         const int code = (int)((src >> (64 - BITS * (jj + 1))) & ((1u << BITS) - 1));
-        __nv_bfloat16 k = __int2bfloat16_rn(code - qBias);
-        __nv_bfloat16 p = __hmul_rn(step, k);  // _rn: never contracted with the subtraction (two roundings, as on the reference build)
-        out[e0 + j]     = __bfloat16_as_ushort(__hsub_rn(p, zero));
+        out[e0 + j]    = kf_deq_scalar<FMA>(code - qBias, zero_step.y, zero_step.x);
     }
 }
 __global__ void __launch_bounds__(256) kf_f8e5m2_decode_kernel(const uint8_t* __restrict__ in, size_t n, uint16_t* __restrict__ out) {
@@ -247,12 +245,18 @@ extern "C" int kf_dequant(kf_ctx* ctx, const kf_tensor_desc* w, void* out) {
     const size_t nWords = n / per;
     unsigned blocks     = (unsigned)((nWords + 255) / 256);
     const uint16_t *gz = kf_gama_zero(*w), *gs = kf_gama_step(*w);
+#define KF_DEQ_LAUNCH(B)                                                                                                                      \
+    (ctx->deq_fma ? kf_dequant_kernel<B, true><<<blocks, 256, 0, ctx->stream>>>((const uint4*)w->data_dev, nWords, w->group, w->qbias, gz, gs,  \
+                                                                                (uint16_t*)out)                                                 \
+                  : kf_dequant_kernel<B, false><<<blocks, 256, 0, ctx->stream>>>((const uint4*)w->data_dev, nWords, w->group, w->qbias, gz, gs, \
+                                                                                 (uint16_t*)out))
     if (bits == 4)
-        kf_dequant_kernel<4><<<blocks, 256, 0, ctx->stream>>>((const uint4*)w->data_dev, nWords, w->group, w->qbias, gz, gs, (uint16_t*)out);
+        KF_DEQ_LAUNCH(4);
     else if (bits == 2)
-        kf_dequant_kernel<2><<<blocks, 256, 0, ctx->stream>>>((const uint4*)w->data_dev, nWords, w->group, w->qbias, gz, gs, (uint16_t*)out);
+        KF_DEQ_LAUNCH(2);
     else
-        kf_dequant_kernel<1><<<blocks, 256, 0, ctx->stream>>>((const uint4*)w->data_dev, nWords, w->group, w->qbias, gz, gs, (uint16_t*)out);
+        KF_DEQ_LAUNCH(1);
+#undef KF_DEQ_LAUNCH
     KF_LAUNCH_CHECK(ctx);
     return KF_OK;
 }

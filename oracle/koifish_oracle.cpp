@@ -230,8 +230,21 @@ extern "C" int kfo_quantize(const uint16_t* w, int rows, int cols, int bits, int
 
 /* ------------------------------------------------------------------------------------------------
  * Dequant: CU_Q128toX_, src/Device/CUDA/T.cu:245-294.  g0 = (step * (floatGama)(q - qBias) - zero) * sR with bf16
- * operators and sR = 1: p = RN_bf16(step*k) ; w = RN_bf16(p - zero).
+ * operators and sR = 1.  How many roundings that expression has depends on how the reference is BUILT, and it is pinned against
+ * the reference's own kernel compiled both ways (oracle/ref_kernels.cu, tests/test_gpu_refkernels.py):
+ *   fused (default)  nvcc's default -fmad=true (implied by the reference's -use_fast_math, CMakeLists.txt:141) contracts the bf16
+ *                    multiply and subtract into ONE fma.rn.bf16 on sm_90+ (SASS: HFMA2.BF16 step, k, -zero):  w = RN_bf16(step*k - zero);
+ *   two roundings    -fmad=false, and every pre-sm_90 build (there the bf16 operators go through fp32 with a rounding after each
+ *                    operator):  p = RN_bf16(step*k) ; w = RN_bf16(p - zero).
  * ---------------------------------------------------------------------------------------------- */
+static int g_dequant_fma = 1;
+extern "C" void kfo_set_dequant_fma(int fused) { g_dequant_fma = fused ? 1 : 0; }
+extern "C" int kfo_get_dequant_fma(void) { return g_dequant_fma; }
+/* RN_bf16(a*b - c) with a single rounding: the product of two bf16 numbers is exact in double, and so is the difference unless the
+ * exponents are > 2^29 apart (never for quantiser scales) */
+extern "C" uint16_t kfo_bf16_fms(uint16_t a, uint16_t b, uint16_t c) {
+    return f64_to_bf16((double)kfo_bf16_to_f32(a) * (double)kfo_bf16_to_f32(b) - (double)kfo_bf16_to_f32(c));
+}
 extern "C" int kfo_dequant(const uint8_t* data, const uint16_t* gama, int rows, int cols, int bits, int group, int qbias, uint16_t* out) {
     if (bits != 4 && bits != 2 && bits != 1)
         return -1;
@@ -250,8 +263,8 @@ extern "C" int kfo_dequant(const uint8_t* data, const uint16_t* gama, int rows, 
             unpack_word(data + ((size_t)g * group * bits / 8) + 16 * i, bits, qq);
             for (int pos = 0; pos < per128; pos++) {
                 uint16_t kq = kfo_f32_to_bf16((float)(qq[pos] - qbias)); /* small integers are exact in bf16 */
-                uint16_t p  = kfo_bf16_mul(step, kq);
-                out[(size_t)g * group + i * per128 + pos] = kfo_bf16_sub(p, zero);
+                out[(size_t)g * group + i * per128 + pos] =
+                    g_dequant_fma ? kfo_bf16_fms(step, kq, zero) : kfo_bf16_sub(kfo_bf16_mul(step, kq), zero);
             }
         }
     }

@@ -13,6 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "libkoifish_oracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_ref.so")
+# the reference's own CUDA kernels (src/Device/CUDA/T.cu + headers) compiled for sm_100a: with the reference's nvcc flags ("fma": the bf16
+# multiply-subtract of the dequant is contracted to one fma.rn.bf16), and with -fmad=false / no fast-math ("nofma": two roundings, IEEE division)
+REFGPU_SO = {"fma": os.path.join(ORACLE_DIR, "_ref", "libkoifish_refgpu.so"), "nofma": os.path.join(ORACLE_DIR, "_ref", "libkoifish_refgpu_nofma.so")}
 
 RTN_ASYM, RTN_SYM, YYANG = 0, 1, 2
 
@@ -23,6 +26,11 @@ def build_oracle(force=False):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "libkoifish_oracle.so"], stdout=subprocess.DEVNULL)
     if os.path.exists("/root/reference/src/PackedQ.hpp") and (force or not os.path.exists(REF_SO)):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
+    if os.path.exists("/root/reference/src/Device/CUDA/T.cu"):
+        src = os.path.join(ORACLE_DIR, "ref_kernels.cu")
+        stale = any(not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src) for so in REFGPU_SO.values())
+        if force or stale:
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "refgpu"], stdout=subprocess.DEVNULL)
 
 
 class ModelConfig(C.Structure):
@@ -52,6 +60,7 @@ _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 
 _lib = None
 _ref = None
+_refgpu = {}
 
 
 def lib():
@@ -99,8 +108,38 @@ def lib():
         L.kfo_tensor_seed.restype = C.c_uint64
         L.kfo_tensor_seed.argtypes = [C.c_uint64, C.c_int]
         L.kfo_num_threads.restype = C.c_int
+        L.kfo_set_dequant_fma.argtypes = [C.c_int]
+        L.kfo_get_dequant_fma.restype = C.c_int
+        L.kfo_bf16_fms.restype = C.c_uint16
+        L.kfo_bf16_fms.argtypes = [C.c_uint16, C.c_uint16, C.c_uint16]
         _lib = L
     return _lib
+
+
+def set_dequant_fma(fused):
+    """1 (default): one bf16 rounding in the dequant, as the reference built for sm_90+; 0: two roundings (see koifish_oracle.h)."""
+    lib().kfo_set_dequant_fma(int(fused))
+
+
+def refgpu(variant="fma"):
+    """The reference's own CUDA kernels (oracle/ref_kernels.cu); needs a GPU to call.  None when the library was never built."""
+    if variant not in _refgpu:
+        build_oracle()
+        so = REFGPU_SO[variant]
+        if not os.path.exists(so):
+            return None
+        R = C.CDLL(so)
+        vp, i = C.c_void_p, C.c_int
+        R.refk_q128tox.argtypes = [i, i, i, i, vp, vp, vp, vp]
+        R.refk_xtoq128.argtypes = [i, i, i, i, i, i, i, i, vp, vp, vp, vp]
+        R.refk_rmsnorm.argtypes = [vp, vp, vp, i, i]
+        R.refk_rmsnorm_multihead.argtypes = [vp, vp, i, i, i]
+        R.refk_rope2.argtypes = [vp, vp, i, i, i, i, C.c_float]
+        R.refk_attention.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i]
+        R.refk_f8_decode.argtypes = [vp, vp, C.c_size_t]
+        R.refk_f8_encode.argtypes = [vp, vp, C.c_size_t]
+        _refgpu[variant] = R
+    return _refgpu[variant]
 
 
 def ref():

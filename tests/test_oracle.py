@@ -174,8 +174,11 @@ def test_quantize_invariants(bits, mode):
         assert (np.abs(dq - wf) <= bound + 1e-9).all()
 
 
-def test_dequant_values_are_two_roundings():
-    # T.cu:274 : w = RN(RN(step*k) - zero), checked against an independent float64 evaluation
+@pytest.mark.parametrize("fused", [1, 0])
+def test_dequant_rounding_modes(fused):
+    # T.cu:274 (step * (bf16)k - zero) in bf16: fused = 1 -> ONE rounding, w = RN(step*k - zero) (the reference's kernel as nvcc builds it
+    # for sm_90+, fma.rn.bf16; pinned on the GPU by tests/test_gpu_refkernels.py); fused = 0 -> TWO, w = RN(RN(step*k) - zero)
+    # (-fmad=false / pre-sm_90 builds).  Checked against an independent float64 evaluation.
     rows, cols, G, bits = 8, 256, 128, 4
     w = ol.fill_normal(rows * cols, seed=11, sigma=0.02)
     data, gama = ol.quantize(w, rows, cols, bits, G, ol.RTN_ASYM)
@@ -183,12 +186,19 @@ def test_dequant_values_are_two_roundings():
     codes = ol.unpack_codes(data, rows * cols, bits).reshape(nG, G)
     zero = ol.bf16_to_f32(gama[rows + cols: rows + cols + nG]).astype(np.float64)
     step = ol.bf16_to_f32(gama[rows + cols + nG:]).astype(np.float64)
-    dq = ol.dequant(data, gama, rows, cols, bits, G, 0).reshape(nG, G)
+    ol.set_dequant_fma(fused)
+    try:
+        dq = ol.dequant(data, gama, rows, cols, bits, G, 0).reshape(nG, G)
+    finally:
+        ol.set_dequant_fma(1)
     for g in range(nG):
         for i in range(G):
-            p = _rn_bf16_from_f64(float(step[g]) * int(codes[g, i]))
-            pf = float(ol.bf16_to_f32(np.array([p], dtype=np.uint16))[0])
-            assert dq[g, i] == _rn_bf16_from_f64(pf - float(zero[g]))
+            if fused:
+                assert dq[g, i] == _rn_bf16_from_f64(float(step[g]) * int(codes[g, i]) - float(zero[g]))
+            else:
+                p = _rn_bf16_from_f64(float(step[g]) * int(codes[g, i]))
+                pf = float(ol.bf16_to_f32(np.array([p], dtype=np.uint16))[0])
+                assert dq[g, i] == _rn_bf16_from_f64(pf - float(zero[g]))
 
 
 def test_ternary_and_binary_levels():
