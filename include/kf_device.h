@@ -78,9 +78,15 @@ const char* kf_status_string(int status);
 const char* kf_last_error(kf_ctx* ctx);
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t kf_launch_count(kf_ctx* ctx);
+/* bumped whenever the context re-allocates one of its scratch buffers (split-K / attention workspaces, tensor-core staging): a CUDA graph
+ * captured before the change still points at the freed buffer and must be re-captured.  The model runtime (kf_model.h) checks this before
+ * every replay; callers that capture their own graphs with kf_graph_begin / kf_graph_end must do the same. */
+uint64_t kf_scratch_generation(kf_ctx* ctx);
 /* tuning knobs for sweeps: "gemv_splitk" (0 = heuristic), "gemv_variant", "gemv_exact" (0: factored dequant, NOT reference-exact),
  * "gemv_cluster" (single-token split-K merged inside a thread-block cluster), "attn_split", "attn_warps", "pdl" (programmatic
- * dependent launch), "debug_skip" (timing experiments only: bit 0 skips attention launches, bit 1 the skinny GEMVs -- results are garbage),
+ * dependent launch), "deq_fma" (1, default: the dequant expression step*k - zero rounds ONCE in bf16, as the reference's kernel does when built
+ * for sm_90+; 0: twice, as its -fmad=false / pre-sm_90 builds), "gemv_tma" (1, default: decode GEMVs of 4-bit weights take the persistent
+ * TMA-fed stream-K kernel; 0: the round-1 cp.async kernel), "gemv_tma_occ" (CTAs per SM, 1 or 2), "gemv_tma_smem_kb" (shared-memory budget),
  * "gqa_min_ctx" (single-sequence decode: context length beyond which the kv-group tensor-core attention replaces the fused per-head
  * kernel; default 1024), "tc_min_m" (token count from which kf_linear* use the tcgen05 GEMM: -1 = measured per-type crossover, 0 = never, n = from n) */
 int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value);

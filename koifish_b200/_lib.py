@@ -48,6 +48,7 @@ SIGNATURES = {
     "kf_status_string": (C.c_char_p, [_I]),
     "kf_last_error": (C.c_char_p, [_P]),
     "kf_launch_count": (_U64, [_P]),
+    "kf_scratch_generation": (_U64, [_P]),
     "kf_ctx_get_int": (_I, [_P, C.c_char_p, _P]),
     "kf_ctx_set_int": (_I, [_P, C.c_char_p, _I]),
     "kf_malloc": (_I, [_P, _SZ, C.POINTER(_P)]),

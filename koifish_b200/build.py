@@ -14,8 +14,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libkoifish_b200.so")
+TAG = os.environ.get("KF_BUILD_TAG", "")  # tuning builds: KF_BUILD_TAG=dbg KF_NVCC_DEFS=-DKF_DEBUG_KNOBS -> libkoifish_b200_dbg.so (load with KF_LIB_PATH)
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libkoifish_b200%s.so" % ("_" + TAG if TAG else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 NVCC_FLAGS = [

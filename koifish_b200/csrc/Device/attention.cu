@@ -867,7 +867,9 @@ extern "C" int kf_qkv_attention(kf_ctx* ctx, void* out, const void* q, const voi
     if (!ctx || !out || !q || !k || !v || !kc || !vc || !table || !pos_dev) return KF_ERR_BAD_ARG;
     KF_REQUIRE(ctx, (hd == 128 || hd == 64) && n_head % n_kv == 0 && M >= 1 && max_seq >= 1, "head_dim 64/128, GQA");
     KF_REQUIRE(ctx, M == 1 || seq_stride > 0, "the fused path needs one sequence per token (use kf_qknorm_rope_kvappend + kf_attn_decode for panels)");
+#ifdef KF_DEBUG_KNOBS
     if (ctx->debug_skip & 1) return KF_OK;
+#endif
     int nsplit = ctx->attn_split;
     const int len_hint = std::max(1, std::min(max_seq, max_pos_hint + 1));
     // contexts up to 2K tokens: every cached row of a warp's first pass is in flight before the dependency wait and the slices of a

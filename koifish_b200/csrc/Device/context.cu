@@ -84,6 +84,7 @@ extern "C" int kf_ctx_destroy(kf_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     kf_p2p_destroy(ctx);
+    kf_gemv_tma_destroy(ctx);
     if (ctx->nccl) {
         auto f = (fn_ncclCommDestroy)nccl_sym("ncclCommDestroy");
         if (f)
@@ -116,6 +117,7 @@ extern "C" void* kf_ctx_stream(kf_ctx* ctx) { return ctx ? (void*)ctx->stream : 
 extern "C" int kf_ctx_sm_count(kf_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 extern "C" const char* kf_last_error(kf_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 extern "C" uint64_t kf_launch_count(kf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t kf_scratch_generation(kf_ctx* ctx) { return ctx ? ctx->scratch_gen : 0; }
 extern "C" int kf_ctx_get_int(kf_ctx* ctx, const char* key, int* value_out) {
     if (!ctx || !key || !value_out) return KF_ERR_BAD_ARG;
     if (!strcmp(key, "gqa_min_ctx"))
@@ -157,8 +159,16 @@ extern "C" int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value) {
         ctx->gqa_min_ctx = value;
     else if (!strcmp(key, "attn_warps"))
         ctx->attn_warps = value;
+    else if (!strcmp(key, "gemv_tma"))
+        ctx->gemv_tma_on = value ? 1 : 0;
+    else if (!strcmp(key, "gemv_tma_occ"))
+        ctx->gemv_tma_occ = value;
+    else if (!strcmp(key, "gemv_tma_smem_kb"))
+        ctx->gemv_tma_smem_kb = value;
+#ifdef KF_DEBUG_KNOBS
     else if (!strcmp(key, "debug_skip"))
         ctx->debug_skip = value;
+#endif
     else
         return KF_ERR_BAD_ARG;
     return KF_OK;
@@ -174,6 +184,7 @@ int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters) {
         size_t want = bytes + bytes / 4;
         KF_CUDA(ctx, cudaMalloc(&ctx->gemv_ws, want));
         ctx->gemv_ws_bytes = want;
+        ctx->scratch_gen++;
     }
     if (counters > ctx->gemv_cnt_n) {
         KF_REQUIRE(ctx, !ctx->capturing, "split-K counters must be sized before graph capture");
@@ -185,6 +196,7 @@ int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters) {
         KF_CUDA(ctx, cudaMalloc(&ctx->gemv_cnt, sizeof(unsigned) * want));
         KF_CUDA(ctx, cudaMemsetAsync(ctx->gemv_cnt, 0, sizeof(unsigned) * want, ctx->stream));
         ctx->gemv_cnt_n = want;
+        ctx->scratch_gen++;
     }
     return KF_OK;
 }
@@ -197,6 +209,7 @@ int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes) {
         ctx->attn_ws = nullptr, ctx->attn_ws_bytes = 0;
         KF_CUDA(ctx, cudaMalloc(&ctx->attn_ws, bytes * 2));
         ctx->attn_ws_bytes = bytes * 2;
+        ctx->scratch_gen++;
     }
     return KF_OK;
 }
@@ -210,6 +223,7 @@ int kf_ensure_buf(kf_ctx* ctx, void** buf, size_t* cap, size_t bytes) {
         *buf = nullptr, *cap = 0;
         KF_CUDA(ctx, cudaMalloc(buf, bytes + bytes / 8 + 256));
         *cap = bytes + bytes / 8;
+        ctx->scratch_gen++;
     }
     return KF_OK;
 }
@@ -224,6 +238,7 @@ int kf_ensure_attn_cnt(kf_ctx* ctx, int counters) {
         KF_CUDA(ctx, cudaMalloc(&ctx->attn_cnt, sizeof(unsigned) * want));
         KF_CUDA(ctx, cudaMemsetAsync(ctx->attn_cnt, 0, sizeof(unsigned) * want, ctx->stream));
         ctx->attn_cnt_n = want;
+        ctx->scratch_gen++;
     }
     return KF_OK;
 }
@@ -284,14 +299,13 @@ extern "C" int kf_host_free(void* p) {
 }
 
 // ---------------------------------------------------------------- CUDA graphs
-static uint64_t g_capture_base = 0;
 extern "C" int kf_graph_begin(kf_ctx* ctx) {
     if (!ctx)
         return KF_ERR_BAD_ARG;
     KF_REQUIRE(ctx, !ctx->capturing, "already capturing");
     KF_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     ctx->capturing = true;
-    g_capture_base = ctx->launches;
+    ctx->capture_base = ctx->launches;
     return KF_OK;
 }
 extern "C" int kf_graph_end(kf_ctx* ctx, kf_graph** out) {
@@ -306,8 +320,8 @@ extern "C" int kf_graph_end(kf_ctx* ctx, kf_graph** out) {
         delete g;
         return KF_ERR_CUDA;
     }
-    g->launches   = ctx->launches - g_capture_base;
-    ctx->launches = g_capture_base;  // nothing ran during capture
+    g->launches   = ctx->launches - ctx->capture_base;
+    ctx->launches = ctx->capture_base;  // nothing ran during capture
     e = cudaGraphInstantiate(&g->exec, g->graph, 0);
     if (e != cudaSuccess) {
         ctx->last_error = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e);

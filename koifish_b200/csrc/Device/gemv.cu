@@ -833,6 +833,12 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
 
 int kf_gemv_small(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                   const void* norm_w, float norm_eps) {
+#ifdef KF_DEBUG_KNOBS
     if (ctx->debug_skip & 2) return KF_OK;
+#endif
+    if (M <= 8) {  // the persistent TMA-fed stream-K kernel covers the decode shapes (4-bit, group 128, K % 512 == 0)
+        const int rc = kf_gemv_tma(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
+        if (rc != 1) return rc;
+    }
     return gemv_dispatch(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
 }

@@ -47,7 +47,13 @@ struct kf_ctx {
     int attn_split   = 0;
     int gqa_min_ctx  = 1024;  // single-sequence decode: contexts beyond this use the kv-group tensor-core attention (Transformer layer reads it)
     int attn_warps   = 0;  // warps per CTA of the cluster attention (0 = default)
-    int debug_skip   = 0;  // timing experiments only (results are garbage): bit 0 skips the attention launch, bit 1 the skinny GEMV launches
+    int debug_skip   = 0;  // only honoured in builds with -DKF_DEBUG_KNOBS (timing experiments: bit 0 skips attention, bit 1 the skinny GEMVs)
+    // persistent TMA-fed stream-K GEMV (gemv_tma.cu): on / CTAs per SM / shared-memory budget per SM in KB
+    int gemv_tma_on = 1, gemv_tma_occ = 1, gemv_tma_smem_kb = 200;
+    void* gemv_tma  = nullptr;  // its state (tensor-map cache, stream-K workspace)
+    // bumped whenever a context scratch buffer is reallocated: CUDA graphs captured before hold stale pointers and must be re-captured
+    uint64_t scratch_gen = 0;
+    uint64_t capture_base = 0;  // launches counted when the current graph capture began
     // tensor parallel
     ncclComm* nccl = nullptr;
     int rank = 0, world = 1;
@@ -111,6 +117,10 @@ static inline const uint16_t* kf_gama_step(const kf_tensor_desc& w) {
 static inline bool kf_has_gama(const kf_tensor_desc& w) { return w.gama_dev || (w.zero_dev && w.step_dev); }
 
 void kf_p2p_destroy(kf_ctx* ctx);
+void kf_gemv_tma_destroy(kf_ctx* ctx);
+// gemv_tma.cu: KF_OK = launched, 1 = request not covered by this kernel (caller falls back to gemv.cu), < 0 = error
+int kf_gemv_tma(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
+                const void* norm_w, float norm_eps);
 int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters);
 int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes);
 int kf_qknorm_rope_kv_warp(kf_ctx* ctx, void* q, const void* k, const void* v, const void* qw, const void* kw, void* kcache, void* vcache,

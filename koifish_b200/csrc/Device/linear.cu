@@ -3,9 +3,14 @@
 // dequant-GEMV (gemv.cu); larger M to the tcgen05 / TMEM dequant-GEMM (gemm_tc.cu).
 #include "kf_common.cuh"
 
+// same storage type, K, group and bias: the weights can share one launch
+static bool tc_fusable(const kf_tensor_desc* a, const kf_tensor_desc* b) {
+    return a->type == b->type && a->cols == b->cols && a->group == b->group && a->qbias == b->qbias;
+}
+
 // M > 64 through the skinny kernel in 64-token panels (used when the tensor-core path is switched off: ctx knob tc_min_m = 0)
-static int linear_panels(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
-                         const void* norm_w, float norm_eps) {
+static int linear_panels_same(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
+                              const void* norm_w, float norm_eps) {
     if (M <= 64) return kf_gemv_small(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
     const int K = w[0].cols;
     for (int m0 = 0; m0 < M; m0 += 64) {
@@ -18,6 +23,38 @@ static int linear_panels(kf_ctx* ctx, int n, void* const* y, const kf_tensor_des
         if (epilogue == 2) yy[1] = yy[0];
         const void* res = residual ? (const void*)((const uint16_t*)residual + (size_t)m0 * w[0].rows) : nullptr;
         int rc = kf_gemv_small(ctx, n, yy, w, (const uint16_t*)x + (size_t)m0 * K, mm, epilogue, res, norm_w, norm_eps);
+        if (rc) return rc;
+    }
+    return KF_OK;
+}
+// The quantizer card selects the storage type per tensor-name substring (QUANT_CARD::Init4Neuron, reference src/Tensor/GeQuant.cpp:
+// 1186-1285), so Q / K / V (or gate / up) of one block may differ in type, group or bias, e.g. {"q_proj": {"quant_method": "RTN", "bits": 4}}.
+// Weights that agree share one launch; the others get their own (the RMSNorm folded into each: same arithmetic, same result).
+static int linear_panels(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
+                         const void* norm_w, float norm_eps) {
+    bool same = true;
+    for (int i = 1; i < n; i++) same = same && tc_fusable(&w[0], &w[i]);
+    if (same) return linear_panels_same(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
+    if (epilogue == 2) {  // SwiGLU of a mixed gate / up pair: two matmuls into scratch, then CU_swiglu_v0 as a stand-alone op
+        const size_t bytes = (size_t)M * w[0].rows * 2;
+        int rc = kf_ensure_buf(ctx, &ctx->tmp0, &ctx->tmp0_bytes, bytes);
+        if (!rc) rc = kf_ensure_buf(ctx, &ctx->tmp1, &ctx->tmp1_bytes, bytes);
+        void* g1[1] = {ctx->tmp0};
+        void* u1[1] = {ctx->tmp1};
+        if (!rc) rc = linear_panels_same(ctx, 1, g1, &w[0], x, M, 0, nullptr, norm_w, norm_eps);
+        if (!rc) rc = linear_panels_same(ctx, 1, u1, &w[1], x, M, 0, nullptr, norm_w, norm_eps);
+        if (!rc) rc = kf_swiglu(ctx, y[0], ctx->tmp0, ctx->tmp1, (size_t)M * w[0].rows);
+        return rc;
+    }
+    bool done[3] = {false, false, false};
+    for (int i = 0; i < n; i++) {
+        if (done[i]) continue;
+        kf_tensor_desc gw[3];
+        void* gy[3];
+        int gn = 0;
+        for (int j = i; j < n; j++)
+            if (!done[j] && tc_fusable(&w[i], &w[j])) gw[gn] = w[j], gy[gn] = y[j], gn++, done[j] = true;
+        int rc = linear_panels_same(ctx, gn, gy, gw, x, M, epilogue, residual, norm_w, norm_eps);
         if (rc) return rc;
     }
     return KF_OK;
@@ -36,11 +73,6 @@ static bool use_tensor_cores(const kf_ctx* ctx, int n, const kf_tensor_desc* w, 
         if (M < need) return false;
     }
     return true;
-}
-
-// same storage type, K, group and bias: the weights can share one tensor-core launch
-static bool tc_fusable(const kf_tensor_desc* a, const kf_tensor_desc* b) {
-    return a->type == b->type && a->cols == b->cols && a->group == b->group && a->qbias == b->qbias;
 }
 
 // epilogue: 0 none, 1 residual, 2 swiglu(w[0] gate, w[1] up -> y[0]), 4 fp32

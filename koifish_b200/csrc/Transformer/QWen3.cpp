@@ -212,6 +212,16 @@ void Fish::ResetGraphs() {
         if (g.second) kf_graph_destroy(g.second);
     graphs.clear();
 }
+// A captured graph holds raw pointers into the context's scratch buffers (split-K / attention workspaces, tensor-core staging).  Those
+// buffers are re-allocated when a later eager call -- a bigger batch, a prefill panel, another model on the same context -- needs more
+// room; the context counts such events and every replay path checks the count first.
+void Fish::SyncGraphGeneration() {
+    const uint64_t gen = kf_scratch_generation(ctx);
+    if (gen != graph_gen) {
+        ResetGraphs();
+        graph_gen = gen;
+    }
+}
 int Fish::AllocTensor(const std::string& name, int rows, int cols, int id, hGTensor& out) {
     out = std::make_shared<GTensor>(ctx, name, rows, cols);
     // only 2-D weight matrices are quantised, norms never (isWMAT, GeQuant.cpp:155-156)
@@ -462,7 +472,9 @@ int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, ui
         }
         h_stage[m] = tokens[m], h_stage[max_tokens + m] = pos[m];
     }
+    SyncGraphGeneration();
     staged_pos_max = *std::max_element(pos, pos + M);
+    staged_M = M;
     seq_mode = mode == 1 ? 1 : 0;
     last_only = mode == 2;
     panel_consecutive = seq_mode == 0;
@@ -508,6 +520,7 @@ int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, ui
         KF_TRY(kf_h2d(ctx, d_pos, h_stage + max_tokens, 4));
         KF_TRY(kf_ctx_sync(ctx));
         staged_pos_max = pos[M - 1] + 1;
+        staged_M = 1;
     }
     return KF_OK;
 }
@@ -516,11 +529,23 @@ int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, ui
 // positions staged by the last Forward() call are the starting state.
 int Fish::DecodeLoop(int n_steps, int M) {
     std::string* hFishErr = &error;
-    if (M < 1 || M > max_tokens || n_steps < 0) return KF_ERR_BAD_ARG;
+    if (M < 1 || M > max_tokens || n_steps < 0) {
+        error = "DecodeLoop: 1 <= M <= " + std::to_string(max_tokens) + ", n_steps >= 0";
+        return KF_ERR_BAD_ARG;
+    }
+    if (staged_M < M) {  // the loop continues from what the last Forward() staged: there must be M (token, position) pairs on the device
+        error = "DecodeLoop: call Forward() with at least " + std::to_string(M) + " token(s) first (it stages the starting tokens / positions)";
+        return KF_ERR_BAD_ARG;
+    }
+    if (M > 1 && (M > config.max_batch || M > logit_rows)) {  // M independent sequences: each needs its own KV region and logits row
+        error = "DecodeLoop: batched decode needs gpt.max_batch >= M (and at most " + std::to_string(logit_rows) + " sequences)";
+        return KF_ERR_BAD_ARG;
+    }
     if (staged_pos_max + n_steps >= config.max_seq_len) {
         error = "DecodeLoop: would run past gpt.max_seq_len";
         return KF_ERR_BAD_ARG;
     }
+    SyncGraphGeneration();
     staged_pos_max += n_steps;
     seq_mode = M > 1 ? 1 : seq_mode, last_only = false, panel_consecutive = false;
     const int key = UseGraph(M, true) | (1 << 2);
@@ -537,6 +562,7 @@ int Fish::DecodeLoop(int n_steps, int M) {
         if (n_steps == 0) return KF_OK;
         KF_TRY(body());  // eager first step sizes every workspace
         done = 1;
+        SyncGraphGeneration();  // ... which may have re-allocated scratch that older graphs point to
         if (use_graphs) {
             KF_TRY(kf_graph_begin(ctx));
             int rc      = body();

@@ -136,6 +136,9 @@ struct Fish {
     bool use_graphs = true;
     void* rope_table_shared = nullptr;
     int staged_pos_max = 0;
+    int staged_M       = 0;      // tokens / positions staged on the device by the last Forward() (0: nothing staged yet)
+    uint64_t graph_gen = 0;      // kf_scratch_generation() the captured graphs were recorded under
+    void SyncGraphGeneration();  // drop the graphs when a context scratch buffer they point to has been re-allocated since
     std::string error;
     size_t weight_bytes = 0;
 
