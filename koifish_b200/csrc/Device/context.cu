@@ -165,6 +165,8 @@ extern "C" int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value) {
         ctx->gemv_tma_occ = value;
     else if (!strcmp(key, "gemv_tma_smem_kb"))
         ctx->gemv_tma_smem_kb = value;
+    else if (!strcmp(key, "gemv_tma_warps"))
+        ctx->gemv_tma_warps = value;
 #ifdef KF_DEBUG_KNOBS
     else if (!strcmp(key, "debug_skip"))
         ctx->debug_skip = value;

@@ -30,7 +30,14 @@
 namespace {
 
 enum { FMT_BF16 = 0, FMT_F8 = 1, FMT_Q4 = 2, FMT_Q2 = 3, FMT_Q1 = 4 };
-enum { MODE_PLAIN = 0, MODE_AFFINE = 1, MODE_AFFINE_SYM = 2, MODE_SCALE = 3, MODE_FACTOR = 4, MODE_AFFINE_FMA = 5 };
+enum { MODE_PLAIN = 0, MODE_AFFINE = 1, MODE_AFFINE_SYM = 2, MODE_SCALE = 3, MODE_FACTOR = 4, MODE_AFFINE_FMA = 5, MODE_FAST = 6 };
+// MODE_FAST (4-bit, the DEFAULT for decode: ctx knob gemv_exact = 0): the codes go to the tensor cores as fp16 numbers 1024 + c and
+// 1024 + 16 c, each built with ONE LOP3 (both nibbles of a byte sit inside fp16's 10 mantissa bits; one byte permute per 8 codes replaces
+// the six funnel shifts of the bf16 forms -- a funnel shift costs ~5 clk per warp instruction and scheduler on B200, tools/ubench/deq_rate2.cu:
+// 105-160 clk per [128 x 128] tile against 335 for MODE_FACTOR and 432 for the bit-exact forms, which is MORE than the tile's bytes take at
+// the HBM rate).  The group's step / zero / code bias are applied to the fp32 group sums, y += step * (sum c x - qbias Sx) - zero Sx:
+// the reference's affine dequant without its per-weight bf16 rounding.  Activations are staged as fp16 with a power-of-two scale per
+// 128-k group (exact for bf16 inputs within 2^27 of the group's largest magnitude).
 // MODE_AFFINE / MODE_AFFINE_SYM: the reference's dequant with TWO bf16 roundings (ctx knob deq_fma = 0) ; MODE_AFFINE_FMA: with ONE
 // (fma.rn.bf16, the default: what the reference's kernel computes when built for sm_90+, see kf_common.cuh deq_fma)
 // MODE_FACTOR (opt-in, ctx knob gemv_exact = 0): A = 128 + code, un-dequantised; per group y += step*(acc_g - (128+qbias)*Sx) - zero*Sx with
@@ -114,6 +121,20 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (a & IMM) | 0x64006400 (fp16x2 1024.0) in ONE LOP3 with the mask as an immediate
+template <uint32_t IMM>
+__device__ __forceinline__ uint32_t and_or_1024(uint32_t a, uint32_t magic) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "n"(IMM), "r"(magic));
+    return d;
+}
+
 // asynchronous global -> shared copy (LDGSTS): no register staging, so many k-steps can be in flight per thread
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
@@ -173,7 +194,13 @@ template <int FMT, int MODE, int NR>
 __device__ __forceinline__ void build_a(uint32_t (&a)[4], const uint32_t (&wa)[NR], const uint32_t (&wb)[NR], int u, int h, const uint32_t (&gm)[6],
                                         uint32_t bias2, uint32_t mask, uint32_t magic) {
     // gm = {step2a, zero2a, nb2a, step2b, zero2b, nb2b}
-    if constexpr (FMT == FMT_Q4) {
+    if constexpr (FMT == FMT_Q4 && MODE == MODE_FAST) {
+        // codes {7,3} / {5,1} of the 8 in this register: low nibbles of the bytes -> 1024 + c ; {6,2} / {4,0}: high nibbles -> 1024 + 16 c
+        uint32_t ra = wa[3 - u], rb = wb[3 - u];
+        if (h) ra = __byte_perm(ra, 0u, 0x4321), rb = __byte_perm(rb, 0u, 0x4321);  // >> 8 as a byte permute
+        a[0] = and_or_1024<0x000F000Fu>(ra, magic), a[1] = and_or_1024<0x000F000Fu>(rb, magic);
+        a[2] = and_or_1024<0x00F000F0u>(ra, magic), a[3] = and_or_1024<0x00F000F0u>(rb, magic);
+    } else if constexpr (FMT == FMT_Q4) {
         const uint32_t ra = wa[3 - u], rb = wb[3 - u];
         a[0] = deq_pair<MODE>(ra, 8 * h, gm[0], gm[1], gm[2], bias2, mask, magic);
         a[1] = deq_pair<MODE>(rb, 8 * h, gm[3], gm[4], gm[5], bias2, mask, magic);
@@ -392,6 +419,34 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
 #pragma unroll
                 for (int i = 0; i < KT / 2; i++) src[i] = 0u;
             }
+            if (MODE == MODE_FAST) {
+                // fp16 staging with a power-of-two scale per 128-k group (the quad's 4 x 32 values; the 4 lanes of a quad are always
+                // active together): the group's largest magnitude lands in [2^13, 2^14); the elements that meet the codes carrying a
+                // factor 16 (even elements of every 8: the fp16 number built from a byte's high nibble) are divided by 16.
+                // sxs[s][m] = {1024 Sxe + qbias Sx, Sx, 1 / scale}: Sx the group sum of the scaled activations, Sxe the sum as the MMA sees it
+                const unsigned qm = 0xFu << (lane & ~3);
+                uint32_t amax = 0;
+#pragma unroll
+                for (int i = 0; i < KT / 2; i++) amax = max(amax, max(src[i] & 0x7fffu, (src[i] >> 16) & 0x7fffu));
+                amax = max(amax, __shfl_xor_sync(qm, amax, 1));
+                amax = max(amax, __shfl_xor_sync(qm, amax, 2));
+                const int shift = amax == 0 ? 0 : max(-100, min(100, 140 - (int)(amax >> 7)));  // 140 = 127 + 13
+                const float scl = __uint_as_float((uint32_t)(127 + shift) << 23);
+                float sum = 0.f, sume = 0.f;
+#pragma unroll
+                for (int i = 0; i < KT / 2; i++) {
+                    const float a = bf16lo(src[i]) * scl, b = bf16hi(src[i]) * scl;
+                    const __half ha = __float2half_rn(a * 0.0625f), hb = __float2half_rn(b);
+                    sum += a, sum += b;
+                    sume += __half2float(ha), sume += __half2float(hb);
+                    src[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+                }
+                sum += __shfl_xor_sync(qm, sum, 1), sum += __shfl_xor_sync(qm, sum, 2);  // fixed order: bit-reproducible
+                sume += __shfl_xor_sync(qm, sume, 1), sume += __shfl_xor_sync(qm, sume, 2);
+                if (tt == 0)
+                    reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(smem) + p.sx_off)[s * MX + m] =
+                        make_float4(fmaf(1024.0f, sume, (float)p.qbias * sum), sum, __uint_as_float((uint32_t)(127 - shift) << 23), 0.f);
+            }
 #pragma unroll
             for (int u = 0; u < UNITS; u++) {
                 uint32_t o[4];
@@ -469,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
                     }
             uint32_t gm[RT][6];
             float fstep[RT][2];
-            if (MODE != MODE_PLAIN && MODE != MODE_FACTOR) {
+            if (MODE != MODE_PLAIN && MODE != MODE_FACTOR && MODE != MODE_FAST) {
 #pragma unroll
                 for (int rt = 0; rt < RT; rt++) {
                     const uint32_t ga = gbase[s * GS + rt * 16], gb = gbase[s * GS + rt * 16 + 8];
@@ -493,6 +548,20 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
 #pragma unroll
                         for (int j = 0; j < 4; j++) accg[rt][nt][j] = 0.f;
             }
+            float4 sv[NT][2];  // MODE_FAST: {1024 Sxe + qbias Sx, Sx, 1 / scale} of this k-step's group for the thread's two token columns
+            if (MODE == MODE_FAST) {
+                const float4* sx4 = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(smem) + p.sx_off) + s * MX;
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) {
+                    sv[nt][0] = sx4[MX >= 8 ? nt * 8 + 2 * t : ((2 * t) & (MX - 1))];
+                    sv[nt][1] = sx4[MX >= 8 ? nt * 8 + 2 * t + 1 : ((2 * t + 1) & (MX - 1))];
+#pragma unroll
+                    for (int rt = 0; rt < RT; rt++) {  // the group sums start at -(1024 Sxe + qbias Sx): the MMAs leave sum((c - qbias) x')
+                        accg[rt][nt][0] = accg[rt][nt][2] = -sv[nt][0].x;
+                        accg[rt][nt][1] = accg[rt][nt][3] = -sv[nt][1].x;
+                    }
+                }
+            }
 #pragma unroll
             for (int u = 0; u < UNITS; u++) {
                 uint4 xb[NT];
@@ -507,7 +576,9 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
 #pragma unroll
                         for (int nt = 0; nt < NT; nt++) {
                             const uint32_t b0 = h ? xb[nt].z : xb[nt].x, b1 = h ? xb[nt].w : xb[nt].y;
-                            if (MODE == MODE_SCALE || MODE == MODE_FACTOR)
+                            if (MODE == MODE_FAST)
+                                mma_f16_16816(accg[rt][nt], a, b0, b1);
+                            else if (MODE == MODE_SCALE || MODE == MODE_FACTOR)
                                 mma_bf16_16816(accg[rt][nt], a, b0, b1);
                             else
                                 mma_bf16_16816(acc[rt][nt], a, b0, b1);
@@ -525,6 +596,20 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
                         acc[rt][nt][2] = fmaf(fstep[rt][1], accg[rt][nt][2], acc[rt][nt][2]);
                         acc[rt][nt][3] = fmaf(fstep[rt][1], accg[rt][nt][3], acc[rt][nt][3]);
                     }
+            }
+            if (MODE == MODE_FAST) {  // y += 2^-shift * (step * sum((c - qbias) x') - zero * Sx')
+#pragma unroll
+                for (int rt = 0; rt < RT; rt++) {
+                    const uint32_t ga = gbase[s * GS + rt * 16], gb = gbase[s * GS + rt * 16 + 8];
+                    const float sa = bf16hi(ga), sb = bf16hi(gb), za = bf16lo(ga), zb = bf16lo(gb);
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) {
+                        acc[rt][nt][0] = fmaf(sv[nt][0].z, fmaf(sa, accg[rt][nt][0], -za * sv[nt][0].y), acc[rt][nt][0]);
+                        acc[rt][nt][1] = fmaf(sv[nt][1].z, fmaf(sa, accg[rt][nt][1], -za * sv[nt][1].y), acc[rt][nt][1]);
+                        acc[rt][nt][2] = fmaf(sv[nt][0].z, fmaf(sb, accg[rt][nt][2], -zb * sv[nt][0].y), acc[rt][nt][2]);
+                        acc[rt][nt][3] = fmaf(sv[nt][1].z, fmaf(sb, accg[rt][nt][3], -zb * sv[nt][1].y), acc[rt][nt][3]);
+                    }
+                }
             }
             if (MODE == MODE_FACTOR) {
                 const float off = (float)(128 + p.qbias);
@@ -661,7 +746,8 @@ static size_t ring_bytes(int fmt, int rt) {
 }
 // shared bytes per k-step: activations + gama
 static size_t step_bytes(int mode, int mx, int rows_cta) {
-    return (size_t)UNITS * mx * 64 + (mode == MODE_PLAIN ? 0 : (size_t)(rows_cta + 1) * 4) + (mode == MODE_FACTOR ? (size_t)mx * 4 : 0);
+    return (size_t)UNITS * mx * 64 + (mode == MODE_PLAIN ? 0 : (size_t)(rows_cta + 1) * 4) + (mode == MODE_FACTOR ? (size_t)mx * 4 : 0) +
+           (mode == MODE_FAST ? (size_t)mx * 16 : 0);
 }
 
 template <int FMT, int MODE, int NT, int MXS, int RT>
@@ -673,7 +759,7 @@ int launch_one(kf_ctx* ctx, const GemvParams& p0) {
     size_t tilebytes = (size_t)MP * (ROWS + 4) * 4;
     p.ring_off       = (int)((head + 15) & ~(size_t)15);
     p.sx_off         = (int)(p.ring_off + ring_bytes(FMT, RT));
-    size_t sxbytes   = MODE == MODE_FACTOR ? (size_t)p.nsteps_max * MX * 4 : 0;
+    size_t sxbytes   = MODE == MODE_FACTOR ? (size_t)p.nsteps_max * MX * 4 : MODE == MODE_FAST ? (size_t)p.nsteps_max * MX * 16 : 0;
     size_t smem      = std::max((size_t)p.sx_off + sxbytes, tilebytes);
     if (p.cluster) {
         p.red_off = (int)((smem + 15) & ~(size_t)15);
@@ -729,7 +815,7 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     switch (type) {
         case KF_T_BF16: fmt = FMT_BF16, mode = MODE_PLAIN; break;
         case KF_T_F8E5M2: fmt = FMT_F8, mode = MODE_PLAIN; break;
-        case KF_T_Q4: fmt = FMT_Q4, mode = !ctx->gemv_exact ? MODE_FACTOR : ctx->deq_fma ? MODE_AFFINE_FMA : w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
+        case KF_T_Q4: fmt = FMT_Q4, mode = !ctx->gemv_exact ? MODE_FAST : ctx->deq_fma ? MODE_AFFINE_FMA : w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
         case KF_T_Q2: fmt = FMT_Q2, mode = !ctx->gemv_exact ? MODE_FACTOR : ctx->deq_fma ? MODE_AFFINE_FMA : w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
         case KF_T_SIGN: fmt = FMT_Q2, mode = MODE_SCALE; break;
         case KF_T_BINARY: fmt = FMT_Q1, mode = MODE_SCALE; break;
@@ -741,7 +827,8 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     p.nseg = n, p.x = (const uint16_t*)x, p.residual = (const uint16_t*)residual, p.M = M, p.K = K;
     p.norm_w = (const uint16_t*)norm_w, p.norm_eps = norm_eps;
     p.steps_total = K / KSTEP, p.qbias = w[0].qbias, p.epilogue = epilogue;
-    p.lop_mask = fmt == FMT_Q4 ? 0x000F000Fu : fmt == FMT_Q2 ? 0x00030003u : 0x00010001u, p.lop_magic = 0x43004300u;
+    p.lop_mask = fmt == FMT_Q4 ? 0x000F000Fu : fmt == FMT_Q2 ? 0x00030003u : 0x00010001u;
+    p.lop_magic = mode == MODE_FAST ? 0x64006400u : 0x43004300u;  // fp16x2 1024.0 / bf16x2 128.0
     int total_rows = 0;
     for (int i = 0; i < n; i++) {
         KF_REQUIRE(ctx, w[i].type == type && w[i].cols == K && w[i].qbias == w[0].qbias && w[i].group == w[0].group,
@@ -817,7 +904,7 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     KF_GEMV_CASE(FMT_Q2, MODE_AFFINE_FMA)
     KF_GEMV_CASE(FMT_Q4, MODE_AFFINE)
     KF_GEMV_CASE(FMT_Q4, MODE_AFFINE_SYM)
-    KF_GEMV_CASE(FMT_Q4, MODE_FACTOR)
+    KF_GEMV_CASE(FMT_Q4, MODE_FAST)
     KF_GEMV_CASE(FMT_Q2, MODE_FACTOR)
     KF_GEMV_CASE(FMT_Q2, MODE_AFFINE)
     KF_GEMV_CASE(FMT_Q2, MODE_AFFINE_SYM)

@@ -5,21 +5,28 @@
 // CU_Q128toX_ T.cu:245-294) + CU_mm_blasLt (cuBLASLt GEMM, src/Device/CUDA/kernel/gemm.cu:93-214) as called from SLP::Forw
 // (src/Device/CUDA/NeuronFuse.cu:305-381), with the neighbouring CU_rms_infer / CU_swiglu_v0 / CU_add3 launches folded in.
 //
-// HBM-bound: every packed byte is read exactly once, 0.53 B / weight.  What this kernel changes against gemv.cu (round 1: per-thread
-// LDGSTS rings, one CTA per (row block, k slice), 400+ CTAs each paying the prologue):
-//   * ONE producer thread per CTA streams whole [128 rows x 128 k] tiles of packed bytes with TMA (cp.async.bulk.tensor, UTMALDG) into an
-//     mbarrier ring; the 8 consumer warps only do LDS + dequant + mma.sync -- no per-thread address arithmetic, no cp.async bookkeeping;
-//   * PERSISTENT stream-K grid: one CTA per SM walks an equal, contiguous share of the (row block, k step) tiles, so the prologue
-//     (RMSNorm sum, activation staging) is paid once per SM and all SMs finish together whatever the shape; a row block that spans
-//     CTAs is reduced in a fixed order (partials through L2, the last contributor adds them up in CTA order: bit-reproducible);
-//   * zero / step travel through the same async pipeline: one [128 rows x 8 groups] TMA tile of each per 8 k steps into a second, small
-//     ring (a plain global load per chunk was the first version: with ~13 MB of TMA requests queued in front of it, its latency -- not
-//     the HBM rate -- paced the whole kernel, 1.8 TB/s);
-//   * the shared-memory footprint is kept below half an SM so that the NEXT kernel of the stream (programmatic dependent launch)
-//     becomes resident and fills its own ring while this one still computes: the HBM stream does not stop at kernel boundaries.
-// Dequant arithmetic (template MODE): DM_FMA = the reference's expression with one bf16 rounding (fma.rn.bf16, what the reference's
-// kernel computes on sm_90+, ctx deq_fma = 1), DM_TWO = two roundings (deq_fma = 0), DM_FACTOR = factored scale / zero (gemv_exact = 0:
-// not weight-exact, measures what the roundings cost).  The k order inside a 32-weight slot is permuted exactly as in gemv.cu.
+// The op is HBM-bound on paper (0.53 B / weight, every packed byte read once).  What actually limited round 1's kernel (gemv.cu) was the
+// ALU pipe: tools/ubench/deq_rate*.cu measure, from registers only, 432 clk per [128 rows x 128 k] tile and SM for the bit-exact bf16
+// unpack (SHF + LOP3 + HSUB2 + HFMA2 per pair of weights; a funnel shift alone costs ~5 clk per warp instruction and scheduler on this
+// part) -- MORE than the 392 clk the tile's bytes take at the measured HBM rate.  Hence two arithmetic modes (template MODE):
+//   DM_FAST (default)  the codes go to the tensor cores as fp16 numbers 1024 + c / 1024 + 16 c, built with ONE LOP3 each (both nibbles of
+//                      a byte sit inside fp16's 10 mantissa bits; one byte-permute per 8 codes replaces six funnel shifts): ~105-160 clk
+//                      per tile.  The group's step / zero / code bias are applied to the fp32 group sums:
+//                          y += step * (sum_k c_k x_k - qbias * Sx) - zero * Sx,   Sx = sum_k x_k
+//                      i.e. the reference's affine dequant WITHOUT its intermediate bf16 rounding of every weight (logits agree within the
+//                      stated tolerance; the dequantised weights themselves stay bit-exact through kf_dequant).  Activations are staged as
+//                      fp16 with a power-of-two scale per 128-k group (exact for bf16 inputs over 28 binades).
+//   DM_FMA / DM_TWO    the reference's expression evaluated per weight in bf16 with one / two roundings (ctx gemv_exact = 1 with
+//                      deq_fma = 1 / 0): bit-exact weights inside the matmul, ALU-bound at ~0.6 of the HBM peak.
+// Structure (all modes):
+//   * PERSISTENT stream-K grid: one CTA per SM (or two: gemv_tma_occ) walks an equal, contiguous share of the (row block, k step) tiles:
+//     the prologue (RMSNorm sum, activation staging) is paid once per SM and all SMs finish together whatever the shape; a row block
+//     that spans CTAs is reduced in a fixed order (partials through L2, the last contributor adds them in CTA order: bit-reproducible);
+//   * ONE producer thread per CTA streams [128 rows x 4 k steps] stages of packed bytes with TMA (cp.async.bulk.tensor, UTMALDG) into an
+//     mbarrier ring, and the zero / step tiles of 8 k steps into a second, small ring; the consumer warps only do LDS + unpack +
+//     mma.sync: no per-thread address arithmetic, no cp.async bookkeeping;
+//   * the shared-memory / register footprint of the 8-warp variant is below half an SM, so the NEXT kernel of the stream (programmatic
+//     dependent launch) becomes resident and fills its own ring while this one drains: the HBM stream does not stop at kernel boundaries.
 #include <string.h>
 
 #include <algorithm>
@@ -30,14 +37,10 @@
 namespace {
 using namespace kfa;
 
-enum { DM_FMA = 0, DM_TWO = 1, DM_FACTOR = 2 };
+enum { DM_FMA = 0, DM_TWO = 1, DM_FAST = 2 };
 enum { EPI_NONE = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_F32 = 4 };
 
-constexpr int kWG       = 2;               // consumer warp groups: group w takes k steps 2w, 2w+1 of every 4-step stage
-constexpr int kCW       = 8 * kWG;         // consumer warps (measured: 8 warps per SM issue ~0.27 instructions / clk / scheduler, 16 ~0.45+)
-constexpr int kCT       = kCW * 32;        // consumer threads
-constexpr int kThreads  = kCT + 32;        // + the producer warp
-constexpr int UROWS     = 128;             // weight rows per tile
+constexpr int UROWS     = 128;             // weight rows per tile (8 warps x 16 rows)
 constexpr int UBYTES    = UROWS * 64;      // one k step of a tile: 4-bit, 64 bytes per row
 constexpr int CHUNK     = 4;               // k steps per ring stage
 constexpr int SBYTES    = CHUNK * UBYTES;  // 32 KB per stage
@@ -75,7 +78,6 @@ struct TParams {
     int xs;        // k steps of activations staged at once (multiple of 4)
     int qbias, epilogue;
     int dbg;  // -DKF_DEBUG_KNOBS builds only (timing experiments, results are garbage): 1 = consumers skip the math, 2 = no weight TMA
-    uint32_t lop_mask, lop_magic;
     float* ws;        // [grid][8][UROWS] partial tiles of row blocks that span CTAs
     unsigned* flags;  // [grid] "partial of CTA c is in ws" (self-resetting)
     // byte offsets inside dynamic shared memory
@@ -88,34 +90,43 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (a & IMM) | c in ONE LOP3 with the mask as an immediate: two register reads (no bank conflict on the third source)
+template <uint32_t IMM>
+__device__ __forceinline__ uint32_t and_or_imm(uint32_t a, uint32_t c) {
     uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "n"(IMM), "r"(c));
     return d;
 }
-// permuted k order inside a 32-weight slot (gemv.cu xperm<FMT_Q4>): codes 16 bits apart in a register form one bf16x2
+// permuted k order inside a 32-weight slot (gemv.cu xperm<FMT_Q4>): codes 16 bits apart in a register form one 16-bit pair
 __host__ __device__ constexpr int xperm4(int o) { return 8 * (o >> 3) + ((o & 1) ? 3 : 7) - ((o & 7) >> 1); }
 
-// one pair of codes (16 bits apart in `reg` after the shift) -> bf16x2 weights.  gz = -zero (DM_FMA) / zero (DM_TWO)
+// bit-exact modes: one pair of codes (16 bits apart in `reg` after the shift) -> bf16x2 weights.  gz = -zero (DM_FMA) / zero (DM_TWO)
 template <int MODE>
-__device__ __forceinline__ uint32_t deq_pair(uint32_t reg, int shift, uint32_t step2, uint32_t gz, uint32_t bias2, uint32_t mask, uint32_t magic) {
-    const uint32_t v = and_or(reg >> shift, mask, magic);  // bf16x2 {128 + c_lo, 128 + c_hi}, exact
-    if (MODE == DM_FACTOR) return v;
+__device__ __forceinline__ uint32_t deq_pair(uint32_t reg, int shift, uint32_t step2, uint32_t gz, uint32_t bias2, uint32_t magic) {
+    const uint32_t v = and_or_imm<0x000F000Fu>(reg >> shift, magic);            // bf16x2 {128 + c_lo, 128 + c_hi}, exact
     const __nv_bfloat162 k = __hsub2_rn(u32_as_bf162(v), u32_as_bf162(bias2));  // code - qbias: a small integer, exact
     if (MODE == DM_FMA) return bf162_as_u32(__hfma2(k, u32_as_bf162(step2), u32_as_bf162(gz)));  // RN(step*k - zero): ONE rounding (T.cu:274 as built for sm_90+)
     const __nv_bfloat162 p = __hmul2_rn(u32_as_bf162(step2), k);                                   // RN(step*k)
     return bf162_as_u32(__hsub2_rn(p, u32_as_bf162(gz)));                                          // RN(p - zero): TWO roundings
 }
 
-// MX: token rows staged in shared memory (1, 2, 4 or 8; the MMA's 8 columns replicate them)
-template <int MODE, int MX>
-__global__ void __launch_bounds__(kThreads, 1)
+// MX: token rows staged in shared memory (1, 2, 4 or 8; the MMA's 8 columns replicate them) ; NWG: consumer warp groups of 8 warps
+// (group w takes k steps [w * 4 / NWG, (w + 1) * 4 / NWG) of every stage)
+template <int MODE, int MX, int NWG>
+__global__ void __launch_bounds__(256 * NWG + 32, NWG == 1 ? 2 : 1)
 kf_gemv_tma_kernel(const __grid_constant__ TMaps tm, const TParams p) {
+    constexpr int kCW = 8 * NWG, kCT = 256 * NWG, UPW = CHUNK / NWG;  // consumer warps / threads, k steps per warp group and stage
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ float s_red[8];
     __shared__ float s_scale[8];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    kf_grid_launch_dependents();  // the next kernel of the stream may be scheduled as soon as our CTAs retire
+    kf_grid_launch_dependents();  // the next kernel of the stream may become resident and start its own weight stream
 
     const int u0 = blockIdx.x * p.upc, u1 = min(u0 + p.upc, p.units), n = u1 - u0;
     const int NS = p.nstage;
@@ -196,14 +207,14 @@ kf_gemv_tma_kernel(const __grid_constant__ TMaps tm, const TParams p) {
     const int wg = warp >> 3, wl = warp & 7;  // warp group (which k steps of a stage) / warp inside the group (which 16 rows)
     auto cbar = [] { named_bar_sync(1, kCT); };
     uint4* xs    = reinterpret_cast<uint4*>(smem + p.off_x);      // [slot][4 units][MX][4 thread slots] x 16 bytes
-    float* sxs   = reinterpret_cast<float*>(smem + p.off_sx);     // [slot][MX] group sums of the staged activations (DM_FACTOR)
-    float* tile  = reinterpret_cast<float*>(smem + p.off_tile);   // [kWG][MX][TS]: one partial tile per warp group
+    float4* sxs  = reinterpret_cast<float4*>(smem + p.off_sx);    // DM_FAST: [slot][MX] {1024 Sxe + qbias Sx, Sx, 1 / scale, -} of the staged group
+    float* tile  = reinterpret_cast<float*>(smem + p.off_tile);   // [NWG][MX][TS]: one partial tile per warp group
     float* stash = reinterpret_cast<float*>(smem + p.off_stash);  // [MX][TS] partial of the row block this CTA will reduce at the end
     constexpr int TILE1 = MX * TS;
 
     // rows of this thread inside a tile: warp wl of a group owns rows 16 wl .. 16 wl + 15 (halves: warps 0-3 / 4-7), thread rows g, g + 8
     const int trow = 16 * wl + g;
-    const uint32_t woff = (uint32_t)(2 * wg) * UBYTES + (uint32_t)trow * 64 + 16 * t;
+    const uint32_t woff = (uint32_t)(UPW * wg) * UBYTES + (uint32_t)trow * 64 + 16 * t;
 
     // ---- everything above touched nothing the previous kernel writes.  From here on we read x / residual and write y / ws ----------
     kf_grid_dependency_wait();
@@ -242,7 +253,8 @@ kf_gemv_tma_kernel(const __grid_constant__ TMaps tm, const TParams p) {
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[c][j] = 0.f;
     const uint32_t bias2 = pack_bf16x2((float)(128 + p.qbias), (float)(128 + p.qbias));
-    const int xcol       = (MX >= 8 ? g : (g & (MX - 1))) * 4 + t;  // column g of the MMA reads token g mod MX
+    const uint32_t magic = MODE == DM_FAST ? 0x64006400u : 0x43004300u;  // fp16x2 1024.0 / bf16x2 128.0
+    const int xcol       = (MX >= 8 ? g : (g & (MX - 1))) * 4 + t;       // column g of the MMA reads token g mod MX
     int stage = 0, phase = 0, gstage = 0, gphase = 0;
     int pend_rb = -1;             // row block whose reduction this CTA owns (its first, partial, segment), done after the last tile
     int seg_k0  = u0 % p.ksteps;  // first k step of the segment being accumulated
@@ -296,12 +308,13 @@ kf_gemv_tma_kernel(const __grid_constant__ TMaps tm, const TParams p) {
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[c][j] = 0.f;
         cbar();
-        // the two warp groups hold different k steps of the same rows: add them in a fixed order into group 0's slot
-        for (int e = tid; e < p.M * UROWS; e += kCT) {
-            const int i = (e / UROWS) * TS + (e % UROWS);
-            tile[i] = tile[i] + tile[TILE1 + i];
+        if (NWG > 1) {  // the warp groups hold different k steps of the same rows: add them in a fixed order into group 0's slot
+            for (int e = tid; e < p.M * UROWS; e += kCT) {
+                const int i = (e / UROWS) * TS + (e % UROWS);
+                tile[i] = tile[i] + tile[TILE1 + i];
+            }
+            cbar();
         }
-        cbar();
         if (k0 == 0 && k1 == p.ksteps) {
             epilogue(rb);
         } else if (k1 == p.ksteps) {  // we hold the LAST k steps of rb: we are its reducer; keep our share, reduce after the last tile
@@ -316,8 +329,6 @@ kf_gemv_tma_kernel(const __grid_constant__ TMaps tm, const TParams p) {
         }
         cbar();  // the tiles may be overwritten by the next flush
     };
-
-    uint32_t gz_a[4], gs_a[4], gz_b[4], gs_b[4];  // zero / step of rows g and g + 8 for the current block of 8 groups (persist across windows)
 
     // ================================================================================================ main loop over x windows ======
     for (int wb = ubase; wb < u1; wb += p.xs) {
@@ -356,10 +367,35 @@ kf_gemv_tma_kernel(const __grid_constant__ TMaps tm, const TParams p) {
 #pragma unroll
                     for (int i = 0; i < 16; i++) src[i] = 0u;
                 }
-                float gsum = 0.f;
-                if (MODE == DM_FACTOR) {
+                if (MODE == DM_FAST) {
+                    // fp16 staging with a power-of-two scale per 128-k group (the quad's 4 x 32 values): the group's largest magnitude
+                    // lands in [2^13, 2^14), so every bf16 input within 2^27 of it converts exactly; the elements that meet the codes
+                    // carrying a factor 16 (even codes of every 8: the fp16 number built from the byte's high nibble) are divided by 16
+                    const unsigned qm = 0xFu << (lane & ~3);
+                    uint32_t amax = 0;
 #pragma unroll
-                    for (int i = 0; i < 16; i++) gsum += bf16lo(src[i]), gsum += bf16hi(src[i]);
+                    for (int i = 0; i < 16; i++) amax = max(amax, max(src[i] & 0x7fffu, (src[i] >> 16) & 0x7fffu));
+                    amax = max(amax, __shfl_xor_sync(qm, amax, 1));
+                    amax = max(amax, __shfl_xor_sync(qm, amax, 2));
+                    const int e      = (int)(amax >> 7);                          // biased bf16 exponent of the largest magnitude
+                    const int shift  = amax == 0 ? 0 : max(-100, min(100, 140 - e));  // 140 = 127 + 13
+                    const float scl  = __uint_as_float((uint32_t)(127 + shift) << 23);
+                    float sum = 0.f, sume = 0.f;  // Sx' (scaled) and Sxe (scaled, with the 1/16 factors as the MMA sees them)
+                    uint32_t hsrc[16];            // fp16 pairs, natural order
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        // elements 2i (even index within its 8-block: code parity even -> factor 16 on the weight side) and 2i + 1
+                        const float a = bf16lo(src[i]) * scl, b = bf16hi(src[i]) * scl;
+                        const __half ha = __float2half_rn(a * 0.0625f), hb = __float2half_rn(b);
+                        sum += a, sum += b;
+                        sume += __half2float(ha), sume += __half2float(hb);
+                        hsrc[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+                    }
+                    sum += __shfl_xor_sync(qm, sum, 1), sum += __shfl_xor_sync(qm, sum, 2);      // fixed order: bit-reproducible
+                    sume += __shfl_xor_sync(qm, sume, 1), sume += __shfl_xor_sync(qm, sume, 2);
+                    if (tt == 0) sxs[slot * MX + m] = make_float4(fmaf(1024.0f, sume, (float)p.qbias * sum), sum, __uint_as_float((uint32_t)(127 - shift) << 23), 0.f);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) src[i] = hsrc[i];
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -373,12 +409,6 @@ kf_gemv_tma_kernel(const __grid_constant__ TMaps tm, const TParams p) {
                     }
                     xs[((slot * 4 + u) * MX + m) * 4 + tt] = make_uint4(o[0], o[1], o[2], o[3]);
                 }
-                if (MODE == DM_FACTOR) {  // group sum = the four 32-wide slots of the quad (4 consecutive lanes, active together), fixed order
-                    const unsigned qm = 0xFu << (lane & ~3);
-                    gsum += __shfl_xor_sync(qm, gsum, 1);
-                    gsum += __shfl_xor_sync(qm, gsum, 2);
-                    if (tt == 0) sxs[slot * MX + m] = gsum;
-                }
             }
         }
         cbar();
@@ -390,81 +420,95 @@ kf_gemv_tma_kernel(const __grid_constant__ TMaps tm, const TParams p) {
         for (; uc < wend; uc += CHUNK) {
             // ---- zero / step: a new tile every 8 k steps (and at the start of this CTA's share, which may sit mid-block) ----
             if ((ks0 & (GBLK - 1)) == 0 || uc == ubase) {
+                if (uc != ubase) {  // the previous block is no longer read by this warp
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(gempty0 + 8 * gstage);
+                    if (++gstage == kGStage) gstage = 0, gphase ^= 1;
+                }
                 mbar_wait(gfull0 + 8 * gstage, gphase);
-                const uint32_t ga = gring0 + gstage * GBYTES + (uint32_t)trow * 16;
-                lds128(ga, gz_a), lds128(ga + 128, gz_b), lds128(ga + GBYTES / 2, gs_a), lds128(ga + GBYTES / 2 + 128, gs_b);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(gempty0 + 8 * gstage);
-                if (++gstage == kGStage) gstage = 0, gphase ^= 1;
             }
-            // the register of this warp group's two groups: block half (ks0 & 4), then pair wg inside the half
-            const int gi = ((ks0 & 4) ? 2 : 0) + wg;
-            const uint32_t za32 = gi == 0 ? gz_a[0] : gi == 1 ? gz_a[1] : gi == 2 ? gz_a[2] : gz_a[3];
-            const uint32_t sa32 = gi == 0 ? gs_a[0] : gi == 1 ? gs_a[1] : gi == 2 ? gs_a[2] : gs_a[3];
-            const uint32_t zb32 = gi == 0 ? gz_b[0] : gi == 1 ? gz_b[1] : gi == 2 ? gz_b[2] : gz_b[3];
-            const uint32_t sb32 = gi == 0 ? gs_b[0] : gi == 1 ? gs_b[1] : gi == 2 ? gs_b[2] : gs_b[3];
-            // ---- this thread's 2 k steps x 2 rows x 16 bytes of the stage, then the stage goes back to the producer ----
+            const uint32_t ga = gring0 + gstage * GBYTES + (uint32_t)trow * 16 + (ks0 & (GBLK - 1)) * 2;  // zero of (row trow, group ks0)
             mbar_wait(full0 + 8 * stage, phase);
-            uint32_t ra[2][4], rb8[2][4];
 #pragma unroll
-            for (int jj = 0; jj < 2; jj++) {
-                lds128(ring0 + stage * SBYTES + woff + jj * UBYTES, ra[jj]);
-                lds128(ring0 + stage * SBYTES + woff + jj * UBYTES + 512, rb8[jj]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * stage);  // one arrival per warp
-            if (++stage == NS) stage = 0, phase ^= 1;
+            for (int jp = 0; jp < UPW; jp += 2) {  // this warp group's k steps of the stage, two at a time
+                const int j0 = UPW * wg + jp;
+                uint32_t ra[2][4], rb8[2][4];
 #pragma unroll
-            for (int jj = 0; jj < 2; jj++) {
-                const int u = uc + 2 * wg + jj;
-                if (u < wbeg || u >= wend) continue;  // uniform over the warp group
+                for (int jj = 0; jj < 2; jj++) {
+                    lds128(ring0 + stage * SBYTES + woff + (jp + jj) * UBYTES, ra[jj]);
+                    lds128(ring0 + stage * SBYTES + woff + (jp + jj) * UBYTES + 512, rb8[jj]);
+                }
+                if (jp + 2 >= UPW) {  // last read of the stage: hand it back to the producer (one arrival per warp)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 2; jj++) {
+                    const int u = uc + j0 + jj;
+                    if (u < wbeg || u >= wend) continue;  // uniform over the warp group (ragged ends of the share)
 #ifdef KF_DEBUG_KNOBS
-                if (p.dbg & 1) {
-                    acc[0][0] += __uint_as_float(ra[jj][0] ^ rb8[jj][1]);
-                    continue;
-                }
+                    if (p.dbg & 1) {
+                        acc[0][0] += __uint_as_float(ra[jj][0] ^ rb8[jj][1]);
+                        continue;
+                    }
 #endif
-                const uint32_t sel    = jj ? 0x3232u : 0x1010u;
-                const uint32_t step2a = __byte_perm(sa32, 0u, sel), step2b = __byte_perm(sb32, 0u, sel);
-                uint32_t gza = __byte_perm(za32, 0u, sel), gzb = __byte_perm(zb32, 0u, sel);
-                if (MODE == DM_FMA) gza ^= 0x80008000u, gzb ^= 0x80008000u;  // -zero
-                const int slot = u - wb;
-                float accg[2][4];
-                if (MODE == DM_FACTOR) {
+                    // zero / step of this k step's group for rows trow and trow + 8 (bf16 in the staged tile: [zero | step][128 rows][8 groups])
+                    uint32_t za16, zb16, sa16, sb16;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(za16) : "r"(ga + (j0 + jj) * 2));
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(zb16) : "r"(ga + (j0 + jj) * 2 + 128));
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(sa16) : "r"(ga + (j0 + jj) * 2 + GBYTES / 2));
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(sb16) : "r"(ga + (j0 + jj) * 2 + GBYTES / 2 + 128));
+                    const int slot = u - wb;
+                    if (MODE == DM_FAST) {
+                        // ---- fp16 codes 1024 + c / 1024 + 16 c straight into the tensor cores; affine map applied to the group sums ----
+                        const float4 sv0 = sxs[slot * MX + ((2 * t) & (MX - 1))], sv1 = sxs[slot * MX + ((2 * t + 1) & (MX - 1))];
+                        float accg[2][4];
+                        accg[0][0] = accg[0][2] = -sv0.x, accg[0][1] = accg[0][3] = -sv1.x;  // -(1024 Sxe + qbias Sx)
 #pragma unroll
-                    for (int c = 0; c < 2; c++)
+                        for (int q = 0; q < 4; q++) accg[1][q] = 0.f;
 #pragma unroll
-                        for (int q = 0; q < 4; q++) accg[c][q] = 0.f;
-                }
+                        for (int uu = 0; uu < 4; uu++) {
+                            const uint4 xb = xs[((slot * 4 + uu) * MX) * 4 + xcol];
+                            const uint32_t wa = ra[jj][3 - uu], wb8 = rb8[jj][3 - uu];  // the 128-bit words keep the first codes in the LAST register
+                            const uint32_t wa_s = __byte_perm(wa, 0u, 0x4321), wb_s = __byte_perm(wb8, 0u, 0x4321);  // >> 8 as a byte permute
+                            uint32_t a[4];
+                            a[0] = and_or_imm<0x000F000Fu>(wa, magic), a[1] = and_or_imm<0x000F000Fu>(wb8, magic);   // codes {7, 3}
+                            a[2] = and_or_imm<0x00F000F0u>(wa, magic), a[3] = and_or_imm<0x00F000F0u>(wb8, magic);   // codes {6, 2} x 16
+                            mma_f16_16816(accg[0], a, xb.x, xb.y);
+                            a[0] = and_or_imm<0x000F000Fu>(wa_s, magic), a[1] = and_or_imm<0x000F000Fu>(wb_s, magic);  // codes {5, 1}
+                            a[2] = and_or_imm<0x00F000F0u>(wa_s, magic), a[3] = and_or_imm<0x00F000F0u>(wb_s, magic);  // codes {4, 0} x 16
+                            mma_f16_16816(accg[1], a, xb.z, xb.w);
+                        }
+                        // y += 2^-shift * (step * sum((c - qbias) x') - zero * Sx')
+                        const float fa = __uint_as_float(sa16 << 16), fb = __uint_as_float(sb16 << 16);
+                        const float za = __uint_as_float(za16 << 16), zb = __uint_as_float(zb16 << 16);
+                        acc[0][0] = fmaf(sv0.z, fmaf(fa, accg[0][0] + accg[1][0], -za * sv0.y), acc[0][0]);
+                        acc[0][1] = fmaf(sv1.z, fmaf(fa, accg[0][1] + accg[1][1], -za * sv1.y), acc[0][1]);
+                        acc[0][2] = fmaf(sv0.z, fmaf(fb, accg[0][2] + accg[1][2], -zb * sv0.y), acc[0][2]);
+                        acc[0][3] = fmaf(sv1.z, fmaf(fb, accg[0][3] + accg[1][3], -zb * sv1.y), acc[0][3]);
+                    } else {
+                        // ---- the reference's per-weight dequant in bf16 (one or two roundings) ----
+                        const uint32_t step2a = sa16 * 0x00010001u, step2b = sb16 * 0x00010001u;
+                        uint32_t gza = za16 * 0x00010001u, gzb = zb16 * 0x00010001u;
+                        if (MODE == DM_FMA) gza ^= 0x80008000u, gzb ^= 0x80008000u;  // -zero
 #pragma unroll
-                for (int uu = 0; uu < 4; uu++) {
-                    const uint4 xb = xs[((slot * 4 + uu) * MX) * 4 + xcol];
-                    const uint32_t wa = ra[jj][3 - uu], wb8 = rb8[jj][3 - uu];  // the 128-bit words keep the first codes in the LAST register
+                        for (int uu = 0; uu < 4; uu++) {
+                            const uint4 xb = xs[((slot * 4 + uu) * MX) * 4 + xcol];
+                            const uint32_t wa = ra[jj][3 - uu], wb8 = rb8[jj][3 - uu];
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        uint32_t a[4];
-                        a[0] = deq_pair<MODE>(wa, 8 * h, step2a, gza, bias2, p.lop_mask, p.lop_magic);
-                        a[1] = deq_pair<MODE>(wb8, 8 * h, step2b, gzb, bias2, p.lop_mask, p.lop_magic);
-                        a[2] = deq_pair<MODE>(wa, 8 * h + 4, step2a, gza, bias2, p.lop_mask, p.lop_magic);
-                        a[3] = deq_pair<MODE>(wb8, 8 * h + 4, step2b, gzb, bias2, p.lop_mask, p.lop_magic);
-                        const uint32_t b0 = h ? xb.z : xb.x, b1 = h ? xb.w : xb.y;
-                        if (MODE == DM_FACTOR)
-                            mma_bf16_16816(accg[h], a, b0, b1);
-                        else
-                            mma_bf16_16816(acc[h], a, b0, b1);  // two independent accumulation chains
+                            for (int h = 0; h < 2; h++) {
+                                uint32_t a[4];
+                                a[0] = deq_pair<MODE>(wa, 8 * h, step2a, gza, bias2, magic);
+                                a[1] = deq_pair<MODE>(wb8, 8 * h, step2b, gzb, bias2, magic);
+                                a[2] = deq_pair<MODE>(wa, 8 * h + 4, step2a, gza, bias2, magic);
+                                a[3] = deq_pair<MODE>(wb8, 8 * h + 4, step2b, gzb, bias2, magic);
+                                mma_bf16_16816(acc[h], a, h ? xb.z : xb.x, h ? xb.w : xb.y);  // two independent accumulation chains
+                            }
+                        }
                     }
                 }
-                if (MODE == DM_FACTOR) {  // y += step * (sum (128 + c) x  -  (128 + qbias) Sx) - zero * Sx
-                    const float off = (float)(128 + p.qbias);
-                    const float fa = bf16hi(step2a), fb = bf16hi(step2b);
-                    const float ka = fmaf(off, fa, bf16hi(gza)), kb = fmaf(off, fb, bf16hi(gzb));
-                    const float sx0 = sxs[slot * MX + ((2 * t) & (MX - 1))], sx1 = sxs[slot * MX + ((2 * t + 1) & (MX - 1))];
-                    acc[0][0] += fmaf(fa, accg[0][0] + accg[1][0], -ka * sx0);
-                    acc[0][1] += fmaf(fa, accg[0][1] + accg[1][1], -ka * sx1);
-                    acc[0][2] += fmaf(fb, accg[0][2] + accg[1][2], -kb * sx0);
-                    acc[0][3] += fmaf(fb, accg[0][3] + accg[1][3], -kb * sx1);
-                }
             }
+            if (++stage == NS) stage = 0, phase ^= 1;
             // ---- end of a row block (always the end of a stage) or of this CTA's share: hand the sums over ----
             if (ks0 + CHUNK == p.ksteps || uc + CHUNK >= u1) {
                 flush(rb, seg_k0, ks0 + min(CHUNK, u1 - uc));
@@ -511,33 +555,37 @@ struct TmaState {
     float* ws       = nullptr;
     unsigned* flags = nullptr;
     int ws_ctas     = 0;
-    uint64_t attr_devices[3 * 4] = {};  // per kernel instantiation: devices whose MaxDynamicSharedMemorySize has been set
+    uint64_t attr_devices[3 * 4 * 2] = {};  // per kernel instantiation: devices whose MaxDynamicSharedMemorySize has been set
 };
 TmaState* state_of(kf_ctx* ctx) {
     if (!ctx->gemv_tma) ctx->gemv_tma = new TmaState();
     return reinterpret_cast<TmaState*>(ctx->gemv_tma);
 }
 
-template <int MODE, int MX>
+template <int MODE, int MX, int NWG>
 int launch(kf_ctx* ctx, TmaState* st, const TParams& p, const TMaps& tm, int grid, size_t smem) {
-    auto kern = kf_gemv_tma_kernel<MODE, MX>;
-    constexpr int slot = MODE * 4 + (MX == 1 ? 0 : MX == 2 ? 1 : MX == 4 ? 2 : 3);
+    auto kern = kf_gemv_tma_kernel<MODE, MX, NWG>;
+    constexpr int slot = (MODE * 4 + (MX == 1 ? 0 : MX == 2 ? 1 : MX == 4 ? 2 : 3)) * 2 + (NWG - 1);
     if (!(st->attr_devices[slot] >> (ctx->device & 63) & 1)) {
         KF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         st->attr_devices[slot] |= 1ull << (ctx->device & 63);
     }
-    KF_CUDA(ctx, kf_launch_pdl(ctx, kern, dim3(grid), dim3(kThreads), smem, tm, p));
+    KF_CUDA(ctx, kf_launch_pdl(ctx, kern, dim3(grid), dim3(256 * NWG + 32), smem, tm, p));
     KF_LAUNCH_CHECK(ctx);
     return KF_OK;
 }
-template <int MODE>
+template <int MODE, int NWG>
 int launch_mx(kf_ctx* ctx, TmaState* st, const TParams& p, const TMaps& tm, int grid, size_t smem, int mx) {
     switch (mx) {
-        case 1: return launch<MODE, 1>(ctx, st, p, tm, grid, smem);
-        case 2: return launch<MODE, 2>(ctx, st, p, tm, grid, smem);
-        case 4: return launch<MODE, 4>(ctx, st, p, tm, grid, smem);
-        default: return launch<MODE, 8>(ctx, st, p, tm, grid, smem);
+        case 1: return launch<MODE, 1, NWG>(ctx, st, p, tm, grid, smem);
+        case 2: return launch<MODE, 2, NWG>(ctx, st, p, tm, grid, smem);
+        case 4: return launch<MODE, 4, NWG>(ctx, st, p, tm, grid, smem);
+        default: return launch<MODE, 8, NWG>(ctx, st, p, tm, grid, smem);
     }
+}
+template <int MODE>
+int launch_wg(kf_ctx* ctx, TmaState* st, const TParams& p, const TMaps& tm, int grid, size_t smem, int mx, int nwg) {
+    return nwg == 2 ? launch_mx<MODE, 2>(ctx, st, p, tm, grid, smem, mx) : launch_mx<MODE, 1>(ctx, st, p, tm, grid, smem, mx);
 }
 }  // namespace
 
@@ -566,12 +614,8 @@ int kf_make_tensor_map_2d(kf_ctx* ctx, CUtensorMap* tm, CUtensorMapDataType dt, 
     cuuint64_t strides[1] = {inner * (uint64_t)esize};
     cuuint32_t box[2]     = {box_inner, box_outer};
     cuuint32_t estr[2]    = {1, 1};
-    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-#ifdef KF_DEBUG_KNOBS
-    const int pk = (ctx->debug_skip >> 12) & 3;  // experiments: 1 = 128-byte promotion, 2 = 64-byte, 3 = none
-    promo = pk == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : pk == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : pk == 3 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo;
-#endif
-    CUresult r = fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char b[128];
         snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -601,7 +645,6 @@ int kf_gemv_tma(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, con
     memset(&p, 0, sizeof(p));
     p.nseg = n, p.x = (const uint16_t*)x, p.residual = (const uint16_t*)residual, p.norm_w = (const uint16_t*)norm_w, p.norm_eps = norm_eps;
     p.M = M, p.K = K, p.ksteps = K / 128, p.qbias = w[0].qbias, p.epilogue = epilogue;
-    p.lop_mask = 0x000F000Fu, p.lop_magic = 0x43004300u;
     p.dbg = (ctx->debug_skip >> 4) & 0xff;
     TMaps tm;
     int rb = 0;
@@ -613,8 +656,8 @@ int kf_gemv_tma(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, con
         auto it = st->maps.find(key);
         if (it == st->maps.end()) {
             TmaState::WMaps m;
-            int rc = kf_make_tensor_map_2d(ctx, &m.w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w[i].data_dev, (uint64_t)K / 2, (uint64_t)w[i].rows, 64,
-                                           (p.dbg & 4) ? 128 : 64, CU_TENSOR_MAP_SWIZZLE_NONE);
+            int rc = kf_make_tensor_map_2d(ctx, &m.w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w[i].data_dev, (uint64_t)K / 2, (uint64_t)w[i].rows, 64, 64,
+                                           CU_TENSOR_MAP_SWIZZLE_NONE);
             if (!rc)
                 rc = kf_make_tensor_map_2d(ctx, &m.z, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, p.seg[i].zero, (uint64_t)K / 128, (uint64_t)w[i].rows, GBLK, 64,
                                            CU_TENSOR_MAP_SWIZZLE_NONE);
@@ -632,20 +675,24 @@ int kf_gemv_tma(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, con
     p.total_rb = rb;
     p.units    = rb * p.ksteps;
 
-    const int mx = M == 1 ? 1 : M == 2 ? 2 : M <= 4 ? 4 : 8;
-    int grid     = std::min(p.units, ctx->sm_count);  // one persistent CTA per SM (17 warps, up to ~200 KB of shared memory)
-    p.upc        = (p.units + grid - 1) / grid;
-    grid         = (p.units + p.upc - 1) / p.upc;
-    // shared memory: weight ring | zero / step ring | x window | group sums | 2 tiles | stash | barriers
-    const int mode = !ctx->gemv_exact ? DM_FACTOR : ctx->deq_fma ? DM_FMA : DM_TWO;
-    const size_t budget = (size_t)std::max(96, std::min(ctx->gemv_tma_smem_kb, 220)) * 1024;
+    // launch geometry.  gemv_tma_warps = 8 (default): one CTA of 8 consumer warps + the producer per SM and HALF an SM's shared memory, so
+    // that the next kernel of the stream becomes resident beside it; 16: two warp groups; gemv_tma_occ = 2: two CTAs per SM of the same launch
+    const int mx   = M == 1 ? 1 : M == 2 ? 2 : M <= 4 ? 4 : 8;
+    const int mode = !ctx->gemv_exact ? DM_FAST : ctx->deq_fma ? DM_FMA : DM_TWO;
+    const int nwg  = ctx->gemv_tma_warps >= 16 ? 2 : 1;
+    const int occ  = (ctx->gemv_tma_occ >= 2 && nwg == 1) ? 2 : 1;
+    int grid       = std::min(p.units, ctx->sm_count * occ);
+    p.upc          = (p.units + grid - 1) / grid;
+    grid           = (p.units + p.upc - 1) / p.upc;
+    // shared memory: weight ring | zero / step ring | x window | group sums | tiles | stash | barriers
+    const size_t budget = (size_t)std::max(72, std::min(ctx->gemv_tma_smem_kb, 220)) * 1024;
     int xs_cap = (int)std::min<size_t>(64, (32 * 1024) / ((size_t)mx * 256));
     int xs     = std::min(xs_cap, ((p.upc + 3 + 3) & ~3));  // a CTA's share starts up to 3 steps after a 4-aligned slot
     xs         = std::max(4, xs & ~3);
-    const size_t xbytes = (size_t)xs * mx * 256, sxbytes = mode == DM_FACTOR ? (size_t)xs * mx * 4 : 0;
+    const size_t xbytes = (size_t)xs * mx * 256, sxbytes = mode == DM_FAST ? (size_t)xs * mx * 16 : 0;
     const size_t tileb  = ((size_t)mx * TS * 4 + 15) & ~(size_t)15;
     const size_t barb   = 2 * 8 * kMaxStage + 2 * 8 * kGStage;
-    const size_t fixed  = (size_t)kGStage * GBYTES + xbytes + ((sxbytes + 15) & ~(size_t)15) + (kWG + 1) * tileb + barb + 64;
+    const size_t fixed  = (size_t)kGStage * GBYTES + xbytes + sxbytes + (nwg + 1) * tileb + barb + 64;
     if (fixed + 2 * SBYTES > budget) return 1;
     int ns = (int)std::min<size_t>(kMaxStage, (budget - fixed) / SBYTES);
     ns     = std::min(ns, std::max(2, (p.upc + 2 * CHUNK - 1) / CHUNK));
@@ -653,8 +700,8 @@ int kf_gemv_tma(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, con
     p.off_g     = ns * SBYTES;
     p.off_x     = p.off_g + kGStage * GBYTES;
     p.off_sx    = p.off_x + (int)xbytes;
-    p.off_tile  = p.off_sx + (int)((sxbytes + 15) & ~(size_t)15);
-    p.off_stash = p.off_tile + (int)(kWG * tileb);
+    p.off_tile  = p.off_sx + (int)sxbytes;
+    p.off_stash = p.off_tile + (int)(nwg * tileb);
     p.off_bar   = p.off_stash + (int)tileb;
     const size_t smem = (size_t)p.off_bar + barb;
 
@@ -672,7 +719,7 @@ int kf_gemv_tma(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, con
         ctx->scratch_gen++;
     }
     p.ws = st->ws, p.flags = st->flags;
-    if (mode == DM_FMA) return launch_mx<DM_FMA>(ctx, st, p, tm, grid, smem, mx);
-    if (mode == DM_TWO) return launch_mx<DM_TWO>(ctx, st, p, tm, grid, smem, mx);
-    return launch_mx<DM_FACTOR>(ctx, st, p, tm, grid, smem, mx);
+    if (mode == DM_FMA) return launch_wg<DM_FMA>(ctx, st, p, tm, grid, smem, mx, nwg);
+    if (mode == DM_TWO) return launch_wg<DM_TWO>(ctx, st, p, tm, grid, smem, mx, nwg);
+    return launch_wg<DM_FAST>(ctx, st, p, tm, grid, smem, mx, nwg);
 }

@@ -49,7 +49,7 @@ struct kf_ctx {
     int attn_warps   = 0;  // warps per CTA of the cluster attention (0 = default)
     int debug_skip   = 0;  // only honoured in builds with -DKF_DEBUG_KNOBS (timing experiments: bit 0 skips attention, bit 1 the skinny GEMVs)
     // persistent TMA-fed stream-K GEMV (gemv_tma.cu): on / CTAs per SM / shared-memory budget per SM in KB
-    int gemv_tma_on = 1, gemv_tma_occ = 1, gemv_tma_smem_kb = 200;
+    int gemv_tma_on = 1, gemv_tma_occ = 1, gemv_tma_smem_kb = 112, gemv_tma_warps = 8;
     void* gemv_tma  = nullptr;  // its state (tensor-map cache, stream-K workspace)
     // bumped whenever a context scratch buffer is reallocated: CUDA graphs captured before hold stale pointers and must be re-captured
     uint64_t scratch_gen = 0;
