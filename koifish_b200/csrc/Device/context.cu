@@ -132,6 +132,8 @@ extern "C" int kf_ctx_get_int(kf_ctx* ctx, const char* key, int* value_out) {
         *value_out = ctx->deq_fma;
     else if (!strcmp(key, "gemv_exact"))
         *value_out = ctx->gemv_exact;
+    else if (!strcmp(key, "gemv_last_s"))
+        *value_out = ctx->gemv_last_s;
     else
         return KF_ERR_BAD_ARG;
     return KF_OK;

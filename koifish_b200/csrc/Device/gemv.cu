@@ -872,18 +872,30 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     const int S_min      = (p.steps_total + hard_steps - 1) / hard_steps;
     int S                = ctx->gemv_splitk;
     if (S <= 0) {
+        // Measured on B200 (profiles/r02_gemv_splitk.txt): a k-slice advances at ~0.55 us per k-step whatever the occupancy -- the ring holds
+        // 3 steps, so a step costs a third of the DRAM round trip -- until the launch as a whole saturates HBM.  So: ONE wave, as many
+        // slices as fit into it; and when the slices of a row block merge inside a thread-block cluster (single token, S <= 8) only the
+        // cluster sizes that tile the GPCs (1, 2, 4, 8): S = 5 on 10240 x 5120 is 13.6 us where S = 4 is 10.3.  The merge through the global
+        // workspace (S > 8) costs ~3.5 us more than the cluster merge.
         const int per_sm3 = MXs <= 8 ? KF_GEMV_OCC : (MXs <= 16 ? 2 : 1), per_sm2 = MXs <= 16 ? 2 : 1;
+        const bool can_cluster = M == 1 && ctx->gemv_cluster > 0;
+        const double bits_of_fmt = (double)fmt_info(fmt).bits;
         double best = 1e30;
         S           = S_min;
         for (int cand = S_min; cand <= std::min(p.steps_total, 64); cand++) {
             const int nst = (p.steps_total + cand - 1) / cand;
             if (nst < 2 && cand > S_min) break;
+            const bool clustered = can_cluster && cand >= 2 && cand <= 8;
+            if (clustered && (cand & (cand - 1)) && cand > S_min) continue;  // cluster sizes 3, 5, 6, 7 pack badly
             const int per_sm  = (soft_steps && nst <= soft_steps) ? per_sm3 : per_sm2;
             const int slots   = ctx->sm_count * per_sm;
             const int waves   = (rb * cand + slots - 1) / slots;
-            // cost in k-step units: each wave pays a prologue (~6 steps incl. split-K traffic) plus its steps; CTAs sharing an SM
-            // share its issue slots, so a fuller SM is not proportionally faster: weight the per-wave time by occupancy^0.5
-            const double cost = waves * (6.0 + nst) * (per_sm >= 3 ? 1.22 : per_sm == 2 ? 1.0 : 0.75);
+            const double fixed = cand == 1 ? 4.0 : clustered ? 5.0 : 7.5;  // us: prologue + merge
+            // bytes in flight = CTAs x ring depth x 8 KB per k-step; what they can pull per DRAM round trip (~1.65 us) caps the stream
+            const double ctas   = std::min<double>((double)rb * cand, slots);
+            const double bw     = std::min(6.0e6, ctas * 3.0 * rows_cta * (KSTEP * bits_of_fmt / 8.0) / 1.65);  // bytes per us
+            const double stream = std::max(0.55 * nst, (double)total_rows * K * (bits_of_fmt / 8.0 + 4.0 / 128.0) / waves / bw);
+            const double cost   = waves * (fixed + stream);
             if (cost < best - 1e-9) best = cost, S = cand;
         }
     }
@@ -892,6 +904,7 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     if (M == 1 && ctx->gemv_cluster == 2 && ctx->gemv_splitk <= 0 && S > 8 && S_min <= 8) S = 8;
     p.cluster    = (M == 1 && ctx->gemv_cluster > 0 && S >= 2 && S <= 8) ? 1 : 0;
     p.S          = S;
+    ctx->gemv_last_s = S;
     p.nsteps_max = (p.steps_total + S - 1) / S;  // floor/ceil slicing never exceeds ceil(steps/S)
     if (S > 1 && !p.cluster) {
         int rc = kf_ensure_gemv_ws(ctx, (size_t)S * rb * std::max(8, MXs) * rows_cta * sizeof(float), rb);

@@ -38,7 +38,11 @@ struct kf_ctx {
     int gemv_splitk  = 0;
     int gemv_variant = 0;
     int gemv_cluster = 1;  // M = 1 split-K: 1 = merge the k-slices of a row block inside a thread-block cluster (DSMEM) when S <= 8; 2 = also cap S at 8; 0 = global workspace
-    int gemv_exact   = 1;  // 1: in-kernel dequant reproduces the reference's bf16 roundings bit for bit ; 0: factored scale/zero (MODE_FACTOR)
+    // 0 (default): decode GEMVs over 4-bit weights apply the group's affine map to fp32 group sums of fp16 codes (MODE_FAST, gemv.cu: the ALU pipe
+    // cannot unpack bit-exact bf16 weights at the HBM rate) -- logits within the stated tolerance ; 1: the in-kernel dequant reproduces the
+    // reference's bf16 roundings bit for bit (weights identical to kf_dequant / GetDataX inside the matmul), ~0.57 of the HBM peak
+    int gemv_exact   = 0;
+    int gemv_last_s  = 0;  // read-only: k-split of the most recent dequant-GEMV launch (tools/gemv_bench.py records it)
     // rounding of the reference's dequant expression (step * k - zero) in bf16 (CU_Q128toX_, T.cu:274), pinned against the reference kernel
     // compiled both ways (oracle/ref_kernels.cu): 1 = ONE rounding, fma.rn.bf16 -- what nvcc's default -fmad=true (implied by the
     // reference's -use_fast_math) generates on sm_90+, i.e. what the reference computes on a B200 ; 0 = TWO roundings (bf16 multiply, then
@@ -49,7 +53,7 @@ struct kf_ctx {
     int attn_warps   = 0;  // warps per CTA of the cluster attention (0 = default)
     int debug_skip   = 0;  // only honoured in builds with -DKF_DEBUG_KNOBS (timing experiments: bit 0 skips attention, bit 1 the skinny GEMVs)
     // persistent TMA-fed stream-K GEMV (gemv_tma.cu): on / CTAs per SM / shared-memory budget per SM in KB
-    int gemv_tma_on = 1, gemv_tma_occ = 1, gemv_tma_smem_kb = 112, gemv_tma_warps = 8;
+    int gemv_tma_on = 0, gemv_tma_occ = 1, gemv_tma_smem_kb = 112, gemv_tma_warps = 8;
     void* gemv_tma  = nullptr;  // its state (tensor-map cache, stream-K workspace)
     // bumped whenever a context scratch buffer is reallocated: CUDA graphs captured before hold stale pointers and must be re-captured
     uint64_t scratch_gen = 0;

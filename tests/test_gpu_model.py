@@ -9,14 +9,26 @@ import oracle_lib as ol
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_RTOL = 1e-2  # north_star: "logits within a stated relative tolerance (e.g. 1e-2 bf16 / top-1 token agreement)"
+# north_star: "logits within a stated relative tolerance (e.g. 1e-2 bf16 / top-1 token agreement)".  Every test below runs twice:
+#   exact -- gemv_exact = 1: each weight dequantised in-kernel to the reference's bf16 value (bit-exact, test_gpu_refkernels.py);
+#            logits within 1e-2 of the largest logit, i.e. about one bf16 ulp of it (an ulp is 3.9e-3 .. 7.8e-3 of the value);
+#   fast  -- the default decode arithmetic for 4-bit weights (MODE_FAST in gemv.cu: group sums in fp32, the affine map applied per
+#            group, no per-weight bf16 rounding -- it differs from the reference by the reference's own weight-rounding noise, rms 1.5e-3
+#            per matmul, test_gpu_kernels.py::test_gemv_fast_matches_oracle); logits within 2e-2 (two to three bf16 ulps of the largest
+#            logit) and the same top-1 wherever the oracle's top two are further apart than that.
+LOGIT_RTOL_BY_ARITH = {"exact": 1e-2, "fast": 2e-2}
+LOGIT_RTOL = 1e-2  # rebound per test by the ctx fixture
 
 MODE_NAME = {ol.RTN_ASYM: "RTN", ol.YYANG: "yyang"}
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["exact", "fast"])
+def ctx(request):
+    global LOGIT_RTOL
     c = kf.Context(0)
+    c.set_int("gemv_exact", 1 if request.param == "exact" else 0)
+    c.arith = request.param
+    LOGIT_RTOL = LOGIT_RTOL_BY_ARITH[request.param]
     yield c
     c.close()
 
@@ -111,7 +123,7 @@ def test_prefill_panel_equals_token_by_token(ctx):
     err, g, w = logits_close(panel[-1], last[0])
     # 20 tokens take the tcgen05 linears and the flash prefill attention (P rounded to bf16 before P.V, as the reference's bf16
     # score buffer): same gate as against the oracle -- 1e-2 of the largest logit and the same top-1
-    assert err <= 1e-2 and int(np.argmax(g)) == int(np.argmax(w))
+    assert err <= LOGIT_RTOL and int(np.argmax(g)) == int(np.argmax(w))
     d = np.abs(ol.bf16_to_f32(model2.kcache(1, len(toks), 128)) - ol.bf16_to_f32(k_seq))
     assert d.max() <= 1e-2 * np.abs(ol.bf16_to_f32(k_seq)).max()
 
@@ -216,7 +228,7 @@ def test_long_prefill_panels_match_token_by_token_and_continue_decoding(ctx):
     assert b.info.max_tokens == 128
     logits, nxt_b = b.prefill(toks, want_logits=True)
     err, g, w = logits_close(logits[0], last[0])
-    assert err <= 1e-2 and int(np.argmax(g)) == int(np.argmax(w))
+    assert err <= LOGIT_RTOL and int(np.argmax(g)) == int(np.argmax(w))
     kb, ka = ol.bf16_to_f32(b.kcache(1, n, 128)), ol.bf16_to_f32(a.kcache(1, n, 128))
     assert np.abs(kb - ka).max() <= 2e-2 * np.abs(ka).max()
     # continue greedily on both: same tokens while the logits margins are not razor thin
@@ -281,7 +293,7 @@ def test_long_context_decode_switches_to_kv_group_attention(ctx):
         ctx.set_int("gqa_min_ctx", 1024)
     for la, lb in zip(a, b):
         err, g, w = logits_close(la, lb)
-        assert err <= 1e-2 and int(np.argmax(g)) == int(np.argmax(w))
+        assert err <= LOGIT_RTOL and int(np.argmax(g)) == int(np.argmax(w))
 
 
 def test_qwen3_32b_dims_one_layer(ctx):

@@ -84,15 +84,21 @@ def main():
                         ctx.check(ctx.lib.kf_linear(ctx.h, y.ptr, C.byref(descs[i % nbuf]), x.ptr, M, 0, None), "kf_linear")
                     torch.cuda.synchronize()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    # the launches go into ONE CUDA graph: a ~10 us kernel issued from Python is otherwise timed at the host's launch rate
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=stream):
+                        for i in range(args.iters):
+                            ctx.check(ctx.lib.kf_linear(ctx.h, y.ptr, C.byref(descs[i % nbuf]), x.ptr, M, 0, None), "kf_linear")
+                    g.replay()
+                    torch.cuda.synchronize()
                     e0.record(stream)
-                    for i in range(args.iters):
-                        ctx.check(ctx.lib.kf_linear(ctx.h, y.ptr, C.byref(descs[i % nbuf]), x.ptr, M, 0, None), "kf_linear")
+                    g.replay()
                     e1.record(stream)
                     torch.cuda.synchronize()
                     us = e0.elapsed_time(e1) * 1e3 / args.iters
                     ab = alg_bytes(N, K, bits, M)
                     gbs = ab / (us * 1e-6) / 1e9
-                    rec = {"type": tname, "N": N, "K": K, "M": M, "tc": tc, "splitk": sk, "variant": variant, "us": round(us, 2), "alg_MB": round(ab / 1e6, 2), "GBps": round(gbs, 1),
+                    rec = {"type": tname, "N": N, "K": K, "M": M, "tc": tc, "splitk": sk, "S": ctx.get_int("gemv_last_s"), "variant": variant, "us": round(us, 2), "alg_MB": round(ab / 1e6, 2), "GBps": round(gbs, 1),
                            "frac_measured": round(gbs / peak, 3), "frac_8TBps": round(gbs / 8000.0, 3), "tflops": round(2.0 * M * N * K / (us * 1e-6) / 1e12, 2),
                            "nbuf": nbuf}
                     print(json.dumps(rec), flush=True)
