@@ -95,6 +95,19 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+GEMV_SOURCES = ("koifish_b200/csrc/Device/gemv.cu", "koifish_b200/csrc/Device/kf_common.cuh")
+TRAFFIC_FILE = "profiles/r02_traffic_decode.json"
+
+
+def kernel_digest():
+    """sha256 over the sources of the dominant kernel: a committed ncu traffic figure is only reported for the kernel it was taken from"""
+    import hashlib
+    h = hashlib.sha256()
+    for rel in GEMV_SOURCES:
+        h.update(open(os.path.join(ROOT, rel), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def gemv_algorithmic_bytes(rows, cols, bits, group, M):
     """SURVEY.md 8d / BASELINE.md 3: N*K*bits/8 + (N*K/G)*4 [packed types] + 2*M*K + 2*M*N"""
     b = rows * cols * bits / 8.0 + 2.0 * M * cols + 2.0 * M * rows
@@ -155,14 +168,17 @@ def run_reference(args, dims):
             ref.ref_matvec_seconds.argtypes = [C.c_int] * 3
     except Exception:
         ref = None
-    steps = max(1, min(args.steps, 8))
     if ref is not None:
-        t_block = ref.ref_decode_block_seconds(dims["n_embd"], dims["n_ff"], dims["n_head"], dims["n_kv_head"], 128, args.ctx, steps + args.warmup)
+        # a step = ONE decode block (the bounded sample of a token): `warmup` untimed passes, then exactly `steps` timed ones, mean taken
+        ref.ref_decode_block_run.restype = C.c_double
+        ref.ref_decode_block_run.argtypes = [C.c_int] * 8
+        t_block = ref.ref_decode_block_run(dims["n_embd"], dims["n_ff"], dims["n_head"], dims["n_kv_head"], 128, args.ctx, args.warmup, args.steps)
         t_head = ref.ref_matvec_seconds(dims["n_embd"], 151936 // 16, 2) * 16
         tok_s = 1.0 / (dims["n_layer"] * t_block + t_head)
         kind, cores = "reference", os.cpu_count()
-        sample = "1 of %d blocks at ctx %d from oracle/_ref (reference GST_float.cpp primitives, fp32 weights, OpenMP), best of %d; + 1/16 lm_head x16" % (
-            dims["n_layer"], args.ctx, steps)
+        sample = ("each step = 1 of %d blocks at ctx %d from oracle/_ref (reference GST_float.cpp primitives, fp32 weights, OpenMP): mean of %d timed "
+                  "steps after %d warm-up (%.2f ms per block); + 1/16 of the lm_head rows x16 (%.2f ms); extrapolated to one token"
+                  % (dims["n_layer"], args.ctx, args.steps, args.warmup, t_block * 1e3, t_head * 1e3))
     else:
         cb = cpu_baseline(dims, args.ctx)
         tok_s, kind, cores, sample = cb["value"], "port", cb["cores"], cb["sample"]
@@ -212,6 +228,7 @@ def main():
                  "gemv_tma_smem_kb", "deq_fma"):  # tuning experiments only, e.g. KF_ATTN_SPLIT=16
         if os.environ.get("KF_" + knob.upper()):
             ctx.set_int(knob, int(os.environ["KF_" + knob.upper()]))
+    gemv_exact = ctx.get_int("gemv_exact")
     if world > 1:
         ctx.init_tensor_parallel(rank, world, p2p=os.environ.get("KF_P2P", "1") != "0")  # KF_P2P=0: NCCL exchange only, for comparison
 
@@ -349,14 +366,20 @@ def main():
     traffic, traffic_src = None, None
     if world == 1 and args.workload == "qwen3-32b-q4" and not args.layers:
         try:
-            t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_decode.json")))["kernels"]["kf_gemv_kernel"]
-            traffic = t["avg_dram_read_bytes"] + t["avg_dram_write_bytes"]
-            traffic_src = "profiles/r01_traffic_decode.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, avg of %d launches)" % t["launches"]
+            tf = json.load(open(os.path.join(ROOT, TRAFFIC_FILE)))
+            if tf.get("kernel_digest") != kernel_digest() or tf.get("gemv_exact") != gemv_exact:
+                traffic_src = "%s is stale (taken from kernel digest %s / gemv_exact %s, this build is %s / %s): not reported" % (
+                    TRAFFIC_FILE, tf.get("kernel_digest"), tf.get("gemv_exact"), kernel_digest(), gemv_exact)
+            else:
+                t = tf["kernels"]["kf_gemv_kernel"]
+                traffic = t["avg_dram_read_bytes"] + t["avg_dram_write_bytes"]
+                traffic_src = "%s (ncu dram__bytes_read.sum + dram__bytes_write.sum, avg of %d launches, kernel digest %s)" % (
+                    TRAFFIC_FILE, t["launches"], tf["kernel_digest"])
         except Exception:
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
-                "kernel": "kf_gemv_kernel (fused unpack+dequant GEMV, M=1)", "launches_per_step": n_gemv,
+                "kernel": "kf_gemv_kernel (fused unpack+dequant GEMV, M=1, %s)" % ("in-kernel dequant to the reference's bf16 weights" if gemv_exact else "fp16-code tensor-core arithmetic, group affine on fp32 sums"), "launches_per_step": n_gemv,
                 "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_us": per_launch_s * 1e6, "gemv_share_of_step": gemv_ms_pass / ms_step,
                 "peak_source": peak_src, "frac_of_8TBps": achieved / 8000.0,
                 "step_gbps_all_kernels": step_alg_bytes / (ms_step / 1e3) / 1e9, "step_frac_of_peak": step_alg_bytes / (ms_step / 1e3) / 1e9 / peak}
@@ -369,6 +392,7 @@ def main():
             "config": {"workload": "Qwen3-%s decode, batch 1, ctx %d, %s" % (dims_key, args.ctx, args.workload), "model": "Qwen3-" + dims_key,
                        "quantizer": quantizer, "global_batch": 1, "seq_len": args.ctx, "parallelism": "tp%d" % world,
                        "weights": "random-init N(0,0.02^2)-like, quantised at load on the GPU", "lm_head": "bf16",
+                       "gemv_exact": gemv_exact,
                        "l2": "weights per token (%.1f GB) exceed the 126 MB L2; no reuse between steps" % ((alg_bytes + head_bytes) / 1e9),
                        "layers": info.n_layers, "setup_s": round(t_setup, 1)},
             "e2e": {"value": e2e_tok_s, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 151936 * 2 + 4},

@@ -54,6 +54,11 @@ class Context:
     def set_int(self, key, value):
         self.check(self.lib.kf_ctx_set_int(self.h, key.encode(), int(value)), "kf_ctx_set_int")
 
+    def get_int(self, key):
+        v = C.c_int(0)
+        self.check(self.lib.kf_ctx_get_int(self.h, key.encode(), C.byref(v)), "kf_ctx_get_int")
+        return int(v.value)
+
     def init_tensor_parallel(self, rank, world, max_floats=64 * 8192, p2p=True):
         """NCCL communicator + peer-memory exchange buffers for this rank; the ids / IPC handles travel through torch.distributed
         (one process per GPU, process group already initialised)."""

@@ -94,8 +94,10 @@ extern "C" double ref_decode_block_seconds(int E, int F, int H, int KV, int hd, 
      * i.e. it reads numbers as bit patterns; real K/V values would decode to NaN.  The harness therefore stores small positive
      * integers (valid fp16 bit patterns): the arithmetic cost is identical and only time is measured. */
     for (size_t i = 0; i < kc.size(); i++) kc[i] = (__gcc_fp16)(float)(512 + (i % 1024)), vc[i] = (__gcc_fp16)(float)(512 + (i * 7 % 1024));
-    double best = 1e30;
-    for (int it = 0; it < iters + 1; it++) {
+    double best = 1e30, total = 0.0;
+    const bool mean_mode = iters < 0;  /* ref_decode_block_run: |iters| = warmup * 65536 + steps, returns the MEAN of the timed steps */
+    const int warm = mean_mode ? (-iters) >> 16 : 1, timed = mean_mode ? (-iters) & 0xffff : iters;
+    for (int it = 0; it < warm + timed; it++) {
         auto t0 = std::chrono::steady_clock::now();
         rmsnorm(h.data(), x.data(), n1.data(), E, 1e-6f);
         D_matvec(q.data(), h.data(), wq.data(), nullptr, E, QD, dotprod_fp32);
@@ -116,9 +118,18 @@ extern "C" double ref_decode_block_seconds(int E, int F, int H, int KV, int hd, 
         D_matvec(d.data(), g.data(), wd.data(), nullptr, F, E, dotprod_fp32);
         for (int i = 0; i < E; i++) x[i] = 0.5f * x[i] + 0.01f * d[i];
         double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (it > 0 && dt < best) best = dt;  /* first pass is the warm-up */
+        if (it >= warm && dt < best) best = dt;  /* the first pass(es) are the warm-up */
+        if (it >= warm) total += dt;
     }
-    return best;
+    return mean_mode ? total / (timed > 0 ? timed : 1) : best;
+}
+/* bench.py --impl reference: `warmup` untimed passes, then exactly `steps` timed ones; returns their mean duration in seconds */
+extern "C" double ref_decode_block_run(int E, int F, int H, int KV, int hd, int kv_len, int warmup, int steps) {
+    if (warmup < 0) warmup = 0;
+    if (warmup > 32767) warmup = 32767;
+    if (steps < 1) steps = 1;
+    if (steps > 65535) steps = 65535;
+    return ref_decode_block_seconds(E, F, H, KV, hd, kv_len, -((warmup << 16) | steps));
 }
 extern "C" double ref_matvec_seconds(int nIn, int nOut, int iters) {
     std::vector<float> w((size_t)nIn * nOut, 0.01f), x(nIn, 1.f), y(nOut);

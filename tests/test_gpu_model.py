@@ -314,3 +314,92 @@ def test_qwen3_32b_dims_one_layer(ctx):
         want = oracle.forward(tok, 4 + i)
     err, g, w = logits_close(lg[-1], want)
     assert err <= LOGIT_RTOL, err
+
+
+@pytest.mark.parametrize("bits,name", [(2, "ternary"), (1, "binary")])
+def test_qwen3_8b_dims_one_layer_low_bit(ctx, bits, name):
+    # BASELINE configs[3] shapes (Qwen3-8B: E 4096, FFN 12288, H32/KV8, hd 128), every block linear 2-bit ternary / 1-bit (yyang, g=128),
+    # ONE of the 36 layers and a 16 K-row vocabulary: the full-size low-bit GEMV shapes token by token, then a 24-token panel through the
+    # tcgen05 dequant-GEMM, against the oracle
+    model, oracle = build_pair(ctx, n_layer=1, n_embd=4096, n_ff=12288, n_head=32, n_kv_head=8, head_dim=128, vocab=16384, max_seq=64,
+                               attn=(bits, ol.YYANG), mlp=(bits, ol.YYANG), tie=False, norm_sigma=0.0)
+    for wname, wid in (("model.layers.0.mlp.down_proj.weight", 16 + 10), ("model.layers.0.self_attn.q_proj.weight", 17)):
+        assert np.array_equal(model.dequant_tensor(wname).reshape(-1), oracle.weight(wid)), wname
+    toks = prompt(4, 16384)
+    for pos, tok in enumerate(toks):
+        lg, _ = model.forward([tok], [pos])
+        err, g, w = logits_close(lg[0], oracle.forward(tok, pos))
+        assert err <= LOGIT_RTOL, (pos, err)
+    panel = prompt(28, 16384)[4:]
+    lg, _ = model.forward(panel, list(range(4, 28)), seq_mode=0)
+    for i, tok in enumerate(panel):
+        want = oracle.forward(tok, 4 + i)
+    err, g, w = logits_close(lg[-1], want)
+    assert err <= LOGIT_RTOL, err
+
+
+def test_context_512_prefill_then_decode_matches_oracle(ctx):
+    # "ctx 512".  A 500-token prompt through the prefill panels (tcgen05 linears + flash prefill attention), then 24
+    # teacher-forced decode steps across position 512 (split-context decode attention over 500..523 cached rows), every step against the
+    # oracle fed the same 524 tokens one by one.  Qwen3-0.6B head geometry (16 heads / 8 KV heads of 128), two layers.
+    model, oracle = build_pair(ctx, n_layer=2, n_embd=1024, n_ff=3072, n_head=16, n_kv_head=8, head_dim=128, vocab=4096, max_seq=640)
+    toks = prompt(524, 4096)
+    n0 = 500
+    lg, _ = model.prefill(toks[:n0], want_logits=True)
+    for pos in range(n0):
+        want = oracle.forward(toks[pos], pos)
+    err, g, w = logits_close(lg, want)
+    assert err <= LOGIT_RTOL and int(np.argmax(g)) == int(np.argmax(w)), err
+    for pos in range(n0, len(toks)):
+        lg, _ = model.forward([toks[pos]], [pos])
+        err, g, w = logits_close(lg[0], oracle.forward(toks[pos], pos))
+        assert err <= LOGIT_RTOL, (pos, err)
+    for layer in (0, 1):
+        got, want = model.kcache(layer, len(toks), 8 * 128), oracle.kcache(layer, len(toks))
+        d = np.abs(ol.bf16_to_f32(got) - ol.bf16_to_f32(want))
+        assert d.max() <= 2e-2 * np.abs(ol.bf16_to_f32(want)).max()
+
+
+# Full depth: the activations between the 28 layers are bf16, and a different fp32 accumulation order (split-K, MMA fragments against the
+# oracle's sequential loop) flips individual activations by one bf16 ulp (0.4 .. 0.8 % of the value).  Those flips random-walk through the
+# depth: measured rms logit error 7e-3 of the rms logit after 2 layers, 1.4e-2 after 28 (tools/greedy_gate.py ->
+# profiles/r02_greedy_gate.txt), in the bit-faithful arithmetic as well as in the fast one.  The per-layer gate stays 1e-2 (the tests above);
+# the 28-layer gate is the measured worst case (1.8e-2 exact, 2.2e-2 fast) plus a third, and -- the other half of north_star's gate -- top-1
+# agreement at every position where the oracle's best two logits are further apart than DECISIVE_GAP.
+DEEP_RTOL_BY_ARITH = {"exact": 2.5e-2, "fast": 3e-2}
+DECISIVE_GAP = 1.5e-2
+
+
+@pytest.mark.parametrize("theta", [1e6, 1e4])
+def test_qwen3_0p6b_greedy_128_tokens_top1(ctx, theta):
+    # BASELINE configs[0] / SURVEY.md 8(d) config 1 in full: Qwen3-0.6B (28 layers, E 1024, FFN 3072, H16/KV8, hd 128, vocab 151936, tied
+    # bf16 head), 4-bit RTN blocks, seed 42; prompt (1000 + 37 i) mod 151936 for 16 tokens, then 128 greedy tokens chosen by the ORACLE and
+    # teacher-forced into the GPU path.  Gates at every one of the 144 positions: see above.
+    steps = 128 if theta == 1e6 else 32
+    rtol = DEEP_RTOL_BY_ARITH[ctx.arith]
+    model, oracle = build_pair(ctx, n_layer=28, n_embd=1024, n_ff=3072, n_head=16, n_kv_head=8, head_dim=128, vocab=151936, max_seq=512,
+                               theta=theta)
+    toks = prompt(16, 151936)
+    agree = decided = same = 0
+    worst = 0.0
+    pos = 0
+    while pos < len(toks):
+        lg, nxt = model.forward([toks[pos]], [pos], want_logits=True, want_next=True)
+        want = oracle.forward(toks[pos], pos)
+        err, g, w = logits_close(lg[0], want)
+        worst = max(worst, err)
+        assert err <= rtol, (pos, err)
+        assert nxt[0] == int(np.argmax(g))
+        if pos >= 15:
+            top2 = np.sort(w)[-2:]
+            same += int(np.argmax(g) == np.argmax(w))
+            if top2[1] - top2[0] > DECISIVE_GAP * np.abs(w).max():
+                decided += 1
+                agree += int(np.argmax(g) == np.argmax(w))
+            if len(toks) < 16 + steps:
+                toks.append(int(np.argmax(w)))  # the oracle's greedy token
+        pos += 1
+    print("0.6B greedy (%s, theta %g): %d positions, worst logits err %.2e, top-1 equal at %d/%d, decisive %d/%d"
+          % (ctx.arith, theta, pos, worst, same, steps + 1, agree, decided))
+    assert agree == decided and decided >= (steps + 1) // 4
+    assert same >= int(0.95 * (steps + 1))  # undecided positions are near-ties; nearly all still agree

@@ -25,6 +25,9 @@ for n, m in per.items():
     out[n] = {"launches": cnt[n], "avg_us": m['gpu__time_duration.sum'] / cnt[n],
               "avg_dram_read_bytes": m['dram__bytes_read.sum'] / cnt[n], "avg_dram_write_bytes": m['dram__bytes_write.sum'] / cnt[n]}
     print("%-28s n=%4d avg %8.2f us  read %10.3f MB  write %8.3f MB" % (n, cnt[n], out[n]['avg_us'], out[n]['avg_dram_read_bytes'] / 1e6, out[n]['avg_dram_write_bytes'] / 1e6))
-json.dump({"how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum over 2 decode steps of bench.py (KF_PROFILE=1), per launch averages", "kernels": out},
+import os, sys
+sys.path.insert(0, '.')
+import bench
+json.dump({"kernel_digest": bench.kernel_digest(), "gemv_exact": int(os.environ.get("KF_GEMV_EXACT", "0")), "how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum over 2 decode steps of bench.py (KF_PROFILE=1), per launch averages", "kernels": out},
           open('gpurun_out/traffic_decode.json', 'w'), indent=1)
 PY
