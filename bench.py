@@ -224,7 +224,7 @@ def main():
     stream = torch.cuda.Stream()          # a real (non-default) stream: torch events and our kernels share it
     torch.cuda.set_stream(stream)
     ctx = kf.Context(local, stream.cuda_stream)
-    for knob in ("attn_split", "gemv_splitk", "pdl", "gemv_exact", "tc_min_m", "attn_warps", "gemv_cluster", "gqa_min_ctx", "gemv_tma", "gemv_tma_occ",
+    for knob in ("tp_fused", "attn_split", "gemv_splitk", "pdl", "gemv_exact", "tc_min_m", "attn_warps", "gemv_cluster", "gqa_min_ctx", "gemv_tma", "gemv_tma_occ",
                  "gemv_tma_smem_kb", "deq_fma"):  # tuning experiments only, e.g. KF_ATTN_SPLIT=16
         if os.environ.get("KF_" + knob.upper()):
             ctx.set_int(knob, int(os.environ["KF_" + knob.upper()]))

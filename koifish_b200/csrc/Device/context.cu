@@ -134,6 +134,8 @@ extern "C" int kf_ctx_get_int(kf_ctx* ctx, const char* key, int* value_out) {
         *value_out = ctx->gemv_exact;
     else if (!strcmp(key, "gemv_last_s"))
         *value_out = ctx->gemv_last_s;
+    else if (!strcmp(key, "tp_fused"))
+        *value_out = ctx->tp_fused;
     else
         return KF_ERR_BAD_ARG;
     return KF_OK;
@@ -149,6 +151,8 @@ extern "C" int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value) {
         ctx->gemv_cluster = value;
     else if (!strcmp(key, "gemv_exact"))
         ctx->gemv_exact = value;
+    else if (!strcmp(key, "tp_fused"))
+        ctx->tp_fused = value;
     else if (!strcmp(key, "deq_fma"))
         ctx->deq_fma = value ? 1 : 0;
     else if (!strcmp(key, "pdl"))

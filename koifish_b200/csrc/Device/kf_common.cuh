@@ -62,6 +62,9 @@ struct kf_ctx {
     ncclComm* nccl = nullptr;
     int rank = 0, world = 1;
     void* p2p = nullptr;  // peer-memory exchange state (p2p.cu)
+    int tp_fused  = 1;    // knob: the decode exchange rides on the matmul kernels (kf_tp.cuh) when the peer buffers are attached
+    int tp_stride = 256;  // epochs reserved per forward (>= exchanges per forward, even)
+    int tp_xid    = 0;    // ordinal of the next fused exchange of the current forward (kf_tp_begin resets it)
     std::string last_error;
 };
 

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include "kf_common.cuh"
+#include "kf_tp.cuh"
 
 namespace {
 constexpr int kMaxWorld = 8;
@@ -27,6 +28,8 @@ struct P2PState {
     uint8_t* local = nullptr;     // this rank's symmetric buffer
     uint8_t* peer[kMaxWorld] = {};  // every rank's buffer mapped into this process (peer[rank] == local)
     unsigned* epoch = nullptr;    // device counters, one per CTA index
+    size_t ll_off = 0;            // byte offset of the flag-in-data area of the fused exchange (kf_tp.cuh) inside a symmetric buffer
+    unsigned* tok = nullptr;      // device token counter of the fused exchange
 };
 // layout of a symmetric buffer: flags[2][kMaxCtas][kMaxWorld] u32 | data[2][world][nmax] f32
 __host__ __device__ inline size_t p2p_flags_bytes() { return (size_t)2 * kMaxCtas * kMaxWorld * 4; }
@@ -130,11 +133,13 @@ extern "C" int kf_p2p_alloc(kf_ctx* ctx, size_t max_floats, int world, void* han
     kf_p2p_destroy(ctx);
     P2PState* s = new P2PState();
     s->world = world, s->nmax = (max_floats + 3) & ~(size_t)3;
-    const size_t bytes = p2p_flags_bytes() + (size_t)2 * world * s->nmax * 4;
+    s->ll_off          = (p2p_flags_bytes() + (size_t)2 * world * s->nmax * 4 + 255) & ~(size_t)255;
+    const size_t bytes = s->ll_off + kf_tp_ll_bytes(world);
     KF_CUDA(ctx, cudaMalloc(&s->local, bytes));
-    KF_CUDA(ctx, cudaMemset(s->local, 0, bytes));
-    KF_CUDA(ctx, cudaMalloc(&s->epoch, kMaxCtas * 4));
-    KF_CUDA(ctx, cudaMemset(s->epoch, 0, kMaxCtas * 4));
+    KF_CUDA(ctx, cudaMemset(s->local, 0, bytes));  // epoch 0 everywhere: the first exchange is epoch 1
+    KF_CUDA(ctx, cudaMalloc(&s->epoch, kMaxCtas * 4 + 4));
+    KF_CUDA(ctx, cudaMemset(s->epoch, 0, kMaxCtas * 4 + 4));
+    s->tok = s->epoch + kMaxCtas;
     cudaIpcMemHandle_t h;
     KF_CUDA(ctx, cudaIpcGetMemHandle(&h, s->local));
     memcpy(handle_out_64_bytes, &h, 64);
@@ -168,6 +173,54 @@ extern "C" int kf_p2p_release(kf_ctx* ctx) {
     kf_p2p_destroy(ctx);
     return KF_OK;
 }
+// ---- the fused exchange (kf_tp.cuh): view for the matmul kernels, token counter, unpack ------------------------------------------
+int kf_tp_view(kf_ctx* ctx, KfTpView* out) {
+    P2PState* s = state_of(ctx);
+    if (!s || !s->peer[0] || !ctx->tp_fused) return KF_ERR_UNSUPPORTED;
+    memset(out, 0, sizeof(*out));
+    for (int w = 0; w < s->world; w++) out->peer[w] = s->peer[w] + s->ll_off;
+    out->tok = s->tok, out->world = s->world, out->rank = s->rank, out->stride = ctx->tp_stride;
+    return KF_OK;
+}
+namespace {
+__global__ void kf_tp_begin_kernel(unsigned* tok) {
+    kf_grid_dependency_wait();  // the previous forward (its last consumer) is complete
+    *tok = *tok + 1;
+}
+// gather buffer of exchange xid -> plain bf16 (all of it has arrived: the consumer kernels before us polled it; poll anyway, it is free)
+__global__ void __launch_bounds__(256) kf_tp_unpack_kernel(const KfTpView v, int xid, uint16_t* out, size_t n) {
+    kf_grid_dependency_wait();
+    const unsigned e = *reinterpret_cast<const volatile unsigned*>(v.tok) * (unsigned)v.stride + (unsigned)xid + 1u;
+    const uint8_t* g = kftp::gath(v, v.rank, e & 1u);
+    kftp::SpinGuard sg;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (size_t)gridDim.x * blockDim.x * 4)
+        *reinterpret_cast<uint2*>(out + i) = kftp::poll_gath4(g, i, e, sg);
+}
+}  // namespace
+extern "C" int kf_tp_begin(kf_ctx* ctx) {
+    if (!ctx) return KF_ERR_BAD_ARG;
+    P2PState* s = state_of(ctx);
+    ctx->tp_xid = 0;
+    if (!s || !s->peer[0] || !ctx->tp_fused) return KF_OK;  // nothing to advance: the callers take the unfused path
+    KF_CUDA(ctx, kf_launch_pdl(ctx, kf_tp_begin_kernel, dim3(1), dim3(1), 0, s->tok));
+    KF_LAUNCH_CHECK(ctx);
+    return KF_OK;
+}
+extern "C" int kf_exchange_fused_ready(kf_ctx* ctx, int M, int cols) {
+    KfTpView v;
+    return ctx && M >= 1 && M <= 8 && cols % 128 == 0 && (size_t)M * cols <= KF_TP_LL_ELEMS && kf_tp_view(ctx, &v) == KF_OK ? 1 : 0;
+}
+extern "C" int kf_exchange_unpack(kf_ctx* ctx, void* out_bf16, int M, int cols) {
+    if (!ctx || !out_bf16) return KF_ERR_BAD_ARG;
+    KfTpView v;
+    KF_REQUIRE(ctx, kf_tp_view(ctx, &v) == KF_OK && ctx->tp_xid > 0, "no fused exchange has run in this forward");
+    const size_t n = (size_t)M * cols;
+    KF_REQUIRE(ctx, n <= KF_TP_LL_ELEMS && (n & 3) == 0, "M x cols");
+    KF_CUDA(ctx, kf_launch_pdl(ctx, kf_tp_unpack_kernel, dim3((unsigned)((n / 4 + 255) / 256)), dim3(256), 0, v, ctx->tp_xid - 1, (uint16_t*)out_bf16, n));
+    KF_LAUNCH_CHECK(ctx);
+    return KF_OK;
+}
+
 extern "C" int kf_p2p_ready(kf_ctx* ctx) { return ctx && state_of(ctx) && state_of(ctx)->peer[0] ? 1 : 0; }
 
 // out = residual + sum over ranks of partial (both roundings of the single-GPU path); out may alias residual

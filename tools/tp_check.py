@@ -40,8 +40,25 @@ def main():
         ref.init_random()
     toks = [(1000 + 37 * i) % 16384 for i in range(12)]
     worst, ok = 0.0, True
+    fused = ctx.lib.kf_exchange_fused_ready(ctx.h, 1, 1024) == 1
+    if rank == 0:
+        print("tp_check: exchange fused into the O / down epilogues and the QKV / gate-up prologues: %s" % ("yes" if fused else "NO"), flush=True)
+    # (a) the same tokens with the stand-alone exchange kernel (knob tp_fused = 0): the fused path adds the partials in the same rank order
+    #     and rounds at the same points, so the logits must be BIT-identical -- eager, captured graph and replays alike
+    unfused = []
+    ctx.set_int("tp_fused", 0)
+    m0 = kf.Model(ctx, cfg, rank, world)
+    m0.init_random()
+    for pos, tok in enumerate(toks):
+        lg, _ = m0.forward([tok], [pos], want_logits=True)
+        unfused.append(lg[0].copy())
+    lg2u, _ = m0.forward([5, 9], [12, 12], seq_mode=1)
+    m0.close()
+    ctx.set_int("tp_fused", 1)
+    same_bits = True
     for pos, tok in enumerate(toks):
         lg, nx = model.forward([tok], [pos], want_logits=True, want_next=True)
+        same_bits = same_bits and bool(np.array_equal(lg[0], unfused[pos]))
         if rank == 0:
             lr, nr = ref.forward([tok], [pos], want_logits=True, want_next=True)
             a = (lg[0].astype(np.uint32) << 16).view(np.float32)
@@ -50,6 +67,10 @@ def main():
             worst = max(worst, err)
     # batched decode (2 independent sequences) and a prefill panel through the sharded path
     lg2, _ = model.forward([5, 9], [12, 12], seq_mode=1)
+    same_bits = same_bits and bool(np.array_equal(lg2, lg2u))
+    if fused and not same_bits:
+        print("tp_check: rank %d: fused exchange differs from the stand-alone exchange kernel" % rank, flush=True)
+        ok = False
     lgp, _ = model.forward(toks[:8], list(range(20, 28)), seq_mode=0)
     if rank == 0:
         l2, _ = ref.forward([5, 9], [12, 12], seq_mode=1)
@@ -58,10 +79,10 @@ def main():
             a = (x.astype(np.uint32) << 16).view(np.float32)
             b = (y.astype(np.uint32) << 16).view(np.float32)
             worst = max(worst, float(np.abs(a - b).max() / np.abs(b).max()))
-        ok = worst <= 1e-2
+        ok = ok and worst <= 1e-2
         print("tp_check: world %d  worst logits rel err vs TP=1: %.3e  -> %s" % (world, worst, "OK" if ok else "FAIL"), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.broadcast(flag, 0)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     model.close()
     ctx.close()
     dist.destroy_process_group()
