@@ -215,20 +215,16 @@ int kf_p2p_ready(kf_ctx* ctx);
 int kf_p2p_release(kf_ctx* ctx); /* drop the peer buffers: kf_allreduce_residual then takes the NCCL path (all ranks must agree) */
 int kf_allreduce_residual(kf_ctx* ctx, void* out_bf16_dev, const void* residual_bf16_dev, const float* partial_f32_dev, size_t n);
 
-/* ---- the same exchange WITHOUT a launch of its own (kf_tp.cuh): for decode steps of up to 8 tokens it rides on the matmul kernels either
- *      side of it.  kf_linear_exchange = the row-parallel matmul (this rank's K-shard of O / down: SLP::Forw of proj_cat / down,
- *      src/Device/CUDA/QKV.cu:676-688, NeuronFuse.cu:640-652) whose epilogue scatters the fp32 partial rows to the rank that owns the row
- *      block; the owner adds them in rank order, rounds, adds the residual and broadcasts the bf16 rows into every rank's gather buffer
- *      (flag-in-data stores over NVLink: no fence, no separate flag).  residual_plain_dev: bf16 [M][rows], or NULL = the result of the
- *      previous fused exchange of this forward.  kf_rmsnorm_linear_exchanged = kf_rmsnorm_linear whose activations are the result of the
- *      last fused exchange, polled in the kernel's prologue.  kf_tp_begin: first call of every forward on every rank (advances the device
- *      epoch counter, resets the exchange ordinal); kf_exchange_unpack: the result of the last exchange as plain bf16 (final norm / head).
+/* ---- the same exchange WITHOUT a launch of its own (kf_tp.cuh): for decode steps of up to 8 tokens it is the epilogue of the row-parallel
+ *      matmul.  kf_linear_exchange = this rank's K-shard of O / down (SLP::Forw of proj_cat / down followed by the residual add,
+ *      src/Device/CUDA/QKV.cu:676-688, NeuronFuse.cu:640-652): the epilogue pushes the fp32 partial rows into every peer's slot
+ *      (flag-in-data stores over NVLink: no fence, no separate flag), adds the partials of all ranks in rank order, rounds, adds the
+ *      residual and writes y -- y = bf16(residual + bf16(sum over ranks)), identical on every rank; y may alias residual.
+ *      kf_tp_begin: first call of every forward on every rank (advances the device epoch counter, resets the exchange ordinal).
  *      kf_exchange_fused_ready: 1 when the path is available (peer buffers attached, knob tp_fused, M <= 8, M x cols within a slot). */
 int kf_tp_begin(kf_ctx* ctx);
 int kf_exchange_fused_ready(kf_ctx* ctx, int M, int cols);
-int kf_linear_exchange(kf_ctx* ctx, const kf_tensor_desc* w, const void* x_dev, int M, const void* residual_plain_dev);
-int kf_rmsnorm_linear_exchanged(kf_ctx* ctx, int n, void* const* y_dev, const kf_tensor_desc* w, const void* norm_w_dev, float eps, int M, int mode);
-int kf_exchange_unpack(kf_ctx* ctx, void* out_bf16_dev, int M, int cols);
+int kf_linear_exchange(kf_ctx* ctx, void* y_dev, const kf_tensor_desc* w, const void* x_dev, int M, const void* residual_dev);
 
 #ifdef __cplusplus
 }

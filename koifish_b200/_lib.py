@@ -84,9 +84,7 @@ SIGNATURES = {
     "kf_allreduce_residual": (_I, [_P, _P, _P, _P, _SZ]),
     "kf_tp_begin": (_I, [_P]),
     "kf_exchange_fused_ready": (_I, [_P, _I, _I]),
-    "kf_linear_exchange": (_I, [_P, _P, _P, _I, _P]),
-    "kf_rmsnorm_linear_exchanged": (_I, [_P, _I, _P, _P, _P, C.c_float, _I, _I]),
-    "kf_exchange_unpack": (_I, [_P, _P, _I, _I]),
+    "kf_linear_exchange": (_I, [_P, _P, _P, _P, _I, _P]),
     "kf_attn_prefill": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
     "kf_attn_decode_gqa": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _SZ]),
     "kf_qkv_attention": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _SZ, _I]),

@@ -103,11 +103,9 @@ struct GemvParams {
     uint32_t lop_mask, lop_magic;  // code-field mask (0x000F000F / 0x00030003 / 0x00010001) and bf16x2 128.0 (0x43004300)
     float* ws;
     unsigned* cnt;
-    // fused tensor-parallel exchange (kf_tp.cuh): tp_in >= 0 -- x is the result of that exchange (gather buffer); epilogue EPI_TP -- the
-    // result is reduced over the ranks as exchange tp_out, residual from tp_res (plain bf16) or from the gather buffer of tp_out - 1
+    // fused tensor-parallel exchange (kf_tp.cuh), epilogue EPI_TP: y = residual + sum over the ranks of this matmul, as exchange #tp_out
     KfTpView tp;
-    int tp_in, tp_out;
-    const uint16_t* tp_res;
+    int tp_out;
 };
 
 // ---- permuted k-order of the activations inside one thread slot (see header) -------------------------------------------------
@@ -374,33 +372,12 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
     kf_grid_dependency_wait();
 
     // ---- optional fused RMSNorm: the same arithmetic, in the same order, as kf_rmsnorm_kernel (ops.cu) --------------------------
-    // tensor parallel: the activations are the result of exchange tp_in, arriving in this rank's gather buffer from the owners of the
-    // row blocks.  Every CTA polls ALL of it once (inside the sum of squares below, or on its own when there is no norm); after the
-    // barrier that follows, the staging code reads it without checks.
-    const uint8_t* xll = nullptr;
-    unsigned xep       = 0;
-    if (p.tp_in >= 0) {
-        xep = kftp::epoch(p.tp, p.tp_in);
-        xll = kftp::gath(p.tp, p.tp.rank, xep & 1u);
-        if (!p.norm_w) {
-            kftp::SpinGuard sgd;
-            for (size_t i = (size_t)tid * 4; i < (size_t)p.M * p.K; i += kThreads * 4) (void)kftp::poll_gath4(xll, i, xep, sgd);
-            __syncthreads();
-        }
-    }
     if (p.norm_w) {
-        kftp::SpinGuard sgd;
         for (int m = 0; m < p.M; m++) {
             const uint16_t* xr = p.x + (size_t)m * p.K;
             float ss = 0.f;
             for (int i = tid * 8; i < p.K; i += kThreads * 8) {
-                uint4 v;
-                if (xll) {
-                    const uint2 a = kftp::poll_gath4(xll, (size_t)m * p.K + i, xep, sgd), b = kftp::poll_gath4(xll, (size_t)m * p.K + i + 4, xep, sgd);
-                    v = make_uint4(a.x, a.y, b.x, b.y);
-                } else {
-                    v = __ldg(reinterpret_cast<const uint4*>(xr + i));
-                }
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + i));
                 const uint32_t q[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -425,13 +402,7 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
                 const uint4* gp = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + k0);
 #pragma unroll
                 for (int i = 0; i < KT / 8; i++) {
-                    uint4 v;
-                    if (xll) {
-                        const uint2 a = kftp::read_gath4(xll, (size_t)m * p.K + k0 + 8 * i), b = kftp::read_gath4(xll, (size_t)m * p.K + k0 + 8 * i + 4);
-                        v = make_uint4(a.x, a.y, b.x, b.y);
-                    } else {
-                        v = __ldg(gp + i);
-                    }
+                    uint4 v = __ldg(gp + i);
                     src[4 * i + 0] = v.x, src[4 * i + 1] = v.y, src[4 * i + 2] = v.z, src[4 * i + 3] = v.w;
                 }
                 if (p.norm_w) {  // (x * s) * w, rounded to bf16 like the stand-alone kernel's output
@@ -728,22 +699,24 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
 
     // ---- epilogue -----------------------------------------------------------------------------------------------------------
     if (p.epilogue == EPI_TP) {
-        // fused tensor-parallel exchange (kf_tp.cuh): scatter the fp32 tile to the owner of this row block; the owner adds the `world`
-        // partials in rank order, applies the two roundings of the single-GPU epilogue (bf16 of the matmul, bf16 of residual + that) and
-        // broadcasts the bf16 rows to every rank's gather buffer.  Flag-in-data: each 8 bytes carry their epoch.
-        const int E = p.seg[0].rows, rbase = rb * ROWS, W = p.tp.world, me = p.tp.rank, owner = rb % W;
+        // fused tensor-parallel exchange (kf_tp.cuh): push the fp32 rows of this tile into slot [rank] of EVERY peer, then add the `world`
+        // partials of the row block in rank order (every rank does, with identical results), apply the two roundings of the single-GPU
+        // epilogue (bf16 of the matmul, bf16 of residual + that) and write the rows of y -- the next kernel of the stream reads plain
+        // activations and knows nothing of the exchange.  Flag-in-data: each 8 bytes that cross NVLink carry their epoch.
+        const GemvSeg& sg = p.seg[0];
+        const int E = sg.rows, rbase = rb * ROWS, W = p.tp.world, me = p.tp.rank;
         const unsigned e = kftp::epoch(p.tp, p.tp_out), par = e & 1u;
         constexpr int HP = ROWS / 2;  // row pairs of the tile
-        if (owner != me) {
-            uint8_t* dst = kftp::scat(p.tp, owner, par, me);
-            for (int idx = tid; idx < p.M * HP; idx += kThreads) {
-                const int m = idx / HP, r = (idx % HP) * 2, row = rbase + r;
-                if (row >= E) continue;
-                kftp::st16_sys(dst + ((size_t)m * E + row) * 8, __float_as_uint(tile[m * TS + r]), e, __float_as_uint(tile[m * TS + r + 1]), e);
+        for (int idx = tid; idx < p.M * HP; idx += kThreads) {
+            const int m = idx / HP, r = (idx % HP) * 2, row = rbase + r;
+            if (row >= E) continue;
+            const size_t off   = ((size_t)m * E + row) * 8;
+            const uint32_t v0 = __float_as_uint(tile[m * TS + r]), v1 = __float_as_uint(tile[m * TS + r + 1]);
+            for (int w = 1; w < W; w++) {
+                const int peer = me + w < W ? me + w : me + w - W;  // everybody starts at a different peer
+                kftp::st16_sys(kftp::scat(p.tp, peer, par, me) + off, v0, e, v1, e);
             }
-            return;
         }
-        const uint8_t* resll = p.tp_res ? nullptr : kftp::gath(p.tp, me, par ^ 1u);
         kftp::SpinGuard sgd;
         for (int idx = tid; idx < p.M * HP; idx += kThreads) {
             const int m = idx / HP, r = (idx % HP) * 2, row = rbase + r;
@@ -767,16 +740,9 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
                 }
                 a0 += __uint_as_float(v[w].x), a1 += __uint_as_float(v[w].z);
             }
-            uint32_t rp;
-            if (p.tp_res)
-                rp = *reinterpret_cast<const uint32_t*>(p.tp_res + el);
-            else
-                asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(rp) : "l"(resll + (el >> 1) * 8) : "memory");
-            const uint32_t o = pack_bf16x2(bf16lo(rp) + bf16_bits_to_f32(f32_to_bf16_bits(a0)), bf16hi(rp) + bf16_bits_to_f32(f32_to_bf16_bits(a1)));
-            for (int w = 0; w < W; w++) {
-                const int peer = me + w < W ? me + w : me + w - W;  // everybody starts at a different peer
-                kftp::st8_sys(kftp::gath(p.tp, peer, par) + (el >> 1) * 8, o, e);
-            }
+            const uint32_t rp = *reinterpret_cast<const uint32_t*>(p.residual + el);
+            *reinterpret_cast<uint32_t*>(sg.y + el) =
+                pack_bf16x2(bf16lo(rp) + bf16_bits_to_f32(f32_to_bf16_bits(a0)), bf16hi(rp) + bf16_bits_to_f32(f32_to_bf16_bits(a1)));
         }
         return;
     }
@@ -894,8 +860,8 @@ int launch_nt(kf_ctx* ctx, const GemvParams& p, int rt) {
 }
 
 int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
-                  const void* norm_w, float norm_eps, const KfTpCall* tp = nullptr) {
-    KF_REQUIRE(ctx, n >= 1 && n <= 3 && M >= 1 && M <= 64 && (x || (tp && tp->xid_in >= 0)), "1..3 weights, 1..64 tokens");
+                  const void* norm_w, float norm_eps, int xid_out = -1) {
+    KF_REQUIRE(ctx, n >= 1 && n <= 3 && M >= 1 && M <= 64 && x, "1..3 weights, 1..64 tokens");
     const int type = w[0].type, K = w[0].cols;
     int fmt, mode;
     switch (type) {
@@ -915,26 +881,19 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     p.steps_total = K / KSTEP, p.qbias = w[0].qbias, p.epilogue = epilogue;
     p.lop_mask = fmt == FMT_Q4 ? 0x000F000Fu : fmt == FMT_Q2 ? 0x00030003u : 0x00010001u;
     p.lop_magic = mode == MODE_FAST ? 0x64006400u : 0x43004300u;  // fp16x2 1024.0 / bf16x2 128.0
-    p.tp_in = p.tp_out = -1;
-    if (tp && (tp->xid_in >= 0 || tp->xid_out >= 0)) {
+    p.tp_out = -1;
+    if (xid_out >= 0) {
         KF_REQUIRE(ctx, kf_tp_view(ctx, &p.tp) == KF_OK, "fused exchange: peer buffers not attached");
-        KF_REQUIRE(ctx, M <= 8 && tp->xid_in < p.tp.stride && tp->xid_out < p.tp.stride, "fused exchange: M <= 8, ordinal < stride");
-        if (tp->xid_in >= 0) {
-            KF_REQUIRE(ctx, (size_t)M * K <= KF_TP_LL_ELEMS, "fused exchange: M x K too large");
-            p.tp_in = tp->xid_in;
-        }
-        if (tp->xid_out >= 0) {
-            KF_REQUIRE(ctx, n == 1 && epilogue == EPI_TP && (size_t)M * w[0].rows <= KF_TP_LL_ELEMS && (tp->res_plain || tp->xid_out > 0),
-                       "fused exchange: one weight, M x rows within the slot, a residual");
-            p.tp_out = tp->xid_out, p.tp_res = (const uint16_t*)tp->res_plain;
-        }
+        KF_REQUIRE(ctx, M <= 8 && xid_out < p.tp.stride && n == 1 && epilogue == EPI_TP && residual && (size_t)M * w[0].rows <= KF_TP_LL_ELEMS,
+                   "fused exchange: one weight, <= 8 tokens, M x rows within a slot, a residual");
+        p.tp_out = xid_out;
     }
     KF_REQUIRE(ctx, (epilogue == EPI_TP) == (p.tp_out >= 0), "fused exchange epilogue");
     int total_rows = 0;
     for (int i = 0; i < n; i++) {
         KF_REQUIRE(ctx, w[i].type == type && w[i].cols == K && w[i].qbias == w[0].qbias && w[i].group == w[0].group,
                    "fused weights must share type / K / quant card");
-        KF_REQUIRE(ctx, w[i].rows % 16 == 0 && w[i].rows >= 16 && w[i].data_dev && (y[i] || epilogue == EPI_TP), "rows must be a multiple of 16");
+        KF_REQUIRE(ctx, w[i].rows % 16 == 0 && w[i].rows >= 16 && w[i].data_dev && y[i], "rows must be a multiple of 16");
         if (mode != MODE_PLAIN)
             KF_REQUIRE(ctx, kf_has_gama(w[i]) && w[i].group >= 128 && (w[i].group & (w[i].group - 1)) == 0 && K % w[i].group == 0,
                        "fused path needs group = 128 * 2^n dividing K");
@@ -1044,37 +1003,13 @@ int kf_gemv_small(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     return gemv_dispatch(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
 }
 
-// ---- tensor-parallel decode with the exchange fused into the matmuls either side of it (kf_tp.cuh) ------------------------------
-// kf_linear_exchange: row-parallel matmul (this rank's K-shard of O / down) whose epilogue reduces the partials over the ranks, adds the
-// residual and leaves the new activations in every rank's gather buffer.  residual_plain: bf16 [M][rows], or null = the result of the
-// previous fused exchange of this forward.
-extern "C" int kf_linear_exchange(kf_ctx* ctx, const kf_tensor_desc* w, const void* x, int M, const void* residual_plain) {
-    if (!ctx || !w || !x) return KF_ERR_BAD_ARG;
-    KfTpCall tp;
-    tp.xid_out = ctx->tp_xid, tp.res_plain = residual_plain;
-    void* ys[1] = {nullptr};
-    const int rc = gemv_dispatch(ctx, 1, ys, w, x, M, EPI_TP, nullptr, nullptr, 0.f, &tp);
+// ---- tensor-parallel decode: the row-parallel matmul (this rank's K-shard of O / down) whose epilogue IS the exchange (kf_tp.cuh) -----
+// y = bf16(residual + bf16(sum over the ranks of x . w^T)), identical on every rank; y may alias residual.  Exchange ordinal = calls since
+// kf_tp_begin on this context (every rank issues the same sequence).
+extern "C" int kf_linear_exchange(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* x, int M, const void* residual) {
+    if (!ctx || !y || !w || !x || !residual) return KF_ERR_BAD_ARG;
+    void* ys[1]  = {y};
+    const int rc = gemv_dispatch(ctx, 1, ys, w, x, M, EPI_TP, residual, nullptr, 0.f, ctx->tp_xid);
     if (rc == KF_OK) ctx->tp_xid++;
     return rc;
-}
-// kf_rmsnorm_linear_exchanged: kf_rmsnorm_linear whose activations are the result of the last fused exchange (polled in the prologue of
-// the kernel).  mode: 0 = n plain outputs, 2 = SwiGLU(w[0] gate, w[1] up) -> y[0].  Weights of different storage types take one launch each.
-extern "C" int kf_rmsnorm_linear_exchanged(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* norm_w, float eps, int M, int mode) {
-    if (!ctx || !y || !w || !norm_w) return KF_ERR_BAD_ARG;
-    KF_REQUIRE(ctx, (mode == 0 || mode == 2) && M >= 1 && M <= 8 && n >= 1 && n <= 3 && ctx->tp_xid > 0, "mode / M / n / no exchange to consume");
-    KfTpCall tp;
-    tp.xid_in = ctx->tp_xid - 1;
-    bool same = true;
-    for (int i = 1; i < n; i++) same = same && w[i].type == w[0].type && w[i].cols == w[0].cols && w[i].group == w[0].group && w[i].qbias == w[0].qbias;
-    if (mode == 2) {
-        KF_REQUIRE(ctx, n == 2 && same, "swiglu takes gate and up of one storage type");
-        void* ys[2] = {y[0], y[0]};
-        return gemv_dispatch(ctx, 2, ys, w, nullptr, M, EPI_SWIGLU, nullptr, norm_w, eps, &tp);
-    }
-    if (same) return gemv_dispatch(ctx, n, y, w, nullptr, M, EPI_NONE, nullptr, norm_w, eps, &tp);
-    for (int i = 0; i < n; i++) {
-        const int rc = gemv_dispatch(ctx, 1, &y[i], &w[i], nullptr, M, EPI_NONE, nullptr, norm_w, eps, &tp);
-        if (rc) return rc;
-    }
-    return KF_OK;
 }

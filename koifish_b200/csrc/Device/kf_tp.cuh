@@ -5,18 +5,17 @@
 // kernels either side of it, in the flag-in-data ("LL") style: every 8 bytes that cross NVLink carry 4 bytes of payload and the 4-byte
 // epoch of the exchange, so that a reader polls the data itself -- one NVLink traversal, no fence, no separate flag.
 //
-//   producer  (epilogue of the O / down GEMV, the CTA that holds the final fp32 tile of row block rb):
-//     scatter : store the tile into slot [rank] of the OWNER of the row block (owner = rb mod world) -- {v0, e, v1, e} 16-byte stores;
-//     reduce  : on the owner, poll the `world` slots of that row block, add them in RANK ORDER, round to bf16, add the residual, round
-//               (the two roundings of the single-GPU epilogue), and
-//     gather  : broadcast the bf16 result to EVERY rank's gather buffer -- {bf16x2, e} 8-byte stores.
-//   consumer  (prologue of the next QKV / gate-up GEMV, every CTA): poll the local gather buffer while computing the RMSNorm sum of
-//               squares, then stage its k-slice from it.  The residual stream of a decode step therefore lives in the gather buffers
-//               (two parities, alternating by exchange); kf_exchange_unpack copies it out for the final norm.
+//   epilogue of the O / down GEMV, the CTA that holds the final fp32 tile of row block rb, on EVERY rank:
+//     push   : store the tile into slot [rank] of every peer -- {v0, e, v1, e} 16-byte stores, each 8-byte half self-validating;
+//     reduce : poll the `world - 1` remote slots of that row block in local memory, add the partials in RANK ORDER (bit-identical on
+//              every rank), round to bf16, add the residual, round (the two roundings of the single-GPU epilogue), write the rows of y.
+//   The next kernel of the stream (RMSNorm + QKV / gate-up) reads plain activations after its griddepcontrol.wait and knows nothing of
+//   the exchange: one NVLink traversal per exchange, no launch, no fence, no flag, no extra pass over the activations.
 //
 // Epoch of an exchange = token counter * stride + ordinal + 1: the token counter sits in device memory and is advanced by kf_tp_begin
-// (one thread, first kernel of a forward), the ordinal is baked into the launch -- CUDA-graph replayable.  Two parities suffice: a rank
-// pushes exchange e + 1 only after it consumed e, i.e. after EVERY rank pushed e and every owner finished reading e - 1's slots.
+// (one thread, first kernel of a forward), the ordinal is baked into the launch -- CUDA-graph replayable.  Two parities suffice: a peer
+// writes exchange e + 2 into the slots of e only after its epilogue of e + 1 completed, which needed OUR partial of e + 1, which our
+// stream issues after every CTA of our epilogue of e has finished reading.
 #pragma once
 #include "kf_common.cuh"
 
@@ -28,16 +27,8 @@ struct KfTpView {                     // by-value kernel parameter
     const unsigned* tok;              // device token counter
     int world, rank, stride;          // stride: epochs reserved per token (>= exchanges per token, even)
 };
-// LL area: scat[2][world][LL_ELEMS] x {f32, epoch} | gath[2][LL_ELEMS / 2] x {bf16x2, epoch}
-__host__ __device__ inline size_t kf_tp_scat_bytes(int world) { return (size_t)2 * world * KF_TP_LL_ELEMS * 8; }
-__host__ __device__ inline size_t kf_tp_ll_bytes(int world) { return kf_tp_scat_bytes(world) + (size_t)2 * (KF_TP_LL_ELEMS / 2) * 8; }
-
-// the fused-exchange roles of one GEMV launch (all -1 / null: an ordinary launch)
-struct KfTpCall {
-    int xid_out = -1;                 // >= 0: the result is reduced over the ranks as exchange #xid_out (epilogue)
-    int xid_in  = -1;                 // >= 0: the activations are the result of exchange #xid_in (prologue)
-    const void* res_plain = nullptr;  // producer: residual as plain bf16 [M][rows]; null = the result of exchange xid_out - 1
-};
+// LL area: scat[2 parities][world][LL_ELEMS] x {f32, epoch}
+__host__ __device__ inline size_t kf_tp_ll_bytes(int world) { return (size_t)2 * world * KF_TP_LL_ELEMS * 8; }
 // p2p.cu
 int kf_tp_view(kf_ctx* ctx, KfTpView* out);  // KF_OK when the fused exchange is available on this context
 
@@ -45,9 +36,6 @@ int kf_tp_view(kf_ctx* ctx, KfTpView* out);  // KF_OK when the fused exchange is
 namespace kftp {
 __device__ __forceinline__ void st16_sys(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void st8_sys(void* p, uint32_t a, uint32_t b) {
-    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ uint4 ld16_sys(const void* p) {
     uint4 v;
@@ -60,9 +48,6 @@ __device__ __forceinline__ unsigned epoch(const KfTpView& v, int xid) {
 }
 __device__ __forceinline__ uint8_t* scat(const KfTpView& v, int dst_rank, unsigned parity, int src_rank) {
     return v.peer[dst_rank] + ((size_t)(parity * v.world + src_rank) * KF_TP_LL_ELEMS) * 8;
-}
-__device__ __forceinline__ uint8_t* gath(const KfTpView& v, int dst_rank, unsigned parity) {
-    return v.peer[dst_rank] + kf_tp_scat_bytes(v.world) + (size_t)parity * (KF_TP_LL_ELEMS / 2) * 8;
 }
 // a lost peer fails the launch instead of hanging the GPU: wall-clock bound on every poll loop (ranks may be seconds apart at the first
 // exchange, e.g. while one of them still quantises its shard)
@@ -78,20 +63,5 @@ struct SpinGuard {
         }
     }
 };
-// 4 consecutive bf16 of the gather buffer (element index i0, a multiple of 4) once both halves carry epoch e
-__device__ __forceinline__ uint2 poll_gath4(const uint8_t* g, size_t i0, unsigned e, SpinGuard& sg) {
-    const uint8_t* p = g + (i0 >> 1) * 8;
-    uint4 v          = ld16_sys(p);
-    while (v.y != e || v.w != e) {
-        sg.tick();
-        v = ld16_sys(p);
-    }
-    return make_uint2(v.x, v.z);
-}
-// the same without the poll: the caller has already seen epoch e on these bytes (or on all of the buffer)
-__device__ __forceinline__ uint2 read_gath4(const uint8_t* g, size_t i0) {
-    const uint4 v = ld16_sys(g + (i0 >> 1) * 8);
-    return make_uint2(v.x, v.z);
-}
 }  // namespace kftp
 #endif

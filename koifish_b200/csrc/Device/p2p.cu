@@ -187,15 +187,6 @@ __global__ void kf_tp_begin_kernel(unsigned* tok) {
     kf_grid_dependency_wait();  // the previous forward (its last consumer) is complete
     *tok = *tok + 1;
 }
-// gather buffer of exchange xid -> plain bf16 (all of it has arrived: the consumer kernels before us polled it; poll anyway, it is free)
-__global__ void __launch_bounds__(256) kf_tp_unpack_kernel(const KfTpView v, int xid, uint16_t* out, size_t n) {
-    kf_grid_dependency_wait();
-    const unsigned e = *reinterpret_cast<const volatile unsigned*>(v.tok) * (unsigned)v.stride + (unsigned)xid + 1u;
-    const uint8_t* g = kftp::gath(v, v.rank, e & 1u);
-    kftp::SpinGuard sg;
-    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (size_t)gridDim.x * blockDim.x * 4)
-        *reinterpret_cast<uint2*>(out + i) = kftp::poll_gath4(g, i, e, sg);
-}
 }  // namespace
 extern "C" int kf_tp_begin(kf_ctx* ctx) {
     if (!ctx) return KF_ERR_BAD_ARG;
@@ -210,17 +201,6 @@ extern "C" int kf_exchange_fused_ready(kf_ctx* ctx, int M, int cols) {
     KfTpView v;
     return ctx && M >= 1 && M <= 8 && cols % 128 == 0 && (size_t)M * cols <= KF_TP_LL_ELEMS && kf_tp_view(ctx, &v) == KF_OK ? 1 : 0;
 }
-extern "C" int kf_exchange_unpack(kf_ctx* ctx, void* out_bf16, int M, int cols) {
-    if (!ctx || !out_bf16) return KF_ERR_BAD_ARG;
-    KfTpView v;
-    KF_REQUIRE(ctx, kf_tp_view(ctx, &v) == KF_OK && ctx->tp_xid > 0, "no fused exchange has run in this forward");
-    const size_t n = (size_t)M * cols;
-    KF_REQUIRE(ctx, n <= KF_TP_LL_ELEMS && (n & 3) == 0, "M x cols");
-    KF_CUDA(ctx, kf_launch_pdl(ctx, kf_tp_unpack_kernel, dim3((unsigned)((n / 4 + 255) / 256)), dim3(256), 0, v, ctx->tp_xid - 1, (uint16_t*)out_bf16, n));
-    KF_LAUNCH_CHECK(ctx);
-    return KF_OK;
-}
-
 extern "C" int kf_p2p_ready(kf_ctx* ctx) { return ctx && state_of(ctx) && state_of(ctx)->peer[0] ? 1 : 0; }
 
 // out = residual + sum over ranks of partial (both roundings of the single-GPU path); out may alias residual

@@ -101,10 +101,7 @@ int SelfAttention::cuInfer(void* inpL, int M) {
     kf_tensor_desc w3[3] = {Q.w->Desc(), K.w->Desc(), V.w->Desc()};
     void* y3[3]          = {f->q, f->k, f->v};
     // norm.cuFlow + the three SLP::Forw calls share one launch; the normalised activations never leave the chip
-    if (f->tp_fuse && f->x_exchanged)  // the activations arrive in the gather buffer of the previous block's exchange: polled in the prologue
-        KF_TRY(kf_rmsnorm_linear_exchanged(f->ctx, 3, y3, w3, norm.w->data, norm.rms_eps, M, 0));
-    else
-        KF_TRY(kf_rmsnorm_linear(f->ctx, 3, y3, w3, inpL, norm.w->data, norm.rms_eps, M, 0));
+    KF_TRY(kf_rmsnorm_linear(f->ctx, 3, y3, w3, inpL, norm.w->data, norm.rms_eps, M, 0));
     const int lay   = layid - 1;
     const size_t ss = f->seq_mode ? f->cache.seq_stride() : 0;
     int gqa_min_ctx = 1024;
@@ -136,8 +133,7 @@ int SelfAttention::cuInfer(void* inpL, int M) {
         KF_TRY(proj_cat.Forw(inpL, f->att, M, KF_EPI_RESIDUAL, inpL));  // out = residual + proj (CU_add3, QKV.cu:682-688)
     } else if (f->tp_fuse) {  // row-parallel, the exchange + residual add in the epilogue of the matmul (kf_tp.cuh): no launch of its own
         kf_tensor_desc d = proj_cat.w->Desc();
-        KF_TRY(kf_linear_exchange(f->ctx, &d, f->att, M, f->x_exchanged ? nullptr : inpL));
-        f->x_exchanged = true;
+        KF_TRY(kf_linear_exchange(f->ctx, inpL, &d, f->att, M, inpL));
     } else {  // row-parallel: fp32 partial sums -> all-reduce over NVLink -> residual add
         KF_TRY(proj_cat.Forw(f->part_f32, f->att, M, KF_EPI_F32, nullptr));
         KF_TRY(kf_allreduce_residual(f->ctx, inpL, inpL, f->part_f32, nE));  // one launch over NVLink peer memory (p2p.cu); NCCL fallback
@@ -150,17 +146,13 @@ int FFN::cuInfer(void* inpL, int M) {
     std::string* hFishErr = &f->error;
     kf_tensor_desc gu[2] = {gate.w->Desc(), up.w->Desc()};
     void* y2[2]          = {f->hb, f->hb};
-    if (f->tp_fuse && f->x_exchanged)
-        KF_TRY(kf_rmsnorm_linear_exchanged(f->ctx, 2, y2, gu, norm.w->data, norm.rms_eps, M, 2));
-    else
-        KF_TRY(kf_rmsnorm_linear(f->ctx, 2, y2, gu, inpL, norm.w->data, norm.rms_eps, M, 2));  // norm + gate/up + SwiGLU in one launch
+    KF_TRY(kf_rmsnorm_linear(f->ctx, 2, y2, gu, inpL, norm.w->data, norm.rms_eps, M, 2));  // norm + gate/up + SwiGLU in one launch
     const size_t nE = (size_t)M * f->config.n_embd;
     if (f->tp_world == 1) {
         KF_TRY(down.Forw(inpL, f->hb, M, KF_EPI_RESIDUAL, inpL));
     } else if (f->tp_fuse) {
         kf_tensor_desc d = down.w->Desc();
-        KF_TRY(kf_linear_exchange(f->ctx, &d, f->hb, M, f->x_exchanged ? nullptr : inpL));
-        f->x_exchanged = true;
+        KF_TRY(kf_linear_exchange(f->ctx, inpL, &d, f->hb, M, inpL));
     } else {
         KF_TRY(down.Forw(f->part_f32, f->hb, M, KF_EPI_F32, nullptr));
         KF_TRY(kf_allreduce_residual(f->ctx, inpL, inpL, f->part_f32, nE));  // one launch over NVLink peer memory (p2p.cu); NCCL fallback
@@ -443,27 +435,17 @@ hGTensor Fish::GetTensor(const std::string& name) const {
 // Fish::ForwardOnRLS (reference src/Manifold/gLLM.cpp:755-769): run every neuron's cuInfer in graph order
 int Fish::ForwardOnRLS(int M, bool want_logits) {
     std::string* hFishErr = &error;
-    // tensor-parallel decode of up to 8 tokens: the exchange after O / down rides on the matmul kernels either side of it (5 launches per
-    // block instead of 7); the residual stream then lives in the exchange's gather buffers until it is unpacked for the final norm
-    x_exchanged = false;
-    tp_fuse     = false;
+    // tensor-parallel decode of up to 8 tokens: the exchange after O / down is the epilogue of those matmuls (kf_tp.cuh): 5 launches
+    // per block instead of 7
+    tp_fuse = false;
     if (tp_world > 1) {
         KF_TRY(kf_tp_begin(ctx));
-        tp_fusable = true;
-        for (auto& m : ffn) {
-            const kf_tensor_desc g = m->gate.w->Desc(), u = m->up.w->Desc();
-            tp_fusable = tp_fusable && g.type == u.type && g.group == u.group && g.qbias == u.qbias;
-        }
-        tp_fuse = tp_fusable && 2 * (int)attn.size() <= 256 && kf_exchange_fused_ready(ctx, M, config.n_embd) == 1;
+        tp_fuse = 2 * (int)attn.size() <= 256 && kf_exchange_fused_ready(ctx, M, config.n_embd) == 1;
     }
     KF_TRY(embed.cuInfer(x, M));
     for (size_t l = 0; l < attn.size(); l++) {
         KF_TRY(attn[l]->cuInfer(x, M));
         KF_TRY(ffn[l]->cuInfer(x, M));
-    }
-    if (x_exchanged) {
-        KF_TRY(kf_exchange_unpack(ctx, x, M, config.n_embd));
-        x_exchanged = false;
     }
     if (want_logits) {
         if (last_only)  // prefill: only the last token of the panel feeds the sampler

@@ -129,9 +129,7 @@ struct Fish {
     int logit_rows = 0;           // rows of the logits buffers (max(64, max_batch)); bigger panels report the last token only
     bool panel_consecutive = false;  // prefill panel at positions pos[0] .. pos[0] + M - 1 -> tensor-core flash attention
     bool last_only = false;       // mode 2: logits / argmax of the last token of the panel only
-    bool tp_fusable = true;       // every gate / up pair shares one storage type (the fused exchange's consumer takes them in one launch)
-    bool tp_fuse = false;         // this forward runs the fused exchange (tensor parallel, <= 8 tokens, peer buffers attached)
-    bool x_exchanged = false;     // the residual stream currently lives in the gather buffer of the last fused exchange
+    bool tp_fuse = false;         // this forward runs the exchange as the epilogue of O / down (tensor parallel, <= 8 tokens, peer buffers)
     int attn_hint = 0;            // upper bound of the positions of the current forward (power-of-two bucket - 1): sizes the attention split
     int CtxBucket() const;        // log2 of that bucket; part of the graph key, so graphs are re-captured as the context grows
     std::map<int, kf_graph*> graphs;  // per (M, mode) replayable token graphs

@@ -42,7 +42,7 @@ def main():
     worst, ok = 0.0, True
     fused = ctx.lib.kf_exchange_fused_ready(ctx.h, 1, 1024) == 1
     if rank == 0:
-        print("tp_check: exchange fused into the O / down epilogues and the QKV / gate-up prologues: %s" % ("yes" if fused else "NO"), flush=True)
+        print("tp_check: exchange fused into the O / down epilogues: %s" % ("yes" if fused else "NO"), flush=True)
     # (a) the same tokens with the stand-alone exchange kernel (knob tp_fused = 0): the fused path adds the partials in the same rank order
     #     and rounds at the same points, so the logits must be BIT-identical -- eager, captured graph and replays alike
     unfused = []
