@@ -32,13 +32,16 @@ namespace {
 
 enum { FMT_BF16 = 0, FMT_F8 = 1, FMT_Q4 = 2, FMT_Q2 = 3, FMT_Q1 = 4 };
 enum { MODE_PLAIN = 0, MODE_AFFINE = 1, MODE_AFFINE_SYM = 2, MODE_SCALE = 3, MODE_FACTOR = 4, MODE_AFFINE_FMA = 5, MODE_FAST = 6 };
-// MODE_FAST (4-bit, the DEFAULT for decode: ctx knob gemv_exact = 0): the codes go to the tensor cores as fp16 numbers 1024 + c and
-// 1024 + 16 c, each built with ONE LOP3 (both nibbles of a byte sit inside fp16's 10 mantissa bits; one byte permute per 8 codes replaces
-// the six funnel shifts of the bf16 forms -- a funnel shift costs ~5 clk per warp instruction and scheduler on B200, tools/ubench/deq_rate2.cu:
-// 105-160 clk per [128 x 128] tile against 335 for MODE_FACTOR and 432 for the bit-exact forms, which is MORE than the tile's bytes take at
-// the HBM rate).  The group's step / zero / code bias are applied to the fp32 group sums, y += step * (sum c x - qbias Sx) - zero Sx:
-// the reference's affine dequant without its per-weight bf16 rounding.  Activations are staged as fp16 with a power-of-two scale per
-// 128-k group (exact for bf16 inputs within 2^27 of the group's largest magnitude).
+// MODE_FAST (4 / 2 / 1-bit, the DEFAULT for decode: ctx knob gemv_exact = 0): the codes go to the tensor cores as fp16 SUBNORMALS.  A code
+// field that lies inside the low 10 bits of a 16-bit half IS the fp16 number c * 2^b * 2^-24 (exponent field 0: no implicit one, no offset to
+// cancel), so ONE LOP3 (`word & mask`, mask an immediate) turns two packed codes into an MMA operand pair; the fields above bit 9 come down
+// with one byte permute (>> 8) per register.  mma.sync handles fp16 subnormals exactly (tools/ubench/hmma_subnormal.cu).  The activation that
+// meets the field at bit b is staged as fp16 x * 2^-b (exact), with a power-of-two scale per 128-k group that puts the group's largest
+// magnitude in [2^13, 2^14).  Per weight that is 0.56 .. 0.62 integer-pipe instructions instead of 3 (shift + LOP3 + bf16 subtract of the
+// bf16 forms; a funnel shift alone costs ~5 clk per warp instruction and scheduler on B200, tools/ubench/deq_rate2.cu: the bit-exact forms
+// need 432 clk per [128 x 128] tile, MORE than the tile's bytes take at the HBM rate).  The group's step / zero / code bias are applied to
+// the fp32 group sums, y += step * (sum c x - qbias Sx) - zero Sx: the reference's affine dequant without its per-weight bf16 rounding (for
+// the yyang ternary / binary types, whose weights step * k are exact in bf16, that is the SAME arithmetic as the reference's).
 // MODE_AFFINE / MODE_AFFINE_SYM: the reference's dequant with TWO bf16 roundings (ctx knob deq_fma = 0) ; MODE_AFFINE_FMA: with ONE
 // (fma.rn.bf16, the default: what the reference's kernel computes when built for sm_90+, see kf_common.cuh deq_fma)
 // MODE_FACTOR (opt-in, ctx knob gemv_exact = 0): A = 128 + code, un-dequantised; per group y += step*(acc_g - (128+qbias)*Sx) - zero*Sx with
@@ -131,12 +134,22 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// (a & IMM) | 0x64006400 (fp16x2 1024.0) in ONE LOP3 with the mask as an immediate
-template <uint32_t IMM>
-__device__ __forceinline__ uint32_t and_or_1024(uint32_t a, uint32_t magic) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "n"(IMM), "r"(magic));
-    return d;
+// MODE_FAST: bit position (inside each 16-bit half of a packed register) of the code that feeds MMA slot j = 2h + {0: a[0]/a[1], 1: a[2]/a[3]}
+// of unit u, and the exponent of the fp16 subnormal it becomes (fields whose top bit lies above bit 9 are used from the register >> 8)
+template <int BITS>
+__host__ __device__ constexpr int fast_bit(int u, int j) {
+    return BITS == 4 ? 8 * (j >> 1) + 4 * (j & 1) : BITS == 2 ? 8 * (u & 1) + 4 * (j >> 1) + 2 * (j & 1) : 4 * u + 2 * (j >> 1) + (j & 1);
+}
+template <int BITS>
+__host__ __device__ constexpr int fast_exp(int u, int j) {
+    return fast_bit<BITS>(u, j) + BITS <= 10 ? fast_bit<BITS>(u, j) : fast_bit<BITS>(u, j) - 8;
+}
+// the pair of codes at bit b of both halves as fp16x2 subnormals: c * 2^fast_exp * 2^-24
+template <int BITS>
+__device__ __forceinline__ uint32_t fast_pair(uint32_t r, uint32_t r8, int u, int j) {
+    const int b         = fast_bit<BITS>(u, j);
+    const uint32_t mask = ((1u << BITS) - 1u) * 0x00010001u;
+    return b + BITS <= 10 ? (r & (mask << b)) : (r8 & (mask << (b - 8)));
 }
 
 // asynchronous global -> shared copy (LDGSTS): no register staging, so many k-steps can be in flight per thread
@@ -198,12 +211,13 @@ template <int FMT, int MODE, int NR>
 __device__ __forceinline__ void build_a(uint32_t (&a)[4], const uint32_t (&wa)[NR], const uint32_t (&wb)[NR], int u, int h, const uint32_t (&gm)[6],
                                         uint32_t bias2, uint32_t mask, uint32_t magic) {
     // gm = {step2a, zero2a, nb2a, step2b, zero2b, nb2b}
-    if constexpr (FMT == FMT_Q4 && MODE == MODE_FAST) {
-        // codes {7,3} / {5,1} of the 8 in this register: low nibbles of the bytes -> 1024 + c ; {6,2} / {4,0}: high nibbles -> 1024 + 16 c
-        uint32_t ra = wa[3 - u], rb = wb[3 - u];
-        if (h) ra = __byte_perm(ra, 0u, 0x4321), rb = __byte_perm(rb, 0u, 0x4321);  // >> 8 as a byte permute
-        a[0] = and_or_1024<0x000F000Fu>(ra, magic), a[1] = and_or_1024<0x000F000Fu>(rb, magic);
-        a[2] = and_or_1024<0x00F000F0u>(ra, magic), a[3] = and_or_1024<0x00F000F0u>(rb, magic);
+    if constexpr (MODE == MODE_FAST) {
+        constexpr int BITS = Fmt<FMT>::BITS;
+        const int ri       = BITS == 4 ? 3 - u : BITS == 2 ? 1 - (u >> 1) : 0;
+        const uint32_t ra = wa[ri], rb = wb[ri];
+        const uint32_t ra8 = __byte_perm(ra, 0u, 0x4321), rb8 = __byte_perm(rb, 0u, 0x4321);  // >> 8 as a byte permute (shared by the units)
+        a[0] = fast_pair<BITS>(ra, ra8, u, 2 * h), a[1] = fast_pair<BITS>(rb, rb8, u, 2 * h);
+        a[2] = fast_pair<BITS>(ra, ra8, u, 2 * h + 1), a[3] = fast_pair<BITS>(rb, rb8, u, 2 * h + 1);
     } else if constexpr (FMT == FMT_Q4) {
         const uint32_t ra = wa[3 - u], rb = wb[3 - u];
         a[0] = deq_pair<MODE>(ra, 8 * h, gm[0], gm[1], gm[2], bias2, mask, magic);
@@ -423,11 +437,11 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
 #pragma unroll
                 for (int i = 0; i < KT / 2; i++) src[i] = 0u;
             }
+            float fscl = 1.0f;  // MODE_FAST: the group's power-of-two scale
             if (MODE == MODE_FAST) {
                 // fp16 staging with a power-of-two scale per 128-k group (the quad's 4 x 32 values; the 4 lanes of a quad are always
-                // active together): the group's largest magnitude lands in [2^13, 2^14); the elements that meet the codes carrying a
-                // factor 16 (even elements of every 8: the fp16 number built from a byte's high nibble) are divided by 16.
-                // sxs[s][m] = {1024 Sxe + qbias Sx, Sx, 1 / scale}: Sx the group sum of the scaled activations, Sxe the sum as the MMA sees it
+                // active together): the group's largest magnitude lands in [2^13, 2^14).  sxs[s][m] = {0, Sx, 2^24 / scale} with
+                // Sx = 2^-24 x the group sum of the scaled activations (the MMA's sums carry the 2^-24 of the subnormal codes)
                 const unsigned qm = 0xFu << (lane & ~3);
                 uint32_t amax = 0;
 #pragma unroll
@@ -435,21 +449,15 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
                 amax = max(amax, __shfl_xor_sync(qm, amax, 1));
                 amax = max(amax, __shfl_xor_sync(qm, amax, 2));
                 const int shift = amax == 0 ? 0 : max(-100, min(100, 140 - (int)(amax >> 7)));  // 140 = 127 + 13
-                const float scl = __uint_as_float((uint32_t)(127 + shift) << 23);
-                float sum = 0.f, sume = 0.f;
+                fscl = __uint_as_float((uint32_t)(127 + shift) << 23);
+                float sum = 0.f;
 #pragma unroll
-                for (int i = 0; i < KT / 2; i++) {
-                    const float a = bf16lo(src[i]) * scl, b = bf16hi(src[i]) * scl;
-                    const __half ha = __float2half_rn(a * 0.0625f), hb = __float2half_rn(b);
-                    sum += a, sum += b;
-                    sume += __half2float(ha), sume += __half2float(hb);
-                    src[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
-                }
+                for (int i = 0; i < KT / 2; i++) sum += bf16lo(src[i]) * fscl, sum += bf16hi(src[i]) * fscl;
                 sum += __shfl_xor_sync(qm, sum, 1), sum += __shfl_xor_sync(qm, sum, 2);  // fixed order: bit-reproducible
-                sume += __shfl_xor_sync(qm, sume, 1), sume += __shfl_xor_sync(qm, sume, 2);
+                sum *= 5.9604644775390625e-8f;                                            // 2^-24
                 if (tt == 0)
                     reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(smem) + p.sx_off)[s * MX + m] =
-                        make_float4(fmaf(1024.0f, sume, (float)p.qbias * sum), sum, __uint_as_float((uint32_t)(127 - shift) << 23), 0.f);
+                        make_float4(0.f, sum, __uint_as_float((uint32_t)(127 + 24 - shift) << 23), 0.f);
             }
 #pragma unroll
             for (int u = 0; u < UNITS; u++) {
@@ -457,8 +465,13 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int e0 = xperm<FMT>(u * 8 + 2 * j), e1 = xperm<FMT>(u * 8 + 2 * j + 1);
-                    const uint32_t lo = (src[e0 >> 1] >> ((e0 & 1) * 16)) & 0xffffu;
-                    const uint32_t hi = (src[e1 >> 1] >> ((e1 & 1) * 16)) & 0xffffu;
+                    uint32_t lo = (src[e0 >> 1] >> ((e0 & 1) * 16)) & 0xffffu;
+                    uint32_t hi = (src[e1 >> 1] >> ((e1 & 1) * 16)) & 0xffffu;
+                    if (MODE == MODE_FAST) {  // fp16(x * scale * 2^-b): b = the bit position of the code field this element meets
+                        const float f = fscl * __uint_as_float((uint32_t)(127 - fast_exp<F::BITS>(u, j)) << 23);
+                        lo = __half_as_ushort(__float2half_rn(bf16_bits_to_f32(lo) * f));
+                        hi = __half_as_ushort(__float2half_rn(bf16_bits_to_f32(hi) * f));
+                    }
                     o[j] = lo | (hi << 16);
                 }
                 // destination (unit, thread slot): packed formats keep the 32-k slot of thread tt; the byte / bf16 streams interleave
@@ -501,7 +514,8 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
             for (int j = 0; j < 4; j++) acc[rt][nt][j] = 0.f;
 
     if (wactive) {
-        const uint32_t bias2  = pack_bf16x2((float)(128 + p.qbias), (float)(128 + p.qbias));
+        const uint32_t bias2 = pack_bf16x2((float)(128 + p.qbias), (float)(128 + p.qbias));
+        const float fqb      = (float)p.qbias;
         const int xlane       = (MX >= 8 ? g : (g & (MX - 1))) * 4 + t;  // column g of the MMA reads token g mod MX
         const uint32_t* gbase = sgam + warp * WROWS + g;
         int slot = 0;
@@ -552,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
 #pragma unroll
                         for (int j = 0; j < 4; j++) accg[rt][nt][j] = 0.f;
             }
-            float4 sv[NT][2];  // MODE_FAST: {1024 Sxe + qbias Sx, Sx, 1 / scale} of this k-step's group for the thread's two token columns
+            float4 sv[NT][2];  // MODE_FAST: {-, 2^-24 Sx, 2^24 / scale} of this k-step's group for the thread's two token columns
             if (MODE == MODE_FAST) {
                 const float4* sx4 = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(smem) + p.sx_off) + s * MX;
 #pragma unroll
@@ -560,10 +574,9 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
                     sv[nt][0] = sx4[MX >= 8 ? nt * 8 + 2 * t : ((2 * t) & (MX - 1))];
                     sv[nt][1] = sx4[MX >= 8 ? nt * 8 + 2 * t + 1 : ((2 * t + 1) & (MX - 1))];
 #pragma unroll
-                    for (int rt = 0; rt < RT; rt++) {  // the group sums start at -(1024 Sxe + qbias Sx): the MMAs leave sum((c - qbias) x')
-                        accg[rt][nt][0] = accg[rt][nt][2] = -sv[nt][0].x;
-                        accg[rt][nt][1] = accg[rt][nt][3] = -sv[nt][1].x;
-                    }
+                    for (int rt = 0; rt < RT; rt++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) accg[rt][nt][j] = 0.f;
                 }
             }
 #pragma unroll
@@ -601,11 +614,12 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
                         acc[rt][nt][3] = fmaf(fstep[rt][1], accg[rt][nt][3], acc[rt][nt][3]);
                     }
             }
-            if (MODE == MODE_FAST) {  // y += 2^-shift * (step * sum((c - qbias) x') - zero * Sx')
+            if (MODE == MODE_FAST) {  // y += 2^(24 - shift) * (step * sum(c x') - (zero + qbias step) * Sx')
 #pragma unroll
                 for (int rt = 0; rt < RT; rt++) {
                     const uint32_t ga = gbase[s * GS + rt * 16], gb = gbase[s * GS + rt * 16 + 8];
-                    const float sa = bf16hi(ga), sb = bf16hi(gb), za = bf16lo(ga), zb = bf16lo(gb);
+                    const float sa = bf16hi(ga), sb = bf16hi(gb);
+                    const float za = fmaf(fqb, sa, bf16lo(ga)), zb = fmaf(fqb, sb, bf16lo(gb));
 #pragma unroll
                     for (int nt = 0; nt < NT; nt++) {
                         acc[rt][nt][0] = fmaf(sv[nt][0].z, fmaf(sa, accg[rt][nt][0], -za * sv[nt][0].y), acc[rt][nt][0]);
@@ -868,9 +882,9 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
         case KF_T_BF16: fmt = FMT_BF16, mode = MODE_PLAIN; break;
         case KF_T_F8E5M2: fmt = FMT_F8, mode = MODE_PLAIN; break;
         case KF_T_Q4: fmt = FMT_Q4, mode = !ctx->gemv_exact ? MODE_FAST : ctx->deq_fma ? MODE_AFFINE_FMA : w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
-        case KF_T_Q2: fmt = FMT_Q2, mode = !ctx->gemv_exact ? MODE_FACTOR : ctx->deq_fma ? MODE_AFFINE_FMA : w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
-        case KF_T_SIGN: fmt = FMT_Q2, mode = MODE_SCALE; break;
-        case KF_T_BINARY: fmt = FMT_Q1, mode = MODE_SCALE; break;
+        case KF_T_Q2: fmt = FMT_Q2, mode = !ctx->gemv_exact ? MODE_FAST : ctx->deq_fma ? MODE_AFFINE_FMA : w[0].qbias == 0 ? MODE_AFFINE : MODE_AFFINE_SYM; break;
+        case KF_T_SIGN: fmt = FMT_Q2, mode = !ctx->gemv_exact ? MODE_FAST : MODE_SCALE; break;
+        case KF_T_BINARY: fmt = FMT_Q1, mode = !ctx->gemv_exact ? MODE_FAST : MODE_SCALE; break;
         default: return KF_ERR_UNSUPPORTED;
     }
     KF_REQUIRE(ctx, K % KSTEP == 0, "K must be a multiple of 128");
@@ -880,7 +894,7 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     p.norm_w = (const uint16_t*)norm_w, p.norm_eps = norm_eps;
     p.steps_total = K / KSTEP, p.qbias = w[0].qbias, p.epilogue = epilogue;
     p.lop_mask = fmt == FMT_Q4 ? 0x000F000Fu : fmt == FMT_Q2 ? 0x00030003u : 0x00010001u;
-    p.lop_magic = mode == MODE_FAST ? 0x64006400u : 0x43004300u;  // fp16x2 1024.0 / bf16x2 128.0
+    p.lop_magic = 0x43004300u;  // bf16x2 128.0
     p.tp_out = -1;
     if (xid_out >= 0) {
         KF_REQUIRE(ctx, kf_tp_view(ctx, &p.tp) == KF_OK, "fused exchange: peer buffers not attached");
@@ -978,7 +992,8 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     KF_GEMV_CASE(FMT_Q4, MODE_AFFINE)
     KF_GEMV_CASE(FMT_Q4, MODE_AFFINE_SYM)
     KF_GEMV_CASE(FMT_Q4, MODE_FAST)
-    KF_GEMV_CASE(FMT_Q2, MODE_FACTOR)
+    KF_GEMV_CASE(FMT_Q2, MODE_FAST)
+    KF_GEMV_CASE(FMT_Q1, MODE_FAST)
     KF_GEMV_CASE(FMT_Q2, MODE_AFFINE)
     KF_GEMV_CASE(FMT_Q2, MODE_AFFINE_SYM)
     KF_GEMV_CASE(FMT_Q2, MODE_SCALE)

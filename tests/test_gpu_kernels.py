@@ -188,17 +188,63 @@ def test_gemv_matches_oracle(ctx, kind, M, N, K):
 FAST_NOISE = 8e-3
 
 
-@pytest.mark.parametrize("mode", [ol.RTN_ASYM, ol.RTN_SYM], ids=["asym", "sym"])
+FAST_KINDS = [(4, ol.RTN_ASYM), (4, ol.RTN_SYM), (2, ol.RTN_ASYM), (2, ol.YYANG), (1, ol.YYANG)]
+
+
+def _fast_noise(kind):
+    # yyang ternary / binary weights are step * k with k in {-1, 0, 1}: exact in bf16, so the fast arithmetic IS the reference's and the gate
+    # is the bit-faithful mode's; the RTN kinds differ by the reference's per-weight rounding noise
+    return 2e-3 if kind[1] == ol.YYANG else FAST_NOISE
+
+
+@pytest.mark.parametrize("kind", FAST_KINDS, ids=str)
 @pytest.mark.parametrize("M,N,K", [(1, 256, 1024), (1, 1040, 4096), (2, 128, 512), (3, 5120, 2048), (8, 384, 2048), (16, 256, 1024), (64, 256, 512)])
-def test_gemv_fast_matches_oracle(ctx, mode, M, N, K):
-    t, wdq = make_weight(ctx, (4, mode), N, K, 1000 + M)
+def test_gemv_fast_matches_oracle(ctx, kind, M, N, K):
+    t, wdq = make_weight(ctx, kind, N, K, 1000 + M)
     x = rand_bf16(np.random.default_rng(M * 7 + N), (M, K))
     y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16)
-    _check_linear(y, wdq, x, M, N, K, noise=FAST_NOISE)
+    _check_linear(y, wdq, x, M, N, K, noise=_fast_noise(kind))
     # ... and the noise really is that small on average: rms error <= 3e-3 of the rms output (1.5e-3 expected + the bf16 result rounding)
     ref = ol.linear_f32(wdq, x, M, N, K)
     got = ol.bf16_to_f32(y).reshape(M, N)
     assert np.sqrt(np.mean((got - ref) ** 2)) <= 3e-3 * np.sqrt(np.mean(ref ** 2))
+
+
+@pytest.mark.parametrize("kind", FAST_KINDS, ids=str)
+def test_gemv_fast_one_signed_activations(ctx, kind):
+    # all-positive activations with a large mean (mean / std = 5): the group sums of x are as large as they get.  Two things are pinned:
+    # (a) the subnormal code operands lose nothing visible (the tensor cores keep 24 bits below a product's NOMINAL exponent, which for a
+    #     subnormal sits up to 2^10 above a small code: the yyang kinds, which have no rounding difference to hide behind, still pass the
+    #     bit-faithful gate);
+    # (b) for the RTN kinds the difference to the reference is LARGER here than for zero-mean activations: the reference's rounding error
+    #     of a weight is shared by every element of the group that carries the same code (16 distinct weights per group), so against
+    #     same-signed activations it does not average out over k -- sigma = 4.7e-3 of the rms output in this set-up (4-bit asym: 16 codes x
+    #     32 groups), gate 5 sigma.  The fast arithmetic is the one without that error.
+    M, N, K = 2, 384, 4096
+    t, wdq = make_weight(ctx, kind, N, K, 77)
+    rng = np.random.default_rng(8)
+    x = ol.f32_to_bf16((np.abs(rng.standard_normal((M, K))) + 3.0).astype(np.float32))
+    y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16)
+    _check_linear(y, wdq, x, M, N, K, noise=2e-3 if kind[1] == ol.YYANG else 2.5e-2)
+
+
+@pytest.mark.parametrize("kind", [(2, ol.YYANG), (1, ol.YYANG), (2, ol.RTN_ASYM)], ids=str)
+def test_gemv_fast_onehot_low_bit(ctx, kind):
+    # one-hot rows through the fast arithmetic: y = step * k - zero evaluated in fp32 and rounded once -- the dequantised weight itself
+    # for the yyang kinds (exact in bf16), within one bf16 ulp of it for 2-bit RTN; pins the field / activation-slot pairing of every bit position
+    rows, cols = 160, 1024
+    t, wdq = make_weight(ctx, kind, rows, cols, 901)
+    for k0 in (0, 37, 128 + 5, 511, 1023):
+        x = np.zeros((8, cols), dtype=np.uint16)
+        ks = [(k0 + 3 * m) % cols for m in range(8)]
+        x[np.arange(8), ks] = 0x3F80
+        y = kf.linear(ctx, t, ctx.array(x), 8).numpy(np.uint16).reshape(8, rows)
+        for m in range(8):
+            a, b = ol.bf16_to_f32(y[m]), ol.bf16_to_f32(wdq[:, ks[m]])
+            if kind[1] == ol.YYANG:
+                assert np.array_equal(y[m], wdq[:, ks[m]]), (k0, m)
+            else:
+                assert np.all(np.abs(a - b) <= np.maximum(np.abs(a), np.abs(b)) * 2.0 ** -7 + 1e-12)
 
 
 def test_gemv_fast_wide_dynamic_range_and_onehot(ctx):

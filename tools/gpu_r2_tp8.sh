@@ -6,7 +6,7 @@ TAG=${1:-v1}
 tr() { n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29541 "$@"; }
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29540 tools/tp_check.py > gpurun_out/r2_tp_check_n8_$TAG.txt 2>&1; echo "tp_check rc=$?"
 grep "tp_check" gpurun_out/r2_tp_check_n8_$TAG.txt | tail -4
-for cfg in "8 1" "8 0" "4 1"; do
+for cfg in "8 1" "4 1"; do
   set -- $cfg
   KF_TP_FUSED=$2 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $1 --steps 64 --warmup 8 > gpurun_out/r2_bench_tp$1_fused$2_$TAG.log 2>&1; echo "bench N=$1 fused=$2 rc=$?"
   grep '^{' gpurun_out/r2_bench_tp$1_fused$2_$TAG.log | python -c "
