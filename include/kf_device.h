@@ -195,6 +195,13 @@ int kf_advance_pos(kf_ctx* ctx, int32_t* pos_dev, int M);
 int kf_embed(kf_ctx* ctx, void* out_dev, const kf_tensor_desc* w, const int32_t* tokens_dev, int M);
 /* greedy sampler on device (the reference copies logits to the host, GoPT.cpp:614-630): out_token[m] = argmax(logits[m]) */
 int kf_argmax(kf_ctx* ctx, int32_t* out_tokens_dev, const void* logits_bf16_dev, int M, int vocab);
+/* Temperature / top-k / top-p sampling on the device, one token per logits row (GeneratOnPrompt::Sample, src/Manifold/GoPT.cpp:614-630 with
+ * TopK :632-640, UpdateLogits :751-766, TopP :729-748, Qu_FlipCoin :768-786; the reference copies the logits to the host and samples there).
+ * rng_state_dev: one 64-bit xorshift64* state per row (GoPT.cpp:594-600), advanced by the call.  temperature == 0 or top_k == 1: kf_argmax.
+ * selection 0: the top_k largest logits, ties to the lower index; 1: what TOPK_heap::Select (GoPT.cpp:667-700) keeps as written (its heap
+ * orders indices: {0 .. k-2} plus the first maximum of the rest).  top_k <= 1024. */
+int kf_sample(kf_ctx* ctx, int32_t* out_tokens_dev, const void* logits_bf16_dev, int M, int vocab, float temperature, int top_k, float top_p,
+              uint64_t* rng_state_dev, int selection);
 
 /* ---- tensor parallel: no reference equivalent (multi_gpu.cuh is dead code).  One process per GPU;
  *      the unique id is exchanged by the caller (torch.distributed / MPI) ---- */

@@ -66,6 +66,10 @@ int kf_model_decode_loop(kf_model* m, int n_steps, int M);
 /* current device-side tokens / positions (after a decode loop) */
 int kf_model_read_state(kf_model* m, int32_t* tokens_host, int32_t* pos_host, int M);
 int kf_model_set_graphs(kf_model* m, int enable);
+/* CHAT_SAMPLER (src/CLI_params.hpp:663-719): how kf_model_forward's next token and kf_model_decode_loop's feedback token are drawn.
+ * temperature 0 (the default) = greedy.  Every sequence row starts from the same seed, as the reference's LogitsInfo::rng_state
+ * (src/Manifold/GoPT.cpp:709).  See kf_sample for `selection`. */
+int kf_model_set_sampler(kf_model* m, float temperature, int top_k, float top_p, uint64_t seed, int selection);
 /* Save / load every resident tensor exactly as it sits in HBM (packed data || gama, the reference's per-tensor SerialGamaData payload,
  * src/Device/CUDA/huTensor.cu:413-458): loading skips the quantiser.  The file must come from a model built from the same config
  * (names, shapes, storage types and groups are checked); tensor-parallel ranks use one file per rank. */

@@ -94,6 +94,7 @@ SIGNATURES = {
     "kf_advance_pos": (_I, [_P, _P, _I]),
     "kf_embed": (_I, [_P, _P, _DESCP, _P, _I]),
     "kf_argmax": (_I, [_P, _P, _P, _I, _I]),
+    "kf_sample": (_I, [_P, _P, _P, _I, _I, C.c_float, _I, C.c_float, _P, _I]),
     "kf_nccl_unique_id": (_I, [_P]),
     "kf_ctx_init_nccl": (_I, [_P, _P, _I, _I]),
     "kf_allreduce_bf16": (_I, [_P, _P, _SZ]),
@@ -118,6 +119,7 @@ SIGNATURES = {
     "kf_model_save": (_I, [_P, C.c_char_p]),
     "kf_model_load": (_I, [_P, C.c_char_p]),
     "kf_model_set_graphs": (_I, [_P, _I]),
+    "kf_model_set_sampler": (_I, [_P, C.c_float, _I, C.c_float, _U64, _I]),
     "kf_config_dims": (_I, [C.c_char_p, C.POINTER(ModelInfo), C.POINTER(_P)]),
     "kf_config_quant_of": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_P)]),
     "kf_config_shard_of": (_I, [C.c_char_p, C.c_char_p, _I, _I, C.POINTER(_I), C.POINTER(_P)]),

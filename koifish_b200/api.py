@@ -319,6 +319,14 @@ def argmax(ctx, logits, M, vocab):
     return out
 
 
+def sample(ctx, logits, M, vocab, temperature, top_k, top_p, rng_state, selection=0):
+    """rng_state: device buffer of M uint64 xorshift64* states (advanced in place); returns the device buffer of M int32 tokens"""
+    out = ctx.empty(M * 4)
+    ctx.check(ctx.lib.kf_sample(ctx.h, out.ptr, logits.ptr, M, vocab, float(temperature), int(top_k), float(top_p), rng_state.ptr, int(selection)),
+              "kf_sample")
+    return out
+
+
 class Model:
     """The Qwen3 runtime behind include/kf_model.h (reference: Fish::MakeInstance + Fish::Chat's per-token ForwardOnRLS)."""
 
@@ -417,6 +425,9 @@ class Model:
 
     def load(self, path):
         self._check(self.lib.kf_model_load(self.h, str(path).encode()), "kf_model_load")
+
+    def set_sampler(self, temperature, top_k=50, top_p=0.95, seed=42, selection=0):
+        self._check(self.lib.kf_model_set_sampler(self.h, float(temperature), int(top_k), float(top_p), int(seed), int(selection)), "kf_model_set_sampler")
 
     def set_graphs(self, enable):
         self._check(self.lib.kf_model_set_graphs(self.h, int(bool(enable))), "kf_model_set_graphs")

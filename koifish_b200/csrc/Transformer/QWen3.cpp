@@ -206,7 +206,7 @@ Fish::Fish(kf_ctx* c, const MODEL_CARD& card, int rank, int world) : ctx(c), con
 Fish::~Fish() {
     ResetGraphs();
     tensors.clear();
-    void* bufs[] = {x, xb, q, k, v, att, hb, logits, part_f32, d_tokens, d_pos, d_next, cache.key, cache.value};
+    void* bufs[] = {x, xb, q, k, v, att, hb, logits, part_f32, d_tokens, d_pos, d_next, d_rng, cache.key, cache.value};
     for (void* b : bufs)
         if (b) kf_free(ctx, b);
     if (rope_table_shared) kf_free(ctx, rope_table_shared);
@@ -456,6 +456,26 @@ int Fish::ForwardOnRLS(int M, bool want_logits) {
     return KF_OK;
 }
 
+int Fish::PickNext(int rows) {
+    if (samp_temperature == 0.f || samp_top_k == 1) return kf_argmax(ctx, d_next, logits, rows, config.vocab);
+    return kf_sample(ctx, d_next, logits, rows, config.vocab, samp_temperature, samp_top_k, samp_top_p, d_rng, samp_selection);
+}
+int Fish::SetSampler(float temperature, int top_k, float top_p, uint64_t seed, int selection) {
+    std::string* hFishErr = &error;
+    if (temperature < 0.f || top_p <= 0.f || (selection != 0 && selection != 1)) {
+        error = "sampler: temperature >= 0, top_p > 0, selection 0 / 1";
+        return KF_ERR_BAD_ARG;
+    }
+    ResetGraphs();  // the captured steps carry the sampler's launch
+    samp_temperature = temperature, samp_top_k = top_k, samp_top_p = top_p, samp_selection = selection;
+    const size_t rows = (size_t)std::max(logit_rows, max_tokens);
+    if (!d_rng) KF_TRY(kf_malloc(ctx, rows * 8, (void**)&d_rng));
+    std::vector<uint64_t> st(rows, seed);
+    KF_TRY(kf_h2d(ctx, d_rng, st.data(), rows * 8));
+    KF_TRY(kf_ctx_sync(ctx));
+    return KF_OK;
+}
+
 // graph key: M<<12 | ctx bucket<<7 | want_logits | seq_mode<<1 | feedback<<2 | argmax<<3 | last_only<<5 | consecutive<<6
 // contexts are bucketed by powers of two (>= 512): the attention launch geometry (slices, kernel choice) follows the bucket
 int Fish::CtxBucket() const {
@@ -505,7 +525,7 @@ int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, ui
     if (use_graphs && it == graphs.end() && warm.count(key)) {  // second call with this signature: capture it
         KF_TRY(kf_graph_begin(ctx));
         int rc = ForwardOnRLS(M, want_logits);
-        if (!rc && next_out) rc = kf_argmax(ctx, d_next, logits, R, config.vocab);
+        if (!rc && next_out) rc = PickNext(R);
         kf_graph* g = nullptr;
         int rc2     = kf_graph_end(ctx, &g);
         if (rc || rc2) {
@@ -519,7 +539,7 @@ int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, ui
         KF_TRY(kf_graph_launch(ctx, it->second));
     } else {
         KF_TRY(ForwardOnRLS(M, want_logits));
-        if (next_out) KF_TRY(kf_argmax(ctx, d_next, logits, R, config.vocab));
+        if (next_out) KF_TRY(PickNext(R));
         warm.insert(key);
     }
     if (logits_out) KF_TRY(kf_d2h(ctx, h_logits, logits, (size_t)R * config.vocab * 2));
@@ -565,7 +585,7 @@ int Fish::DecodeLoop(int n_steps, int M) {
     auto it       = graphs.find(key);
     auto body     = [&]() -> int {
         int rc = ForwardOnRLS(M, true);
-        if (!rc) rc = kf_argmax(ctx, d_next, logits, M, config.vocab);
+        if (!rc) rc = PickNext(M);
         if (!rc) rc = kf_d2d(ctx, d_tokens, d_next, (size_t)M * 4);
         if (!rc) rc = kf_advance_pos(ctx, d_pos, M);
         return rc;

@@ -122,6 +122,12 @@ struct Fish {
     void *x = nullptr, *xb = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *att = nullptr, *hb = nullptr, *logits = nullptr;
     float* part_f32 = nullptr;
     int32_t *d_tokens = nullptr, *d_pos = nullptr, *d_next = nullptr;
+    // CHAT_SAMPLER (CLI_params.hpp:663-719): temperature 0 = greedy; d_rng = one xorshift64* state per sequence row
+    float samp_temperature = 0.f, samp_top_p = 0.95f;
+    int samp_top_k = 50, samp_selection = 0;
+    uint64_t* d_rng = nullptr;
+    int SetSampler(float temperature, int top_k, float top_p, uint64_t seed, int selection);
+    int PickNext(int rows);  // d_next[r] = argmax or a sample of logits row r
     int32_t* h_stage  = nullptr;  // pinned staging: tokens | pos | next
     uint16_t* h_logits = nullptr; // pinned
     int seq_mode = 0;             // 0: the M tokens of a forward are one sequence (prefill) ; 1: M independent sequences

@@ -188,6 +188,10 @@ extern "C" int kf_model_load(kf_model* m, const char* path) {
     if (!m || !path) return KF_ERR_BAD_ARG;
     return m->fish->LoadBlobs(path);
 }
+extern "C" int kf_model_set_sampler(kf_model* m, float temperature, int top_k, float top_p, uint64_t seed, int selection) {
+    if (!m) return KF_ERR_BAD_ARG;
+    return m->fish->SetSampler(temperature, top_k, top_p, seed, selection);
+}
 extern "C" int kf_model_set_graphs(kf_model* m, int enable) {
     if (!m) return KF_ERR_BAD_ARG;
     m->fish->use_graphs = enable != 0;

@@ -570,3 +570,80 @@ extern "C" int kfo_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampler: GeneratOnPrompt::Sample, src/Manifold/GoPT.cpp:614-630 -- TopK :632-640 (TOPK_heap::Select :667-700), UpdateLogits :751-766,
+ * TopP :729-748, Qu_FlipCoin :768-786, random_u32 / random_f32 :594-600.
+ * selection 0: the top_k largest logits, ties to the lower index (what Select is meant to keep);
+ * selection 1: what Select keeps as written: its std::priority_queue<int> orders the INDICES, so heap.top() is always the newest index and
+ *              `isLarge(i, heap.top())` compares with the last pushed element -- the result is {0 .. k-2} plus the first maximum of the rest.
+ * Candidates are then ordered by (logit descending, index ascending); the reference's std::sort on `a > b` leaves the order of equal
+ * logits unspecified -- this is one valid outcome of it.
+ * ---------------------------------------------------------------------------------------------- */
+static inline uint32_t samp_key(uint16_t b) { return (b & 0x8000u) ? (uint32_t)(uint16_t)~b : (uint32_t)(b | 0x8000u); }
+extern "C" int kfo_sample(const uint16_t* logits, int vocab, float temperature, int top_k, float top_p, uint64_t* rng_state, int selection,
+                          int* n_pick_out) {
+    if (temperature == 0.0f || top_k == 1) { /* sample_argmax :602-612 */
+        int best = 0;
+        for (int i = 1; i < vocab; i++)
+            if (kfo_bf16_to_f32(logits[i]) > kfo_bf16_to_f32(logits[best])) best = i;
+        return best;
+    }
+    if (top_k <= 0 || top_k > vocab) top_k = vocab;
+    std::vector<int> picks;
+    if (selection == 1) {
+        for (int i = 0; i < top_k - 1; i++) picks.push_back(i);
+        int best = top_k - 1;
+        for (int i = top_k; i < vocab; i++)
+            if (kfo_bf16_to_f32(logits[i]) > kfo_bf16_to_f32(logits[best])) best = i;
+        picks.push_back(best);
+    } else {
+        std::vector<int> idx(vocab);
+        for (int i = 0; i < vocab; i++) idx[i] = i;
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return samp_key(logits[a]) > samp_key(logits[b]); });
+        picks.assign(idx.begin(), idx.begin() + top_k);
+    }
+    std::stable_sort(picks.begin(), picks.end(), [&](int a, int b) {
+        const float va = kfo_bf16_to_f32(logits[a]), vb = kfo_bf16_to_f32(logits[b]);
+        return va > vb || (va == vb && a < b);
+    });
+    std::vector<float> p(top_k);
+    const float mx = kfo_bf16_to_f32(logits[picks[0]]);
+    float sum      = 0.f;
+    for (int i = 0; i < top_k; i++) {
+        p[i] = expf((kfo_bf16_to_f32(logits[picks[i]]) - mx) / temperature);
+        sum += p[i];
+    }
+    for (int i = 0; i < top_k; i++) p[i] /= sum;
+    int n_pick = top_k;
+    if (top_p < 1.0f) {
+        float cum = 0.f;
+        int last  = top_k - 1;
+        for (int i = 0; i < top_k; i++) {
+            cum += p[i];
+            if (cum > top_p) {
+                last = i;
+                break;
+            }
+        }
+        n_pick = last + 1;
+    }
+    if (n_pick_out) *n_pick_out = n_pick;
+    float psum = 0.f;
+    for (int i = 0; i < n_pick; i++) psum += p[i];
+    uint64_t s = *rng_state;
+    s ^= s >> 12, s ^= s << 25, s ^= s >> 27;
+    *rng_state       = s;
+    const uint32_t r = (uint32_t)((s * 0x2545F4914F6CDD1Dull) >> 32);
+    const float coin = (float)(r >> 8) / 16777216.0f * psum;
+    int q            = picks[n_pick - 1];
+    float cdf        = 0.f;
+    for (int i = 0; i < n_pick; i++) {
+        cdf += p[i];
+        if (coin < cdf) {
+            q = picks[i];
+            break;
+        }
+    }
+    return q;
+}

@@ -22,9 +22,11 @@ RTN_ASYM, RTN_SYM, YYANG = 0, 1, 2
 
 def build_oracle(force=False):
     """Compile oracle/ (and oracle/_ref when /root/reference is present). Building the checker is not using it."""
-    if force or not os.path.exists(ORACLE_SO):
-        subprocess.check_call(["make", "-C", ORACLE_DIR, "libkoifish_oracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.exists("/root/reference/src/PackedQ.hpp") and (force or not os.path.exists(REF_SO)):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("koifish_oracle.cpp", "koifish_oracle.h")]
+    if force or not os.path.exists(ORACLE_SO) or any(os.path.getmtime(f) > os.path.getmtime(ORACLE_SO) for f in srcs):
+        subprocess.check_call(["make", "-B" if force else "-s", "-C", ORACLE_DIR, "libkoifish_oracle.so"], stdout=subprocess.DEVNULL)
+    shim = os.path.join(ORACLE_DIR, "ref_shim.cpp")
+    if os.path.exists("/root/reference/src/PackedQ.hpp") and (force or not os.path.exists(REF_SO) or os.path.getmtime(shim) > os.path.getmtime(REF_SO)):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
     if os.path.exists("/root/reference/src/Device/CUDA/T.cu"):
         src = os.path.join(ORACLE_DIR, "ref_kernels.cu")
@@ -92,6 +94,8 @@ def lib():
         L.kfo_rope.argtypes = [_u16p, C.c_int, C.c_int, C.c_int, C.c_float]
         L.kfo_swiglu.argtypes = [_u16p, _u16p, _u16p, C.c_size_t]
         L.kfo_add.argtypes = [_u16p, _u16p, _u16p, C.c_size_t]
+        L.kfo_sample.restype = C.c_int
+        L.kfo_sample.argtypes = [_u16p, C.c_int, C.c_float, C.c_int, C.c_float, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]
         L.kfo_attention_decode.argtypes = [_u16p, _u16p, _u16p, _u16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.kfo_model_create.restype = C.c_void_p
         L.kfo_model_create.argtypes = [C.POINTER(ModelConfig)]
@@ -257,6 +261,15 @@ def swiglu(g, u):
     out = np.zeros(g.size, dtype=np.uint16)
     lib().kfo_swiglu(out, g, u, g.size)
     return out
+
+
+def sample(logits, temperature, top_k, top_p, state, selection=0):
+    """CPU port of GeneratOnPrompt::Sample; state: [uint64] advanced in place (a one-element list); returns (token, n_pick)"""
+    lg = np.ascontiguousarray(logits, dtype=np.uint16).reshape(-1)
+    st, npick = C.c_uint64(state[0]), C.c_int(0)
+    tok = lib().kfo_sample(lg, lg.size, temperature, top_k, top_p, C.byref(st), selection, C.byref(npick))
+    state[0] = st.value
+    return int(tok), int(npick.value)
 
 
 def add(a, b):

@@ -792,3 +792,39 @@ def test_attn_prefill_at_the_end_of_the_cache(ctx):
     got = kf.attn_prefill(ctx, qd, kcd, vcd, posd, M, n_head, n_kv, hd, max_seq).numpy(np.uint16)
     g, w = ol.bf16_to_f32(got), ol.bf16_to_f32(want)
     assert np.allclose(g, w, rtol=2.0 ** -6, atol=6e-3), np.abs(g - w).max()
+
+
+# ---------------------------------------------------------------------------------------------- device sampler (GoPT.cpp:614-630)
+@pytest.mark.parametrize("selection", [0, 1])
+@pytest.mark.parametrize("vocab,top_k,top_p,T", [(151936, 50, 0.95, 0.6), (4096, 1000, 0.9, 1.3), (32768, 7, 1.0, 0.7), (151936, 64, 0.5, 2.0)])
+def test_device_sampler_matches_cpu_port(ctx, selection, vocab, top_k, top_p, T):
+    # same logits, same seeds: the device sampler must draw the token the CPU port of GeneratOnPrompt::Sample draws.  The two use different
+    # expf implementations (last-ulp differences of the probabilities), so a draw whose coin lands within 1e-5 of a cdf boundary may differ:
+    # allowed for at most 1 draw in 100.  bf16 logits tie massively (8 mantissa bits over 152 K values): the tie rules are exercised.
+    M, rounds = 4, 25
+    rng = np.random.default_rng(vocab + top_k)
+    lg = ol.f32_to_bf16((rng.standard_normal((M, vocab)) * 2.5).astype(np.float32))
+    lgd = ctx.array(lg)
+    seeds = np.array([42, 43, 0x9E3779B97F4A7C15, 7], dtype=np.uint64)
+    std = ctx.array(seeds.view(np.uint16))
+    states = [[int(s)] for s in seeds]
+    diff = 0
+    for _ in range(rounds):
+        got = kf.sample(ctx, lgd, M, vocab, T, top_k, top_p, std, selection).numpy(np.int32)
+        for m in range(M):
+            want, _ = ol.sample(lg[m], T, top_k, top_p, states[m], selection)
+            diff += int(got[m] != want)
+    assert diff <= 1, diff
+    assert np.array_equal(std.numpy(np.uint64), np.array([s[0] for s in states], dtype=np.uint64))  # generator states advanced identically
+
+
+def test_device_sampler_greedy_paths_and_errors(ctx):
+    vocab = 5000
+    lg = ol.f32_to_bf16(np.random.default_rng(3).standard_normal((2, vocab)).astype(np.float32))
+    lgd = ctx.array(lg)
+    st = ctx.array(np.array([1, 2], dtype=np.uint64).view(np.uint16))
+    want = np.argmax(ol.bf16_to_f32(lg).reshape(2, vocab), axis=1)
+    assert np.array_equal(kf.sample(ctx, lgd, 2, vocab, 0.0, 50, 0.9, st).numpy(np.int32), want)
+    assert np.array_equal(kf.sample(ctx, lgd, 2, vocab, 0.7, 1, 0.9, st).numpy(np.int32), want)
+    with pytest.raises(kf.KoifishError):
+        kf.sample(ctx, lgd, 2, vocab, 0.7, 2000, 0.9, st)  # more than 1024 candidates

@@ -336,3 +336,55 @@ def test_model_weight_is_dequant_of_quantized_synthetic():
     data, gama = ol.quantize(raw, QD, E, 4, 128, ol.RTN_ASYM)
     assert np.array_equal(m.weight(17), ol.dequant(data, gama, QD, E, 4, 128, 0).reshape(-1))
     assert np.array_equal(m.weight(16), np.full(E, 0x3F80, dtype=np.uint16))  # norms are 1 (FIX_1)
+
+
+# ---------------------------------------------------------------------------------------------- sampler (GoPT.cpp:614-630)
+def _sampler_logits(seed, vocab=4096, sigma=2.0):
+    rng = np.random.default_rng(seed)
+    return ol.f32_to_bf16((rng.standard_normal(vocab) * sigma).astype(np.float32))
+
+
+def test_sampler_port_greedy_and_distribution():
+    lg = _sampler_logits(1)
+    f = ol.bf16_to_f32(lg)
+    st = [42]
+    assert ol.sample(lg, 0.0, 50, 0.95, st)[0] == int(np.argmax(f)) and st[0] == 42  # temperature 0: argmax, generator untouched
+    assert ol.sample(lg, 0.7, 1, 0.95, st)[0] == int(np.argmax(f))                    # top_k 1: argmax
+    # top_p -> 0 keeps only the best candidate; the draw is then always the arg-max
+    for _ in range(8):
+        tok, npick = ol.sample(lg, 0.7, 50, 1e-6, st)
+        assert tok == int(np.argmax(f)) and npick == 1
+    # the empirical distribution over many draws follows softmax(top-50 / T) restricted to the top-p prefix
+    T, k, top_p = 0.8, 50, 0.9
+    order = np.lexsort((np.arange(f.size), -f))[:k]
+    p = np.exp((f[order] - f[order[0]]) / T)
+    p /= p.sum()
+    keep = int(np.argmax(np.cumsum(p) > top_p)) + 1
+    st = [12345]
+    draws = [ol.sample(lg, T, k, top_p, st) for _ in range(4000)]
+    assert all(n == keep for _, n in draws)
+    counts = np.array([sum(1 for t, _ in draws if t == int(order[i])) for i in range(keep)], dtype=np.float64)
+    assert counts.sum() == len(draws)  # never outside the kept prefix
+    expect = p[:keep] / p[:keep].sum() * len(draws)
+    assert np.all(np.abs(counts - expect) <= 5 * np.sqrt(expect) + 5)
+
+
+def test_sampler_port_generator_is_xorshift64star():
+    # random_u32 (GoPT.cpp:594-599) by hand
+    s = 42
+    s ^= s >> 12
+    s ^= (s << 25) & 0xFFFFFFFFFFFFFFFF
+    s ^= s >> 27
+    st = [42]
+    ol.sample(_sampler_logits(2), 0.7, 10, 1.0, st)
+    assert st[0] == s
+
+
+def test_sampler_port_reference_heap_selection():
+    # selection 1 = TOPK_heap::Select as written (GoPT.cpp:667-700): candidates are indices 0 .. k-2 plus the first maximum of the rest
+    lg = _sampler_logits(3)
+    f = ol.bf16_to_f32(lg)
+    k = 8
+    allowed = set(range(k - 1)) | {int(k - 1 + np.argmax(f[k - 1:]))}
+    st = [7]
+    assert all(ol.sample(lg, 5.0, k, 1.0, st, selection=1)[0] in allowed for _ in range(200))
