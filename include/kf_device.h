@@ -135,6 +135,9 @@ int kf_dequant(kf_ctx* ctx, const kf_tensor_desc* w, void* out_bf16_dev);
  *      is per weight type (bf16: always tcgen05, everything else from 9 tokens; profiles/r01_tc_crossover.txt). ---- */
 enum { KF_EPI_NONE = 0, KF_EPI_RESIDUAL = 1, KF_EPI_F32 = 4 /* y is float [M][rows], unrounded partial sums (tensor parallel) */ };
 int kf_linear(kf_ctx* ctx, void* y_dev, const kf_tensor_desc* w, const void* x_dev, int M, int epilogue, const void* residual_dev);
+/* TASKA_AxB in full (src/Tensor/GTensor.hpp:698-741): d = alpha * x . w^T + beta * d + bias (bias: one bf16 per output row, or NULL),
+ * fp32 epilogue, one rounding -- what CU_mm_blasLt hands to cuBLASLt.  The inference path uses alpha 1, beta 0, no bias (= kf_linear). */
+int kf_linear_axb(kf_ctx* ctx, void* d_dev, const kf_tensor_desc* w, const void* x_dev, int M, float alpha, float beta, const void* bias_dev);
 /* up to 3 weights sharing x (Q/K/V: SelfAttention::cuInfer, src/Device/CUDA/QKV.cu:648-652) in one launch; y_dev[i] is [M][rows_i] */
 int kf_linear_multi(kf_ctx* ctx, int n, void* const* y_dev, const kf_tensor_desc* w, const void* x_dev, int M);
 /* FFN gate/up + CU_swiglu_v0 (src/Device/CUDA/NeuronFuse.cu:628-637, Activation.cu:86-93): y = silu(bf16(Wg x)) * bf16(Wu x) */

@@ -93,6 +93,7 @@ SIGNATURES = {
     "kf_residual_add_f32": (_I, [_P, _P, _P, _P, _SZ]),
     "kf_advance_pos": (_I, [_P, _P, _I]),
     "kf_embed": (_I, [_P, _P, _DESCP, _P, _I]),
+    "kf_linear_axb": (_I, [_P, _P, _P, _P, _I, C.c_float, C.c_float, _P]),
     "kf_argmax": (_I, [_P, _P, _P, _I, _I]),
     "kf_sample": (_I, [_P, _P, _P, _I, _I, C.c_float, _I, C.c_float, _P, _I]),
     "kf_nccl_unique_id": (_I, [_P]),

@@ -221,6 +221,13 @@ def linear(ctx, w, x, M, epilogue=L.KF_EPI_NONE, residual=None, out=None):
     return out
 
 
+def linear_axb(ctx, w, x, M, d, alpha=1.0, beta=0.0, bias=None):
+    """TASKA_AxB in full: d = alpha * x . deq(W)^T + beta * d + bias (in place on the device buffer d)"""
+    desc = w.desc()
+    ctx.check(ctx.lib.kf_linear_axb(ctx.h, d.ptr, C.byref(desc), x.ptr, M, float(alpha), float(beta), bias.ptr if bias is not None else None), "kf_linear_axb")
+    return d
+
+
 def linear_multi(ctx, ws, x, M):
     outs = [ctx.empty(M * w.rows * 2) for w in ws]
     descs = (TensorDesc * len(ws))(*[w.desc() for w in ws])

@@ -129,6 +129,7 @@ void kf_gemv_tma_destroy(kf_ctx* ctx);
 int kf_gemv_tma(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                 const void* norm_w, float norm_eps);
 int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters);
+int kf_axb_epilogue(kf_ctx* ctx, void* d, const float* acc, const void* bias, float alpha, float beta, int rows, size_t n);  // ops.cu
 int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes);
 int kf_qknorm_rope_kv_warp(kf_ctx* ctx, void* q, const void* k, const void* v, const void* qw, const void* kw, void* kcache, void* vcache,
                            const void* table, const int32_t* pos_dev, int M, int n_head, int n_kv, int hd, float eps, size_t seq_stride);

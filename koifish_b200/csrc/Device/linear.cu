@@ -133,6 +133,22 @@ extern "C" int kf_linear(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const vo
     void* ys[1] = {y};
     return linear_any(ctx, 1, ys, w, x, M, epilogue, residual, nullptr, 0.f);
 }
+// TASKA_AxB in full (src/Tensor/GTensor.hpp:698-741): d = alpha * x . w^T + beta * d + bias, bias one bf16 per output row or NULL.  The
+// matmul runs through the same kernels with fp32 partial output, then one fp32 epilogue rounds once -- as cuBLASLt's epilogue does.
+// alpha = 1, beta = 0, bias = NULL is kf_linear(..., KF_EPI_NONE) (SLP::Forw of the inference path).
+extern "C" int kf_linear_axb(kf_ctx* ctx, void* d, const kf_tensor_desc* w, const void* x, int M, float alpha, float beta, const void* bias) {
+    if (!ctx || !d || !w || !x) return KF_ERR_BAD_ARG;
+    KF_REQUIRE(ctx, M >= 1, "M");
+    if (alpha == 0.f && beta == 0.f && !bias) return KF_OK;  // TASKA_AxB::isPass
+    if (alpha == 1.f && beta == 0.f && !bias) return kf_linear(ctx, d, w, x, M, KF_EPI_NONE, nullptr);
+    const size_t n = (size_t)M * w->rows;
+    int rc = kf_ensure_buf(ctx, &ctx->tmp0, &ctx->tmp0_bytes, n * 4);
+    if (rc) return rc;
+    void* ys[1] = {ctx->tmp0};
+    rc = linear_any(ctx, 1, ys, w, x, M, KF_EPI_F32, nullptr, nullptr, 0.f);
+    if (rc) return rc;
+    return kf_axb_epilogue(ctx, d, (const float*)ctx->tmp0, bias, alpha, beta, w->rows, n);
+}
 extern "C" int kf_linear_multi(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M) {
     if (!ctx || !y || !w || !x) return KF_ERR_BAD_ARG;
     KF_REQUIRE(ctx, M >= 1 && n >= 1 && n <= 3, "M, n");

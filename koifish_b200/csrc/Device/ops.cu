@@ -148,6 +148,17 @@ __global__ void __launch_bounds__(256) kf_residual_add_f32_kernel(uint16_t* __re
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = f32_to_bf16_bits(bf16_bits_to_f32(res[i]) + bf16_bits_to_f32(f32_to_bf16_bits(sum[i])));
 }
+// d = alpha * acc + beta * d + bias[row]: the epilogue of TASKA_AxB (src/Tensor/GTensor.hpp:698-741, cuBLASLt computes it in fp32 and
+// rounds once to bf16)
+__global__ void __launch_bounds__(256) kf_axb_epilogue_kernel(uint16_t* __restrict__ d, const float* __restrict__ acc, const uint16_t* __restrict__ bias,
+                                                              float alpha, float beta, int rows, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = alpha * acc[i];
+    if (beta != 0.f) v = fmaf(beta, bf16_bits_to_f32(d[i]), v);
+    if (bias) v += bf16_bits_to_f32(bias[i % rows]);
+    d[i] = f32_to_bf16_bits(v);
+}
 __global__ void kf_advance_pos_kernel(int32_t* pos, int M) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < M) pos[i] += 1;
@@ -156,6 +167,11 @@ extern "C" int kf_residual_add_f32(kf_ctx* ctx, void* out, const void* res, cons
     if (!ctx || !out || !res || !sum) return KF_ERR_BAD_ARG;
     if (!n) return KF_OK;
     kf_residual_add_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint16_t*)out, (const uint16_t*)res, sum, n);
+    KF_LAUNCH_CHECK(ctx);
+    return KF_OK;
+}
+int kf_axb_epilogue(kf_ctx* ctx, void* d, const float* acc, const void* bias, float alpha, float beta, int rows, size_t n) {
+    kf_axb_epilogue_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint16_t*)d, acc, (const uint16_t*)bias, alpha, beta, rows, n);
     KF_LAUNCH_CHECK(ctx);
     return KF_OK;
 }

@@ -828,3 +828,25 @@ def test_device_sampler_greedy_paths_and_errors(ctx):
     assert np.array_equal(kf.sample(ctx, lgd, 2, vocab, 0.7, 1, 0.9, st).numpy(np.int32), want)
     with pytest.raises(kf.KoifishError):
         kf.sample(ctx, lgd, 2, vocab, 0.7, 2000, 0.9, st)  # more than 1024 candidates
+
+
+@pytest.mark.parametrize("kind", [(4, ol.RTN_ASYM), "bf16", (2, ol.YYANG)], ids=str)
+@pytest.mark.parametrize("M", [1, 5, 96])
+def test_linear_axb_alpha_beta_bias(ctx, kind, M):
+    # TASKA_AxB (GTensor.hpp:698-741): d = alpha * x . w^T + beta * d + bias, fp32 epilogue, one rounding (GEMV for small M, tcgen05 for 96)
+    N, K = 256, 1024
+    t, wdq = make_weight(ctx, kind, N, K, 4242)
+    rng = np.random.default_rng(M)
+    x, d0, bias = rand_bf16(rng, (M, K)), rand_bf16(rng, (M, N)), rand_bf16(rng, (N,))
+    alpha, beta = 0.5, -1.25
+    ctx.set_int("gemv_exact", 1)
+    dd = ctx.array(d0)
+    kf.linear_axb(ctx, t, ctx.array(x), M, dd, alpha, beta, ctx.array(bias))
+    got = ol.bf16_to_f32(dd.numpy(np.uint16)).reshape(M, N)
+    acc = ol.linear_f32(wdq, x, M, N, K).reshape(M, N)
+    want = alpha * acc + beta * ol.bf16_to_f32(d0).reshape(M, N) + ol.bf16_to_f32(bias)[None, :]
+    assert np.all(np.abs(got - want) <= np.abs(want) * 2.0 ** -8 + 2e-3 * np.sqrt(np.mean(want ** 2)))
+    # alpha 1, beta 0, no bias is kf_linear
+    dd = ctx.array(d0)
+    kf.linear_axb(ctx, t, ctx.array(x), M, dd)
+    assert np.array_equal(dd.numpy(np.uint16), kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16))
