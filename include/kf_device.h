@@ -40,6 +40,9 @@ enum {
     KF_T_Q2       = 3, /* typNUMBER::Q2       2-bit RTN codes in 128-bit words                   */
     KF_T_SIGN     = 4, /* typNUMBER::T_SIGN   2-bit ternary {-1,0,1}+1 (yyang / bitnet)          */
     KF_T_BINARY   = 5, /* typNUMBER::T_BINARY 1-bit {0,1} (yyang)                                */
+    KF_T_NF4      = 6, /* typNUMBER::Q4 under QUANT_MODE::RTNf ({"bits": 4} without a quant_method): NormalFloat4 codes as an MSB-first
+                          nibble stream (BIT_SET_k, CLI_params.cpp:2177-2191), gama = [R_SCALE rows][C_SCALE cols][rows][16] bf16
+                          per-row codebooks (GeQuant::_row_lut, GeQuant.cpp:696-732; CU_Q42X_NF4, quantizer.cu:612-654)            */
 };
 
 /* ---- quantisation modes (QUANT_CARD, src/CLI_params.hpp:509-554; GeQuant ctor src/Tensor/GeQuant.cpp:107-124) ---- */

@@ -98,7 +98,7 @@ extern "C" int kf_ctx_destroy(kf_ctx* ctx) {
         cudaFree(ctx->attn_ws);
     if (ctx->attn_cnt)
         cudaFree(ctx->attn_cnt);
-    void* scratch[4] = {ctx->xperm, ctx->xnorm, ctx->tmp0, ctx->tmp1};
+    void* scratch[5] = {ctx->xperm, ctx->xnorm, ctx->tmp0, ctx->tmp1, ctx->deq_w};
     for (void* b : scratch)
         if (b)
             cudaFree(b);

@@ -33,6 +33,8 @@ struct kf_ctx {
     // scratch of the tensor-core (M > 64) path: permuted / normalised activations and the gate / up panels of a SwiGLU
     void *xperm = nullptr, *xnorm = nullptr, *tmp0 = nullptr, *tmp1 = nullptr;
     size_t xperm_bytes = 0, xnorm_bytes = 0, tmp0_bytes = 0, tmp1_bytes = 0;
+    void* deq_w        = nullptr;  // dequantised copy of ONE NormalFloat4 weight for the many-token path (nf4.cu)
+    size_t deq_w_bytes = 0;
     int tc_min_m = -1;  // token count from which kf_linear* use the tcgen05 GEMM: -1 = per weight type (linear.cu), 0 = never
     // tuning
     int gemv_splitk  = 0;
@@ -103,7 +105,8 @@ static inline int kf_type_bits(int type) {
     switch (type) {
         case KF_T_BF16: return 16;
         case KF_T_F8E5M2: return 8;
-        case KF_T_Q4: return 4;
+        case KF_T_Q4:
+        case KF_T_NF4: return 4;
         case KF_T_Q2:
         case KF_T_SIGN: return 2;
         case KF_T_BINARY: return 1;
@@ -129,6 +132,11 @@ void kf_gemv_tma_destroy(kf_ctx* ctx);
 int kf_gemv_tma(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                 const void* norm_w, float norm_eps);
 int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters);
+// nf4.cu
+int kf_nf4_quantize(kf_ctx* ctx, const void* w_bf16, int rows, int cols, void* data, void* gama);
+int kf_nf4_dequant(kf_ctx* ctx, const kf_tensor_desc* w, void* out_bf16);
+int kf_nf4_embed(kf_ctx* ctx, void* out, const kf_tensor_desc* w, const int32_t* tokens, int M);
+int kf_nf4_gemv(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual);
 int kf_axb_epilogue(kf_ctx* ctx, void* d, const float* acc, const void* bias, float alpha, float beta, int rows, size_t n);  // ops.cu
 int kf_ensure_attn_ws(kf_ctx* ctx, size_t bytes);
 int kf_qknorm_rope_kv_warp(kf_ctx* ctx, void* q, const void* k, const void* v, const void* qw, const void* kw, void* kcache, void* vcache,

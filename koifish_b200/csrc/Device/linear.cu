@@ -77,7 +77,49 @@ static bool use_tensor_cores(const kf_ctx* ctx, int n, const kf_tensor_desc* w, 
 
 // epilogue: 0 none, 1 residual, 2 swiglu(w[0] gate, w[1] up -> y[0]), 4 fp32
 static int linear_any(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
+                      const void* norm_w, float norm_eps);
+// NormalFloat4 weights (nf4.cu): RMSNorm as its own launch, then per weight either the warp-per-row LUT GEMV (<= 8 tokens) or dequantise into a
+// context scratch + the bf16 tensor-core GEMM (the reference's own route for every format: GTensor::GetDataX + cuBLASLt)
+static int linear_nf4(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                       const void* norm_w, float norm_eps) {
+    const int K = w[0].cols;
+    int rc      = KF_OK;
+    if (norm_w) {
+        rc = kf_ensure_buf(ctx, &ctx->xnorm, &ctx->xnorm_bytes, (size_t)M * K * 2);
+        if (!rc) rc = kf_rmsnorm(ctx, ctx->xnorm, x, norm_w, M, K, norm_eps);
+        if (rc) return rc;
+        x = ctx->xnorm;
+    }
+    auto one = [&](void* yy, const kf_tensor_desc& ww, int epi, const void* res) -> int {
+        if (ww.type != KF_T_NF4) {
+            void* ys[1] = {yy};
+            return linear_any(ctx, 1, ys, &ww, x, M, epi, res, nullptr, 0.f);
+        }
+        if (M <= 8) return kf_nf4_gemv(ctx, yy, &ww, x, M, epi, res);
+        int r = kf_ensure_buf(ctx, &ctx->deq_w, &ctx->deq_w_bytes, (size_t)ww.rows * ww.cols * 2);
+        if (!r) r = kf_nf4_dequant(ctx, &ww, ctx->deq_w);
+        if (r) return r;
+        kf_tensor_desc bw = {};
+        bw.data_dev = ctx->deq_w, bw.rows = ww.rows, bw.cols = ww.cols, bw.type = KF_T_BF16;
+        void* ys[1] = {yy};
+        return linear_any(ctx, 1, ys, &bw, x, M, epi, res, nullptr, 0.f);
+    };
+    if (epilogue == 2) {  // SwiGLU: gate and up into scratch, then CU_swiglu_v0
+        const size_t bytes = (size_t)M * w[0].rows * 2;
+        rc = kf_ensure_buf(ctx, &ctx->tmp0, &ctx->tmp0_bytes, bytes);
+        if (!rc) rc = kf_ensure_buf(ctx, &ctx->tmp1, &ctx->tmp1_bytes, bytes);
+        if (!rc) rc = one(ctx->tmp0, w[0], 0, nullptr);
+        if (!rc) rc = one(ctx->tmp1, w[1], 0, nullptr);
+        if (!rc) rc = kf_swiglu(ctx, y[0], ctx->tmp0, ctx->tmp1, (size_t)M * w[0].rows);
+        return rc;
+    }
+    for (int i = 0; i < n && !rc; i++) rc = one(y[i], w[i], epilogue, residual);
+    return rc;
+}
+static int linear_any(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
+                      const void* norm_w, float norm_eps) {
+    for (int i = 0; i < n; i++)
+        if (w[i].type == KF_T_NF4) return linear_nf4(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
     if (!use_tensor_cores(ctx, n, w, M)) return linear_panels(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
     // ---- tensor-core path: RMSNorm (if any) once into a scratch, then one tcgen05 GEMM per weight ----
     const int K    = w[0].cols;

@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(256) kf_embed_kernel(uint16_t* __restrict__ ou
 extern "C" int kf_embed(kf_ctx* ctx, void* out, const kf_tensor_desc* w, const int32_t* tokens, int M) {
     if (!ctx || !out || !w || !tokens || !w->data_dev) return KF_ERR_BAD_ARG;
     KF_REQUIRE(ctx, M >= 1, "M");
+    if (w->type == KF_T_NF4) return kf_nf4_embed(ctx, out, w, tokens, M);
     const int bits = kf_type_bits(w->type);
     KF_REQUIRE(ctx, bits > 0, "type");
     const uint16_t *gz = nullptr, *gs = nullptr;

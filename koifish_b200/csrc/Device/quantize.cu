@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(256) kf_f8e5m2_encode_kernel(const uint16_t* _
 
 extern "C" size_t kf_quant_data_bytes(int rows, int cols, int type) { return (size_t)rows * cols * kf_type_bits(type) / 8; }
 extern "C" size_t kf_quant_gama_bytes(int rows, int cols, int type, int group) {
+    if (type == KF_T_NF4) return 2 * ((size_t)rows + cols + 16 * (size_t)rows);  // szGama of RT_NormalF, GeQuant.cpp:744
     if (!kf_type_packed(type) || group <= 0)
         return 0;
     return 2 * ((size_t)rows + cols + 2 * ((size_t)rows * cols / group));  // szGama, GeQuant.cpp:518
@@ -168,6 +169,10 @@ extern "C" int kf_quantize(kf_ctx* ctx, const void* w, int rows, int cols, int t
         if (qbias_out)
             *qbias_out = 0;
         return KF_OK;
+    }
+    if (type == KF_T_NF4) {
+        if (qbias_out) *qbias_out = 0;
+        return kf_nf4_quantize(ctx, w, rows, cols, data, gama);
     }
     KF_REQUIRE(ctx, kf_type_packed(type) && gama, "packed type needs a gama buffer");
     const int bits = kf_type_bits(type);
@@ -239,6 +244,7 @@ extern "C" int kf_dequant(kf_ctx* ctx, const kf_tensor_desc* w, void* out) {
         KF_LAUNCH_CHECK(ctx);
         return KF_OK;
     }
+    if (w->type == KF_T_NF4) return kf_nf4_dequant(ctx, w, out);
     KF_REQUIRE(ctx, kf_type_packed(w->type) && kf_has_gama(*w) && w->group > 0, "packed tensor needs gama + group");
     const int bits = kf_type_bits(w->type), per = 128 / bits;
     KF_REQUIRE(ctx, n % w->group == 0 && w->group % per == 0, "group / word alignment");

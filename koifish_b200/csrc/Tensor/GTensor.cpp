@@ -16,6 +16,7 @@ int kfType(typNUMBER t) {
         case typNUMBER::Q2: return KF_T_Q2;
         case typNUMBER::T_SIGN: return KF_T_SIGN;
         case typNUMBER::T_BINARY: return KF_T_BINARY;
+        case typNUMBER::Q4_NF: return KF_T_NF4;
     }
     return KF_T_BF16;
 }
@@ -27,6 +28,7 @@ const char* typName(typNUMBER t) {
         case typNUMBER::Q2: return "Q2";
         case typNUMBER::T_SIGN: return "T_SIGN";
         case typNUMBER::T_BINARY: return "T_BINARY";
+        case typNUMBER::Q4_NF: return "Q4(NF4)";
     }
     return "?";
 }
@@ -34,7 +36,8 @@ double BitPE(typNUMBER t) {
     switch (t) {
         case typNUMBER::BF16: return 16;
         case typNUMBER::F8E5M2: return 8;
-        case typNUMBER::Q4: return 4;
+        case typNUMBER::Q4:
+        case typNUMBER::Q4_NF: return 4;
         case typNUMBER::Q2:
         case typNUMBER::T_SIGN: return 2;
         case typNUMBER::T_BINARY: return 1;
@@ -89,6 +92,7 @@ bool QUANT_CARD::Init4Neuron(const std::string& name, const JSON& jQuant) {
 }
 typNUMBER QUANT_CARD::tpQuant() const {
     if (type == F8Ex) return typNUMBER::F8E5M2;
+    if (type == RTNf) return typNUMBER::Q4_NF;
     if (yyang == I_TERNARY) return typNUMBER::T_SIGN;  // bit2typ(), GeQuant.cpp:127-137
     switch (default_bits) {
         case 4: return typNUMBER::Q4;
@@ -178,7 +182,10 @@ hQUANT GeQuant::MakeInstance(const std::string& neuron_name, const JSON& jQuant)
     switch (card.type) {
         case RTN:
         case F8Ex: break;
-        case RTNf: throw std::runtime_error("quantizer entry '" + card.matched_key + "': NF4 / RTNf (no quant_method) is a 'next' row (SURVEY 8f N2), not built yet");
+        case RTNf:
+            if (card.default_bits != 4)  // RT_NormalF also accepts 3 bits (NF3), which no PackedQ storage type carries
+                throw std::runtime_error("quantizer entry '" + card.matched_key + "': NormalFloat (no quant_method) is built for bits = 4 only");
+            break;
         case AWQ: throw std::runtime_error("quantizer entry '" + card.matched_key + "': vendor AWQ layout is a 'next' row (SURVEY 8f N2), not built yet");
         default: return nullptr;
     }

@@ -16,7 +16,7 @@
 namespace koifish {
 
 // g_float.hpp:84-117 (the subset on the hot path)
-enum class typNUMBER : uint8_t { BF16, F8E5M2, Q4, Q2, T_SIGN, T_BINARY };
+enum class typNUMBER : uint8_t { BF16, F8E5M2, Q4, Q2, T_SIGN, T_BINARY, Q4_NF /* Q4 under QUANT_MODE::RTNf: NormalFloat4 + per-row LUT */ };
 int kfType(typNUMBER t);               // -> KF_T_*
 const char* typName(typNUMBER t);
 double BitPE(typNUMBER t);             // bits per element (src/Utils/GST_float.cpp:51)

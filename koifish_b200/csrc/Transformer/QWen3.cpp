@@ -441,6 +441,8 @@ int Fish::ForwardOnRLS(int M, bool want_logits) {
     if (tp_world > 1) {
         KF_TRY(kf_tp_begin(ctx));
         tp_fuse = 2 * (int)attn.size() <= 256 && kf_exchange_fused_ready(ctx, M, config.n_embd) == 1;
+        for (size_t l = 0; l < attn.size() && tp_fuse; l++)  // NormalFloat4 weights have their own matmul (nf4.cu): stand-alone exchange
+            tp_fuse = attn[l]->proj_cat.w->type != typNUMBER::Q4_NF && ffn[l]->down.w->type != typNUMBER::Q4_NF;
     }
     KF_TRY(embed.cuInfer(x, M));
     for (size_t l = 0; l < attn.size(); l++) {

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <limits>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -445,6 +446,65 @@ struct kfo_model {
     std::vector<std::vector<uint16_t>> w; /* dequantised bf16 weights by tensor id */
     std::vector<uint16_t> kc, vc;         /* [L][max_seq][kv_dim] : KVCache, src/Utils/Cache.cpp:14-60 */
 };
+/* ------------------------------------------------------------------------------------------------
+ * NormalFloat4, QUANT_MODE::RTNf -- what {"bits": 4} without a quant_method selects (GeQuant.cpp:1270-1280).
+ * Quantise: GeQuant::_row_lut (GeQuant.cpp:696-732): per row, Distri_PIPE::Next over the fp32 values (vmin / vmax / abs_max, GTensor.hpp:141-148),
+ * Prepare(16) in its default symmetric case (:674-681: scale = abs_max > 0 ? 1 / abs_max : 1 ; codebook[i] = table[i] / scale), the LUT stored
+ * as bf16 (Float2T<floatGama>), the code = first minimum of |w - codebook[i]| over the FP32 codebook (X2NormalF :684-700), packed by
+ * BIT_SET_k (CLI_params.cpp:2177-2191: MSB-first bit stream, element i at bit 4 i).  No row / column normalisation (NORMAL_MODE::NO_NORMAL).
+ * Dequant: CU_Q42X_NF4 (quantizer.cu:612-654) with rc_normal = 0: w = lut[row][code] (id0 = high nibble = the even element).
+ * ---------------------------------------------------------------------------------------------- */
+static const float kfo_nf4_table[16] = {-1.0f, -0.6961928009986877f, -0.5250730514526367f, -0.39491748809814453f, -0.28444138169288635f,
+                                        -0.18477343022823334f, -0.09105003625154495f, 0.0f, 0.07958029955625534f, 0.16093020141124725f,
+                                        0.24611230194568634f, 0.33791524171829224f, 0.44070982933044434f, 0.5626170039176941f,
+                                        0.7229568362236023f, 1.0f}; /* NF4_LUT::table, src/g_float.hpp:543-558 */
+extern "C" int kfo_nf4_quantize(const uint16_t* w, int rows, int cols, uint8_t* data_out, uint16_t* gama_out) {
+    if (cols % 2) return -1;
+    memset(gama_out, 0, sizeof(uint16_t) * ((size_t)rows + cols));
+    memset(data_out, 0, (size_t)rows * cols / 2);
+#pragma omp parallel for schedule(static)
+    for (int row = 0; row < rows; row++) {
+        const uint16_t* wr = w + (size_t)row * cols;
+        float vmin = FLT_MAX, vmax = -FLT_MAX;
+        for (int i = 0; i < cols; i++) {
+            const float a = kfo_bf16_to_f32(wr[i]);
+            vmax = std::max(vmax, a), vmin = std::min(vmin, a);
+        }
+        const float abs_max = std::max(std::fabs(vmin), std::fabs(vmax));
+        const float scale   = abs_max > 0 ? 1.0f / abs_max : 1.0f;
+        float cb[16];
+        uint16_t* lut = gama_out + rows + cols + (size_t)row * 16;
+        for (int i = 0; i < 16; i++) cb[i] = kfo_nf4_table[i] / scale, lut[i] = kfo_f32_to_bf16(cb[i]);
+        uint8_t* q = data_out + (size_t)row * cols / 2;
+        for (int i = 0; i < cols; i++) {
+            const float a = kfo_bf16_to_f32(wr[i]);
+            float best    = std::numeric_limits<float>::max();
+            int bi        = 0;
+            for (int c = 0; c < 16; c++) {
+                const float d = std::abs(a - cb[c]);
+                if (d < best) best = d, bi = c;
+            }
+            size_t boff = (size_t)i * 4; /* BIT_SET_k */
+            for (int b = 0; b < 4; b++, boff++)
+                if ((bi >> (3 - b)) & 1) q[boff / 8] |= (uint8_t)(1u << (7 - boff % 8));
+        }
+    }
+    return 0;
+}
+extern "C" int kfo_nf4_dequant(const uint8_t* data, const uint16_t* gama, int rows, int cols, uint16_t* out) {
+    if (cols % 2) return -1;
+#pragma omp parallel for schedule(static)
+    for (int row = 0; row < rows; row++) {
+        const uint16_t* lut = gama + rows + cols + (size_t)row * 16;
+        const uint8_t* q    = data + (size_t)row * cols / 2;
+        for (int k = 0; k < cols / 2; k++) {
+            out[(size_t)row * cols + 2 * k]     = lut[(q[k] >> 4) & 0x0F];
+            out[(size_t)row * cols + 2 * k + 1] = lut[q[k] & 0x0F];
+        }
+    }
+    return 0;
+}
+
 static void make_weight(std::vector<uint16_t>& dst, int rows, int cols, int bits, int mode, int group, uint64_t seed, float sigma) {
     const size_t n = (size_t)rows * cols;
     dst.resize(n);
@@ -455,6 +515,13 @@ static void make_weight(std::vector<uint16_t>& dst, int rows, int cols, int bits
         std::vector<uint8_t> q(n);
         kfo_f8e5m2_encode(dst.data(), n, q.data());
         kfo_f8e5m2_decode(q.data(), n, dst.data());
+        return;
+    }
+    if (mode == KFO_NF4) {
+        std::vector<uint8_t> data(n / 2);
+        std::vector<uint16_t> gama((size_t)rows + cols + 16 * (size_t)rows);
+        kfo_nf4_quantize(dst.data(), rows, cols, data.data(), gama.data());
+        kfo_nf4_dequant(data.data(), gama.data(), rows, cols, dst.data());
         return;
     }
     kfo_qrange qr;
@@ -480,8 +547,8 @@ extern "C" kfo_model* kfo_model_create(const kfo_model_config* cfg) {
     auto S = [&](int id) { return kfo_tensor_seed(c.seed, id); };
     make_weight(m->w[0], c.vocab, E, c.embed_bits, c.embed_mode, c.group, S(0), c.sigma);
     make_norm(m->w[1], E, S(1), c.norm_sigma);
-    if (!c.tie_embed)
-        make_weight(m->w[2], c.vocab, E, c.embed_bits, c.embed_mode, c.group, S(2), c.sigma);
+    if (!c.tie_embed) /* the quantizer keys select by tensor-name substring (G_Has_, GeQuant.cpp:1226): "embed_tokens" does not match lm_head.weight */
+        make_weight(m->w[2], c.vocab, E, 16, 0, c.group, S(2), c.sigma);
     for (int l = 0; l < c.n_layer; l++) {
         const int b = 16 + 16 * l;
         make_norm(m->w[b + 0], E, S(b + 0), c.norm_sigma);

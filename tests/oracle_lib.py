@@ -16,8 +16,9 @@ REF_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_ref.so")
 # the reference's own CUDA kernels (src/Device/CUDA/T.cu + headers) compiled for sm_100a: with the reference's nvcc flags ("fma": the bf16
 # multiply-subtract of the dequant is contracted to one fma.rn.bf16), and with -fmad=false / no fast-math ("nofma": two roundings, IEEE division)
 REFGPU_SO = {"fma": os.path.join(ORACLE_DIR, "_ref", "libkoifish_refgpu.so"), "nofma": os.path.join(ORACLE_DIR, "_ref", "libkoifish_refgpu_nofma.so")}
+REFQ_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_refq.so")  # the reference's quantizer.cu (NF4 dequant kernel)
 
-RTN_ASYM, RTN_SYM, YYANG = 0, 1, 2
+RTN_ASYM, RTN_SYM, YYANG, NF4 = 0, 1, 2, 3
 
 
 def build_oracle(force=False):
@@ -31,6 +32,8 @@ def build_oracle(force=False):
     if os.path.exists("/root/reference/src/Device/CUDA/T.cu"):
         src = os.path.join(ORACLE_DIR, "ref_kernels.cu")
         stale = any(not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src) for so in REFGPU_SO.values())
+        srcq = os.path.join(ORACLE_DIR, "ref_kernels_q.cu")
+        stale = stale or not os.path.exists(REFQ_SO) or os.path.getmtime(REFQ_SO) < os.path.getmtime(srcq)
         if force or stale:
             subprocess.check_call(["make", "-C", ORACLE_DIR, "refgpu"], stdout=subprocess.DEVNULL)
 
@@ -94,6 +97,8 @@ def lib():
         L.kfo_rope.argtypes = [_u16p, C.c_int, C.c_int, C.c_int, C.c_float]
         L.kfo_swiglu.argtypes = [_u16p, _u16p, _u16p, C.c_size_t]
         L.kfo_add.argtypes = [_u16p, _u16p, _u16p, C.c_size_t]
+        L.kfo_nf4_quantize.argtypes = [_u16p, C.c_int, C.c_int, _u8p, _u16p]
+        L.kfo_nf4_dequant.argtypes = [_u8p, _u16p, C.c_int, C.c_int, _u16p]
         L.kfo_sample.restype = C.c_int
         L.kfo_sample.argtypes = [_u16p, C.c_int, C.c_float, C.c_int, C.c_float, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]
         L.kfo_attention_decode.argtypes = [_u16p, _u16p, _u16p, _u16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -123,6 +128,18 @@ def lib():
 def set_dequant_fma(fused):
     """1 (default): one bf16 rounding in the dequant, as the reference built for sm_90+; 0: two roundings (see koifish_oracle.h)."""
     lib().kfo_set_dequant_fma(int(fused))
+
+
+_refq = None
+
+
+def refq():
+    """the reference's quantizer.cu compiled for sm_100a (CU_Q42X_NF4), or None when it was not built (reference tree absent)"""
+    global _refq
+    if _refq is None and os.path.exists(REFQ_SO):
+        _refq = C.CDLL(REFQ_SO)
+        _refq.refq_nf4_dequant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    return _refq
 
 
 def refgpu(variant="fma"):
@@ -195,6 +212,20 @@ def quantize(w, rows, cols, bits, group=128, mode=RTN_ASYM):
     rc = lib().kfo_quantize(w, rows, cols, bits, group, mode, data, gama)
     assert rc == 0, rc
     return data, gama
+
+
+def nf4_quantize(w, rows, cols):
+    w = np.ascontiguousarray(w, dtype=np.uint16).reshape(-1)
+    data = np.zeros(rows * cols // 2, dtype=np.uint8)
+    gama = np.zeros(rows + cols + 16 * rows, dtype=np.uint16)
+    assert lib().kfo_nf4_quantize(w, rows, cols, data, gama) == 0
+    return data, gama
+
+
+def nf4_dequant(data, gama, rows, cols):
+    out = np.zeros(rows * cols, dtype=np.uint16)
+    assert lib().kfo_nf4_dequant(np.ascontiguousarray(data), np.ascontiguousarray(gama), rows, cols, out) == 0
+    return out.reshape(rows, cols)
 
 
 def pack_codes(codes, bits):

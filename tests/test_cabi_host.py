@@ -87,9 +87,23 @@ def test_quant_card_selection_matches_reference_rules():
     assert (t, m, qb) == (kf.KF_T_BINARY, kf.KF_Q_YYANG, 0)
 
 
+def test_bits_without_method_selects_normalfloat4():
+    # {"bits": 4} with no quant_method: QUANT_MODE::RTNf (GeQuant.cpp:1270-1280) -> typNUMBER::Q4 carrying NormalFloat4 codes + per-row codebooks
+    cfg = kf.qwen3_config(2, 1024, 3072, 16, 8, quantizer={"self_attn": {"bits": 4}, "mlp": {"bits": 8}})
+    st, t, *_ = _quant_of(cfg, "model.layers.0.self_attn.q_proj.weight")
+    assert (st, t) == (0, kf.KF_T_NF4)
+    assert _quant_of(cfg, "model.layers.0.mlp.up_proj.weight")[1] == kf.KF_T_F8E5M2
+    # bits outside {1, 2, 4, 8} fall back to 4 (Init4Neuron, GeQuant.cpp:1253-1256: `default_bits = 4; assert(0)` -- a release build carries on)
+    cfg = kf.qwen3_config(2, 1024, 3072, 16, 8, quantizer={"self_attn": {"bits": 3}})
+    assert _quant_of(cfg, "model.layers.0.self_attn.q_proj.weight")[:2] == (0, kf.KF_T_NF4)
+    # bits 2 without a method is not a reference mode (RT_NormalF asserts 4 or 3 bits)
+    cfg = kf.qwen3_config(2, 1024, 3072, 16, 8, quantizer={"self_attn": {"bits": 2}})
+    st, *_, msg = _quant_of(cfg, "model.layers.0.self_attn.q_proj.weight")
+    assert st == kf.KF_ERR_UNSUPPORTED and msg
+
+
 def test_out_of_scope_quant_methods_fail_loudly():
-    for q in ({"self_attn": {"bits": 4}},                       # no method -> NF4 (RTNf): a 'next' row
-              {"self_attn": {"quant_method": "awq", "bits": 4}},  # vendor AWQ: a 'next' row
+    for q in ({"self_attn": {"quant_method": "awq", "bits": 4}},  # vendor AWQ: a 'next' row
               {"self_attn": {"quant_method": "bitnet"}},
               {"self_attn": {"quant_method": "RTN", "bits": 1}}):
         cfg = kf.qwen3_config(2, 1024, 3072, 16, 8, quantizer=q)

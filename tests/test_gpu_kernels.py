@@ -850,3 +850,58 @@ def test_linear_axb_alpha_beta_bias(ctx, kind, M):
     dd = ctx.array(d0)
     kf.linear_axb(ctx, t, ctx.array(x), M, dd)
     assert np.array_equal(dd.numpy(np.uint16), kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16))
+
+
+# ---------------------------------------------------------------------------------------------- NormalFloat4 ({"bits": 4} without a quant_method)
+def _nf4_tensor(ctx, rows, cols, seed):
+    w = ol.fill_normal(rows * cols, seed, 0.02)
+    data, gama = ol.nf4_quantize(w, rows, cols)
+    t = kf.QTensor.from_packed(ctx, data, gama, rows, cols, kf.KF_T_NF4, 0, 0)
+    return w, data, gama, t, ol.nf4_dequant(data, gama, rows, cols)
+
+
+@pytest.mark.parametrize("rows,cols", [(64, 256), (300, 1024), (16, 5120)])
+def test_nf4_quantize_and_dequant_bit_exact(ctx, rows, cols):
+    w, data, gama, t, wdq = _nf4_tensor(ctx, rows, cols, rows + cols)
+    q = kf.quantize(ctx, ctx.array(w), rows, cols, kf.KF_T_NF4, 0, 0)
+    assert np.array_equal(q.gama_numpy(), gama)  # per-row bf16 codebooks
+    assert np.array_equal(q.data_numpy(), data)  # codes: nearest entry of the fp32 codebook, MSB-first nibble stream
+    assert np.array_equal(kf.dequant(ctx, t).numpy(np.uint16).reshape(rows, cols), wdq)
+    toks = np.array([0, rows - 1, rows // 2], dtype=np.int32)
+    got = kf.embed(ctx, t, ctx.array(toks.view(np.uint16)), 3).numpy(np.uint16).reshape(3, cols)
+    assert np.array_equal(got, wdq[toks])
+
+
+def test_nf4_dequant_matches_reference_kernel(ctx):
+    # the reference's own CU_Q42X_NF4 (src/Device/CUDA/kernel/quantizer.cu:612-654, compiled where it lies: oracle/ref_kernels_q.cu) on the
+    # same packed bytes and codebooks
+    ref = ol.refq()
+    if ref is None:
+        pytest.skip("oracle/_ref/libkoifish_refq.so not built (reference tree absent at build time)")
+    rows, cols = 96, 2048
+    w, data, gama, t, wdq = _nf4_tensor(ctx, rows, cols, 5)
+    out = ctx.empty(rows * cols * 2)
+    ctx.sync()
+    assert ref.refq_nf4_dequant(t.gama_ptr, t.data_ptr, out.ptr, rows, cols) == 0
+    assert np.array_equal(out.numpy(np.uint16).reshape(rows, cols), wdq)
+    assert np.array_equal(kf.dequant(ctx, t).numpy(np.uint16).reshape(rows, cols), wdq)
+
+
+@pytest.mark.parametrize("M", [1, 3, 8, 40])
+def test_nf4_linear_matches_oracle(ctx, M):
+    N, K = 272, 2048
+    w, data, gama, t, wdq = _nf4_tensor(ctx, N, K, 17)
+    rng = np.random.default_rng(M)
+    x = rand_bf16(rng, (M, K))
+    y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16)
+    _check_linear(y, wdq, x, M, N, K)
+    res = rand_bf16(rng, (M, N))
+    yr = kf.linear(ctx, t, ctx.array(x), M, kf.KF_EPI_RESIDUAL, ctx.array(res)).numpy(np.uint16)
+    assert np.array_equal(yr.reshape(M, N), ol.add(res, y).reshape(M, N))
+    # fused norm + SwiGLU entry point through the NF4 route
+    nw = ol.f32_to_bf16((1.0 + 0.1 * rng.standard_normal(K)).astype(np.float32))
+    w2, d2, g2, t2, wdq2 = _nf4_tensor(ctx, N, K, 18)
+    got = ol.bf16_to_f32(kf.rmsnorm_linear(ctx, [t, t2], ctx.array(x), ctx.array(nw), M, 1e-6, swiglu=True).numpy(np.uint16)).reshape(M, N)
+    xn = ol.rmsnorm(x, nw, M, K)
+    want = ol.bf16_to_f32(ol.swiglu(ol.linear(wdq, xn, M, N, K), ol.linear(wdq2, xn, M, N, K))).reshape(M, N)
+    assert np.abs(got - want).max() <= 2e-2 * np.abs(want).max()

@@ -38,6 +38,8 @@ def quant_entry(bits, mode):
         return None
     if bits == 8:
         return {"bits": 8}
+    if mode == ol.NF4:
+        return {"bits": 4}  # no quant_method: QUANT_MODE::RTNf
     return {"quant_method": MODE_NAME[mode], "bits": bits}
 
 
@@ -77,7 +79,8 @@ TENSOR_IDS = {"model.embed_tokens.weight": 0, "model.norm.weight": 1, "model.lay
 
 
 @pytest.mark.parametrize("attn,mlp,embed", [((4, ol.RTN_ASYM), (4, ol.RTN_ASYM), (16, 0)), ((8, 0), (4, ol.RTN_ASYM), (16, 0)),
-                                            ((2, ol.YYANG), (1, ol.YYANG), (4, ol.RTN_ASYM))], ids=["q4", "hybrid8_4", "ternary_binary_q4embed"])
+                                            ((2, ol.YYANG), (1, ol.YYANG), (4, ol.RTN_ASYM)), ((4, ol.NF4), (4, ol.NF4), (4, ol.NF4))],
+                         ids=["q4", "hybrid8_4", "ternary_binary_q4embed", "nf4"])
 def test_resident_weights_bit_exact(ctx, attn, mlp, embed):
     model, oracle = build_pair(ctx, attn=attn, mlp=mlp, embed=embed)
     for name, tid in TENSOR_IDS.items():
@@ -87,8 +90,9 @@ def test_resident_weights_bit_exact(ctx, attn, mlp, embed):
 
 @pytest.mark.parametrize("attn,mlp,embed,tie", [((4, ol.RTN_ASYM), (4, ol.RTN_ASYM), (16, 0), True), ((8, 0), (4, ol.RTN_ASYM), (16, 0), True),
                                                 ((2, ol.YYANG), (2, ol.YYANG), (16, 0), False), ((1, ol.YYANG), (1, ol.YYANG), (16, 0), False),
-                                                ((16, 0), (16, 0), (16, 0), True), ((4, ol.RTN_ASYM), (4, ol.RTN_ASYM), (4, ol.RTN_ASYM), True)],
-                         ids=["q4", "hybrid8_4", "ternary", "binary", "bf16", "q4_all"])
+                                                ((16, 0), (16, 0), (16, 0), True), ((4, ol.RTN_ASYM), (4, ol.RTN_ASYM), (4, ol.RTN_ASYM), True),
+                                                ((4, ol.NF4), (4, ol.NF4), (16, 0), True), ((4, ol.NF4), (4, ol.RTN_ASYM), (4, ol.NF4), False)],
+                         ids=["q4", "hybrid8_4", "ternary", "binary", "bf16", "q4_all", "nf4", "nf4_mixed"])
 def test_decode_logits_match_oracle(ctx, attn, mlp, embed, tie):
     model, oracle = build_pair(ctx, attn=attn, mlp=mlp, embed=embed, tie=tie)
     toks = prompt(14, 1024)

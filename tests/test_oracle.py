@@ -388,3 +388,35 @@ def test_sampler_port_reference_heap_selection():
     allowed = set(range(k - 1)) | {int(k - 1 + np.argmax(f[k - 1:]))}
     st = [7]
     assert all(ol.sample(lg, 5.0, k, 1.0, st, selection=1)[0] in allowed for _ in range(200))
+
+
+# ---------------------------------------------------------------------------------------------- NormalFloat4 (QUANT_MODE::RTNf)
+def test_nf4_port_layout_codebook_and_nearest_code():
+    rows, cols = 6, 64
+    w = ol.fill_normal(rows * cols, 11, 0.02).reshape(rows, cols).copy()
+    w[3, :] = 0  # an all-zero row: scale = 1, codebook = the table itself, every code = 7 (0.0)
+    data, gama = ol.nf4_quantize(w, rows, cols)
+    f = ol.bf16_to_f32(w).reshape(rows, cols)
+    table = np.array([-1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453, -0.28444138169288635, -0.18477343022823334,
+                      -0.09105003625154495, 0.0, 0.07958029955625534, 0.16093020141124725, 0.24611230194568634, 0.33791524171829224,
+                      0.44070982933044434, 0.5626170039176941, 0.7229568362236023, 1.0], dtype=np.float32)  # NF4_LUT, g_float.hpp:543-558
+    assert np.all(gama[:rows + cols] == 0)
+    for r in range(rows):
+        amax = np.float32(np.abs(f[r]).max())
+        scale = np.float32(1.0) / amax if amax > 0 else np.float32(1.0)
+        cb = (table / scale).astype(np.float32)
+        assert np.array_equal(gama[rows + cols + 16 * r: rows + cols + 16 * (r + 1)], ol.f32_to_bf16(cb))  # the LUT is bf16(codebook)
+        codes = np.argmin(np.abs(f[r][:, None] - cb[None, :]), axis=1)                                      # first minimum, fp32 codebook
+        byts = data[r * cols // 2:(r + 1) * cols // 2]
+        assert np.array_equal(byts >> 4, codes[0::2]) and np.array_equal(byts & 15, codes[1::2])            # even element = high nibble
+    assert np.all(data[3 * cols // 2:4 * cols // 2] == 0x77)
+    deq = ol.nf4_dequant(data, gama, rows, cols)
+    lut = gama[rows + cols:].reshape(rows, 16)
+    for r in range(rows):
+        byts = data[r * cols // 2:(r + 1) * cols // 2]
+        assert np.array_equal(deq[r, 0::2], lut[r][byts >> 4]) and np.array_equal(deq[r, 1::2], lut[r][byts & 15])
+    # the extreme of every row is reproduced exactly (code 0 or 15 = -+abs_max)
+    fd = ol.bf16_to_f32(deq).reshape(rows, cols)
+    for r in (0, 1, 2, 4, 5):
+        k = int(np.argmax(np.abs(f[r])))
+        assert fd[r, k] == f[r, k]
