@@ -214,6 +214,8 @@ int kf_sample(kf_ctx* ctx, int32_t* out_tokens_dev, const void* logits_bf16_dev,
 int kf_nccl_unique_id(void* id_out_128_bytes);
 int kf_ctx_init_nccl(kf_ctx* ctx, const void* id_128_bytes, int rank, int world);
 int kf_allreduce_bf16(kf_ctx* ctx, void* buf_dev, size_t count); /* in-place sum over ranks, on the stream */
+/* all-gathered vocabulary slices [world][M][vl] (bf16) -> logits rows [M][world * vl] in one launch (vocab-sharded lm_head) */
+int kf_relayout_wmv(kf_ctx* ctx, void* out_dev, const void* in_dev, int world, int M, int vl);
 int kf_allreduce_f32(kf_ctx* ctx, float* buf_dev, size_t count);
 int kf_allgather(kf_ctx* ctx, void* out_dev, const void* in_dev, size_t bytes_per_rank);
 /* ---- the decode exchange over NVLink / NVSwitch PEER MEMORY, fused with the residual add (p2p.cu): one launch instead of

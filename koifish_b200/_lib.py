@@ -82,6 +82,7 @@ SIGNATURES = {
     "kf_p2p_ready": (_I, [_P]),
     "kf_p2p_release": (_I, [_P]),
     "kf_allreduce_residual": (_I, [_P, _P, _P, _P, _SZ]),
+    "kf_relayout_wmv": (_I, [_P, _P, _P, _I, _I, _I]),
     "kf_tp_begin": (_I, [_P]),
     "kf_exchange_fused_ready": (_I, [_P, _I, _I]),
     "kf_linear_exchange": (_I, [_P, _P, _P, _P, _I, _P]),

@@ -85,6 +85,7 @@ extern "C" int kf_ctx_destroy(kf_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     kf_p2p_destroy(ctx);
     kf_gemv_tma_destroy(ctx);
+    kf_tmap_cache_destroy(ctx);
     if (ctx->nccl) {
         auto f = (fn_ncclCommDestroy)nccl_sym("ncclCommDestroy");
         if (f)

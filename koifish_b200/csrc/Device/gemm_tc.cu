@@ -23,11 +23,16 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <tuple>
 
 #include "kf_common.cuh"
 
-#ifndef KF_TC_EXP
-#define KF_TC_EXP 0  // tuning experiments only (bit 0: no expansion, 1: no TMEM store, 2: no scale / zero fetch in the loop)
+// tuning experiments (bit 0: no expansion, 1: no TMEM store, 2: no scale / zero fetch in the loop ...): debug builds only
+// (KF_NVCC_DEFS="-DKF_DEBUG_KNOBS -DKF_TC_EXP=n"); a release build compiles them out
+#if !defined(KF_DEBUG_KNOBS) || !defined(KF_TC_EXP)
+#undef KF_TC_EXP
+#define KF_TC_EXP 0
 #endif
 
 namespace {
@@ -764,6 +769,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
 // ---- host side --------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct TmapKey {
+    const void* base;
+    uint64_t inner, outer;
+    uint32_t box_inner, box_outer, dt, sw, esize;
+    bool operator<(const TmapKey& o) const {
+        return std::tie(base, inner, outer, box_inner, box_outer, dt, sw, esize) <
+               std::tie(o.base, o.inner, o.outer, o.box_inner, o.box_outer, o.dt, o.sw, o.esize);
+    }
+};
+using TmapCache = std::map<TmapKey, CUtensorMap>;
 EncodeTiledFn encode_fn() {
     static EncodeTiledFn fn = [] {
         void* f = nullptr;
@@ -775,6 +790,16 @@ EncodeTiledFn encode_fn() {
 }
 int make_map_2d(kf_ctx* ctx, CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
                 uint32_t box_outer, CUtensorMapSwizzle sw) {
+    // a tensor map depends only on (address, geometry, box, swizzle): encode each once per context and reuse it (weights and the context's
+    // activation scratch keep their addresses from token to token)
+    TmapKey key = {base, inner, outer, box_inner, box_outer, (uint32_t)dt, (uint32_t)sw, (uint32_t)esize};
+    TmapCache* cache = reinterpret_cast<TmapCache*>(ctx->tmap_cache);
+    if (!cache) ctx->tmap_cache = cache = new TmapCache();
+    auto hit = cache->find(key);
+    if (hit != cache->end()) {
+        *tm = hit->second;
+        return KF_OK;
+    }
     EncodeTiledFn fn = encode_fn();
     KF_REQUIRE(ctx, fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     KF_REQUIRE(ctx, ((uintptr_t)base & 15) == 0 && (inner * esize) % 16 == 0, "TMA needs 16-byte aligned rows");
@@ -790,6 +815,8 @@ int make_map_2d(kf_ctx* ctx, CUtensorMap* tm, CUtensorMapDataType dt, int esize,
         ctx->last_error = b;
         return KF_ERR_CUDA;
     }
+    if (cache->size() > 4096) cache->clear();  // models hold a few hundred weights; bound it anyway
+    (*cache)[key] = *tm;
     return KF_OK;
 }
 
@@ -799,10 +826,10 @@ int launch_tc(kf_ctx* ctx, GemmParams& p, const void* const* wdata, int nw, cons
     constexpr bool A_TMEM = FMT != TF_BF16;
     const size_t smem    = Rings<FMT, BN>::SMEM;
     auto kern            = kf_gemm_tc_kernel<FMT, MODE, BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kf_ctx::kMaxDevices] = {};  // function attributes are per device (one flag per instantiation and device)
+    if (!attr_set[ctx->device]) {
         KF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[ctx->device] = true;
     }
     // ---- decomposition: row tiles x token tiles x split-K, walked round-robin by one CTA per SM ----
     p.n_tiles = 0;
@@ -872,6 +899,10 @@ int tc_format(const kf_tensor_desc* w, int* fmt, int* mode, int deq_fma) {
 }
 
 }  // namespace
+void kf_tmap_cache_destroy(kf_ctx* ctx) {
+    delete reinterpret_cast<TmapCache*>(ctx->tmap_cache);
+    ctx->tmap_cache = nullptr;
+}
 
 // The k order the tensor-core kernel expects for weights of w's type: identity for bf16 / f8, the extraction-friendly permutation
 // inside every 32-wide slot for the packed types.  Returns x itself or the context's scratch holding the permuted copy.

@@ -839,10 +839,10 @@ int launch_one(kf_ctx* ctx, const GemvParams& p0) {
     }
     KF_REQUIRE(ctx, smem <= kSmemCap, "internal: k-slice does not fit shared memory");
     auto kern            = kf_gemv_kernel<FMT, MODE, NT, MXS, RT>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
+    static bool attr_set[kf_ctx::kMaxDevices] = {};  // function attributes are per device (one flag per instantiation and device)
+    if (!attr_set[ctx->device]) {
         KF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
-        attr_set = true;
+        attr_set[ctx->device] = true;
     }
     dim3 grid(p.total_rb, p.S);
     if (p.cluster) {

@@ -13,6 +13,7 @@
 struct ncclComm;
 
 struct kf_ctx {
+    static constexpr int kMaxDevices = 64;
     int device           = 0;
     cudaStream_t stream  = nullptr;
     bool own_stream      = false;
@@ -63,6 +64,7 @@ struct kf_ctx {
     // tensor parallel
     ncclComm* nccl = nullptr;
     int rank = 0, world = 1;
+    void* tmap_cache = nullptr;  // encoded TMA tensor maps, keyed by (address, geometry, box) (gemm_tc.cu)
     void* p2p = nullptr;  // peer-memory exchange state (p2p.cu)
     int tp_fused  = 1;    // knob: the decode exchange rides on the matmul kernels (kf_tp.cuh) when the peer buffers are attached
     int tp_stride = 256;  // epochs reserved per forward (>= exchanges per forward, even)
@@ -128,6 +130,7 @@ static inline bool kf_has_gama(const kf_tensor_desc& w) { return w.gama_dev || (
 
 void kf_p2p_destroy(kf_ctx* ctx);
 void kf_gemv_tma_destroy(kf_ctx* ctx);
+void kf_tmap_cache_destroy(kf_ctx* ctx);  // gemm_tc.cu
 // gemv_tma.cu: KF_OK = launched, 1 = request not covered by this kernel (caller falls back to gemv.cu), < 0 = error
 int kf_gemv_tma(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                 const void* norm_w, float norm_eps);

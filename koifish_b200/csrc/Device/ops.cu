@@ -170,6 +170,21 @@ extern "C" int kf_residual_add_f32(kf_ctx* ctx, void* out, const void* res, cons
     KF_LAUNCH_CHECK(ctx);
     return KF_OK;
 }
+// all-gathered vocabulary slices [W][M][vl] -> logits rows [M][W * vl], 16 bytes per thread
+__global__ void __launch_bounds__(256) kf_relayout_wmv_kernel(uint4* __restrict__ out, const uint4* __restrict__ in, int W, int M, int vl8) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)W * M * vl8;
+    if (i >= n) return;
+    const int j = (int)(i % vl8), m = (int)((i / vl8) % M), r = (int)(i / ((size_t)vl8 * M));
+    out[((size_t)m * W + r) * vl8 + j] = in[i];
+}
+extern "C" int kf_relayout_wmv(kf_ctx* ctx, void* out, const void* in, int W, int M, int vl) {
+    if (!ctx || !out || !in || out == in) return KF_ERR_BAD_ARG;
+    KF_REQUIRE(ctx, vl % 8 == 0 && (((uintptr_t)out | (uintptr_t)in) & 15) == 0, "vocabulary slice must be a multiple of 8 bf16, 16-byte aligned");
+    const size_t n = (size_t)W * M * (vl / 8);
+    kf_relayout_wmv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint4*)out, (const uint4*)in, W, M, vl / 8);
+    KF_LAUNCH_CHECK(ctx);
+    return KF_OK;
+}
 int kf_axb_epilogue(kf_ctx* ctx, void* d, const float* acc, const void* bias, float alpha, float beta, int rows, size_t n) {
     kf_axb_epilogue_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((uint16_t*)d, acc, (const uint16_t*)bias, alpha, beta, rows, n);
     KF_LAUNCH_CHECK(ctx);

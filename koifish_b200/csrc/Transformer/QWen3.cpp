@@ -191,12 +191,10 @@ int Head4Token::cuInfer_1(void* logits, const void* inp, int M) {
     uint16_t* local = (uint16_t*)logits + (size_t)f->logit_rows * f->config.vocab;
     KF_TRY(kf_linear(f->ctx, local, &d, f->xb, M, KF_EPI_NONE, nullptr));
     KF_TRY(kf_allgather(f->ctx, logits, local, (size_t)M * vl * 2));
-    if (M > 1) {  // [W][M][vl] -> [M][W*vl]
+    if (M > 1) {  // [W][M][vl] -> [M][W*vl]: one copy out of the way + one re-layout kernel (not W x M memcpy nodes)
         uint16_t* tmp = local;
         KF_TRY(kf_d2d(f->ctx, tmp, logits, (size_t)M * f->config.vocab * 2));
-        for (int r = 0; r < W; r++)
-            for (int m = 0; m < M; m++)
-                KF_TRY(kf_d2d(f->ctx, (uint16_t*)logits + (size_t)m * f->config.vocab + (size_t)r * vl, tmp + ((size_t)r * M + m) * vl, (size_t)vl * 2));
+        KF_TRY(kf_relayout_wmv(f->ctx, logits, tmp, W, M, vl));
     }
     return KF_OK;
 }
