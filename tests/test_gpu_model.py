@@ -188,7 +188,7 @@ def test_forward_argument_errors(ctx):
         with pytest.raises(kf.KoifishError):
             model.forward(toks, pos, seq_mode=mode)
     with pytest.raises(kf.KoifishError):
-        kf.Model(ctx, kf.qwen3_config(2, 256, 512, 4, 2, 64, 1024, {"self_attn": {"bits": 4}}))  # NF4: not built
+        kf.Model(ctx, kf.qwen3_config(2, 256, 512, 4, 2, 64, 1024, {"self_attn": {"quant_method": "awq", "bits": 4}}))  # vendor AWQ layout: not built
     with pytest.raises(kf.KoifishError):
         model.set_tensor("model.layers.0.nope.weight", np.zeros((4, 4), dtype=np.uint16))
 
