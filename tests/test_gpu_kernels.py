@@ -905,3 +905,56 @@ def test_nf4_linear_matches_oracle(ctx, M):
     xn = ol.rmsnorm(x, nw, M, K)
     want = ol.bf16_to_f32(ol.swiglu(ol.linear(wdq, xn, M, N, K), ol.linear(wdq2, xn, M, N, K))).reshape(M, N)
     assert np.abs(got - want).max() <= 2e-2 * np.abs(want).max()
+
+
+# ---------------------------------------------------------------------------------------------- round-2 regressions
+@pytest.mark.parametrize("M", [1, 5, 40])
+def test_mixed_storage_types_share_a_call(ctx, M):
+    # the quantizer card selects the type per tensor-name substring (Init4Neuron), so Q / K / V or gate / up of one block may differ:
+    # kf_rmsnorm_linear / kf_linear_multi group the weights that agree into one launch each; results equal the separate calls
+    K = 1024
+    rng = np.random.default_rng(99 + M)
+    ws = [make_weight(ctx, kind, n, K, 600 + i)[0] for i, (kind, n) in enumerate((((4, ol.RTN_ASYM), 256), ("f8", 128), ((4, ol.RTN_ASYM), 128)))]
+    xd = ctx.array(rand_bf16(rng, (M, K)))
+    outs = kf.linear_multi(ctx, ws, xd, M)
+    for w, o in zip(ws, outs):
+        assert np.array_equal(o.numpy(np.uint16), kf.linear(ctx, w, xd, M).numpy(np.uint16))
+    nw = ctx.array(ol.f32_to_bf16((1.0 + 0.1 * rng.standard_normal(K)).astype(np.float32)))
+    xn = kf.rmsnorm(ctx, xd, nw, M, K)
+    for w, o in zip(ws, kf.rmsnorm_linear(ctx, ws, xd, nw, M)):
+        assert np.array_equal(o.numpy(np.uint16), kf.linear(ctx, w, xn, M).numpy(np.uint16))
+    # SwiGLU of a mixed gate / up pair: two matmuls + the stand-alone CU_swiglu_v0
+    wg, wu = make_weight(ctx, (4, ol.RTN_ASYM), 256, K, 610)[0], make_weight(ctx, "bf16", 256, K, 611)[0]
+    fused = kf.rmsnorm_linear(ctx, [wg, wu], xd, nw, M, swiglu=True).numpy(np.uint16)
+    g, u = kf.linear(ctx, wg, xn, M), kf.linear(ctx, wu, xn, M)
+    want = kf.swiglu(ctx, g, u, M * 256).numpy(np.uint16)
+    # a bf16 weight on its own goes to the tensor-core kernel, inside the mixed pair to the skinny one: same values, another fp32 summation
+    # order -- equal to within one bf16 ulp of the gate / up products
+    a, b = ol.bf16_to_f32(fused), ol.bf16_to_f32(want)
+    assert np.all(np.abs(a - b) <= np.maximum(np.abs(a), np.abs(b)) * 2.0 ** -6 + 1e-3 * np.sqrt(np.mean(b ** 2)))
+    assert (fused == want).mean() > 0.97
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 512, 2048), (4, 384, 4096), (8, 256, 1024)])
+def test_gemv_tma_exact_variant_matches_oracle(ctx, M, N, K):
+    # the opt-in persistent TMA-fed stream-K kernel (gemv_tma.cu, knob gemv_tma = 1), bit-faithful arithmetic
+    t, wdq = make_weight(ctx, (4, ol.RTN_ASYM), N, K, 1700 + M)
+    x = rand_bf16(np.random.default_rng(M), (M, K))
+    ctx.set_int("gemv_tma", 1)
+    try:
+        y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16)
+    finally:
+        ctx.set_int("gemv_tma", 0)
+    _check_linear(y, wdq, x, M, N, K)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 512, 2048), (8, 256, 1024)])
+def test_gemv_tma_fast_variant_matches_oracle(ctx, M, N, K):
+    t, wdq = make_weight(ctx, (4, ol.RTN_ASYM), N, K, 1800 + M)
+    x = rand_bf16(np.random.default_rng(M), (M, K))
+    ctx.set_int("gemv_tma", 1)
+    try:
+        y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16)
+    finally:
+        ctx.set_int("gemv_tma", 0)
+    _check_linear(y, wdq, x, M, N, K, noise=FAST_NOISE)

@@ -407,3 +407,79 @@ def test_qwen3_0p6b_greedy_128_tokens_top1(ctx, theta):
           % (ctx.arith, theta, pos, worst, same, steps + 1, agree, decided))
     assert agree == decided and decided >= (steps + 1) // 4
     assert same >= int(0.95 * (steps + 1))  # undecided positions are near-ties; nearly all still agree
+
+
+def test_graphs_are_recaptured_when_a_context_scratch_moves(ctx):
+    # a captured decode step holds raw pointers into the context's scratch buffers (split-K workspace, tensor-core staging).  When a later
+    # call grows one of them (here: a prefill panel that needs the tensor-core staging buffers, then a much larger stand-alone matmul),
+    # kf_scratch_generation() changes and the runtime must drop and re-capture its graphs instead of replaying into freed memory.
+    model, _ = build_pair(ctx)
+    ref, _ = build_pair(ctx)
+    ref.set_graphs(False)
+    toks = prompt(40, 1024)
+    gen0 = ctx.lib.kf_scratch_generation(ctx.h)
+
+    def step(m, tok, pos):
+        lg, _ = m.forward([tok], [pos])
+        return lg[0].copy()
+
+    for pos in range(3):  # eager, capture, replay
+        assert np.array_equal(step(model, toks[pos], pos), step(ref, toks[pos], pos))
+    for m in (model, ref):
+        m.forward(toks[3:35], list(range(3, 35)), seq_mode=0)  # 32-token panel: tcgen05 linears, new scratch
+    big, _ = make_big_weight(ctx)
+    kf.linear(ctx, big, ctx.array(np.zeros((64, 8192), dtype=np.uint16)), 64)  # grows the split-K workspace / staging again
+    assert ctx.lib.kf_scratch_generation(ctx.h) > gen0
+    for pos in range(35, 39):
+        assert np.array_equal(step(model, toks[pos], pos), step(ref, toks[pos], pos))
+
+
+def make_big_weight(ctx):
+    rows, cols = 2048, 8192
+    w = ol.fill_normal(rows * cols, 31337, 0.02)
+    t = kf.quantize(ctx, ctx.array(w), rows, cols, kf.KF_T_Q4, 128, kf.KF_Q_RTN_ASYM)
+    return t, None
+
+
+def test_decode_loop_checks_what_was_staged(ctx):
+    # the device-resident loop continues from the tokens / positions the last forward left on the device: asking for more sequences than
+    # were staged, or more than the model was built for, must fail instead of reading stale rows
+    model, _ = build_pair(ctx, max_batch=2)
+    model.forward([5], [0], want_logits=False)
+    with pytest.raises(kf.KoifishError):
+        model.decode_loop(2, 2)   # one sequence staged, two requested
+    with pytest.raises(kf.KoifishError):
+        model.decode_loop(2, 3)   # beyond max_batch
+    model.forward([5, 6], [1, 1], seq_mode=1, want_logits=False)
+    model.decode_loop(2, 2)
+    ctx.sync()
+    t, p = model.read_state(2)
+    assert list(p) == [3, 3]
+
+
+def test_model_sampler_is_seeded_and_feeds_the_decode_loop(ctx):
+    # kf_model_set_sampler: the next token of forward() and the feedback token of the device-resident loop are drawn on the device
+    # (temperature / top-k / top-p, xorshift64* seeded per sequence); same seed -> same continuation, and it matches the CPU port fed the
+    # logits the model returned
+    model, _ = build_pair(ctx)
+    toks = prompt(4, 1024)
+    for p_, t_ in enumerate(toks[:-1]):
+        model.forward([t_], [p_], want_logits=False)
+
+    def run(seed):
+        model.set_sampler(0.9, 20, 0.95, seed)
+        out, tok, state = [], toks[-1], [seed]
+        for i in range(12):
+            lg, nxt = model.forward([tok], [len(toks) - 1 + i], want_logits=True, want_next=True)
+            want, _ = ol.sample(lg[0], 0.9, 20, 0.95, state)
+            out.append((int(nxt[0]), want))
+            tok = int(nxt[0])
+        return out
+
+    a = run(1234)
+    assert sum(int(g != w) for g, w in a) <= 1           # device draw == CPU port on the same logits (an expf ulp may flip one)
+    assert [g for g, _ in a] == [g for g, _ in run(1234)]  # reproducible
+    assert [g for g, _ in a] != [g for g, _ in run(99)]    # and actually seeded
+    model.set_sampler(0.0, 1, 1.0, 0)                       # back to greedy
+    lg, nxt = model.forward([toks[-1]], [len(toks) - 1], want_logits=True, want_next=True)
+    assert int(nxt[0]) == int(np.argmax(ol.bf16_to_f32(lg[0])))
