@@ -99,7 +99,7 @@ extern "C" int kf_ctx_destroy(kf_ctx* ctx) {
         cudaFree(ctx->attn_ws);
     if (ctx->attn_cnt)
         cudaFree(ctx->attn_cnt);
-    void* scratch[5] = {ctx->xperm, ctx->xnorm, ctx->tmp0, ctx->tmp1, ctx->deq_w};
+    void* scratch[6] = {ctx->xperm, ctx->xnorm, ctx->tmp0, ctx->tmp1, ctx->deq_w, ctx->xg_buf};
     for (void* b : scratch)
         if (b)
             cudaFree(b);
@@ -137,6 +137,8 @@ extern "C" int kf_ctx_get_int(kf_ctx* ctx, const char* key, int* value_out) {
         *value_out = ctx->gemv_last_s;
     else if (!strcmp(key, "tp_fused"))
         *value_out = ctx->tp_fused;
+    else if (!strcmp(key, "gemv_xg_min_m"))
+        *value_out = ctx->gemv_xg_min_m;
     else
         return KF_ERR_BAD_ARG;
     return KF_OK;
@@ -154,6 +156,8 @@ extern "C" int kf_ctx_set_int(kf_ctx* ctx, const char* key, int value) {
         ctx->gemv_exact = value;
     else if (!strcmp(key, "tp_fused"))
         ctx->tp_fused = value;
+    else if (!strcmp(key, "gemv_xg_min_m"))
+        ctx->gemv_xg_min_m = value;
     else if (!strcmp(key, "deq_fma"))
         ctx->deq_fma = value ? 1 : 0;
     else if (!strcmp(key, "pdl"))

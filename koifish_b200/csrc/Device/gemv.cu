@@ -104,6 +104,13 @@ struct GemvParams {
     int gshift;    // log2(group / 128): gama index = row*(K/group) + (step >> gshift)
     int epilogue;
     uint32_t lop_mask, lop_magic;  // code-field mask (0x000F000F / 0x00030003 / 0x00010001) and bf16x2 128.0 (0x43004300)
+    // activations pre-staged in GLOBAL memory by kf_gemv_xprep_kernel (XG variants: 4..8-token decode): same layout as the shared-memory
+    // staging area, all k-steps of K
+    const uint4* xg;
+    const float4* sxg;
+    uint4* xg_out;    // xprep only
+    float4* sxg_out;  // xprep only
+    int prep_steps;   // xprep only: k-steps per CTA
     float* ws;
     unsigned* cnt;
     // fused tensor-parallel exchange (kf_tp.cuh), epilogue EPI_TP: y = residual + sum over the ranks of this matmul, as exchange #tp_out
@@ -248,9 +255,124 @@ __device__ __forceinline__ void build_a(uint32_t (&a)[4], const uint32_t (&wa)[N
     }
 }
 
+// ---- activation staging, shared by the matmul kernel (destination: its shared memory, one k-slice) and by kf_gemv_xprep_kernel (destination:
+//      global memory, all of K, once per launch sequence).  dstx[((s * UNITS + u) * MX + m) * 4 + slot] = the 8 activations unit u / thread slot
+//      `slot` of k-step s_begin + s needs, in fragment order; dstsx[s * MX + m] = the group sums of MODE_FAST.  256 threads.
+template <int FMT, int MODE, int MX>
+__device__ __forceinline__ void gemv_stage_x(uint4* __restrict__ dstx, float4* __restrict__ dstsx, const GemvParams& p, int s_begin, int nsteps,
+                                             float* s_red, float* s_scale) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    // ---- optional fused RMSNorm: the same arithmetic, in the same order, as kf_rmsnorm_kernel (ops.cu) --------------------------
+    if (p.norm_w) {
+        for (int m = 0; m < p.M; m++) {
+            const uint16_t* xr = p.x + (size_t)m * p.K;
+            float ss = 0.f;
+            for (int i = tid * 8; i < p.K; i += kThreads * 8) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + i));
+                const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float a = bf16lo(q[j]), b = bf16hi(q[j]);
+                    ss = fmaf(a, a, ss), ss = fmaf(b, b, ss);
+                }
+            }
+            ss = block_sum(ss, s_red);
+            if (tid == 0) s_scale[m] = 1.0f / sqrtf(fmaf(ss, 1.0f / (float)p.K, p.norm_eps));
+        }
+        __syncthreads();
+    }
+
+    // ---- stage the activations of this k-slice in shared memory, permuted to the fragment order --------------------------------
+    {
+        const int items = MX * nsteps * 4;
+        for (int it = tid; it < items; it += kThreads) {
+            const int tt = it & 3, m = (it >> 2) % MX, s = it / (4 * MX);
+            uint32_t src[KT / 2];
+            if (m < p.M) {
+                const size_t k0 = (size_t)(s_begin + s) * KSTEP + tt * KT;
+                const uint4* gp = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + k0);
+#pragma unroll
+                for (int i = 0; i < KT / 8; i++) {
+                    uint4 v = __ldg(gp + i);
+                    src[4 * i + 0] = v.x, src[4 * i + 1] = v.y, src[4 * i + 2] = v.z, src[4 * i + 3] = v.w;
+                }
+                if (p.norm_w) {  // (x * s) * w, rounded to bf16 like the stand-alone kernel's output
+                    const float sc  = s_scale[m];
+                    const uint4* wp = reinterpret_cast<const uint4*>(p.norm_w + k0);
+#pragma unroll
+                    for (int i = 0; i < KT / 8; i++) {
+                        const uint4 wv = __ldg(wp + i);
+                        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t xv = src[4 * i + j];
+                            src[4 * i + j]    = pack_bf16x2((bf16lo(xv) * sc) * bf16lo(ww[j]), (bf16hi(xv) * sc) * bf16hi(ww[j]));
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < KT / 2; i++) src[i] = 0u;
+            }
+            float fscl = 1.0f;  // MODE_FAST: the group's power-of-two scale
+            if (MODE == MODE_FAST) {
+                // fp16 staging with a power-of-two scale per 128-k group (the quad's 4 x 32 values; the 4 lanes of a quad are always
+                // active together): the group's largest magnitude lands in [2^13, 2^14).  sxs[s][m] = {0, Sx, 2^24 / scale} with
+                // Sx = 2^-24 x the group sum of the scaled activations (the MMA's sums carry the 2^-24 of the subnormal codes)
+                const unsigned qm = 0xFu << (lane & ~3);
+                uint32_t amax = 0;
+#pragma unroll
+                for (int i = 0; i < KT / 2; i++) amax = max(amax, max(src[i] & 0x7fffu, (src[i] >> 16) & 0x7fffu));
+                amax = max(amax, __shfl_xor_sync(qm, amax, 1));
+                amax = max(amax, __shfl_xor_sync(qm, amax, 2));
+                const int shift = amax == 0 ? 0 : max(-100, min(100, 140 - (int)(amax >> 7)));  // 140 = 127 + 13
+                fscl = __uint_as_float((uint32_t)(127 + shift) << 23);
+                float sum = 0.f;
+#pragma unroll
+                for (int i = 0; i < KT / 2; i++) sum += bf16lo(src[i]) * fscl, sum += bf16hi(src[i]) * fscl;
+                sum += __shfl_xor_sync(qm, sum, 1), sum += __shfl_xor_sync(qm, sum, 2);  // fixed order: bit-reproducible
+                sum *= 5.9604644775390625e-8f;                                            // 2^-24
+                if (tt == 0)
+                    dstsx[s * MX + m] =
+                        make_float4(0.f, sum, __uint_as_float((uint32_t)(127 + 24 - shift) << 23), 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < UNITS; u++) {
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int e0 = xperm<FMT>(u * 8 + 2 * j), e1 = xperm<FMT>(u * 8 + 2 * j + 1);
+                    uint32_t lo = (src[e0 >> 1] >> ((e0 & 1) * 16)) & 0xffffu;
+                    uint32_t hi = (src[e1 >> 1] >> ((e1 & 1) * 16)) & 0xffffu;
+                    if (MODE == MODE_FAST) {  // fp16(x * scale * 2^-b): b = the bit position of the code field this element meets
+                        const float f = fscl * __uint_as_float((uint32_t)(127 - fast_exp<Fmt<FMT>::BITS>(u, j)) << 23);
+                        lo = __half_as_ushort(__float2half_rn(bf16_bits_to_f32(lo) * f));
+                        hi = __half_as_ushort(__float2half_rn(bf16_bits_to_f32(hi) * f));
+                    }
+                    o[j] = lo | (hi << 16);
+                }
+                // destination (unit, thread slot): packed formats keep the 32-k slot of thread tt; the byte / bf16 streams interleave
+                // 16-byte chunks across the quad (chunk ch of thread t covers bytes (4*ch + t)*16 of the k-step)
+                int du = u, dt = tt;
+                if (FMT == FMT_BF16) {
+                    du = tt, dt = u;  // natural 8-k block B = 4*tt + u  ->  unit B >> 2, thread B & 3
+                } else if (FMT == FMT_F8) {
+                    const int C = 2 * tt + (u >> 1);  // 16-k chunk index
+                    du = 2 * (C >> 2) + (u & 1), dt = C & 3;
+                }
+                dstx[((s * UNITS + du) * MX + m) * 4 + dt] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
 // NT: 8-token column tiles ; MXS: token rows staged in shared memory when NT == 1 (1, 2, 4 or 8: the MMA's 8 columns replicate them, so
 // a 2-token step stages a quarter of the activations of an 8-token one) ; RT: 16-row tiles per warp
-template <int FMT, int MODE, int NT, int MXS, int RT>
+// XG: the activations come pre-staged from global memory (kf_gemv_xprep_kernel) instead of being staged per CTA in shared memory.  With 4..8
+// tokens the staging area (2 KB per k-step) otherwise caps the k-slice at 18-28 steps, i.e. forces 2-3 k-splits and as many waves on the
+// large shapes, and every CTA repeats the fp16 conversion of its slice; pre-staged, the slice length is free (one wave) and the
+// conversion happens once.  The fragment loads hit L1 (every warp of every CTA on the SM reads the same 2 KB per k-step).
+template <int FMT, int MODE, int NT, int MXS, int RT, int XG = 0>
 #ifndef KF_GEMV_OCC
 #define KF_GEMV_OCC 3
 #endif
@@ -273,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
     const int rb = blockIdx.x, split = blockIdx.y;
     const bool swiglu = p.epilogue == EPI_SWIGLU;
     kf_grid_launch_dependents();  // the next kernel of the stream may start its own weight prefetch as soon as all our CTAs are running
-    if (M1 && p.cluster) cluster_arrive();  // matched by the wait in front of the first remote store: by then every CTA of the cluster runs
+    if (NT == 1 && p.cluster) cluster_arrive();  // matched by the wait in front of the first remote store: by then every CTA of the cluster runs
 
     // ---- which rows does this CTA / warp own? -------------------------------------------------------------------------------
     int segi = 0;
@@ -287,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
     const int s_begin = (int)(((long long)split * p.steps_total) / p.S);
     const int s_end   = (int)(((long long)(split + 1) * p.steps_total) / p.S);
     const int nsteps  = s_end - s_begin;
-    uint32_t* sgam    = reinterpret_cast<uint32_t*>(smem + (size_t)p.nsteps_max * UNITS * MX * 4);
+    uint32_t* sgam    = reinterpret_cast<uint32_t*>(smem + (XG ? (size_t)0 : (size_t)p.nsteps_max * UNITS * MX * 4));
     // per-thread ring of packed weight words: [DEPTH][RT][2 (row g / g+8)][NCH][256 threads] x CPB bytes
     uint8_t* ring = reinterpret_cast<uint8_t*>(smem) + p.ring_off;
 
@@ -385,108 +507,9 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
     //      programmatic dependent launch this CTA may have been running for a while already, with its weight stream in flight -------
     kf_grid_dependency_wait();
 
-    // ---- optional fused RMSNorm: the same arithmetic, in the same order, as kf_rmsnorm_kernel (ops.cu) --------------------------
-    if (p.norm_w) {
-        for (int m = 0; m < p.M; m++) {
-            const uint16_t* xr = p.x + (size_t)m * p.K;
-            float ss = 0.f;
-            for (int i = tid * 8; i < p.K; i += kThreads * 8) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + i));
-                const uint32_t q[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float a = bf16lo(q[j]), b = bf16hi(q[j]);
-                    ss = fmaf(a, a, ss), ss = fmaf(b, b, ss);
-                }
-            }
-            ss = block_sum(ss, s_red);
-            if (tid == 0) s_scale[m] = 1.0f / sqrtf(fmaf(ss, 1.0f / (float)p.K, p.norm_eps));
-        }
-        __syncthreads();
-    }
-
-    // ---- stage the activations of this k-slice in shared memory, permuted to the fragment order --------------------------------
-    {
-        const int items = MX * nsteps * 4;
-        for (int it = tid; it < items; it += kThreads) {
-            const int tt = it & 3, m = (it >> 2) % MX, s = it / (4 * MX);
-            uint32_t src[KT / 2];
-            if (m < p.M) {
-                const size_t k0 = (size_t)(s_begin + s) * KSTEP + tt * KT;
-                const uint4* gp = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + k0);
-#pragma unroll
-                for (int i = 0; i < KT / 8; i++) {
-                    uint4 v = __ldg(gp + i);
-                    src[4 * i + 0] = v.x, src[4 * i + 1] = v.y, src[4 * i + 2] = v.z, src[4 * i + 3] = v.w;
-                }
-                if (p.norm_w) {  // (x * s) * w, rounded to bf16 like the stand-alone kernel's output
-                    const float sc  = s_scale[m];
-                    const uint4* wp = reinterpret_cast<const uint4*>(p.norm_w + k0);
-#pragma unroll
-                    for (int i = 0; i < KT / 8; i++) {
-                        const uint4 wv = __ldg(wp + i);
-                        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint32_t xv = src[4 * i + j];
-                            src[4 * i + j]    = pack_bf16x2((bf16lo(xv) * sc) * bf16lo(ww[j]), (bf16hi(xv) * sc) * bf16hi(ww[j]));
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < KT / 2; i++) src[i] = 0u;
-            }
-            float fscl = 1.0f;  // MODE_FAST: the group's power-of-two scale
-            if (MODE == MODE_FAST) {
-                // fp16 staging with a power-of-two scale per 128-k group (the quad's 4 x 32 values; the 4 lanes of a quad are always
-                // active together): the group's largest magnitude lands in [2^13, 2^14).  sxs[s][m] = {0, Sx, 2^24 / scale} with
-                // Sx = 2^-24 x the group sum of the scaled activations (the MMA's sums carry the 2^-24 of the subnormal codes)
-                const unsigned qm = 0xFu << (lane & ~3);
-                uint32_t amax = 0;
-#pragma unroll
-                for (int i = 0; i < KT / 2; i++) amax = max(amax, max(src[i] & 0x7fffu, (src[i] >> 16) & 0x7fffu));
-                amax = max(amax, __shfl_xor_sync(qm, amax, 1));
-                amax = max(amax, __shfl_xor_sync(qm, amax, 2));
-                const int shift = amax == 0 ? 0 : max(-100, min(100, 140 - (int)(amax >> 7)));  // 140 = 127 + 13
-                fscl = __uint_as_float((uint32_t)(127 + shift) << 23);
-                float sum = 0.f;
-#pragma unroll
-                for (int i = 0; i < KT / 2; i++) sum += bf16lo(src[i]) * fscl, sum += bf16hi(src[i]) * fscl;
-                sum += __shfl_xor_sync(qm, sum, 1), sum += __shfl_xor_sync(qm, sum, 2);  // fixed order: bit-reproducible
-                sum *= 5.9604644775390625e-8f;                                            // 2^-24
-                if (tt == 0)
-                    reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(smem) + p.sx_off)[s * MX + m] =
-                        make_float4(0.f, sum, __uint_as_float((uint32_t)(127 + 24 - shift) << 23), 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < UNITS; u++) {
-                uint32_t o[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int e0 = xperm<FMT>(u * 8 + 2 * j), e1 = xperm<FMT>(u * 8 + 2 * j + 1);
-                    uint32_t lo = (src[e0 >> 1] >> ((e0 & 1) * 16)) & 0xffffu;
-                    uint32_t hi = (src[e1 >> 1] >> ((e1 & 1) * 16)) & 0xffffu;
-                    if (MODE == MODE_FAST) {  // fp16(x * scale * 2^-b): b = the bit position of the code field this element meets
-                        const float f = fscl * __uint_as_float((uint32_t)(127 - fast_exp<F::BITS>(u, j)) << 23);
-                        lo = __half_as_ushort(__float2half_rn(bf16_bits_to_f32(lo) * f));
-                        hi = __half_as_ushort(__float2half_rn(bf16_bits_to_f32(hi) * f));
-                    }
-                    o[j] = lo | (hi << 16);
-                }
-                // destination (unit, thread slot): packed formats keep the 32-k slot of thread tt; the byte / bf16 streams interleave
-                // 16-byte chunks across the quad (chunk ch of thread t covers bytes (4*ch + t)*16 of the k-step)
-                int du = u, dt = tt;
-                if (FMT == FMT_BF16) {
-                    du = tt, dt = u;  // natural 8-k block B = 4*tt + u  ->  unit B >> 2, thread B & 3
-                } else if (FMT == FMT_F8) {
-                    const int C = 2 * tt + (u >> 1);  // 16-k chunk index
-                    du = 2 * (C >> 2) + (u & 1), dt = C & 3;
-                }
-                smem[((s * UNITS + du) * MX + m) * 4 + dt] = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-        }
-    }
+    // ---- optional fused RMSNorm + the activations of this k-slice into shared memory, permuted to the fragment order ------------------
+    if constexpr (!XG)
+        gemv_stage_x<FMT, MODE, MX>(smem, reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(smem) + p.sx_off), p, s_begin, nsteps, s_red, s_scale);
     __syncthreads();
     float* sxs = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem) + p.sx_off);  // [nsteps][MX] group sums of the activations
     if (MODE == MODE_FACTOR) {
@@ -568,11 +591,16 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
             }
             float4 sv[NT][2];  // MODE_FAST: {-, 2^-24 Sx, 2^24 / scale} of this k-step's group for the thread's two token columns
             if (MODE == MODE_FAST) {
-                const float4* sx4 = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(smem) + p.sx_off) + s * MX;
+                const float4* sx4 = XG ? p.sxg + (size_t)(s_begin + s) * MX
+                                       : reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(smem) + p.sx_off) + s * MX;
 #pragma unroll
                 for (int nt = 0; nt < NT; nt++) {
-                    sv[nt][0] = sx4[MX >= 8 ? nt * 8 + 2 * t : ((2 * t) & (MX - 1))];
-                    sv[nt][1] = sx4[MX >= 8 ? nt * 8 + 2 * t + 1 : ((2 * t + 1) & (MX - 1))];
+                    const int i0 = MX >= 8 ? nt * 8 + 2 * t : ((2 * t) & (MX - 1)), i1 = MX >= 8 ? nt * 8 + 2 * t + 1 : ((2 * t + 1) & (MX - 1));
+                    if constexpr (XG) {
+                        sv[nt][0] = __ldg(sx4 + i0), sv[nt][1] = __ldg(sx4 + i1);
+                    } else {
+                        sv[nt][0] = sx4[i0], sv[nt][1] = sx4[i1];
+                    }
 #pragma unroll
                     for (int rt = 0; rt < RT; rt++)
 #pragma unroll
@@ -583,7 +611,12 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
             for (int u = 0; u < UNITS; u++) {
                 uint4 xb[NT];
 #pragma unroll
-                for (int nt = 0; nt < NT; nt++) xb[nt] = smem[((s * UNITS + u) * MX + (MX >= 8 ? nt * 8 : 0)) * 4 + xlane];
+                for (int nt = 0; nt < NT; nt++) {
+                    if constexpr (XG)
+                        xb[nt] = __ldg(p.xg + (((size_t)(s_begin + s) * UNITS + u) * MX + (MX >= 8 ? nt * 8 : 0)) * 4 + xlane);
+                    else
+                        xb[nt] = smem[((s * UNITS + u) * MX + (MX >= 8 ? nt * 8 : 0)) * 4 + xlane];
+                }
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
 #pragma unroll
@@ -671,19 +704,21 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
     __syncthreads();
 
     // ---- split-K: publish the partial tile; the last CTA of this row block reduces in fixed order ---------------------------
-    if (M1 && p.cluster) {
-        // the k-slices of this row block are the CTAs of one cluster: every slice stores its ROWS partial sums into the leader's shared
-        // memory, the leader adds them in slice order (deterministic).  No global workspace, no atomics, no second DRAM/L2 round trip.
-        float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem) + p.red_off);
+    if (NT == 1 && p.cluster) {
+        // the k-slices of this row block are the CTAs of one cluster (up to 8 tokens): every slice stores its M x ROWS partial sums into the
+        // leader's shared memory, the leader adds them in slice order (deterministic).  No global workspace, no atomics, no second
+        // DRAM/L2 round trip.
+        float* red  = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem) + p.red_off);
+        const int n = p.M * ROWS;
         cluster_wait();
-        for (int e = tid; e < ROWS; e += kThreads) st_cluster_f32(red + split * ROWS + e, 0, tile[e]);
+        for (int e = tid; e < n; e += kThreads) st_cluster_f32(red + (size_t)split * n + e, 0, tile[(e / ROWS) * TS + (e % ROWS)]);
         cluster_arrive();
         cluster_wait();
         if (split != 0) return;
-        for (int e = tid; e < ROWS; e += kThreads) {
+        for (int e = tid; e < n; e += kThreads) {
             float sum = 0.f;
-            for (int sp = 0; sp < p.S; sp++) sum += red[sp * ROWS + e];
-            tile[e] = sum;
+            for (int sp = 0; sp < p.S; sp++) sum += red[(size_t)sp * n + e];
+            tile[(e / ROWS) * TS + (e % ROWS)] = sum;
         }
         __syncthreads();
     } else if (p.S > 1) {
@@ -787,6 +822,17 @@ __global__ void __launch_bounds__(kThreads, (NT >= 4 ? 1 : NT == 1 ? KF_GEMV_OCC
     }
 }
 
+// RMSNorm (optional) + fragment-order fp16 staging of ALL of x, once, for the XG variants of the kernel above: grid = ceil(k-steps / prep_steps)
+template <int FMT, int MX>
+__global__ void __launch_bounds__(kThreads) kf_gemv_xprep_kernel(const GemvParams p) {
+    __shared__ float s_red[32];
+    __shared__ float s_scale[64];
+    kf_grid_launch_dependents();  // the matmul behind us may start streaming its weights
+    kf_grid_dependency_wait();    // x comes from the kernel before us
+    const int s0 = blockIdx.x * p.prep_steps, n = min(p.prep_steps, p.steps_total - s0);
+    gemv_stage_x<FMT, MODE_FAST, MX>(p.xg_out + (size_t)s0 * UNITS * MX * 4, p.sxg_out + (size_t)s0 * MX, p, s0, n, s_red, s_scale);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------------------
 constexpr size_t kSmemCap  = 100 * 1024;  // two CTAs per SM
 #ifndef KF_GEMV_SOFT_KB
@@ -811,26 +857,26 @@ static size_t ring_bytes(int fmt, int rt) {
     return (size_t)(rt == 2 ? f.d2 : f.d1) * rt * 2 * f.nch * kThreads * f.cpb;
 }
 // shared bytes per k-step: activations + gama
-static size_t step_bytes(int mode, int mx, int rows_cta) {
+static size_t step_bytes(int mode, int mx, int rows_cta, bool xg = false) {
+    if (xg) return (size_t)(rows_cta + 1) * 4;  // activations and group sums live in global memory: only zero / step are staged
     return (size_t)UNITS * mx * 64 + (mode == MODE_PLAIN ? 0 : (size_t)(rows_cta + 1) * 4) + (mode == MODE_FACTOR ? (size_t)mx * 4 : 0) +
            (mode == MODE_FAST ? (size_t)mx * 16 : 0);
 }
 
-template <int FMT, int MODE, int NT, int MXS, int RT>
+template <int FMT, int MODE, int NT, int MXS, int RT, int XG = 0>
 int launch_one(kf_ctx* ctx, const GemvParams& p0) {
     constexpr int MX = NT == 1 ? MXS : 8 * NT, MP = 8 * NT, ROWS = 128 * RT;
-    constexpr bool M1 = MX == 1;
     GemvParams p     = p0;
-    size_t head      = (size_t)p.nsteps_max * step_bytes(MODE, MX, ROWS);
+    size_t head      = (size_t)p.nsteps_max * step_bytes(MODE, MX, ROWS, XG != 0);
     size_t tilebytes = (size_t)MP * (ROWS + 4) * 4;
     p.ring_off       = (int)((head + 15) & ~(size_t)15);
     p.sx_off         = (int)(p.ring_off + ring_bytes(FMT, RT));
-    size_t sxbytes   = MODE == MODE_FACTOR ? (size_t)p.nsteps_max * MX * 4 : MODE == MODE_FAST ? (size_t)p.nsteps_max * MX * 16 : 0;
+    size_t sxbytes   = XG ? 0 : MODE == MODE_FACTOR ? (size_t)p.nsteps_max * MX * 4 : MODE == MODE_FAST ? (size_t)p.nsteps_max * MX * 16 : 0;
     size_t smem      = std::max((size_t)p.sx_off + sxbytes, tilebytes);
     if (p.cluster) {
         p.red_off = (int)((smem + 15) & ~(size_t)15);
-        smem      = (size_t)p.red_off + (size_t)p.S * ROWS * 4;
-        if (!M1 || smem > kSmemCap) {  // no room for the merge area: global workspace + last-CTA reduction
+        smem      = (size_t)p.red_off + (size_t)p.S * p.M * ROWS * 4;
+        if (NT != 1 || smem > kSmemCap) {  // no room for the merge area: global workspace + last-CTA reduction
             p.cluster = 0, smem = std::max((size_t)p.sx_off + sxbytes, tilebytes);
             int rc = kf_ensure_gemv_ws(ctx, (size_t)p.S * p.total_rb * MP * ROWS * sizeof(float), p.total_rb);
             if (rc) return rc;
@@ -838,7 +884,7 @@ int launch_one(kf_ctx* ctx, const GemvParams& p0) {
         }
     }
     KF_REQUIRE(ctx, smem <= kSmemCap, "internal: k-slice does not fit shared memory");
-    auto kern            = kf_gemv_kernel<FMT, MODE, NT, MXS, RT>;
+    auto kern            = kf_gemv_kernel<FMT, MODE, NT, MXS, RT, XG>;
     static bool attr_set[kf_ctx::kMaxDevices] = {};  // function attributes are per device (one flag per instantiation and device)
     if (!attr_set[ctx->device]) {
         KF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
@@ -864,6 +910,20 @@ int launch_one(kf_ctx* ctx, const GemvParams& p0) {
 
 template <int FMT, int MODE>
 int launch_nt(kf_ctx* ctx, const GemvParams& p, int rt) {
+    if constexpr (MODE == MODE_FAST) {
+        if (p.xg && rt == 1) {  // pre-staged activations (4..8 tokens): stage them once, then the matmul
+            constexpr int PS = 8;
+            GemvParams q = p;
+            q.prep_steps = PS;
+            const dim3 grid((p.steps_total + PS - 1) / PS);
+            if (p.M <= 4)
+                KF_CUDA(ctx, kf_launch_pdl(ctx, kf_gemv_xprep_kernel<FMT, 4>, grid, dim3(kThreads), 0, q));
+            else
+                KF_CUDA(ctx, kf_launch_pdl(ctx, kf_gemv_xprep_kernel<FMT, 8>, grid, dim3(kThreads), 0, q));
+            KF_LAUNCH_CHECK(ctx);
+            return p.M <= 4 ? launch_one<FMT, MODE, 1, 4, 1, 1>(ctx, p) : launch_one<FMT, MODE, 1, 8, 1, 1>(ctx, p);
+        }
+    }
     if (p.M == 1) return rt == 2 ? launch_one<FMT, MODE, 1, 1, 2>(ctx, p) : launch_one<FMT, MODE, 1, 1, 1>(ctx, p);
     if (p.M == 2 && rt != 2) return launch_one<FMT, MODE, 1, 2, 1>(ctx, p);
     if (p.M <= 4 && rt != 2) return launch_one<FMT, MODE, 1, 4, 1>(ctx, p);
@@ -940,43 +1000,73 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
 
     // ---- k-split: pick the S that minimises  waves(S) x (fixed CTA cost + k-steps per CTA)  under the shared-memory budget -------
     const int MXs      = M == 1 ? 1 : M == 2 ? 2 : M <= 4 ? 4 : (M <= 8 ? 8 : M <= 16 ? 16 : M <= 32 ? 32 : 64);
-    const size_t stepb = step_bytes(mode, MXs, rows_cta), ringb = ring_bytes(fmt, rt);
-    const int hard_steps = (int)std::max<size_t>(1, (kSmemCap - 256 - ringb) / stepb);
-    const int soft_steps = ringb + 4 * stepb <= kSmemSoft ? (int)((kSmemSoft - ringb) / stepb) : 0;
-    const int S_min      = (p.steps_total + hard_steps - 1) / hard_steps;
-    int S                = ctx->gemv_splitk;
-    if (S <= 0) {
-        // Measured on B200 (profiles/r02_gemv_splitk.txt): a k-slice advances at ~0.55 us per k-step whatever the occupancy -- the ring holds
-        // 3 steps, so a step costs a third of the DRAM round trip -- until the launch as a whole saturates HBM.  So: ONE wave, as many
-        // slices as fit into it; and when the slices of a row block merge inside a thread-block cluster (single token, S <= 8) only the
-        // cluster sizes that tile the GPCs (1, 2, 4, 8): S = 5 on 10240 x 5120 is 13.6 us where S = 4 is 10.3.  The merge through the global
-        // workspace (S > 8) costs ~3.5 us more than the cluster merge.
+    // Plan the k-split for a given staging of the activations; returns the number of waves of the chosen plan.
+    // Measured on B200 (profiles/r02_gemv_splitk.jsonl): a k-slice advances at ~0.55 us per k-step whatever the occupancy until the launch
+    // as a whole saturates HBM.  So: ONE wave, as many slices as fit into it; and when the slices of a row block merge inside a thread-block
+    // cluster (single token, S <= 8) only the cluster sizes that tile the GPCs (1, 2, 4, 8): S = 5 on 10240 x 5120 is 13.6 us where S = 4 is
+    // 10.3.  The merge through the global workspace (S > 8) costs ~3.5 us more than the cluster merge.
+    const size_t ringb = ring_bytes(fmt, rt);
+    int S = 0, S_min = 1;
+    auto plan = [&](bool xg_) -> int {
+        const size_t stepb   = step_bytes(mode, MXs, rows_cta, xg_);
+        const int hard_steps = (int)std::max<size_t>(1, (kSmemCap - 256 - ringb) / stepb);
+        const int soft_steps = ringb + 4 * stepb <= kSmemSoft ? (int)((kSmemSoft - ringb) / stepb) : 0;
         const int per_sm3 = MXs <= 8 ? KF_GEMV_OCC : (MXs <= 16 ? 2 : 1), per_sm2 = MXs <= 16 ? 2 : 1;
-        const bool can_cluster = M == 1 && ctx->gemv_cluster > 0;
-        const double bits_of_fmt = (double)fmt_info(fmt).bits;
-        double best = 1e30;
-        S           = S_min;
-        for (int cand = S_min; cand <= std::min(p.steps_total, 64); cand++) {
-            const int nst = (p.steps_total + cand - 1) / cand;
-            if (nst < 2 && cand > S_min) break;
-            const bool clustered = can_cluster && cand >= 2 && cand <= 8;
-            if (clustered && (cand & (cand - 1)) && cand > S_min) continue;  // cluster sizes 3, 5, 6, 7 pack badly
-            const int per_sm  = (soft_steps && nst <= soft_steps) ? per_sm3 : per_sm2;
-            const int slots   = ctx->sm_count * per_sm;
-            const int waves   = (rb * cand + slots - 1) / slots;
-            const double fixed = cand == 1 ? 4.0 : clustered ? 5.0 : 7.5;  // us: prologue + merge
-            // bytes in flight = CTAs x ring depth x 8 KB per k-step; what they can pull per DRAM round trip (~1.65 us) caps the stream
-            const double ctas   = std::min<double>((double)rb * cand, slots);
-            const double bw     = std::min(6.0e6, ctas * 3.0 * rows_cta * (KSTEP * bits_of_fmt / 8.0) / 1.65);  // bytes per us
-            const double stream = std::max(0.55 * nst, (double)total_rows * K * (bits_of_fmt / 8.0 + 4.0 / 128.0) / waves / bw);
-            const double cost   = waves * (fixed + stream);
-            if (cost < best - 1e-9) best = cost, S = cand;
+        S_min = (p.steps_total + hard_steps - 1) / hard_steps;
+        S     = ctx->gemv_splitk;
+        auto waves_of = [&](int cand) {
+            const int nst   = (p.steps_total + cand - 1) / cand;
+            const int slots = ctx->sm_count * ((soft_steps && nst <= soft_steps) ? per_sm3 : per_sm2);
+            return (rb * cand + slots - 1) / slots;
+        };
+        if (S <= 0) {
+            const bool can_cluster = M <= 8 && ctx->gemv_cluster > 0;
+            const double bits_of_fmt = (double)fmt_info(fmt).bits;
+            double best = 1e30;
+            S           = S_min;
+            for (int cand = S_min; cand <= std::min(p.steps_total, 64); cand++) {
+                const int nst = (p.steps_total + cand - 1) / cand;
+                if (nst < 2 && cand > S_min) break;
+                const bool clustered = can_cluster && cand >= 2 && cand <= 8;
+                if (clustered && (cand & (cand - 1)) && cand > S_min) continue;  // cluster sizes 3, 5, 6, 7 pack badly
+                const int per_sm  = (soft_steps && nst <= soft_steps) ? per_sm3 : per_sm2;
+                const int slots   = ctx->sm_count * per_sm;
+                const int waves   = (rb * cand + slots - 1) / slots;
+                const double fixed = cand == 1 ? 4.0 : clustered ? 5.0 : 7.5;  // us: prologue + merge
+                // bytes in flight = CTAs x ring depth x 8 KB per k-step; what they can pull per DRAM round trip (~1.65 us) caps the stream
+                const double ctas   = std::min<double>((double)rb * cand, slots);
+                const double bw     = std::min(6.0e6, ctas * 3.0 * rows_cta * (KSTEP * bits_of_fmt / 8.0) / 1.65);  // bytes per us
+                const double stream = std::max(0.55 * nst, (double)total_rows * K * (bits_of_fmt / 8.0 + 4.0 / 128.0) / waves / bw);
+                const double cost   = waves * (fixed + stream);
+                if (cost < best - 1e-9) best = cost, S = cand;
+            }
+        }
+        return waves_of(std::max(S, S_min));
+    };
+    // 4..8 tokens of the decode arithmetic: the per-CTA staging area (2 KB per k-step at 8 tokens) caps the k-slice, which on the large
+    // shapes forces k-splits that no longer fit one wave.  There the activations are pre-staged ONCE in global memory
+    // (kf_gemv_xprep_kernel, one more launch: 51200 x 5120 at 8 tokens 49 -> 34.5 us) and the split is planned without that cap; the
+    // small shapes, which fit a wave anyway, keep the per-CTA staging (the extra launch would cost them ~2 us).  Knob gemv_xg_min_m:
+    // token count from which this is considered (0 = never; negative = always from |value| tokens, for tests).
+    bool xg = false;
+    {
+        const int thr       = ctx->gemv_xg_min_m;
+        const bool eligible = mode == MODE_FAST && rt == 1 && M <= 8 && MXs >= 4 && thr != 0 && M >= (thr < 0 ? -thr : thr);
+        const int waves     = plan(false);
+        if (eligible && (thr < 0 || waves >= 2)) {
+            xg = true;
+            plan(true);
+            const size_t xbytes = (size_t)p.steps_total * UNITS * MXs * 64, sbytes = (size_t)p.steps_total * MXs * 16;
+            int rc = kf_ensure_buf(ctx, &ctx->xg_buf, &ctx->xg_bytes, xbytes + sbytes);
+            if (rc) return rc;
+            p.xg = p.xg_out = (uint4*)ctx->xg_buf;
+            p.sxg = p.sxg_out = (float4*)((uint8_t*)ctx->xg_buf + xbytes);
         }
     }
     S = std::max(S, S_min);
     S = std::max(1, std::min(S, p.steps_total));
     if (M == 1 && ctx->gemv_cluster == 2 && ctx->gemv_splitk <= 0 && S > 8 && S_min <= 8) S = 8;
-    p.cluster    = (M == 1 && ctx->gemv_cluster > 0 && S >= 2 && S <= 8) ? 1 : 0;
+    p.cluster    = (M <= 8 && ctx->gemv_cluster > 0 && S >= 2 && S <= 8) ? 1 : 0;
     p.S          = S;
     ctx->gemv_last_s = S;
     p.nsteps_max = (p.steps_total + S - 1) / S;  // floor/ceil slicing never exceeds ceil(steps/S)

@@ -34,6 +34,9 @@ struct kf_ctx {
     // scratch of the tensor-core (M > 64) path: permuted / normalised activations and the gate / up panels of a SwiGLU
     void *xperm = nullptr, *xnorm = nullptr, *tmp0 = nullptr, *tmp1 = nullptr;
     size_t xperm_bytes = 0, xnorm_bytes = 0, tmp0_bytes = 0, tmp1_bytes = 0;
+    void* xg_buf       = nullptr;  // activations pre-staged in fragment order for the 4..8-token decode GEMV (gemv.cu, XG variants)
+    size_t xg_bytes    = 0;
+    int gemv_xg_min_m  = 3;        // token count from which they are, where the k-split plan would otherwise need two waves (0 = never, < 0 = always from |n|)
     void* deq_w        = nullptr;  // dequantised copy of ONE NormalFloat4 weight for the many-token path (nf4.cu)
     size_t deq_w_bytes = 0;
     int tc_min_m = -1;  // token count from which kf_linear* use the tcgen05 GEMM: -1 = per weight type (linear.cu), 0 = never

@@ -958,3 +958,32 @@ def test_gemv_tma_fast_variant_matches_oracle(ctx, M, N, K):
     finally:
         ctx.set_int("gemv_tma", 0)
     _check_linear(y, wdq, x, M, N, K, noise=FAST_NOISE)
+
+
+@pytest.mark.parametrize("kind", [(4, ol.RTN_ASYM), (2, ol.YYANG), (1, ol.YYANG)], ids=str)
+@pytest.mark.parametrize("M", [3, 4, 7, 8])
+def test_gemv_fast_prestaged_activations_equal_per_cta_staging(ctx, kind, M):
+    # 4..8 tokens: the activations are converted to fragment order ONCE by kf_gemv_xprep_kernel and fetched from global memory in the k-loop
+    # (knob gemv_xg_min_m), instead of every CTA staging its slice in shared memory.  Same staging code, same k-split -> the same bits;
+    # with the fused RMSNorm, the residual epilogue and SwiGLU as well
+    N, K = 384, 2048
+    rng = np.random.default_rng(40 + M)
+    t, wdq = make_weight(ctx, kind, N, K, 2100 + M)
+    t2, _ = make_weight(ctx, kind, N, K, 2200 + M)
+    xd = ctx.array(rand_bf16(rng, (M, K)))
+    nw = ctx.array(ol.f32_to_bf16((1.0 + 0.1 * rng.standard_normal(K)).astype(np.float32)))
+    res = ctx.array(rand_bf16(rng, (M, N)))
+    outs = {}
+    ctx.set_int("gemv_splitk", 2)
+    try:
+        for xg in (0, 3):
+            ctx.set_int("gemv_xg_min_m", -xg)  # negative: always from |value| tokens (the default only where the plan needs two waves)
+            outs[xg] = (kf.linear(ctx, t, xd, M).numpy(np.uint16), kf.linear(ctx, t, xd, M, kf.KF_EPI_RESIDUAL, res).numpy(np.uint16),
+                        kf.rmsnorm_linear(ctx, [t, t2], xd, nw, M, swiglu=True).numpy(np.uint16),
+                        kf.rmsnorm_linear(ctx, [t, t2], xd, nw, M)[1].numpy(np.uint16))
+    finally:
+        ctx.set_int("gemv_splitk", 0)
+        ctx.set_int("gemv_xg_min_m", 3)
+    for a, b in zip(outs[0], outs[3]):
+        assert np.array_equal(a, b)
+    _check_linear(outs[3][0], wdq, xd.numpy(np.uint16).reshape(M, K), M, N, K, noise=_fast_noise(kind))

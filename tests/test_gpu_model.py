@@ -413,6 +413,9 @@ def test_graphs_are_recaptured_when_a_context_scratch_moves(ctx):
     # a captured decode step holds raw pointers into the context's scratch buffers (split-K workspace, tensor-core staging).  When a later
     # call grows one of them (here: a prefill panel that needs the tensor-core staging buffers, then a much larger stand-alone matmul),
     # kf_scratch_generation() changes and the runtime must drop and re-capture its graphs instead of replaying into freed memory.
+    arith = ctx.arith
+    ctx = kf.Context(0)  # a context of its own: the module's shared one has long grown every scratch buffer
+    ctx.set_int("gemv_exact", 1 if arith == "exact" else 0)
     model, _ = build_pair(ctx)
     ref, _ = build_pair(ctx)
     ref.set_graphs(False)
@@ -432,6 +435,9 @@ def test_graphs_are_recaptured_when_a_context_scratch_moves(ctx):
     assert ctx.lib.kf_scratch_generation(ctx.h) > gen0
     for pos in range(35, 39):
         assert np.array_equal(step(model, toks[pos], pos), step(ref, toks[pos], pos))
+    model.close()
+    ref.close()
+    ctx.close()
 
 
 def make_big_weight(ctx):
