@@ -43,6 +43,11 @@ enum {
     KF_T_NF4      = 6, /* typNUMBER::Q4 under QUANT_MODE::RTNf ({"bits": 4} without a quant_method): NormalFloat4 codes as an MSB-first
                           nibble stream (BIT_SET_k, CLI_params.cpp:2177-2191), gama = [R_SCALE rows][C_SCALE cols][rows][16] bf16
                           per-row codebooks (GeQuant::_row_lut, GeQuant.cpp:696-732; CU_Q42X_NF4, quantizer.cu:612-654)            */
+    KF_T_AWQ4     = 7, /* typNUMBER::Q4 under QUANT_MODE::AWQ: the vendor layout, STORED [in_features][out_features] (SLP::Forw uses
+                          transA = 0 for it): data_dev = qweight int32 [cols][rows / 8] with AWQ_REVERSE_ORDER nibbles, zero_dev = qzeros
+                          int32 [cols / 128][rows / 8], step_dev = scales fp16 [cols / 128][rows]; w = bf16(float(q - z) * scale)
+                          (CU_Q42X_awq, quantizer.cu:132-156; CU_I2Q4_unpack, packedN.cuh:109-116).  rows = out_features, cols =
+                          in_features, group = 128.  Device-level only: kf_dequant / kf_linear*; no quantiser (vendor checkpoints)   */
 };
 
 /* ---- quantisation modes (QUANT_CARD, src/CLI_params.hpp:509-554; GeQuant ctor src/Tensor/GeQuant.cpp:107-124) ---- */

@@ -11,10 +11,10 @@ LIB_PATH = os.environ.get("KF_LIB_PATH") or os.path.join(HERE, "libkoifish_b200.
 
 KF_OK = 0
 KF_ERR_NO_DEVICE, KF_ERR_CUDA, KF_ERR_BAD_ARG, KF_ERR_UNSUPPORTED, KF_ERR_OOM, KF_ERR_NCCL, KF_ERR_QUANT = -100, -101, -102, -103, -104, -105, -701
-KF_T_BF16, KF_T_F8E5M2, KF_T_Q4, KF_T_Q2, KF_T_SIGN, KF_T_BINARY, KF_T_NF4 = 0, 1, 2, 3, 4, 5, 6
+KF_T_BF16, KF_T_F8E5M2, KF_T_Q4, KF_T_Q2, KF_T_SIGN, KF_T_BINARY, KF_T_NF4, KF_T_AWQ4 = 0, 1, 2, 3, 4, 5, 6, 7
 KF_Q_RTN_ASYM, KF_Q_RTN_SYM, KF_Q_YYANG = 0, 1, 2
 KF_EPI_NONE, KF_EPI_RESIDUAL, KF_EPI_F32 = 0, 1, 4
-TYPE_BITS = {KF_T_BF16: 16, KF_T_F8E5M2: 8, KF_T_Q4: 4, KF_T_Q2: 2, KF_T_SIGN: 2, KF_T_BINARY: 1, KF_T_NF4: 4}
+TYPE_BITS = {KF_T_BF16: 16, KF_T_F8E5M2: 8, KF_T_Q4: 4, KF_T_Q2: 2, KF_T_SIGN: 2, KF_T_BINARY: 1, KF_T_NF4: 4, KF_T_AWQ4: 4}
 
 
 class KoifishError(RuntimeError):

@@ -183,6 +183,19 @@ class QTensor:
         return t
 
 
+class AwqTensor:
+    """A weight in the vendor AWQ layout (KF_T_AWQ4): qweight int32 [in][out / 8], qzeros int32 [in / 128][out / 8], scales fp16 [in / 128][out]."""
+
+    def __init__(self, ctx, qweight, qzeros, scales_f16, in_features, out_features):
+        self.ctx, self.rows, self.cols, self.type, self.group, self.qbias = ctx, out_features, in_features, L.KF_T_AWQ4, 128, 0
+        self.qw = ctx.array(np.ascontiguousarray(qweight, dtype=np.uint32).view(np.uint16))
+        self.qz = ctx.array(np.ascontiguousarray(qzeros, dtype=np.uint32).view(np.uint16))
+        self.sc = ctx.array(np.ascontiguousarray(scales_f16, dtype=np.uint16))
+
+    def desc(self):
+        return TensorDesc(self.qw.ptr, None, self.rows, self.cols, self.type, self.group, 0, self.qz.ptr, self.sc.ptr)
+
+
 def fill_normal(ctx, n, seed, sigma=0.02, mean=0.0):
     d = ctx.empty(n * 2)
     ctx.check(ctx.lib.kf_fill_normal(ctx.h, d.ptr, n, seed, sigma, mean), "kf_fill_normal")

@@ -99,7 +99,7 @@ extern "C" int kf_ctx_destroy(kf_ctx* ctx) {
         cudaFree(ctx->attn_ws);
     if (ctx->attn_cnt)
         cudaFree(ctx->attn_cnt);
-    void* scratch[6] = {ctx->xperm, ctx->xnorm, ctx->tmp0, ctx->tmp1, ctx->deq_w, ctx->xg_buf};
+    void* scratch[7] = {ctx->xperm, ctx->xnorm, ctx->tmp0, ctx->tmp1, ctx->deq_w, ctx->xg_buf, ctx->awq_ws};
     for (void* b : scratch)
         if (b)
             cudaFree(b);

@@ -37,6 +37,8 @@ struct kf_ctx {
     void* xg_buf       = nullptr;  // activations pre-staged in fragment order for the 4..8-token decode GEMV (gemv.cu, XG variants)
     size_t xg_bytes    = 0;
     int gemv_xg_min_m  = 3;        // token count from which they are, where the k-split plan would otherwise need two waves (0 = never, < 0 = always from |n|)
+    void* awq_ws        = nullptr;  // k-slice partial sums of the AWQ GEMV (awq.cu)
+    size_t awq_ws_bytes = 0;
     void* deq_w        = nullptr;  // dequantised copy of ONE NormalFloat4 weight for the many-token path (nf4.cu)
     size_t deq_w_bytes = 0;
     int tc_min_m = -1;  // token count from which kf_linear* use the tcgen05 GEMM: -1 = per weight type (linear.cu), 0 = never
@@ -111,7 +113,8 @@ static inline int kf_type_bits(int type) {
         case KF_T_BF16: return 16;
         case KF_T_F8E5M2: return 8;
         case KF_T_Q4:
-        case KF_T_NF4: return 4;
+        case KF_T_NF4:
+        case KF_T_AWQ4: return 4;
         case KF_T_Q2:
         case KF_T_SIGN: return 2;
         case KF_T_BINARY: return 1;
@@ -138,6 +141,9 @@ void kf_tmap_cache_destroy(kf_ctx* ctx);  // gemm_tc.cu
 int kf_gemv_tma(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                 const void* norm_w, float norm_eps);
 int kf_ensure_gemv_ws(kf_ctx* ctx, size_t bytes, int counters);
+// awq.cu
+int kf_awq_dequant(kf_ctx* ctx, const kf_tensor_desc* w, void* out_bf16, int transposed);
+int kf_awq_gemv(kf_ctx* ctx, void* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual);
 // nf4.cu
 int kf_nf4_quantize(kf_ctx* ctx, const void* w_bf16, int rows, int cols, void* data, void* gama);
 int kf_nf4_dequant(kf_ctx* ctx, const kf_tensor_desc* w, void* out_bf16);

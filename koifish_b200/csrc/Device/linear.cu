@@ -78,7 +78,7 @@ static bool use_tensor_cores(const kf_ctx* ctx, int n, const kf_tensor_desc* w, 
 // epilogue: 0 none, 1 residual, 2 swiglu(w[0] gate, w[1] up -> y[0]), 4 fp32
 static int linear_any(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                       const void* norm_w, float norm_eps);
-// NormalFloat4 weights (nf4.cu): RMSNorm as its own launch, then per weight either the warp-per-row LUT GEMV (<= 8 tokens) or dequantise into a
+// NormalFloat4 (nf4.cu) and vendor-AWQ (awq.cu) weights: RMSNorm as its own launch, then per weight either the warp-per-row LUT GEMV (<= 8 tokens) or dequantise into a
 // context scratch + the bf16 tensor-core GEMM (the reference's own route for every format: GTensor::GetDataX + cuBLASLt)
 static int linear_nf4(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                       const void* norm_w, float norm_eps) {
@@ -91,13 +91,13 @@ static int linear_nf4(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* 
         x = ctx->xnorm;
     }
     auto one = [&](void* yy, const kf_tensor_desc& ww, int epi, const void* res) -> int {
-        if (ww.type != KF_T_NF4) {
+        if (ww.type != KF_T_NF4 && ww.type != KF_T_AWQ4) {
             void* ys[1] = {yy};
             return linear_any(ctx, 1, ys, &ww, x, M, epi, res, nullptr, 0.f);
         }
-        if (M <= 8) return kf_nf4_gemv(ctx, yy, &ww, x, M, epi, res);
+        if (M <= 8) return ww.type == KF_T_NF4 ? kf_nf4_gemv(ctx, yy, &ww, x, M, epi, res) : kf_awq_gemv(ctx, yy, &ww, x, M, epi, res);
         int r = kf_ensure_buf(ctx, &ctx->deq_w, &ctx->deq_w_bytes, (size_t)ww.rows * ww.cols * 2);
-        if (!r) r = kf_nf4_dequant(ctx, &ww, ctx->deq_w);
+        if (!r) r = ww.type == KF_T_NF4 ? kf_nf4_dequant(ctx, &ww, ctx->deq_w) : kf_awq_dequant(ctx, &ww, ctx->deq_w, 1);
         if (r) return r;
         kf_tensor_desc bw = {};
         bw.data_dev = ctx->deq_w, bw.rows = ww.rows, bw.cols = ww.cols, bw.type = KF_T_BF16;
@@ -119,7 +119,7 @@ static int linear_nf4(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* 
 static int linear_any(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, const void* x, int M, int epilogue, const void* residual,
                       const void* norm_w, float norm_eps) {
     for (int i = 0; i < n; i++)
-        if (w[i].type == KF_T_NF4) return linear_nf4(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
+        if (w[i].type == KF_T_NF4 || w[i].type == KF_T_AWQ4) return linear_nf4(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
     if (!use_tensor_cores(ctx, n, w, M)) return linear_panels(ctx, n, y, w, x, M, epilogue, residual, norm_w, norm_eps);
     // ---- tensor-core path: RMSNorm (if any) once into a scratch, then one tcgen05 GEMM per weight ----
     const int K    = w[0].cols;

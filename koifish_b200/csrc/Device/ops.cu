@@ -248,6 +248,7 @@ extern "C" int kf_embed(kf_ctx* ctx, void* out, const kf_tensor_desc* w, const i
     if (!ctx || !out || !w || !tokens || !w->data_dev) return KF_ERR_BAD_ARG;
     KF_REQUIRE(ctx, M >= 1, "M");
     if (w->type == KF_T_NF4) return kf_nf4_embed(ctx, out, w, tokens, M);
+    KF_REQUIRE(ctx, w->type != KF_T_AWQ4, "embedding tables in the AWQ layout are not supported");
     const int bits = kf_type_bits(w->type);
     KF_REQUIRE(ctx, bits > 0, "type");
     const uint16_t *gz = nullptr, *gs = nullptr;

@@ -170,6 +170,7 @@ extern "C" int kf_quantize(kf_ctx* ctx, const void* w, int rows, int cols, int t
             *qbias_out = 0;
         return KF_OK;
     }
+    KF_REQUIRE(ctx, type != KF_T_AWQ4, "AWQ tensors come packed from vendor checkpoints: there is no AWQ quantiser (nor has the reference one)");
     if (type == KF_T_NF4) {
         if (qbias_out) *qbias_out = 0;
         return kf_nf4_quantize(ctx, w, rows, cols, data, gama);
@@ -245,6 +246,7 @@ extern "C" int kf_dequant(kf_ctx* ctx, const kf_tensor_desc* w, void* out) {
         return KF_OK;
     }
     if (w->type == KF_T_NF4) return kf_nf4_dequant(ctx, w, out);
+    if (w->type == KF_T_AWQ4) return kf_awq_dequant(ctx, w, out, 1);  // [rows = out_features][cols = in_features], like every other type
     KF_REQUIRE(ctx, kf_type_packed(w->type) && kf_has_gama(*w) && w->group > 0, "packed tensor needs gama + group");
     const int bits = kf_type_bits(w->type), per = 128 / bits;
     KF_REQUIRE(ctx, n % w->group == 0 && w->group % per == 0, "group / word alignment");

@@ -447,6 +447,81 @@ struct kfo_model {
     std::vector<uint16_t> kc, vc;         /* [L][max_seq][kv_dim] : KVCache, src/Utils/Cache.cpp:14-60 */
 };
 /* ------------------------------------------------------------------------------------------------
+ * Vendor AWQ layout: CU_Q42X_awq (quantizer.cu:132-156) with CU_I2Q4_unpack (packedN.cuh:109-116).
+ * ---------------------------------------------------------------------------------------------- */
+static const int kfo_awq_order[8] = {0, 4, 1, 5, 2, 6, 3, 7}; /* AWQ_REVERSE_ORDER: element k of a word sits at nibble order[k] */
+static inline float kfo_f16_to_f32(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1f, man = h & 0x3ffu;
+    uint32_t bits;
+    if (exp == 0) {
+        if (man == 0) {
+            bits = sign;
+        } else { /* subnormal */
+            int e = -1;
+            uint32_t m = man;
+            do { e++, m <<= 1; } while (!(m & 0x400u));
+            bits = sign | (uint32_t)(127 - 15 - e) << 23 | (m & 0x3ffu) << 13;
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7f800000u | man << 13;
+    } else {
+        bits = sign | (exp + 112) << 23 | man << 13;
+    }
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+extern "C" int kfo_awq_dequant(const uint32_t* qweight, const uint32_t* qzeros, const uint16_t* scales_f16, int M, int N, uint16_t* out) {
+    if (N % 8 || M % 128) return -1;
+#pragma omp parallel for schedule(static)
+    for (int row = 0; row < M; row++) {
+        const uint32_t* q = qweight + (size_t)row * (N / 8);
+        const uint32_t* z = qzeros + (size_t)(row / 128) * (N / 8);
+        const uint16_t* sc = scales_f16 + (size_t)(row / 128) * N;
+        for (int c = 0; c < N / 8; c++)
+            for (int k = 0; k < 8; k++) {
+                const int sft = kfo_awq_order[k] * 4;
+                const int qv = (q[c] >> sft) & 0xF, zv = (z[c] >> sft) & 0xF;
+                const float g0 = (float)(qv - zv) * kfo_f16_to_f32(sc[8 * c + k]); /* (q8[i] - z8[i]) * (float)scale8[i] */
+                out[(size_t)row * N + 8 * c + k] = kfo_f32_to_bf16(g0);
+            }
+    }
+    return 0;
+}
+extern "C" int kfo_awq_pack(const uint16_t* w, int M, int N, uint32_t* qweight, uint32_t* qzeros, uint16_t* scales_f16) {
+    if (N % 8 || M % 128) return -1;
+    memset(qweight, 0, sizeof(uint32_t) * (size_t)M * (N / 8));
+    memset(qzeros, 0, sizeof(uint32_t) * (size_t)(M / 128) * (N / 8));
+    for (int g = 0; g < M / 128; g++)
+        for (int col = 0; col < N; col++) {
+            float vmin = FLT_MAX, vmax = -FLT_MAX;
+            for (int r = 0; r < 128; r++) {
+                const float a = kfo_bf16_to_f32(w[(size_t)(g * 128 + r) * N + col]);
+                vmin = std::min(vmin, a), vmax = std::max(vmax, a);
+            }
+            float scale = (vmax - vmin) / 15.0f;
+            if (!(scale > 0)) scale = 1.0f;
+            /* fp16 scale, round to nearest via the float -> half conversion of the compiler */
+            const _Float16 hs = (_Float16)scale;
+            uint16_t hbits;
+            memcpy(&hbits, &hs, 2);
+            scales_f16[(size_t)g * N + col] = hbits;
+            const float s = (float)hs;
+            int zq = (int)lrintf(-vmin / s);
+            zq     = std::max(0, std::min(15, zq));
+            const int word = col / 8, sft = kfo_awq_order[col % 8] * 4;
+            qzeros[(size_t)g * (N / 8) + word] |= (uint32_t)zq << sft;
+            for (int r = 0; r < 128; r++) {
+                const float a = kfo_bf16_to_f32(w[(size_t)(g * 128 + r) * N + col]);
+                int qv        = (int)lrintf(a / s) + zq;
+                qv            = std::max(0, std::min(15, qv));
+                qweight[(size_t)(g * 128 + r) * (N / 8) + word] |= (uint32_t)qv << sft;
+            }
+        }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * NormalFloat4, QUANT_MODE::RTNf -- what {"bits": 4} without a quant_method selects (GeQuant.cpp:1270-1280).
  * Quantise: GeQuant::_row_lut (GeQuant.cpp:696-732): per row, Distri_PIPE::Next over the fp32 values (vmin / vmax / abs_max, GTensor.hpp:141-148),
  * Prepare(16) in its default symmetric case (:674-681: scale = abs_max > 0 ? 1 / abs_max : 1 ; codebook[i] = table[i] / scale), the LUT stored

@@ -97,6 +97,9 @@ def lib():
         L.kfo_rope.argtypes = [_u16p, C.c_int, C.c_int, C.c_int, C.c_float]
         L.kfo_swiglu.argtypes = [_u16p, _u16p, _u16p, C.c_size_t]
         L.kfo_add.argtypes = [_u16p, _u16p, _u16p, C.c_size_t]
+        _u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+        L.kfo_awq_dequant.argtypes = [_u32p, _u32p, _u16p, C.c_int, C.c_int, _u16p]
+        L.kfo_awq_pack.argtypes = [_u16p, C.c_int, C.c_int, _u32p, _u32p, _u16p]
         L.kfo_nf4_quantize.argtypes = [_u16p, C.c_int, C.c_int, _u8p, _u16p]
         L.kfo_nf4_dequant.argtypes = [_u8p, _u16p, C.c_int, C.c_int, _u16p]
         L.kfo_sample.restype = C.c_int
@@ -139,6 +142,7 @@ def refq():
     if _refq is None and os.path.exists(REFQ_SO):
         _refq = C.CDLL(REFQ_SO)
         _refq.refq_nf4_dequant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        _refq.refq_awq_dequant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     return _refq
 
 
@@ -212,6 +216,20 @@ def quantize(w, rows, cols, bits, group=128, mode=RTN_ASYM):
     rc = lib().kfo_quantize(w, rows, cols, bits, group, mode, data, gama)
     assert rc == 0, rc
     return data, gama
+
+
+def awq_pack(w_in_out, M, N):
+    """test helper: bf16 [M = in_features][N = out_features] -> (qweight int32 [M][N/8], qzeros int32 [M/128][N/8], scales fp16 [M/128][N])"""
+    w = np.ascontiguousarray(w_in_out, dtype=np.uint16).reshape(-1)
+    qw, qz, sc = np.zeros(M * N // 8, np.uint32), np.zeros(M // 128 * N // 8, np.uint32), np.zeros(M // 128 * N, np.uint16)
+    assert lib().kfo_awq_pack(w, M, N, qw, qz, sc) == 0
+    return qw, qz, sc
+
+
+def awq_dequant(qw, qz, sc, M, N):
+    out = np.zeros(M * N, dtype=np.uint16)
+    assert lib().kfo_awq_dequant(np.ascontiguousarray(qw), np.ascontiguousarray(qz), np.ascontiguousarray(sc), M, N, out) == 0
+    return out.reshape(M, N)
 
 
 def nf4_quantize(w, rows, cols):

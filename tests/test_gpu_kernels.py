@@ -987,3 +987,38 @@ def test_gemv_fast_prestaged_activations_equal_per_cta_staging(ctx, kind, M):
     for a, b in zip(outs[0], outs[3]):
         assert np.array_equal(a, b)
     _check_linear(outs[3][0], wdq, xd.numpy(np.uint16).reshape(M, K), M, N, K, noise=_fast_noise(kind))
+
+
+# ---------------------------------------------------------------------------------------------- vendor AWQ layout (device level)
+def _awq_tensor(ctx, IC, OC, seed):
+    w_io = ol.fill_normal(IC * OC, seed, 0.02)  # [in][out]
+    qw, qz, sc = ol.awq_pack(w_io, IC, OC)
+    deq_io = ol.awq_dequant(qw, qz, sc, IC, OC)  # bf16 [in][out], the reference's GetDataX order
+    return kf.AwqTensor(ctx, qw, qz, sc, IC, OC), np.ascontiguousarray(deq_io.T), deq_io
+
+
+@pytest.mark.parametrize("IC,OC", [(256, 512), (1024, 264), (4096, 1024)])
+def test_awq_dequant_bit_exact_and_matches_reference_kernel(ctx, IC, OC):
+    t, wdq, deq_io = _awq_tensor(ctx, IC, OC, IC + OC)
+    assert np.array_equal(kf.dequant(ctx, t).numpy(np.uint16).reshape(OC, IC), wdq)  # [out][in], like every other type
+    ref = ol.refq()
+    if ref is None:
+        pytest.skip("oracle/_ref/libkoifish_refq.so not built (reference tree absent at build time)")
+    out = ctx.empty(IC * OC * 2)
+    ctx.sync()
+    # the reference's own CU_Q42X_awq (quantizer.cu:132-156) on the same buffers: [in][out]
+    assert ref.refq_awq_dequant(t.qz.ptr, t.sc.ptr, t.qw.ptr, out.ptr, IC, OC) == 0
+    assert np.array_equal(out.numpy(np.uint16).reshape(IC, OC), deq_io)
+
+
+@pytest.mark.parametrize("M", [1, 3, 8, 40])
+def test_awq_linear_matches_oracle(ctx, M):
+    IC, OC = 2048, 528
+    t, wdq, _ = _awq_tensor(ctx, IC, OC, 77)
+    rng = np.random.default_rng(M)
+    x = rand_bf16(rng, (M, IC))
+    y = kf.linear(ctx, t, ctx.array(x), M).numpy(np.uint16)
+    _check_linear(y, wdq, x, M, OC, IC)
+    res = rand_bf16(rng, (M, OC))
+    yr = kf.linear(ctx, t, ctx.array(x), M, kf.KF_EPI_RESIDUAL, ctx.array(res)).numpy(np.uint16)
+    assert np.array_equal(yr.reshape(M, OC), ol.add(res, y).reshape(M, OC))

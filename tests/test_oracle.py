@@ -420,3 +420,24 @@ def test_nf4_port_layout_codebook_and_nearest_code():
     for r in (0, 1, 2, 4, 5):
         k = int(np.argmax(np.abs(f[r])))
         assert fd[r, k] == f[r, k]
+
+
+# ---------------------------------------------------------------------------------------------- vendor AWQ layout (CU_Q42X_awq)
+def test_awq_port_nibble_order_and_arithmetic():
+    M, N = 256, 32  # [in_features][out_features]
+    rng = np.random.default_rng(4)
+    qw = rng.integers(0, 2 ** 32, size=M * N // 8, dtype=np.uint64).astype(np.uint32)
+    qz = rng.integers(0, 2 ** 32, size=M // 128 * N // 8, dtype=np.uint64).astype(np.uint32)
+    sc = (rng.uniform(0.001, 0.02, size=M // 128 * N)).astype(np.float16)
+    got = ol.bf16_to_f32(ol.awq_dequant(qw, qz, sc.view(np.uint16), M, N)).reshape(M, N)
+    order = [0, 4, 1, 5, 2, 6, 3, 7]  # AWQ_REVERSE_ORDER, packedN.cuh:110
+    q = np.stack([(qw.reshape(M, N // 8) >> (4 * order[k])) & 15 for k in range(8)], axis=-1).reshape(M, N).astype(np.int32)
+    z = np.stack([(qz.reshape(M // 128, N // 8) >> (4 * order[k])) & 15 for k in range(8)], axis=-1).reshape(M // 128, N).astype(np.int32)
+    want = (q - np.repeat(z, 128, axis=0)).astype(np.float32) * np.repeat(sc.reshape(M // 128, N).astype(np.float32), 128, axis=0)
+    assert np.array_equal(got, ol.bf16_to_f32(ol.f32_to_bf16(want)).reshape(M, N))
+    # the test-side packer round-trips within half a step
+    w = ol.fill_normal(M * N, 9, 0.02)
+    pw, pz, ps = ol.awq_pack(w, M, N)
+    back = ol.bf16_to_f32(ol.awq_dequant(pw, pz, ps, M, N)).reshape(M, N)
+    step = np.repeat(ps.view(np.float16).astype(np.float32).reshape(M // 128, N), 128, axis=0)
+    assert np.all(np.abs(back - ol.bf16_to_f32(w).reshape(M, N)) <= 0.51 * step + 1e-4)
