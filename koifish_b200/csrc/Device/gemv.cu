@@ -1027,12 +1027,19 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
             for (int cand = S_min; cand <= std::min(p.steps_total, 64); cand++) {
                 const int nst = (p.steps_total + cand - 1) / cand;
                 if (nst < 2 && cand > S_min) break;
-                const bool clustered = can_cluster && cand >= 2 && cand <= 8;
+                // the merge area must fit next to the slice (launch_one falls back to the global merge otherwise)
+                // ... and, with several tokens, the slices short: measured at 8 tokens on 5120 x 25600, 8 cluster-merged slices of 25
+                // k-steps take 34.6 us against 29.4 for 11 slices through the global workspace
+                const bool clustered = can_cluster && cand >= 2 && cand <= 8 && (M == 1 || nst <= 16) &&
+                                       ringb + (size_t)nst * stepb + (size_t)cand * M * rows_cta * 4 + 1024 <= kSmemCap;
                 if (clustered && (cand & (cand - 1)) && cand > S_min) continue;  // cluster sizes 3, 5, 6, 7 pack badly
-                const int per_sm  = (soft_steps && nst <= soft_steps) ? per_sm3 : per_sm2;
+                // the cluster merge area ([S][M][rows] floats in the leader) counts against the shared memory that decides 3 or 2 CTAs per SM
+                const size_t smem_c = ringb + (size_t)nst * stepb + (clustered ? (size_t)cand * M * rows_cta * 4 : 0);
+                const int per_sm  = (soft_steps && nst <= soft_steps && smem_c <= kSmemSoft) ? per_sm3 : per_sm2;
                 const int slots   = ctx->sm_count * per_sm;
                 const int waves   = (rb * cand + slots - 1) / slots;
-                const double fixed = cand == 1 ? 4.0 : clustered ? 5.0 : 7.5;  // us: prologue + merge
+                // us: prologue + merge; the merge moves M x rows floats per slice (measured at 8 tokens: global merge ~ +4 us, cluster ~ +1)
+                const double fixed = cand == 1 ? 4.0 : clustered ? 5.0 + 0.15 * (MXs - 1) : 7.5 + 0.6 * (MXs - 1);
                 // bytes in flight = CTAs x ring depth x 8 KB per k-step; what they can pull per DRAM round trip (~1.65 us) caps the stream
                 const double ctas   = std::min<double>((double)rb * cand, slots);
                 const double bw     = std::min(6.0e6, ctas * 3.0 * rows_cta * (KSTEP * bits_of_fmt / 8.0) / 1.65);  // bytes per us
@@ -1066,7 +1073,7 @@ int gemv_dispatch(kf_ctx* ctx, int n, void* const* y, const kf_tensor_desc* w, c
     S = std::max(S, S_min);
     S = std::max(1, std::min(S, p.steps_total));
     if (M == 1 && ctx->gemv_cluster == 2 && ctx->gemv_splitk <= 0 && S > 8 && S_min <= 8) S = 8;
-    p.cluster    = (M <= 8 && ctx->gemv_cluster > 0 && S >= 2 && S <= 8) ? 1 : 0;
+    p.cluster    = (M <= 8 && ctx->gemv_cluster > 0 && S >= 2 && S <= 8 && (M == 1 || (p.steps_total + S - 1) / S <= 16 || ctx->gemv_splitk > 0)) ? 1 : 0;
     p.S          = S;
     ctx->gemv_last_s = S;
     p.nsteps_max = (p.steps_total + S - 1) / S;  // floor/ceil slicing never exceeds ceil(steps/S)
