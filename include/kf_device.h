@@ -80,6 +80,9 @@ typedef struct kf_ctx kf_ctx;
 int kf_ctx_create(int device, void* cuda_stream /* cudaStream_t or NULL: the context creates its own */, kf_ctx** out);
 int kf_ctx_destroy(kf_ctx* ctx);
 int kf_ctx_sync(kf_ctx* ctx);
+/* One process per GPU is the intended use.  A process that holds contexts on several devices must make the context's device current
+ * (cudaSetDevice) before calling into it; kf_ctx_make_current does that.  The model runtime (kf_model.h) calls it on every forward. */
+int kf_ctx_make_current(kf_ctx* ctx);
 void* kf_ctx_stream(kf_ctx* ctx);
 int kf_ctx_sm_count(kf_ctx* ctx);
 const char* kf_status_string(int status);

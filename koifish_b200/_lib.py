@@ -43,6 +43,7 @@ SIGNATURES = {
     "kf_ctx_create": (_I, [_I, _P, C.POINTER(_P)]),
     "kf_ctx_destroy": (_I, [_P]),
     "kf_ctx_sync": (_I, [_P]),
+    "kf_ctx_make_current": (_I, [_P]),
     "kf_ctx_stream": (_P, [_P]),
     "kf_ctx_sm_count": (_I, [_P]),
     "kf_status_string": (C.c_char_p, [_I]),

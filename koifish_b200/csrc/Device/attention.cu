@@ -970,18 +970,18 @@ extern "C" int kf_attn_prefill(kf_ctx* ctx, void* out, const void* q, const void
     dim3 grid((M + kPfQ - 1) / kPfQ, n_head);
     const float sq = sqrtf((float)hd);
     if (hd == 128) {
-        static bool set = false;
-        if (!set) {
+        static bool set[kf_ctx::kMaxDevices] = {};  // function attributes are per device
+        if (!set[ctx->device]) {
             KF_CUDA(ctx, cudaFuncSetAttribute(kf_attn_prefill_kernel<128, KF_PF_BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set = true;
+            set[ctx->device] = true;
         }
         kf_attn_prefill_kernel<128, KF_PF_BKV><<<grid, 128, smem, ctx->stream>>>((uint16_t*)out, (const uint16_t*)q, (const uint16_t*)kc, (const uint16_t*)vc,
                                                                       pos_dev, M, n_head, n_kv, max_seq, sq);
     } else {
-        static bool set = false;
-        if (!set) {
+        static bool set[kf_ctx::kMaxDevices] = {};  // function attributes are per device
+        if (!set[ctx->device]) {
             KF_CUDA(ctx, cudaFuncSetAttribute(kf_attn_prefill_kernel<64, KF_PF_BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set = true;
+            set[ctx->device] = true;
         }
         kf_attn_prefill_kernel<64, KF_PF_BKV><<<grid, 128, smem, ctx->stream>>>((uint16_t*)out, (const uint16_t*)q, (const uint16_t*)kc, (const uint16_t*)vc,
                                                                      pos_dev, M, n_head, n_kv, max_seq, sq);
@@ -1013,18 +1013,18 @@ extern "C" int kf_attn_decode_gqa(kf_ctx* ctx, void* out, const void* q, const v
     dim3 grid(n_kv, M, nsplit);
     const float sq = sqrtf((float)hd);
     if (hd == 128) {
-        static bool set = false;
-        if (!set) {
+        static bool set[kf_ctx::kMaxDevices] = {};  // function attributes are per device
+        if (!set[ctx->device]) {
             KF_CUDA(ctx, cudaFuncSetAttribute(kf_attn_gqa_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set = true;
+            set[ctx->device] = true;
         }
         kf_attn_gqa_kernel<128><<<grid, 128, smem, ctx->stream>>>((uint16_t*)out, ws, (const uint16_t*)q, (const uint16_t*)kc, (const uint16_t*)vc,
                                                                   pos_dev, n_head, n_kv, nsplit, sq, seq_stride);
     } else {
-        static bool set = false;
-        if (!set) {
+        static bool set[kf_ctx::kMaxDevices] = {};  // function attributes are per device
+        if (!set[ctx->device]) {
             KF_CUDA(ctx, cudaFuncSetAttribute(kf_attn_gqa_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set = true;
+            set[ctx->device] = true;
         }
         kf_attn_gqa_kernel<64><<<grid, 128, smem, ctx->stream>>>((uint16_t*)out, ws, (const uint16_t*)q, (const uint16_t*)kc, (const uint16_t*)vc,
                                                                  pos_dev, n_head, n_kv, nsplit, sq, seq_stride);

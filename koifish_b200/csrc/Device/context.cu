@@ -108,6 +108,11 @@ extern "C" int kf_ctx_destroy(kf_ctx* ctx) {
     delete ctx;
     return KF_OK;
 }
+extern "C" int kf_ctx_make_current(kf_ctx* ctx) {
+    if (!ctx) return KF_ERR_BAD_ARG;
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    return KF_OK;
+}
 extern "C" int kf_ctx_sync(kf_ctx* ctx) {
     if (!ctx)
         return KF_ERR_BAD_ARG;

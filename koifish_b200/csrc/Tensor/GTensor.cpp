@@ -79,6 +79,9 @@ bool QUANT_CARD::Init4Neuron(const std::string& name, const JSON& jQuant) {
         if (const JSON* g = jQ.find("group_size")) T_group = g->as_int(T_group);
         if (T_group <= 0 || T_group >= 102400) throw std::runtime_error("quantizer: bad group_size");
         if (const JSON* z = jQ.find("zero_point")) isZeroPoint = z->as_bool(isZeroPoint);
+        // "filterQ" is read into the card by the reference too (GeQuant.cpp:1231-1233) and then never consulted: QUANT_CARD::isPass
+        // (:1286-1296) returns `type == NO_QUANT`, the name filter below it is commented out.  Same here: accepted, without effect.
+        has_filterQ = jQ.find("filterQ") != nullptr;
         if (has_ci(info, "AWQ"))
             type = AWQ;
         else if (has_ci(info, "RTN") || has_ci(info, "bitnet"))

@@ -30,6 +30,7 @@ struct QUANT_CARD {
     float T_errQ      = 0.3f;
     bool isSymmetric  = false;
     bool isZeroPoint  = false;
+    bool has_filterQ  = false;  // "filterQ" present in the matched entry (parsed by the reference, unused by its isPass)
     bool isVendorQuant = false;
     QUANT_YYANG_ yyang = I_OFF;
     QUANT_MODE type    = NO_QUANT;

@@ -490,6 +490,7 @@ int Fish::UseGraph(int M, bool want_logits) {
 
 int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, uint16_t* logits_out, int32_t* next_out) {
     std::string* hFishErr = &error;
+    KF_TRY(kf_ctx_make_current(ctx));
     if (!tokens || !pos || M < 1 || M > max_tokens) {
         error = "Forward: 1 <= M <= " + std::to_string(max_tokens);
         return KF_ERR_BAD_ARG;
@@ -562,6 +563,7 @@ int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, ui
 // positions staged by the last Forward() call are the starting state.
 int Fish::DecodeLoop(int n_steps, int M) {
     std::string* hFishErr = &error;
+    KF_TRY(kf_ctx_make_current(ctx));
     if (M < 1 || M > max_tokens || n_steps < 0) {
         error = "DecodeLoop: 1 <= M <= " + std::to_string(max_tokens) + ", n_steps >= 0";
         return KF_ERR_BAD_ARG;
