@@ -15,7 +15,12 @@
  *     CU_rmsnorm_multihead), RoPE (CU_rope2_v0), decode attention (attention_qk_kernel / CU_softmax_multihead / attention_v_kernel)
  *     and the E5M2 byte codec: the reference's OWN CUDA kernels, compiled for sm_100a from src/Device/CUDA/T.cu and the headers it
  *     includes (oracle/ref_kernels.cu -> oracle/_ref/libkoifish_refgpu*.so) and run on the B200 next to koifish_b200's kernels
- *     (tests/test_gpu_refkernels.py, -m gpu).  Committed fixtures generated by those kernels: tests/golden/refgpu_*.npz.
+ *     (tests/test_gpu_refkernels.py, -m gpu);
+ *   - NormalFloat4 and vendor-AWQ dequant: CU_Q42X_NF4 / CU_Q42X_awq from src/Device/CUDA/kernel/quantizer.cu (oracle/ref_kernels_q.cu ->
+ *     oracle/_ref/libkoifish_refq.so; tests/test_gpu_kernels.py);
+ *   - outputs of all of these reference kernels on seeded inputs are committed as tests/golden/refgpu_golden.npz (generator
+ *     tests/golden/make_golden_refgpu.py, inputs tests/golden_cases.py) and checked against the oracle WITHOUT a GPU by
+ *     tests/test_oracle_golden_refgpu.py.
  * Still unpinned: the CPU packer GeQuant::RTN_x / YinYang (src/Tensor/GeQuant.cpp:428-628) -- it only links with the whole framework;
  * it is restated from the cited lines and cross-checked against the reference's GPU packer (same algorithm, float arithmetic that
  * differs in documented places) -- and the cuBLASLt GEMM (closed source; fp32 accumulation, order unspecified => tolerance).
