@@ -73,6 +73,13 @@ int kf_model_set_sampler(kf_model* m, float temperature, int top_k, float top_p,
 /* Save / load every resident tensor exactly as it sits in HBM (packed data || gama, the reference's per-tensor SerialGamaData payload,
  * src/Device/CUDA/huTensor.cu:413-458): loading skips the quantiser.  The file must come from a model built from the same config
  * (names, shapes, storage types and groups are checked); tensor-parallel ranks use one file per rank. */
+/* HF checkpoints (Fish::LoadFolderOfST -> SAFETENSOR2Gensors -> GTensor::LoadParam, src/Manifold/Serialize.cpp:1010-1100, :145-230):
+ * every tensor of `path_or_dir` ("model.safetensors", or a directory of *.safetensors shards) whose name the model knows is converted
+ * to bf16 (BF16 / F16 / F32 sources), sharded for this rank and quantised per the quantizer card, as kf_model_set_tensor does.  Unknown
+ * names are skipped and counted; vendor-quantised AWQ tensors (.qweight / .qzeros / .scales) are refused.
+ * kf_safetensors_index: the header of one file as JSON text [{"name","dtype","shape","nbytes"}, ...] (host only; free with kf_string_free). */
+int kf_model_load_safetensors(kf_model* m, const char* path_or_dir, int* n_loaded_out, int* n_skipped_out);
+int kf_safetensors_index(const char* path, char** json_out, char** err_out);
 int kf_model_save(kf_model* m, const char* path);
 int kf_model_load(kf_model* m, const char* path);
 

@@ -347,6 +347,21 @@ def sample(ctx, logits, M, vocab, temperature, top_k, top_p, rng_state, selectio
     return out
 
 
+def safetensors_index(path):
+    """header of a .safetensors file: list of {"name", "dtype", "shape", "nbytes"} in file order (host only)"""
+    lib = L.load()
+    out, err = C.c_void_p(), C.c_void_p()
+    st = lib.kf_safetensors_index(str(path).encode(), C.byref(out), C.byref(err))
+    msg = C.cast(err, C.c_char_p).value.decode() if err.value else ""
+    if err.value:
+        lib.kf_string_free(err)
+    if st != L.KF_OK:
+        raise L.KoifishError(st, "kf_safetensors_index", msg)
+    text = C.cast(out, C.c_char_p).value.decode()
+    lib.kf_string_free(out)
+    return json.loads(text)
+
+
 class Model:
     """The Qwen3 runtime behind include/kf_model.h (reference: Fish::MakeInstance + Fish::Chat's per-token ForwardOnRLS)."""
 
@@ -445,6 +460,12 @@ class Model:
 
     def load(self, path):
         self._check(self.lib.kf_model_load(self.h, str(path).encode()), "kf_model_load")
+
+    def load_safetensors(self, path_or_dir):
+        """HF model.safetensors (or a directory of shards) -> (tensors loaded, tensors skipped)"""
+        a, b = C.c_int(0), C.c_int(0)
+        self._check(self.lib.kf_model_load_safetensors(self.h, str(path_or_dir).encode(), C.byref(a), C.byref(b)), "kf_model_load_safetensors")
+        return a.value, b.value
 
     def set_sampler(self, temperature, top_k=50, top_p=0.95, seed=42, selection=0):
         self._check(self.lib.kf_model_set_sampler(self.h, float(temperature), int(top_k), float(top_p), int(seed), int(selection)), "kf_model_set_sampler")

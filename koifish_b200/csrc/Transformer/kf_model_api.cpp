@@ -3,6 +3,7 @@
 #include <cstring>
 #include <stdexcept>
 
+#include "../Tensor/Safetensors.hpp"
 #include "QWen3.hpp"
 #include "kf_model.h"
 
@@ -196,5 +197,79 @@ extern "C" int kf_model_set_graphs(kf_model* m, int enable) {
     if (!m) return KF_ERR_BAD_ARG;
     m->fish->use_graphs = enable != 0;
     if (!enable) m->fish->ResetGraphs();
+    return KF_OK;
+}
+
+// ---- HF safetensors (Fish::LoadFolderOfST, reference src/Manifold/Serialize.cpp:1010-1100) ------------------------------------------
+// index of one file as JSON text: [{"name","dtype","shape","nbytes"}, ...] in file order.  Host only: no device, no model.
+extern "C" int kf_safetensors_index(const char* path, char** json_out, char** err_out) {
+    if (err_out) *err_out = nullptr;
+    if (!path || !json_out) return KF_ERR_BAD_ARG;
+    *json_out = nullptr;
+    KfStFile f;
+    std::string err;
+    if (kf_st_parse(path, &f, &err) != 0) {
+        if (err_out) *err_out = dup_cstr(err);
+        return KF_ERR_BAD_ARG;
+    }
+    std::string j = "[";
+    for (size_t i = 0; i < f.entries.size(); i++) {
+        const KfStEntry& e = f.entries[i];
+        j += (i ? ",{\"name\":\"" : "{\"name\":\"") + e.name + "\",\"dtype\":\"" + e.dtype + "\",\"shape\":[";
+        for (size_t d = 0; d < e.shape.size(); d++) j += (d ? "," : "") + std::to_string(e.shape[d]);
+        j += "],\"nbytes\":" + std::to_string(e.end - e.begin) + "}";
+    }
+    j += "]";
+    *json_out = dup_cstr(j);
+    return KF_OK;
+}
+// Every tensor of the file (or of every *.safetensors of the directory) whose name the model knows is set from it -- BF16 / F16 / F32
+// sources, rounded to bf16, sharded for this rank and quantised per the quantizer card exactly as kf_model_set_tensor does.  Names the
+// model does not have (rotary inv_freq, a tied lm_head.weight, biases ...) are skipped and counted.  Vendor-quantised tensors
+// (.qweight / .qzeros / .scales of an AWQ checkpoint) are refused: the runtime has no loader for them.
+extern "C" int kf_model_load_safetensors(kf_model* m, const char* path_or_dir, int* n_loaded_out, int* n_skipped_out) {
+    if (!m || !path_or_dir) return KF_ERR_BAD_ARG;
+    int loaded = 0, skipped = 0;
+    if (n_loaded_out) *n_loaded_out = 0;
+    if (n_skipped_out) *n_skipped_out = 0;
+    try {
+        std::vector<std::string> files;
+        std::string err;
+        if (kf_st_list(path_or_dir, &files, &err) != 0) throw std::runtime_error(err);
+        std::vector<uint8_t> raw;
+        std::vector<uint16_t> bf;
+        for (const std::string& path : files) {
+            KfStFile f;
+            if (kf_st_parse(path, &f, &err) != 0) throw std::runtime_error(err);
+            for (const KfStEntry& e : f.entries) {
+                auto ends_with = [&](const char* suf) {
+                    const size_t n = strlen(suf);
+                    return e.name.size() > n && e.name.compare(e.name.size() - n, n, suf) == 0;
+                };
+                if (ends_with(".qweight") || ends_with(".qzeros") || ends_with(".scales"))
+                    throw std::runtime_error("'" + e.name + "': vendor-quantised (AWQ) checkpoints are not supported by the model runtime");
+                if (!m->fish->GetTensor(e.name)) {
+                    skipped++;
+                    continue;
+                }
+                if (e.dtype != "BF16" && e.dtype != "F16" && e.dtype != "F32") throw std::runtime_error("'" + e.name + "': dtype " + e.dtype + " cannot be a weight");
+                if (e.shape.empty() || e.shape.size() > 2) throw std::runtime_error("'" + e.name + "': expected a vector or a matrix");
+                const int64_t rows = e.shape.size() == 2 ? e.shape[0] : 1, cols = e.shape.back();
+                if (rows <= 0 || cols <= 0 || rows > 0x7fffffff || cols > 0x7fffffff) throw std::runtime_error("'" + e.name + "': bad shape");
+                raw.resize(e.end - e.begin);
+                if (kf_st_read(f, e, raw.data(), &err) != 0) throw std::runtime_error(err);
+                bf.resize((size_t)rows * cols);
+                kf_st_to_bf16(e.dtype, raw.data(), bf.size(), bf.data());
+                const int rc = m->fish->SetTensor(e.name, bf.data(), (int)rows, (int)cols);
+                if (rc) return rc;  // Fish::error is set
+                loaded++;
+            }
+        }
+    } catch (const std::exception& e) {
+        m->fish->error = std::string("load_safetensors: ") + e.what();
+        return KF_ERR_BAD_ARG;
+    }
+    if (n_loaded_out) *n_loaded_out = loaded;
+    if (n_skipped_out) *n_skipped_out = skipped;
     return KF_OK;
 }

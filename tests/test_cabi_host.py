@@ -157,3 +157,28 @@ def test_integration_doc_names_real_symbols():
         pytest.skip("INTEGRATION.md not written yet")
     used = set(re.findall(r"\b(kf_[a-z0-9_]+)\s*\(", open(p).read()))
     assert used and used <= _declared_symbols(), used - _declared_symbols()
+
+
+# ---------------------------------------------------------------------------------------------- HF safetensors header (host only)
+def test_safetensors_index_and_malformed_files(tmp_path):
+    import numpy as np
+    from st_util import write_safetensors
+    p = tmp_path / "model.safetensors"
+    write_safetensors(p, [("model.norm.weight", "BF16", np.arange(8, dtype=np.uint16)),
+                          ("model.layers.0.mlp.up_proj.weight", "F32", np.ones((4, 6), dtype=np.float32)),
+                          ("model.layers.0.self_attn.q_proj.qweight", "I32", np.zeros((2, 3), dtype=np.int32))], metadata={"format": "pt"})
+    idx = kf.safetensors_index(p)
+    assert [e["name"] for e in idx] == ["model.norm.weight", "model.layers.0.mlp.up_proj.weight", "model.layers.0.self_attn.q_proj.qweight"]
+    assert idx[0] == {"name": "model.norm.weight", "dtype": "BF16", "shape": [8], "nbytes": 16}
+    assert idx[1]["shape"] == [4, 6] and idx[1]["nbytes"] == 96 and idx[2]["dtype"] == "I32"
+    # malformed: missing file, truncated, header length beyond the file, offsets that do not match shape x dtype
+    with pytest.raises(kf.KoifishError):
+        kf.safetensors_index(tmp_path / "nope.safetensors")
+    raw = p.read_bytes()
+    (tmp_path / "short.safetensors").write_bytes(raw[:5])
+    (tmp_path / "cut.safetensors").write_bytes(raw[:40])
+    (tmp_path / "len.safetensors").write_bytes((10 ** 9).to_bytes(8, "little") + raw[8:])
+    (tmp_path / "off.safetensors").write_bytes(raw.replace(b'"data_offsets":[0,16]', b'"data_offsets":[0,12]'))
+    for name in ("short", "cut", "len", "off"):
+        with pytest.raises(kf.KoifishError):
+            kf.safetensors_index(tmp_path / (name + ".safetensors"))

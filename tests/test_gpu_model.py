@@ -489,3 +489,49 @@ def test_model_sampler_is_seeded_and_feeds_the_decode_loop(ctx):
     model.set_sampler(0.0, 1, 1.0, 0)                       # back to greedy
     lg, nxt = model.forward([toks[-1]], [len(toks) - 1], want_logits=True, want_next=True)
     assert int(nxt[0]) == int(np.argmax(ol.bf16_to_f32(lg[0])))
+
+
+def test_load_safetensors_equals_set_tensor(ctx, tmp_path):
+    # an HF-style checkpoint (two shards in a directory; BF16, F16 and F32 tensors; names the model does not have) loaded with
+    # kf_model_load_safetensors gives the same resident tensors and the same logits as setting every tensor with kf_model_set_tensor
+    from st_util import write_safetensors
+    quantizer = {"group_size": 128, "self_attn": {"quant_method": "RTN", "bits": 4}, "mlp": {"bits": 4}, "embed_tokens": {"bits": 8}}
+    cfg = kf.qwen3_config(2, 256, 512, 4, 2, 64, 1024, quantizer, False, 64, 1, 42, 1e6)
+    a, b = kf.Model(ctx, cfg), kf.Model(ctx, cfg)
+    a.init_random()  # allocates every tensor (and tells the test their shapes); all of them are overwritten below
+    b.init_random()
+    rng = np.random.default_rng(2025)
+    shards, kinds = [[], []], ["BF16", "F16", "F32"]
+    for i, name in enumerate(a.tensor_names()):
+        d = a.tensor_desc(name)
+        rows, cols = d.rows, d.cols
+        w = (rng.standard_normal((rows, cols)) * 0.05 + (1.0 if "norm" in name else 0.0)).astype(np.float32)
+        kind = kinds[i % 3]
+        if kind == "F16":
+            src = w.astype(np.float16)
+            bits = ol.f32_to_bf16(src.astype(np.float32))
+        elif kind == "F32":
+            src = w
+            bits = ol.f32_to_bf16(w)
+        else:
+            src = bits = ol.f32_to_bf16(w)
+        b.set_tensor(name, bits.reshape(rows, cols))
+        shaped = src.reshape(cols) if rows == 1 else src.reshape(rows, cols)  # norm weights are vectors in HF checkpoints
+        shards[i % 2].append((name, kind, shaped))
+    shards[0].append(("model.rotary_emb.inv_freq", "F32", np.ones(32, dtype=np.float32)))  # a name the model does not have
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    write_safetensors(d / "model-00001-of-00002.safetensors", shards[0], metadata={"format": "pt"})
+    write_safetensors(d / "model-00002-of-00002.safetensors", shards[1])
+    loaded, skipped = a.load_safetensors(d)
+    assert loaded == len(a.tensor_names()) and skipped == 1
+    for name in ("model.layers.1.mlp.down_proj.weight", "model.embed_tokens.weight", "lm_head.weight", "model.layers.0.self_attn.q_norm.weight"):
+        assert np.array_equal(a.dequant_tensor(name), b.dequant_tensor(name)), name
+    for pos, tok in enumerate(prompt(5, 1024)):
+        la, _ = a.forward([tok], [pos])
+        lb, _ = b.forward([tok], [pos])
+        assert np.array_equal(la, lb)
+    # a vendor-quantised (AWQ) checkpoint is refused with a message
+    write_safetensors(tmp_path / "awq.safetensors", [("model.layers.0.mlp.up_proj.qweight", "I32", np.zeros((4, 4), dtype=np.int32))])
+    with pytest.raises(kf.KoifishError):
+        a.load_safetensors(tmp_path / "awq.safetensors")
