@@ -80,6 +80,8 @@ int kf_model_set_sampler(kf_model* m, float temperature, int top_k, float top_p,
  * kf_safetensors_index: the header of one file as JSON text [{"name","dtype","shape","nbytes"}, ...] (host only; free with kf_string_free). */
 int kf_model_load_safetensors(kf_model* m, const char* path_or_dir, int* n_loaded_out, int* n_skipped_out);
 int kf_safetensors_index(const char* path, char** json_out, char** err_out);
+/* one tensor of one file converted to bf16 exactly as the loader converts it (host only) */
+int kf_safetensors_read_bf16(const char* path, const char* name, void* out_bf16_host, size_t capacity_elems, char** err_out);
 int kf_model_save(kf_model* m, const char* path);
 int kf_model_load(kf_model* m, const char* path);
 

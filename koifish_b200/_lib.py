@@ -124,6 +124,7 @@ SIGNATURES = {
     "kf_model_set_graphs": (_I, [_P, _I]),
     "kf_model_load_safetensors": (_I, [_P, C.c_char_p, C.POINTER(_I), C.POINTER(_I)]),
     "kf_safetensors_index": (_I, [C.c_char_p, C.POINTER(_P), C.POINTER(_P)]),
+    "kf_safetensors_read_bf16": (_I, [C.c_char_p, C.c_char_p, _P, _SZ, C.POINTER(_P)]),
     "kf_model_set_sampler": (_I, [_P, C.c_float, _I, C.c_float, _U64, _I]),
     "kf_config_dims": (_I, [C.c_char_p, C.POINTER(ModelInfo), C.POINTER(_P)]),
     "kf_config_quant_of": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_P)]),

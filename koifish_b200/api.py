@@ -362,6 +362,19 @@ def safetensors_index(path):
     return json.loads(text)
 
 
+def safetensors_read_bf16(path, name, n):
+    """one tensor of a .safetensors file as bf16 bit patterns (BF16 / F16 / F32 sources), converted as the loader converts it (host only)"""
+    lib = L.load()
+    out, err = np.zeros(n, dtype=np.uint16), C.c_void_p()
+    st = lib.kf_safetensors_read_bf16(str(path).encode(), name.encode(), out.ctypes.data, n, C.byref(err))
+    msg = C.cast(err, C.c_char_p).value.decode() if err.value else ""
+    if err.value:
+        lib.kf_string_free(err)
+    if st != L.KF_OK:
+        raise L.KoifishError(st, "kf_safetensors_read_bf16", msg)
+    return out
+
+
 class Model:
     """The Qwen3 runtime behind include/kf_model.h (reference: Fish::MakeInstance + Fish::Chat's per-token ForwardOnRLS)."""
 

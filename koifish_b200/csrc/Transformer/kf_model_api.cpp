@@ -223,6 +223,34 @@ extern "C" int kf_safetensors_index(const char* path, char** json_out, char** er
     *json_out = dup_cstr(j);
     return KF_OK;
 }
+// one tensor of one file as bf16 (BF16 / F16 / F32 sources, round to nearest even), host only: out_bf16 holds `capacity` elements
+extern "C" int kf_safetensors_read_bf16(const char* path, const char* name, void* out_bf16, size_t capacity, char** err_out) {
+    if (err_out) *err_out = nullptr;
+    if (!path || !name || !out_bf16) return KF_ERR_BAD_ARG;
+    KfStFile f;
+    std::string err;
+    int rc = kf_st_parse(path, &f, &err);
+    if (!rc) {
+        rc = -1, err = std::string("'") + path + "': no tensor '" + name + "'";
+        for (const KfStEntry& e : f.entries) {
+            if (e.name != name) continue;
+            size_t n = 1;
+            for (int64_t d : e.shape) n *= (size_t)d;
+            if (e.dtype != "BF16" && e.dtype != "F16" && e.dtype != "F32") {
+                err = "'" + e.name + "': dtype " + e.dtype + " cannot be read as bf16";
+            } else if (n > capacity) {
+                err = "'" + e.name + "': " + std::to_string(n) + " elements, buffer holds " + std::to_string(capacity);
+            } else {
+                std::vector<uint8_t> raw(e.end - e.begin);
+                rc = kf_st_read(f, e, raw.data(), &err);
+                if (!rc) kf_st_to_bf16(e.dtype, raw.data(), n, (uint16_t*)out_bf16);
+            }
+            break;
+        }
+    }
+    if (rc && err_out) *err_out = dup_cstr(err);
+    return rc ? KF_ERR_BAD_ARG : KF_OK;
+}
 // Every tensor of the file (or of every *.safetensors of the directory) whose name the model knows is set from it -- BF16 / F16 / F32
 // sources, rounded to bf16, sharded for this rank and quantised per the quantizer card exactly as kf_model_set_tensor does.  Names the
 // model does not have (rotary inv_freq, a tied lm_head.weight, biases ...) are skipped and counted.  Vendor-quantised tensors

@@ -182,3 +182,24 @@ def test_safetensors_index_and_malformed_files(tmp_path):
     for name in ("short", "cut", "len", "off"):
         with pytest.raises(kf.KoifishError):
             kf.safetensors_index(tmp_path / (name + ".safetensors"))
+
+
+def test_safetensors_dtype_conversions_match_the_oracle(tmp_path):
+    # F32 and F16 sources are rounded to bf16 (nearest even) exactly as the oracle's f32 -> bf16; incl. fp16 subnormals, infinities, signed zeros
+    import numpy as np
+    import oracle_lib as ol
+    from st_util import write_safetensors
+    rng = np.random.default_rng(1)
+    f32 = np.concatenate([rng.standard_normal(4096).astype(np.float32) * 10.0 ** rng.integers(-8, 8, 4096),
+                          np.array([0.0, -0.0, np.inf, -np.inf, 1.0, 1.00390625, 1.01171875, 3.3895314e38, 1e-40], dtype=np.float32)])
+    f16 = np.concatenate([rng.standard_normal(4096).astype(np.float16), np.array([0.0, -0.0, 6e-8, -6e-8, 6.1e-5, 65504.0, np.inf, -np.inf], dtype=np.float16)])
+    b16 = rng.integers(0, 65536, size=512).astype(np.uint16)
+    p = tmp_path / "t.safetensors"
+    write_safetensors(p, [("a", "F32", f32), ("b", "F16", f16), ("c", "BF16", b16)])
+    assert np.array_equal(kf.safetensors_read_bf16(p, "a", f32.size), ol.f32_to_bf16(f32))
+    assert np.array_equal(kf.safetensors_read_bf16(p, "b", f16.size), ol.f32_to_bf16(f16.astype(np.float32)))
+    assert np.array_equal(kf.safetensors_read_bf16(p, "c", b16.size), b16)
+    with pytest.raises(kf.KoifishError):
+        kf.safetensors_read_bf16(p, "nope", 8)
+    with pytest.raises(kf.KoifishError):
+        kf.safetensors_read_bf16(p, "a", 8)  # buffer too small
