@@ -184,7 +184,11 @@ def run_reference(args, dims):
         tok_s, kind, cores, sample = cb["value"], "port", cb["cores"], cb["sample"]
     line = {"impl": "reference", "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 / tok_s, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload + " decode, batch 1, ctx %d" % args.ctx, "model": "Qwen3-" + WORKLOADS[args.workload][0]},
+            # the same workload description as our arm's line (same name, model, quantizer card, batch, context): what differs is who computes it
+            "config": {"workload": "Qwen3-%s decode, batch 1, ctx %d, %s" % (WORKLOADS[args.workload][0], args.ctx, args.workload),
+                       "model": "Qwen3-" + WORKLOADS[args.workload][0], "quantizer": WORKLOADS[args.workload][1], "global_batch": 1, "seq_len": args.ctx,
+                       "parallelism": "host cores (the reference has no CPU inference path: its fp32 CPU primitives assembled into a block)",
+                       "weights": "synthetic fp32 (the reference's CPU primitives take fp32 weights)", "layers": dims["n_layer"]},
             "cpu_baseline": {"value": tok_s, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": tok_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))

@@ -203,3 +203,27 @@ def test_safetensors_dtype_conversions_match_the_oracle(tmp_path):
         kf.safetensors_read_bf16(p, "nope", 8)
     with pytest.raises(kf.KoifishError):
         kf.safetensors_read_bf16(p, "a", 8)  # buffer too small
+
+
+def test_bench_reference_arm_under_torchrun_two_ranks():
+    # the driver launches `--impl reference` like our own arm (torchrun for N > 1): rank 0 alone runs the reference's CPU primitives and
+    # prints ONE json line describing our arm's workload; the other rank exits 0 without output.  Exactly --steps timed samples.
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29613",
+           os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "3", "--warmup", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["steps"] == 3 and d["warmup"] == 1 and d["n_gpus"] == 2 and d["higher_is_better"] is True
+    assert d["metric"].startswith("decode tokens/s") and d["unit"] == "tokens/s" and d["value"] > 0
+    assert d["config"]["workload"] == "Qwen3-32B decode, batch 1, ctx 512, qwen3-32b-q4" and d["config"]["global_batch"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    if d["cpu_baseline"]["kind"] == "reference":  # oracle/_ref present: the reference's own primitives, exactly --steps timed samples
+        assert "3 timed" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
