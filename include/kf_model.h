@@ -43,6 +43,14 @@ int kf_model_init_random(kf_model* m);
 /* SERIALIZE path: hand over one FULL (unsharded) bf16 tensor by its HF name (NN2NAME, src/Transformer/QWen.cpp:61-145);
  * it is sharded for this rank and quantised at load */
 int kf_model_set_tensor(kf_model* m, const char* hf_name, const void* host_bf16, int rows, int cols);
+/* One linear of a vendor-quantised (AWQ) checkpoint by the HF name of its weight ("....q_proj.weight"), FULL shape, in the arrays the
+ * checkpoint stores (GeQuant::ExTensor src/Tensor/GeQuant.cpp:144-200, GTensor::LoadParam src/Manifold/Serialize.cpp:145-230, unpack
+ * CU_Q42X_awq src/Device/CUDA/kernel/quantizer.cu:132-156): qweight int32 [in][out / 8] (nibbles in AWQ_REVERSE_ORDER), qzeros int32
+ * [in / 128][out / 8], scales fp16 [in / 128][out].  The quantizer card must select "quant_method": "awq" for the tensor (an HF config's
+ * "quantization_config" does: QUANT_CARD::Vendor2JSONx, src/Utils/CLI_params.cpp:240-262).  The arrays are cut to the rank's window and
+ * stay in the vendor layout on the device (type KF_T_AWQ4). */
+int kf_model_set_tensor_awq(kf_model* m, const char* hf_name, const void* qweight_i32, const void* qzeros_i32, const void* scales_f16,
+                            int in_features, int out_features);
 /* descriptor of the device-resident (possibly packed) tensor: for parity tests (GetDataX equivalent via kf_dequant) */
 int kf_model_tensor_desc(kf_model* m, const char* hf_name, kf_tensor_desc* out);
 int kf_model_tensor_count(kf_model* m);
@@ -76,7 +84,8 @@ int kf_model_set_sampler(kf_model* m, float temperature, int top_k, float top_p,
 /* HF checkpoints (Fish::LoadFolderOfST -> SAFETENSOR2Gensors -> GTensor::LoadParam, src/Manifold/Serialize.cpp:1010-1100, :145-230):
  * every tensor of `path_or_dir` ("model.safetensors", or a directory of *.safetensors shards) whose name the model knows is converted
  * to bf16 (BF16 / F16 / F32 sources), sharded for this rank and quantised per the quantizer card, as kf_model_set_tensor does.  Unknown
- * names are skipped and counted; vendor-quantised AWQ tensors (.qweight / .qzeros / .scales) are refused.
+ * names are skipped and counted.  Vendor-quantised AWQ linears (<prefix>.qweight I32 / .qzeros I32 / .scales F16, possibly in different
+ * shards) become <prefix>.weight in the AWQ layout as kf_model_set_tensor_awq does; each complete triple counts as one loaded tensor.
  * kf_safetensors_index: the header of one file as JSON text [{"name","dtype","shape","nbytes"}, ...] (host only; free with kf_string_free). */
 int kf_model_load_safetensors(kf_model* m, const char* path_or_dir, int* n_loaded_out, int* n_skipped_out);
 int kf_safetensors_index(const char* path, char** json_out, char** err_out);
@@ -94,6 +103,11 @@ int kf_config_quant_of(const char* config_json, const char* tensor_name, int* ty
 /* tensor-parallel shard plan: shape_out[6] = {rows_global, cols_global, rows_local, cols_local, row0, col0} of `tensor_name` on
  * rank `rank` of `world` (Q/K/V/gate/up split by output rows, O/down by input columns in whole quant groups, the rest replicated) */
 int kf_config_shard_of(const char* config_json, const char* tensor_name, int rank, int world, int* shape_out, char** err_out);
+
+/* the same plan applied to a vendor AWQ linear (host only): rank `rank`'s blob qweight || qzeros || scales -- exactly the bytes
+ * kf_model_set_tensor_awq uploads -- cut from the FULL arrays.  *bytes_out = blob size; out_blob may be NULL to query it. */
+int kf_config_awq_shard(const char* config_json, const char* tensor_name, int rank, int world, const void* qweight_i32, const void* qzeros_i32,
+                        const void* scales_f16, void* out_blob, size_t capacity, size_t* bytes_out, char** err_out);
 
 #ifdef __cplusplus
 }

@@ -111,6 +111,7 @@ SIGNATURES = {
     "kf_model_info_get": (_I, [_P, C.POINTER(ModelInfo)]),
     "kf_model_init_random": (_I, [_P]),
     "kf_model_set_tensor": (_I, [_P, C.c_char_p, _P, _I, _I]),
+    "kf_model_set_tensor_awq": (_I, [_P, C.c_char_p, _P, _P, _P, _I, _I]),
     "kf_model_tensor_desc": (_I, [_P, C.c_char_p, _DESCP]),
     "kf_model_tensor_count": (_I, [_P]),
     "kf_model_tensor_name": (C.c_char_p, [_P, _I]),
@@ -128,6 +129,7 @@ SIGNATURES = {
     "kf_model_set_sampler": (_I, [_P, C.c_float, _I, C.c_float, _U64, _I]),
     "kf_config_dims": (_I, [C.c_char_p, C.POINTER(ModelInfo), C.POINTER(_P)]),
     "kf_config_quant_of": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_P)]),
+    "kf_config_awq_shard": (_I, [C.c_char_p, C.c_char_p, _I, _I, _P, _P, _P, _P, _SZ, C.POINTER(_SZ), C.POINTER(_P)]),
     "kf_config_shard_of": (_I, [C.c_char_p, C.c_char_p, _I, _I, C.POINTER(_I), C.POINTER(_P)]),
 }
 

@@ -420,6 +420,14 @@ class Model:
         rows, cols = (1, w.size) if w.ndim == 1 else w.shape
         self._check(self.lib.kf_model_set_tensor(self.h, name.encode(), w.ctypes.data, rows, cols), "kf_model_set_tensor(%s)" % name)
 
+    def set_tensor_awq(self, name, qweight, qzeros, scales_f16):
+        """one linear in the vendor AWQ layout, full shape: qweight int32 [in][out / 8], qzeros int32 [in / 128][out / 8], scales fp16 bits [in / 128][out]"""
+        qw = np.ascontiguousarray(qweight).view(np.uint32)
+        qz = np.ascontiguousarray(qzeros).view(np.uint32)
+        sc = np.ascontiguousarray(scales_f16).view(np.uint16)
+        self._check(self.lib.kf_model_set_tensor_awq(self.h, name.encode(), qw.ctypes.data, qz.ctypes.data, sc.ctypes.data, qw.shape[0], sc.shape[1]),
+                    "kf_model_set_tensor_awq(%s)" % name)
+
     def tensor_names(self):
         return [self.lib.kf_model_tensor_name(self.h, i).decode() for i in range(self.lib.kf_model_tensor_count(self.h))]
 

@@ -17,6 +17,7 @@ int kfType(typNUMBER t) {
         case typNUMBER::T_SIGN: return KF_T_SIGN;
         case typNUMBER::T_BINARY: return KF_T_BINARY;
         case typNUMBER::Q4_NF: return KF_T_NF4;
+        case typNUMBER::Q4_AWQ: return KF_T_AWQ4;
     }
     return KF_T_BF16;
 }
@@ -29,6 +30,7 @@ const char* typName(typNUMBER t) {
         case typNUMBER::T_SIGN: return "T_SIGN";
         case typNUMBER::T_BINARY: return "T_BINARY";
         case typNUMBER::Q4_NF: return "Q4(NF4)";
+        case typNUMBER::Q4_AWQ: return "Q4(AWQ)";
     }
     return "?";
 }
@@ -37,6 +39,7 @@ double BitPE(typNUMBER t) {
         case typNUMBER::BF16: return 16;
         case typNUMBER::F8E5M2: return 8;
         case typNUMBER::Q4:
+        case typNUMBER::Q4_AWQ:
         case typNUMBER::Q4_NF: return 4;
         case typNUMBER::Q2:
         case typNUMBER::T_SIGN: return 2;
@@ -96,6 +99,7 @@ bool QUANT_CARD::Init4Neuron(const std::string& name, const JSON& jQuant) {
 typNUMBER QUANT_CARD::tpQuant() const {
     if (type == F8Ex) return typNUMBER::F8E5M2;
     if (type == RTNf) return typNUMBER::Q4_NF;
+    if (type == AWQ) return typNUMBER::Q4_AWQ;
     if (yyang == I_TERNARY) return typNUMBER::T_SIGN;  // bit2typ(), GeQuant.cpp:127-137
     switch (default_bits) {
         case 4: return typNUMBER::Q4;
@@ -139,9 +143,27 @@ kf_tensor_desc GTensor::Desc() const {
     d.group = hQuant ? hQuant->params.T_group : 128;
     d.qbias = qBias;
     d.zero_dev = nullptr, d.step_dev = nullptr;
+    if (type == typNUMBER::Q4_AWQ) {  // include/kf_device.h KF_T_AWQ4: data_dev = qweight, zero_dev = qzeros, step_dev = scales
+        d.gama_dev = nullptr, d.group = 128;
+        d.zero_dev = (const uint8_t*)data + szData;
+        d.step_dev = (const uint8_t*)data + szData + awqZeroBytes();
+    }
     return d;
 }
+int GTensor::AllocAWQ() {
+    if (data) {
+        kf_free(ctx, data);
+        data = nullptr;
+    }
+    // whole 128-row groups, whole 32-column blocks: every section of the blob stays 16-byte aligned (awq.cu reads 8 scales as one uint4)
+    if (ne[1] % 128 || ne[0] % 32) return KF_ERR_BAD_ARG;
+    type   = typNUMBER::Q4_AWQ;
+    szData = (size_t)ne[1] * (ne[0] / 8) * 4;
+    szGama = awqZeroBytes() + (size_t)(ne[1] / 128) * ne[0] * 2;
+    return kf_malloc(ctx, szData + szGama + 16, &data);
+}
 int GTensor::Alloc(typNUMBER tp, int group) {
+    if (tp == typNUMBER::Q4_AWQ) return AllocAWQ();
     if (data) {
         kf_free(ctx, data);
         data = nullptr;
@@ -189,7 +211,10 @@ hQUANT GeQuant::MakeInstance(const std::string& neuron_name, const JSON& jQuant)
             if (card.default_bits != 4)  // RT_NormalF also accepts 3 bits (NF3), which no PackedQ storage type carries
                 throw std::runtime_error("quantizer entry '" + card.matched_key + "': NormalFloat (no quant_method) is built for bits = 4 only");
             break;
-        case AWQ: throw std::runtime_error("quantizer entry '" + card.matched_key + "': vendor AWQ layout is a 'next' row (SURVEY 8f N2), not built yet");
+        case AWQ:  // Q_AWQ (GeQuant.cpp:989-1013): 4-bit codes, 128-row groups, explicit .qzeros / .scales tensors from the vendor checkpoint
+            if (card.default_bits != 4 || card.T_group != 128)
+                throw std::runtime_error("quantizer entry '" + card.matched_key + "': the vendor AWQ layout is built for bits = 4, group_size = 128");
+            break;
         default: return nullptr;
     }
     if (card.type == RTN && card.default_bits == 1 && card.yyang == I_OFF)
@@ -201,6 +226,9 @@ int GeQuant::LowBit_worker(const hGTensor& t, const void* srcData, int flag) {
     if (!t || !srcData) return KF_ERR_BAD_ARG;
     const typNUMBER tp = params.tpQuant();
     const int rows = t->ne[0], cols = t->ne[1];
+    // AWQ tensors arrive packed from vendor checkpoints (Fish::SetTensorAWQ); like the reference there is no AWQ quantiser: kf_quantize
+    // refuses the type with a message
+    if (tp == typNUMBER::Q4_AWQ) return kf_quantize(t->ctx, srcData, rows, cols, KF_T_AWQ4, 128, KF_Q_RTN_ASYM, const_cast<void*>(srcData) /* never written */, nullptr, nullptr);
     int rc = t->Alloc(tp, params.T_group);
     if (rc) return rc;
     void* src_dev = const_cast<void*>(srcData);

@@ -16,7 +16,11 @@
 namespace koifish {
 
 // g_float.hpp:84-117 (the subset on the hot path)
-enum class typNUMBER : uint8_t { BF16, F8E5M2, Q4, Q2, T_SIGN, T_BINARY, Q4_NF /* Q4 under QUANT_MODE::RTNf: NormalFloat4 + per-row LUT */ };
+enum class typNUMBER : uint8_t {
+    BF16, F8E5M2, Q4, Q2, T_SIGN, T_BINARY,
+    Q4_NF,  /* Q4 under QUANT_MODE::RTNf: NormalFloat4 + per-row LUT */
+    Q4_AWQ  /* Q4 under QUANT_MODE::AWQ: the vendor layout, stored [in_features][out_features] (GeQuant::ExTensor, GeQuant.cpp:144-200) */
+};
 int kfType(typNUMBER t);               // -> KF_T_*
 const char* typName(typNUMBER t);
 double BitPE(typNUMBER t);             // bits per element (src/Utils/GST_float.cpp:51)
@@ -71,6 +75,11 @@ class GTensor : public std::enable_shared_from_this<GTensor> {
     kf_tensor_desc Desc() const;
     // Allocate as plain bf16 and upload / fill
     int Alloc(typNUMBER tp, int group);
+    // vendor AWQ (GeQuant::ExTensor, GeQuant.cpp:144-200: hBase -> .qweight, aux .scales / .qzeros): ONE blob
+    //   qweight int32 [cols][rows / 8]  ||  qzeros int32 [cols / 128][rows / 8]  ||  scales fp16 [cols / 128][rows]      (rows = out, cols = in)
+    // szData = the qweight bytes, szGama = qzeros + scales.
+    int AllocAWQ();
+    size_t awqZeroBytes() const { return (size_t)(ne[1] / 128) * (ne[0] / 8) * 4; }
     int SetBF16FromDevice(const void* bf16_dev);  // un-quantised tensors (norms, bf16 embed)
     // GTensor::GetDataX (quantizer.cu:249-392): dequantise to a caller-provided bf16 device buffer (test hook)
     int GetDataX(void* out_bf16_dev) const;

@@ -38,8 +38,18 @@ MODEL_CARD MODEL_CARD::FromJSON(const JSON& j0) {
         if (const JSON* t = h.find("rope_theta")) c.rope_theta = (float)t->as_double(c.rope_theta);
         if (const JSON* e = h.find("rms_norm_eps")) c.norm_rms_eps = (float)e->as_double(c.norm_rms_eps);
         if (const JSON* t = h.find("tie_word_embeddings")) c.tie_word_embeddings = t->as_bool(false);
-        if (h.contains("quantization_config"))
-            throw std::runtime_error("HF quantization_config (vendor AWQ) is a 'next' row (SURVEY 8f N2), not built yet");
+        if (const JSON* vq = h.find("quantization_config")) {
+            // QUANT_CARD::Vendor2JSONx (src/Utils/CLI_params.cpp:240-262, called from MODEL_CARD::InitHugFace :2285-2290): the vendor's block
+            // {"bits", "group_size", "quant_method": "awq", "zero_point", ...} becomes the card of every self_attn / mlp linear
+            if (!vq->is_object() || vq->empty()) throw std::runtime_error("HF quantization_config must be a non-empty object");
+            JSON q, yes;
+            q.kind = JSON::Object, yes.kind = JSON::Bool, yes.b = true;
+            q.obj.push_back({"self_attn", *vq});
+            q.obj.push_back({"mlp", *vq});
+            q.obj.push_back({"VendorQuant", yes});
+            if (vq->contains("quant_method") && vq->at("quant_method").as_string() == "awq") q.obj.push_back({"ExplicitZS", yes});
+            c.jQuant = q;
+        }
     }
     if (const JSON* m = j0.find("model")) {  // Koifish JSON (cases/qwen3/*.json)
         if (const JSON* a = m->find("arch")) c.arch = a->as_string(c.arch);
@@ -425,6 +435,61 @@ int Fish::SetTensor(const std::string& name, const void* host, int rows, int col
     if (rc) error = "SetTensor(" + name + ") -> " + kf_status_string(rc) + " : " + kf_last_error(ctx);
     return rc;
 }
+// The window [out r0, r0 + OCl) x [in c0, c0 + ICl) of a full AWQ triple as ONE blob qweight || qzeros || scales (GTensor::AllocAWQ).  r0 and OCl
+// are multiples of 8 (whole int32 words), c0 and ICl of 128 (whole groups).  Pure host code (the tensor-parallel shard plan of SURVEY 8e applied
+// to the vendor layout); out_blob holds ICl * OCl / 2 + (ICl / 128) * (OCl / 8) * 4 + (ICl / 128) * OCl * 2 bytes.
+void AwqShardWindow(const void* qweight, const void* qzeros, const void* scales, int IC, int OC, int r0, int OCl, int c0, int ICl, uint8_t* out_blob) {
+    (void)IC;
+    const size_t W8g = (size_t)OC / 8, W8l = (size_t)OCl / 8, w0 = (size_t)r0 / 8, g0 = (size_t)c0 / 128;
+    uint32_t* qw = (uint32_t*)out_blob;
+    uint32_t* qz = qw + (size_t)ICl * W8l;
+    uint16_t* sc = (uint16_t*)(qz + (size_t)(ICl / 128) * W8l);
+    const uint32_t* fqw = (const uint32_t*)qweight;
+    const uint32_t* fqz = (const uint32_t*)qzeros;
+    const uint16_t* fsc = (const uint16_t*)scales;
+    for (int i = 0; i < ICl; i++) memcpy(qw + (size_t)i * W8l, fqw + (size_t)(c0 + i) * W8g + w0, W8l * 4);
+    for (int g = 0; g < ICl / 128; g++) {
+        memcpy(qz + (size_t)g * W8l, fqz + (g0 + g) * W8g + w0, W8l * 4);
+        memcpy(sc + (size_t)g * OCl, fsc + (g0 + g) * (size_t)OC + r0, (size_t)OCl * 2);
+    }
+}
+// Vendor AWQ tensors (GeQuant::ExTensor + GTensor::LoadParam of .qweight / .qzeros / .scales, reference src/Tensor/GeQuant.cpp:144-200,
+// src/Manifold/Serialize.cpp:145-230): the FULL (unsharded) arrays as the checkpoint stores them --
+//   qweight int32 [IC][OC / 8], qzeros int32 [IC / 128][OC / 8], scales fp16 [IC / 128][OC]     (IC = in_features, OC = out_features)
+// -- cut to this rank's window (Q/K/V/gate/up: a column range of every array; O/down: a row range, whole 128-row groups) and uploaded
+// as one blob.  No arithmetic touches the codes: the device reads the vendor layout as it is (awq.cu).
+int Fish::SetTensorAWQ(const std::string& name, const void* qweight, const void* qzeros, const void* scales, int IC, int OC) {
+    std::string* hFishErr = &error;
+    auto it = tensors.find(name);
+    if (it == tensors.end()) {
+        error = "unknown tensor '" + name + "'";
+        return KF_ERR_BAD_ARG;
+    }
+    hGTensor t = it->second;
+    if (!t->hQuant || t->hQuant->params.type != AWQ) {
+        error = "tensor '" + name + "': the checkpoint holds it in the vendor AWQ layout but the quantizer card does not say \"quant_method\": \"awq\" for it";
+        return KF_ERR_BAD_ARG;
+    }
+    int rg, cg, r0, c0;  // rows = OC, cols = IC
+    shard_window(*this, name, t->ne[0], t->ne[1], &rg, &cg, &r0, &c0);
+    if (OC != rg || IC != cg || !qweight || !qzeros || !scales) {
+        error = "tensor '" + name + "': expected AWQ arrays of the full shape in_features " + std::to_string(cg) + ", out_features " + std::to_string(rg);
+        return KF_ERR_BAD_ARG;
+    }
+    const int OCl = t->ne[0], ICl = t->ne[1];
+    int rc = t->AllocAWQ();
+    if (rc) {
+        error = "tensor '" + name + "': the AWQ layout needs in_features in whole 128-row groups and out_features a multiple of 32 per rank";
+        return rc;
+    }
+    std::vector<uint8_t> blob(t->nByte());
+    AwqShardWindow(qweight, qzeros, scales, IC, OC, r0, OCl, c0, ICl, blob.data());
+    KF_TRY(kf_h2d(ctx, t->data, blob.data(), blob.size()));
+    KF_TRY(kf_ctx_sync(ctx));
+    t->qBias = 0;
+    ResetGraphs();
+    return KF_OK;
+}
 hGTensor Fish::GetTensor(const std::string& name) const {
     auto it = tensors.find(name);
     return it == tensors.end() ? nullptr : it->second;
@@ -439,8 +504,9 @@ int Fish::ForwardOnRLS(int M, bool want_logits) {
     if (tp_world > 1) {
         KF_TRY(kf_tp_begin(ctx));
         tp_fuse = 2 * (int)attn.size() <= 256 && kf_exchange_fused_ready(ctx, M, config.n_embd) == 1;
-        for (size_t l = 0; l < attn.size() && tp_fuse; l++)  // NormalFloat4 weights have their own matmul (nf4.cu): stand-alone exchange
-            tp_fuse = attn[l]->proj_cat.w->type != typNUMBER::Q4_NF && ffn[l]->down.w->type != typNUMBER::Q4_NF;
+        auto own_matmul = [](const hGTensor& t) { return t->type == typNUMBER::Q4_NF || t->type == typNUMBER::Q4_AWQ; };
+        for (size_t l = 0; l < attn.size() && tp_fuse; l++)  // NormalFloat4 / AWQ weights have their own matmul (nf4.cu, awq.cu): stand-alone exchange
+            tp_fuse = !own_matmul(attn[l]->proj_cat.w) && !own_matmul(ffn[l]->down.w);
     }
     KF_TRY(embed.cuInfer(x, M));
     for (size_t l = 0; l < attn.size(); l++) {
@@ -505,6 +571,14 @@ int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, ui
             return KF_ERR_BAD_ARG;
         }
         h_stage[m] = tokens[m], h_stage[max_tokens + m] = pos[m];
+    }
+    if (!all_resident) {  // a model whose weights come tensor by tensor (SetTensor / SetTensorAWQ / a checkpoint) must have all of them
+        for (auto& kv : tensors)
+            if (!kv.second->data) {
+                error = "Forward: tensor '" + kv.first + "' has no data yet (init_random, set_tensor or a checkpoint must provide every tensor)";
+                return KF_ERR_BAD_ARG;
+            }
+        all_resident = true;
     }
     SyncGraphGeneration();
     staged_pos_max = *std::max_element(pos, pos + M);

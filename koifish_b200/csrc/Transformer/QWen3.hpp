@@ -44,6 +44,8 @@ struct Fish;
 bool ShardPlan(const MODEL_CARD& c, const std::string& name, int rank, int world, int* rows_g, int* cols_g, int* rows_l, int* cols_l, int* row0,
                int* col0);
 
+void AwqShardWindow(const void* qweight, const void* qzeros, const void* scales, int IC, int OC, int r0, int OCl, int c0, int ICl, uint8_t* out_blob);
+
 // ---- neurons --------------------------------------------------------------------------------------------------------------
 struct GeNeuron {
     std::string name;
@@ -154,6 +156,9 @@ struct Fish {
     int Build();                 // allocate tensors + buffers (Fish::MakeInstance -> Build, Fish.cpp:13-95)
     int InitParamRandom();       // huTensor::InitParam random path + quantise at load
     int SetTensor(const std::string& hf_name, const void* host_bf16, int rows, int cols);  // SERIALIZE path: full (unsharded) tensor
+    // vendor AWQ arrays of one linear (full shape), cut to this rank's window and kept in the vendor layout (GeQuant::ExTensor, GeQuant.cpp:144-200)
+    int SetTensorAWQ(const std::string& hf_name, const void* qweight_i32, const void* qzeros_i32, const void* scales_f16, int in_features, int out_features);
+    bool all_resident = false;  // every tensor has device data (checked once by Forward)
     hGTensor GetTensor(const std::string& hf_name) const;
     // one forward over M tokens already staged in d_tokens / d_pos (ForwardOnRLS, gLLM.cpp:755-769); logits for all M rows
     int ForwardOnRLS(int M, bool want_logits);

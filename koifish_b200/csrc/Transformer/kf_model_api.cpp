@@ -59,7 +59,9 @@ extern "C" int kf_model_info_get(kf_model* m, kf_model_info* o) {
     o->head_dim = c.head_dim, o->vocab = c.vocab, o->max_seq_len = c.max_seq_len, o->max_batch = c.max_batch, o->max_tokens = f.max_tokens;
     o->tp_rank = f.tp_rank, o->tp_world = f.tp_world, o->tie_word_embeddings = c.tie_word_embeddings;
     o->rope_theta = c.rope_theta, o->norm_rms_eps = c.norm_rms_eps;
-    o->weight_bytes = f.weight_bytes, o->kv_bytes = f.cache.bytes();
+    o->weight_bytes = 0, o->kv_bytes = f.cache.bytes();
+    for (auto& kv : f.tensors)  // what is resident now (random init, set tensor by tensor, or from a checkpoint)
+        if (kv.second->data) o->weight_bytes += kv.second->nByte();
     if (!f.attn.empty()) {
         auto nb = [](const hGTensor& t) { return t ? (uint64_t)t->nByte() : 0ull; };
         SelfAttention& a = *f.attn[0];
@@ -83,6 +85,16 @@ extern "C" int kf_model_set_tensor(kf_model* m, const char* name, const void* ho
     if (!m || !name || !host) return KF_ERR_BAD_ARG;
     try {
         return m->fish->SetTensor(name, host, rows, cols);
+    } catch (const std::exception& e) {
+        m->fish->error = e.what();
+        return KF_ERR_BAD_ARG;
+    }
+}
+extern "C" int kf_model_set_tensor_awq(kf_model* m, const char* name, const void* qweight, const void* qzeros, const void* scales, int in_features,
+                                       int out_features) {
+    if (!m || !name) return KF_ERR_BAD_ARG;
+    try {
+        return m->fish->SetTensorAWQ(name, qweight, qzeros, scales, in_features, out_features);
     } catch (const std::exception& e) {
         m->fish->error = e.what();
         return KF_ERR_BAD_ARG;
@@ -163,6 +175,31 @@ extern "C" int kf_config_quant_of(const char* config_json, const char* tensor_na
     } catch (const std::exception& e) {
         if (err_out) *err_out = dup_cstr(e.what());
         return KF_ERR_UNSUPPORTED;
+    }
+}
+// Host only: rank `rank` of `world`'s blob (qweight || qzeros || scales, what kf_model_set_tensor_awq uploads) of the AWQ linear `tensor_name`
+// given its FULL arrays -- the tensor-parallel plan of kf_config_shard_of applied to the vendor layout.  *bytes_out receives the blob size;
+// out_blob may be NULL to query it.
+extern "C" int kf_config_awq_shard(const char* config_json, const char* tensor_name, int rank, int world, const void* qweight, const void* qzeros,
+                                   const void* scales, void* out_blob, size_t capacity, size_t* bytes_out, char** err_out) {
+    if (err_out) *err_out = nullptr;
+    if (!config_json || !tensor_name || !bytes_out) return KF_ERR_BAD_ARG;
+    try {
+        MODEL_CARD c = MODEL_CARD::FromJSON(JSON::parse(config_json));
+        int sh[6];
+        if (!ShardPlan(c, tensor_name, rank, world, sh, sh + 1, sh + 2, sh + 3, sh + 4, sh + 5) || sh[2] % 32 || sh[3] % 128 || sh[4] % 8 || sh[5] % 128) {
+            if (err_out) *err_out = dup_cstr("unknown tensor name, or the tensor-parallel window is not in whole 32-column blocks / 128-row groups");
+            return KF_ERR_BAD_ARG;
+        }
+        const int OC = sh[0], IC = sh[1], OCl = sh[2], ICl = sh[3];
+        *bytes_out = (size_t)ICl * OCl / 2 + (size_t)(ICl / 128) * (OCl / 8) * 4 + (size_t)(ICl / 128) * OCl * 2;
+        if (!out_blob) return KF_OK;
+        if (!qweight || !qzeros || !scales || capacity < *bytes_out) return KF_ERR_BAD_ARG;
+        AwqShardWindow(qweight, qzeros, scales, IC, OC, sh[4], OCl, sh[5], ICl, (uint8_t*)out_blob);
+        return KF_OK;
+    } catch (const std::exception& e) {
+        if (err_out) *err_out = dup_cstr(e.what());
+        return KF_ERR_BAD_ARG;
     }
 }
 extern "C" int kf_config_shard_of(const char* config_json, const char* tensor_name, int rank, int world, int* shape_out /* rows_g, cols_g, rows_l,
@@ -253,8 +290,21 @@ extern "C" int kf_safetensors_read_bf16(const char* path, const char* name, void
 }
 // Every tensor of the file (or of every *.safetensors of the directory) whose name the model knows is set from it -- BF16 / F16 / F32
 // sources, rounded to bf16, sharded for this rank and quantised per the quantizer card exactly as kf_model_set_tensor does.  Names the
-// model does not have (rotary inv_freq, a tied lm_head.weight, biases ...) are skipped and counted.  Vendor-quantised tensors
-// (.qweight / .qzeros / .scales of an AWQ checkpoint) are refused: the runtime has no loader for them.
+// model does not have (rotary inv_freq, a tied lm_head.weight, biases ...) are skipped and counted.
+// Vendor-quantised linears (an AWQ checkpoint, e.g. Qwen3-32B-AWQ: <prefix>.qweight I32 [in][out / 8], <prefix>.qzeros I32 [in / 128][out / 8],
+// <prefix>.scales F16 [in / 128][out]; reference GeQuant::ExTensor GeQuant.cpp:144-200, src/Python/test_awq.py:33-71) become the model's
+// <prefix>.weight in the AWQ layout (kf_model_set_tensor_awq) once all three arrays have been seen -- they may sit in different shards;
+// a triple left incomplete at the end is an error.  Each complete triple counts as one loaded tensor.
+namespace {
+struct AwqPart {
+    std::vector<uint8_t> bytes;
+    std::vector<int64_t> shape;
+    bool seen = false;
+};
+struct AwqTriple {
+    AwqPart qweight, qzeros, scales;
+};
+}  // namespace
 extern "C" int kf_model_load_safetensors(kf_model* m, const char* path_or_dir, int* n_loaded_out, int* n_skipped_out) {
     if (!m || !path_or_dir) return KF_ERR_BAD_ARG;
     int loaded = 0, skipped = 0;
@@ -266,6 +316,7 @@ extern "C" int kf_model_load_safetensors(kf_model* m, const char* path_or_dir, i
         if (kf_st_list(path_or_dir, &files, &err) != 0) throw std::runtime_error(err);
         std::vector<uint8_t> raw;
         std::vector<uint16_t> bf;
+        std::map<std::string, AwqTriple> awq;  // by <prefix>
         for (const std::string& path : files) {
             KfStFile f;
             if (kf_st_parse(path, &f, &err) != 0) throw std::runtime_error(err);
@@ -274,8 +325,35 @@ extern "C" int kf_model_load_safetensors(kf_model* m, const char* path_or_dir, i
                     const size_t n = strlen(suf);
                     return e.name.size() > n && e.name.compare(e.name.size() - n, n, suf) == 0;
                 };
-                if (ends_with(".qweight") || ends_with(".qzeros") || ends_with(".scales"))
-                    throw std::runtime_error("'" + e.name + "': vendor-quantised (AWQ) checkpoints are not supported by the model runtime");
+                const int part = ends_with(".qweight") ? 0 : ends_with(".qzeros") ? 1 : ends_with(".scales") ? 2 : -1;
+                if (part >= 0) {
+                    const std::string prefix = e.name.substr(0, e.name.rfind('.'));
+                    const std::string wname  = prefix + ".weight";
+                    if (!m->fish->GetTensor(wname)) {
+                        skipped++;
+                        continue;
+                    }
+                    if (e.dtype != (part == 2 ? "F16" : "I32") || e.shape.size() != 2)
+                        throw std::runtime_error("'" + e.name + "': the AWQ layout stores qweight / qzeros as 2-D I32 and scales as 2-D F16, found " + e.dtype);
+                    AwqTriple& t = awq[prefix];
+                    AwqPart& p   = part == 0 ? t.qweight : part == 1 ? t.qzeros : t.scales;
+                    if (p.seen) throw std::runtime_error("'" + e.name + "' appears twice");
+                    p.bytes.resize(e.end - e.begin);
+                    if (kf_st_read(f, e, p.bytes.data(), &err) != 0) throw std::runtime_error(err);
+                    p.shape = e.shape, p.seen = true;
+                    if (t.qweight.seen && t.qzeros.seen && t.scales.seen) {
+                        const int64_t IC = t.qweight.shape[0], OC = t.scales.shape[1];
+                        if (IC <= 0 || OC <= 0 || IC > 0x7fffffff || OC > 0x7fffffff || IC % 128 || OC % 8 || t.qweight.shape[1] != OC / 8 ||
+                            t.qzeros.shape[0] != IC / 128 || t.qzeros.shape[1] != OC / 8 || t.scales.shape[0] != IC / 128)
+                            throw std::runtime_error("'" + prefix + "': qweight / qzeros / scales shapes are not [in][out/8], [in/128][out/8], [in/128][out] "
+                                                     "(4-bit codes, group_size 128)");
+                        const int rc = m->fish->SetTensorAWQ(wname, t.qweight.bytes.data(), t.qzeros.bytes.data(), t.scales.bytes.data(), (int)IC, (int)OC);
+                        if (rc) return rc;  // Fish::error is set
+                        awq.erase(prefix);
+                        loaded++;
+                    }
+                    continue;
+                }
                 if (!m->fish->GetTensor(e.name)) {
                     skipped++;
                     continue;
@@ -293,6 +371,8 @@ extern "C" int kf_model_load_safetensors(kf_model* m, const char* path_or_dir, i
                 loaded++;
             }
         }
+        if (!awq.empty())
+            throw std::runtime_error("'" + awq.begin()->first + "': incomplete AWQ tensor (needs .qweight, .qzeros and .scales)");
     } catch (const std::exception& e) {
         m->fish->error = std::string("load_safetensors: ") + e.what();
         return KF_ERR_BAD_ARG;

@@ -5,6 +5,7 @@ import json
 import os
 import re
 
+import numpy as np
 import pytest
 
 import koifish_b200 as kf
@@ -103,12 +104,75 @@ def test_bits_without_method_selects_normalfloat4():
 
 
 def test_out_of_scope_quant_methods_fail_loudly():
-    for q in ({"self_attn": {"quant_method": "awq", "bits": 4}},  # vendor AWQ: a 'next' row
+    for q in ({"self_attn": {"quant_method": "awq", "bits": 8}},  # the vendor AWQ layout is 4-bit / group 128 only
+              {"self_attn": {"quant_method": "awq", "bits": 4, "group_size": 64}},
               {"self_attn": {"quant_method": "bitnet"}},
               {"self_attn": {"quant_method": "RTN", "bits": 1}}):
         cfg = kf.qwen3_config(2, 1024, 3072, 16, 8, quantizer=q)
         st, *_, msg = _quant_of(cfg, "model.layers.0.self_attn.q_proj.weight")
         assert st == kf.KF_ERR_UNSUPPORTED and msg
+
+
+def test_vendor_awq_card_and_hf_quantization_config():
+    # {"quant_method": "awq"} selects typNUMBER::Q4 under QUANT_MODE::AWQ (Init4Neuron, GeQuant.cpp:1272-1273) = the library's KF_T_AWQ4
+    cfg = kf.qwen3_config(2, 1024, 3072, 16, 8, quantizer={"self_attn": {"quant_method": "awq", "bits": 4, "zero_point": True}})
+    st, t, g, m, qb, msg = _quant_of(cfg, "model.layers.0.self_attn.q_proj.weight")
+    assert (st, t, g, qb) == (0, kf.KF_T_AWQ4, 128, 0), msg
+    assert _quant_of(cfg, "model.layers.0.mlp.up_proj.weight")[1] == kf.KF_T_BF16
+    # an HF config.json of a vendor checkpoint (Qwen3-32B-AWQ): QUANT_CARD::Vendor2JSONx (CLI_params.cpp:240-262) spreads the vendor's block
+    # over every self_attn / mlp linear; embeddings, norms and the head stay bf16
+    hf = {"hidden_size": 1024, "intermediate_size": 3072, "num_hidden_layers": 2, "num_attention_heads": 16, "num_key_value_heads": 8,
+          "head_dim": 128, "vocab_size": 151936, "rope_theta": 1e6, "model_type": "qwen3",
+          "quantization_config": {"bits": 4, "group_size": 128, "modules_to_not_convert": None, "quant_method": "awq", "version": "gemm",
+                                  "zero_point": True}}
+    for name in ("model.layers.1.self_attn.o_proj.weight", "model.layers.0.mlp.down_proj.weight"):
+        st, t, g, *_, msg = _quant_of(hf, name)
+        assert (st, t, g) == (0, kf.KF_T_AWQ4, 128), msg
+    for name in ("model.embed_tokens.weight", "lm_head.weight", "model.norm.weight"):
+        assert _quant_of(hf, name)[:2] == (0, kf.KF_T_BF16)
+    # an explicit "quantizer" block next to the HF config wins over the vendor's
+    both = {"hf_config": hf, "quantizer": {"mlp": {"quant_method": "RTN", "bits": 4}}}
+    assert _quant_of(both, "model.layers.0.mlp.up_proj.weight")[1] == kf.KF_T_Q4
+    assert _quant_of(both, "model.layers.0.self_attn.q_proj.weight")[1] == kf.KF_T_BF16
+
+
+def test_awq_shard_windows_dequantise_to_the_windows_of_the_full_weight():
+    # the tensor-parallel plan on the vendor AWQ layout (what kf_model_set_tensor_awq uploads on each rank): Q/K/V/gate/up keep a column range of
+    # qweight / qzeros / scales, O / down a row range in whole 128-row groups.  Checked through the oracle's CU_Q42X_awq port: the window's arrays
+    # dequantise to the window of the full dequantised weight, for every rank, and world 1 is the identity.
+    import oracle_lib as ol
+    lib = kf.load()
+    hf = {"hidden_size": 512, "intermediate_size": 1024, "num_hidden_layers": 1, "num_attention_heads": 8, "num_key_value_heads": 4, "head_dim": 64,
+          "vocab_size": 1024, "quantization_config": {"bits": 4, "group_size": 128, "quant_method": "awq", "zero_point": True}}
+    text = json.dumps(hf).encode()
+    for name, OC, IC in (("model.layers.0.self_attn.q_proj.weight", 512, 512), ("model.layers.0.self_attn.k_proj.weight", 256, 512),
+                         ("model.layers.0.self_attn.o_proj.weight", 512, 512), ("model.layers.0.mlp.up_proj.weight", 1024, 512),
+                         ("model.layers.0.mlp.down_proj.weight", 512, 1024)):
+        w_io = ol.fill_normal(IC * OC, IC + OC + len(name), 0.05).reshape(IC, OC)
+        qw, qz, sc = ol.awq_pack(w_io, IC, OC)
+        full = ol.awq_dequant(qw, qz, sc, IC, OC)  # bf16 [in][out]
+        for world in (1, 2, 4):
+            for rank in range(world):
+                shape = (C.c_int * 6)()
+                assert lib.kf_config_shard_of(text, name.encode(), rank, world, shape, None) == 0
+                _, _, OCl, ICl, r0, c0 = list(shape)
+                n, err = C.c_size_t(0), C.c_void_p()
+                assert lib.kf_config_awq_shard(text, name.encode(), rank, world, None, None, None, None, 0, C.byref(n), C.byref(err)) == 0
+                assert n.value == ICl * OCl // 2 + (ICl // 128) * (OCl // 8) * 4 + (ICl // 128) * OCl * 2
+                blob = np.zeros(n.value, dtype=np.uint8)
+                assert lib.kf_config_awq_shard(text, name.encode(), rank, world, qw.ctypes.data, qz.ctypes.data, sc.ctypes.data, blob.ctypes.data,
+                                               blob.nbytes, C.byref(n), C.byref(err)) == 0
+                a, b = ICl * OCl // 2, ICl * OCl // 2 + (ICl // 128) * (OCl // 8) * 4
+                lqw, lqz, lsc = blob[:a].view(np.uint32), blob[a:b].view(np.uint32), blob[b:].view(np.uint16)
+                got = ol.awq_dequant(lqw, lqz, lsc, ICl, OCl)
+                assert np.array_equal(got, full[c0:c0 + ICl, r0:r0 + OCl]), (name, world, rank)
+                if world == 1:
+                    assert np.array_equal(lqw, qw) and np.array_equal(lqz, qz) and np.array_equal(lsc, sc)
+    # a window that would split a 128-row group or an int32 word is refused
+    n, err = C.c_size_t(0), C.c_void_p()
+    assert lib.kf_config_awq_shard(text, b"model.layers.0.self_attn.k_proj.weight", 0, 3, None, None, None, None, 0, C.byref(n), C.byref(err)) != 0
+    if err.value:
+        lib.kf_string_free(err)
 
 
 def _dims(text):

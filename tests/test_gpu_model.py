@@ -188,7 +188,7 @@ def test_forward_argument_errors(ctx):
         with pytest.raises(kf.KoifishError):
             model.forward(toks, pos, seq_mode=mode)
     with pytest.raises(kf.KoifishError):
-        kf.Model(ctx, kf.qwen3_config(2, 256, 512, 4, 2, 64, 1024, {"self_attn": {"quant_method": "awq", "bits": 4}}))  # vendor AWQ layout: not built
+        kf.Model(ctx, kf.qwen3_config(2, 256, 512, 4, 2, 64, 1024, {"self_attn": {"quant_method": "awq", "bits": 8}}))  # vendor AWQ layout: 4-bit only
     with pytest.raises(kf.KoifishError):
         model.set_tensor("model.layers.0.nope.weight", np.zeros((4, 4), dtype=np.uint16))
 
@@ -531,7 +531,104 @@ def test_load_safetensors_equals_set_tensor(ctx, tmp_path):
         la, _ = a.forward([tok], [pos])
         lb, _ = b.forward([tok], [pos])
         assert np.array_equal(la, lb)
-    # a vendor-quantised (AWQ) checkpoint is refused with a message
-    write_safetensors(tmp_path / "awq.safetensors", [("model.layers.0.mlp.up_proj.qweight", "I32", np.zeros((4, 4), dtype=np.int32))])
+    # vendor-quantised (AWQ) arrays for a tensor whose card does not say "awq" are refused with a message
+    triple = [("model.layers.0.mlp.up_proj.qweight", "I32", np.zeros((256, 64), dtype=np.int32)),
+              ("model.layers.0.mlp.up_proj.qzeros", "I32", np.zeros((2, 64), dtype=np.int32)),
+              ("model.layers.0.mlp.up_proj.scales", "F16", np.zeros((2, 512), dtype=np.float16))]
+    write_safetensors(tmp_path / "awq.safetensors", triple)
     with pytest.raises(kf.KoifishError):
         a.load_safetensors(tmp_path / "awq.safetensors")
+
+
+# ---------------------------------------------------------------------------------------------- vendor AWQ checkpoints
+AWQ_VENDOR_BLOCK = {"bits": 4, "group_size": 128, "modules_to_not_convert": None, "quant_method": "awq", "version": "gemm", "zero_point": True}
+
+
+def _awq_models(ctx, tmp_path, max_batch=1):
+    """an AWQ checkpoint on disk (two shards, the three arrays of a linear spread over both), the model that loads it, and a bf16 model
+    holding exactly the weights the reference's CU_Q42X_awq (oracle port, pinned to the reference kernel in test_gpu_kernels.py) reads
+    out of those arrays"""
+    from st_util import write_safetensors
+    dims = dict(n_layer=2, n_embd=256, n_ff=512, n_head=4, n_kv_head=2, head_dim=64, vocab=1024)
+    hf = {"hf_config": {"hidden_size": 256, "intermediate_size": 512, "num_hidden_layers": 2, "num_attention_heads": 4, "num_key_value_heads": 2,
+                        "head_dim": 64, "vocab_size": 1024, "rope_theta": 1e6, "tie_word_embeddings": False, "model_type": "qwen3",
+                        "quantization_config": AWQ_VENDOR_BLOCK},
+          "gpt": {"max_seq_len": 64, "max_batch": max_batch}}
+    a = kf.Model(ctx, hf)
+    b = kf.Model(ctx, kf.qwen3_config(2, 256, 512, 4, 2, 64, 1024, None, False, 64, max_batch, 42, 1e6))
+    b.init_random()
+    shards, want = [[], []], {}
+    for i, name in enumerate(b.tensor_names()):
+        d = b.tensor_desc(name)
+        rows, cols = d.rows, d.cols
+        if "self_attn" in name and "proj" in name or "mlp" in name:
+            w_oi = ol.fill_normal(rows * cols, 5000 + i, 0.05).reshape(rows, cols)  # [out][in]
+            qw, qz, sc = ol.awq_pack(np.ascontiguousarray(w_oi.T), cols, rows)
+            want[name] = np.ascontiguousarray(ol.awq_dequant(qw, qz, sc, cols, rows).T)  # bf16 [out][in]
+            b.set_tensor(name, want[name])
+            prefix = name[:-len(".weight")]
+            shards[i % 2].append((prefix + ".qweight", "I32", qw.view(np.int32).reshape(cols, rows // 8)))
+            shards[(i + 1) % 2].append((prefix + ".qzeros", "I32", qz.view(np.int32).reshape(cols // 128, rows // 8)))
+            shards[i % 2].append((prefix + ".scales", "F16", sc.view(np.float16).reshape(cols // 128, rows)))
+        else:
+            w = ol.fill_normal(rows * cols, 5000 + i, 0.05, 1.0 if "norm" in name else 0.0)
+            b.set_tensor(name, w.reshape(rows, cols))
+            shards[i % 2].append((name, "BF16", w.reshape(cols) if rows == 1 else w.reshape(rows, cols)))
+    d = tmp_path / "awq_ckpt"
+    d.mkdir()
+    write_safetensors(d / "model-00001-of-00002.safetensors", shards[0], metadata={"format": "pt"})
+    write_safetensors(d / "model-00002-of-00002.safetensors", shards[1])
+    return a, b, d, want
+
+
+def test_awq_checkpoint_loads_into_the_vendor_layout(ctx, tmp_path):
+    a, b, d, want = _awq_models(ctx, tmp_path)
+    with pytest.raises(kf.KoifishError):
+        a.forward([1], [0])  # no tensor has data yet: refused, not a crash
+    loaded, skipped = a.load_safetensors(d)
+    assert (loaded, skipped) == (len(b.tensor_names()), 0)
+    for name, w in want.items():
+        t = a.tensor_desc(name)
+        assert (t.type, t.rows, t.cols, t.group) == (kf.KF_T_AWQ4, w.shape[0], w.shape[1], 128), name
+        assert np.array_equal(a.dequant_tensor(name), w), name  # GetDataX of the resident tensor == CU_Q42X_awq of the checkpoint's arrays
+    assert a.tensor_desc("model.embed_tokens.weight").type == kf.KF_T_BF16
+    with pytest.raises(kf.KoifishError):
+        a.init_random()  # there is no AWQ quantiser (nor has the reference one)
+    with pytest.raises(kf.KoifishError):
+        a.set_tensor("model.layers.0.mlp.up_proj.weight", want["model.layers.0.mlp.up_proj.weight"])
+
+
+def test_awq_model_matches_the_bf16_model_of_the_dequantised_weights(ctx, tmp_path):
+    # same weights value for value, so the logits may differ only by accumulation order and the bf16 roundings it flips
+    a, b, d, _ = _awq_models(ctx, tmp_path)
+    a.load_safetensors(d)
+    toks = prompt(12, 1024)
+    for pos, tok in enumerate(toks[:6]):  # decode, one token at a time: the column-walking AWQ GEMV
+        la, na = a.forward([tok], [pos], want_next=True)
+        lb, nb = b.forward([tok], [pos], want_next=True)
+        err, g, w = logits_close(la[0], lb[0])
+        assert err <= 2e-2, (pos, err)
+        top2 = np.sort(w)[-2:]
+        if top2[1] - top2[0] > 2 * 2e-2 * np.abs(w).max():
+            assert int(na[0]) == int(nb[0])
+    # a 12-token prefill panel from position 0: dequantise + the tcgen05 GEMM
+    la, _ = a.forward(toks, list(range(12)))
+    lb, _ = b.forward(toks, list(range(12)))
+    for m in range(12):
+        err, _, _ = logits_close(la[m], lb[m])
+        assert err <= 2e-2, (m, err)
+
+
+def test_awq_model_blob_save_load_round_trip(ctx, tmp_path):
+    a, _, d, _ = _awq_models(ctx, tmp_path)
+    a.load_safetensors(d)
+    a.save(tmp_path / "awq.kfb")
+    c = kf.Model(ctx, {"hf_config": {"hidden_size": 256, "intermediate_size": 512, "num_hidden_layers": 2, "num_attention_heads": 4,
+                                     "num_key_value_heads": 2, "head_dim": 64, "vocab_size": 1024, "rope_theta": 1e6,
+                                     "tie_word_embeddings": False, "quantization_config": AWQ_VENDOR_BLOCK},
+                       "gpt": {"max_seq_len": 64, "max_batch": 1}})
+    c.load(tmp_path / "awq.kfb")
+    for pos, tok in enumerate(prompt(4, 1024)):
+        la, _ = a.forward([tok], [pos])
+        lc, _ = c.forward([tok], [pos])
+        assert np.array_equal(la, lc)
