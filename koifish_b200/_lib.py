@@ -127,6 +127,22 @@ SIGNATURES = {
     "kf_safetensors_index": (_I, [C.c_char_p, C.POINTER(_P), C.POINTER(_P)]),
     "kf_safetensors_read_bf16": (_I, [C.c_char_p, C.c_char_p, _P, _SZ, C.POINTER(_P)]),
     "kf_model_set_sampler": (_I, [_P, C.c_float, _I, C.c_float, _U64, _I]),
+    "kf_tokenizer_load": (_I, [C.c_char_p, C.POINTER(_P), C.POINTER(_P)]),
+    "kf_tokenizer_from_json": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_P), C.POINTER(_P)]),
+    "kf_tokenizer_destroy": (_I, [_P]),
+    "kf_tokenizer_encode": (_I, [_P, C.c_char_p, _SZ, _P, _SZ, C.POINTER(_SZ)]),
+    "kf_tokenizer_decode": (_I, [_P, _P, _SZ, _I, C.POINTER(_P)]),
+    "kf_tokenizer_token_to_id": (_I, [_P, C.c_char_p]),
+    "kf_tokenizer_id_to_token": (_I, [_P, _I, C.POINTER(_P)]),
+    "kf_tokenizer_vocab_size": (_I, [_P]),
+    "kf_tokenizer_eos_id": (_I, [_P]),
+    "kf_tokenizer_bos_id": (_I, [_P]),
+    "kf_tokenizer_pad_id": (_I, [_P]),
+    "kf_tokenizer_is_special": (_I, [_P, _I]),
+    "kf_text_nfc": (_I, [C.c_char_p, _SZ, C.POINTER(_P)]),
+    "kf_tokenizer_pre_tokenize": (_I, [_P, C.c_char_p, _SZ, C.POINTER(_P)]),
+    "kf_chatml_prompt": (_I, [C.c_char_p, C.c_char_p, _I, C.POINTER(_P)]),
+    "kf_chatml_render": (_I, [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _I, _I, C.POINTER(_P)]),
     "kf_config_dims": (_I, [C.c_char_p, C.POINTER(ModelInfo), C.POINTER(_P)]),
     "kf_config_quant_of": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_P)]),
     "kf_config_awq_shard": (_I, [C.c_char_p, C.c_char_p, _I, _I, _P, _P, _P, _P, _SZ, C.POINTER(_SZ), C.POINTER(_P)]),

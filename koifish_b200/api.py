@@ -542,3 +542,115 @@ QWEN3_DIMS = {  # SURVEY.md section 8 table (HF Qwen3 configs)
     "8B": dict(n_layer=36, n_embd=4096, n_ff=12288, n_head=32, n_kv_head=8, tie=False),
     "32B": dict(n_layer=64, n_embd=5120, n_ff=25600, n_head=64, n_kv_head=8, tie=False),
 }
+
+
+# ---------------------------------------------------------------------------------------------- text side of the chat loop (host only)
+def _take_string(lib, p):
+    s = C.cast(p, C.c_char_p).value
+    lib.kf_string_free(p)
+    return s.decode("utf-8", errors="surrogateescape")
+
+
+class Tokenizer:
+    """include/kf_tokenizer.h: HF tokenizer.json of the Qwen family (reference src/TokenSet/HF_Tokenizer.cpp).  Host only."""
+
+    def __init__(self, path=None, json_text=None, config_text=None):
+        self.lib = L.load()
+        h, err = C.c_void_p(), C.c_void_p()
+        if path is not None:
+            st = self.lib.kf_tokenizer_load(str(path).encode(), C.byref(h), C.byref(err))
+        else:
+            st = self.lib.kf_tokenizer_from_json(json_text.encode(), config_text.encode() if config_text else None, C.byref(h), C.byref(err))
+        if st != L.KF_OK:
+            raise KoifishError(st, "kf_tokenizer_load", _take_string(self.lib, err) if err.value else "")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kf_tokenizer_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def encode(self, text):
+        raw = text if isinstance(text, bytes) else text.encode("utf-8")
+        n = C.c_size_t(0)
+        st = self.lib.kf_tokenizer_encode(self.h, raw, len(raw), None, 0, C.byref(n))
+        if st != L.KF_OK:
+            raise KoifishError(st, "kf_tokenizer_encode", "text is not valid UTF-8")
+        ids = np.zeros(max(1, n.value), dtype=np.int32)
+        st = self.lib.kf_tokenizer_encode(self.h, raw, len(raw), ids.ctypes.data, ids.size, C.byref(n))
+        if st != L.KF_OK:
+            raise KoifishError(st, "kf_tokenizer_encode")
+        return [int(x) for x in ids[:n.value]]
+
+    def decode(self, ids, skip_special_tokens=False):
+        a = np.ascontiguousarray(ids, dtype=np.int32).reshape(-1)
+        out = C.c_void_p()
+        st = self.lib.kf_tokenizer_decode(self.h, a.ctypes.data if a.size else None, a.size, int(skip_special_tokens), C.byref(out))
+        if st != L.KF_OK:
+            raise KoifishError(st, "kf_tokenizer_decode")
+        return _take_string(self.lib, out)
+
+    def pre_tokenize(self, text):
+        raw = text.encode("utf-8")
+        out = C.c_void_p()
+        st = self.lib.kf_tokenizer_pre_tokenize(self.h, raw, len(raw), C.byref(out))
+        if st != L.KF_OK:
+            raise KoifishError(st, "kf_tokenizer_pre_tokenize")
+        return json.loads(_take_string(self.lib, out))
+
+    def token_to_id(self, token):
+        return self.lib.kf_tokenizer_token_to_id(self.h, token.encode("utf-8"))
+
+    def id_to_token(self, i):
+        out = C.c_void_p()
+        st = self.lib.kf_tokenizer_id_to_token(self.h, int(i), C.byref(out))
+        if st != L.KF_OK:
+            raise KoifishError(st, "kf_tokenizer_id_to_token")
+        return _take_string(self.lib, out)
+
+    vocab_size = property(lambda self: self.lib.kf_tokenizer_vocab_size(self.h))
+    eos_id = property(lambda self: self.lib.kf_tokenizer_eos_id(self.h))
+    bos_id = property(lambda self: self.lib.kf_tokenizer_bos_id(self.h))
+    pad_id = property(lambda self: self.lib.kf_tokenizer_pad_id(self.h))
+
+    def is_special(self, i):
+        return bool(self.lib.kf_tokenizer_is_special(self.h, int(i)))
+
+
+def nfc(text):
+    lib = L.load()
+    raw = text.encode("utf-8")
+    out = C.c_void_p()
+    st = lib.kf_text_nfc(raw, len(raw), C.byref(out))
+    if st != L.KF_OK:
+        raise KoifishError(st, "kf_text_nfc")
+    return _take_string(lib, out)
+
+
+def chatml_prompt(user, system=None, enable_thinking=False):
+    """CHAT_SAMPLER::InitPrefillTemplate (reference src/Utils/CLI_params.cpp:1990-2008)"""
+    lib = L.load()
+    out = C.c_void_p()
+    st = lib.kf_chatml_prompt(system.encode("utf-8") if system else None, user.encode("utf-8"), int(enable_thinking), C.byref(out))
+    if st != L.KF_OK:
+        raise KoifishError(st, "kf_chatml_prompt")
+    return _take_string(lib, out)
+
+
+def chatml_render(lines, enable_thinking=False):
+    """CHAT_SAMPLER::toChatML (reference src/Utils/CLI_params.cpp:2010-2031); lines: [(role, content), ...]"""
+    lib = L.load()
+    n = len(lines)
+    roles = (C.c_char_p * max(1, n))(*[r.encode("utf-8") for r, _ in lines])
+    texts = (C.c_char_p * max(1, n))(*[c.encode("utf-8") for _, c in lines])
+    out = C.c_void_p()
+    st = lib.kf_chatml_render(roles, texts, n, int(enable_thinking), C.byref(out))
+    if st != L.KF_OK:
+        raise KoifishError(st, "kf_chatml_render")
+    return _take_string(lib, out)

@@ -2,7 +2,7 @@
 
     python -m koifish_b200.build [--force] [--verbose]
 
-Sources: csrc/Device/*.cu (kernels + C ABI), csrc/Tensor/*.cpp, csrc/Transformer/*.cpp (host runtime).
+Sources: csrc/Device/*.cu (kernels + C ABI), csrc/Tensor/*.cpp, csrc/Transformer/*.cpp (host runtime), csrc/TokenSet/*.cpp (tokenizer, host only).
 """
 import glob
 import hashlib
@@ -30,7 +30,8 @@ HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 def _sources():
     cu = sorted(glob.glob(os.path.join(CSRC, "Device", "*.cu")))
-    cpp = sorted(glob.glob(os.path.join(CSRC, "Tensor", "*.cpp")) + glob.glob(os.path.join(CSRC, "Transformer", "*.cpp")))
+    cpp = sorted(glob.glob(os.path.join(CSRC, "Tensor", "*.cpp")) + glob.glob(os.path.join(CSRC, "Transformer", "*.cpp")) +
+                 glob.glob(os.path.join(CSRC, "TokenSet", "*.cpp")))
     return cu, cpp
 
 

@@ -168,14 +168,34 @@ class JSON {
                     case 'b': out += '\b'; break;
                     case 'f': out += '\f'; break;
                     case 'u': {
-                        unsigned cp = 0;
-                        for (int i = 0; i < 4 && p < s.size(); i++) cp = cp * 16 + (unsigned)std::strtol(std::string(1, s[p++]).c_str(), nullptr, 16);
+                        auto hex4 = [&](size_t at, unsigned* v) {
+                            if (at + 4 > s.size()) return false;
+                            unsigned x = 0;
+                            for (int i = 0; i < 4; i++) {
+                                const char h = s[at + i];
+                                if (!std::isxdigit((unsigned char)h)) return false;
+                                x = x * 16 + (unsigned)(std::isdigit((unsigned char)h) ? h - '0' : (std::tolower((unsigned char)h) - 'a' + 10));
+                            }
+                            *v = x;
+                            return true;
+                        };
+                        unsigned cp = 0, lo = 0;
+                        if (!hex4(p, &cp)) throw std::runtime_error("json: bad \\u escape at offset " + std::to_string(p));
+                        p += 4;
+                        // a UTF-16 surrogate pair written as two escapes is one code point
+                        if (cp >= 0xD800 && cp <= 0xDBFF && p + 6 <= s.size() && s[p] == '\\' && s[p + 1] == 'u' && hex4(p + 2, &lo) && lo >= 0xDC00 && lo <= 0xDFFF) {
+                            cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+                            p += 6;
+                        }
                         if (cp < 0x80)
                             out += (char)cp;
                         else if (cp < 0x800)
                             out += (char)(0xC0 | (cp >> 6)), out += (char)(0x80 | (cp & 0x3F));
-                        else
+                        else if (cp < 0x10000)
                             out += (char)(0xE0 | (cp >> 12)), out += (char)(0x80 | ((cp >> 6) & 0x3F)), out += (char)(0x80 | (cp & 0x3F));
+                        else
+                            out += (char)(0xF0 | (cp >> 18)), out += (char)(0x80 | ((cp >> 12) & 0x3F)), out += (char)(0x80 | ((cp >> 6) & 0x3F)),
+                                out += (char)(0x80 | (cp & 0x3F));
                         break;
                     }
                     default: out += e;

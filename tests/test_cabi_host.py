@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     names = set()
-    for h in ("kf_device.h", "kf_model.h"):
+    for h in ("kf_device.h", "kf_model.h", "kf_tokenizer.h"):
         text = open(os.path.join(ROOT, "include", h)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names |= set(re.findall(r"\b(kf_[a-z0-9_]+)\s*\(", text))
@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_headers_compile_as_plain_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "kf_device.h"\n#include "kf_model.h"\nint main(void){ kf_tensor_desc d; (void)d; return KF_OK; }\n')
+    src.write_text('#include "kf_device.h"\n#include "kf_model.h"\n#include "kf_tokenizer.h"\nint main(void){ kf_tensor_desc d; (void)d; return KF_OK; }\n')
     import subprocess
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")])
