@@ -71,6 +71,13 @@ int kf_model_forward(kf_model* m, const int32_t* tokens_host, const int32_t* pos
 /* n_steps greedy decode steps entirely on the device (each step a CUDA-graph replay feeding its argmax back as the next token),
  * continuing from the tokens/positions of the last kf_model_forward.  Asynchronous; kf_ctx_sync() to wait. */
 int kf_model_decode_loop(kf_model* m, int n_steps, int M);
+/* The generation loop of Fish::Chat (reference src/Manifold/GoPT.cpp:1111-1235): the prompt (int32[n_prompt], host) is prefilled at positions
+ * pos0 .. pos0 + n_prompt - 1 (pos0 > 0 continues a conversation whose earlier turns are in the KV cache), then tokens are drawn with the
+ * model's sampler (kf_model_set_sampler; greedy by default) and fed back until one equals eos_id (not emitted; pass -1 for none),
+ * max_new_tokens have been produced, or the context window (gpt.max_seq_len) is full.  out_ids holds max_new_tokens ids; *n_out receives the
+ * count; *stop_reason_out (optional): 1 eos, 2 max_new_tokens, 3 context window full.  Synchronous. */
+int kf_model_generate(kf_model* m, const int32_t* prompt_ids, int n_prompt, int pos0, int max_new_tokens, int eos_id, int32_t* out_ids, int* n_out,
+                      int* stop_reason_out);
 /* current device-side tokens / positions (after a decode loop) */
 int kf_model_read_state(kf_model* m, int32_t* tokens_host, int32_t* pos_host, int M);
 int kf_model_set_graphs(kf_model* m, int enable);

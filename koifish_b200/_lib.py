@@ -122,6 +122,7 @@ SIGNATURES = {
     "kf_model_read_state": (_I, [_P, _P, _P, _I]),
     "kf_model_save": (_I, [_P, C.c_char_p]),
     "kf_model_load": (_I, [_P, C.c_char_p]),
+    "kf_model_generate": (_I, [_P, _P, _I, _I, _I, _I, _P, C.POINTER(_I), C.POINTER(_I)]),
     "kf_model_set_graphs": (_I, [_P, _I]),
     "kf_model_load_safetensors": (_I, [_P, C.c_char_p, C.POINTER(_I), C.POINTER(_I)]),
     "kf_safetensors_index": (_I, [C.c_char_p, C.POINTER(_P), C.POINTER(_P)]),

@@ -476,6 +476,15 @@ class Model:
         self._check(self.lib.kf_model_read_state(self.h, t.ctypes.data, p.ctypes.data, M), "kf_model_read_state")
         return t, p
 
+    def generate(self, prompt_ids, max_new_tokens, eos_id=-1, pos0=0):
+        """Fish::Chat's generation loop -> (generated ids, stop reason: 1 eos / 2 max_new_tokens / 3 context window full)"""
+        p = np.ascontiguousarray(prompt_ids, dtype=np.int32).reshape(-1)
+        out = np.zeros(max(1, max_new_tokens), dtype=np.int32)
+        n, why = C.c_int(0), C.c_int(0)
+        self._check(self.lib.kf_model_generate(self.h, p.ctypes.data, p.size, int(pos0), int(max_new_tokens), int(eos_id), out.ctypes.data, C.byref(n),
+                                               C.byref(why)), "kf_model_generate")
+        return [int(x) for x in out[:n.value]], why.value
+
     def save(self, path):
         self._check(self.lib.kf_model_save(self.h, str(path).encode()), "kf_model_save")
 
@@ -654,3 +663,10 @@ def chatml_render(lines, enable_thinking=False):
     if st != L.KF_OK:
         raise KoifishError(st, "kf_chatml_render")
     return _take_string(lib, out)
+
+
+def chat_once(model, tokenizer, user, system=None, max_new_tokens=256, enable_thinking=False, pos0=0):
+    """one turn of Fish::Chat: ChatML prompt -> token ids -> kf_model_generate (stops at the tokenizer's eos) -> text"""
+    ids = tokenizer.encode(chatml_prompt(user, system, enable_thinking))
+    out, why = model.generate(ids, max_new_tokens, tokenizer.eos_id, pos0)
+    return tokenizer.decode(out, skip_special_tokens=True), out, why

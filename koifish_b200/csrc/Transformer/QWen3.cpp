@@ -633,6 +633,59 @@ int Fish::Forward(const int32_t* tokens, const int32_t* pos, int M, int mode, ui
     return KF_OK;
 }
 
+// The generation loop of Fish::Chat (reference src/Manifold/GoPT.cpp:1111-1235): prefill the prompt, then sample -> stop on eos or a full
+// context window -> feed the token back.  The reference prefills token by token (one Evaluate per prompt token, :1140-1147); here the prompt
+// goes through in panels of up to max_tokens (seq_mode 2: only the last token's logits are formed) and every generated token is one
+// Forward() with a 4-byte result.  The token that equals eos_id is not emitted, as the reference does not print it (:1171).
+int Fish::Generate(const int32_t* prompt, int n_prompt, int pos0, int max_new, int eos_id, int32_t* out, int* n_out, int* stop_reason) {
+    if (n_out) *n_out = 0;
+    if (stop_reason) *stop_reason = 0;
+    if (!prompt || n_prompt < 1 || pos0 < 0 || max_new < 0 || (max_new > 0 && !out) || !n_out) {
+        error = "Generate: needs a prompt of at least one token, pos0 >= 0, max_new_tokens >= 0 and an output buffer";
+        return KF_ERR_BAD_ARG;
+    }
+    if ((long long)pos0 + n_prompt > config.max_seq_len) {
+        error = "Generate: the prompt does not fit the context window (gpt.max_seq_len = " + std::to_string(config.max_seq_len) + ")";
+        return KF_ERR_BAD_ARG;
+    }
+    std::vector<int32_t> posv((size_t)max_tokens);
+    int32_t next = -1;
+    for (int off = 0; off < n_prompt; off += max_tokens) {
+        const int m = std::min(max_tokens, n_prompt - off);
+        for (int i = 0; i < m; i++) posv[i] = pos0 + off + i;
+        const bool last = off + m == n_prompt;
+        const int rc    = Forward(prompt + off, posv.data(), m, 2, nullptr, last ? &next : nullptr);
+        if (rc) return rc;
+    }
+    int32_t pos = pos0 + n_prompt;  // where the next token will sit
+    int n       = 0;
+    for (;;) {
+        if (next == eos_id) {
+            if (stop_reason) *stop_reason = 1;
+            break;
+        }
+        if (n >= max_new) {
+            if (stop_reason) *stop_reason = 2;
+            break;
+        }
+        out[n++] = next;
+        if (n >= max_new) {
+            if (stop_reason) *stop_reason = 2;
+            break;
+        }
+        if (pos >= config.max_seq_len) {  // "context window full!" (GoPT.cpp:1175)
+            if (stop_reason) *stop_reason = 3;
+            break;
+        }
+        int32_t fed = next;
+        const int rc = Forward(&fed, &pos, 1, 0, nullptr, &next);
+        if (rc) return rc;
+        pos++;
+    }
+    *n_out = n;
+    return KF_OK;
+}
+
 // Device-resident greedy decoding: each step = one CUDA-graph replay of [forward, argmax, token feedback, pos++].  The tokens and
 // positions staged by the last Forward() call are the starting state.
 int Fish::DecodeLoop(int n_steps, int M) {

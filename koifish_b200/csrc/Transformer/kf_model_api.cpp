@@ -230,6 +230,16 @@ extern "C" int kf_model_set_sampler(kf_model* m, float temperature, int top_k, f
     if (!m) return KF_ERR_BAD_ARG;
     return m->fish->SetSampler(temperature, top_k, top_p, seed, selection);
 }
+extern "C" int kf_model_generate(kf_model* m, const int32_t* prompt_ids, int n_prompt, int pos0, int max_new_tokens, int eos_id, int32_t* out_ids, int* n_out,
+                                 int* stop_reason_out) {
+    if (!m) return KF_ERR_BAD_ARG;
+    try {
+        return m->fish->Generate(prompt_ids, n_prompt, pos0, max_new_tokens, eos_id, out_ids, n_out, stop_reason_out);
+    } catch (const std::exception& e) {
+        m->fish->error = e.what();
+        return KF_ERR_BAD_ARG;
+    }
+}
 extern "C" int kf_model_set_graphs(kf_model* m, int enable) {
     if (!m) return KF_ERR_BAD_ARG;
     m->fish->use_graphs = enable != 0;
