@@ -100,6 +100,22 @@ int kf_safetensors_index(const char* path, char** json_out, char** err_out);
 int kf_safetensors_read_bf16(const char* path, const char* name, void* out_bf16_host, size_t capacity_elems, char** err_out);
 int kf_model_save(kf_model* m, const char* path);
 int kf_model_load(kf_model* m, const char* path);
+/* The reference's own container, "fish.kun" (CKP_KOIFISH): a safetensors file whose header entries are {"dtype": K_FLOATS name ("Q<4>",
+ * "TERNARY", "BINARY", "F8E5M2", "BF16(E8)" ...; src/g_float.hpp:127-151), "shape", "data_offsets", "loAB", "szGama", "szData"} (GTensor::jDesc,
+ * src/Manifold/Serialize.cpp:61-100), whose payloads are the device blobs data || gama (GTensor::SerialGamaData, src/Device/CUDA/huTensor.cu:
+ * 413-458) and whose "__koifish__config__" entry is the writer's JSON config as msgpack (K_SafeTensors::insertJS, src/Tensor/Safetensors.hpp:
+ * 87-102).  kf_model_save_kun writes every resident tensor that way (AWQ tensors are refused: they have a checkpoint format of their own);
+ * kf_model_load_kun reads such a file -- this library's or the reference's -- into a model built from a matching config (dtype, shape, szData
+ * and szGama are checked against what the config selects; unknown names are skipped and counted; training-state files, whose payloads carry
+ * optimizer moments, are refused).  Loading skips the quantiser, like the reference's Serial_Quant_MMAP when the stored type is the card's. */
+int kf_model_save_kun(kf_model* m, const char* path);
+int kf_model_load_kun(kf_model* m, const char* path, int* n_loaded_out, int* n_skipped_out);
+/* host only: the header of a .kun file as JSON text [{"name","dtype","shape","szData","szGama","offset"}, ...]; its config entry decoded from
+ * msgpack to JSON text ("" when absent); and a writer from host blobs (shapes: n x 2, second 0 for a vector; blobs[i] = szData + szGama bytes) */
+int kf_kun_index(const char* path, char** json_out, char** err_out);
+int kf_kun_config(const char* path, char** json_out, char** err_out);
+int kf_kun_write(const char* path, const char* config_json, int n, const char* const* names, const char* const* dtypes, const int64_t* shapes,
+                 const uint64_t* sz_data, const uint64_t* sz_gama, const void* const* blobs, char** err_out);
 
 /* Host-only config logic (no device needed): parse a config and report the model dimensions, and which storage type the
  * quantizer block selects for a tensor name (QUANT_CARD::Init4Neuron, reference src/Tensor/GeQuant.cpp:1186-1285; MakeInstance

@@ -123,6 +123,12 @@ SIGNATURES = {
     "kf_model_save": (_I, [_P, C.c_char_p]),
     "kf_model_load": (_I, [_P, C.c_char_p]),
     "kf_model_generate": (_I, [_P, _P, _I, _I, _I, _I, _P, C.POINTER(_I), C.POINTER(_I)]),
+    "kf_model_save_kun": (_I, [_P, C.c_char_p]),
+    "kf_model_load_kun": (_I, [_P, C.c_char_p, C.POINTER(_I), C.POINTER(_I)]),
+    "kf_kun_index": (_I, [C.c_char_p, C.POINTER(_P), C.POINTER(_P)]),
+    "kf_kun_config": (_I, [C.c_char_p, C.POINTER(_P), C.POINTER(_P)]),
+    "kf_kun_write": (_I, [C.c_char_p, C.c_char_p, _I, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(_U64), C.POINTER(_U64),
+                          C.POINTER(_P), C.POINTER(_P)]),
     "kf_model_set_graphs": (_I, [_P, _I]),
     "kf_model_load_safetensors": (_I, [_P, C.c_char_p, C.POINTER(_I), C.POINTER(_I)]),
     "kf_safetensors_index": (_I, [C.c_char_p, C.POINTER(_P), C.POINTER(_P)]),

@@ -491,6 +491,15 @@ class Model:
     def load(self, path):
         self._check(self.lib.kf_model_load(self.h, str(path).encode()), "kf_model_load")
 
+    def save_kun(self, path):
+        """the reference's own container (fish.kun)"""
+        self._check(self.lib.kf_model_save_kun(self.h, str(path).encode()), "kf_model_save_kun")
+
+    def load_kun(self, path):
+        a, b = C.c_int(0), C.c_int(0)
+        self._check(self.lib.kf_model_load_kun(self.h, str(path).encode(), C.byref(a), C.byref(b)), "kf_model_load_kun")
+        return a.value, b.value
+
     def load_safetensors(self, path_or_dir):
         """HF model.safetensors (or a directory of shards) -> (tensors loaded, tensors skipped)"""
         a, b = C.c_int(0), C.c_int(0)
@@ -670,3 +679,41 @@ def chat_once(model, tokenizer, user, system=None, max_new_tokens=256, enable_th
     ids = tokenizer.encode(chatml_prompt(user, system, enable_thinking))
     out, why = model.generate(ids, max_new_tokens, tokenizer.eos_id, pos0)
     return tokenizer.decode(out, skip_special_tokens=True), out, why
+
+
+def _host_json_call(fn_name, path):
+    lib = L.load()
+    out, err = C.c_void_p(), C.c_void_p()
+    st = getattr(lib, fn_name)(str(path).encode(), C.byref(out), C.byref(err))
+    if st != L.KF_OK:
+        raise KoifishError(st, fn_name, _take_string(lib, err) if err.value else "")
+    return _take_string(lib, out)
+
+
+def kun_index(path):
+    """header of a fish.kun file (host only): [{"name", "dtype", "shape", "szData", "szGama", "offset"}, ...]"""
+    return json.loads(_host_json_call("kf_kun_index", path))
+
+
+def kun_config(path):
+    """the msgpack "__koifish__config__" entry of a fish.kun file as a dict (None when absent)"""
+    text = _host_json_call("kf_kun_config", path)
+    return json.loads(text) if text else None
+
+
+def kun_write(path, config, tensors):
+    """write a fish.kun from host arrays (host only).  tensors: [(name, K_FLOATS dtype name, shape tuple, szData, szGama, bytes-like blob)]"""
+    lib = L.load()
+    n = len(tensors)
+    names = (C.c_char_p * max(1, n))(*[t[0].encode() for t in tensors])
+    dtypes = (C.c_char_p * max(1, n))(*[t[1].encode() for t in tensors])
+    shapes = (C.c_int64 * max(2, 2 * n))(*[d for t in tensors for d in (t[2][0], t[2][1] if len(t[2]) > 1 else 0)])
+    szd = (C.c_uint64 * max(1, n))(*[t[3] for t in tensors])
+    szg = (C.c_uint64 * max(1, n))(*[t[4] for t in tensors])
+    keep = [np.frombuffer(bytes(t[5]), dtype=np.uint8) for t in tensors]
+    blobs = (C.c_void_p * max(1, n))(*[k.ctypes.data for k in keep])
+    err = C.c_void_p()
+    cfg = json.dumps(config).encode() if config is not None else None
+    st = lib.kf_kun_write(str(path).encode(), cfg, n, names, dtypes, shapes, szd, szg, blobs, C.byref(err))
+    if st != L.KF_OK:
+        raise KoifishError(st, "kf_kun_write", _take_string(lib, err) if err.value else "")

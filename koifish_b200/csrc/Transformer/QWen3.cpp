@@ -1,6 +1,8 @@
 // QWen3.cpp -- Qwen3 decode / prefill on top of the device C ABI (see QWen3.hpp for the reference interfaces mirrored here).
 #include "QWen3.hpp"
 
+#include "../Tensor/KunFile.hpp"
+
 #include <algorithm>
 #include <cstring>
 #include <stdexcept>
@@ -838,6 +840,117 @@ int Fish::LoadBlobs(const std::string& path) {
         }
     }
     fclose(f);
+    ResetGraphs();
+    return KF_OK;
+}
+
+// ---- the reference's own container, fish.kun (CKP_KOIFISH; csrc/Tensor/KunFile.cpp has the format): every resident tensor as
+// {"dtype": K_FLOATS name, "shape", "data_offsets", "loAB", "szGama", "szData"} + payload data || gama, and the model config as the msgpack
+// "__koifish__config__" entry.  What Fish::SAFETENSOR_Serialize writes / SAFETENSOR2Gensors + GTensor::LoadParam + Serial_Quant_MMAP read
+// (reference src/Manifold/Serialize.cpp:145-230, 770-1010; src/Device/CUDA/huTensor.cu:487-588) for the inference tensors.
+static const char* kunDtype(typNUMBER t) {  // K_FLOATS, src/g_float.hpp:127-151
+    switch (t) {
+        case typNUMBER::BF16: return "BF16(E8)";
+        case typNUMBER::F8E5M2: return "F8E5M2";
+        case typNUMBER::Q4:
+        case typNUMBER::Q4_NF: return "Q<4>";  // NormalFloat4 is typNUMBER::Q4 under QUANT_MODE::RTNf: the quant card tells them apart
+        case typNUMBER::Q2: return "Q<2>";
+        case typNUMBER::T_SIGN: return "TERNARY";
+        case typNUMBER::T_BINARY: return "BINARY";
+        case typNUMBER::Q4_AWQ: return nullptr;
+    }
+    return nullptr;
+}
+int Fish::SaveKun(const std::string& path, const std::string& config_json) {
+    std::vector<std::vector<uint8_t>> host(tensors.size());
+    std::vector<KunTensorOut> outs;
+    size_t i = 0;
+    for (auto& kv : tensors) {
+        const hGTensor& t = kv.second;
+        const char* dt    = kunDtype(t->type);
+        if (!t->data || !dt) {
+            error = !t->data ? "SaveKun: tensor '" + kv.first + "' has no data"
+                             : "SaveKun: '" + kv.first + "' is in the vendor AWQ layout -- it already has a checkpoint format of its own (.qweight / .qzeros / .scales)";
+            return KF_ERR_BAD_ARG;
+        }
+        host[i].resize(t->nByte());
+        int rc = kf_d2h(ctx, host[i].data(), t->data, t->nByte());
+        if (!rc) rc = kf_ctx_sync(ctx);
+        if (rc) {
+            error = std::string("SaveKun: ") + kf_last_error(ctx);
+            return rc;
+        }
+        KunTensorOut o;
+        o.name = kv.first, o.dtype = dt;
+        if (t->ne[0] == 1)
+            o.shape[0] = t->ne[1], o.shape[1] = 0;  // norm weights are vectors
+        else
+            o.shape[0] = t->ne[0], o.shape[1] = t->ne[1];
+        o.szData = t->szData, o.szGama = t->szGama, o.blob = host[i].data();
+        outs.push_back(o);
+        i++;
+    }
+    std::string err;
+    if (kun_write(path, config_json, outs, &err) != 0) {
+        error = "SaveKun('" + path + "'): " + err;
+        return KF_ERR_BAD_ARG;
+    }
+    return KF_OK;
+}
+int Fish::LoadKun(const std::string& path, int* n_loaded, int* n_skipped) {
+    KunFile file;
+    std::string err;
+    if (kun_parse(path, &file, &err) != 0) {
+        error = "LoadKun: " + err;
+        return KF_ERR_BAD_ARG;
+    }
+    auto fail = [&](const std::string& why) {
+        error = "LoadKun('" + path + "'): " + why;
+        return KF_ERR_BAD_ARG;
+    };
+    int loaded = 0, skipped = 0;
+    std::vector<uint8_t> host;
+    for (const KunEntry& e : file.entries) {
+        auto it = tensors.find(e.name);
+        if (it == tensors.end()) {  // the reference treats an unknown key as an error (Serialize.cpp:800-804); a tied "model.out.weight" or
+            skipped++;              // rotary tables of another writer are harmless here, so they are counted instead
+            continue;
+        }
+        const hGTensor& t   = it->second;
+        const bool quantised = t->hQuant && t->ne[0] > 1;
+        const typNUMBER want = quantised ? t->hQuant->params.tpQuant() : typNUMBER::BF16;
+        const char* dt       = kunDtype(want);
+        // accept the HF spelling for plain tensors ("BF16"), otherwise the K_FLOATS name this model's config selects for the tensor
+        if (!dt || !(e.dtype == dt || (want == typNUMBER::BF16 && e.dtype == "BF16")))
+            return fail("tensor '" + e.name + "' is stored as " + e.dtype + ", this config selects " + (dt ? dt : "the AWQ layout"));
+        uint64_t numel = 1;
+        for (int64_t d : e.shape) numel *= (uint64_t)d;
+        const bool shape_ok = t->ne[0] == 1 ? numel == t->size()
+                                            : (e.shape.size() == 2 && e.shape[0] == t->ne[0] && e.shape[1] == t->ne[1]);
+        if (!shape_ok) return fail("tensor '" + e.name + "' has another shape than the model built from this config (tensor-parallel ranks use one file per rank)");
+        if (!t->data || t->type != want) {
+            const int rc = t->Alloc(want, quantised ? t->hQuant->params.T_group : 0);
+            if (rc) {
+                error = std::string("LoadKun: ") + kf_last_error(ctx);
+                return rc;
+            }
+        }
+        if (e.szData != t->szData || e.szGama != t->szGama)
+            return fail("tensor '" + e.name + "': szData / szGama (" + std::to_string(e.szData) + " / " + std::to_string(e.szGama) + ") differ from this config's (" +
+                        std::to_string(t->szData) + " / " + std::to_string(t->szGama) + "): another group size?");
+        host.resize(t->nByte());
+        if (kun_read(file, e, host.data(), &err) != 0) return fail(err);
+        t->qBias = quantised ? t->hQuant->qBias : 0;
+        int rc = kf_h2d(ctx, t->data, host.data(), host.size());
+        if (!rc) rc = kf_ctx_sync(ctx);
+        if (rc) {
+            error = std::string("LoadKun: ") + kf_last_error(ctx);
+            return rc;
+        }
+        loaded++;
+    }
+    if (n_loaded) *n_loaded = loaded;
+    if (n_skipped) *n_skipped = skipped;
     ResetGraphs();
     return KF_OK;
 }

@@ -167,6 +167,9 @@ struct Fish {
     // the resident tensors exactly as they sit in HBM (data || gama per tensor): SerialGamaData, reference huTensor.cu:413-458
     int SaveBlobs(const std::string& path);
     int LoadBlobs(const std::string& path);
+    // the reference's own container (fish.kun, CKP_KOIFISH): the same payloads behind a safetensors header with szData / szGama per tensor
+    int SaveKun(const std::string& path, const std::string& config_json);
+    int LoadKun(const std::string& path, int* n_loaded, int* n_skipped);
     // Fish::Chat's generation loop (GoPT.cpp:1111-1235): prefill, then sample / stop on eos or a full window / feed back.  stop_reason: 1 eos,
     // 2 max_new tokens produced, 3 context window full
     int Generate(const int32_t* prompt, int n_prompt, int pos0, int max_new, int eos_id, int32_t* out, int* n_out, int* stop_reason);

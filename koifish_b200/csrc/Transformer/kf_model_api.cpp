@@ -3,6 +3,7 @@
 #include <cstring>
 #include <stdexcept>
 
+#include "../Tensor/KunFile.hpp"
 #include "../Tensor/Safetensors.hpp"
 #include "QWen3.hpp"
 #include "kf_model.h"
@@ -12,6 +13,7 @@ using namespace koifish;
 struct kf_model {
     std::unique_ptr<Fish> fish;
     std::vector<std::string> names;
+    std::string config_text;  // the JSON the model was created from (written into fish.kun files)
 };
 
 static char* dup_cstr(const std::string& s) {
@@ -35,6 +37,7 @@ extern "C" int kf_model_create(kf_ctx* ctx, const char* config_json, int tp_rank
             return rc;
         }
         for (auto& kv : m->fish->tensors) m->names.push_back(kv.first);
+        m->config_text = json_dump(j);
         *out = m.release();
         return KF_OK;
     } catch (const std::exception& e) {
@@ -180,6 +183,88 @@ extern "C" int kf_config_quant_of(const char* config_json, const char* tensor_na
 // Host only: rank `rank` of `world`'s blob (qweight || qzeros || scales, what kf_model_set_tensor_awq uploads) of the AWQ linear `tensor_name`
 // given its FULL arrays -- the tensor-parallel plan of kf_config_shard_of applied to the vendor layout.  *bytes_out receives the blob size;
 // out_blob may be NULL to query it.
+// ---- fish.kun, the reference's own container (csrc/Tensor/KunFile.cpp) --------------------------------------------------------------
+extern "C" int kf_model_save_kun(kf_model* m, const char* path) {
+    if (!m || !path) return KF_ERR_BAD_ARG;
+    try {
+        // jsConfig of Fish::SAFETENSOR_Serialize (Serialize.cpp:912-922): {"vendor", "CLI_params": {"config": ...}, "tokenizer": {"tokens": ""}}
+        const std::string cfg = "{\"vendor\":\"koifish_b200\",\"CLI_params\":{\"config\":" + m->config_text + "},\"tokenizer\":{\"tokens\":\"\"}}";
+        return m->fish->SaveKun(path, cfg);
+    } catch (const std::exception& e) {
+        m->fish->error = std::string("save_kun: ") + e.what();
+        return KF_ERR_BAD_ARG;
+    }
+}
+extern "C" int kf_model_load_kun(kf_model* m, const char* path, int* n_loaded_out, int* n_skipped_out) {
+    if (!m || !path) return KF_ERR_BAD_ARG;
+    if (n_loaded_out) *n_loaded_out = 0;
+    if (n_skipped_out) *n_skipped_out = 0;
+    try {
+        return m->fish->LoadKun(path, n_loaded_out, n_skipped_out);
+    } catch (const std::exception& e) {
+        m->fish->error = std::string("load_kun: ") + e.what();
+        return KF_ERR_BAD_ARG;
+    }
+}
+// host only: the header of a .kun file as JSON text [{"name","dtype","shape","szData","szGama","offset"}, ...] in file order
+extern "C" int kf_kun_index(const char* path, char** json_out, char** err_out) {
+    if (err_out) *err_out = nullptr;
+    if (!path || !json_out) return KF_ERR_BAD_ARG;
+    *json_out = nullptr;
+    KunFile f;
+    std::string err;
+    if (kun_parse(path, &f, &err) != 0) {
+        if (err_out) *err_out = dup_cstr(err);
+        return KF_ERR_BAD_ARG;
+    }
+    std::string j = "[";
+    for (size_t i = 0; i < f.entries.size(); i++) {
+        const KunEntry& e = f.entries[i];
+        JSON name;
+        name.kind = JSON::String, name.str = e.name;
+        JSON dt;
+        dt.kind = JSON::String, dt.str = e.dtype;
+        j += (i ? ",{\"name\":" : "{\"name\":") + json_dump(name) + ",\"dtype\":" + json_dump(dt) + ",\"shape\":[";
+        for (size_t d = 0; d < e.shape.size(); d++) j += (d ? "," : "") + std::to_string(e.shape[d]);
+        j += "],\"szData\":" + std::to_string(e.szData) + ",\"szGama\":" + std::to_string(e.szGama) + ",\"offset\":" + std::to_string(e.begin) + "}";
+    }
+    j += "]";
+    *json_out = dup_cstr(j);
+    return KF_OK;
+}
+// host only: the "__koifish__config__" entry (msgpack) as JSON text; "" when the file has none
+extern "C" int kf_kun_config(const char* path, char** json_out, char** err_out) {
+    if (err_out) *err_out = nullptr;
+    if (!path || !json_out) return KF_ERR_BAD_ARG;
+    *json_out = nullptr;
+    KunFile f;
+    std::string err, text;
+    if (kun_parse(path, &f, &err) != 0 || kun_config_json(f, &text, &err) != 0) {
+        if (err_out) *err_out = dup_cstr(err);
+        return KF_ERR_BAD_ARG;
+    }
+    *json_out = dup_cstr(text);
+    return KF_OK;
+}
+// host only: write a .kun from host blobs (what kf_model_save_kun does after copying every tensor off the device).  shapes: n x 2 (second 0 = vector)
+extern "C" int kf_kun_write(const char* path, const char* config_json, int n, const char* const* names, const char* const* dtypes, const int64_t* shapes,
+                            const uint64_t* sz_data, const uint64_t* sz_gama, const void* const* blobs, char** err_out) {
+    if (err_out) *err_out = nullptr;
+    if (!path || n < 0 || (n && (!names || !dtypes || !shapes || !sz_data || !sz_gama || !blobs))) return KF_ERR_BAD_ARG;
+    std::vector<KunTensorOut> outs((size_t)n);
+    for (int i = 0; i < n; i++) {
+        if (!names[i] || !dtypes[i]) return KF_ERR_BAD_ARG;
+        outs[i].name = names[i], outs[i].dtype = dtypes[i];
+        outs[i].shape[0] = shapes[2 * i], outs[i].shape[1] = shapes[2 * i + 1];
+        outs[i].szData = sz_data[i], outs[i].szGama = sz_gama[i], outs[i].blob = blobs[i];
+    }
+    std::string err;
+    if (kun_write(path, config_json ? config_json : "", outs, &err) != 0) {
+        if (err_out) *err_out = dup_cstr(err);
+        return KF_ERR_BAD_ARG;
+    }
+    return KF_OK;
+}
 extern "C" int kf_config_awq_shard(const char* config_json, const char* tensor_name, int rank, int world, const void* qweight, const void* qzeros,
                                    const void* scales, void* out_blob, size_t capacity, size_t* bytes_out, char** err_out) {
     if (err_out) *err_out = nullptr;

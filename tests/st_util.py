@@ -23,3 +23,21 @@ def write_safetensors(path, tensors, metadata=None):
         f.write(text)
         for b in blobs:
             f.write(b)
+
+
+def write_kun_reference_style(path, tensors, config, moments=1):
+    """tensors: [(name, dtype name, shape, szData, szGama, blob bytes)]; the config entry registered after the tensors, as insertJS does"""
+    header, off, blobs = {"__metadata__": {"format": "pt", "writer": "koifish"}}, 0, []
+    for name, dt, shape, szd, szg, blob in tensors:
+        payload = bytes(blob) * moments
+        header[name] = {"dtype": dt, "shape": list(shape), "data_offsets": [off, off + len(payload)], "loAB": 0, "szGama": szg, "szData": szd}
+        off += len(payload)
+        blobs.append(payload)
+    if config is not None:
+        import msgpack
+        mp = msgpack.packb(config, use_bin_type=True)
+        header["__koifish__config__"] = {"dtype": "U8", "shape": [len(mp)], "data_offsets": [off, off + len(mp)], "loAB": 0, "szGama": 0, "szData": 0}
+        blobs.append(mp)
+    text = json.dumps(header).encode()
+    with open(path, "wb") as f:
+        f.write(len(text).to_bytes(8, "little") + text + b"".join(blobs))
