@@ -441,3 +441,32 @@ def test_awq_port_nibble_order_and_arithmetic():
     back = ol.bf16_to_f32(ol.awq_dequant(pw, pz, ps, M, N)).reshape(M, N)
     step = np.repeat(ps.view(np.float16).astype(np.float32).reshape(M // 128, N), 128, axis=0)
     assert np.all(np.abs(back - ol.bf16_to_f32(w).reshape(M, N)) <= 0.51 * step + 1e-4)
+
+
+def test_awq_port_against_the_reference_python_unpack():
+    # tests/golden/awq_ref_py.npz: the reference's OWN unpack_awq / reverse_awq_order / Dequant_1 (src/Python/test_awq.py:33-134) run on seeded
+    # arrays (tests/golden/make_awq_golden.py).  Case c has unit scales, so the weights ARE the code differences q - z: bit-exact, which pins the
+    # nibble order of both qweight and qzeros.  Cases a / b have real scales: the Python path multiplies in fp16 and then rounds to bf16, the CUDA
+    # kernel this port follows (CU_Q42X_awq, quantizer.cu:132-156) multiplies in fp32 -- equal except where the fp16 product is inexact, and then by
+    # one bf16 ulp at most.
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "awq_ref_py.npz"))
+    for tag in "abc":
+        qw, qz, sc = g[tag + "_qweight"].view(np.uint32), g[tag + "_qzeros"].view(np.uint32), g[tag + "_scales"]
+        IC, OC = qw.shape[0], sc.shape[1]
+        got = ol.awq_dequant(qw.reshape(-1), qz.reshape(-1), sc.reshape(-1), IC, OC)
+        want = g[tag + "_deq_bf16"]
+        if tag == "c":
+            assert np.array_equal(got, want)
+            codes = g["c_codes"].astype(np.int32) - np.repeat(g["c_zeros"].astype(np.int32), 128, axis=0)
+            assert np.array_equal(ol.bf16_to_f32(got), codes.astype(np.float32))
+            continue
+        gf, wf = ol.bf16_to_f32(got), ol.bf16_to_f32(want)
+        differ = gf != wf
+        assert differ.mean() < 0.10, differ.mean()
+        ulp = np.abs(wf) * 2.0 ** -7
+        assert np.all(np.abs(gf - wf)[differ] <= ulp[differ] * 1.001)
+        # recomputing the Python arithmetic from the golden codes gives the golden values exactly: the difference above is the rounding, not the layout
+        q = g[tag + "_codes"].astype(np.float16) - np.repeat(g[tag + "_zeros"].astype(np.float16), 128, axis=0)
+        prod16 = (q * np.repeat(sc.view(np.float16), 128, axis=0)).astype(np.float16)
+        assert np.array_equal(ol.f32_to_bf16(prod16.astype(np.float32)).reshape(IC, OC), want)
