@@ -145,8 +145,10 @@ kf_tensor_desc GTensor::Desc() const {
     d.zero_dev = nullptr, d.step_dev = nullptr;
     if (type == typNUMBER::Q4_AWQ) {  // include/kf_device.h KF_T_AWQ4: data_dev = qweight, zero_dev = qzeros, step_dev = scales
         d.gama_dev = nullptr, d.group = 128;
-        d.zero_dev = (const uint8_t*)data + szData;
-        d.step_dev = (const uint8_t*)data + szData + awqZeroBytes();
+        if (data) {
+            d.zero_dev = (const uint8_t*)data + szData;
+            d.step_dev = (const uint8_t*)data + szData + awqZeroBytes();
+        }
     }
     return d;
 }
