@@ -224,6 +224,7 @@ Fish::~Fish() {
     if (h_logits) kf_host_free(h_logits);
 }
 void Fish::ResetGraphs() {
+    weights_dirty = true;  // every path that changes a resident tensor ends here: kf_model_info_get recounts the resident bytes once
     for (auto& g : graphs)
         if (g.second) kf_graph_destroy(g.second);
     graphs.clear();

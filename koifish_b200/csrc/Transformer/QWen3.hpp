@@ -150,6 +150,7 @@ struct Fish {
     void SyncGraphGeneration();  // drop the graphs when a context scratch buffer they point to has been re-allocated since
     std::string error;
     size_t weight_bytes = 0;
+    bool weights_dirty  = true;  // weight_bytes must be recounted (set by ResetGraphs, which every tensor-changing path calls)
 
     Fish(kf_ctx* ctx, const MODEL_CARD& card, int tp_rank, int tp_world);
     ~Fish();

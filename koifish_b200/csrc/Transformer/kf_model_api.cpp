@@ -62,9 +62,13 @@ extern "C" int kf_model_info_get(kf_model* m, kf_model_info* o) {
     o->head_dim = c.head_dim, o->vocab = c.vocab, o->max_seq_len = c.max_seq_len, o->max_batch = c.max_batch, o->max_tokens = f.max_tokens;
     o->tp_rank = f.tp_rank, o->tp_world = f.tp_world, o->tie_word_embeddings = c.tie_word_embeddings;
     o->rope_theta = c.rope_theta, o->norm_rms_eps = c.norm_rms_eps;
-    o->weight_bytes = 0, o->kv_bytes = f.cache.bytes();
-    for (auto& kv : f.tensors)  // what is resident now (random init, set tensor by tensor, or from a checkpoint)
-        if (kv.second->data) o->weight_bytes += kv.second->nByte();
+    if (f.weights_dirty) {  // what is resident now (random init, set tensor by tensor, or from a checkpoint)
+        f.weight_bytes = 0;
+        for (auto& kv : f.tensors)
+            if (kv.second->data) f.weight_bytes += kv.second->nByte();
+        f.weights_dirty = false;
+    }
+    o->weight_bytes = f.weight_bytes, o->kv_bytes = f.cache.bytes();
     if (!f.attn.empty()) {
         auto nb = [](const hGTensor& t) { return t ? (uint64_t)t->nByte() : 0ull; };
         SelfAttention& a = *f.attn[0];
