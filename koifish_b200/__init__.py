@@ -6,4 +6,4 @@ from ._lib import (KF_EPI_F32, KF_EPI_NONE, KF_EPI_RESIDUAL, KF_ERR_BAD_ARG, KF_
                    TYPE_BITS, KoifishError, load)
 from .api import (QWEN3_DIMS, AwqTensor, Context, DevArray, Model, ModelInfo, QTensor, TensorDesc, add, argmax, sample, linear_axb, attn_decode, attn_decode_gqa, attn_prefill, dequant, embed,  # noqa: F401
                   fill_normal, fill_normal_2d, linear, linear_multi, linear_swiglu, qknorm_rope_kvappend, qkv_attention, quantize, qwen3_config,
-                  rmsnorm, rmsnorm_linear, rope_table, safetensors_index, safetensors_read_bf16, swiglu, Tokenizer, nfc, chatml_prompt, chatml_render, chat_once, kun_index, kun_config, kun_write)
+                  rmsnorm, rmsnorm_linear, rope_table, safetensors_index, safetensors_read_bf16, swiglu, Tokenizer, nfc, chatml_prompt, chatml_render, chat_once, from_pretrained, kun_index, kun_config, kun_write)

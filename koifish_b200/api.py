@@ -717,3 +717,21 @@ def kun_write(path, config, tensors):
     st = lib.kf_kun_write(str(path).encode(), cfg, n, names, dtypes, shapes, szd, szg, blobs, C.byref(err))
     if st != L.KF_OK:
         raise KoifishError(st, "kf_kun_write", _take_string(lib, err) if err.value else "")
+
+
+def from_pretrained(ctx, model_dir, quantizer=None, max_seq_len=1024, max_batch=1, tp_rank=0, tp_world=1):
+    """the reference's `--hf <dir>` path (MODEL_CARD::InitHugFace, src/Utils/CLI_params.cpp:2224-2300 + Fish::LoadFolderOfST): an HF checkpoint
+    directory (config.json, *.safetensors, tokenizer.json) -> (Model with every tensor loaded, Tokenizer).  `quantizer`: a Koifish "quantizer"
+    block to quantise a bf16 checkpoint at load; a vendor-quantised (AWQ) checkpoint brings its own through config.json's quantization_config."""
+    import os
+    with open(os.path.join(str(model_dir), "config.json")) as f:
+        hf = json.load(f)
+    cfg = {"hf_config": hf, "gpt": {"max_seq_len": int(max_seq_len), "max_batch": int(max_batch)}}
+    if quantizer:
+        cfg["quantizer"] = quantizer
+    model = Model(ctx, cfg, tp_rank, tp_world)
+    loaded, _ = model.load_safetensors(model_dir)
+    missing = len(model.tensor_names()) - loaded
+    if missing:
+        raise KoifishError(L.KF_ERR_BAD_ARG, "from_pretrained", "%d of the model's tensors are not in '%s'" % (missing, model_dir))
+    return model, Tokenizer(model_dir)
