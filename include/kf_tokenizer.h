@@ -27,6 +27,15 @@ int kf_tokenizer_destroy(kf_tokenizer* t);
 int kf_tokenizer_encode(const kf_tokenizer* t, const char* text, size_t text_bytes, int32_t* ids_out, size_t capacity, size_t* n_out);
 /* HF_Tokenizer::decode(ids, skip_special_tokens) */
 int kf_tokenizer_decode(const kf_tokenizer* t, const int32_t* ids, size_t n, int skip_special_tokens, char** text_out);
+/* Piece-by-piece printing (Fish::Chat prints tokenizer->T2STR(token) per step, GoPT.cpp:1203-1230): byte-level BPE splits rare characters and
+ * emoji over several tokens, so T2STR of each alone prints U+FFFD pieces.  push returns the text that is certain after one more token and holds
+ * back an unfinished multi-byte character; flush returns what is left (end of the answer).  The concatenation of every push and the flush equals
+ * kf_tokenizer_decode of the whole sequence.  Returned strings are NUL-terminated (a decoded U+0000 ends them). */
+typedef struct kf_decode_stream kf_decode_stream;
+int kf_decode_stream_create(kf_decode_stream** out);
+int kf_decode_stream_destroy(kf_decode_stream* s);
+int kf_decode_stream_push(const kf_tokenizer* t, kf_decode_stream* s, int id, int skip_special_tokens, char** text_out);
+int kf_decode_stream_flush(kf_decode_stream* s, char** text_out);
 int kf_tokenizer_token_to_id(const kf_tokenizer* t, const char* token); /* -1 when absent */
 int kf_tokenizer_id_to_token(const kf_tokenizer* t, int id, char** token_out);
 int kf_tokenizer_vocab_size(const kf_tokenizer* t); /* largest id + 1, added tokens included */

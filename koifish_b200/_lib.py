@@ -139,6 +139,10 @@ SIGNATURES = {
     "kf_tokenizer_destroy": (_I, [_P]),
     "kf_tokenizer_encode": (_I, [_P, C.c_char_p, _SZ, _P, _SZ, C.POINTER(_SZ)]),
     "kf_tokenizer_decode": (_I, [_P, _P, _SZ, _I, C.POINTER(_P)]),
+    "kf_decode_stream_create": (_I, [C.POINTER(_P)]),
+    "kf_decode_stream_destroy": (_I, [_P]),
+    "kf_decode_stream_push": (_I, [_P, _P, _I, _I, C.POINTER(_P)]),
+    "kf_decode_stream_flush": (_I, [_P, C.POINTER(_P)]),
     "kf_tokenizer_token_to_id": (_I, [_P, C.c_char_p]),
     "kf_tokenizer_id_to_token": (_I, [_P, _I, C.POINTER(_P)]),
     "kf_tokenizer_vocab_size": (_I, [_P]),

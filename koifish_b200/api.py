@@ -614,6 +614,23 @@ class Tokenizer:
             raise KoifishError(st, "kf_tokenizer_decode")
         return _take_string(self.lib, out)
 
+    def stream(self, ids, skip_special_tokens=False):
+        """generator of text pieces, one per id (possibly empty), then the flushed rest: whole characters only"""
+        h = C.c_void_p()
+        self.lib.kf_decode_stream_create(C.byref(h))
+        try:
+            for i in ids:
+                out = C.c_void_p()
+                st = self.lib.kf_decode_stream_push(self.h, h, int(i), int(skip_special_tokens), C.byref(out))
+                if st != L.KF_OK:
+                    raise KoifishError(st, "kf_decode_stream_push")
+                yield _take_string(self.lib, out)
+            out = C.c_void_p()
+            self.lib.kf_decode_stream_flush(h, C.byref(out))
+            yield _take_string(self.lib, out)
+        finally:
+            self.lib.kf_decode_stream_destroy(h)
+
     def pre_tokenize(self, text):
         raw = text.encode("utf-8")
         out = C.c_void_p()

@@ -62,8 +62,9 @@ void utf8_append(std::string* s, uint32_t cp) {
     else
         *s += (char)(0xF0 | (cp >> 18)), *s += (char)(0x80 | ((cp >> 12) & 0x3F)), *s += (char)(0x80 | ((cp >> 6) & 0x3F)), *s += (char)(0x80 | (cp & 0x3F));
 }
-// String::from_utf8_lossy: every maximal ill-formed prefix becomes one U+FFFD
-std::string utf8_lossy(const std::string& s) {
+// String::from_utf8_lossy: every maximal ill-formed prefix becomes one U+FFFD.  hold_tail: a sequence that is well-formed so far but cut by the
+// end of the buffer is left alone (*consumed stops in front of it) -- the streaming decoder waits for the bytes of the next token.
+std::string utf8_lossy_prefix(const std::string& s, bool hold_tail, size_t* consumed) {
     std::string out;
     const unsigned char* p = (const unsigned char*)s.data();
     const size_t n         = s.size();
@@ -87,19 +88,26 @@ std::string utf8_lossy(const std::string& s) {
             continue;
         }
         size_t k = 1;
+        bool cut = false;
         for (; k < (size_t)len; k++) {
-            if (i + k >= n) break;
+            if (i + k >= n) {
+                cut = true;
+                break;
+            }
             const unsigned b = p[i + k];
             if (k == 1 ? (b < lo || b > hi) : ((b & 0xC0) != 0x80)) break;
         }
+        if (cut && hold_tail) break;
         if (k == (size_t)len)
             out.append(s, i, len);
         else
             out += "\xEF\xBF\xBD";
         i += k;
     }
+    if (consumed) *consumed = i;
     return out;
 }
+std::string utf8_lossy(const std::string& s) { return utf8_lossy_prefix(s, false, nullptr); }
 
 // ------------------------------------------------------------------------------------------------ Unicode properties
 bool in_ranges(const uint32_t (*r)[2], int n, uint32_t cp) {
@@ -462,27 +470,43 @@ std::vector<int> HF_Tokenizer::encode(const std::string& text) const {
 }
 
 // ------------------------------------------------------------------------------------------------ decode
-std::string HF_Tokenizer::decode(const std::vector<int>& ids, bool skip_special) const {
-    const ByteChars& bc = byte_chars();
-    std::string bytes;
+std::string HF_Tokenizer::token_bytes(int id, bool skip_special) const {
+    if (id < 0 || id >= (int)id2tok_.size()) return std::string();
+    if (skip_special && special_[id]) return std::string();
+    const ByteChars& bc    = byte_chars();
+    const std::string& tok = id2tok_[id];
+    // a token whose characters are all byte-level characters is those bytes; anything else stands for itself
     std::vector<uint32_t> cps;
-    for (int id : ids) {
-        if (id < 0 || id >= (int)id2tok_.size()) continue;
-        if (skip_special && special_[id]) continue;
-        const std::string& tok = id2tok_[id];
-        // a token whose characters are all byte-level characters is those bytes; anything else stands for itself
-        bool ok = utf8_decode(tok, &cps);
-        std::string b;
-        for (size_t i = 0; ok && i < cps.size(); i++) {
-            auto it = bc.back.find(cps[i]);
-            if (it == bc.back.end())
-                ok = false;
-            else
-                b += (char)it->second;
-        }
-        bytes += ok ? b : tok;
+    bool ok = utf8_decode(tok, &cps);
+    std::string b;
+    for (size_t i = 0; ok && i < cps.size(); i++) {
+        auto it = bc.back.find(cps[i]);
+        if (it == bc.back.end())
+            ok = false;
+        else
+            b += (char)it->second;
     }
+    return ok ? b : tok;
+}
+std::string HF_Tokenizer::decode(const std::vector<int>& ids, bool skip_special) const {
+    std::string bytes;
+    for (int id : ids) bytes += token_bytes(id, skip_special);
     return utf8_lossy(bytes);
+}
+// Streaming: the text that is certain after one more token.  A multi-byte character split over several tokens (byte-level BPE does that to rare
+// characters and emoji) comes out whole with the token that completes it instead of as U+FFFD pieces; the concatenation of every push and the
+// final flush equals decode() of the whole sequence.
+std::string HF_Tokenizer::stream_push(std::string* pending, int id, bool skip_special) const {
+    *pending += token_bytes(id, skip_special);
+    size_t used = 0;
+    std::string out = utf8_lossy_prefix(*pending, true, &used);
+    pending->erase(0, used);
+    return out;
+}
+std::string HF_Tokenizer::stream_flush(std::string* pending) {
+    std::string out = utf8_lossy(*pending);
+    pending->clear();
+    return out;
 }
 int HF_Tokenizer::token_to_id(const std::string& token) const {
     auto it = tok2id_.find(token);

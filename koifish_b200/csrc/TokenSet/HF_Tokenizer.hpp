@@ -36,6 +36,10 @@ class HF_Tokenizer {
     std::vector<int> encode(const std::string& text) const;
     std::string decode(const std::vector<int>& ids, bool skip_special_tokens) const;
     std::string T2STR(int id) const { return decode({id}, false); }  // the printable piece of one token (Fish::Chat prints these)
+    // piece-by-piece printing without broken characters: push returns the text that is certain after this token, flush what is left
+    std::string stream_push(std::string* pending, int id, bool skip_special_tokens) const;
+    static std::string stream_flush(std::string* pending);
+    std::string token_bytes(int id, bool skip_special_tokens) const;  // the raw bytes a token stands for
     int token_to_id(const std::string& token) const;                 // -1 when absent
     std::string id_to_token(int id) const;                           // "" when absent
     int vocab_size() const { return (int)id2tok_.size(); }           // largest id + 1 (model vocab + added tokens)

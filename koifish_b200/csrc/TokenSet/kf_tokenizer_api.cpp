@@ -80,6 +80,28 @@ extern "C" int kf_tokenizer_decode(const kf_tokenizer* t, const int32_t* ids, si
         return KF_ERR_BAD_ARG;
     }
 }
+struct kf_decode_stream {
+    std::string pending;
+};
+extern "C" int kf_decode_stream_create(kf_decode_stream** out) {
+    if (!out) return KF_ERR_BAD_ARG;
+    *out = new kf_decode_stream();
+    return KF_OK;
+}
+extern "C" int kf_decode_stream_destroy(kf_decode_stream* s) {
+    delete s;
+    return KF_OK;
+}
+extern "C" int kf_decode_stream_push(const kf_tokenizer* t, kf_decode_stream* s, int id, int skip_special, char** text_out) {
+    if (!t || !s || !text_out) return KF_ERR_BAD_ARG;
+    *text_out = dup_str(t->tk->stream_push(&s->pending, id, skip_special != 0));
+    return *text_out ? KF_OK : KF_ERR_OOM;
+}
+extern "C" int kf_decode_stream_flush(kf_decode_stream* s, char** text_out) {
+    if (!s || !text_out) return KF_ERR_BAD_ARG;
+    *text_out = dup_str(HF_Tokenizer::stream_flush(&s->pending));
+    return *text_out ? KF_OK : KF_ERR_OOM;
+}
 extern "C" int kf_tokenizer_token_to_id(const kf_tokenizer* t, const char* token) { return t && token ? t->tk->token_to_id(token) : -1; }
 extern "C" int kf_tokenizer_id_to_token(const kf_tokenizer* t, int id, char** out) {
     if (!t || !out) return KF_ERR_BAD_ARG;

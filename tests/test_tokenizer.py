@@ -156,3 +156,22 @@ def test_random_strings_against_the_library_live(tok, tok_l3):
         if k % 10 == 0:
             cut = want[:rng.randint(0, len(want))]
             assert tok.decode(cut, skip_special_tokens=True) == hf.decode(cut, skip_special_tokens=True), repr(s)
+
+
+def test_streaming_decode_yields_whole_characters_and_sums_to_decode(tok, gold):
+    rng = random.Random(3)
+    texts = [c["text"] for c in gold["cases"]] + ["天\U0001f600é" * 3]
+    for text in texts:
+        ids = tok.encode(text)
+        pieces = list(tok.stream(ids))
+        assert len(pieces) == len(ids) + 1
+        assert "".join(pieces) == tok.decode(ids), repr(text)
+        for p in pieces[:-1]:
+            assert "�" not in p or "�" in text, repr(text)  # no broken characters while the sequence is a real encoding
+    # arbitrary id sequences (cut characters, stray continuation bytes): still the same text as decode() in one go, pieces still valid UTF-8
+    usable = [i for i in range(tok.vocab_size) if "\u0100" not in tok.id_to_token(i)]  # U+0100 is byte 0: NUL would end the returned C string
+    for _ in range(300):
+        ids = [rng.choice(usable) for _ in range(rng.randint(0, 30))]
+        for skip in (False, True):
+            pieces = list(tok.stream(ids, skip_special_tokens=skip))
+            assert "".join(pieces) == tok.decode(ids, skip_special_tokens=skip), ids
