@@ -48,7 +48,10 @@ int kf_model_set_tensor(kf_model* m, const char* hf_name, const void* host_bf16,
  * CU_Q42X_awq src/Device/CUDA/kernel/quantizer.cu:132-156): qweight int32 [in][out / 8] (nibbles in AWQ_REVERSE_ORDER), qzeros int32
  * [in / 128][out / 8], scales fp16 [in / 128][out].  The quantizer card must select "quant_method": "awq" for the tensor (an HF config's
  * "quantization_config" does: QUANT_CARD::Vendor2JSONx, src/Utils/CLI_params.cpp:240-262).  The arrays are cut to the rank's window and
- * stay in the vendor layout on the device (type KF_T_AWQ4). */
+ * stay in the vendor layout on the device (type KF_T_AWQ4), read as CU_Q42X_awq reads them (bit-equal weights; a functional, untuned matmul).
+ * With "gpt": {"awq_repack": 1} in the config they are instead re-laid-out at load into the library's own 4-bit storage (type KF_T_Q4: the
+ * same codes in PackedQ words over [out][in], step = bf16(scale), zero = bf16(zero_point * scale)) so that the tuned decode / tensor-core
+ * kernels run on them; the weights then differ from CU_Q42X_awq's by the bf16 rounding of step and zero (a few 1e-3 of the group's range). */
 int kf_model_set_tensor_awq(kf_model* m, const char* hf_name, const void* qweight_i32, const void* qzeros_i32, const void* scales_f16,
                             int in_features, int out_features);
 /* descriptor of the device-resident (possibly packed) tensor: for parity tests (GetDataX equivalent via kf_dequant) */
@@ -128,7 +131,8 @@ int kf_config_quant_of(const char* config_json, const char* tensor_name, int* ty
 int kf_config_shard_of(const char* config_json, const char* tensor_name, int rank, int world, int* shape_out, char** err_out);
 
 /* the same plan applied to a vendor AWQ linear (host only): rank `rank`'s blob qweight || qzeros || scales -- exactly the bytes
- * kf_model_set_tensor_awq uploads -- cut from the FULL arrays.  *bytes_out = blob size; out_blob may be NULL to query it. */
+ * kf_model_set_tensor_awq uploads -- cut from the FULL arrays.  *bytes_out = blob size; out_blob may be NULL to query it.  When the config
+ * says gpt.awq_repack = 1 the blob is the re-laid-out one (PackedQ 4-bit data || gama of the window). */
 int kf_config_awq_shard(const char* config_json, const char* tensor_name, int rank, int world, const void* qweight_i32, const void* qzeros_i32,
                         const void* scales_f16, void* out_blob, size_t capacity, size_t* bytes_out, char** err_out);
 

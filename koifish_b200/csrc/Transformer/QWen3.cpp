@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 
 namespace koifish {
 
@@ -72,6 +73,7 @@ MODEL_CARD MODEL_CARD::FromJSON(const JSON& j0) {
     c.max_seq_len = jint(j0, {"gpt", "max_seq_len"}, c.max_seq_len);
     c.max_batch   = jint(j0, {"gpt", "max_batch"}, c.max_batch);
     c.max_prefill = jint(j0, {"gpt", "max_prefill"}, c.max_prefill);
+    c.awq_repack  = jint(j0, {"gpt", "awq_repack"}, c.awq_repack);
     if (const JSON* s = j0.path({"init", "sigma"})) c.init_sigma = (float)s->as_double(c.init_sigma);
     if (const JSON* s = j0.path({"init", "norm_sigma"})) c.norm_sigma = (float)s->as_double(c.norm_sigma);
     std::string a = c.arch;
@@ -456,6 +458,95 @@ void AwqShardWindow(const void* qweight, const void* qzeros, const void* scales,
         memcpy(sc + (size_t)g * OCl, fsc + (g0 + g) * (size_t)OC + r0, (size_t)OCl * 2);
     }
 }
+// gpt.awq_repack = 1: the same window re-laid-out at load into the library's own 4-bit storage -- PackedQ words over [out][in] rows (reference
+// src/PackedQ.hpp:99-183: code i < 16 of a word in `high` at bit 60 - 4i, the rest in `low`; bytes 0-7 = low) + the bf16 gama array
+// [R_SCALE][C_SCALE][ZERO][STEP] (GTensor.cpp:456-510) with step = bf16(scale), zero = bf16(zero_point * scale) per (out row, 128 input columns)
+// -- so the decode GEMV / tcgen05 kernels of section 3.1 / 3.2 run on it at full speed.  The codes move unchanged (an AWQ group IS a PackedQ
+// group: 128 consecutive input columns of one output row); the arithmetic becomes the RTN one, step * code - zero, with bf16 step / zero instead
+// of (code - zero_point) * fp16 scale: off from CU_Q42X_awq by the bf16 rounding of the two products (tests state the bound).  Host code.
+static inline uint16_t f32_to_bf16_host(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x0040u);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static inline float f16_to_f32_host(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1f, man = h & 0x3ffu;
+    uint32_t bits;
+    if (exp == 0) {
+        if (man == 0) {
+            bits = sign;
+        } else {
+            int e = -1;
+            uint32_t m = man;
+            do { e++, m <<= 1; } while (!(m & 0x400u));
+            bits = sign | (uint32_t)(127 - 15 - e) << 23 | (m & 0x3ffu) << 13;
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7f800000u | man << 13;
+    } else {
+        bits = sign | (exp + 112) << 23 | man << 13;
+    }
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+size_t AwqRepackBytes(int OCl, int ICl) { return (size_t)OCl * ICl / 2 + 2 * ((size_t)OCl + ICl + 2 * ((size_t)OCl * ICl / 128)); }
+void AwqRepackWindow(const void* qweight, const void* qzeros, const void* scales, int IC, int OC, int r0, int OCl, int c0, int ICl, uint8_t* out_blob) {
+    (void)IC;
+    static const int kOrder[8] = {0, 4, 1, 5, 2, 6, 3, 7};  // AWQ_REVERSE_ORDER: element k of a word sits in nibble kOrder[k]
+    const uint32_t* fqw = (const uint32_t*)qweight;
+    const uint32_t* fqz = (const uint32_t*)qzeros;
+    const uint16_t* fsc = (const uint16_t*)scales;
+    const size_t W8g = (size_t)OC / 8, gpr = (size_t)ICl / 128, nG = (size_t)OCl * gpr;
+    uint64_t* words = (uint64_t*)out_blob;  // {low, high} per 32 codes
+    uint16_t* gama  = (uint16_t*)(out_blob + (size_t)OCl * ICl / 2);
+    memset(gama, 0, 2 * ((size_t)OCl + ICl));  // R / C scales: unused (NO_NORMAL)
+    uint16_t* gZero = gama + OCl + ICl;
+    uint16_t* gStep = gZero + nG;
+    for (int o = 0; o < OCl; o++) {
+        const int oc = r0 + o, shift = 4 * kOrder[oc & 7];
+        const size_t wcol = (size_t)oc / 8;
+        for (size_t g = 0; g < gpr; g++) {
+            const size_t gg = (size_t)c0 / 128 + g;
+            const int z     = (int)((fqz[gg * W8g + wcol] >> shift) & 0xFu);
+            const float sc  = f16_to_f32_host(fsc[gg * (size_t)OC + oc]);
+            gStep[(size_t)o * gpr + g] = f32_to_bf16_host(sc);
+            gZero[(size_t)o * gpr + g] = f32_to_bf16_host((float)z * sc);
+        }
+    }
+    // codes: 32 input rows at a time, every vendor word read once (it holds one input row of 8 output columns); a few host threads share the blocks
+    const int nBlock = ICl / 32, W8l = OCl / 8, w0 = r0 / 8;
+    auto work = [&](int b0, int b1) {
+        for (int w = b0; w < b1; w++)
+            for (int wc = 0; wc < W8l; wc++) {
+                uint64_t high[8] = {0, 0, 0, 0, 0, 0, 0, 0}, low[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int i = 0; i < 32; i++) {
+                    const uint32_t word = fqw[((size_t)c0 + (size_t)w * 32 + i) * W8g + w0 + wc];
+                    for (int k = 0; k < 8; k++) {
+                        const uint64_t q = (word >> (4 * kOrder[k])) & 0xFu;
+                        if (i < 16)
+                            high[k] |= q << (60 - 4 * i);
+                        else
+                            low[k] |= q << (60 - 4 * (i - 16));
+                    }
+                }
+                for (int k = 0; k < 8; k++) {
+                    uint64_t* dst = words + 2 * ((size_t)(wc * 8 + k) * nBlock + w);
+                    dst[0] = low[k], dst[1] = high[k];
+                }
+            }
+    };
+    const int nThread = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, nBlock}));
+    if (nThread == 1 || (size_t)OCl * ICl < (1u << 22)) {
+        work(0, nBlock);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nThread; t++) pool.emplace_back(work, (int)((long long)nBlock * t / nThread), (int)((long long)nBlock * (t + 1) / nThread));
+        for (auto& th : pool) th.join();
+    }
+}
 // Vendor AWQ tensors (GeQuant::ExTensor + GTensor::LoadParam of .qweight / .qzeros / .scales, reference src/Tensor/GeQuant.cpp:144-200,
 // src/Manifold/Serialize.cpp:145-230): the FULL (unsharded) arrays as the checkpoint stores them --
 //   qweight int32 [IC][OC / 8], qzeros int32 [IC / 128][OC / 8], scales fp16 [IC / 128][OC]     (IC = in_features, OC = out_features)
@@ -480,13 +571,20 @@ int Fish::SetTensorAWQ(const std::string& name, const void* qweight, const void*
         return KF_ERR_BAD_ARG;
     }
     const int OCl = t->ne[0], ICl = t->ne[1];
-    int rc = t->AllocAWQ();
-    if (rc) {
+    if (ICl % 128 || OCl % 32) {
         error = "tensor '" + name + "': the AWQ layout needs in_features in whole 128-row groups and out_features a multiple of 32 per rank";
+        return KF_ERR_BAD_ARG;
+    }
+    int rc = config.awq_repack ? t->Alloc(typNUMBER::Q4, 128) : t->AllocAWQ();
+    if (rc) {
+        error = "tensor '" + name + "': " + kf_last_error(ctx);
         return rc;
     }
     std::vector<uint8_t> blob(t->nByte());
-    AwqShardWindow(qweight, qzeros, scales, IC, OC, r0, OCl, c0, ICl, blob.data());
+    if (config.awq_repack)  // the library's own 4-bit storage: the fast matmul kernels apply (see AwqRepackWindow)
+        AwqRepackWindow(qweight, qzeros, scales, IC, OC, r0, OCl, c0, ICl, blob.data());
+    else
+        AwqShardWindow(qweight, qzeros, scales, IC, OC, r0, OCl, c0, ICl, blob.data());
     KF_TRY(kf_h2d(ctx, t->data, blob.data(), blob.size()));
     KF_TRY(kf_ctx_sync(ctx));
     t->qBias = 0;

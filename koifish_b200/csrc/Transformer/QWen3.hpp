@@ -33,6 +33,7 @@ struct MODEL_CARD {
     float init_sigma = 0.02f, norm_sigma = 0.0f;  // huTensor.cu:204 ; norms FIX_1
     int max_batch = 1;                            // independent sequences (batched decode)
     int max_prefill = 64;                         // tokens per prefill panel (gpt.max_prefill): sizes the activation buffers
+    int awq_repack  = 0;                          // gpt.awq_repack: vendor AWQ tensors re-laid-out at load into PackedQ 4-bit storage (fast kernels)
 
     // accepts a Koifish JSON (cases/qwen3/*.json layout) or an HF config.json, optionally wrapped as {"hf_config": {...}}
     static MODEL_CARD FromJSON(const JSON& j);
@@ -44,6 +45,8 @@ struct Fish;
 bool ShardPlan(const MODEL_CARD& c, const std::string& name, int rank, int world, int* rows_g, int* cols_g, int* rows_l, int* cols_l, int* row0,
                int* col0);
 
+size_t AwqRepackBytes(int OCl, int ICl);
+void AwqRepackWindow(const void* qweight, const void* qzeros, const void* scales, int IC, int OC, int r0, int OCl, int c0, int ICl, uint8_t* out_blob);
 void AwqShardWindow(const void* qweight, const void* qzeros, const void* scales, int IC, int OC, int r0, int OCl, int c0, int ICl, uint8_t* out_blob);
 
 // ---- neurons --------------------------------------------------------------------------------------------------------------

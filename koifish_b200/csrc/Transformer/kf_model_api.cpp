@@ -275,6 +275,18 @@ extern "C" int kf_config_awq_shard(const char* config_json, const char* tensor_n
     if (!config_json || !tensor_name || !bytes_out) return KF_ERR_BAD_ARG;
     try {
         MODEL_CARD c = MODEL_CARD::FromJSON(JSON::parse(config_json));
+        if (c.awq_repack) {  // gpt.awq_repack = 1: the blob is PackedQ 4-bit data || gama of the window (AwqRepackWindow)
+            int sh[6];
+            if (!ShardPlan(c, tensor_name, rank, world, sh, sh + 1, sh + 2, sh + 3, sh + 4, sh + 5) || sh[2] % 32 || sh[3] % 128 || sh[4] % 8 || sh[5] % 128) {
+                if (err_out) *err_out = dup_cstr("unknown tensor name, or the tensor-parallel window is not in whole 32-column blocks / 128-row groups");
+                return KF_ERR_BAD_ARG;
+            }
+            *bytes_out = AwqRepackBytes(sh[2], sh[3]);
+            if (!out_blob) return KF_OK;
+            if (!qweight || !qzeros || !scales || capacity < *bytes_out) return KF_ERR_BAD_ARG;
+            AwqRepackWindow(qweight, qzeros, scales, sh[1], sh[0], sh[4], sh[2], sh[5], sh[3], (uint8_t*)out_blob);
+            return KF_OK;
+        }
         int sh[6];
         if (!ShardPlan(c, tensor_name, rank, world, sh, sh + 1, sh + 2, sh + 3, sh + 4, sh + 5) || sh[2] % 32 || sh[3] % 128 || sh[4] % 8 || sh[5] % 128) {
             if (err_out) *err_out = dup_cstr("unknown tensor name, or the tensor-parallel window is not in whole 32-column blocks / 128-row groups");

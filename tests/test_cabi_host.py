@@ -175,6 +175,50 @@ def test_awq_shard_windows_dequantise_to_the_windows_of_the_full_weight():
         lib.kf_string_free(err)
 
 
+def test_awq_repack_into_packedq_storage_matches_the_vendor_read():
+    # gpt.awq_repack = 1: the window of an AWQ linear re-laid-out into PackedQ 4-bit words + gama (what kf_model_set_tensor_awq uploads then).  The
+    # oracle's CU_Q128toX_ port reads it back: with unit scales the weights are the code differences q - z, so equality with CU_Q42X_awq's read of
+    # the vendor arrays is bit-exact and pins the whole re-layout (nibble order, [in][out] -> [out][in], the 128-bit word layout, the group index);
+    # with real scales the two reads differ only by the bf16 rounding of step = scale and zero = zero_point * scale.
+    import oracle_lib as ol
+    lib = kf.load()
+    hf = {"hf_config": {"hidden_size": 512, "intermediate_size": 1024, "num_hidden_layers": 1, "num_attention_heads": 8, "num_key_value_heads": 4,
+                        "head_dim": 64, "vocab_size": 1024,
+                        "quantization_config": {"bits": 4, "group_size": 128, "quant_method": "awq", "zero_point": True}},
+          "gpt": {"awq_repack": 1}}
+    text = json.dumps(hf).encode()
+    rng = np.random.default_rng(11)
+    for name, OC, IC in (("model.layers.0.self_attn.q_proj.weight", 512, 512), ("model.layers.0.self_attn.o_proj.weight", 512, 512),
+                         ("model.layers.0.mlp.up_proj.weight", 1024, 512), ("model.layers.0.mlp.down_proj.weight", 512, 1024)):
+        for unit in (True, False):
+            qw = rng.integers(0, 2 ** 32, size=IC * OC // 8, dtype=np.uint64).astype(np.uint32)
+            qz = rng.integers(0, 2 ** 32, size=IC // 128 * OC // 8, dtype=np.uint64).astype(np.uint32)
+            sc = (np.ones(IC // 128 * OC) if unit else rng.uniform(0.001, 0.02, size=IC // 128 * OC)).astype(np.float16)
+            full = ol.awq_dequant(qw, qz, sc.view(np.uint16), IC, OC)  # bf16 [in][out], CU_Q42X_awq
+            for world in (1, 2):
+                for rank in range(world):
+                    shape = (C.c_int * 6)()
+                    assert lib.kf_config_shard_of(text, name.encode(), rank, world, shape, None) == 0
+                    _, _, OCl, ICl, r0, c0 = list(shape)
+                    n, err = C.c_size_t(0), C.c_void_p()
+                    assert lib.kf_config_awq_shard(text, name.encode(), rank, world, None, None, None, None, 0, C.byref(n), C.byref(err)) == 0
+                    nG = OCl * ICl // 128
+                    assert n.value == OCl * ICl // 2 + 2 * (OCl + ICl + 2 * nG)  # szData + szGama of a Q4 tensor (GeQuant.cpp:518)
+                    blob = np.zeros(n.value, dtype=np.uint8)
+                    assert lib.kf_config_awq_shard(text, name.encode(), rank, world, qw.ctypes.data, qz.ctypes.data, sc.ctypes.data, blob.ctypes.data,
+                                                   blob.nbytes, C.byref(n), C.byref(err)) == 0
+                    data, gama = blob[:OCl * ICl // 2], blob[OCl * ICl // 2:].view(np.uint16)
+                    got = ol.bf16_to_f32(ol.dequant(data, gama, OCl, ICl, 4, 128, 0))  # [out][in], CU_Q128toX_
+                    want = ol.bf16_to_f32(full)[c0:c0 + ICl, r0:r0 + OCl].T
+                    if unit:
+                        assert np.array_equal(got, want), (name, world, rank)
+                    else:
+                        step = np.repeat(sc.astype(np.float32).reshape(IC // 128, OC)[c0 // 128:(c0 + ICl) // 128, r0:r0 + OCl].T, 128, axis=1)
+                        # |step * q - zero| terms are each rounded to bf16 (2^-9 relative at most, q and z <= 15) plus the final rounding
+                        assert np.all(np.abs(got - want) <= step * 15 * 3 * 2.0 ** -8), (name, world, rank)
+                        assert np.abs(got - want).mean() <= 0.02 * step.mean()
+
+
 def _dims(text):
     lib = kf.load()
     info, err = kf.ModelInfo(), C.c_void_p()
