@@ -1017,8 +1017,9 @@ int Fish::LoadKun(const std::string& path, int* n_loaded, int* n_skipped) {
         }
         const hGTensor& t   = it->second;
         const bool quantised = t->hQuant && t->ne[0] > 1;
-        const typNUMBER want = quantised ? t->hQuant->params.tpQuant() : typNUMBER::BF16;
-        const char* dt       = kunDtype(want);
+        typNUMBER want = quantised ? t->hQuant->params.tpQuant() : typNUMBER::BF16;
+        if (want == typNUMBER::Q4_AWQ && config.awq_repack) want = typNUMBER::Q4;  // repacked at load: stored (and saved) as the library's own Q4
+        const char* dt = kunDtype(want);
         // accept the HF spelling for plain tensors ("BF16"), otherwise the K_FLOATS name this model's config selects for the tensor
         if (!dt || !(e.dtype == dt || (want == typNUMBER::BF16 && e.dtype == "BF16")))
             return fail("tensor '" + e.name + "' is stored as " + e.dtype + ", this config selects " + (dt ? dt : "the AWQ layout"));
