@@ -21,9 +21,14 @@
  *   - outputs of all of these reference kernels on seeded inputs are committed as tests/golden/refgpu_golden.npz (generator
  *     tests/golden/make_golden_refgpu.py, inputs tests/golden_cases.py) and checked against the oracle WITHOUT a GPU by
  *     tests/test_oracle_golden_refgpu.py.
- * Still unpinned: the CPU packer GeQuant::RTN_x / YinYang (src/Tensor/GeQuant.cpp:428-628) -- it only links with the whole framework;
- * it is restated from the cited lines and cross-checked against the reference's GPU packer (same algorithm, float arithmetic that
- * differs in documented places) -- and the cuBLASLt GEMM (closed source; fp32 accumulation, order unspecified => tolerance).
+ *   - the CPU packers GeQuant::RTN_x (4- / 2-bit asymmetric, symmetric, ternary), GeQuant::YinYang (1-bit) and RT_NormalF / _row_lut
+ *     (NormalFloat4) with BIT_SET_k: the reference's own src/Tensor/GeQuant.cpp, src/Tensor/GTensor.cpp and src/Utils/CLI_params.cpp compiled
+ *     where they lie and driven by oracle/ref_cpu_quant.cpp (-> oracle/_ref/libkoifish_refcpu.so; the rest of the framework those files
+ *     mention is bound to 0 at link time and never reached).  kfo_quantize / kfo_nf4_quantize produce the SAME bytes and gama, bit for bit
+ *     (tests/test_oracle.py: live against the library, and against tests/golden/refcpu_quant.npz generated from it by
+ *     tests/golden/make_golden_refcpu.py);
+ *   - the AWQ nibble order / values also against the reference's Python unpack (src/Python/test_awq.py, tests/golden/awq_ref_py.npz).
+ * Still unpinned: the cuBLASLt GEMM (closed source; fp32 accumulation, order unspecified => tolerance).
  *
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
  */

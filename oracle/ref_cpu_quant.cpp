@@ -1,0 +1,67 @@
+// ref_cpu_quant.cpp -- TEST INFRASTRUCTURE ONLY.  Runs the reference's own CPU packers -- GeQuant::RTN_x (4- / 2-bit, asymmetric, symmetric, ternary
+// yyang) and GeQuant::YinYang (1-bit), reference src/Tensor/GeQuant.cpp:428-533, 536-628 -- on caller buffers, so that the oracle's restatement
+// (kfo_quantize) can be pinned to the code the reference compiles.  oracle/Makefile builds the reference's GeQuant.cpp and GTensor.cpp where they
+// lie into objects and links them with this shim into oracle/_ref/libkoifish_refcpu.so; every symbol of the rest of the framework those two files
+// mention (Fish, CUDA runtime, optimizers ...) is bound to 0 at link time and never reached: the packers touch only the members set up below.
+// The GeQuant / GTensor objects are built with the classes' own default constructors and deliberately leaked (their destructors belong to the
+// framework).  Nothing of the reference is copied.
+#include "Tensor/GeQuant.hpp"
+#include "Tensor/GTensor.hpp"
+#include "Utils/GST_util.hpp"
+
+double SUM::tQuant = 0, SUM::tF8Ex = 0, SUM::tLowBit = 0;  // defined in src/Utils/GST_util.cpp, which drags the framework in
+
+namespace {
+struct QuantShim : public GeQuant {  // reach the protected working buffers of the packers
+    void Setup(int bits_, int group, int mode, hBITARR data, floatGama* gama_) {
+        params.default_bits = bits_, params.T_group = group, params.blockAt = BLOCK_at_GROUP;
+        params.isNormalFloat = mode == 3, params.norm = NORMAL_MODE::NO_NORMAL;  // NO_NORMAL is forced at GeQuant.cpp:844-852
+        params.isSymmetric = mode == 1;
+        params.yyang       = mode == 2 ? (bits_ == 1 ? QUANT_YYANG_::I_01 : QUANT_YYANG_::I_TERNARY) : QUANT_YYANG_::I_OFF;
+        params.type        = QUANT_MODE::RTN;
+        bits               = bits_;
+        // code ranges exactly as GeQuant::GeQuant sets them (GeQuant.cpp:107-124)
+        if (params.yyang != QUANT_YYANG_::I_OFF) {
+            if (bits == 2) {
+                qMax = 1, qMin = -1, qBias = 1, params.isSymmetric = true;
+            } else {
+                qMax = 1, qMin = 0, qBias = 0, params.isSymmetric = false;
+            }
+        } else if (params.isSymmetric) {
+            qMin = -(1 << (bits - 1)), qMax = (1 << (bits - 1)) - 1, qBias = -qMin;
+        } else {
+            qMin = 0, qMax = (1 << bits) - 1, qBias = 0;
+        }
+        isGPU      = false;
+        quant_data = data;
+        gama       = gama_;
+    }
+};
+struct TensorShim : public GTensor {  // hQuant is protected: GTensor::gama_T asks it for the group count
+    void Setup(int rows, int cols, GeQuant* q) {
+        for (int i = 0; i < N_DIMS; i++) ne[i] = 1;
+        ne[0] = rows, ne[1] = cols;
+        shape  = {rows, cols};
+        hQuant = std::shared_ptr<GeQuant>(q, [](GeQuant*) {});
+    }
+};
+}  // namespace
+
+// mode: 0 asymmetric RTN, 1 symmetric RTN, 2 yyang (2-bit ternary through RTN_x, 1-bit through YinYang), 3 NormalFloat4 (RTN_x -> RT_NormalF ->
+// _row_lut, GeQuant.cpp:706-752: per-row codebook + MSB-first bitstream).  w: bf16 [rows][cols]; data_out: rows * cols * bits / 8 bytes;
+// gama_out: rows + cols + 2 * (rows * cols / group) bf16 ([R_SCALE][C_SCALE][ZERO][STEP]), or rows + cols + 16 * rows for mode 3 ([..][..][LUT]).
+extern "C" int refcpu_quantize(const void* w_bf16, int rows, int cols, int bits, int group, int mode, void* data_out, void* gama_out, int* qbias_out) {
+    if (!w_bf16 || !data_out || !gama_out || rows <= 0 || cols <= 0 || group <= 0 || ((size_t)rows * cols) % group) return -1;
+    if (!(bits == 4 || bits == 2 || bits == 1) || (bits == 1 && mode != 2) || (mode == 3 && bits != 4)) return -2;
+    auto* q = new QuantShim();
+    q->Setup(bits, group, mode, (hBITARR)data_out, (floatGama*)gama_out);
+    auto* t = new TensorShim();
+    t->Setup(rows, cols, q);
+    std::shared_ptr<GTensor> ht(t, [](GTensor*) {});
+    if (bits == 1)
+        q->YinYang(ht, w_bf16, 0);
+    else
+        q->RTN_x(ht, w_bf16, 0);
+    if (qbias_out) *qbias_out = q->qBias;
+    return 0;
+}

@@ -17,6 +17,7 @@ REF_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_ref.so")
 # multiply-subtract of the dequant is contracted to one fma.rn.bf16), and with -fmad=false / no fast-math ("nofma": two roundings, IEEE division)
 REFGPU_SO = {"fma": os.path.join(ORACLE_DIR, "_ref", "libkoifish_refgpu.so"), "nofma": os.path.join(ORACLE_DIR, "_ref", "libkoifish_refgpu_nofma.so")}
 REFQ_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_refq.so")  # the reference's quantizer.cu (NF4 dequant kernel)
+REFCPU_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_refcpu.so")  # the reference's CPU packers (GeQuant.cpp: RTN_x, YinYang, RT_NormalF)
 
 RTN_ASYM, RTN_SYM, YYANG, NF4 = 0, 1, 2, 3
 
@@ -29,6 +30,10 @@ def build_oracle(force=False):
     shim = os.path.join(ORACLE_DIR, "ref_shim.cpp")
     if os.path.exists("/root/reference/src/PackedQ.hpp") and (force or not os.path.exists(REF_SO) or os.path.getmtime(shim) > os.path.getmtime(REF_SO)):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
+    shim_q = os.path.join(ORACLE_DIR, "ref_cpu_quant.cpp")
+    if os.path.exists("/root/reference/src/Tensor/GeQuant.cpp") and (force or not os.path.exists(REFCPU_SO) or
+                                                                      os.path.getmtime(shim_q) > os.path.getmtime(REFCPU_SO)):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "refcpu"], stdout=subprocess.DEVNULL)
     if os.path.exists("/root/reference/src/Device/CUDA/T.cu"):
         src = os.path.join(ORACLE_DIR, "ref_kernels.cu")
         stale = any(not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src) for so in REFGPU_SO.values())
@@ -144,6 +149,32 @@ def refq():
         _refq.refq_nf4_dequant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _refq.refq_awq_dequant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     return _refq
+
+
+_refcpu = None
+
+
+def refcpu():
+    """the reference's own CPU packers compiled from src/Tensor/GeQuant.cpp (oracle/ref_cpu_quant.cpp), or None when the library was never built"""
+    global _refcpu
+    if _refcpu is None:
+        build_oracle()
+        if not os.path.exists(REFCPU_SO):
+            return None
+        _refcpu = C.CDLL(REFCPU_SO)
+        _refcpu.refcpu_quantize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    return _refcpu
+
+
+def refcpu_quantize(w, rows, cols, bits, group=128, mode=RTN_ASYM):
+    """GeQuant::RTN_x / YinYang / RT_NormalF of the reference itself -> (data bytes, gama bf16 bits, qBias); mode as kfo_quantize (NF4 = 3)"""
+    w = np.ascontiguousarray(w, dtype=np.uint16).reshape(-1)
+    data = np.zeros(rows * cols * bits // 8, dtype=np.uint8)
+    gama = np.zeros(rows + cols + (16 * rows if mode == NF4 else 2 * (rows * cols // group)), dtype=np.uint16)
+    qb = C.c_int(0)
+    rc = refcpu().refcpu_quantize(w.ctypes.data, rows, cols, bits, group, mode, data.ctypes.data, gama.ctypes.data, C.byref(qb))
+    assert rc == 0, rc
+    return data, gama, qb.value
 
 
 def refgpu(variant="fma"):

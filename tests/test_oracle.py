@@ -470,3 +470,48 @@ def test_awq_port_against_the_reference_python_unpack():
         q = g[tag + "_codes"].astype(np.float16) - np.repeat(g[tag + "_zeros"].astype(np.float16), 128, axis=0)
         prod16 = (q * np.repeat(sc.view(np.float16), 128, axis=0)).astype(np.float16)
         assert np.array_equal(ol.f32_to_bf16(prod16.astype(np.float32)).reshape(IC, OC), want)
+
+
+# ---------------------------------------------------------------------------------------------- the reference's own CPU packers
+def _restated(w, rows, cols, bits, mode):
+    if mode == ol.NF4:
+        return ol.nf4_quantize(w, rows, cols)
+    return ol.quantize(w, rows, cols, bits, 128, mode)
+
+
+def test_packers_against_golden_bytes_of_the_reference_cpu_packers():
+    # tests/golden/refcpu_quant.npz: GeQuant::RTN_x / YinYang / RT_NormalF of the reference itself (compiled from src/Tensor/GeQuant.cpp,
+    # tests/golden/make_golden_refcpu.py) on seeded inputs.  Packed bytes and the written part of gama (ZERO / STEP, or the per-row codebooks) must be
+    # equal bit for bit; R_SCALE / C_SCALE are never written by either (NO_NORMAL) and are not compared.
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refcpu_quant.npz"))
+    tags = sorted(k[:-5] for k in g.files if k.endswith("_meta"))
+    assert len(tags) == 9
+    for tag in tags:
+        rows, cols, bits, mode, seed, qb = (int(x) for x in g[tag + "_meta"])
+        w = ol.fill_normal(rows * cols, seed, float(g[tag + "_sigma"][0]))
+        data, gama = _restated(w, rows, cols, bits, mode)
+        assert np.array_equal(data, g[tag + "_data"]), tag
+        assert np.array_equal(gama[rows + cols:], g[tag + "_gama"][rows + cols:]), tag
+        if mode != ol.NF4:
+            assert ol.qrange(bits, mode)[2] == qb, tag
+
+
+def test_packers_against_the_reference_cpu_packers_live():
+    # the same comparison against the compiled reference code itself on more shapes, when oracle/_ref/libkoifish_refcpu.so exists (it is built where
+    # /root/reference is present and travels with the repository snapshot)
+    if ol.refcpu() is None:
+        pytest.skip("oracle/_ref/libkoifish_refcpu.so not built (reference tree absent at build time)")
+    rng = np.random.default_rng(5)
+    for rows, cols in ((8, 128), (40, 384), (64, 2048), (3, 5120)):
+        for bits, mode in ((4, ol.RTN_ASYM), (4, ol.RTN_SYM), (2, ol.RTN_ASYM), (2, ol.YYANG), (1, ol.YYANG), (4, ol.NF4)):
+            for sigma in (0.02, 3.0):
+                w = ol.fill_normal(rows * cols, int(rng.integers(1, 1 << 30)), sigma)
+                if rng.random() < 0.5:  # a few exact zeros and one outlier per call
+                    w = w.copy()
+                    w[rng.integers(0, w.size, 16)] = 0
+                    w[int(rng.integers(0, w.size))] = ol.f32_to_bf16(np.array([sigma * 40], dtype=np.float32))[0]
+                want_d, want_g, qb = ol.refcpu_quantize(w, rows, cols, bits, 128, mode)
+                got_d, got_g = _restated(w, rows, cols, bits, mode)
+                assert np.array_equal(got_d, want_d), (rows, cols, bits, mode, sigma)
+                assert np.array_equal(got_g[rows + cols:], want_g[rows + cols:]), (rows, cols, bits, mode, sigma)
