@@ -3,8 +3,8 @@
 // (kfo_quantize) can be pinned to the code the reference compiles.  oracle/Makefile builds the reference's GeQuant.cpp and GTensor.cpp where they
 // lie into objects and links them with this shim into oracle/_ref/libkoifish_refcpu.so; every symbol of the rest of the framework those two files
 // mention (Fish, CUDA runtime, optimizers ...) is bound to 0 at link time and never reached: the packers touch only the members set up below.
-// The GeQuant / GTensor objects are built with the classes' own default constructors and deliberately leaked (their destructors belong to the
-// framework).  Nothing of the reference is copied.
+// The GeQuant object is built by the reference's own constructor (GeQuant.cpp:83-124: code ranges from the quantizer card), the GTensor by its
+// default constructor; both are deliberately leaked (their destructors belong to the framework).  Nothing of the reference is copied.
 #include "Tensor/GeQuant.hpp"
 #include "Tensor/GTensor.hpp"
 #include "Utils/GST_util.hpp"
@@ -13,25 +13,11 @@ double SUM::tQuant = 0, SUM::tF8Ex = 0, SUM::tLowBit = 0;  // defined in src/Uti
 
 namespace {
 struct QuantShim : public GeQuant {  // reach the protected working buffers of the packers
-    void Setup(int bits_, int group, int mode, hBITARR data, floatGama* gama_) {
-        params.default_bits = bits_, params.T_group = group, params.blockAt = BLOCK_at_GROUP;
-        params.isNormalFloat = mode == 3, params.norm = NORMAL_MODE::NO_NORMAL;  // NO_NORMAL is forced at GeQuant.cpp:844-852
-        params.isSymmetric = mode == 1;
-        params.yyang       = mode == 2 ? (bits_ == 1 ? QUANT_YYANG_::I_01 : QUANT_YYANG_::I_TERNARY) : QUANT_YYANG_::I_OFF;
-        params.type        = QUANT_MODE::RTN;
-        bits               = bits_;
-        // code ranges exactly as GeQuant::GeQuant sets them (GeQuant.cpp:107-124)
-        if (params.yyang != QUANT_YYANG_::I_OFF) {
-            if (bits == 2) {
-                qMax = 1, qMin = -1, qBias = 1, params.isSymmetric = true;
-            } else {
-                qMax = 1, qMin = 0, qBias = 0, params.isSymmetric = false;
-            }
-        } else if (params.isSymmetric) {
-            qMin = -(1 << (bits - 1)), qMax = (1 << (bits - 1)) - 1, qBias = -qMin;
-        } else {
-            qMin = 0, qMax = (1 << bits) - 1, qBias = 0;
-        }
+    // the reference's own constructor (GeQuant.cpp:83-124) derives the code range qMin / qMax / qBias from the card
+    QuantShim(QUANT_CARD& card) : GeQuant("refcpu", nullptr, card, 0x0) {}
+    void Target(hBITARR data, floatGama* gama_) {
+        // the constructor sized its own buffers for the framework's tensors (max(nGroup, T_group) * 2^bits + ...), which a short-and-wide test matrix
+        // can exceed: the packers write into the caller's buffers instead (the constructor's allocations are leaked with the object)
         isGPU      = false;
         quant_data = data;
         gama       = gama_;
@@ -53,8 +39,14 @@ struct TensorShim : public GTensor {  // hQuant is protected: GTensor::gama_T as
 extern "C" int refcpu_quantize(const void* w_bf16, int rows, int cols, int bits, int group, int mode, void* data_out, void* gama_out, int* qbias_out) {
     if (!w_bf16 || !data_out || !gama_out || rows <= 0 || cols <= 0 || group <= 0 || ((size_t)rows * cols) % group) return -1;
     if (!(bits == 4 || bits == 2 || bits == 1) || (bits == 1 && mode != 2) || (mode == 3 && bits != 4)) return -2;
-    auto* q = new QuantShim();
-    q->Setup(bits, group, mode, (hBITARR)data_out, (floatGama*)gama_out);
+    QUANT_CARD card;
+    card.default_bits = bits, card.T_group = group, card.blockAt = BLOCK_at_GROUP, card.type = QUANT_MODE::RTN;
+    card.isNormalFloat = mode == 3, card.norm = NORMAL_MODE::NO_NORMAL;  // NO_NORMAL is forced at GeQuant.cpp:844-852
+    card.isSymmetric   = mode == 1;
+    card.yyang         = mode == 2 ? (bits == 1 ? QUANT_YYANG_::I_01 : QUANT_YYANG_::I_TERNARY) : QUANT_YYANG_::I_OFF;  // Init4Neuron, GeQuant.cpp:1248-1250
+    card.spMost        = {rows, cols};
+    auto* q = new QuantShim(card);
+    q->Target((hBITARR)data_out, (floatGama*)gama_out);
     auto* t = new TensorShim();
     t->Setup(rows, cols, q);
     std::shared_ptr<GTensor> ht(t, [](GTensor*) {});
