@@ -124,6 +124,9 @@ int kf_kun_write(const char* path, const char* config_json, int n, const char* c
  * quantizer block selects for a tensor name (QUANT_CARD::Init4Neuron, reference src/Tensor/GeQuant.cpp:1186-1285; MakeInstance
  * :23-81).  type_out: KF_T_* (KF_T_BF16 when the tensor is not quantised); mode_out: KF_Q_*. */
 int kf_config_dims(const char* config_json, kf_model_info* out, char** err_out);
+/* the "quantizer" block the config resolves to, as JSON text ("" when none): an HF config's "quantization_config" goes through the mapping of
+ * QUANT_CARD::Vendor2JSONx (reference src/Utils/CLI_params.cpp:240-262) */
+int kf_config_quantizer_json(const char* config_json, char** json_out, char** err_out);
 int kf_config_quant_of(const char* config_json, const char* tensor_name, int* type_out, int* group_out, int* mode_out, int* qbias_out,
                        char** err_out);
 /* tensor-parallel shard plan: shape_out[6] = {rows_global, cols_global, rows_local, cols_local, row0, col0} of `tensor_name` on

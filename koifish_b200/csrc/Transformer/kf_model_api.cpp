@@ -167,6 +167,21 @@ extern "C" int kf_config_dims(const char* config_json, kf_model_info* o, char** 
         return KF_ERR_BAD_ARG;
     }
 }
+// host only: the "quantizer" block the config resolves to, as JSON text -- for an HF config with "quantization_config" this is what
+// QUANT_CARD::Vendor2JSONx builds (reference src/Utils/CLI_params.cpp:240-262); "" when the config quantises nothing
+extern "C" int kf_config_quantizer_json(const char* config_json, char** json_out, char** err_out) {
+    if (err_out) *err_out = nullptr;
+    if (!config_json || !json_out) return KF_ERR_BAD_ARG;
+    *json_out = nullptr;
+    try {
+        MODEL_CARD c = MODEL_CARD::FromJSON(JSON::parse(config_json));
+        *json_out    = dup_cstr(c.jQuant.is_null() ? std::string() : json_dump(c.jQuant));
+        return KF_OK;
+    } catch (const std::exception& e) {
+        if (err_out) *err_out = dup_cstr(e.what());
+        return KF_ERR_UNSUPPORTED;
+    }
+}
 extern "C" int kf_config_quant_of(const char* config_json, const char* tensor_name, int* type_out, int* group_out, int* mode_out,
                                   int* qbias_out, char** err_out) {
     if (err_out) *err_out = nullptr;

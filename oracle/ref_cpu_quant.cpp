@@ -5,6 +5,8 @@
 // mention (Fish, CUDA runtime, optimizers ...) is bound to 0 at link time and never reached: the packers touch only the members set up below.
 // The GeQuant object is built by the reference's own constructor (GeQuant.cpp:83-124: code ranges from the quantizer card), the GTensor by its
 // default constructor; both are deliberately leaked (their destructors belong to the framework).  Nothing of the reference is copied.
+#include <cstring>
+
 #include "Tensor/GeQuant.hpp"
 #include "Tensor/GTensor.hpp"
 #include "Utils/GST_util.hpp"
@@ -56,4 +58,15 @@ extern "C" int refcpu_quantize(const void* w_bf16, int rows, int cols, int bits,
         q->RTN_x(ht, w_bf16, 0);
     if (qbias_out) *qbias_out = q->qBias;
     return 0;
+}
+
+// QUANT_CARD::Vendor2JSONx (reference src/Utils/CLI_params.cpp:240-262): an HF checkpoint's "quantization_config" block -> the "quantizer" block the
+// reference builds from it.  JSON text in, JSON text out (the reference's own nlohmann dump); returns the length, or -1 when `cap` is too small.
+extern "C" int refcpu_vendor2jsonx(const char* vendor_json, char* out, int cap) {
+    if (!vendor_json || !out) return -1;
+    const JSON jx     = JSON::parse(vendor_json);
+    const std::string s = QUANT_CARD::Vendor2JSONx(jx).dump();
+    if ((int)s.size() + 1 > cap) return -1;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
 }

@@ -163,6 +163,7 @@ def refcpu():
             return None
         _refcpu = C.CDLL(REFCPU_SO)
         _refcpu.refcpu_quantize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        _refcpu.refcpu_vendor2jsonx.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     return _refcpu
 
 
@@ -175,6 +176,15 @@ def refcpu_quantize(w, rows, cols, bits, group=128, mode=RTN_ASYM):
     rc = refcpu().refcpu_quantize(w.ctypes.data, rows, cols, bits, group, mode, data.ctypes.data, gama.ctypes.data, C.byref(qb))
     assert rc == 0, rc
     return data, gama, qb.value
+
+
+def refcpu_vendor2jsonx(vendor_block):
+    """QUANT_CARD::Vendor2JSONx of the reference itself: dict in, dict out (key order preserved)"""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    n = refcpu().refcpu_vendor2jsonx(json.dumps(vendor_block).encode(), buf, len(buf))
+    assert n >= 0
+    return json.loads(buf.value.decode())
 
 
 def refgpu(variant="fma"):

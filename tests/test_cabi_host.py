@@ -219,6 +219,26 @@ def test_awq_repack_into_packedq_storage_matches_the_vendor_read():
                         assert np.abs(got - want).mean() <= 0.02 * step.mean()
 
 
+def test_hf_quantization_config_mapping_equals_the_reference_function():
+    # QUANT_CARD::Vendor2JSONx (CLI_params.cpp:240-262) compiled from the reference tree (oracle/_ref/libkoifish_refcpu.so) against the quantizer block
+    # this library derives from the same HF config
+    import oracle_lib as ol
+    if ol.refcpu() is None:
+        pytest.skip("oracle/_ref/libkoifish_refcpu.so not built (reference tree absent at build time)")
+    lib = kf.load()
+    for vendor in ({"bits": 4, "group_size": 128, "modules_to_not_convert": None, "quant_method": "awq", "version": "gemm", "zero_point": True},
+                   {"bits": 4, "group_size": 128, "quant_method": "gptq", "desc_act": False, "sym": True},
+                   {"quant_method": "awq", "bits": 4}):
+        hf = {"hidden_size": 1024, "intermediate_size": 3072, "num_hidden_layers": 2, "num_attention_heads": 16, "num_key_value_heads": 8, "head_dim": 128,
+              "quantization_config": vendor}
+        out, err = C.c_void_p(), C.c_void_p()
+        assert lib.kf_config_quantizer_json(json.dumps(hf).encode(), C.byref(out), C.byref(err)) == 0
+        got = json.loads(C.cast(out, C.c_char_p).value.decode())
+        lib.kf_string_free(out)
+        want = ol.refcpu_vendor2jsonx(vendor)
+        assert got == want and list(got) == list(want), (got, want)
+
+
 def _dims(text):
     lib = kf.load()
     info, err = kf.ModelInfo(), C.c_void_p()
