@@ -1,4 +1,6 @@
-// ref_cpu_quant.cpp -- TEST INFRASTRUCTURE ONLY.  Runs the reference's own CPU packers -- GeQuant::RTN_x (4- / 2-bit, asymmetric, symmetric, ternary
+// ref_cpu_quant.cpp -- TEST INFRASTRUCTURE ONLY.  Runs the reference's own host code on caller buffers: the CPU packers (below), and three pure
+// functions of src/Utils/CLI_params.cpp -- QUANT_CARD::Vendor2JSONx, CHAT_SAMPLER::toChatML, CHAT_SAMPLER::InitPrefillTemplate (end of file).
+// The CPU packers -- GeQuant::RTN_x (4- / 2-bit, asymmetric, symmetric, ternary
 // yyang) and GeQuant::YinYang (1-bit), reference src/Tensor/GeQuant.cpp:428-533, 536-628 -- on caller buffers, so that the oracle's restatement
 // (kfo_quantize) can be pinned to the code the reference compiles.  oracle/Makefile builds the reference's GeQuant.cpp and GTensor.cpp where they
 // lie into objects and links them with this shim into oracle/_ref/libkoifish_refcpu.so; every symbol of the rest of the framework those two files
@@ -66,6 +68,31 @@ extern "C" int refcpu_vendor2jsonx(const char* vendor_json, char* out, int cap) 
     if (!vendor_json || !out) return -1;
     const JSON jx     = JSON::parse(vendor_json);
     const std::string s = QUANT_CARD::Vendor2JSONx(jx).dump();
+    if ((int)s.size() + 1 > cap) return -1;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+// CHAT_SAMPLER::toChatML (reference src/Utils/CLI_params.cpp:2010-2031) over n (role, content) lines; text out as refcpu_vendor2jsonx
+extern "C" int refcpu_tochatml(const char* const* roles, const char* const* contents, int n, int enable_thinking, char* out, int cap) {
+    if (n < 0 || !out) return -1;
+    CHAT_SAMPLER cs;
+    cs.enable_thinking = enable_thinking != 0;
+    std::vector<ChatML_samp> lines;
+    for (int i = 0; i < n; i++) lines.emplace_back(std::string(roles[i]), std::string(contents[i]));
+    const std::string s = cs.toChatML(lines);
+    if ((int)s.size() + 1 > cap) return -1;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+// CHAT_SAMPLER::InitPrefillTemplate (:1990-2008): the two printf templates (user only; system + user) for enable_thinking on / off, joined by '\x01'
+extern "C" int refcpu_prefill_templates(int enable_thinking, char* out, int cap) {
+    if (!out) return -1;
+    auto* cfg = new CLI_params();  // leaked: its destructor belongs to the framework
+    cfg->model.enable_thinking = enable_thinking != 0;
+    CHAT_SAMPLER cs;
+    cs.InitPrefillTemplate(cfg);
+    const std::string s = cs.prompt_template + "\x01" + cs.system_prompt_template;
     if ((int)s.size() + 1 > cap) return -1;
     memcpy(out, s.c_str(), s.size() + 1);
     return (int)s.size();

@@ -164,6 +164,8 @@ def refcpu():
         _refcpu = C.CDLL(REFCPU_SO)
         _refcpu.refcpu_quantize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         _refcpu.refcpu_vendor2jsonx.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        _refcpu.refcpu_tochatml.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_char_p, C.c_int]
+        _refcpu.refcpu_prefill_templates.argtypes = [C.c_int, C.c_char_p, C.c_int]
     return _refcpu
 
 
@@ -185,6 +187,24 @@ def refcpu_vendor2jsonx(vendor_block):
     n = refcpu().refcpu_vendor2jsonx(json.dumps(vendor_block).encode(), buf, len(buf))
     assert n >= 0
     return json.loads(buf.value.decode())
+
+
+def refcpu_tochatml(lines, enable_thinking):
+    """CHAT_SAMPLER::toChatML of the reference itself"""
+    n = len(lines)
+    roles = (C.c_char_p * max(1, n))(*[r.encode() for r, _ in lines])
+    texts = (C.c_char_p * max(1, n))(*[c.encode() for _, c in lines])
+    buf = C.create_string_buffer(1 << 16)
+    assert refcpu().refcpu_tochatml(roles, texts, n, int(enable_thinking), buf, len(buf)) >= 0
+    return buf.value.decode()
+
+
+def refcpu_prefill_templates(enable_thinking):
+    """CHAT_SAMPLER::InitPrefillTemplate of the reference itself -> (prompt_template, system_prompt_template), printf-style"""
+    buf = C.create_string_buffer(1 << 12)
+    assert refcpu().refcpu_prefill_templates(int(enable_thinking), buf, len(buf)) >= 0
+    a, b = buf.value.decode().split("\x01")
+    return a, b
 
 
 def refgpu(variant="fma"):

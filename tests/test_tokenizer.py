@@ -127,6 +127,21 @@ def test_chatml_templates_follow_the_reference():
     assert kf.chatml_render([]) == ""
 
 
+def test_chatml_equals_the_reference_functions_compiled_from_its_tree():
+    # CHAT_SAMPLER::InitPrefillTemplate / toChatML (reference src/Utils/CLI_params.cpp:1990-2031) from oracle/_ref/libkoifish_refcpu.so
+    import oracle_lib as ol
+    if ol.refcpu() is None:
+        pytest.skip("oracle/_ref/libkoifish_refcpu.so not built (reference tree absent at build time)")
+    for thinking in (False, True):
+        user_t, sys_t = ol.refcpu_prefill_templates(thinking)
+        for user, system in (("hi", None), ("What is 2 + 2?", "You are a helpful assistant."), ("多行\n文本 100%", "sys % s")):
+            want = (sys_t.replace("%s", "{}").format(system, user)) if system else user_t.replace("%s", "{}").format(user)
+            assert kf.chatml_prompt(user, system, enable_thinking=thinking) == want
+        for lines in ([], [("user", "Hello")], [("system", "You are a dog."), ("user", "Hello"), ("assistant", "Fine")],
+                      [("user", "a"), ("assistant", "b"), ("user", "c"), ("assistant", "d\n")]):
+            assert kf.chatml_render(lines, enable_thinking=thinking) == ol.refcpu_tochatml(lines, thinking)
+
+
 def test_chat_prompt_round_trip(tok, gold):
     p = kf.chatml_prompt("What is the capital of France?", "You are a helpful assistant.")
     ids = tok.encode(p)
