@@ -127,6 +127,10 @@ int kf_config_dims(const char* config_json, kf_model_info* out, char** err_out);
 /* the "quantizer" block the config resolves to, as JSON text ("" when none): an HF config's "quantization_config" goes through the mapping of
  * QUANT_CARD::Vendor2JSONx (reference src/Utils/CLI_params.cpp:240-262) */
 int kf_config_quantizer_json(const char* config_json, char** json_out, char** err_out);
+/* the quantizer card QUANT_CARD::Init4Neuron fills for a tensor name, field by field (parity hook): out[8] = {selected, QUANT_MODE in the
+ * reference's numbering (0 none, 1 RTN, 2 AWQ, 3 RTNf, 5 F8Ex; src/CLI_params.hpp:479-492), default_bits, T_group, yyang, isSymmetric,
+ * isZeroPoint, isVendorQuant}; *errq_out = T_errQ */
+int kf_config_quant_card(const char* config_json, const char* tensor_name, int* out, float* errq_out, char** err_out);
 int kf_config_quant_of(const char* config_json, const char* tensor_name, int* type_out, int* group_out, int* mode_out, int* qbias_out,
                        char** err_out);
 /* tensor-parallel shard plan: shape_out[6] = {rows_global, cols_global, rows_local, cols_local, row0, col0} of `tensor_name` on

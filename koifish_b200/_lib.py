@@ -156,6 +156,7 @@ SIGNATURES = {
     "kf_chatml_render": (_I, [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _I, _I, C.POINTER(_P)]),
     "kf_config_dims": (_I, [C.c_char_p, C.POINTER(ModelInfo), C.POINTER(_P)]),
     "kf_config_quantizer_json": (_I, [C.c_char_p, C.POINTER(_P), C.POINTER(_P)]),
+    "kf_config_quant_card": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_I), C.POINTER(C.c_float), C.POINTER(_P)]),
     "kf_config_quant_of": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_P)]),
     "kf_config_awq_shard": (_I, [C.c_char_p, C.c_char_p, _I, _I, _P, _P, _P, _P, _SZ, C.POINTER(_SZ), C.POINTER(_P)]),
     "kf_config_shard_of": (_I, [C.c_char_p, C.c_char_p, _I, _I, C.POINTER(_I), C.POINTER(_P)]),

@@ -182,6 +182,25 @@ extern "C" int kf_config_quantizer_json(const char* config_json, char** json_out
         return KF_ERR_UNSUPPORTED;
     }
 }
+// host only: the quantizer card Init4Neuron fills for a tensor name, field by field -- out[8] = {selected, mode (0 none, 1 RTN, 2 AWQ, 3 RTNf,
+// 5 F8Ex: the reference's QUANT_MODE numbering, src/CLI_params.hpp:479-492), default_bits, T_group, yyang, isSymmetric, isZeroPoint, isVendorQuant}
+extern "C" int kf_config_quant_card(const char* config_json, const char* tensor_name, int* out, float* errq_out, char** err_out) {
+    if (err_out) *err_out = nullptr;
+    if (!config_json || !tensor_name || !out) return KF_ERR_BAD_ARG;
+    try {
+        MODEL_CARD c = MODEL_CARD::FromJSON(JSON::parse(config_json));
+        QUANT_CARD card;
+        const bool sel = card.Init4Neuron(tensor_name, c.jQuant);
+        const int mode = card.type == RTN ? 1 : card.type == AWQ ? 2 : card.type == RTNf ? 3 : card.type == F8Ex ? 5 : 0;
+        out[0] = sel, out[1] = mode, out[2] = card.default_bits, out[3] = card.T_group, out[4] = (int)card.yyang, out[5] = card.isSymmetric,
+        out[6] = card.isZeroPoint, out[7] = card.isVendorQuant;
+        if (errq_out) *errq_out = card.T_errQ;
+        return KF_OK;
+    } catch (const std::exception& e) {
+        if (err_out) *err_out = dup_cstr(e.what());
+        return KF_ERR_UNSUPPORTED;
+    }
+}
 extern "C" int kf_config_quant_of(const char* config_json, const char* tensor_name, int* type_out, int* group_out, int* mode_out,
                                   int* qbias_out, char** err_out) {
     if (err_out) *err_out = nullptr;

@@ -9,6 +9,8 @@
 // default constructor; both are deliberately leaked (their destructors belong to the framework).  Nothing of the reference is copied.
 #include <cstring>
 
+#include "Manifold/Fish.hpp"
+#include "Manifold/Neuron.hpp"
 #include "Tensor/GeQuant.hpp"
 #include "Tensor/GTensor.hpp"
 #include "Utils/GST_util.hpp"
@@ -96,4 +98,28 @@ extern "C" int refcpu_prefill_templates(int enable_thinking, char* out, int cap)
     if ((int)s.size() + 1 > cap) return -1;
     memcpy(out, s.c_str(), s.size() + 1);
     return (int)s.size();
+}
+
+// QUANT_CARD::Init4Neuron (reference src/Tensor/GeQuant.cpp:1186-1285): which quantiser the "quantizer" block selects for a tensor name.  The
+// function asks its neuron for hFish->isAtPhase(P_CHAT_1) and copies hFish->config.distill; both objects are zero-filled storage of the right size
+// (never constructed, never destroyed), and Fish::isAtPhase -- a one-line accessor of src/Manifold/Fish.cpp, which is not linked -- is answered here.
+bool Fish::isAtPhase(LIFE_PHASE) const { return true; }  // the chat phase: the only effect is QUANT_CARD::isDequant4Generate
+namespace {
+struct NeuronAccess : public GeNeuron {
+    static void SetFish(GeNeuron* n, Fish* f) { static_cast<NeuronAccess*>(n)->hFish = f; }
+};
+}  // namespace
+// out[8] = {selected (0 / 1), type (QUANT_MODE), default_bits, T_group, yyang, isSymmetric, isZeroPoint, isVendorQuant}; *errq_out = T_errQ
+extern "C" int refcpu_init4neuron(const char* tensor_name, const char* quantizer_json, int* out, float* errq_out) {
+    if (!tensor_name || !quantizer_json || !out) return -1;
+    static void* fish   = calloc(1, sizeof(Fish));
+    static void* neuron = calloc(1, sizeof(GeNeuron));
+    NeuronAccess::SetFish((GeNeuron*)neuron, (Fish*)fish);
+    const JSON jq = JSON::parse(quantizer_json);
+    QUANT_CARD card;
+    const bool sel = card.Init4Neuron(tensor_name, jq, neuron, 0x0);
+    out[0] = sel, out[1] = (int)card.type, out[2] = card.default_bits, out[3] = card.T_group, out[4] = (int)card.yyang, out[5] = card.isSymmetric,
+    out[6] = card.isZeroPoint, out[7] = card.isVendorQuant;
+    if (errq_out) *errq_out = card.T_errQ;
+    return 0;
 }

@@ -164,6 +164,7 @@ def refcpu():
         _refcpu = C.CDLL(REFCPU_SO)
         _refcpu.refcpu_quantize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         _refcpu.refcpu_vendor2jsonx.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        _refcpu.refcpu_init4neuron.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
         _refcpu.refcpu_tochatml.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_char_p, C.c_int]
         _refcpu.refcpu_prefill_templates.argtypes = [C.c_int, C.c_char_p, C.c_int]
     return _refcpu
@@ -187,6 +188,14 @@ def refcpu_vendor2jsonx(vendor_block):
     n = refcpu().refcpu_vendor2jsonx(json.dumps(vendor_block).encode(), buf, len(buf))
     assert n >= 0
     return json.loads(buf.value.decode())
+
+
+def refcpu_init4neuron(tensor_name, quantizer_block):
+    """QUANT_CARD::Init4Neuron of the reference itself -> ([selected, mode, bits, group, yyang, sym, zero_point, vendor], T_errQ)"""
+    import json
+    out, errq = (C.c_int * 8)(), C.c_float(0)
+    assert refcpu().refcpu_init4neuron(tensor_name.encode(), json.dumps(quantizer_block).encode(), out, C.byref(errq)) == 0
+    return list(out), errq.value
 
 
 def refcpu_tochatml(lines, enable_thinking):

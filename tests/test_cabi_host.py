@@ -239,6 +239,31 @@ def test_hf_quantization_config_mapping_equals_the_reference_function():
         assert got == want and list(got) == list(want), (got, want)
 
 
+def test_quantizer_card_selection_equals_the_reference_init4neuron():
+    # QUANT_CARD::Init4Neuron (GeQuant.cpp:1186-1285) compiled from the reference tree, field by field against this library's card, over the
+    # reference's own quantizer block (cases/qwen3/qwen3_596M_q4.json), the HF vendor mapping, and blocks exercising every branch
+    import oracle_lib as ol
+    if ol.refcpu() is None:
+        pytest.skip("oracle/_ref/libkoifish_refcpu.so not built (reference tree absent at build time)")
+    lib = kf.load()
+    vendor = ol.refcpu_vendor2jsonx({"bits": 4, "group_size": 128, "quant_method": "awq", "zero_point": True, "version": "gemm"})
+    blocks = [REF_Q4_QUANTIZER, vendor,
+              {"group_size": 64, "self_attn": {"quant_method": "RTN", "bits": 2}, "mlp": {"quant_method": "yyang", "bits": 1}, "embed_tokens": {"bits": 8}},
+              {"self_attn": {"bits": 4}, "mlp": {"quant_method": "yyang", "bits": 2, "group_size": 256}, "# lm_head": {"bits": 4}, "debug": {"x": 1}},
+              {"q_proj": {"quant_method": "RTN", "bits": 4, "zero_point": True}, "down_proj": {"bits": 8}, "layers.1.": {"quant_method": "rtn", "bits": 2}},
+              {"mlp": {"quant_method": "AWQ", "bits": 4}, "self_attn": {"bits": 3}, "filter": {"bits": 4, "filterQ": ["x"]}}]
+    names = ["model.layers.0.self_attn.q_proj.weight", "model.layers.1.self_attn.o_proj.weight", "model.layers.0.mlp.up_proj.weight",
+             "model.layers.1.mlp.down_proj.weight", "model.embed_tokens.weight", "lm_head.weight", "model.layers.0.input_layernorm.weight"]
+    for q in blocks:
+        cfg = kf.qwen3_config(2, 1024, 3072, 16, 8, quantizer=q)
+        for name in names:
+            out, errq, err = (C.c_int * 8)(), C.c_float(0), C.c_void_p()
+            st = lib.kf_config_quant_card(json.dumps(cfg).encode(), name.encode(), out, C.byref(errq), C.byref(err))
+            assert st == 0, name
+            want, want_errq = ol.refcpu_init4neuron(name, q)
+            assert list(out) == want and abs(errq.value - want_errq) < 1e-6, (q, name, list(out), want)
+
+
 def _dims(text):
     lib = kf.load()
     info, err = kf.ModelInfo(), C.c_void_p()
