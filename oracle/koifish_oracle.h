@@ -27,6 +27,8 @@
  *     mention is bound to 0 at link time and never reached).  kfo_quantize / kfo_nf4_quantize produce the SAME bytes and gama, bit for bit
  *     (tests/test_oracle.py: live against the library, and against tests/golden/refcpu_quant.npz generated from it by
  *     tests/golden/make_golden_refcpu.py);
+ *   - the sampler port kfo_sample(selection = 1) against GeneratOnPrompt::Sample / LogitsInfo of src/Manifold/GoPT.cpp in the same library
+ *     (tests/test_oracle.py);
  *   - the same library runs QUANT_CARD::Init4Neuron, QUANT_CARD::Vendor2JSONx and CHAT_SAMPLER::toChatML / InitPrefillTemplate of the reference:
  *     the product's quantizer-card selection, HF quantization_config mapping and ChatML templates are compared with them field by field /
  *     byte by byte (tests/test_cabi_host.py, tests/test_tokenizer.py);

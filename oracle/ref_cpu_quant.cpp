@@ -1,5 +1,5 @@
-// ref_cpu_quant.cpp -- TEST INFRASTRUCTURE ONLY.  Runs the reference's own host code on caller buffers: the CPU packers (below), and three pure
-// functions of src/Utils/CLI_params.cpp -- QUANT_CARD::Vendor2JSONx, CHAT_SAMPLER::toChatML, CHAT_SAMPLER::InitPrefillTemplate (end of file).
+// ref_cpu_quant.cpp -- TEST INFRASTRUCTURE ONLY.  Runs the reference's own host code on caller buffers: the CPU packers (below), and, at the end of
+// the file, QUANT_CARD::Vendor2JSONx / Init4Neuron, CHAT_SAMPLER::toChatML / InitPrefillTemplate and the sampler (LogitsInfo, src/Manifold/GoPT.cpp).
 // The CPU packers -- GeQuant::RTN_x (4- / 2-bit, asymmetric, symmetric, ternary
 // yyang) and GeQuant::YinYang (1-bit), reference src/Tensor/GeQuant.cpp:428-533, 536-628 -- on caller buffers, so that the oracle's restatement
 // (kfo_quantize) can be pinned to the code the reference compiles.  oracle/Makefile builds the reference's GeQuant.cpp and GTensor.cpp where they
@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "Manifold/Fish.hpp"
+#include "Manifold/GoPT.hpp"
 #include "Manifold/Neuron.hpp"
 #include "Tensor/GeQuant.hpp"
 #include "Tensor/GTensor.hpp"
@@ -30,6 +31,7 @@ struct QuantShim : public GeQuant {  // reach the protected working buffers of t
     }
 };
 struct TensorShim : public GTensor {  // hQuant is protected: GTensor::gama_T asks it for the group count
+    void SetHost(void* p) { host_data = p; }
     void Setup(int rows, int cols, GeQuant* q) {
         for (int i = 0; i < N_DIMS; i++) ne[i] = 1;
         ne[0] = rows, ne[1] = cols;
@@ -122,4 +124,39 @@ extern "C" int refcpu_init4neuron(const char* tensor_name, const char* quantizer
     out[6] = card.isZeroPoint, out[7] = card.isVendorQuant;
     if (errq_out) *errq_out = card.T_errQ;
     return 0;
+}
+
+// The sampler of the chat loop: GeneratOnPrompt::Sample (reference src/Manifold/GoPT.cpp:614-630) = LogitsInfo::TopK (:632-640, TOPK_heap::Select
+// :667-700) -> UpdateLogits (:751-766) -> TopP (:729-748) -> Qu_FlipCoin (:768-786, xorshift64* :594-600), on bf16 logits in host memory.
+// LogitsInfo's constructor reads hFish->config.common.seed and the virtual hFish->nClass(): the Fish is zero-filled storage whose vtable pointer is
+// aimed at a table where every slot answers with the vocabulary size (Itanium ABI: a slot is a plain function taking `this`).
+namespace {
+size_t g_vocab = 0;
+size_t AnswerVocab(const void*) { return g_vocab; }
+}  // namespace
+extern "C" int refcpu_sample(const void* logits_bf16, int vocab, float temperature, int top_k, float top_p, unsigned long long* rng_state, int* n_pick_out) {
+    if (!logits_bf16 || vocab < 4 || !rng_state || temperature <= 0.f || top_k < 2) return -1;
+    static void* slots[2048];
+    static void* fish = nullptr;
+    if (!fish) {
+        for (auto& s : slots) s = (void*)&AnswerVocab;
+        fish           = calloc(1, sizeof(Fish));
+        *(void***)fish = slots;
+    }
+    g_vocab = (size_t)vocab;
+    auto* t = new TensorShim();
+    t->SetHost(const_cast<void*>(logits_bf16));
+    std::shared_ptr<GTensor> ht(t, [](GTensor*) {});
+    LogitsInfo li(0, (const Fish*)fish, ht);
+    li.rng_state = *rng_state;
+    CHAT_SAMPLER samp;
+    samp.temperature = temperature, samp.top_k = top_k, samp.top_p = top_p;
+    const int nCanTopK = top_k < vocab ? top_k : vocab;  // GeneratOnPrompt ctor, GoPT.cpp:389
+    li.TopK(nCanTopK);                                   // Sample(), GoPT.cpp:621-625
+    li.UpdateLogits(samp);
+    li.TopP(samp.top_p, nCanTopK);
+    li.Qu_FlipCoin();
+    *rng_state = li.rng_state;
+    if (n_pick_out) *n_pick_out = li.nPick;
+    return (int)li.qu;
 }

@@ -164,6 +164,7 @@ def refcpu():
         _refcpu = C.CDLL(REFCPU_SO)
         _refcpu.refcpu_quantize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         _refcpu.refcpu_vendor2jsonx.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        _refcpu.refcpu_sample.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
         _refcpu.refcpu_init4neuron.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
         _refcpu.refcpu_tochatml.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_char_p, C.c_int]
         _refcpu.refcpu_prefill_templates.argtypes = [C.c_int, C.c_char_p, C.c_int]
@@ -196,6 +197,15 @@ def refcpu_init4neuron(tensor_name, quantizer_block):
     out, errq = (C.c_int * 8)(), C.c_float(0)
     assert refcpu().refcpu_init4neuron(tensor_name.encode(), json.dumps(quantizer_block).encode(), out, C.byref(errq)) == 0
     return list(out), errq.value
+
+
+def refcpu_sample(logits, temperature, top_k, top_p, state):
+    """GeneratOnPrompt::Sample of the reference itself (LogitsInfo::TopK / UpdateLogits / TopP / Qu_FlipCoin); state as in sample()"""
+    lg = np.ascontiguousarray(logits, dtype=np.uint16).reshape(-1)
+    st, npick = C.c_uint64(state[0]), C.c_int(0)
+    tok = refcpu().refcpu_sample(lg.ctypes.data, lg.size, temperature, top_k, top_p, C.byref(st), C.byref(npick))
+    state[0] = st.value
+    return int(tok), int(npick.value)
 
 
 def refcpu_tochatml(lines, enable_thinking):

@@ -515,3 +515,28 @@ def test_packers_against_the_reference_cpu_packers_live():
                 got_d, got_g = _restated(w, rows, cols, bits, mode)
                 assert np.array_equal(got_d, want_d), (rows, cols, bits, mode, sigma)
                 assert np.array_equal(got_g[rows + cols:], want_g[rows + cols:]), (rows, cols, bits, mode, sigma)
+
+
+def test_sampler_port_against_the_reference_sampler_compiled_from_its_tree():
+    # GeneratOnPrompt::Sample = LogitsInfo::TopK / UpdateLogits / TopP / Qu_FlipCoin of src/Manifold/GoPT.cpp compiled where it lies
+    # (oracle/_ref/libkoifish_refcpu.so) against kfo_sample(selection = 1), the port of that code AS WRITTEN (its heap orders indices).  Same coin,
+    # same cut: the generator state and the nucleus size must be equal, and the token equal -- or, where the k candidates hold equal logits, a
+    # candidate with the same logit (the reference's std::sort on `a > b` leaves the order inside a tie unspecified).  top_p >= 1 is left out: the
+    # reference then never sets nPick and Qu_FlipCoin reads picks[-2].
+    if ol.refcpu() is None:
+        pytest.skip("oracle/_ref/libkoifish_refcpu.so not built (reference tree absent at build time)")
+    rng = np.random.default_rng(3)
+    total = same = 0
+    for vocab in (1024, 4096, 151936):
+        for trial in range(12):
+            lg = ol.f32_to_bf16((rng.standard_normal(vocab) * rng.choice([0.5, 2.0, 6.0])).astype(np.float32))
+            for T, k, p in ((0.6, 50, 0.95), (0.9, 20, 0.8), (1.5, 100, 0.99), (0.3, 8, 0.5), (0.6, 2, 0.95), (2.0, 300, 0.9)):
+                s1, s2 = [1234 + trial], [1234 + trial]
+                for _ in range(3):
+                    tok_r, n_r = ol.refcpu_sample(lg, T, k, p, s1)
+                    tok_o, n_o = ol.sample(lg, T, k, p, s2, selection=1)
+                    assert (n_r, s1) == (n_o, s2), (vocab, T, k, p)
+                    assert tok_r == tok_o or lg[tok_r] == lg[tok_o], (vocab, T, k, p, tok_r, tok_o)
+                    total += 1
+                    same += tok_r == tok_o
+    assert same >= 0.97 * total
