@@ -32,6 +32,8 @@
  *   - the same library runs QUANT_CARD::Init4Neuron, QUANT_CARD::Vendor2JSONx and CHAT_SAMPLER::toChatML / InitPrefillTemplate of the reference:
  *     the product's quantizer-card selection, HF quantization_config mapping and ChatML templates are compared with them field by field /
  *     byte by byte (tests/test_cabi_host.py, tests/test_tokenizer.py);
+ *   - the reference's tokenizer (src/TokenSet/HF_Tokenizer.cpp + vendored oniguruma / utf8proc) in oracle/_ref/libkoifish_reftok.so
+ *     (oracle/ref_tokenizer.cpp) against csrc/TokenSet (tests/test_tokenizer.py);
  *   - the AWQ nibble order / values also against the reference's Python unpack (src/Python/test_awq.py, tests/golden/awq_ref_py.npz).
  * Still unpinned: the cuBLASLt GEMM (closed source; fp32 accumulation, order unspecified => tolerance).
  *

@@ -17,6 +17,7 @@ REF_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_ref.so")
 # multiply-subtract of the dequant is contracted to one fma.rn.bf16), and with -fmad=false / no fast-math ("nofma": two roundings, IEEE division)
 REFGPU_SO = {"fma": os.path.join(ORACLE_DIR, "_ref", "libkoifish_refgpu.so"), "nofma": os.path.join(ORACLE_DIR, "_ref", "libkoifish_refgpu_nofma.so")}
 REFQ_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_refq.so")  # the reference's quantizer.cu (NF4 dequant kernel)
+REFTOK_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_reftok.so")  # the reference's tokenizer (HF_Tokenizer.cpp + its vendored oniguruma / utf8proc)
 REFCPU_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_refcpu.so")  # the reference's CPU packers (GeQuant.cpp: RTN_x, YinYang, RT_NormalF)
 
 RTN_ASYM, RTN_SYM, YYANG, NF4 = 0, 1, 2, 3
@@ -34,6 +35,10 @@ def build_oracle(force=False):
     if os.path.exists("/root/reference/src/Tensor/GeQuant.cpp") and (force or not os.path.exists(REFCPU_SO) or
                                                                       os.path.getmtime(shim_q) > os.path.getmtime(REFCPU_SO)):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "refcpu"], stdout=subprocess.DEVNULL)
+    shim_t = os.path.join(ORACLE_DIR, "ref_tokenizer.cpp")
+    if os.path.exists("/root/reference/src/TokenSet/HF_Tokenizer.cpp") and (force or not os.path.exists(REFTOK_SO) or
+                                                                            os.path.getmtime(shim_t) > os.path.getmtime(REFTOK_SO)):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "reftok"], stdout=subprocess.DEVNULL)
     if os.path.exists("/root/reference/src/Device/CUDA/T.cu"):
         src = os.path.join(ORACLE_DIR, "ref_kernels.cu")
         stale = any(not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src) for so in REFGPU_SO.values())
@@ -149,6 +154,37 @@ def refq():
         _refq.refq_nf4_dequant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _refq.refq_awq_dequant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     return _refq
+
+
+class RefTokenizer:
+    """the reference's own HF_Tokenizer (oracle/ref_tokenizer.cpp) on a tokenizer.json text"""
+
+    def __init__(self, json_text):
+        self.lib = C.CDLL(REFTOK_SO)
+        self.lib.reftok_load.restype = C.c_void_p
+        self.lib.reftok_load.argtypes = [C.c_char_p]
+        self.lib.reftok_encode.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int), C.c_int]
+        self.lib.reftok_decode.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_char_p, C.c_int]
+        self.h = self.lib.reftok_load(json_text.encode())
+        assert self.h, "the reference tokenizer refused the file"
+
+    def encode(self, text):
+        ids = (C.c_int * (4 * len(text.encode()) + 16))()
+        n = self.lib.reftok_encode(self.h, text.encode(), ids, len(ids))
+        assert n >= 0
+        return list(ids[:n])
+
+    def decode(self, ids, skip_special_tokens=False):
+        a = (C.c_int * max(1, len(ids)))(*ids)
+        buf = C.create_string_buffer(1 << 16)
+        assert self.lib.reftok_decode(self.h, a, len(ids), int(skip_special_tokens), buf, len(buf)) >= 0
+        return buf.value.decode("utf-8", errors="replace")
+
+
+def reftok(json_text):
+    """RefTokenizer, or None when oracle/_ref/libkoifish_reftok.so was never built"""
+    build_oracle()
+    return RefTokenizer(json_text) if os.path.exists(REFTOK_SO) else None
 
 
 _refcpu = None
