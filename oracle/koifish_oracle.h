@@ -34,6 +34,8 @@
  *     byte by byte (tests/test_cabi_host.py, tests/test_tokenizer.py);
  *   - the reference's tokenizer (src/TokenSet/HF_Tokenizer.cpp + vendored oniguruma / utf8proc) in oracle/_ref/libkoifish_reftok.so
  *     (oracle/ref_tokenizer.cpp) against csrc/TokenSet (tests/test_tokenizer.py);
+ *   - the reference's checkpoint reader (src/Manifold/Serialize.cpp, src/Tensor/Safetensors.cpp) in oracle/_ref/libkoifish_refkun.so
+ *     (oracle/ref_kun.cpp) reads the fish.kun files csrc/Tensor/KunFile.cpp writes (tests/test_kun_host.py);
  *   - the AWQ nibble order / values also against the reference's Python unpack (src/Python/test_awq.py, tests/golden/awq_ref_py.npz).
  * Still unpinned: the cuBLASLt GEMM (closed source; fp32 accumulation, order unspecified => tolerance).
  *

@@ -17,6 +17,7 @@ REF_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_ref.so")
 # multiply-subtract of the dequant is contracted to one fma.rn.bf16), and with -fmad=false / no fast-math ("nofma": two roundings, IEEE division)
 REFGPU_SO = {"fma": os.path.join(ORACLE_DIR, "_ref", "libkoifish_refgpu.so"), "nofma": os.path.join(ORACLE_DIR, "_ref", "libkoifish_refgpu_nofma.so")}
 REFQ_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_refq.so")  # the reference's quantizer.cu (NF4 dequant kernel)
+REFKUN_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_refkun.so")  # the reference's fish.kun reader (Serialize.cpp / Safetensors.cpp)
 REFTOK_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_reftok.so")  # the reference's tokenizer (HF_Tokenizer.cpp + its vendored oniguruma / utf8proc)
 REFCPU_SO = os.path.join(ORACLE_DIR, "_ref", "libkoifish_refcpu.so")  # the reference's CPU packers (GeQuant.cpp: RTN_x, YinYang, RT_NormalF)
 
@@ -35,6 +36,10 @@ def build_oracle(force=False):
     if os.path.exists("/root/reference/src/Tensor/GeQuant.cpp") and (force or not os.path.exists(REFCPU_SO) or
                                                                       os.path.getmtime(shim_q) > os.path.getmtime(REFCPU_SO)):
         subprocess.call(["make", "-C", ORACLE_DIR, "refcpu"], stdout=subprocess.DEVNULL)  # optional checker: tests skip when it did not build
+    shim_k = os.path.join(ORACLE_DIR, "ref_kun.cpp")
+    if os.path.exists("/root/reference/src/Manifold/Serialize.cpp") and (force or not os.path.exists(REFKUN_SO) or
+                                                                         os.path.getmtime(shim_k) > os.path.getmtime(REFKUN_SO)):
+        subprocess.call(["make", "-C", ORACLE_DIR, "refkun"], stdout=subprocess.DEVNULL)  # optional checker: tests skip when it did not build
     shim_t = os.path.join(ORACLE_DIR, "ref_tokenizer.cpp")
     if os.path.exists("/root/reference/src/TokenSet/HF_Tokenizer.cpp") and (force or not os.path.exists(REFTOK_SO) or
                                                                             os.path.getmtime(shim_t) > os.path.getmtime(REFTOK_SO)):
@@ -185,6 +190,21 @@ def reftok(json_text):
     """RefTokenizer, or None when oracle/_ref/libkoifish_reftok.so was never built"""
     build_oracle()
     return RefTokenizer(json_text) if os.path.exists(REFTOK_SO) else None
+
+
+def refkun_read(path):
+    """the reference's own reader on a fish.kun (K_SafeTensors::MMAP + GTensor::jDesc of what it parsed) -> {"config": ..., "tensors": [...]};
+    None when oracle/_ref/libkoifish_refkun.so was never built.  The reader logs to stdout."""
+    import json
+    build_oracle()
+    if not os.path.exists(REFKUN_SO):
+        return None
+    L = C.CDLL(REFKUN_SO)
+    L.refcpu_kun_read.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    buf = C.create_string_buffer(1 << 22)
+    n = L.refcpu_kun_read(str(path).encode(), buf, len(buf))
+    assert n > 0, n
+    return json.loads(buf.value.decode())
 
 
 _refcpu = None

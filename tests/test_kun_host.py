@@ -142,3 +142,29 @@ def test_msgpack_config_both_ways_against_the_msgpack_package(tmp_path):
     text = json.dumps(header).encode()
     open(p, "wb").write(len(text).to_bytes(8, "little") + text + packed32)
     assert kf.kun_config(p) == {"a": 0.5}
+
+
+def test_files_written_here_are_read_by_the_reference_reader(tmp_path):
+    # the reference's own checkpoint reader compiled from its tree (oracle/ref_kun.cpp -> oracle/_ref/libkoifish_refkun.so): K_SafeTensors::MMAP
+    # (mmap_from_file + validate_data_offsets + loadJS of the msgpack config; Serialize.cpp:428-494) on a file kf_kun_write produced, then its own
+    # GTensor::jDesc of every tensor it parsed.  The reference must find the same tensors, in the same order, with the header entries this library
+    # wrote, and decode the same config.
+    import oracle_lib as ol
+    rng = np.random.default_rng(9)
+    tensors = sample_tensors(rng)
+    p = tmp_path / "mine.kun"
+    kf.kun_write(p, CONFIG, tensors)
+    got = ol.refkun_read(p)
+    if got is None:
+        pytest.skip("oracle/_ref/libkoifish_refkun.so not built (reference tree absent at build time)")
+    assert got["config"] == CONFIG
+    parsed = [t for t in got["tensors"] if t["name"] != "__koifish__config__"]
+    assert [t["name"] for t in parsed] == [t[0] for t in tensors]
+    off = 0
+    for t, (name, dt, shape, szd, szg, _) in zip(parsed, tensors):
+        assert t == {"dtype": dt, "shape": list(shape), "data_offsets": [off, off + szd + szg], "loAB": 0, "szGama": szg, "szData": szd, "name": name}
+        off += szd + szg
+    mine = {e["name"]: e for e in kf.kun_index(p)}  # and this library's reader agrees with the reference's on the same file
+    for t in parsed:
+        e = mine[t["name"]]
+        assert (e["dtype"], e["shape"], e["szData"], e["szGama"], e["offset"]) == (t["dtype"], t["shape"], t["szData"], t["szGama"], t["data_offsets"][0])
