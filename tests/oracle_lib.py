@@ -207,6 +207,29 @@ def refkun_read(path):
     return json.loads(buf.value.decode())
 
 
+def refkun_write(path, config, tensors):
+    """the reference's own WRITER (K_SafeTensors::Register + insertJS + Save) on host blobs; tensors as koifish_b200.kun_write takes them.  Returns
+    False when oracle/_ref/libkoifish_refkun.so was never built."""
+    import json
+    build_oracle()
+    if not os.path.exists(REFKUN_SO):
+        return False
+    L = C.CDLL(REFKUN_SO)
+    L.refcpu_kun_write.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_longlong),
+                                   C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_void_p)]
+    n = len(tensors)
+    names = (C.c_char_p * n)(*[t[0].encode() for t in tensors])
+    dtypes = (C.c_char_p * n)(*[t[1].encode() for t in tensors])
+    shapes = (C.c_longlong * (2 * n))(*[d for t in tensors for d in (t[2][0], t[2][1] if len(t[2]) > 1 else 0)])
+    szd = (C.c_ulonglong * n)(*[t[3] for t in tensors])
+    szg = (C.c_ulonglong * n)(*[t[4] for t in tensors])
+    keep = [np.frombuffer(bytes(t[5]), dtype=np.uint8).copy() for t in tensors]
+    blobs = (C.c_void_p * n)(*[k.ctypes.data for k in keep])
+    rc = L.refcpu_kun_write(str(path).encode(), json.dumps(config).encode() if config is not None else None, n, names, dtypes, shapes, szd, szg, blobs)
+    assert rc == 0, rc
+    return True
+
+
 _refcpu = None
 
 

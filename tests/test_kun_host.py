@@ -168,3 +168,45 @@ def test_files_written_here_are_read_by_the_reference_reader(tmp_path):
     for t in parsed:
         e = mine[t["name"]]
         assert (e["dtype"], e["shape"], e["szData"], e["szGama"], e["offset"]) == (t["dtype"], t["shape"], t["szData"], t["szGama"], t["data_offsets"][0])
+
+
+def _check_reference_written(path, tensors, config):
+    idx = kf.kun_index(path)
+    assert [e["name"] for e in idx] == [t[0] for t in tensors]
+    raw = open(path, "rb").read()
+    n = int.from_bytes(raw[:8], "little")
+    data = raw[8 + n:]
+    off = 0
+    for e, (name, dt, shape, szd, szg, blob) in zip(idx, tensors):
+        assert (e["dtype"], tuple(e["shape"]), e["szData"], e["szGama"], e["offset"]) == (dt, tuple(shape), szd, szg, off), name
+        assert data[off:off + szd + szg] == bytes(blob), name
+        off += szd + szg
+    assert kf.kun_config(path) == config
+
+
+def test_reads_the_golden_file_written_by_the_reference_writer():
+    # tests/golden/ref_written.kun: produced by the reference's own K_SafeTensors::Register / insertJS / Save (tests/golden/make_golden_refkun.py)
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import make_golden_refkun as g
+    _check_reference_written(os.path.join(here, "ref_written.kun"), g.tensors(), g.CONFIG)
+
+
+def test_reads_files_written_by_the_reference_writer_live(tmp_path):
+    import oracle_lib as ol
+    rng = np.random.default_rng(21)
+    tensors = sample_tensors(rng)
+    p = tmp_path / "ref.kun"
+    if not ol.refkun_write(p, CONFIG, tensors):
+        pytest.skip("oracle/_ref/libkoifish_refkun.so not built (reference tree absent at build time)")
+    _check_reference_written(p, tensors, CONFIG)
+    # and the two writers agree byte for byte on everything but the JSON header's spacing / padding
+    q = tmp_path / "mine.kun"
+    kf.kun_write(q, CONFIG, tensors)
+    a, b = open(p, "rb").read(), open(q, "rb").read()
+    na, nb = int.from_bytes(a[:8], "little"), int.from_bytes(b[:8], "little")
+    assert json.loads(a[8:8 + na]) == json.loads(b[8:8 + nb])
+    assert list(json.loads(a[8:8 + na])) == list(json.loads(b[8:8 + nb]))  # same key order
+    assert a[8 + na:] == b[8 + nb:]
