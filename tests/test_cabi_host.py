@@ -264,6 +264,27 @@ def test_quantizer_card_selection_equals_the_reference_init4neuron():
             assert list(out) == want and abs(errq.value - want_errq) < 1e-6, (q, name, list(out), want)
 
 
+def test_safetensors_index_equals_the_reference_parser(tmp_path):
+    # the reference's own safetensors reader (K_SafeTensors::MMAP -> mmap_from_file, src/Tensor/Safetensors.cpp, compiled into
+    # oracle/_ref/libkoifish_refkun.so) on an HF-style file, against kf_safetensors_index: same tensors in file order, same dtypes, shapes and byte ranges
+    import oracle_lib as ol
+    from st_util import write_safetensors
+    rng = np.random.default_rng(1)
+    ts = [("model.norm.weight", "BF16", rng.integers(0, 65536, 64, dtype=np.uint16)),
+          ("model.layers.0.mlp.up_proj.weight", "F16", rng.standard_normal((8, 64)).astype(np.float16)),
+          ("lm_head.weight", "F32", rng.standard_normal((4, 64)).astype(np.float32)),
+          ("model.layers.0.mlp.up_proj.qweight", "I32", rng.integers(0, 2 ** 31, (64, 1), dtype=np.int32))]
+    p = tmp_path / "model.safetensors"
+    write_safetensors(p, ts, metadata={"format": "pt"})
+    got = ol.refkun_read(p)
+    if got is None:
+        pytest.skip("oracle/_ref/libkoifish_refkun.so not built (reference tree absent at build time)")
+    mine = kf.safetensors_index(p)
+    assert [(t["name"], t["dtype"], t["shape"], t["data_offsets"][1] - t["data_offsets"][0]) for t in got["tensors"]] == \
+           [(e["name"], e["dtype"], e["shape"], e["nbytes"]) for e in mine]
+    assert got["config"] is None
+
+
 def _dims(text):
     lib = kf.load()
     info, err = kf.ModelInfo(), C.c_void_p()
